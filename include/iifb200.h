@@ -1,0 +1,255 @@
+/*
+ * iifb200.h — C ABI of libiifb200.so: B200-native (sm_100a) nonparametric clique
+ * belief-convolution hot path of IncrementalInference.jl (IIF).
+ *
+ * This is the drop-in boundary a Julia shim binds with `ccall`.
+ * All entry points are `extern "C"`, take plain pointers and sizes, return an int32
+ * status (0 = ok, <0 = error, message via iifb200_last_error) and never throw.
+ * No torch / Julia types cross this boundary.
+ *
+ * Reference interfaces replaced (file:line relative to the IIF v0.35.6 tree):
+ *   iifb200_conv_batch       <- approxConvBelief            src/services/ApproxConv.jl:4-45
+ *                               evalFactor                  src/services/EvalFactor.jl:571-603
+ *                               evalPotentialSpecific       src/services/EvalFactor.jl:321-395, 400-542
+ *                               computeAcrossHypothesis!    src/services/EvalFactor.jl:145-237
+ *                               _prepareHypoRecipe!         src/services/ExplicitDiscreteMarginalizations.jl:142-289
+ *                               approxConvOnElements!       src/services/EvalFactor.jl:14-27
+ *                               _solveCCWNumeric!           src/services/NumericalCalculations.jl:413-452
+ *                               manikde! (AMP, call site)   src/services/ApproxConv.jl:36-42
+ *   iifb200_product_batch    <- AMP.manifoldProduct (call)  src/services/GraphProductOperations.jl:53-60
+ *   iifb200_propagate_batch  <- propagateBelief             src/services/GraphProductOperations.jl:16-64
+ *                               proposalbeliefs!            src/services/ApproxConv.jl:238-304
+ *   iifb200_schedule_*       <- upGibbsCliqueDensity        src/services/SolveTree.jl:164-239
+ *                               fmcmc! / doFMCIteration     src/services/SolveTree.jl:47-142
+ *                               localProductAndUpdate!      src/services/GraphProductOperations.jl:136-155
+ *                               solveCliqDownFrontalProducts! src/CliqueStateMachine/services/CliqStateMachineUtils.jl:479-571
+ *   iifb200_kde_bandwidth    <- AMP.manikde! bandwidth (call sites ApproxConv.jl:38-41, FGOSUtils.jl:118-128)
+ *   belief slots             <- VariableNodeData.val/.bw, TreeBelief   src/entities/BeliefTypes.jl:47-57
+ *   iif_factor_desc          <- CommonConvWrapper           src/entities/FactorOperationalMemory.jl:21-70
+ *   iif_solver_params        <- SolverParams                src/entities/SolverParams.jl:12-75
+ *
+ * Data layout. A "belief slot" is the device-resident analogue of one variable's
+ * (val, bw, infoPerCoord) inside one (sub)graph: `cap` points of `dim` doubles each,
+ * point-major (`pts[n*dim + c]`, identical to Julia's Vector{SVector{dim,Float64}}),
+ * plus `dim` bandwidths and `dim` infoPerCoord values.  Points are stored as
+ * coordinates at the group identity (TranslationGroup(d), RealCircleGroup and their
+ * products: point representation == coordinates; circular coordinates live in [-pi,pi)).
+ */
+#ifndef IIFB200_H
+#define IIFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IIF_MAX_DIM 4           /* max variable dimension handled by the kernels */
+#define IIF_MAX_ARITY 6         /* max variables per factor (four-door multihypo uses 5) */
+#define IIF_MAX_FACTORS 8       /* max factors contributing to one propagateBelief */
+#define IIF_MAX_POINTS 256      /* max particles per belief (kernel shared-memory budget) */
+
+/* status codes */
+#define IIF_OK 0
+#define IIF_ERR_ARG (-1)         /* bad argument / descriptor */
+#define IIF_ERR_CUDA (-2)        /* CUDA runtime error (message has details) */
+#define IIF_ERR_UNSUPPORTED (-3) /* factor / distribution kind with no device implementation */
+#define IIF_ERR_STATE (-4)       /* call order (e.g. run before graph upload) */
+
+/* factor kinds: device residual library (src/Factors/ *.jl) */
+enum iif_factor_kind {
+  IIF_F_PRIOR = 1,             /* Prior            DefaultPrior.jl:8,17      z - x1              */
+  IIF_F_LINEAR_RELATIVE = 2,   /* LinearRelative   LinearRelative.jl:13,42   z - (x2 - x1)       */
+  IIF_F_PRIOR_CIRCULAR = 3,    /* PriorCircular    Circular.jl:54,70                             */
+  IIF_F_CIRCULAR_CIRCULAR = 4, /* CircularCircular Circular.jl:13,24  vee(log(q, exp(p,X)))      */
+  IIF_F_EUCLID_DISTANCE = 5,   /* EuclidDistance   EuclidDistance.jl:9,20    z - norm(x2 - x1)   */
+  IIF_F_MSG_PRIOR = 6,         /* MsgPrior         MsgPrior.jl:10,36         z - x1              */
+  IIF_F_PARTIAL_PRIOR = 7      /* PartialPrior     PartialPrior.jl:11-21  (prior on partial_mask dims) */
+};
+
+/* measurement distributions (SamplableBelief) */
+enum iif_dist_kind {
+  IIF_D_NORMAL = 1,   /* params: [mu, sigma]                                           */
+  IIF_D_MVNORMAL = 2, /* params: [mu(dim), L(dim*dim) row-major lower Cholesky factor]   */
+  IIF_D_MIXTURE = 3,  /* params: [w(ncomp)] then ncomp component blocks of comp_kind     */
+  IIF_D_KDE = 4,      /* ManifoldKernelDensity held in belief slot `slot` (MsgPrior)     */
+  IIF_D_UNIFORM = 5   /* params: [a, b]                                                  */
+};
+
+typedef struct {
+  int32_t kind;      /* iif_dist_kind */
+  int32_t dim;       /* sample dimension z */
+  int32_t ncomp;     /* MIXTURE: number of components */
+  int32_t comp_kind; /* MIXTURE: kind of every component (NORMAL or MVNORMAL) */
+  int32_t slot;      /* KDE: belief slot holding the kernel centres and bandwidths */
+  int32_t poff;      /* offset (doubles) of this distribution's block in the params array */
+} iif_dist_desc;
+
+typedef struct {
+  int32_t dim;       /* variable dimension d (== doubles per point) */
+  int32_t circ_mask; /* bit c set: coordinate c is circular (RealCircleGroup), else Euclid */
+  int32_t cap;       /* capacity in points (>= N) */
+  int32_t pts_off;   /* OUT (filled by iifb200_set_graph): offset in doubles into the arena */
+} iif_slot_desc;
+
+typedef struct {
+  int32_t kind;                /* iif_factor_kind */
+  int32_t arity;               /* number of variables */
+  int32_t zdim;                /* measurement dimension */
+  int32_t dist;                /* index into the distribution table */
+  int32_t slot[IIF_MAX_ARITY]; /* belief slot of each variable, in factor variable order */
+  int32_t nmh;                 /* 0: no multihypo; else == arity */
+  int32_t partial_mask;        /* 0: full; else bit c set: factor informs coordinate c */
+  double mh[IIF_MAX_ARITY];    /* parseusermultihypo output (FactorGraph.jl:639-654): 0.0 = certain */
+  double nullhypo;             /* CCW.nullhypo   FactorOperationalMemory.jl:51 */
+  double inflation;            /* CCW.inflation  FactorOperationalMemory.jl:53 (default 5.0) */
+} iif_factor_desc;
+
+/* SolverParams subset used on the hot path (src/entities/SolverParams.jl) */
+typedef struct {
+  double spreadNH;       /* :57 default 3.0 */
+  double nullSurplusAdd; /* :61 default 0.3 */
+  int32_t inflateCycles; /* :63 default 3   */
+  int32_t gibbsNiter;    /* AMP.manifoldProduct Niter, GraphProductOperations.jl:56 == 1 */
+  uint64_t seed;         /* Philox key for every device-drawn random stream */
+} iif_solver_params;
+
+/* One Chapman-Kolmogorov convolution = one approxConvBelief (the metric's unit of work). */
+typedef struct {
+  int32_t factor;     /* index into factor table */
+  int32_t sfidx;      /* 1-based index of the solve-for variable in the factor's variable order */
+  int32_t N;          /* number of proposal points */
+  int32_t call_id;    /* unique id: selects this op's Philox streams */
+  double nullSurplus; /* ApproxConv.jl:256-265 */
+  /* optional explicit random streams (offset in elements into the arrays passed with the
+   * batch call; -1 => drawn on device from Philox).  These reproduce a host RNG exactly:
+   *   meas:  N*zdim doubles      (sampleFactor!, SolverUtilities.jl:50)
+   *   mhidx: N int32 labels      (_prepareHypoRecipe! rand(Categorical), EDM.jl:186,261)
+   *   uinf:  (inflateCycles+1)*N*d uniforms in [0,1): cycle-major, particle, coord
+   *          (addEntropyOnManifold! rand(), EvalFactor.jl:115-118); the extra block feeds
+   *          the null / other-hypothesis entropy. */
+  int32_t meas_off, mhidx_off, uinf_off, _pad;
+} iif_conv_op;
+
+/* One propagateBelief: F convolutions + manifoldProduct, posterior written to out_slot. */
+typedef struct {
+  int32_t target_slot;             /* destination variable (read: current particles)     */
+  int32_t out_slot;                /* where posterior (pts,bw,ipc) is written (may == target) */
+  int32_t nfactors;                /* F */
+  int32_t N;
+  int32_t factor[IIF_MAX_FACTORS]; /* factor table indices */
+  int32_t sfidx[IIF_MAX_FACTORS];  /* 1-based solve-for index inside each factor */
+  int32_t call_id;                 /* base id; convolution f uses call_id+1+f, product uses call_id */
+  int32_t any_multihypo;           /* proposalbeliefs! sibling nullSurplus rule, ApproxConv.jl:256-265 */
+} iif_prop_op;
+
+/* schedule op kinds (one clique solve = a few of these; one wave = independent ops) */
+enum iif_sched_kind {
+  IIF_S_PROPAGATE = 1, /* propagateBelief + setBelief!  (SolveTree.jl:63-74)                */
+  IIF_S_COPY = 2       /* slot := slot (separator message adoption, TreeMessageUtils.jl:66) */
+};
+
+typedef struct iifb200_ctx iifb200_ctx;
+
+/* ---- lifecycle -------------------------------------------------------------------- */
+int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out);
+void iifb200_free(iifb200_ctx* ctx);
+const char* iifb200_last_error(const iifb200_ctx* ctx); /* ctx may be NULL: last init error */
+int32_t iifb200_version(void);
+
+/* ---- graph upload (descriptor tables; copied, caller keeps ownership) ------------- */
+/* Allocates the device arena.  If ext_arena != NULL the caller supplies device memory of at
+ * least iifb200_arena_bytes(...) bytes (e.g. a torch CUDA tensor used as NCCL buffer). */
+int64_t iifb200_arena_bytes(int32_t nslots, const iif_slot_desc* slots);
+int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots /* in/out */,
+                          int32_t nfactors, const iif_factor_desc* factors, int32_t ndists,
+                          const iif_dist_desc* dists, int32_t nparams, const double* dparams,
+                          const iif_solver_params* sp, void* ext_arena /* device ptr or NULL */);
+int32_t iifb200_set_solver_params(iifb200_ctx* ctx, const iif_solver_params* sp);
+
+/* ---- belief I/O (host <-> device) ------------------------------------------------- */
+int32_t iifb200_upload_belief(iifb200_ctx* ctx, int32_t slot, int32_t npts, const double* pts,
+                              const double* bw /* dim or NULL */, int32_t initialized);
+int32_t iifb200_download_belief(iifb200_ctx* ctx, int32_t slot, int32_t* npts, double* pts,
+                                double* bw, double* ipc);
+/* all slots at once: pts packed by pts_off, bw/ipc as nslots*IIF_MAX_DIM, npts/flags nslots */
+int32_t iifb200_upload_all(iifb200_ctx* ctx, const double* pts, const double* bw,
+                           const int32_t* npts, const int32_t* flags);
+int32_t iifb200_download_all(iifb200_ctx* ctx, double* pts, double* bw, double* ipc,
+                             int32_t* npts);
+/* raw device pointer of a slot's points (for NCCL send/recv of separator messages);
+ * layout: pts[cap*dim]; bw/ipc live in the tail region, see iifb200_slot_msg_ptr */
+int32_t iifb200_slot_device_ptr(iifb200_ctx* ctx, int32_t slot, void** pts_ptr, void** bw_ptr);
+
+/* ---- hot path ---------------------------------------------------------------------- */
+/* K independent convolutions (approxConvBelief).  Outputs are HOST buffers, caller-owned:
+ *   out_pts   K x N x d (packed back to back, op k at sum_{j<k} N_j*d_j)
+ *   out_bw    K x IIF_MAX_DIM,  out_ipc K x IIF_MAX_DIM
+ *   out_mhidx packed like out_pts with N_j ints each (may be NULL)
+ *   out_nan   K ints: particles whose solve produced NaN and were left unchanged
+ *             (NumericalCalculations.jl:348-351)  (may be NULL)
+ * Source/target particles are the current contents of the belief slots; the target slot is
+ * NOT modified (ApproxConv.jl:17, test/testMultiHypo3Door.jl:59-90). */
+int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops,
+                           const double* meas, const int32_t* mhidx, const double* uinf,
+                           double* out_pts, double* out_bw, double* out_ipc,
+                           int32_t* out_mhidx, int32_t* out_nan);
+
+/* V independent KDE products (AMP.manifoldProduct).  Inputs HOST buffers:
+ *   dens_pts  packed F_v x N x d proposals per product, dens_bw F_v x IIF_MAX_DIM,
+ *   dens_mask F_v partial masks (0 = full), old_pts N x d,
+ *   randU / randN optional explicit Gibbs streams (NULL => Philox from call_id). */
+typedef struct {
+  int32_t dim, circ_mask, nfactors, N;
+  int32_t call_id;
+  int32_t randu_off, randn_off; /* -1 => Philox */
+  int32_t _pad;
+} iif_product_op;
+int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op* ops,
+                              const double* dens_pts, const double* dens_bw,
+                              const int32_t* dens_mask, const double* old_pts,
+                              const double* randU, const double* randN, double* out_pts,
+                              double* out_bw, int32_t* out_labels /* V x N x F or NULL */);
+
+/* KDE leave-one-out likelihood bandwidth of K point sets (manikde! with bw === nothing). */
+int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, const int32_t* dim,
+                              const int32_t* circ_mask, const double* pts /* packed */,
+                              double* out_bw /* K x IIF_MAX_DIM */);
+
+/* V independent propagateBelief calls on device-resident slots (one launch sequence).
+ * Posteriors are written into out_slot on the device; nothing is copied to the host. */
+int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* ops);
+
+/* ---- clique / tree schedule (throughput mode, boundary B4) ------------------------ */
+/* A schedule is a sequence of waves; wave w holds ops [wave_off[w], wave_off[w+1]) that are
+ * mutually independent.  Ops are PROPAGATE (index into props) or COPY (src,dst slot).
+ * The schedule is captured once into a CUDA graph and replayed by iifb200_schedule_run. */
+typedef struct {
+  int32_t kind; /* iif_sched_kind */
+  int32_t a;    /* PROPAGATE: index into props;  COPY: source slot */
+  int32_t b;    /* COPY: destination slot */
+  int32_t _pad;
+} iif_sched_op;
+int32_t iifb200_schedule_build(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off,
+                               int32_t nops, const iif_sched_op* ops, int32_t nprops,
+                               const iif_prop_op* props, int32_t* schedule_id_out);
+/* Runs schedule asynchronously on the ctx stream; `first_wave,last_wave` select a wave range
+ * (multi-GPU: run to a cut level, exchange separator messages with NCCL, continue). */
+int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t first_wave,
+                             int32_t last_wave);
+int32_t iifb200_schedule_free(iifb200_ctx* ctx, int32_t schedule_id);
+int32_t iifb200_sync(iifb200_ctx* ctx);
+
+/* ---- instrumentation ---------------------------------------------------------------- */
+/* kernels launched by this ctx since init (for bench.py "gpu_launches") */
+int64_t iifb200_launch_count(const iifb200_ctx* ctx);
+/* cudaStream_t used by the ctx (as void*), so callers can record CUDA events on it */
+void* iifb200_stream(iifb200_ctx* ctx);
+/* time the last schedule_run / *_batch call took on the device, in ms (CUDA events on the
+ * ctx stream; valid after iifb200_sync) */
+float iifb200_last_elapsed_ms(iifb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IIFB200_H */

@@ -1,0 +1,486 @@
+// iif_conv.cuh — the Chapman-Kolmogorov convolution kernel (one CTA per approxConvBelief).
+//
+// Fuses, per convolution:
+//   measurement sampling (sampleFactor!)            SolverUtilities.jl:50-76, Mixture.jl:114-155
+//   hypothesis recipe + per-particle label draw      ExplicitDiscreteMarginalizations.jl:142-289
+//   inflation / null-hypothesis entropy              EvalFactor.jl:40-132
+//   per-particle residual solve                      NumericalCalculations.jl:413-452
+//   prior proposal                                   EvalFactor.jl:400-542
+//   KDE bandwidth (manikde!)                         ApproxConv.jl:36-42
+// One thread owns one particle; block reductions provide the spread statistics.
+#pragma once
+#include "iif_device.cuh"
+
+struct DeviceGraph {
+  const iif_slot_desc* slots;
+  const iif_factor_desc* factors;
+  const iif_dist_desc* dists;
+  const double* dparams;
+  double* pts;
+  double* bw;
+  double* ipc;
+  int32_t* npts;
+  int32_t* flags;
+  iif_solver_params sp;
+  int32_t nslots, nfactors, ndists, _pad;
+};
+
+struct ConvTask {
+  iif_conv_op op;
+  double* out_pts;     // N*d
+  double* out_bw;      // IIF_MAX_DIM
+  double* out_ipc;     // IIF_MAX_DIM
+  int32_t* out_mhidx;  // N or NULL
+  int32_t* out_nan;    // 1 or NULL
+  int32_t* out_status; // 1 or NULL (device-side error code for this task)
+};
+
+struct HypoRecipe {  // HypoRecipe, src/entities/HypoRecipe.jl:4-9 (elements are implicit: mhidx == hyp)
+  int32_t nb;
+  int32_t hyp[IIF_MAX_ARITY + 2];
+  int32_t nv[IIF_MAX_ARITY + 2];
+  int32_t vars[IIF_MAX_ARITY + 2][IIF_MAX_ARITY];
+  int32_t ncert;
+  int32_t cert[IIF_MAX_ARITY];
+  int32_t np;     // categorical support size (0: all labels are 1)
+  int32_t shift;  // subtract from the 1-based categorical draw
+  double p[IIF_MAX_ARITY + 1];
+  int32_t status;
+};
+
+__device__ __forceinline__ bool in_list(const int32_t* l, int n, int v) {
+  for (int i = 0; i < n; ++i)
+    if (l[i] == v) return true;
+  return false;
+}
+
+__device__ __forceinline__ int categorical(const double* p, int np, double u) {  // 1-based
+  double c = 0;
+  int last = 1;
+  for (int k = 0; k < np; ++k) {
+    if (p[k] > 0) last = k + 1;
+    c += p[k];
+    if (u < c) return k + 1;
+  }
+  return last;
+}
+
+// _prepareHypoRecipe! structure (scalar, thread 0) — ExplicitDiscreteMarginalizations.jl:142-289
+__device__ void build_recipe(HypoRecipe& R, const iif_factor_desc& f, int sfidx, const int32_t* isinit,
+                             double nullhypo) {
+  const int lenXi = f.arity;
+  R.status = IIF_OK;
+  if (f.nmh == 0) {  // `Nothing` method :234-289
+    R.np = (nullhypo == 0) ? 0 : 2;
+    R.p[0] = nullhypo;
+    R.p[1] = 1.0 - nullhypo;
+    R.shift = 1;
+    R.ncert = lenXi;
+    for (int i = 0; i < lenXi; ++i) R.cert[i] = i + 1;
+    R.nb = lenXi + 1;
+    for (int b = 0; b <= lenXi; ++b) {
+      R.hyp[b] = b;
+      if (b == 0) { R.nv[b] = 1; R.vars[b][0] = sfidx; }
+      else if (b == 1) { R.nv[b] = lenXi; for (int i = 0; i < lenXi; ++i) R.vars[b][i] = i + 1; }
+      else R.nv[b] = 0;
+    }
+    return;
+  }
+  int32_t uncertn[IIF_MAX_ARITY];
+  int nc = 0, nu = 0;
+  for (int i = 0; i < lenXi; ++i) {  // getHypothesesVectors :17-24
+    if (f.mh[i] == 0.0) R.cert[nc++] = i + 1;
+    else if (f.mh[i] > 0.0) uncertn[nu++] = i + 1;
+  }
+  R.ncert = nc;
+  double p[IIF_MAX_ARITY + 1];
+  int np = lenXi, ninit = 0;
+  for (int i = 0; i < lenXi; ++i) { p[i] = f.mh[i]; ninit += (isinit[i] != 0); }
+  if (ninit < lenXi - 1) {  // :161-172 suppress uninitialised hypotheses
+    double s = 0;
+    for (int i = 0; i < lenXi; ++i) {
+      if (!isinit[i] && (i + 1 != sfidx)) p[i] = 0.0;
+      s += p[i];
+    }
+    for (int i = 0; i < lenXi; ++i) p[i] /= s;
+  }
+  const bool sf_unc = in_list(uncertn, nu, sfidx);
+  if (sf_unc) {  // :176-183 prepend the bad-init null class
+    double nhw = (double)(nu + 1), q[IIF_MAX_ARITY + 1];
+    q[0] = 1.0 / nhw;
+    double s = q[0];
+    for (int i = 0; i < lenXi; ++i) { q[i + 1] = (double)nu / nhw * p[i]; s += q[i + 1]; }
+    for (int i = 0; i <= lenXi; ++i) p[i] = q[i] / s;
+    np = lenXi + 1;
+  }
+  R.np = np;
+  R.shift = sf_unc ? 1 : 0;
+  for (int i = 0; i < np; ++i) R.p[i] = p[i];
+  int pidx = sf_unc ? -1 : 0, nb = 0;
+  const bool sfincer = in_list(R.cert, nc, sfidx);
+  for (int k = 0; k < np; ++k) {  // :195-224
+    pidx += 1;
+    const bool pc = in_list(R.cert, nc, pidx);
+    int nv = 0;
+    int32_t* vars = R.vars[nb];
+    if (!pc && sfincer && pidx != 0) {
+      for (int v = 1; v <= lenXi; ++v) if (in_list(R.cert, nc, v) || v == pidx) vars[nv++] = v;
+    } else if (((pc && !sfincer) || sfidx == pidx) && pidx != 0) {
+      for (int v = 1; v <= lenXi; ++v) if (in_list(R.cert, nc, v) || v == sfidx) vars[nv++] = v;
+    } else if (pc && sfincer && pidx != 0) {
+      nv = 0;
+    } else if (!pc && !sfincer && pidx != 0) {
+      for (int i = 0; i < nu; ++i) vars[nv++] = uncertn[i];
+    } else if (pidx == 0) {
+      vars[nv++] = sfidx;
+    } else R.status = IIF_ERR_ARG;
+    R.hyp[nb] = pidx;
+    R.nv[nb] = nv;
+    nb++;
+  }
+  R.nb = nb;
+}
+
+// ---- measurement sampling ---------------------------------------------------------------
+__device__ __forceinline__ void sample_simple(int kind, int dim, const double* prm, uint64_t seed,
+                                              uint32_t call, int n, int zdim, double* z) {
+  if (kind == IIF_D_NORMAL) {
+    z[0] = prm[0] + prm[1] * rs_normal(seed, call, IIF_RS_MEAS, (uint32_t)(n * zdim));
+  } else if (kind == IIF_D_UNIFORM) {
+    z[0] = prm[0] + (prm[1] - prm[0]) * rs_uniform(seed, call, IIF_RS_MEAS, (uint32_t)(n * zdim));
+  } else {  // MVNORMAL: mu + L*eps
+    double e[IIF_MAX_DIM];
+    for (int c = 0; c < dim; ++c) e[c] = rs_normal(seed, call, IIF_RS_MEAS, (uint32_t)(n * zdim + c));
+    for (int r = 0; r < dim; ++r) {
+      double acc = prm[r];
+      for (int c = 0; c <= r; ++c) acc += prm[dim + r * dim + c] * e[c];
+      z[r] = acc;
+    }
+  }
+}
+
+__device__ int sample_measurement(const DeviceGraph& g, const iif_factor_desc& f, uint32_t call, int n,
+                                  double* z) {
+  const iif_dist_desc D = g.dists[f.dist];
+  const double* prm = g.dparams + D.poff;
+  const uint64_t seed = g.sp.seed;
+  switch (D.kind) {
+    case IIF_D_NORMAL:
+    case IIF_D_UNIFORM:
+    case IIF_D_MVNORMAL: sample_simple(D.kind, D.dim, prm, seed, call, n, f.zdim, z); return IIF_OK;
+    case IIF_D_MIXTURE: {  // Mixture.jl:137-151
+      double u = rs_uniform(seed, call, IIF_RS_MIXLABEL, (uint32_t)n);
+      int lbl = categorical(prm, D.ncomp, u) - 1;
+      int blk = (D.comp_kind == IIF_D_MVNORMAL) ? D.dim + D.dim * D.dim : 2;
+      sample_simple(D.comp_kind, D.dim, prm + D.ncomp + lbl * blk, seed, call, n, f.zdim, z);
+      return IIF_OK;
+    }
+    case IIF_D_KDE: {  // MsgPrior.jl:27-30 -> samplePoint(mkd): kernel pick + bandwidth-scaled jitter
+      const iif_slot_desc S = g.slots[D.slot];
+      int np = g.npts[D.slot];
+      if (np <= 0) return IIF_ERR_STATE;
+      double u = rs_uniform(seed, call, IIF_RS_MIXLABEL, (uint32_t)n);
+      int k = (int)(u * np);
+      if (k >= np) k = np - 1;
+      for (int c = 0; c < S.dim; ++c) {
+        double e = rs_normal(seed, call, IIF_RS_MEAS, (uint32_t)(n * f.zdim + c));
+        z[c] = madd(g.pts[S.pts_off + k * S.dim + c], g.bw[D.slot * IIF_MAX_DIM + c] * e,
+                    is_circ(S.circ_mask, c));
+      }
+      return IIF_OK;
+    }
+    default: return IIF_ERR_UNSUPPORTED;
+  }
+}
+
+// ---- spread statistics (block-wide) -----------------------------------------------------
+// mean(M, pts, GeodesicInterpolation()): Euclid coordinates reduce in parallel (the sequential
+// running mean equals the arithmetic mean up to rounding); circular coordinates follow the
+// sequential geodesic recurrence on one thread (order dependent).  Result in mu_s (shared).
+__device__ void block_geodesic_mean(const double* pts, int n, int d, int32_t cm, double* mu_s, double* red,
+                                    int& parity) {
+  double s[IIF_MAX_DIM] = {0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += IIF_THREADS)
+    for (int c = 0; c < d; ++c) s[c] += pts[i * d + c];
+  block_sum<IIF_MAX_DIM>(s, red, parity);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < d; ++c) {
+      if (!is_circ(cm, c)) { mu_s[c] = n > 0 ? s[c] / n : 0.0; continue; }
+      double mu = n > 0 ? pts[c] : 0.0;
+      for (int i = 1; i < n; ++i) {
+        double t = 1.0 / (double)(i + 1);
+        mu = wrap_pi(mu + t * wrap_pi(pts[i * d + c] - mu));
+      }
+      mu_s[c] = mu;
+    }
+  }
+  __syncthreads();
+}
+
+// mean(M, pts) default estimator: arithmetic (Euclid) / extrinsic atan2 (Circle)
+__device__ void block_default_mean(const double* pts, int n, int d, int32_t cm, double* mu, double* red,
+                                   int& parity) {
+  double s[2 * IIF_MAX_DIM] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += IIF_THREADS)
+    for (int c = 0; c < d; ++c) {
+      double v = pts[i * d + c];
+      if (is_circ(cm, c)) { s[c] += sin(v); s[IIF_MAX_DIM + c] += cos(v); } else s[c] += v;
+    }
+  block_sum<2 * IIF_MAX_DIM>(s, red, parity);
+  for (int c = 0; c < d; ++c)
+    mu[c] = n > 0 ? (is_circ(cm, c) ? atan2(s[c], s[IIF_MAX_DIM + c]) : s[c] / n) : 0.0;
+}
+
+// calcStdBasicSpread — VariableStatistics.jl:22-36
+__device__ double block_std_basic_spread(const double* pts, int n, int d, int32_t cm, double* mu_s, double* red,
+                                         int& parity) {
+  if (n < 2) return 1.0;
+  block_geodesic_mean(pts, n, d, cm, mu_s, red, parity);
+  double acc = 0;
+  for (int i = threadIdx.x; i < n; i += IIF_THREADS)
+    for (int c = 0; c < d; ++c) {
+      double v = mdiff(pts[i * d + c], mu_s[c], is_circ(cm, c));
+      acc += v * v;
+    }
+  acc = block_sum1(acc, red, parity);
+  double sigma = sqrt(acc / (double)(n - 1));
+  return (1e-10 < sigma) ? sigma : 1.0;
+}
+
+// calcVariableDistanceExpectedFractional — EvalFactor.jl:40-92
+__device__ double block_spread_distance(const DeviceGraph& g, const iif_factor_desc& f, int sfidx,
+                                        const double* dest, int N, const HypoRecipe& R, double kappa,
+                                        double* mu_s, double* red, int& parity) {
+  const iif_slot_desc Ssf = g.slots[f.slot[sfidx - 1]];
+  const int d = Ssf.dim;
+  if (in_list(R.cert, R.ncert, sfidx)) return kappa * block_std_basic_spread(dest, N, d, Ssf.circ_mask, mu_s, red, parity);
+  double ref[IIF_MAX_DIM], m[IIF_MAX_DIM];
+  block_default_mean(dest, N, d, Ssf.circ_mask, ref, red, parity);
+  double best = 1e-2;
+  for (int v = 1; v <= f.arity; ++v) {
+    const iif_slot_desc S = g.slots[f.slot[v - 1]];
+    const double* p = (v == sfidx) ? dest : g.pts + S.pts_off;
+    const int np = (v == sfidx) ? N : g.npts[f.slot[v - 1]];
+    if (in_list(R.cert, R.ncert, v)) {
+      __syncthreads();
+      block_geodesic_mean(p, np, S.dim, S.circ_mask, mu_s, red, parity);
+      for (int c = 0; c < S.dim; ++c) m[c] = mu_s[c];
+      __syncthreads();
+    } else {
+      block_default_mean(p, np, S.dim, S.circ_mask, m, red, parity);
+    }
+    double s = 0;
+    for (int c = 0; c < d && c < S.dim; ++c) s += (ref[c] - m[c]) * (ref[c] - m[c]);
+    s = sqrt(s);
+    if (s > best) best = s;
+  }
+  return kappa * best;
+}
+
+// Per-sample solve of the binary residual library (see oracle solve_binary for the derivation):
+// unique-root factors in closed form, EuclidDistance by radial projection of the start point.
+__device__ __forceinline__ void solve_binary(int kind, int d, int32_t cm, const double* z, const double* other,
+                                             bool sf_second, const double* u0, double* out) {
+  if (kind == IIF_F_LINEAR_RELATIVE || kind == IIF_F_CIRCULAR_CIRCULAR) {
+    for (int c = 0; c < d; ++c) out[c] = madd(other[c], sf_second ? z[c] : -z[c], is_circ(cm, c));
+  } else {
+    double dir[IIF_MAX_DIM], nrm = 0;
+    for (int c = 0; c < d; ++c) { dir[c] = u0[c] - other[c]; nrm += dir[c] * dir[c]; }
+    nrm = sqrt(nrm);
+    double r = z[0] > 0 ? z[0] : 0.0;
+    for (int c = 0; c < d; ++c) {
+      double unit = nrm > 0 ? dir[c] / nrm : (c == 0 ? 1.0 : 0.0);
+      out[c] = other[c] + r * unit;
+    }
+  }
+}
+
+__device__ __forceinline__ bool is_prior_kind(int k) {
+  return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR;
+}
+
+__global__ void __launch_bounds__(IIF_THREADS)
+iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double* __restrict__ meas,
+                const int32_t* __restrict__ mhidx_in, const double* __restrict__ uinf,
+                const TreeStruct* __restrict__ trees) {
+  __shared__ double dest[IIF_MAX_POINTS * IIF_MAX_DIM];
+  __shared__ double xa[IIF_MAX_POINTS], xb[IIF_MAX_POINTS];
+  __shared__ double red[IIF_RED_DOUBLES];
+  __shared__ double mu_s[IIF_MAX_DIM];
+  __shared__ HypoRecipe R;
+  __shared__ iif_factor_desc f;
+  __shared__ int s_status;
+
+  const ConvTask t = tasks[blockIdx.x];
+  const iif_conv_op op = t.op;
+  const int n = threadIdx.x;
+  int parity = 0;
+  if (n == 0) {
+    f = g.factors[op.factor];
+    s_status = IIF_OK;
+  }
+  __syncthreads();
+  const int sfidx = op.sfidx, N = op.N;
+  const int sslot = f.slot[sfidx - 1];
+  const iif_slot_desc S = g.slots[sslot];
+  const int d = S.dim;
+  const int32_t cm = S.circ_mask;
+  const uint64_t seed = g.sp.seed;
+  const uint32_t call = (uint32_t)op.call_id;
+  const bool active = n < N;
+
+  // _beforeSolveCCW!: dest = deepcopy(X_sf) resized to N, new slots = identity (CalcFactor.jl:543-565)
+  double my[IIF_MAX_DIM] = {0, 0, 0, 0};
+  {
+    int len_sf = min(g.npts[sslot], N);
+    if (active) {
+      for (int c = 0; c < d; ++c) {
+        my[c] = n < len_sf ? g.pts[S.pts_off + n * d + c] : 0.0;
+        dest[n * d + c] = my[c];
+      }
+    }
+  }
+  // fresh measurements (CalcFactor.jl:578)
+  double z[IIF_MAX_DIM] = {0, 0, 0, 0};
+  if (active) {
+    if (meas != nullptr && op.meas_off >= 0) {
+      for (int c = 0; c < f.zdim; ++c) z[c] = meas[op.meas_off + n * f.zdim + c];
+    } else {
+      int st = sample_measurement(g, f, call, n, z);
+      if (st != IIF_OK) s_status = st;
+    }
+  }
+  // hypothesis recipe structure + per-particle label
+  if (n == 0) {
+    int32_t isinit[IIF_MAX_ARITY];
+    for (int v = 0; v < f.arity; ++v) isinit[v] = g.flags[f.slot[v]] & 1;
+    double runnull = fmax(f.nullhypo, op.nullSurplus);  // EvalFactor.jl:352
+    build_recipe(R, f, sfidx, isinit, runnull);
+    if (R.status != IIF_OK) s_status = R.status;
+    for (int v = 0; v < f.arity; ++v)
+      if (v + 1 != sfidx && g.npts[f.slot[v]] > N) s_status = IIF_ERR_ARG;
+  }
+  __syncthreads();
+  int label = 1;
+  if (active) {
+    if (mhidx_in != nullptr && op.mhidx_off >= 0) label = mhidx_in[op.mhidx_off + n];
+    else if (R.np > 0) label = categorical(R.p, R.np, rs_uniform(seed, call, IIF_RS_LABEL, (uint32_t)n)) - R.shift;
+  }
+  const int32_t fullmask = (1 << d) - 1;
+  const int32_t pmask = f.partial_mask ? f.partial_mask : fullmask;
+  const int C = g.sp.inflateCycles;
+  int nnan = 0;
+
+  auto inflate_u = [&](int cyc, int c) -> double {
+    uint32_t idx = (uint32_t)((cyc * N + n) * d + c);
+    if (uinf != nullptr && op.uinf_off >= 0) return uinf[op.uinf_off + idx];
+    return rs_uniform(seed, call, IIF_RS_INFLATE, idx);
+  };
+  // addEntropyOnManifold! on this thread's particle (EvalFactor.jl:95-132)
+  auto add_entropy = [&](int hyp, int32_t dimmask, double spread, int cyc) {
+    if (active && label == hyp) {
+      for (int c = 0; c < d; ++c) {
+        if (!((dimmask >> c) & 1)) continue;
+        my[c] = madd(my[c], spread * (inflate_u(cyc, c) - 0.5), is_circ(cm, c));
+        dest[n * d + c] = my[c];
+      }
+    }
+  };
+
+  if (s_status == IIF_OK) {
+    if (is_prior_kind(f.kind)) {
+      // evalPotentialSpecific (AbstractPrior) — EvalFactor.jl:400-542
+      double spreadDist = g.sp.spreadNH * block_std_basic_spread(dest, N, d, cm, mu_s, red, parity);  // :464
+      const bool wrap = (f.kind == IIF_F_PRIOR_CIRCULAR || f.kind == IIF_F_MSG_PRIOR);
+      if (active && label == 1) {
+        if (!f.partial_mask) {
+          for (int c = 0; c < d; ++c) my[c] = (wrap && is_circ(cm, c)) ? wrap_pi(z[c]) : z[c];
+        } else {
+          int k = 0;
+          for (int c = 0; c < d; ++c) if ((pmask >> c) & 1) my[c] = z[k++];
+        }
+        for (int c = 0; c < d; ++c) dest[n * d + c] = my[c];
+      }
+      add_entropy(0, pmask, spreadDist, C);
+    } else if (f.arity < 2) {
+      if (n == 0) s_status = IIF_ERR_ARG;
+    } else {
+      // evalPotentialSpecific (AbstractRelative) + computeAcrossHypothesis! — EvalFactor.jl:145-237,321-395
+      const bool sfincer = in_list(R.cert, R.ncert, sfidx);
+      for (int b = 0; b < R.nb; ++b) {
+        const int hyp = R.hyp[b];
+        if ((sfincer && hyp != 0) || in_list(R.cert, R.ncert, hyp) || hyp == sfidx) {
+          const int nel = __syncthreads_count(active && label == hyp);
+          int other = -1;
+          bool sf_second = false;
+          if (nel > 0) {
+            if (R.nv[b] != 2 || !in_list(R.vars[b], 2, sfidx)) {
+              if (n == 0) s_status = IIF_ERR_UNSUPPORTED;
+              break;
+            }
+            other = (R.vars[b][0] == sfidx) ? R.vars[b][1] : R.vars[b][0];
+            sf_second = (R.vars[b][1] == sfidx);
+          }
+          for (int cyc = 0; cyc < C; ++cyc) {
+            __syncthreads();
+            double sp = block_spread_distance(g, f, sfidx, dest, N, R, f.inflation, mu_s, red, parity);
+            add_entropy(hyp, pmask, sp, cyc);
+            if (nel == 0) continue;
+            if (active && label == hyp) {
+              const int oslot = f.slot[other - 1];
+              const iif_slot_desc So = g.slots[oslot];
+              const int lo = g.npts[oslot];
+              int m = n;  // _getindex_anyn, NumericalCalculations.jl:377-381
+              bool ok = true;
+              if (n >= lo) {
+                if (lo <= 0) { s_status = IIF_ERR_STATE; ok = false; }
+                else {
+                  double u = rs_uniform(seed, call, IIF_RS_ANYN, (uint32_t)((other - 1) * N + n));
+                  m = min((int)(u * lo), lo - 1);
+                }
+              }
+              if (ok) {
+                double o[IIF_MAX_DIM], r[IIF_MAX_DIM];
+                for (int c = 0; c < So.dim; ++c) o[c] = g.pts[So.pts_off + m * So.dim + c];
+                solve_binary(f.kind, d, cm, z, o, sf_second, my, r);
+                bool bad = false;
+                for (int c = 0; c < d; ++c) bad |= isnan(r[c]);
+                if (bad) nnan++;  // NumericalCalculations.jl:348-351: particle left unchanged
+                else
+                  for (int c = 0; c < d; ++c)
+                    if ((pmask >> c) & 1) { my[c] = r[c]; dest[n * d + c] = r[c]; }
+              }
+            }
+          }
+        } else {
+          // other-hypothesis (:208-220) and null-hypothesis (:222-231): entropy only, all dims
+          __syncthreads();
+          double sp = block_spread_distance(g, f, sfidx, dest, N, R, g.sp.spreadNH, mu_s, red, parity);
+          add_entropy(hyp, fullmask, sp, C);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int status = s_status;
+  if (t.out_status != nullptr && n == 0) *t.out_status = status;
+  if (status != IIF_OK) return;
+
+  // proposal points out
+  if (active)
+    for (int c = 0; c < d; ++c) t.out_pts[n * d + c] = dest[n * d + c];
+  if (t.out_mhidx != nullptr && active) t.out_mhidx[n] = label;
+  if (t.out_nan != nullptr) {
+    double tot = block_sum1((double)nnan, red, parity);
+    if (n == 0) *t.out_nan = (int32_t)tot;
+  }
+  // approxConvBelief: manikde!(M, pts; partial) — ApproxConv.jl:31-42
+  double bw[IIF_MAX_DIM];
+  block_kde_bandwidth(dest, N, d, cm, trees[N], xa, xb, red, parity, bw);
+  if (n == 0) {
+    for (int c = 0; c < IIF_MAX_DIM; ++c) {
+      t.out_bw[c] = c < d ? (((pmask >> c) & 1) ? bw[c] : 1.0) : 0.0;
+      t.out_ipc[c] = c < d ? (((pmask >> c) & 1) ? 1.0 : 0.0) : 0.0;
+    }
+  }
+}

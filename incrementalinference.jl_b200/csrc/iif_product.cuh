@@ -1,0 +1,350 @@
+// iif_product.cuh — KDE product kernel (one CTA per AMP.manifoldProduct, call site
+// GraphProductOperations.jl:53-60) fused with setBelief! (SolveTree.jl:74) and the re-bandwidth.
+//
+// Multiscale Gibbs sampling from a product of F kernel density estimates (Ihler, Sudderth,
+// Freeman & Willsky, NIPS 2003; KDE.jl prodAppxMSGibbsS):
+//   1. every density gets a median-split ball tree (rank sort inside each node along its
+//      most-spread coordinate; node statistics = moment-matched Gaussian of the member kernels);
+//   2. one warp per output sample walks the levels coarse->fine; per level and density the
+//      lanes evaluate the candidate nodes' weights against the product of the other densities'
+//      selected nodes, a warp scan + ballot picks the label by inverse CDF;
+//   3. the sample is drawn from the product of the selected leaf kernels;
+//   4. the posterior's bandwidth comes from block_kde_bandwidth (same LOO-CV as the proposals).
+#pragma once
+#include "iif_conv.cuh"
+
+struct ProdTask {
+  int32_t dim, circ_mask, F, N;
+  int32_t call_id, randu_off, randn_off;
+  int32_t target_slot;          // >=0: oldPoints come from this slot (padded on device)
+  int32_t out_slot;             // >=0: posterior written into this slot (setBelief!)
+  int32_t mask[IIF_MAX_FACTORS];  // partial masks (0 = full)
+  const double* dens_pts;       // F * N * d
+  const double* dens_bw;        // F * IIF_MAX_DIM
+  const double* old_pts;        // explicit oldPoints N*d (target_slot < 0) or NULL
+  double* out_pts;              // explicit outputs (may be NULL when out_slot >= 0)
+  double* out_bw;
+  int32_t* out_labels;          // N * F or NULL
+  const int32_t* conv_status;   // F status words of the producing convolutions or NULL
+  int32_t* out_status;
+};
+
+// dynamic shared memory layout (doubles first, then int16)
+struct ProdSmem {
+  double* P;      // F*N*d proposals
+  double* mean;   // F*nn*d
+  double* var;    // F*nn*d
+  double* post;   // N*d
+  double* xa;     // N
+  double* xb;     // N
+  double* red;    // IIF_RED_DOUBLES
+  double* bwk;    // F*IIF_MAX_DIM kernel bandwidths
+  int16_t* perm;  // 2*F*N
+};
+
+__host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn) {
+  size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + 2 * (size_t)N + IIF_RED_DOUBLES +
+               (size_t)F * IIF_MAX_DIM;
+  size_t i16 = 2 * (size_t)F * N;
+  return dbl * sizeof(double) + ((i16 * sizeof(int16_t) + 7) / 8) * 8;
+}
+
+// Product of the Gaussians selected in densities != skip along coordinate c
+// (AMP getManiMu/getManiLam: Euclid precision-weighted mean; Circular precision-weighted atan2 mean).
+__device__ __forceinline__ double cond_gauss(int F, const double* mean, const double* var, const int* node,
+                                             const int32_t* masks, int skip, int nn, int d, int c, bool circ,
+                                             double& mu) {
+  double lam = 0, a = 0, sn = 0, cs = 0;
+  for (int k = 0; k < F; ++k) {
+    if (k == skip || !((masks[k] >> c) & 1)) continue;
+    double l = 1.0 / var[(k * nn + node[k]) * d + c];
+    double m = mean[(k * nn + node[k]) * d + c];
+    lam += l;
+    if (circ) { sn += l * sin(m); cs += l * cos(m); } else a += l * m;
+  }
+  if (lam > 0) mu = circ ? atan2(sn, cs) : a / lam;
+  return lam;
+}
+
+__global__ void __launch_bounds__(IIF_THREADS)
+iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const double* __restrict__ randU,
+                   const double* __restrict__ randN, const TreeStruct* __restrict__ trees) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ProdTask t = tasks[blockIdx.x];
+  const int F = t.F, N = t.N, d = t.dim;
+  const int32_t cm = t.circ_mask;
+  const TreeStruct T = trees[N];
+  const int nn = T.nn, L = T.L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int parity = 0;
+
+  // upstream failure: propagate the status and leave the destination untouched
+  if (t.conv_status != nullptr) {
+    int st = IIF_OK;
+    for (int j = 0; j < F; ++j) if (t.conv_status[j] != IIF_OK) st = t.conv_status[j];
+    if (st != IIF_OK) {
+      if (tid == 0 && t.out_status) *t.out_status = st;
+      return;
+    }
+  }
+
+  ProdSmem sm;
+  {
+    double* p = reinterpret_cast<double*>(smem_raw);
+    sm.P = p; p += (size_t)F * N * d;
+    sm.mean = p; p += (size_t)F * nn * d;
+    sm.var = p; p += (size_t)F * nn * d;
+    sm.post = p; p += (size_t)N * d;
+    sm.xa = p; p += N;
+    sm.xb = p; p += N;
+    sm.red = p; p += IIF_RED_DOUBLES;
+    sm.bwk = p; p += F * IIF_MAX_DIM;
+    sm.perm = reinterpret_cast<int16_t*>(p);
+  }
+  const int32_t fullmask = (1 << d) - 1;
+  __shared__ int32_t masks[IIF_MAX_FACTORS];
+  if (tid < F) masks[tid] = t.mask[tid] ? t.mask[tid] : fullmask;
+  for (int i = tid; i < F * N * d; i += IIF_THREADS) sm.P[i] = t.dens_pts[i];
+  for (int i = tid; i < F * IIF_MAX_DIM; i += IIF_THREADS) sm.bwk[i] = t.dens_bw[i];
+  __syncthreads();
+
+  double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
+  const bool passthrough = (F == 1 && masks[0] == fullmask);
+  if (passthrough) {
+    // manifoldProduct of one density returns it unchanged (no Gibbs, no re-bandwidth)
+    for (int i = tid; i < N * d; i += IIF_THREADS) sm.post[i] = sm.P[i];
+    for (int c = 0; c < d; ++c) bw[c] = sm.bwk[c];
+    if (t.out_labels) for (int s = tid; s < N; s += IIF_THREADS) t.out_labels[s] = s;
+    __syncthreads();
+  } else {
+    // ---- 1. ball trees: per level, rank-sort every node along its most-spread coordinate
+    int16_t* permA = sm.perm;
+    int16_t* permB = sm.perm + F * N;
+    for (int i = tid; i < F * N; i += IIF_THREADS) permA[i] = (int16_t)(i % N);
+    __syncthreads();
+    for (int l = 0; l < L; ++l) {
+      for (int it = tid; it < F * N; it += IIF_THREADS) {
+        const int j = it / N, pos = it - j * N;
+        const int z = T.lev_off[l] + T.node_at[l * N + pos];
+        const int lo = T.lo[z], hi = T.hi[z];
+        const int16_t* pj = permA + j * N;
+        const double* Pj = sm.P + (size_t)j * N * d;
+        const int me = pj[pos];
+        if (lo == hi) { permB[j * N + pos] = (int16_t)me; continue; }
+        int best = -1;
+        double bs = -1.0;
+        for (int c = 0; c < d; ++c) {
+          if (!((masks[j] >> c) & 1)) continue;
+          double mn = INFINITY, mx = -INFINITY;
+          for (int i = lo; i <= hi; ++i) {
+            double v = Pj[pj[i] * d + c];
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+          }
+          if (mx - mn > bs) { bs = mx - mn; best = c; }
+        }
+        const double vi = Pj[me * d + best];
+        int r = 0;
+        for (int i = lo; i <= hi; ++i) {
+          const int o = pj[i];
+          const double vo = Pj[o * d + best];
+          r += (vo < vi) || (vo == vi && o < me);
+        }
+        permB[j * N + lo + r] = (int16_t)me;
+      }
+      __syncthreads();
+      int16_t* tmp = permA; permA = permB; permB = tmp;
+    }
+    // ---- node statistics: mean and (kernel variance + member spread) per level-list entry
+    for (int it = tid; it < F * nn; it += IIF_THREADS) {
+      const int j = it / nn, z = it - j * nn;
+      const int lo = T.lo[z], hi = T.hi[z], cnt = hi - lo + 1;
+      const int16_t* pj = permA + j * N;
+      const double* Pj = sm.P + (size_t)j * N * d;
+      for (int c = 0; c < d; ++c) {
+        double s = 0;
+        for (int i = lo; i <= hi; ++i) s += Pj[pj[i] * d + c];
+        const double m = s / cnt;
+        double q = 0;
+        for (int i = lo; i <= hi; ++i) { double e = Pj[pj[i] * d + c] - m; q += e * e; }
+        const double h = sm.bwk[j * IIF_MAX_DIM + c];
+        sm.mean[(size_t)it * d + c] = m;
+        sm.var[(size_t)it * d + c] = h * h + q / cnt;
+      }
+    }
+    __syncthreads();
+
+    // ---- oldPoints for coordinates no proposal informs (GraphProductOperations.jl:37-45)
+    int32_t covered = 0;
+    for (int j = 0; j < F; ++j) covered |= masks[j];
+    // ---- 2./3. multiscale Gibbs: one warp per output sample
+    const int niter = g.sp.gibbsNiter;
+    const uint64_t seed = g.sp.seed;
+    const uint32_t call = (uint32_t)t.call_id;
+    for (int s = warp; s < N; s += IIF_WARPS) {
+      int node[IIF_MAX_FACTORS];
+      for (int j = 0; j < F; ++j) node[j] = 0;  // roots
+      for (int l = 1; l <= L; ++l) {
+        const int z0 = T.lev_off[l], z1 = T.lev_off[l + 1], nz = z1 - z0;
+        for (int j = 0; j < F; ++j) node[j] = z0 + T.child[node[j]];  // levelDown
+        for (int it = 0; it < niter; ++it) {
+          for (int j = 0; j < F; ++j) {  // sampleIndex(j)
+            double cmu[IIF_MAX_DIM] = {0, 0, 0, 0}, clam[IIF_MAX_DIM];
+            for (int c = 0; c < d; ++c)
+              clam[c] = ((masks[j] >> c) & 1)
+                            ? cond_gauss(F, sm.mean, sm.var, node, masks, j, nn, d, c, is_circ(cm, c), cmu[c])
+                            : 0.0;
+            const double* mj = sm.mean + (size_t)j * nn * d;
+            const double* vj = sm.var + (size_t)j * nn * d;
+            double pz[IIF_MAX_POINTS / 32];
+            double pmin = INFINITY;
+#pragma unroll
+            for (int q = 0; q < IIF_MAX_POINTS / 32; ++q) {
+              const int zz = lane + 32 * q;
+              double p = INFINITY;
+              if (zz < nz) {
+                p = 0;
+                for (int c = 0; c < d; ++c) {
+                  if (!(clam[c] > 0)) continue;
+                  double dl = mdiff(mj[(z0 + zz) * d + c], cmu[c], is_circ(cm, c));
+                  double v = vj[(z0 + zz) * d + c] + 1.0 / clam[c];
+                  p += dl * dl / v + log(v);
+                }
+              }
+              pz[q] = p;
+              pmin = fmin(pmin, p);
+            }
+            pmin = warp_min(pmin);
+            double tot = 0;
+#pragma unroll
+            for (int q = 0; q < IIF_MAX_POINTS / 32; ++q) {
+              const int zz = lane + 32 * q;
+              double w = 0;
+              if (zz < nz) {
+                const int lo = T.lo[z0 + zz], hi = T.hi[z0 + zz];
+                w = exp(-0.5 * (pz[q] - pmin)) * ((double)(hi - lo + 1) / (double)N);
+              }
+              pz[q] = w;
+              tot += w;
+            }
+            tot = warp_sum(tot);
+            const uint32_t idx = (uint32_t)(((s * L + (l - 1)) * niter + it) * F + j);
+            const double u = (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx]
+                                                                    : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
+            const double thr = u * tot;
+            int pick = nz - 1;
+            double carry = 0;
+#pragma unroll
+            for (int q = 0; q < IIF_MAX_POINTS / 32; ++q) {
+              if (32 * q >= nz) break;
+              // inclusive warp scan of this chunk's weights (z ascending == lane ascending)
+              double c = pz[q];
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                double y = __shfl_up_sync(0xffffffffu, c, o);
+                if (lane >= o) c += y;
+              }
+              c += carry;
+              const unsigned hit = __ballot_sync(0xffffffffu, (lane + 32 * q < nz) && (thr < c));
+              if (hit) { pick = 32 * q + __ffs(hit) - 1; break; }
+              carry = __shfl_sync(0xffffffffu, c, 31);
+            }
+            node[j] = z0 + pick;
+          }
+        }
+      }
+      // samplePoint: draw from the product of the selected leaf kernels
+      for (int c = 0; c < d; ++c) {
+        double mu = 0;
+        const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, -1, nn, d, c, is_circ(cm, c), mu);
+        if (lane == 0) {
+          double x;
+          if (lam > 0) {
+            const uint32_t idx = (uint32_t)(s * d + c);
+            const double e = (randN != nullptr && t.randn_off >= 0) ? randN[t.randn_off + idx]
+                                                                    : rs_normal(seed, call, IIF_RS_GIBBS_N, idx);
+            x = madd(mu, sqrt(1.0 / lam) * e, is_circ(cm, c));
+          } else if (t.target_slot >= 0) {
+            const iif_slot_desc S = g.slots[t.target_slot];
+            const int len = g.npts[t.target_slot];
+            if (s < len) x = g.pts[S.pts_off + s * d + c];
+            else if (len > 0) {
+              double uu = rs_uniform(seed, call, IIF_RS_OLDPAD, (uint32_t)(s * (d + 1)));
+              int k = min((int)(uu * len), len - 1);
+              double e = rs_normal(seed, call, IIF_RS_OLDPAD, (uint32_t)(s * (d + 1) + 1 + c));
+              x = madd(g.pts[S.pts_off + k * d + c], g.bw[t.target_slot * IIF_MAX_DIM + c] * e, is_circ(cm, c));
+            } else x = 0.0;
+          } else {
+            x = t.old_pts ? t.old_pts[s * d + c] : 0.0;
+          }
+          sm.post[s * d + c] = x;
+        }
+      }
+      if (t.out_labels != nullptr && lane < F) {
+        int nj = 0;
+        for (int j = 0; j < F; ++j) if (j == lane) nj = node[j];
+        t.out_labels[s * F + lane] = permA[lane * N + T.lo[nj]];
+      }
+    }
+    __syncthreads();
+    // ---- 4. re-bandwidth of the posterior (getKDEManifoldBandwidths on the result)
+    block_kde_bandwidth(sm.post, N, d, cm, T, sm.xa, sm.xb, sm.red, parity, bw);
+    (void)covered;
+  }
+
+  // ---- outputs: explicit buffers and / or setBelief! into the destination slot
+  if (t.out_pts != nullptr)
+    for (int i = tid; i < N * d; i += IIF_THREADS) t.out_pts[i] = sm.post[i];
+  if (t.out_bw != nullptr && tid < IIF_MAX_DIM) t.out_bw[tid] = tid < d ? bw[tid] : 0.0;
+  if (t.out_slot >= 0) {
+    const iif_slot_desc O = g.slots[t.out_slot];
+    for (int i = tid; i < N * d; i += IIF_THREADS) g.pts[O.pts_off + i] = sm.post[i];
+    if (tid < IIF_MAX_DIM) {
+      g.bw[t.out_slot * IIF_MAX_DIM + tid] = tid < d ? bw[tid] : 0.0;
+      g.ipc[t.out_slot * IIF_MAX_DIM + tid] = tid < d ? (double)F : 0.0;  // ApproxConv.jl:296-300
+    }
+    if (tid == 0) {
+      g.npts[t.out_slot] = N;
+      g.flags[t.out_slot] |= 1;
+    }
+  }
+  if (tid == 0 && t.out_status) *t.out_status = IIF_OK;
+}
+
+// separator-message adoption: slot b := slot a (updateSubFgFromDownMsgs!, TreeMessageUtils.jl:66)
+__global__ void iif_copy_kernel(DeviceGraph g, const int32_t* __restrict__ pairs, int npairs) {
+  const int k = blockIdx.x;
+  if (k >= npairs) return;
+  const int a = pairs[2 * k], b = pairs[2 * k + 1];
+  const iif_slot_desc A = g.slots[a], B = g.slots[b];
+  const int n = g.npts[a];
+  for (int i = threadIdx.x; i < n * A.dim; i += blockDim.x) g.pts[B.pts_off + i] = g.pts[A.pts_off + i];
+  if (threadIdx.x < IIF_MAX_DIM) {
+    g.bw[b * IIF_MAX_DIM + threadIdx.x] = g.bw[a * IIF_MAX_DIM + threadIdx.x];
+    g.ipc[b * IIF_MAX_DIM + threadIdx.x] = g.ipc[a * IIF_MAX_DIM + threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    g.npts[b] = n;
+    g.flags[b] = g.flags[a];
+  }
+}
+
+// standalone bandwidth kernel (manikde! with bw === nothing on K point sets)
+struct BwTask {
+  const double* pts;
+  double* out_bw;
+  int32_t N, dim, circ_mask, _pad;
+};
+__global__ void __launch_bounds__(IIF_THREADS)
+iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restrict__ trees) {
+  __shared__ double pts[IIF_MAX_POINTS * IIF_MAX_DIM];
+  __shared__ double xa[IIF_MAX_POINTS], xb[IIF_MAX_POINTS];
+  __shared__ double red[IIF_RED_DOUBLES];
+  const BwTask t = tasks[blockIdx.x];
+  int parity = 0;
+  for (int i = threadIdx.x; i < t.N * t.dim; i += IIF_THREADS) pts[i] = t.pts[i];
+  __syncthreads();
+  double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
+  block_kde_bandwidth(pts, t.N, t.dim, t.circ_mask, trees[t.N], xa, xb, red, parity, bw);
+  if (threadIdx.x < IIF_MAX_DIM) t.out_bw[threadIdx.x] = threadIdx.x < t.dim ? bw[threadIdx.x] : 0.0;
+}

@@ -1,0 +1,804 @@
+// iifb200.cu — C-ABI host side of libiifb200.so (see include/iifb200.h for the contract and
+// the reference interfaces each entry point replaces).  No torch, no Julia, no CPU fallback:
+// every hot-path entry point launches the sm_100a kernels in iif_conv.cuh / iif_product.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "iif_product.cuh"
+
+#define IIFB200_VERSION 100
+
+static std::string g_init_error;
+
+struct TreeHost {
+  int L = 0, nn = 0;
+  int16_t* d_blob = nullptr;
+};
+
+struct Wave {
+  int conv0 = 0, nconv = 0, prod0 = 0, nprod = 0, copy0 = 0, ncopy = 0;
+  size_t prod_smem = 0;
+};
+
+struct Schedule {
+  std::vector<Wave> waves;
+  ConvTask* d_conv = nullptr;
+  ProdTask* d_prod = nullptr;
+  int32_t* d_copy = nullptr;
+  double* d_scratch = nullptr;
+  int32_t* d_status = nullptr;
+  int nconv = 0, nprod = 0;
+  std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int>> graphs;  // (exec, kernel nodes)
+};
+
+struct iifb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  std::string err;
+  // graph tables
+  std::vector<iif_slot_desc> slots;
+  std::vector<iif_factor_desc> factors;
+  std::vector<iif_dist_desc> dists;
+  iif_solver_params sp{};
+  DeviceGraph dg{};
+  void* arena = nullptr;
+  bool arena_owned = false;
+  int64_t total_doubles = 0;
+  void* d_tables = nullptr;
+  int32_t* d_err = nullptr;
+  // ball-tree structures per N
+  TreeHost trees[IIF_MAX_POINTS + 1];
+  TreeStruct h_trees[IIF_MAX_POINTS + 1];
+  TreeStruct* d_trees = nullptr;
+  std::vector<Schedule*> schedules;
+  int64_t launches = 0;
+  int max_smem_optin = 0;
+};
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      char b_[512];                                                                    \
+      snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+               __FILE__, __LINE__);                                                    \
+      ctx->err = b_;                                                                   \
+      return IIF_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+static int32_t fail(iifb200_ctx* ctx, int32_t code, const std::string& msg) {
+  ctx->err = msg;
+  return code;
+}
+
+static const char* status_name(int st) {
+  switch (st) {
+    case IIF_ERR_ARG: return "bad argument / descriptor";
+    case IIF_ERR_CUDA: return "CUDA error";
+    case IIF_ERR_UNSUPPORTED: return "unsupported factor / distribution kind on the device";
+    case IIF_ERR_STATE: return "state error (uninitialised source belief?)";
+    default: return "unknown";
+  }
+}
+
+// ---- balanced median-split tree structure for N points (depends on N only) ----------------
+static int32_t ensure_tree(iifb200_ctx* ctx, int N) {
+  if (N < 2 || N > IIF_MAX_POINTS) return fail(ctx, IIF_ERR_ARG, "N out of range [2, IIF_MAX_POINTS]");
+  if (ctx->trees[N].d_blob) return IIF_OK;
+  const int L = (int)std::floor(std::log((double)N) / std::log(2.0) + 1.0);
+  std::vector<int16_t> lev_off(L + 2), lo, hi, child, node_at((size_t)L * N);
+  lo.push_back(0);
+  hi.push_back((int16_t)(N - 1));
+  lev_off[0] = 0;
+  lev_off[1] = 1;
+  for (int l = 0; l < L; ++l) {
+    for (int z = lev_off[l]; z < lev_off[l + 1]; ++z) {
+      int a = lo[z], b = hi[z];
+      child.push_back((int16_t)((int)lo.size() - lev_off[l + 1]));
+      for (int p = a; p <= b; ++p) node_at[(size_t)l * N + p] = (int16_t)(z - lev_off[l]);
+      if (a == b) { lo.push_back((int16_t)a); hi.push_back((int16_t)b); continue; }
+      int mid = (a + b) / 2;
+      lo.push_back((int16_t)a); hi.push_back((int16_t)mid);
+      lo.push_back((int16_t)(mid + 1)); hi.push_back((int16_t)b);
+    }
+    lev_off[l + 2] = (int16_t)lo.size();
+  }
+  for (int z = lev_off[L]; z < lev_off[L + 1]; ++z) child.push_back((int16_t)(z - lev_off[L]));
+  const int nn = (int)lo.size();
+  // blob: lev_off | lo | hi | child | node_at
+  std::vector<int16_t> blob;
+  auto push = [&](const std::vector<int16_t>& v) { size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return o; };
+  size_t o0 = push(lev_off), o1 = push(lo), o2 = push(hi), o3 = push(child), o4 = push(node_at);
+  int16_t* d = nullptr;
+  CK(cudaMalloc(&d, blob.size() * sizeof(int16_t)));
+  CK(cudaMemcpyAsync(d, blob.data(), blob.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->trees[N].L = L;
+  ctx->trees[N].nn = nn;
+  ctx->trees[N].d_blob = d;
+  TreeStruct ts;
+  ts.L = L; ts.nn = nn;
+  ts.lev_off = d + o0; ts.lo = d + o1; ts.hi = d + o2; ts.child = d + o3; ts.node_at = d + o4;
+  ctx->h_trees[N] = ts;
+  CK(cudaMemcpyAsync(ctx->d_trees + N, &ts, sizeof(ts), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IIF_OK;
+}
+
+// =============================================================================================
+extern "C" {
+
+int32_t iifb200_version(void) { return IIFB200_VERSION; }
+
+const char* iifb200_last_error(const iifb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
+  if (!ctx_out) return IIF_ERR_ARG;
+  *ctx_out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_init_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libiifb200 has no CPU fallback)";
+    return IIF_ERR_CUDA;
+  }
+  if (device_ordinal < 0 || device_ordinal >= ndev) { g_init_error = "device ordinal out of range"; return IIF_ERR_ARG; }
+  iifb200_ctx* ctx = new iifb200_ctx();
+  ctx->device = device_ordinal;
+  ctx->sp.spreadNH = 3.0; ctx->sp.nullSurplusAdd = 0.3; ctx->sp.inflateCycles = 3; ctx->sp.gibbsNiter = 1; ctx->sp.seed = 42;
+  auto bail = [&](const char* what, cudaError_t ee) {
+    g_init_error = std::string(what) + ": " + cudaGetErrorString(ee);
+    delete ctx;
+    return IIF_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaMalloc(&ctx->d_trees, sizeof(TreeStruct) * (IIF_MAX_POINTS + 1))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(ctx->d_trees, 0, sizeof(TreeStruct) * (IIF_MAX_POINTS + 1))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMalloc(&ctx->d_err, sizeof(int32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(ctx->d_err, 0, sizeof(int32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_ordinal);
+  if ((e = cudaFuncSetAttribute(iif_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(product smem)", e);
+  *ctx_out = ctx;
+  return IIF_OK;
+}
+
+static void free_schedule(Schedule* s) {
+  if (!s) return;
+  for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second.first);
+  cudaFree(s->d_conv); cudaFree(s->d_prod); cudaFree(s->d_copy); cudaFree(s->d_scratch); cudaFree(s->d_status);
+  delete s;
+}
+
+static void free_graph(iifb200_ctx* ctx) {
+  for (auto*& s : ctx->schedules) { free_schedule(s); s = nullptr; }
+  ctx->schedules.clear();
+  if (ctx->arena_owned && ctx->arena) cudaFree(ctx->arena);
+  ctx->arena = nullptr;
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  ctx->d_tables = nullptr;
+}
+
+void iifb200_free(iifb200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_graph(ctx);
+  for (auto& t : ctx->trees) if (t.d_blob) cudaFree(t.d_blob);
+  cudaFree(ctx->d_trees);
+  cudaFree(ctx->d_err);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+static int64_t layout_slots(int32_t nslots, iif_slot_desc* slots) {
+  int64_t off = 0;
+  for (int s = 0; s < nslots; ++s) {
+    slots[s].pts_off = (int32_t)off;
+    off += (int64_t)slots[s].cap * slots[s].dim;
+  }
+  return off;
+}
+
+int64_t iifb200_arena_bytes(int32_t nslots, const iif_slot_desc* slots) {
+  int64_t tot = 0;
+  for (int s = 0; s < nslots; ++s) tot += (int64_t)slots[s].cap * slots[s].dim;
+  int64_t ns = nslots > 0 ? nslots : 1;
+  return 8 * (tot + 2 * ns * IIF_MAX_DIM) + 4 * 2 * ns + 64;
+}
+
+int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots, int32_t nfactors,
+                          const iif_factor_desc* factors, int32_t ndists, const iif_dist_desc* dists,
+                          int32_t nparams, const double* dparams, const iif_solver_params* sp, void* ext_arena) {
+  if (!ctx) return IIF_ERR_ARG;
+  if (nslots < 1 || !slots || nfactors < 0 || ndists < 0 || !sp) return fail(ctx, IIF_ERR_ARG, "set_graph: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_graph(ctx);
+  for (int s = 0; s < nslots; ++s) {
+    if (slots[s].dim < 1 || slots[s].dim > IIF_MAX_DIM) return fail(ctx, IIF_ERR_ARG, "slot dim out of range");
+    if (slots[s].cap < 1 || slots[s].cap > IIF_MAX_POINTS) return fail(ctx, IIF_ERR_ARG, "slot capacity out of range");
+  }
+  for (int f = 0; f < nfactors; ++f) {
+    const iif_factor_desc& F = factors[f];
+    if (F.kind < IIF_F_PRIOR || F.kind > IIF_F_PARTIAL_PRIOR)
+      return fail(ctx, IIF_ERR_UNSUPPORTED, "factor kind has no device residual (no CPU fallback)");
+    if (F.arity < 1 || F.arity > IIF_MAX_ARITY) return fail(ctx, IIF_ERR_ARG, "factor arity out of range");
+    if (F.dist < 0 || F.dist >= ndists) return fail(ctx, IIF_ERR_ARG, "factor distribution index out of range");
+    if (F.nmh != 0 && F.nmh != F.arity) return fail(ctx, IIF_ERR_ARG, "multihypo length must equal arity");
+    for (int v = 0; v < F.arity; ++v)
+      if (F.slot[v] < 0 || F.slot[v] >= nslots) return fail(ctx, IIF_ERR_ARG, "factor slot out of range");
+  }
+  for (int k = 0; k < ndists; ++k) {
+    if (dists[k].kind < IIF_D_NORMAL || dists[k].kind > IIF_D_UNIFORM)
+      return fail(ctx, IIF_ERR_UNSUPPORTED, "distribution kind has no device sampler");
+    if (dists[k].kind == IIF_D_KDE && (dists[k].slot < 0 || dists[k].slot >= nslots))
+      return fail(ctx, IIF_ERR_ARG, "KDE distribution slot out of range");
+  }
+  ctx->total_doubles = layout_slots(nslots, slots);
+  ctx->slots.assign(slots, slots + nslots);
+  ctx->factors.assign(factors, factors + nfactors);
+  ctx->dists.assign(dists, dists + ndists);
+  ctx->sp = *sp;
+  const int64_t bytes = iifb200_arena_bytes(nslots, slots);
+  if (ext_arena) { ctx->arena = ext_arena; ctx->arena_owned = false; }
+  else { CK(cudaMalloc(&ctx->arena, bytes)); ctx->arena_owned = true; }
+  CK(cudaMemsetAsync(ctx->arena, 0, bytes, ctx->stream));
+  // descriptor tables in one allocation
+  const size_t b_slots = sizeof(iif_slot_desc) * nslots, b_fac = sizeof(iif_factor_desc) * std::max(nfactors, 1),
+               b_dist = sizeof(iif_dist_desc) * std::max(ndists, 1), b_par = sizeof(double) * std::max(nparams, 1);
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  CK(cudaMalloc(&ctx->d_tables, al(b_slots) + al(b_fac) + al(b_dist) + al(b_par)));
+  char* p = (char*)ctx->d_tables;
+  DeviceGraph& dg = ctx->dg;
+  dg.slots = (iif_slot_desc*)p; p += al(b_slots);
+  dg.factors = (iif_factor_desc*)p; p += al(b_fac);
+  dg.dists = (iif_dist_desc*)p; p += al(b_dist);
+  dg.dparams = (double*)p;
+  CK(cudaMemcpyAsync((void*)dg.slots, slots, b_slots, cudaMemcpyHostToDevice, ctx->stream));
+  if (nfactors) CK(cudaMemcpyAsync((void*)dg.factors, factors, sizeof(iif_factor_desc) * nfactors, cudaMemcpyHostToDevice, ctx->stream));
+  if (ndists) CK(cudaMemcpyAsync((void*)dg.dists, dists, sizeof(iif_dist_desc) * ndists, cudaMemcpyHostToDevice, ctx->stream));
+  if (nparams) CK(cudaMemcpyAsync((void*)dg.dparams, dparams, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream));
+  double* a = (double*)ctx->arena;
+  dg.pts = a;
+  dg.bw = a + ctx->total_doubles;
+  dg.ipc = dg.bw + (int64_t)nslots * IIF_MAX_DIM;
+  dg.npts = (int32_t*)(dg.ipc + (int64_t)nslots * IIF_MAX_DIM);
+  dg.flags = dg.npts + nslots;
+  dg.sp = *sp;
+  dg.nslots = nslots; dg.nfactors = nfactors; dg.ndists = ndists;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IIF_OK;
+}
+
+int32_t iifb200_set_solver_params(iifb200_ctx* ctx, const iif_solver_params* sp) {
+  if (!ctx || !sp) return IIF_ERR_ARG;
+  ctx->sp = *sp;
+  ctx->dg.sp = *sp;
+  // captured graphs hold the old params by value: drop them
+  for (auto* s : ctx->schedules)
+    if (s) { for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second.first); s->graphs.clear(); }
+  return IIF_OK;
+}
+
+// ---- belief I/O --------------------------------------------------------------------------
+#define NEED_GRAPH() do { if (!ctx) return IIF_ERR_ARG; if (!ctx->arena) return fail(ctx, IIF_ERR_STATE, "no graph uploaded (call iifb200_set_graph first)"); } while (0)
+
+int32_t iifb200_upload_belief(iifb200_ctx* ctx, int32_t slot, int32_t npts, const double* pts, const double* bw,
+                              int32_t initialized) {
+  NEED_GRAPH();
+  if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "slot out of range");
+  const iif_slot_desc& S = ctx->slots[slot];
+  if (npts < 0 || npts > S.cap) return fail(ctx, IIF_ERR_ARG, "npts exceeds slot capacity");
+  if (npts > 0) CK(cudaMemcpyAsync(ctx->dg.pts + S.pts_off, pts, sizeof(double) * npts * S.dim, cudaMemcpyHostToDevice, ctx->stream));
+  double b[IIF_MAX_DIM] = {0, 0, 0, 0};
+  if (bw) for (int c = 0; c < S.dim; ++c) b[c] = bw[c];
+  CK(cudaMemcpyAsync(ctx->dg.bw + (int64_t)slot * IIF_MAX_DIM, b, sizeof(b), cudaMemcpyHostToDevice, ctx->stream));
+  int32_t fl = initialized ? 1 : 0;
+  CK(cudaMemcpyAsync(ctx->dg.npts + slot, &npts, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dg.flags + slot, &fl, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IIF_OK;
+}
+
+int32_t iifb200_download_belief(iifb200_ctx* ctx, int32_t slot, int32_t* npts, double* pts, double* bw, double* ipc) {
+  NEED_GRAPH();
+  if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "slot out of range");
+  const iif_slot_desc& S = ctx->slots[slot];
+  int32_t n = 0;
+  CK(cudaMemcpyAsync(&n, ctx->dg.npts + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (npts) *npts = n;
+  if (pts && n > 0) CK(cudaMemcpyAsync(pts, ctx->dg.pts + S.pts_off, sizeof(double) * n * S.dim, cudaMemcpyDeviceToHost, ctx->stream));
+  double b[IIF_MAX_DIM], q[IIF_MAX_DIM];
+  CK(cudaMemcpyAsync(b, ctx->dg.bw + (int64_t)slot * IIF_MAX_DIM, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(q, ctx->dg.ipc + (int64_t)slot * IIF_MAX_DIM, sizeof(q), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bw) for (int c = 0; c < S.dim; ++c) bw[c] = b[c];
+  if (ipc) for (int c = 0; c < S.dim; ++c) ipc[c] = q[c];
+  return IIF_OK;
+}
+
+int32_t iifb200_upload_all(iifb200_ctx* ctx, const double* pts, const double* bw, const int32_t* npts, const int32_t* flags) {
+  NEED_GRAPH();
+  const int64_t ns = (int64_t)ctx->slots.size();
+  if (pts) CK(cudaMemcpyAsync(ctx->dg.pts, pts, sizeof(double) * ctx->total_doubles, cudaMemcpyHostToDevice, ctx->stream));
+  if (bw) CK(cudaMemcpyAsync(ctx->dg.bw, bw, sizeof(double) * ns * IIF_MAX_DIM, cudaMemcpyHostToDevice, ctx->stream));
+  if (npts) CK(cudaMemcpyAsync(ctx->dg.npts, npts, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, ctx->stream));
+  if (flags) CK(cudaMemcpyAsync(ctx->dg.flags, flags, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, ctx->stream));
+  return IIF_OK;  // stream-ordered: later launches on the ctx stream see the data
+}
+
+int32_t iifb200_download_all(iifb200_ctx* ctx, double* pts, double* bw, double* ipc, int32_t* npts) {
+  NEED_GRAPH();
+  const int64_t ns = (int64_t)ctx->slots.size();
+  if (pts) CK(cudaMemcpyAsync(pts, ctx->dg.pts, sizeof(double) * ctx->total_doubles, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bw) CK(cudaMemcpyAsync(bw, ctx->dg.bw, sizeof(double) * ns * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ipc) CK(cudaMemcpyAsync(ipc, ctx->dg.ipc, sizeof(double) * ns * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  if (npts) CK(cudaMemcpyAsync(npts, ctx->dg.npts, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IIF_OK;
+}
+
+int32_t iifb200_slot_device_ptr(iifb200_ctx* ctx, int32_t slot, void** pts_ptr, void** bw_ptr) {
+  NEED_GRAPH();
+  if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "slot out of range");
+  if (pts_ptr) *pts_ptr = ctx->dg.pts + ctx->slots[slot].pts_off;
+  if (bw_ptr) *bw_ptr = ctx->dg.bw + (int64_t)slot * IIF_MAX_DIM;
+  return IIF_OK;
+}
+
+// ---- helpers -------------------------------------------------------------------------------
+static bool is_prior_kind_h(int k) {
+  return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR;
+}
+
+static int32_t validate_conv(iifb200_ctx* ctx, const iif_conv_op& op) {
+  if (op.factor < 0 || op.factor >= (int)ctx->factors.size()) return fail(ctx, IIF_ERR_ARG, "conv op: factor index out of range");
+  const iif_factor_desc& F = ctx->factors[op.factor];
+  if (op.sfidx < 1 || op.sfidx > F.arity) return fail(ctx, IIF_ERR_ARG, "conv op: sfidx out of range");
+  if (op.N < 2 || op.N > IIF_MAX_POINTS) return fail(ctx, IIF_ERR_ARG, "conv op: N out of range");
+  if (ctx->slots[F.slot[op.sfidx - 1]].cap < 1) return fail(ctx, IIF_ERR_ARG, "conv op: bad slot");
+  return ensure_tree(ctx, op.N);
+}
+
+// ---- hot path: convolution batch -------------------------------------------------------------
+int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, const double* meas,
+                           const int32_t* mhidx, const double* uinf, double* out_pts, double* out_bw,
+                           double* out_ipc, int32_t* out_mhidx, int32_t* out_nan) {
+  NEED_GRAPH();
+  if (K < 1 || !ops || !out_pts || !out_bw || !out_ipc) return fail(ctx, IIF_ERR_ARG, "conv_batch: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<ConvTask> tasks(K);
+  std::vector<int64_t> poff(K + 1, 0), noff(K + 1, 0);
+  int64_t n_meas = 0, n_lab = 0, n_uinf = 0;
+  for (int k = 0; k < K; ++k) {
+    int32_t st = validate_conv(ctx, ops[k]);
+    if (st != IIF_OK) return st;
+    const iif_factor_desc& F = ctx->factors[ops[k].factor];
+    const int d = ctx->slots[F.slot[ops[k].sfidx - 1]].dim;
+    poff[k + 1] = poff[k] + (int64_t)ops[k].N * d;
+    noff[k + 1] = noff[k] + ops[k].N;
+    if (ops[k].meas_off >= 0) n_meas = std::max<int64_t>(n_meas, ops[k].meas_off + (int64_t)ops[k].N * F.zdim);
+    if (ops[k].mhidx_off >= 0) n_lab = std::max<int64_t>(n_lab, ops[k].mhidx_off + (int64_t)ops[k].N);
+    if (ops[k].uinf_off >= 0) n_uinf = std::max<int64_t>(n_uinf, ops[k].uinf_off + (int64_t)(ctx->sp.inflateCycles + 1) * ops[k].N * d);
+  }
+  if ((n_meas && !meas) || (n_lab && !mhidx) || (n_uinf && !uinf)) return fail(ctx, IIF_ERR_ARG, "conv_batch: explicit stream offset given but array is NULL");
+  double *d_pts = nullptr, *d_bw = nullptr, *d_meas = nullptr, *d_uinf = nullptr;
+  int32_t *d_lab = nullptr, *d_misc = nullptr, *d_labin = nullptr;
+  ConvTask* d_tasks = nullptr;
+  auto cleanup = [&]() { cudaFree(d_pts); cudaFree(d_bw); cudaFree(d_meas); cudaFree(d_uinf); cudaFree(d_lab); cudaFree(d_misc); cudaFree(d_labin); cudaFree(d_tasks); };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return IIF_ERR_CUDA; } } while (0)
+  CKC(cudaMalloc(&d_pts, sizeof(double) * poff[K]));
+  CKC(cudaMalloc(&d_bw, sizeof(double) * 2 * K * IIF_MAX_DIM));
+  CKC(cudaMalloc(&d_lab, sizeof(int32_t) * noff[K]));
+  CKC(cudaMalloc(&d_misc, sizeof(int32_t) * 2 * K));
+  CKC(cudaMalloc(&d_tasks, sizeof(ConvTask) * K));
+  CKC(cudaMemsetAsync(d_misc, 0, sizeof(int32_t) * 2 * K, ctx->stream));
+  if (n_meas) { CKC(cudaMalloc(&d_meas, sizeof(double) * n_meas)); CKC(cudaMemcpyAsync(d_meas, meas, sizeof(double) * n_meas, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (n_lab) { CKC(cudaMalloc(&d_labin, sizeof(int32_t) * n_lab)); CKC(cudaMemcpyAsync(d_labin, mhidx, sizeof(int32_t) * n_lab, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (n_uinf) { CKC(cudaMalloc(&d_uinf, sizeof(double) * n_uinf)); CKC(cudaMemcpyAsync(d_uinf, uinf, sizeof(double) * n_uinf, cudaMemcpyHostToDevice, ctx->stream)); }
+  for (int k = 0; k < K; ++k) {
+    ConvTask& t = tasks[k];
+    t.op = ops[k];
+    t.out_pts = d_pts + poff[k];
+    t.out_bw = d_bw + (int64_t)k * IIF_MAX_DIM;
+    t.out_ipc = d_bw + (int64_t)(K + k) * IIF_MAX_DIM;
+    t.out_mhidx = d_lab + noff[k];
+    t.out_nan = d_misc + k;
+    t.out_status = d_misc + K + k;
+  }
+  CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ConvTask) * K, cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaEventRecord(ctx->ev0, ctx->stream));
+  iif_conv_kernel<<<K, IIF_THREADS, 0, ctx->stream>>>(ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
+  CKC(cudaGetLastError());
+  CKC(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->launches += 1;
+  std::vector<int32_t> misc(2 * K);
+  CKC(cudaMemcpyAsync(out_pts, d_pts, sizeof(double) * poff[K], cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaMemcpyAsync(out_bw, d_bw, sizeof(double) * K * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaMemcpyAsync(out_ipc, d_bw + (int64_t)K * IIF_MAX_DIM, sizeof(double) * K * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_mhidx) CKC(cudaMemcpyAsync(out_mhidx, d_lab, sizeof(int32_t) * noff[K], cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaMemcpyAsync(misc.data(), d_misc, sizeof(int32_t) * 2 * K, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  cleanup();
+#undef CKC
+  if (out_nan) for (int k = 0; k < K; ++k) out_nan[k] = misc[k];
+  for (int k = 0; k < K; ++k)
+    if (misc[K + k] != IIF_OK) {
+      char b[160];
+      snprintf(b, sizeof(b), "conv_batch: op %d failed on device: %s", k, status_name(misc[K + k]));
+      return fail(ctx, misc[K + k], b);
+    }
+  return IIF_OK;
+}
+
+// ---- hot path: product batch -------------------------------------------------------------------
+int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op* ops, const double* dens_pts,
+                              const double* dens_bw, const int32_t* dens_mask, const double* old_pts,
+                              const double* randU, const double* randN, double* out_pts, double* out_bw,
+                              int32_t* out_labels) {
+  if (!ctx) return IIF_ERR_ARG;
+  if (V < 1 || !ops || !dens_pts || !dens_bw || !out_pts || !out_bw) return fail(ctx, IIF_ERR_ARG, "product_batch: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<int64_t> doff(V + 1, 0), foff(V + 1, 0), ooff(V + 1, 0), loff(V + 1, 0);
+  int64_t n_u = 0, n_n = 0;
+  size_t smem = 0;
+  for (int v = 0; v < V; ++v) {
+    const iif_product_op& o = ops[v];
+    if (o.dim < 1 || o.dim > IIF_MAX_DIM || o.nfactors < 1 || o.nfactors > IIF_MAX_FACTORS)
+      return fail(ctx, IIF_ERR_ARG, "product op: dim / nfactors out of range");
+    int32_t st = ensure_tree(ctx, o.N);
+    if (st != IIF_OK) return st;
+    doff[v + 1] = doff[v] + (int64_t)o.nfactors * o.N * o.dim;
+    foff[v + 1] = foff[v] + o.nfactors;
+    ooff[v + 1] = ooff[v] + (int64_t)o.N * o.dim;
+    loff[v + 1] = loff[v] + (int64_t)o.N * o.nfactors;
+    const int L = ctx->trees[o.N].L;
+    if (o.randu_off >= 0) n_u = std::max<int64_t>(n_u, o.randu_off + (int64_t)o.N * L * ctx->sp.gibbsNiter * o.nfactors);
+    if (o.randn_off >= 0) n_n = std::max<int64_t>(n_n, o.randn_off + (int64_t)o.N * o.dim);
+    smem = std::max(smem, prod_smem_bytes(o.nfactors, o.N, o.dim, ctx->trees[o.N].nn));
+  }
+  if ((n_u && !randU) || (n_n && !randN)) return fail(ctx, IIF_ERR_ARG, "product_batch: explicit stream offset given but array is NULL");
+  if ((int)smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "product op exceeds the shared-memory budget (F*N*d too large)");
+  double *d_in = nullptr, *d_bw = nullptr, *d_old = nullptr, *d_u = nullptr, *d_n = nullptr, *d_out = nullptr, *d_obw = nullptr;
+  int32_t *d_lab = nullptr, *d_st = nullptr;
+  ProdTask* d_tasks = nullptr;
+  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_bw); cudaFree(d_old); cudaFree(d_u); cudaFree(d_n); cudaFree(d_out); cudaFree(d_obw); cudaFree(d_lab); cudaFree(d_st); cudaFree(d_tasks); };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return IIF_ERR_CUDA; } } while (0)
+  CKC(cudaMalloc(&d_in, sizeof(double) * doff[V]));
+  CKC(cudaMalloc(&d_bw, sizeof(double) * foff[V] * IIF_MAX_DIM));
+  CKC(cudaMalloc(&d_out, sizeof(double) * ooff[V]));
+  CKC(cudaMalloc(&d_obw, sizeof(double) * V * IIF_MAX_DIM));
+  CKC(cudaMalloc(&d_lab, sizeof(int32_t) * loff[V]));
+  CKC(cudaMalloc(&d_st, sizeof(int32_t) * V));
+  CKC(cudaMalloc(&d_tasks, sizeof(ProdTask) * V));
+  CKC(cudaMemcpyAsync(d_in, dens_pts, sizeof(double) * doff[V], cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(d_bw, dens_bw, sizeof(double) * foff[V] * IIF_MAX_DIM, cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemsetAsync(d_st, 0, sizeof(int32_t) * V, ctx->stream));
+  if (old_pts) { CKC(cudaMalloc(&d_old, sizeof(double) * ooff[V])); CKC(cudaMemcpyAsync(d_old, old_pts, sizeof(double) * ooff[V], cudaMemcpyHostToDevice, ctx->stream)); }
+  if (n_u) { CKC(cudaMalloc(&d_u, sizeof(double) * n_u)); CKC(cudaMemcpyAsync(d_u, randU, sizeof(double) * n_u, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (n_n) { CKC(cudaMalloc(&d_n, sizeof(double) * n_n)); CKC(cudaMemcpyAsync(d_n, randN, sizeof(double) * n_n, cudaMemcpyHostToDevice, ctx->stream)); }
+  std::vector<ProdTask> tasks(V);
+  for (int v = 0; v < V; ++v) {
+    ProdTask& t = tasks[v];
+    memset(&t, 0, sizeof(t));
+    const iif_product_op& o = ops[v];
+    t.dim = o.dim; t.circ_mask = o.circ_mask; t.F = o.nfactors; t.N = o.N;
+    t.call_id = o.call_id; t.randu_off = o.randu_off; t.randn_off = o.randn_off;
+    t.target_slot = -1; t.out_slot = -1;
+    for (int j = 0; j < o.nfactors; ++j) t.mask[j] = dens_mask ? dens_mask[foff[v] + j] : 0;
+    t.dens_pts = d_in + doff[v];
+    t.dens_bw = d_bw + foff[v] * IIF_MAX_DIM;
+    t.old_pts = d_old ? d_old + ooff[v] : nullptr;
+    t.out_pts = d_out + ooff[v];
+    t.out_bw = d_obw + (int64_t)v * IIF_MAX_DIM;
+    t.out_labels = d_lab + loff[v];
+    t.conv_status = nullptr;
+    t.out_status = d_st + v;
+  }
+  CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ProdTask) * V, cudaMemcpyHostToDevice, ctx->stream));
+  DeviceGraph dg = ctx->dg;
+  dg.sp = ctx->sp;
+  CKC(cudaEventRecord(ctx->ev0, ctx->stream));
+  iif_product_kernel<<<V, IIF_THREADS, smem, ctx->stream>>>(dg, d_tasks, d_u, d_n, ctx->d_trees);
+  CKC(cudaGetLastError());
+  CKC(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->launches += 1;
+  CKC(cudaMemcpyAsync(out_pts, d_out, sizeof(double) * ooff[V], cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaMemcpyAsync(out_bw, d_obw, sizeof(double) * V * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_labels) CKC(cudaMemcpyAsync(out_labels, d_lab, sizeof(int32_t) * loff[V], cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  cleanup();
+#undef CKC
+  return IIF_OK;
+}
+
+// ---- KDE bandwidth of K point sets ---------------------------------------------------------------
+int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, const int32_t* dim,
+                              const int32_t* circ_mask, const double* pts, double* out_bw) {
+  if (!ctx) return IIF_ERR_ARG;
+  if (K < 1 || !N || !dim || !circ_mask || !pts || !out_bw) return fail(ctx, IIF_ERR_ARG, "kde_bandwidth: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<int64_t> off(K + 1, 0);
+  for (int k = 0; k < K; ++k) {
+    if (dim[k] < 1 || dim[k] > IIF_MAX_DIM) return fail(ctx, IIF_ERR_ARG, "kde_bandwidth: dim out of range");
+    int32_t st = ensure_tree(ctx, N[k]);
+    if (st != IIF_OK) return st;
+    off[k + 1] = off[k] + (int64_t)N[k] * dim[k];
+  }
+  double *d_pts = nullptr, *d_bw = nullptr;
+  BwTask* d_t = nullptr;
+  CK(cudaMalloc(&d_pts, sizeof(double) * off[K]));
+  CK(cudaMalloc(&d_bw, sizeof(double) * K * IIF_MAX_DIM));
+  CK(cudaMalloc(&d_t, sizeof(BwTask) * K));
+  std::vector<BwTask> t(K);
+  for (int k = 0; k < K; ++k) { t[k].pts = d_pts + off[k]; t[k].out_bw = d_bw + (int64_t)k * IIF_MAX_DIM; t[k].N = N[k]; t[k].dim = dim[k]; t[k].circ_mask = circ_mask[k]; t[k]._pad = 0; }
+  CK(cudaMemcpyAsync(d_pts, pts, sizeof(double) * off[K], cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_t, t.data(), sizeof(BwTask) * K, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  iif_bandwidth_kernel<<<K, IIF_THREADS, 0, ctx->stream>>>(d_t, ctx->d_trees);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(out_bw, d_bw, sizeof(double) * K * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_pts); cudaFree(d_bw); cudaFree(d_t);
+  return IIF_OK;
+}
+
+// ---- schedules: propagateBelief waves captured as a CUDA graph -----------------------------------
+static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
+                              const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, Schedule** out) {
+  // per-prop scratch layout: proposals F*N*d doubles, then bw F*4, ipc F*4 (ipc unused downstream)
+  std::vector<int64_t> soff(nprops + 1, 0);
+  std::vector<int> cidx(nprops + 1, 0);
+  for (int p = 0; p < nprops; ++p) {
+    const iif_prop_op& P = props[p];
+    if (P.nfactors < 1 || P.nfactors > IIF_MAX_FACTORS) return fail(ctx, IIF_ERR_ARG, "prop op: nfactors out of range");
+    if (P.target_slot < 0 || P.target_slot >= (int)ctx->slots.size() || P.out_slot < 0 || P.out_slot >= (int)ctx->slots.size())
+      return fail(ctx, IIF_ERR_ARG, "prop op: slot out of range");
+    const iif_slot_desc& S = ctx->slots[P.target_slot];
+    const iif_slot_desc& O = ctx->slots[P.out_slot];
+    if (O.dim != S.dim || O.cap < P.N) return fail(ctx, IIF_ERR_ARG, "prop op: out slot incompatible with target");
+    for (int f = 0; f < P.nfactors; ++f) {
+      iif_conv_op c{};
+      c.factor = P.factor[f]; c.sfidx = P.sfidx[f]; c.N = P.N;
+      int32_t st = validate_conv(ctx, c);
+      if (st != IIF_OK) return st;
+      if (ctx->factors[c.factor].slot[c.sfidx - 1] != P.target_slot)
+        return fail(ctx, IIF_ERR_ARG, "prop op: factor's solve-for variable is not the target slot");
+    }
+    soff[p + 1] = soff[p] + (int64_t)P.nfactors * P.N * S.dim + 2 * (int64_t)P.nfactors * IIF_MAX_DIM;
+    cidx[p + 1] = cidx[p] + P.nfactors;
+  }
+  Schedule* s = new Schedule();
+  *out = s;
+  s->nconv = cidx[nprops];
+  s->nprod = nprops;
+  std::vector<ConvTask> ct;
+  std::vector<ProdTask> pt;
+  std::vector<int32_t> cp;
+  CK(cudaMalloc(&s->d_scratch, sizeof(double) * std::max<int64_t>(soff[nprops], 1)));
+  CK(cudaMalloc(&s->d_status, sizeof(int32_t) * std::max(s->nconv + s->nprod, 1)));
+  CK(cudaMemsetAsync(s->d_status, 0, sizeof(int32_t) * std::max(s->nconv + s->nprod, 1), ctx->stream));
+  std::vector<char> used(nprops, 0);
+  for (int w = 0; w < nwaves; ++w) {
+    Wave W;
+    W.conv0 = (int)ct.size(); W.prod0 = (int)pt.size(); W.copy0 = (int)cp.size() / 2;
+    if (wave_off[w] < 0 || wave_off[w + 1] > nops || wave_off[w] > wave_off[w + 1]) return fail(ctx, IIF_ERR_ARG, "schedule: bad wave offsets");
+    for (int k = wave_off[w]; k < wave_off[w + 1]; ++k) {
+      const iif_sched_op& o = ops[k];
+      if (o.kind == IIF_S_COPY) {
+        if (o.a < 0 || o.a >= (int)ctx->slots.size() || o.b < 0 || o.b >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "schedule: copy slot out of range");
+        if (ctx->slots[o.a].dim != ctx->slots[o.b].dim || ctx->slots[o.b].cap < ctx->slots[o.a].cap) return fail(ctx, IIF_ERR_ARG, "schedule: copy slots incompatible");
+        cp.push_back(o.a); cp.push_back(o.b);
+      } else if (o.kind == IIF_S_PROPAGATE) {
+        if (o.a < 0 || o.a >= nprops) return fail(ctx, IIF_ERR_ARG, "schedule: prop index out of range");
+        if (used[o.a]) return fail(ctx, IIF_ERR_ARG, "schedule: a prop op may appear once (its Philox call ids are unique)");
+        used[o.a] = 1;
+        const iif_prop_op& P = props[o.a];
+        const iif_slot_desc& S = ctx->slots[P.target_slot];
+        double* base = s->d_scratch + soff[o.a];
+        double* bwbase = base + (int64_t)P.nfactors * P.N * S.dim;
+        ProdTask t;
+        memset(&t, 0, sizeof(t));
+        for (int f = 0; f < P.nfactors; ++f) {
+          const iif_factor_desc& F = ctx->factors[P.factor[f]];
+          ConvTask c;
+          memset(&c, 0, sizeof(c));
+          c.op.factor = P.factor[f]; c.op.sfidx = P.sfidx[f]; c.op.N = P.N;
+          c.op.call_id = P.call_id + 1 + f;
+          // proposalbeliefs!: relative non-multihypo siblings of a multihypo factor (ApproxConv.jl:256-265)
+          c.op.nullSurplus = (P.any_multihypo && !is_prior_kind_h(F.kind) && !F.nmh) ? ctx->sp.nullSurplusAdd : 0.0;
+          c.op.meas_off = c.op.mhidx_off = c.op.uinf_off = -1;
+          c.out_pts = base + (int64_t)f * P.N * S.dim;
+          c.out_bw = bwbase + (int64_t)f * IIF_MAX_DIM;
+          c.out_ipc = bwbase + (int64_t)(P.nfactors + f) * IIF_MAX_DIM;
+          c.out_mhidx = nullptr; c.out_nan = nullptr;
+          c.out_status = s->d_status + cidx[o.a] + f;
+          ct.push_back(c);
+          t.mask[f] = F.partial_mask;
+        }
+        t.dim = S.dim; t.circ_mask = S.circ_mask; t.F = P.nfactors; t.N = P.N;
+        t.call_id = P.call_id; t.randu_off = t.randn_off = -1;
+        t.target_slot = P.target_slot; t.out_slot = P.out_slot;
+        t.dens_pts = base; t.dens_bw = bwbase; t.old_pts = nullptr;
+        t.out_pts = nullptr; t.out_bw = nullptr; t.out_labels = nullptr;
+        t.conv_status = s->d_status + cidx[o.a];
+        t.out_status = s->d_status + s->nconv + o.a;
+        pt.push_back(t);
+        W.prod_smem = std::max(W.prod_smem, prod_smem_bytes(P.nfactors, P.N, S.dim, ctx->trees[P.N].nn));
+      } else return fail(ctx, IIF_ERR_ARG, "schedule: unknown op kind");
+    }
+    W.nconv = (int)ct.size() - W.conv0; W.nprod = (int)pt.size() - W.prod0; W.ncopy = (int)cp.size() / 2 - W.copy0;
+    if ((int)W.prod_smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "schedule: product exceeds the shared-memory budget");
+    s->waves.push_back(W);
+  }
+  CK(cudaMalloc(&s->d_conv, sizeof(ConvTask) * std::max<size_t>(ct.size(), 1)));
+  CK(cudaMalloc(&s->d_prod, sizeof(ProdTask) * std::max<size_t>(pt.size(), 1)));
+  CK(cudaMalloc(&s->d_copy, sizeof(int32_t) * std::max<size_t>(cp.size(), 2)));
+  if (!ct.empty()) CK(cudaMemcpyAsync(s->d_conv, ct.data(), sizeof(ConvTask) * ct.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!pt.empty()) CK(cudaMemcpyAsync(s->d_prod, pt.data(), sizeof(ProdTask) * pt.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!cp.empty()) CK(cudaMemcpyAsync(s->d_copy, cp.data(), sizeof(int32_t) * cp.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IIF_OK;
+}
+
+int32_t iifb200_schedule_build(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
+                               const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props,
+                               int32_t* schedule_id_out) {
+  NEED_GRAPH();
+  if (nwaves < 1 || !wave_off || nops < 0 || !ops || nprops < 0 || !schedule_id_out) return fail(ctx, IIF_ERR_ARG, "schedule_build: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  Schedule* s = nullptr;
+  int32_t st = build_schedule(ctx, nwaves, wave_off, nops, ops, nprops, props, &s);
+  if (st != IIF_OK) { free_schedule(s); return st; }
+  ctx->schedules.push_back(s);
+  *schedule_id_out = (int32_t)ctx->schedules.size() - 1;
+  return IIF_OK;
+}
+
+// enqueue waves [w0, w1) on the ctx stream; returns the number of kernels launched
+static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int* nk) {
+  int k = 0;
+  for (int w = w0; w < w1; ++w) {
+    const Wave& W = s->waves[w];
+    if (W.ncopy) {
+      iif_copy_kernel<<<W.ncopy, 128, 0, ctx->stream>>>(ctx->dg, s->d_copy + 2 * W.copy0, W.ncopy);
+      ++k;
+    }
+    if (W.nconv) {
+      iif_conv_kernel<<<W.nconv, IIF_THREADS, 0, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      ++k;
+    }
+    if (W.nprod) {
+      iif_product_kernel<<<W.nprod, IIF_THREADS, W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      ++k;
+    }
+  }
+  CK(cudaGetLastError());
+  *nk = k;
+  return IIF_OK;
+}
+
+int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t first_wave, int32_t last_wave) {
+  NEED_GRAPH();
+  if (schedule_id < 0 || schedule_id >= (int)ctx->schedules.size() || !ctx->schedules[schedule_id]) return fail(ctx, IIF_ERR_ARG, "schedule_run: bad schedule id");
+  Schedule* s = ctx->schedules[schedule_id];
+  const int nw = (int)s->waves.size();
+  if (first_wave < 0) first_wave = 0;
+  if (last_wave < 0 || last_wave > nw) last_wave = nw;
+  if (first_wave >= last_wave) return IIF_OK;
+  CK(cudaSetDevice(ctx->device));
+  auto key = std::make_pair(first_wave, last_wave);
+  auto it = s->graphs.find(key);
+  if (it == s->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    int nk = 0;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int32_t st = enqueue_waves(ctx, s, first_wave, last_wave, &nk);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (st != IIF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+    if (e != cudaSuccess) return fail(ctx, IIF_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(ctx, IIF_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    it = s->graphs.emplace(key, std::make_pair(exec, nk)).first;
+  }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaGraphLaunch(it->second.first, ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->launches += it->second.second;
+  return IIF_OK;
+}
+
+int32_t iifb200_schedule_free(iifb200_ctx* ctx, int32_t schedule_id) {
+  if (!ctx) return IIF_ERR_ARG;
+  if (schedule_id < 0 || schedule_id >= (int)ctx->schedules.size()) return fail(ctx, IIF_ERR_ARG, "schedule_free: bad id");
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_schedule(ctx->schedules[schedule_id]);
+  ctx->schedules[schedule_id] = nullptr;
+  return IIF_OK;
+}
+
+// V independent propagateBelief calls: a one-wave schedule, not cached
+int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* ops) {
+  NEED_GRAPH();
+  if (V < 1 || !ops) return fail(ctx, IIF_ERR_ARG, "propagate_batch: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<iif_sched_op> so(V);
+  for (int v = 0; v < V; ++v) { so[v].kind = IIF_S_PROPAGATE; so[v].a = v; so[v].b = 0; so[v]._pad = 0; }
+  int32_t wo[2] = {0, V};
+  Schedule* s = nullptr;
+  int32_t st = build_schedule(ctx, 1, wo, V, so.data(), V, ops, &s);
+  if (st != IIF_OK) { free_schedule(s); return st; }
+  int nk = 0;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  st = enqueue_waves(ctx, s, 0, 1, &nk);
+  if (st == IIF_OK) {
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->timed = true;
+    ctx->launches += nk;
+    std::vector<int32_t> stat(s->nconv + s->nprod);
+    cudaError_t e = cudaMemcpyAsync(stat.data(), s->d_status, sizeof(int32_t) * stat.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free_schedule(s); return fail(ctx, IIF_ERR_CUDA, std::string("propagate_batch: ") + cudaGetErrorString(e)); }
+    for (size_t i = 0; i < stat.size(); ++i)
+      if (stat[i] != IIF_OK) { st = fail(ctx, stat[i], std::string("propagate_batch: device reported '") + status_name(stat[i]) + "'"); break; }
+  }
+  free_schedule(s);
+  return st;
+}
+
+int32_t iifb200_sync(iifb200_ctx* ctx) {
+  if (!ctx) return IIF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // surface device-side failures of schedule runs
+  for (auto* s : ctx->schedules) {
+    if (!s) continue;
+    std::vector<int32_t> stat(s->nconv + s->nprod);
+    if (stat.empty()) continue;
+    CK(cudaMemcpy(stat.data(), s->d_status, sizeof(int32_t) * stat.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < stat.size(); ++i)
+      if (stat[i] != IIF_OK) {
+        cudaMemset(s->d_status, 0, sizeof(int32_t) * stat.size());
+        return fail(ctx, stat[i], std::string("schedule: device reported '") + status_name(stat[i]) + "'");
+      }
+  }
+  return IIF_OK;
+}
+
+int64_t iifb200_launch_count(const iifb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* iifb200_stream(iifb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+float iifb200_last_elapsed_ms(iifb200_ctx* ctx) {
+  if (!ctx || !ctx->timed) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+}  // extern "C"

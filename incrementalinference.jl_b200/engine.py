@@ -1,0 +1,173 @@
+"""Thin Python binding of the C-ABI (include/iifb200.h): one Engine == one iifb200_ctx.
+
+This is the analogue of the Julia `ccall` shim in INTEGRATION.md; it holds no numerics.  Every
+method ends in a kernel launch inside libiifb200.so or raises IIFB200Error — there is no CPU
+fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+
+
+class Engine:
+    def __init__(self, frozen, sp_c, device=0, ext_arena_ptr=None):
+        self.lib = A.load_library()
+        self.frozen = frozen
+        self.sp_c = sp_c
+        ctx = C.c_void_p()
+        st = self.lib.iifb200_init(device, C.byref(ctx))
+        if st != A.IIF_OK:
+            raise A.IIFB200Error(f"iifb200_init failed ({st}): {self.lib.iifb200_last_error(None).decode()}")
+        self.ctx = ctx
+        self._check(self.lib.iifb200_set_graph(
+            ctx, frozen["nslots"], frozen["slots"], frozen["nfactors"], frozen["factors"], frozen["ndists"],
+            frozen["dists"], frozen["nparams"], A.as_dp(frozen["dparams"]), C.byref(sp_c),
+            C.c_void_p(ext_arena_ptr) if ext_arena_ptr else None), "set_graph")
+
+    # ---- plumbing
+    def _check(self, st, what):
+        if st != A.IIF_OK:
+            msg = self.lib.iifb200_last_error(self.ctx).decode()
+            raise A.IIFB200Error(f"{what} failed ({st}): {msg}")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.iifb200_free(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_solver_params(self, sp_c):
+        self.sp_c = sp_c
+        self._check(self.lib.iifb200_set_solver_params(self.ctx, C.byref(sp_c)), "set_solver_params")
+
+    # ---- beliefs
+    def upload_arena(self, arena):
+        self._check(self.lib.iifb200_upload_all(self.ctx, A.as_dp(arena.pts), A.as_dp(arena.bw),
+                                                A.as_ip(arena.npts), A.as_ip(arena.flags)), "upload_all")
+
+    def download_arena(self, arena):
+        self._check(self.lib.iifb200_download_all(self.ctx, A.as_dp(arena.pts), A.as_dp(arena.bw),
+                                                  A.as_dp(arena.ipc), A.as_ip(arena.npts)), "download_all")
+        arena.flags[:] = (arena.npts > 0).astype(np.int32) | arena.flags
+
+    def upload_belief(self, slot, pts, bw=None, initialized=True):
+        s = self.frozen["slots"][slot]
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, s.dim)
+        bwa = None if bw is None else np.ascontiguousarray(bw, dtype=np.float64)
+        self._check(self.lib.iifb200_upload_belief(self.ctx, slot, pts.shape[0], A.as_dp(pts), A.as_dp(bwa),
+                                                   1 if initialized else 0), "upload_belief")
+
+    def download_belief(self, slot):
+        s = self.frozen["slots"][slot]
+        n = C.c_int32(0)
+        pts = np.zeros((s.cap, s.dim))
+        bw, ipc = np.zeros(A.IIF_MAX_DIM), np.zeros(A.IIF_MAX_DIM)
+        self._check(self.lib.iifb200_download_belief(self.ctx, slot, C.cast(C.byref(n), A._ip), A.as_dp(pts),
+                                                     A.as_dp(bw), A.as_dp(ipc)), "download_belief")
+        return pts[:n.value].copy(), bw[:s.dim].copy(), ipc[:s.dim].copy()
+
+    def slot_device_ptr(self, slot):
+        p, b = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.iifb200_slot_device_ptr(self.ctx, slot, C.byref(p), C.byref(b)), "slot_device_ptr")
+        return p.value, b.value
+
+    # ---- hot path
+    def conv_batch(self, ops, K, meas=None, mhidx=None, uinf=None):
+        """ops: ctypes array of ConvOp.  Returns list of (pts N x d, bw, ipc, mhidx, nan)."""
+        dims, Ns = [], []
+        for k in range(K):
+            f = self.frozen["factors"][ops[k].factor]
+            dims.append(self.frozen["slots"][f.slot[ops[k].sfidx - 1]].dim)
+            Ns.append(ops[k].N)
+        tot = sum(n * d for n, d in zip(Ns, dims))
+        out_pts = np.zeros(tot)
+        out_bw = np.zeros(K * A.IIF_MAX_DIM)
+        out_ipc = np.zeros(K * A.IIF_MAX_DIM)
+        out_lab = np.zeros(sum(Ns), dtype=np.int32)
+        out_nan = np.zeros(K, dtype=np.int32)
+        meas = None if meas is None else np.ascontiguousarray(meas, dtype=np.float64)
+        mhidx = None if mhidx is None else np.ascontiguousarray(mhidx, dtype=np.int32)
+        uinf = None if uinf is None else np.ascontiguousarray(uinf, dtype=np.float64)
+        self._check(self.lib.iifb200_conv_batch(self.ctx, K, ops, A.as_dp(meas), A.as_ip(mhidx), A.as_dp(uinf),
+                                                A.as_dp(out_pts), A.as_dp(out_bw), A.as_dp(out_ipc),
+                                                A.as_ip(out_lab), A.as_ip(out_nan)), "conv_batch")
+        res, po, no = [], 0, 0
+        for k in range(K):
+            n, d = Ns[k], dims[k]
+            res.append((out_pts[po:po + n * d].reshape(n, d).copy(),
+                        out_bw[k * A.IIF_MAX_DIM:k * A.IIF_MAX_DIM + d].copy(),
+                        out_ipc[k * A.IIF_MAX_DIM:k * A.IIF_MAX_DIM + d].copy(),
+                        out_lab[no:no + n].copy(), int(out_nan[k])))
+            po += n * d
+            no += n
+        return res
+
+    def product(self, dens_pts, dens_bw, dim, circ_mask=0, dens_mask=None, old_pts=None, call_id=0,
+                randU=None, randN=None):
+        """One AMP.manifoldProduct: dens_pts F x N x d, dens_bw F x d -> (pts, bw, labels N x F)."""
+        dens_pts = np.ascontiguousarray(dens_pts, dtype=np.float64)
+        F, N = dens_pts.shape[0], dens_pts.shape[1]
+        op = (A.ProductOp * 1)()
+        op[0].dim, op[0].circ_mask, op[0].nfactors, op[0].N = dim, circ_mask, F, N
+        op[0].call_id = call_id
+        op[0].randu_off = 0 if randU is not None else -1
+        op[0].randn_off = 0 if randN is not None else -1
+        bwp = np.zeros((F, A.IIF_MAX_DIM))
+        bwp[:, :dim] = np.asarray(dens_bw, dtype=np.float64).reshape(F, dim)
+        mask = None if dens_mask is None else np.ascontiguousarray(dens_mask, dtype=np.int32)
+        old = None if old_pts is None else np.ascontiguousarray(old_pts, dtype=np.float64)
+        ru = None if randU is None else np.ascontiguousarray(randU, dtype=np.float64)
+        rn = None if randN is None else np.ascontiguousarray(randN, dtype=np.float64)
+        out = np.zeros((N, dim))
+        obw = np.zeros(A.IIF_MAX_DIM)
+        lab = np.zeros((N, F), dtype=np.int32)
+        self._check(self.lib.iifb200_product_batch(self.ctx, 1, op, A.as_dp(dens_pts), A.as_dp(bwp), A.as_ip(mask),
+                                                   A.as_dp(old), A.as_dp(ru), A.as_dp(rn), A.as_dp(out),
+                                                   A.as_dp(obw), A.as_ip(lab)), "product_batch")
+        return out, obw[:dim].copy(), lab
+
+    def kde_bandwidth(self, pts, circ_mask=0):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        if pts.ndim == 1:
+            pts = pts.reshape(-1, 1)
+        n, d = pts.shape
+        N = np.array([n], dtype=np.int32)
+        D = np.array([d], dtype=np.int32)
+        M = np.array([circ_mask], dtype=np.int32)
+        bw = np.zeros(A.IIF_MAX_DIM)
+        self._check(self.lib.iifb200_kde_bandwidth(self.ctx, 1, A.as_ip(N), A.as_ip(D), A.as_ip(M), A.as_dp(pts),
+                                                   A.as_dp(bw)), "kde_bandwidth")
+        return bw[:d].copy()
+
+    def propagate_batch(self, prop_ops, V):
+        self._check(self.lib.iifb200_propagate_batch(self.ctx, V, prop_ops), "propagate_batch")
+
+    # ---- schedules
+    def schedule_build(self, wave_off, sched_ops, nops, prop_ops, nprops):
+        wo = np.ascontiguousarray(wave_off, dtype=np.int32)
+        sid = C.c_int32(-1)
+        self._check(self.lib.iifb200_schedule_build(self.ctx, len(wo) - 1, A.as_ip(wo), nops, sched_ops, nprops,
+                                                    prop_ops, C.cast(C.byref(sid), A._ip)), "schedule_build")
+        return sid.value
+
+    def schedule_run(self, sid, first=0, last=-1):
+        self._check(self.lib.iifb200_schedule_run(self.ctx, sid, first, last), "schedule_run")
+
+    def sync(self):
+        self._check(self.lib.iifb200_sync(self.ctx), "sync")
+
+    def launch_count(self):
+        return int(self.lib.iifb200_launch_count(self.ctx))
+
+    def last_elapsed_ms(self):
+        return float(self.lib.iifb200_last_elapsed_ms(self.ctx))
+
+    def stream(self):
+        return self.lib.iifb200_stream(self.ctx)

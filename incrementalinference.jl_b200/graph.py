@@ -1,0 +1,342 @@
+"""Host-side mirror of the reference's factor-graph / plugin surface for the hot path.
+
+Julia is the reference's host language and is not installed in this image, so the host
+orchestration above the C-ABI is mirrored in Python with the reference's names and argument
+meaning (`initfg`, `addVariable!` -> `addVariable`, `addFactor!` -> `addFactor`, ...).
+Only what the clique belief-convolution path needs is mirrored; the production host remains
+the Julia package calling `libiifb200.so` through `ccall`.
+
+Reference: src/services/FactorGraph.jl (addVariable! :573-631, addFactor! :806-861,
+parseusermultihypo :633-654), src/Variables/DefaultVariables.jl, src/Factors/*.jl,
+src/entities/SolverParams.jl.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi as A
+
+
+# ---------------------------------------------------------------- variable types
+@dataclass(frozen=True)
+class InferenceVariable:
+    """@defVariable Name Manifold identity (src/Variables/DefaultVariables.jl:9-52)."""
+    name: str
+    dim: int
+    circ_mask: int = 0
+
+
+def Position(n: int) -> InferenceVariable:  # DefaultVariables.jl:9-24
+    return InferenceVariable(f"Position{{{n}}}", n, 0)
+
+
+ContinuousEuclid = Position
+ContinuousScalar = Position(1)              # DefaultVariables.jl:32
+Circular = InferenceVariable("Circular", 1, 1)  # DefaultVariables.jl:52  RealCircleGroup
+
+
+# ---------------------------------------------------------------- SamplableBelief
+@dataclass
+class Normal:
+    mu: float = 0.0
+    sigma: float = 1.0
+    dim: int = 1
+
+
+@dataclass
+class Uniform:
+    a: float = 0.0
+    b: float = 1.0
+    dim: int = 1
+
+
+class MvNormal:
+    def __init__(self, mu, cov):
+        self.mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
+        cov = np.asarray(cov, dtype=np.float64)
+        if cov.ndim == 1:
+            cov = np.diag(cov)
+        self.cov = cov
+        self.L = np.linalg.cholesky(cov)
+        self.dim = self.mu.shape[0]
+
+
+@dataclass
+class ManifoldKernelDensity:
+    """AMP.ManifoldKernelDensity as IIF consumes it: points, per-dim bandwidth, partial, ipc."""
+    vartype: InferenceVariable
+    pts: np.ndarray                      # N x d
+    bw: np.ndarray                       # d
+    partial: Optional[List[int]] = None  # 1-based coordinate list
+    infoPerCoord: Optional[np.ndarray] = None
+
+    @property
+    def dim(self):
+        return self.vartype.dim
+
+
+def getPoints(mkd: ManifoldKernelDensity, _=False):
+    return mkd.pts
+
+
+def getBW(mkd: ManifoldKernelDensity):
+    return mkd.bw
+
+
+def Npts(mkd: ManifoldKernelDensity):
+    return mkd.pts.shape[0]
+
+
+# ---------------------------------------------------------------- factors (src/Factors)
+@dataclass
+class Prior:               # DefaultPrior.jl:8
+    Z: object
+    kind = A.F_PRIOR
+    is_prior = True
+
+
+@dataclass
+class PriorCircular:       # Circular.jl:54
+    Z: object
+    kind = A.F_PRIOR_CIRCULAR
+    is_prior = True
+
+
+@dataclass
+class PartialPrior:        # PartialPrior.jl:11-21
+    Z: object
+    partial: Sequence[int]  # 1-based coordinates
+    kind = A.F_PARTIAL_PRIOR
+    is_prior = True
+
+
+@dataclass
+class MsgPrior:            # MsgPrior.jl:10
+    Z: object              # ManifoldKernelDensity or SlotRef (device-resident belief)
+    infoPerCoord: Optional[np.ndarray] = None
+    kind = A.F_MSG_PRIOR
+    is_prior = True
+
+
+@dataclass
+class LinearRelative:      # LinearRelative.jl:13
+    Z: object
+    kind = A.F_LINEAR_RELATIVE
+    is_prior = False
+
+
+@dataclass
+class CircularCircular:    # Circular.jl:13
+    Z: object
+    kind = A.F_CIRCULAR_CIRCULAR
+    is_prior = False
+
+
+@dataclass
+class EuclidDistance:      # EuclidDistance.jl:9
+    Z: object
+    kind = A.F_EUCLID_DISTANCE
+    is_prior = False
+
+
+class Mixture:
+    """Mixture(mechanics, components, diversity) — src/Factors/Mixture.jl:37-45."""
+
+    def __init__(self, mechanics, components, diversity):
+        self.mechanics = mechanics if isinstance(mechanics, type) else type(mechanics)
+        self.components = list(components)
+        w = np.asarray(diversity, dtype=np.float64)
+        self.diversity = w / w.sum()
+        self.kind = self.mechanics.kind
+        self.is_prior = self.mechanics.is_prior
+        self.Z = self
+
+
+@dataclass
+class SlotRef:
+    """A density that already lives in a device belief slot (separator message)."""
+    slot: int
+    dim: int
+
+
+# ---------------------------------------------------------------- SolverParams
+@dataclass
+class SolverParams:
+    """src/entities/SolverParams.jl:12-75 (hot-path subset, same defaults)."""
+    N: int = 100
+    spreadNH: float = 3.0
+    inflation: float = 5.0
+    nullSurplusAdd: float = 0.3
+    inflateCycles: int = 3
+    gibbsIters: int = 3
+    graphinit: bool = True
+    useMsgLikelihoods: bool = False
+    alwaysFreshMeasurements: bool = True
+    downsolve: bool = True
+    seed: int = 42            # Random.seed! analogue: Philox key of every device stream
+    devParams: Dict[str, str] = field(default_factory=lambda: {"backend": "b200"})
+
+
+# ---------------------------------------------------------------- graph
+@dataclass
+class DFGVariable:
+    label: str
+    vartype: InferenceVariable
+    val: np.ndarray                 # npts x d (VariableNodeData.val)
+    bw: np.ndarray                  # d       (VariableNodeData.bw[:,1])
+    infoPerCoord: np.ndarray
+    initialized: bool = False
+    index: int = -1
+
+
+@dataclass
+class DFGFactor:
+    label: str
+    variables: List[str]            # getVariableOrder
+    fnc: object                     # getFactorType
+    multihypo: Optional[np.ndarray]  # parseusermultihypo output (Categorical.p) or None
+    nullhypo: float
+    inflation: float
+    index: int = -1
+
+    @property
+    def is_prior(self):
+        return self.fnc.is_prior
+
+
+def isMultihypo(f: DFGFactor) -> bool:
+    return f.multihypo is not None
+
+
+def parseusermultihypo(multihypo, nullhypo):
+    """FactorGraph.jl:633-654."""
+    if multihypo is None or len(multihypo) == 0:
+        return None, float(nullhypo)
+    mh = np.array(multihypo, dtype=np.float64)
+    mh[mh > 1 - 1e-10] = 0.0
+    s = mh.sum()
+    assert abs(s % 1) < 1e-10 or 1 - 1e-10 < s % 1, "ensure multihypo sums to an integer, see #1086"
+    assert abs(mh[mh > 1e-10].sum() - 1) < 1e-8
+    mh /= mh.sum()
+    return mh, float(nullhypo)
+
+
+class FactorGraph:
+    def __init__(self, solverParams: Optional[SolverParams] = None):
+        self.variables: Dict[str, DFGVariable] = {}
+        self.factors: Dict[str, DFGFactor] = {}
+        self.solverParams = solverParams or SolverParams()
+        self._engine = None          # lazily-built device engine (solver.Engine)
+        self._version = 0            # bumped on structural change
+
+    # DFG accessors used by the mirrored API
+    def getVariable(self, lbl):
+        return self.variables[lbl]
+
+    def getFactor(self, lbl):
+        return self.factors[lbl]
+
+    def ls(self, lbl=None):
+        return list(self.variables) if lbl is None else self.listNeighbors(lbl)
+
+    def lsf(self, lbl=None):
+        return list(self.factors) if lbl is None else self.listNeighbors(lbl)
+
+    def listNeighbors(self, lbl):
+        if lbl in self.variables:
+            return [f.label for f in self.factors.values() if lbl in f.variables]
+        return list(self.factors[lbl].variables)
+
+
+def initfg(solverParams: Optional[SolverParams] = None) -> FactorGraph:
+    return FactorGraph(solverParams)
+
+
+def getSolverParams(fg: FactorGraph) -> SolverParams:
+    return fg.solverParams
+
+
+def addVariable(fg: FactorGraph, label: str, vartype: InferenceVariable) -> DFGVariable:
+    """addVariable! — FactorGraph.jl:573-631 (uninitialised: no points yet)."""
+    assert label not in fg.variables
+    d = vartype.dim
+    assert d <= A.IIF_MAX_DIM, f"variable dimension {d} > IIF_MAX_DIM"
+    v = DFGVariable(label, vartype, np.zeros((0, d)), np.zeros(d), np.zeros(d), False,
+                    len(fg.variables))
+    fg.variables[label] = v
+    fg._version += 1
+    return v
+
+
+def addFactor(fg: FactorGraph, variables: Sequence[str], fnc, multihypo=None, nullhypo: float = 0.0,
+              graphinit: Optional[bool] = None, inflation: Optional[float] = None,
+              label: Optional[str] = None) -> DFGFactor:
+    """addFactor! — FactorGraph.jl:806-861."""
+    variables = list(variables)
+    for v in variables:
+        assert v in fg.variables, f"unknown variable {v}"
+    assert len(variables) <= A.IIF_MAX_ARITY
+    if not hasattr(fnc, "kind"):
+        raise A.IIFB200Error(
+            f"factor type {type(fnc).__name__} has no device residual: only the built-in residual "
+            "library is supported on the b200 backend (no CPU fallback)")
+    if label is None:
+        base = "".join(variables) + "f"
+        k = 1
+        while f"{base}{k}" in fg.factors:
+            k += 1
+        label = f"{base}{k}"
+    mh, nh = parseusermultihypo(multihypo, nullhypo)
+    if mh is not None:
+        assert len(mh) == len(variables)
+    f = DFGFactor(label, variables, fnc, mh, nh,
+                  fg.solverParams.inflation if inflation is None else float(inflation),
+                  len(fg.factors))
+    fg.factors[label] = f
+    fg._version += 1
+    do_init = fg.solverParams.graphinit if graphinit is None else graphinit
+    if do_init:
+        from .solver import doautoinit
+        for v in variables:
+            doautoinit(fg, v)
+    return f
+
+
+def isInitialized(fg_or_var, lbl=None) -> bool:
+    v = fg_or_var if lbl is None else fg_or_var.variables[lbl]
+    return v.initialized
+
+
+def getVal(v: DFGVariable):
+    return v.val
+
+
+def getBelief(fg: FactorGraph, lbl: str) -> ManifoldKernelDensity:
+    """FactorGraph.jl:335 — rebuild an MKD from VND (val, bw)."""
+    v = fg.variables[lbl]
+    return ManifoldKernelDensity(v.vartype, v.val.copy(), v.bw.copy(), None, v.infoPerCoord.copy())
+
+
+def setValKDE(fg: FactorGraph, lbl: str, mkd: ManifoldKernelDensity, setinit=True, ipc=None):
+    """setValKDE! — FactorGraph.jl:237-286."""
+    v = fg.variables[lbl]
+    v.val = np.ascontiguousarray(mkd.pts, dtype=np.float64).reshape(-1, v.vartype.dim).copy()
+    v.bw = np.asarray(mkd.bw, dtype=np.float64).copy()
+    if ipc is not None:
+        v.infoPerCoord = np.asarray(ipc, dtype=np.float64).copy()
+    if setinit:
+        v.initialized = True
+    if fg._engine is not None:
+        fg._engine.mark_dirty(lbl)
+
+
+def initVariable(fg: FactorGraph, lbl: str, pts, bw=None):
+    """initVariable!(fg, lbl, points) — GraphInit.jl:288-330: manual initialisation."""
+    from .solver import kde_bandwidth
+    v = fg.variables[lbl]
+    pts = np.ascontiguousarray(np.asarray(pts, dtype=np.float64).reshape(-1, v.vartype.dim))
+    if bw is None:
+        bw = kde_bandwidth(fg, v.vartype, pts)
+    setValKDE(fg, lbl, ManifoldKernelDensity(v.vartype, pts, np.asarray(bw, dtype=np.float64)), True,
+              np.zeros(v.vartype.dim))

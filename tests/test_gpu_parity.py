@@ -1,0 +1,110 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI of libiifb200.so) against the CPU
+oracle on identical seeded inputs.  Labels bit-exact; points within parity_cases.TOL_PTS."""
+import numpy as np
+import pytest
+
+import parity_cases as PC
+from iifb200 import compile as CP
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", list(PC.conv_cases()), ids=lambda c: c[0])
+def test_conv_parity(built, case):
+    name, P, specs, streams = case
+    pairs = PC.run_conv_case(P, specs, streams)
+    PC.assert_conv_equal(name, pairs, circ=("circ" in name or "msgprior" in name))
+
+
+@pytest.fixture(scope="module")
+def bare_engine(built):
+    P, xs, fs = PC.chain_problem(n=2, N=8)
+    eng = P.engine()
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("case", list(PC.product_cases()), ids=lambda c: c[0])
+def test_product_parity(bare_engine, case):
+    name, kw = case
+    o, g = PC.run_product_case(kw, bare_engine)
+    PC.assert_product_equal(name, o, g, circ="circ" in name)
+
+
+def test_kde_bandwidth_parity(bare_engine):
+    import oracle as O
+    R = np.random.default_rng(5)
+    for n, d, cm in [(100, 1, 0), (100, 2, 0), (150, 1, 1), (200, 3, 0b010), (256, 1, 0), (2, 1, 0), (17, 4, 0)]:
+        pts = R.normal(0, 1, (n, d)) * R.uniform(0.1, 10, d)
+        for c in range(d):
+            if (cm >> c) & 1:
+                pts[:, c] = PC.wrap(pts[:, c])
+        assert np.allclose(O.kde_bandwidth(pts, cm), bare_engine.kde_bandwidth(pts, cm), rtol=PC.TOL_BW)
+
+
+@pytest.mark.parametrize("circular", [False, True])
+def test_propagate_batch_parity(built, circular):
+    P, xs, fs = PC.chain_problem(n=5, N=100, seed=9, circular=circular)
+    specs = PC.chain_prop_specs(xs, fs, 100)
+    # independent ops only: even variables (their factors read odd variables) into their own slots
+    specs = [s for k, s in enumerate(specs) if k % 2 == 0]
+    props = CP.make_prop_ops(specs)
+    orc = P.oracle()
+    for k in range(len(specs)):
+        orc.propagate(props[k])
+    eng = P.engine()
+    eng.propagate_batch(props, len(specs))
+    ag = P.arena.copy()
+    eng.download_arena(ag)
+    eng.close()
+    PC.assert_arena_equal("propagate", orc.arena, ag, P.frozen, [s["out_slot"] for s in specs], circ=circular)
+
+
+def test_schedule_parity_gauss_seidel(built):
+    """3 Gibbs sweeps over a 4-variable chain (fmcmc!, SolveTree.jl:112-134): each propagate sees the
+    previous one's write (Gauss-Seidel), captured as one CUDA graph."""
+    P, xs, fs = PC.chain_problem(n=4, N=100, seed=21)
+    specs, sched, wave_off = [], [], [0]
+    for sweep in range(3):
+        for s in PC.chain_prop_specs(xs, fs, 100, call0=5000 + 1000 * sweep):
+            specs.append(s)
+            sched.append((CP.A.S_PROPAGATE, len(specs) - 1, 0))
+            wave_off.append(len(sched))
+    props = CP.make_prop_ops(specs)
+    ops = CP.make_sched_ops(sched)
+    orc = P.oracle()
+    orc.schedule_run(wave_off, ops, props)
+    eng = P.engine()
+    sid = eng.schedule_build(wave_off, ops, len(sched), props, len(specs))
+    eng.schedule_run(sid)
+    eng.sync()
+    ag = P.arena.copy()
+    eng.download_arena(ag)
+    n_launch = eng.launch_count()
+    eng.close()
+    assert n_launch == 2 * len(sched)
+    PC.assert_arena_equal("schedule", orc.arena, ag, P.frozen, xs)
+
+
+def test_conv_does_not_mutate_target(built):
+    """approxConv must not change the target variable (testMultiHypo3Door.jl:59-90, ApproxConv.jl:17)."""
+    name, P, specs, streams = next(PC.conv_cases())
+    eng = P.engine()
+    eng.conv_batch(CP.make_conv_ops(specs), len(specs))
+    after = P.arena.copy()
+    eng.download_arena(after)
+    eng.close()
+    assert np.array_equal(after.pts, P.arena.pts) and np.array_equal(after.bw, P.arena.bw)
+
+
+def test_unsupported_and_bad_arguments_fail_loudly(built):
+    from iifb200._abi import IIFB200Error
+    P, xs, fs = PC.chain_problem(n=2, N=16)
+    eng = P.engine()
+    with pytest.raises(IIFB200Error):
+        eng.conv_batch(CP.make_conv_ops([dict(factor=99, sfidx=1, N=16, call_id=1)]), 1)
+    with pytest.raises(IIFB200Error):
+        eng.conv_batch(CP.make_conv_ops([dict(factor=fs[1], sfidx=3, N=16, call_id=1)]), 1)
+    with pytest.raises(IIFB200Error):
+        eng.conv_batch(CP.make_conv_ops([dict(factor=fs[1], sfidx=2, N=1000, call_id=1)]), 1)
+    eng.close()
