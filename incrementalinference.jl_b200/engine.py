@@ -83,9 +83,12 @@ class Engine:
         """ops: ctypes array of ConvOp.  Returns list of (pts N x d, bw, ipc, mhidx, nan)."""
         dims, Ns = [], []
         for k in range(K):
-            f = self.frozen["factors"][ops[k].factor]
-            dims.append(self.frozen["slots"][f.slot[ops[k].sfidx - 1]].dim)
-            Ns.append(ops[k].N)
+            # invalid descriptors are sized conservatively here and rejected by the C side
+            ok = 0 <= ops[k].factor < self.frozen["nfactors"]
+            f = self.frozen["factors"][ops[k].factor] if ok else None
+            ok = ok and 1 <= ops[k].sfidx <= f.arity
+            dims.append(self.frozen["slots"][f.slot[ops[k].sfidx - 1]].dim if ok else A.IIF_MAX_DIM)
+            Ns.append(max(int(ops[k].N), 1))
         tot = sum(n * d for n, d in zip(Ns, dims))
         out_pts = np.zeros(tot)
         out_bw = np.zeros(K * A.IIF_MAX_DIM)

@@ -265,8 +265,9 @@ def product_cases():
                                          randU=R.random(N * 7 * 2), randN=R.normal(0, 1, N))
 
 
-def run_product_case(case, engine, seed=42):
+def run_product_case(case, engine):
     import oracle as O
+    seed = int(engine.sp_c.seed)  # the engine's Philox key drives the Gibbs streams
     kw = dict(case)
     dim = kw.pop("dim")
     o = O.product(kw["dens_pts"], kw["dens_bw"], dim, kw.get("circ_mask", 0), kw.get("dens_mask"),
