@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — clique belief convolutions / second (N=100 particles) on the 1000-pose
+ContinuousScalar odometry chain (BASELINE.json configs[1]), one process per GPU.
+
+A "step" is one solveTree!-equivalent pass (tree up + down solve) over the chain: every
+propagateBelief of the pass runs as sm_100a kernels inside libiifb200.so, replayed as one CUDA
+graph.  `value` = convolutions / s with beliefs resident in HBM (CUDA events on the library's
+stream); `e2e` = the same through the C-ABI with pinned HOST buffers (H2D of the graph's beliefs,
+solve, D2H of the posteriors inside the timed region).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            # CPU reference arm
+
+Multi-GPU (weak scaling): a chain of 1000*N poses is sharded by contiguous segments over the N
+ranks; cliques run on the rank that owns their frontal variable and only the separator messages
+that cross a segment boundary travel over NCCL (torch.distributed, NVLink).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+POSES_PER_GPU = 1000
+NPART = 100
+
+
+# ----------------------------------------------------------------------------- helpers
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def conv_bytes(plan):
+    """algorithmic HBM bytes of every convolution of the plan, device-RNG mode:
+    8*N*[(a-1)*P + P] (sources + target init) + 4*N (labels) + 8*N*P + 16*d (proposal, bw, ipc)."""
+    tot = 0
+    fac, slots = plan.frozen["factors"], plan.frozen["slots"]
+    for pr in plan.props:
+        for fi, sf in pr["factors"]:
+            f = fac[fi]
+            d = slots[f.slot[sf - 1]].dim
+            a = f.arity
+            tot += 8 * pr["N"] * ((a - 1) * d + d) + 4 * pr["N"] + 8 * pr["N"] * d + 16 * d
+    return tot
+
+
+def build_workload(n_poses, order_kind):
+    import iifb200  # noqa: F401
+    from iifb200 import workloads as W
+    fg = W.scalar_chain(n_poses, N=NPART, seed=42)
+    order = W.chain_nd_order(n_poses) if order_kind == "nd" else [f"x{k}" for k in range(n_poses)]
+    return fg, order
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """CPU reference arm.  The reference is pure Julia and no Julia toolchain exists in this image
+    (DESIGN.md), so this times the oracle port of the same path with all host threads (OpenMP over
+    the independent ops of a wave) on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ctypes
+    import oracle as O
+    from iifb200 import compile as CP
+    from iifb200 import tree as TR
+    cores = os.cpu_count() or 1
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        cores = 1
+    n_sample = 100  # poses in the bounded sample (same chain kind, same N, same elimination-order kind)
+    fg, order = build_workload(n_sample, args.order)
+    tree = TR.buildTree(fg, order)
+    plan = TR.compile_solve(fg, tree)
+    base = CP.HostArena(plan.frozen)
+    for l, v in fg.variables.items():
+        base.set(plan.var_slot[l], v.val, v.bw, True)
+    props, ops = CP.make_prop_ops(plan.props), CP.make_sched_ops(plan.sched_waved)
+    times = []
+    for it in range(args.warmup + args.steps):
+        sp = CP.solver_params_c(fg.solverParams, 42 + it)
+        orc = O.Oracle(plan.frozen, base.copy(), sp)
+        t0 = time.perf_counter()
+        orc.schedule_run(plan.wave_off, ops, props)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    val = plan.n_conv * len(times) / tot
+    sample = f"{len(times)} solves of a {n_sample}-pose chain of the same kind ({plan.n_conv} convolutions each)"
+    out = {
+        "impl": "reference", "metric": "clique belief convolutions/sec (N=100 particles)", "value": val,
+        "unit": "conv/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{POSES_PER_GPU}-pose ContinuousScalar odometry chain, N={NPART} (bounded sample: {n_sample} poses)",
+                   "elimination_order": args.order, "N": NPART},
+        "cpu_baseline": {"value": val, "unit": "conv/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "conv/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is pure Julia; Julia is not installed in this image, so the oracle port is timed (kind=port)",
+    }
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------- b200 arm
+def cpu_baseline_sample(order_kind):
+    """oracle port, 1 thread, bounded sample (rank 0, N=1 only)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ctypes
+    import oracle as O
+    from iifb200 import compile as CP
+    from iifb200 import tree as TR
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(1)
+    except OSError:
+        pass
+    n_sample = 100
+    fg, order = build_workload(n_sample, order_kind)
+    plan = TR.compile_solve(fg, TR.buildTree(fg, order))
+    ar = CP.HostArena(plan.frozen)
+    for l, v in fg.variables.items():
+        ar.set(plan.var_slot[l], v.val, v.bw, True)
+    orc = O.Oracle(plan.frozen, ar, CP.solver_params_c(fg.solverParams))
+    nrep, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 12.0:
+        orc.schedule_run(plan.wave_off, CP.make_sched_ops(plan.sched_waved), CP.make_prop_ops(plan.props))
+        nrep += 1
+    dt = time.perf_counter() - t0
+    return {"value": plan.n_conv * nrep / dt, "unit": "conv/s", "cores": 1, "kind": "port",
+            "sample": f"{nrep} solves of a {n_sample}-pose chain of the same kind ({plan.n_conv} convolutions each), 1 thread"}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import iifb200  # noqa: F401
+    from iifb200 import compile as CP
+    from iifb200 import solver as SV
+    from iifb200.multigpu import ShardedTreeSolver
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_poses = POSES_PER_GPU * world
+    fg, order = build_workload(n_poses, args.order)
+    if world == 1:
+        ts = SV.TreeSolver(fg, order, device=local_rank)
+        runner = None
+    else:
+        runner = ShardedTreeSolver(fg, order, rank, world, local_rank, dist)
+        ts = runner.ts
+    plan, eng = ts.plan, ts.eng
+    nvars = len(fg.variables)
+    my_conv = plan.n_conv if runner is None else runner.my_conv
+    total_conv = plan.n_conv
+
+    # pinned host staging of the main-graph slots (slots 0..nvars-1 are the graph's variables)
+    fz = plan.frozen
+    nd = fz["slots"][nvars].pts_off if fz["nslots"] > nvars else fz["total_doubles"]
+    hp = eng.host_alloc(8 * nd).view(np.float64)
+    hbw = eng.host_alloc(8 * nvars * 4).view(np.float64)
+    hipc = eng.host_alloc(8 * nvars * 4).view(np.float64)
+    hn = eng.host_alloc(4 * nvars).view(np.int32)
+    hfl = eng.host_alloc(4 * nvars).view(np.int32)
+    ts.load_from_graph()
+    hp[:] = ts.arena.pts[:nd]
+    hbw[:] = ts.arena.bw[:nvars * 4]
+    hn[:] = ts.arena.npts[:nvars]
+    hfl[:] = ts.arena.flags[:nvars]
+    init_pts = hp.copy()
+    h2d = hp.nbytes + hbw.nbytes + hn.nbytes + hfl.nbytes
+    d2h = hp.nbytes + hbw.nbytes + hipc.nbytes + hn.nbytes
+
+    def set_seed(it):
+        eng.set_solver_params(CP.solver_params_c(fg.solverParams, 42 + it))
+
+    def solve():
+        if runner is None:
+            ts.run()
+        else:
+            runner.run()
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
+
+    def flush_l2():
+        flush.add_(1.0)
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also instantiates the CUDA graphs)
+    eng.upload_slots(0, nvars, hp, hbw, hn, hfl)
+    for it in range(max(args.warmup, 3)):
+        set_seed(1000 + it)
+        solve()
+    barrier()
+
+    # ---- timed: device-resident beliefs, per-step CUDA events on the library's stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    hp[:] = init_pts
+    eng.upload_slots(0, nvars, hp, hbw, hn, hfl)
+    barrier()
+    l0 = eng.launch_count()
+    ms_steps = []
+    for it in range(args.steps):
+        flush_l2()
+        set_seed(it)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+        if runner is None:
+            ts.run()
+            eng.sync()
+            ms_steps.append(eng.last_elapsed_ms())
+        else:
+            ms_steps.append(runner.run_timed())
+    barrier()
+    launches = eng.launch_count() - l0
+    dev_ms = float(sum(ms_steps))
+
+    # ---- timed: end to end through the C-ABI with host buffers
+    e2e_s = 0.0
+    for it in range(args.steps):
+        hp[:] = init_pts
+        flush_l2()
+        set_seed(100 + it)
+        barrier()
+        t0 = time.perf_counter()
+        eng.upload_slots(0, nvars, hp, hbw, hn, hfl)
+        solve()
+        eng.download_slots(0, nvars, hp, hbw, hipc, hn)
+        eng.sync()
+        e2e_s += time.perf_counter() - t0
+    clocks = sampler.stop()
+    post_mean_err = float(np.abs(hp.reshape(nvars, NPART).mean(axis=1) - np.arange(nvars)).max())
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_s, float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+        tl = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl[0])
+
+    # ---- live per-kernel timing for the roofline (CUDA events around every launch, rank 0)
+    roof, prof = None, None
+    if rank == 0:
+        prof = eng.schedule_profile(ts.sid) if runner is None else runner.profile()
+        pk, src = peaks()
+        cms, cl, cb = prof["conv"]
+        byts = conv_bytes(plan) * (my_conv / max(total_conv, 1))
+        ach = byts / (cms * 1e-3) / 1e9 if cms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "iif_conv_kernel", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)",
+                "launch_ms_avg": cms / max(cl, 1), "launches": cl, "blocks": cb,
+                "kernel_ms": {k: v[0] for k, v in prof.items()},
+                "note": "FP64-issue bound, not HBM bound: the exact O(N^2) leave-one-out bandwidth search "
+                        "dominates (see DESIGN.md); traffic: see profiles/"}
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline_sample(args.order) if world == 1 and not args.no_cpu_baseline else None
+    val = total_conv * args.steps / (dev_ms * 1e-3)
+    out = {
+        "metric": "clique belief convolutions/sec (N=100 particles)", "value": val, "unit": "conv/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n_poses}-pose ContinuousScalar odometry chain (Prior + LinearRelative), N={NPART}, "
+                               f"one solveTree pass = {total_conv} convolutions + {plan.n_prod} products",
+                   "poses": n_poses, "N": NPART, "elimination_order": args.order, "waves": len(plan.wave_off) - 1,
+                   "l2": "flushed between timed steps (256 MiB write)", "rng": "device Philox4x32-10, new seed every step",
+                   "sharding": "1 GPU" if world == 1 else f"{world} contiguous 1000-pose segments, NCCL separator messages"},
+        "e2e": {"value": total_conv * args.steps / e2e_s, "unit": "conv/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        "products_per_s": plan.n_prod * args.steps / (dev_ms * 1e-3),
+        "posterior_mean_abs_err_max": post_mean_err,
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--order", default="nd", choices=["nd", "natural"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -177,6 +177,16 @@ int32_t iifb200_upload_all(iifb200_ctx* ctx, const double* pts, const double* bw
                            const int32_t* npts, const int32_t* flags);
 int32_t iifb200_download_all(iifb200_ctx* ctx, double* pts, double* bw, double* ipc,
                              int32_t* npts);
+/* contiguous slot range [first, first+count): pts packed back to back starting at slot `first`'s
+ * offset, bw count*IIF_MAX_DIM, npts/flags count.  Asynchronous on the ctx stream when the host
+ * buffers are pinned (iifb200_host_alloc); call iifb200_sync before reading downloaded data. */
+int32_t iifb200_upload_slots(iifb200_ctx* ctx, int32_t first, int32_t count, const double* pts,
+                             const double* bw, const int32_t* npts, const int32_t* flags);
+int32_t iifb200_download_slots(iifb200_ctx* ctx, int32_t first, int32_t count, double* pts, double* bw,
+                               double* ipc, int32_t* npts);
+/* pinned host memory for the transfers above */
+int32_t iifb200_host_alloc(iifb200_ctx* ctx, int64_t bytes, void** ptr_out);
+int32_t iifb200_host_free(iifb200_ctx* ctx, void* ptr);
 /* raw device pointer of a slot's points (for NCCL send/recv of separator messages);
  * layout: pts[cap*dim]; bw/ipc live in the tail region, see iifb200_slot_msg_ptr */
 int32_t iifb200_slot_device_ptr(iifb200_ctx* ctx, int32_t slot, void** pts_ptr, void** bw_ptr);
@@ -243,8 +253,17 @@ int32_t iifb200_sync(iifb200_ctx* ctx);
 /* ---- instrumentation ---------------------------------------------------------------- */
 /* kernels launched by this ctx since init (for bench.py "gpu_launches") */
 int64_t iifb200_launch_count(const iifb200_ctx* ctx);
+/* Make the ctx launch on a caller-owned cudaStream_t (e.g. the torch stream NCCL collectives are
+ * ordered on), so separator-message exchanges need no host synchronisation.  NULL restores the
+ * ctx's own stream.  Captured CUDA graphs stay valid (they are launched into the new stream). */
+int32_t iifb200_set_stream(iifb200_ctx* ctx, void* stream);
 /* cudaStream_t used by the ctx (as void*), so callers can record CUDA events on it */
 void* iifb200_stream(iifb200_ctx* ctx);
+/* Runs waves [first,last) WITHOUT the CUDA graph, bracketing every kernel launch with CUDA events on
+ * the ctx stream, and returns per-kernel totals: ms[0..2] / launches[0..2] / blocks[0..2] for the
+ * convolution, product and copy kernels.  Used by bench.py for the live roofline figure. */
+int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t first_wave,
+                                 int32_t last_wave, float* ms, int32_t* launches, int64_t* blocks);
 /* time the last schedule_run / *_batch call took on the device, in ms (CUDA events on the
  * ctx stream; valid after iifb200_sync) */
 float iifb200_last_elapsed_ms(iifb200_ctx* ctx);

@@ -85,6 +85,10 @@ SYMBOLS = {
     "iifb200_download_belief": (C.c_int32, [_vp, C.c_int32, _ip, _dp, _dp, _dp]),
     "iifb200_upload_all": (C.c_int32, [_vp, _dp, _dp, _ip, _ip]),
     "iifb200_download_all": (C.c_int32, [_vp, _dp, _dp, _dp, _ip]),
+    "iifb200_upload_slots": (C.c_int32, [_vp, C.c_int32, C.c_int32, _dp, _dp, _ip, _ip]),
+    "iifb200_download_slots": (C.c_int32, [_vp, C.c_int32, C.c_int32, _dp, _dp, _dp, _ip]),
+    "iifb200_host_alloc": (C.c_int32, [_vp, C.c_int64, P(_vp)]),
+    "iifb200_host_free": (C.c_int32, [_vp, _vp]),
     "iifb200_slot_device_ptr": (C.c_int32, [_vp, C.c_int32, P(_vp), P(_vp)]),
     "iifb200_conv_batch": (C.c_int32, [_vp, C.c_int32, P(ConvOp), _dp, _ip, _dp, _dp, _dp, _dp, _ip, _ip]),
     "iifb200_product_batch": (C.c_int32, [_vp, C.c_int32, P(ProductOp), _dp, _dp, _ip, _dp, _dp, _dp,
@@ -95,8 +99,11 @@ SYMBOLS = {
                                            P(PropOp), _ip]),
     "iifb200_schedule_run": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32]),
     "iifb200_schedule_free": (C.c_int32, [_vp, C.c_int32]),
+    "iifb200_schedule_profile": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, P(C.c_float), _ip,
+                                             P(C.c_int64)]),
     "iifb200_sync": (C.c_int32, [_vp]),
     "iifb200_launch_count": (C.c_int64, [_vp]),
+    "iifb200_set_stream": (C.c_int32, [_vp, _vp]),
     "iifb200_stream": (_vp, [_vp]),
     "iifb200_last_elapsed_ms": (C.c_float, [_vp]),
 }

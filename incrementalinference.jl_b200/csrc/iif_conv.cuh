@@ -21,7 +21,7 @@ struct DeviceGraph {
   double* ipc;
   int32_t* npts;
   int32_t* flags;
-  iif_solver_params sp;
+  const iif_solver_params* sp;  // device memory: updated between graph replays without re-capture
   int32_t nslots, nfactors, ndists, _pad;
 };
 
@@ -163,7 +163,7 @@ __device__ int sample_measurement(const DeviceGraph& g, const iif_factor_desc& f
                                   double* z) {
   const iif_dist_desc D = g.dists[f.dist];
   const double* prm = g.dparams + D.poff;
-  const uint64_t seed = g.sp.seed;
+  const uint64_t seed = g.sp->seed;
   switch (D.kind) {
     case IIF_D_NORMAL:
     case IIF_D_UNIFORM:
@@ -325,7 +325,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   const iif_slot_desc S = g.slots[sslot];
   const int d = S.dim;
   const int32_t cm = S.circ_mask;
-  const uint64_t seed = g.sp.seed;
+  const uint64_t seed = g.sp->seed;
   const uint32_t call = (uint32_t)op.call_id;
   const bool active = n < N;
 
@@ -368,7 +368,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   }
   const int32_t fullmask = (1 << d) - 1;
   const int32_t pmask = f.partial_mask ? f.partial_mask : fullmask;
-  const int C = g.sp.inflateCycles;
+  const int C = g.sp->inflateCycles;
   int nnan = 0;
 
   auto inflate_u = [&](int cyc, int c) -> double {
@@ -390,7 +390,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   if (s_status == IIF_OK) {
     if (is_prior_kind(f.kind)) {
       // evalPotentialSpecific (AbstractPrior) — EvalFactor.jl:400-542
-      double spreadDist = g.sp.spreadNH * block_std_basic_spread(dest, N, d, cm, mu_s, red, parity);  // :464
+      double spreadDist = g.sp->spreadNH * block_std_basic_spread(dest, N, d, cm, mu_s, red, parity);  // :464
       const bool wrap = (f.kind == IIF_F_PRIOR_CIRCULAR || f.kind == IIF_F_MSG_PRIOR);
       if (active && label == 1) {
         if (!f.partial_mask) {
@@ -455,7 +455,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
         } else {
           // other-hypothesis (:208-220) and null-hypothesis (:222-231): entropy only, all dims
           __syncthreads();
-          double sp = block_spread_distance(g, f, sfidx, dest, N, R, g.sp.spreadNH, mu_s, red, parity);
+          double sp = block_spread_distance(g, f, sfidx, dest, N, R, g.sp->spreadNH, mu_s, red, parity);
           add_entropy(hyp, fullmask, sp, C);
         }
       }

@@ -178,8 +178,8 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     int32_t covered = 0;
     for (int j = 0; j < F; ++j) covered |= masks[j];
     // ---- 2./3. multiscale Gibbs: one warp per output sample
-    const int niter = g.sp.gibbsNiter;
-    const uint64_t seed = g.sp.seed;
+    const int niter = g.sp->gibbsNiter;
+    const uint64_t seed = g.sp->seed;
     const uint32_t call = (uint32_t)t.call_id;
     for (int s = warp; s < N; s += IIF_WARPS) {
       int node[IIF_MAX_FACTORS];

@@ -42,6 +42,7 @@ struct Schedule {
 struct iifb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   std::string err;
@@ -56,6 +57,8 @@ struct iifb200_ctx {
   int64_t total_doubles = 0;
   void* d_tables = nullptr;
   int32_t* d_err = nullptr;
+  iif_solver_params* d_sp = nullptr;
+  std::vector<void*> pinned;
   // ball-tree structures per N
   TreeHost trees[IIF_MAX_POINTS + 1];
   TreeStruct h_trees[IIF_MAX_POINTS + 1];
@@ -162,13 +165,17 @@ int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
     return IIF_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  ctx->stream = ctx->own_stream;
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->d_trees, sizeof(TreeStruct) * (IIF_MAX_POINTS + 1))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->d_trees, 0, sizeof(TreeStruct) * (IIF_MAX_POINTS + 1))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMalloc(&ctx->d_err, sizeof(int32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->d_err, 0, sizeof(int32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMalloc(&ctx->d_sp, sizeof(iif_solver_params))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemcpy(ctx->d_sp, &ctx->sp, sizeof(iif_solver_params), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+  ctx->dg.sp = ctx->d_sp;
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_ordinal);
   if ((e = cudaFuncSetAttribute(iif_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ctx->max_smem_optin - 4096)) != cudaSuccess)
@@ -201,9 +208,11 @@ void iifb200_free(iifb200_ctx* ctx) {
   for (auto& t : ctx->trees) if (t.d_blob) cudaFree(t.d_blob);
   cudaFree(ctx->d_trees);
   cudaFree(ctx->d_err);
+  cudaFree(ctx->d_sp);
+  for (void* p : ctx->pinned) cudaFreeHost(p);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
@@ -281,7 +290,8 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
   dg.ipc = dg.bw + (int64_t)nslots * IIF_MAX_DIM;
   dg.npts = (int32_t*)(dg.ipc + (int64_t)nslots * IIF_MAX_DIM);
   dg.flags = dg.npts + nslots;
-  dg.sp = *sp;
+  dg.sp = ctx->d_sp;
+  CK(cudaMemcpyAsync(ctx->d_sp, sp, sizeof(iif_solver_params), cudaMemcpyHostToDevice, ctx->stream));
   dg.nslots = nslots; dg.nfactors = nfactors; dg.ndists = ndists;
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
@@ -289,11 +299,11 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
 
 int32_t iifb200_set_solver_params(iifb200_ctx* ctx, const iif_solver_params* sp) {
   if (!ctx || !sp) return IIF_ERR_ARG;
+  // Kernels read the params through a device pointer, so captured CUDA graphs stay valid; the copy
+  // is stream-ordered after earlier launches.  nullSurplusAdd is baked into schedules at build time.
+  CK(cudaSetDevice(ctx->device));
   ctx->sp = *sp;
-  ctx->dg.sp = *sp;
-  // captured graphs hold the old params by value: drop them
-  for (auto* s : ctx->schedules)
-    if (s) { for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second.first); s->graphs.clear(); }
+  CK(cudaMemcpyAsync(ctx->d_sp, &ctx->sp, sizeof(iif_solver_params), cudaMemcpyHostToDevice, ctx->stream));
   return IIF_OK;
 }
 
@@ -353,6 +363,53 @@ int32_t iifb200_download_all(iifb200_ctx* ctx, double* pts, double* bw, double* 
   if (ipc) CK(cudaMemcpyAsync(ipc, ctx->dg.ipc, sizeof(double) * ns * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   if (npts) CK(cudaMemcpyAsync(npts, ctx->dg.npts, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return IIF_OK;
+}
+
+int32_t iifb200_upload_slots(iifb200_ctx* ctx, int32_t first, int32_t count, const double* pts, const double* bw,
+                             const int32_t* npts, const int32_t* flags) {
+  NEED_GRAPH();
+  const int ns = (int)ctx->slots.size();
+  if (first < 0 || count < 1 || first + count > ns) return fail(ctx, IIF_ERR_ARG, "upload_slots: slot range out of bounds");
+  const int64_t o0 = ctx->slots[first].pts_off;
+  const int64_t o1 = (first + count < ns) ? ctx->slots[first + count].pts_off : ctx->total_doubles;
+  if (pts) CK(cudaMemcpyAsync(ctx->dg.pts + o0, pts, sizeof(double) * (o1 - o0), cudaMemcpyHostToDevice, ctx->stream));
+  if (bw) CK(cudaMemcpyAsync(ctx->dg.bw + (int64_t)first * IIF_MAX_DIM, bw, sizeof(double) * count * IIF_MAX_DIM, cudaMemcpyHostToDevice, ctx->stream));
+  if (npts) CK(cudaMemcpyAsync(ctx->dg.npts + first, npts, sizeof(int32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+  if (flags) CK(cudaMemcpyAsync(ctx->dg.flags + first, flags, sizeof(int32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+  return IIF_OK;
+}
+
+int32_t iifb200_download_slots(iifb200_ctx* ctx, int32_t first, int32_t count, double* pts, double* bw, double* ipc,
+                               int32_t* npts) {
+  NEED_GRAPH();
+  const int ns = (int)ctx->slots.size();
+  if (first < 0 || count < 1 || first + count > ns) return fail(ctx, IIF_ERR_ARG, "download_slots: slot range out of bounds");
+  const int64_t o0 = ctx->slots[first].pts_off;
+  const int64_t o1 = (first + count < ns) ? ctx->slots[first + count].pts_off : ctx->total_doubles;
+  if (pts) CK(cudaMemcpyAsync(pts, ctx->dg.pts + o0, sizeof(double) * (o1 - o0), cudaMemcpyDeviceToHost, ctx->stream));
+  if (bw) CK(cudaMemcpyAsync(bw, ctx->dg.bw + (int64_t)first * IIF_MAX_DIM, sizeof(double) * count * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ipc) CK(cudaMemcpyAsync(ipc, ctx->dg.ipc + (int64_t)first * IIF_MAX_DIM, sizeof(double) * count * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  if (npts) CK(cudaMemcpyAsync(npts, ctx->dg.npts + first, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+  return IIF_OK;  // asynchronous: iifb200_sync before reading
+}
+
+int32_t iifb200_host_alloc(iifb200_ctx* ctx, int64_t bytes, void** ptr_out) {
+  if (!ctx || !ptr_out || bytes < 1) return IIF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  CK(cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault));
+  ctx->pinned.push_back(p);
+  *ptr_out = p;
+  return IIF_OK;
+}
+
+int32_t iifb200_host_free(iifb200_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return IIF_ERR_ARG;
+  auto it = std::find(ctx->pinned.begin(), ctx->pinned.end(), ptr);
+  if (it == ctx->pinned.end()) return fail(ctx, IIF_ERR_ARG, "host_free: pointer not from iifb200_host_alloc");
+  ctx->pinned.erase(it);
+  CK(cudaFreeHost(ptr));
   return IIF_OK;
 }
 
@@ -515,10 +572,8 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
     t.out_status = d_st + v;
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ProdTask) * V, cudaMemcpyHostToDevice, ctx->stream));
-  DeviceGraph dg = ctx->dg;
-  dg.sp = ctx->sp;
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_product_kernel<<<V, IIF_THREADS, smem, ctx->stream>>>(dg, d_tasks, d_u, d_n, ctx->d_trees);
+  iif_product_kernel<<<V, IIF_THREADS, smem, ctx->stream>>>(ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -734,6 +789,52 @@ int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t firs
   return IIF_OK;
 }
 
+int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t first_wave, int32_t last_wave,
+                                 float* ms, int32_t* launches, int64_t* blocks) {
+  NEED_GRAPH();
+  if (schedule_id < 0 || schedule_id >= (int)ctx->schedules.size() || !ctx->schedules[schedule_id] || !ms || !launches || !blocks)
+    return fail(ctx, IIF_ERR_ARG, "schedule_profile: bad arguments");
+  Schedule* s = ctx->schedules[schedule_id];
+  const int nw = (int)s->waves.size();
+  if (first_wave < 0) first_wave = 0;
+  if (last_wave < 0 || last_wave > nw) last_wave = nw;
+  CK(cudaSetDevice(ctx->device));
+  for (int k = 0; k < 3; ++k) { ms[k] = 0.f; launches[k] = 0; blocks[k] = 0; }
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+  auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); ev.push_back(e); };
+  for (int w = first_wave; w < last_wave; ++w) {
+    const Wave& W = s->waves[w];
+    if (W.ncopy) {
+      mark();
+      iif_copy_kernel<<<W.ncopy, 128, 0, ctx->stream>>>(ctx->dg, s->d_copy + 2 * W.copy0, W.ncopy);
+      mark(); kind.push_back(2); blocks[2] += W.ncopy;
+    }
+    if (W.nconv) {
+      mark();
+      iif_conv_kernel<<<W.nconv, IIF_THREADS, 0, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      mark(); kind.push_back(0); blocks[0] += W.nconv;
+    }
+    if (W.nprod) {
+      mark();
+      iif_product_kernel<<<W.nprod, IIF_THREADS, W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      mark(); kind.push_back(1); blocks[1] += W.nprod;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  for (size_t i = 0; i < kind.size(); ++i) {
+    float t = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+    ms[kind[i]] += t;
+    launches[kind[i]] += 1;
+  }
+  for (auto x : ev) cudaEventDestroy(x);
+  ctx->launches += (int64_t)kind.size();
+  if (e != cudaSuccess) return fail(ctx, IIF_ERR_CUDA, std::string("schedule_profile: ") + cudaGetErrorString(e));
+  return IIF_OK;
+}
+
 int32_t iifb200_schedule_free(iifb200_ctx* ctx, int32_t schedule_id) {
   if (!ctx) return IIF_ERR_ARG;
   if (schedule_id < 0 || schedule_id >= (int)ctx->schedules.size()) return fail(ctx, IIF_ERR_ARG, "schedule_free: bad id");
@@ -792,6 +893,13 @@ int32_t iifb200_sync(iifb200_ctx* ctx) {
 }
 
 int64_t iifb200_launch_count(const iifb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int32_t iifb200_set_stream(iifb200_ctx* ctx, void* stream) {
+  if (!ctx) return IIF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+  return IIF_OK;
+}
 void* iifb200_stream(iifb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 float iifb200_last_elapsed_ms(iifb200_ctx* ctx) {
   if (!ctx || !ctx->timed) return -1.0f;

@@ -73,6 +73,20 @@ class Engine:
                                                      A.as_dp(bw), A.as_dp(ipc)), "download_belief")
         return pts[:n.value].copy(), bw[:s.dim].copy(), ipc[:s.dim].copy()
 
+    def host_alloc(self, nbytes):
+        """pinned host buffer (numpy uint8 view) for upload_slots / download_slots"""
+        p = C.c_void_p()
+        self._check(self.lib.iifb200_host_alloc(self.ctx, nbytes, C.byref(p)), "host_alloc")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def upload_slots(self, first, count, pts, bw, npts, flags):
+        self._check(self.lib.iifb200_upload_slots(self.ctx, first, count, A.as_dp(pts), A.as_dp(bw), A.as_ip(npts),
+                                                  A.as_ip(flags)), "upload_slots")
+
+    def download_slots(self, first, count, pts, bw, ipc, npts):
+        self._check(self.lib.iifb200_download_slots(self.ctx, first, count, A.as_dp(pts), A.as_dp(bw), A.as_dp(ipc),
+                                                    A.as_ip(npts)), "download_slots")
+
     def slot_device_ptr(self, slot):
         p, b = C.c_void_p(), C.c_void_p()
         self._check(self.lib.iifb200_slot_device_ptr(self.ctx, slot, C.byref(p), C.byref(b)), "slot_device_ptr")
@@ -163,6 +177,14 @@ class Engine:
     def schedule_run(self, sid, first=0, last=-1):
         self._check(self.lib.iifb200_schedule_run(self.ctx, sid, first, last), "schedule_run")
 
+    def schedule_profile(self, sid, first=0, last=-1):
+        """per-kernel CUDA-event totals: dict(conv|product|copy -> (ms, launches, blocks))"""
+        ms = (C.c_float * 3)()
+        ln = (C.c_int32 * 3)()
+        bl = (C.c_int64 * 3)()
+        self._check(self.lib.iifb200_schedule_profile(self.ctx, sid, first, last, ms, ln, bl), "schedule_profile")
+        return {k: (float(ms[i]), int(ln[i]), int(bl[i])) for i, k in enumerate(("conv", "product", "copy"))}
+
     def sync(self):
         self._check(self.lib.iifb200_sync(self.ctx), "sync")
 
@@ -171,6 +193,9 @@ class Engine:
 
     def last_elapsed_ms(self):
         return float(self.lib.iifb200_last_elapsed_ms(self.ctx))
+
+    def set_stream(self, stream_ptr):
+        self._check(self.lib.iifb200_set_stream(self.ctx, C.c_void_p(stream_ptr) if stream_ptr else None), "set_stream")
 
     def stream(self):
         return self.lib.iifb200_stream(self.ctx)

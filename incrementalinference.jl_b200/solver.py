@@ -1,0 +1,268 @@
+"""Reference-facing operator API of the hot path, mirrored in Python above the C-ABI.
+
+Names, argument meaning and error behaviour follow the reference (`!` dropped):
+  approxConvBelief / approxConv   src/services/ApproxConv.jl:4-47
+  propagateBelief                 src/services/GraphProductOperations.jl:16-81
+  localProduct / localProductAndUpdate   src/services/GraphProductOperations.jl:93-155
+  doautoinit / initAll            src/services/GraphInit.jl:132-199, 495-556
+  solveTree / solveGraph          src/services/SolverAPI.jl:326-446
+Every numeric step is a kernel launch in libiifb200.so (Engine); nothing here computes beliefs.
+"""
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi as A
+from . import compile as CP
+from . import graph as G
+from . import tree as TR
+from .engine import Engine
+
+
+# --------------------------------------------------------------------------- per-graph engine
+class GraphEngine:
+    """Device mirror of one FactorGraph: slot i == variable i, factor table == graph factors."""
+
+    def __init__(self, fg: G.FactorGraph, device: int = 0):
+        self.fg = fg
+        self.version = fg._version
+        T = CP.Tables()
+        self.N = fg.solverParams.N
+        self.var_slot = {}
+        for l, v in fg.variables.items():
+            self.var_slot[l] = T.add_slot(v.vartype, max(self.N, v.val.shape[0], 1))
+        self.fac_idx = {}
+        for l, f in fg.factors.items():
+            self.fac_idx[l] = T.add_factor(f.fnc, [self.var_slot[v] for v in f.variables], f.multihypo,
+                                           f.nullhypo, f.inflation)
+        self.frozen = T.freeze()
+        self.sp_c = CP.solver_params_c(fg.solverParams)
+        self.eng = Engine(self.frozen, self.sp_c, device)
+        self.dirty = set(fg.variables)
+        self.call_id = 0
+
+    def mark_dirty(self, lbl):
+        self.dirty.add(lbl)
+
+    def flush(self):
+        for l in list(self.dirty):
+            v = self.fg.variables[l]
+            self.eng.upload_belief(self.var_slot[l], v.val, v.bw, v.initialized)
+        self.dirty.clear()
+
+    def next_call(self, n=16):
+        c = self.call_id
+        self.call_id += n
+        return c
+
+    def close(self):
+        self.eng.close()
+
+
+def _engine(fg: G.FactorGraph) -> GraphEngine:
+    ge = fg._engine
+    if ge is None or ge.version != fg._version or ge.N != fg.solverParams.N:
+        if ge is not None:
+            ge.close()
+        ge = GraphEngine(fg)
+        fg._engine = ge
+    sp_c = CP.solver_params_c(fg.solverParams)
+    if bytes(sp_c) != bytes(ge.sp_c):
+        ge.sp_c = sp_c
+        ge.eng.set_solver_params(sp_c)
+    ge.flush()
+    return ge
+
+
+def kde_bandwidth(fg: G.FactorGraph, vartype: G.InferenceVariable, pts) -> np.ndarray:
+    """manikde!(M, pts) bandwidth selection (AMP; call sites ApproxConv.jl:38-41)."""
+    return _engine(fg).eng.kde_bandwidth(np.asarray(pts, dtype=np.float64).reshape(-1, vartype.dim),
+                                         vartype.circ_mask)
+
+
+def manikde(fg: G.FactorGraph, vartype: G.InferenceVariable, pts, bw=None) -> G.ManifoldKernelDensity:
+    pts = np.ascontiguousarray(np.asarray(pts, dtype=np.float64).reshape(-1, vartype.dim))
+    if bw is None:
+        bw = kde_bandwidth(fg, vartype, pts)
+    return G.ManifoldKernelDensity(vartype, pts, np.asarray(bw, dtype=np.float64))
+
+
+# --------------------------------------------------------------------------- a3: approxConvBelief
+def approxConvBelief(fg: G.FactorGraph, fct: str, target: str, measurement=None, N: Optional[int] = None,
+                     nullSurplus: float = 0.0, mhidx=None, uinf=None, return_labels: bool = False):
+    """approxConvBelief(dfg, fc, target; N, nullSurplus) — ApproxConv.jl:4-45.
+
+    The target variable is NOT modified (ApproxConv.jl:17).  `measurement`, `mhidx`, `uinf` inject
+    host-drawn random streams (Julia-drawn labels stay bit-exact); by default the device draws them.
+    """
+    ge = _engine(fg)
+    f = fg.factors[fct]
+    if target not in f.variables:
+        raise KeyError(f"{target} is not a variable of factor {fct}")
+    v = fg.variables[target]
+    if N is None:
+        N = len(measurement) if measurement is not None and len(measurement) else 0
+    N = N if N else (v.val.shape[0] or fg.solverParams.N)     # ApproxConv.jl:15
+    if N > ge.frozen["slots"][ge.var_slot[target]].cap:
+        fg.solverParams.N = max(fg.solverParams.N, N)          # grow slot capacity
+        ge = _engine(fg)
+    spec = dict(factor=ge.fac_idx[fct], sfidx=f.variables.index(target) + 1, N=N, call_id=ge.next_call(),
+                nullSurplus=nullSurplus)
+    meas = None
+    if measurement is not None and len(measurement):
+        meas = np.ascontiguousarray(np.asarray(measurement, dtype=np.float64).reshape(N, -1))
+        spec["meas_off"] = 0
+    if mhidx is not None:
+        spec["mhidx_off"] = 0
+    if uinf is not None:
+        spec["uinf_off"] = 0
+    ops = CP.make_conv_ops([spec])
+    pts, bw, ipc, lab, nnan = ge.eng.conv_batch(ops, 1, meas, mhidx, uinf)[0]
+    partial = None
+    if np.any(np.abs(ipc) <= 1e-14):                            # ApproxConv.jl:31-42
+        partial = [int(i) + 1 for i in np.nonzero(np.abs(ipc) > 1e-14)[0]]
+    mkd = G.ManifoldKernelDensity(v.vartype, pts, bw, partial, ipc)
+    return (mkd, lab) if return_labels else mkd
+
+
+def approxConv(fg, fct, target, *a, **kw):
+    """approxConv(w...) = getPoints(approxConvBelief(w...), false) — ApproxConv.jl:47."""
+    return G.getPoints(approxConvBelief(fg, fct, target, *a, **kw))
+
+
+# --------------------------------------------------------------------------- a1: propagateBelief
+def propagateBelief(fg: G.FactorGraph, destlbl: str, factors=":", N: Optional[int] = None):
+    """propagateBelief(dfg, destlbl, factors; N) -> (ManifoldKernelDensity, ipc) — GraphProductOperations.jl:16-81.
+    `factors` is ':' (all neighbours) or a list of factor labels."""
+    ge = _engine(fg)
+    N = N or fg.solverParams.N
+    flist = fg.listNeighbors(destlbl) if isinstance(factors, str) and factors == ":" else list(factors)
+    if not flist:
+        raise A.IIFB200Error(f"propagateBelief: no factors for {destlbl}")
+    if len(flist) > A.IIF_MAX_FACTORS:
+        raise A.IIFB200Error(f"propagateBelief: {len(flist)} factors exceed IIF_MAX_FACTORS")
+    T = ge.frozen
+    slot = ge.var_slot[destlbl]
+    # posterior lands in the destination slot on the device, then is read back; the live variable
+    # keeps its value on the host (setBelief! is the caller's decision, SolveTree.jl:74)
+    spec = dict(target_slot=slot, out_slot=slot,
+                factors=[(ge.fac_idx[fl], fg.factors[fl].variables.index(destlbl) + 1) for fl in flist],
+                N=N, call_id=ge.next_call(), any_multihypo=int(any(G.isMultihypo(fg.factors[fl]) for fl in flist)))
+    ge.eng.propagate_batch(CP.make_prop_ops([spec]), 1)
+    pts, bw, ipc = ge.eng.download_belief(slot)
+    ge.mark_dirty(destlbl)   # device slot now differs from the host variable: re-upload before next use
+    del T
+    v = fg.variables[destlbl]
+    return G.ManifoldKernelDensity(v.vartype, pts, bw, None, ipc), ipc
+
+
+def localProduct(fg: G.FactorGraph, sym: str, N: Optional[int] = None):
+    """localProduct — GraphProductOperations.jl:93-120 -> (mkd, dens=None, lbls, ipc)."""
+    lb = fg.listNeighbors(sym)
+    mkd, ipc = propagateBelief(fg, sym, lb, N=N)
+    return mkd, None, lb, ipc
+
+
+def localProductAndUpdate(fg: G.FactorGraph, sym: str, setkde: bool = True):
+    """localProductAndUpdate! — GraphProductOperations.jl:136-155."""
+    mkd, _, lbl, ipc = localProduct(fg, sym)
+    if setkde and G.Npts(mkd) > 0:
+        G.setValKDE(fg, sym, mkd, False, ipc)
+    return mkd, ipc, lbl
+
+
+# --------------------------------------------------------------------------- §8f-1: graph init
+def factorCanInitFromOtherVars(fg: G.FactorGraph, fct: str, lbl: str) -> bool:
+    """GraphInit.jl:39-103: every other variable of the factor is initialised (priors always can;
+    multihypo factors need at least the certain ones — simplified to `all others`)."""
+    f = fg.factors[fct]
+    return all(fg.variables[v].initialized for v in f.variables if v != lbl)
+
+
+def doautoinit(fg: G.FactorGraph, lbl: str, singles: bool = True) -> bool:
+    """doautoinit! — GraphInit.jl:132-199."""
+    v = fg.variables[lbl]
+    if v.initialized:
+        return False
+    nei = fg.listNeighbors(lbl)
+    if not (singles or len(nei) > 1):
+        return False
+    use = [f for f in nei if factorCanInitFromOtherVars(fg, f, lbl)]
+    if not use:
+        return False
+    mkd, ipc = propagateBelief(fg, lbl, use[:A.IIF_MAX_FACTORS])
+    G.setValKDE(fg, lbl, mkd, True, ipc)
+    return True
+
+
+def initAll(fg: G.FactorGraph) -> None:
+    """initAll! — GraphInit.jl:495-556: sweep until nothing new can be initialised."""
+    for _ in range(len(fg.variables) + 1):
+        did = False
+        for l in fg.variables:
+            did |= doautoinit(fg, l)
+        if not did:
+            break
+
+
+# --------------------------------------------------------------------------- solveTree!
+class TreeSolver:
+    """Compiled solveTree!: one device arena with clique-local slots + one CUDA-graph schedule."""
+
+    def __init__(self, fg: G.FactorGraph, eliminationOrder: Optional[Sequence[str]] = None, ordering: str = "qr",
+                 device: int = 0, ext_arena_ptr=None, downsolve: Optional[bool] = None):
+        self.fg = fg
+        order = list(eliminationOrder) if eliminationOrder is not None else TR.getEliminationOrder(fg, ordering)
+        self.tree = TR.buildTree(fg, order)
+        ds = fg.solverParams.downsolve if downsolve is None else downsolve
+        self.plan = TR.compile_solve(fg, self.tree, downsolve=ds)
+        self.sp_c = CP.solver_params_c(fg.solverParams)
+        self.eng = Engine(self.plan.frozen, self.sp_c, device, ext_arena_ptr)
+        self.props_c = CP.make_prop_ops(self.plan.props)
+        self.sched_c = CP.make_sched_ops(self.plan.sched_waved)
+        self.sid = self.eng.schedule_build(self.plan.wave_off, self.sched_c, len(self.plan.sched_waved),
+                                           self.props_c, len(self.plan.props))
+        self.arena = CP.HostArena(self.plan.frozen)
+
+    def load_from_graph(self):
+        for l, v in self.fg.variables.items():
+            self.arena.set(self.plan.var_slot[l], v.val, v.bw, v.initialized, v.infoPerCoord)
+
+    def upload(self):
+        self.eng.upload_arena(self.arena)
+
+    def run(self, first=0, last=-1):
+        self.eng.schedule_run(self.sid, first, last)
+
+    def download(self):
+        self.eng.sync()
+        self.eng.download_arena(self.arena)
+
+    def store_to_graph(self):
+        for l in self.fg.variables:
+            pts, bw, ipc = self.arena.get(self.plan.var_slot[l])
+            G.setValKDE(self.fg, l, G.ManifoldKernelDensity(self.fg.variables[l].vartype, pts, bw), True, ipc)
+
+    def close(self):
+        self.eng.close()
+
+
+def solveTree(fg: G.FactorGraph, eliminationOrder: Optional[Sequence[str]] = None, ordering: str = "qr",
+              device: int = 0):
+    """solveTree!(fg; eliminationOrder) — SolverAPI.jl:326-446 (hot-path subset: graph init, tree build,
+    up + down clique solves, write-back).  Returns the TreeSolver (holds the tree and the plan)."""
+    if fg.solverParams.graphinit:
+        initAll(fg)
+    for l, v in fg.variables.items():
+        if not v.initialized:
+            raise A.IIFB200Error(f"solveTree: variable {l} could not be initialised")
+    ts = TreeSolver(fg, eliminationOrder, ordering, device)
+    ts.load_from_graph()
+    ts.upload()
+    ts.run()
+    ts.download()
+    ts.store_to_graph()
+    return ts
+
+
+solveGraph = solveTree

@@ -1,0 +1,497 @@
+"""Bayes-tree construction and lowering of a `solveTree!` pass to a wave schedule.
+
+Host orchestration is OUT OF SCOPE of the B200 hot path (the factor graph, tree
+build and clique state machine stay in Julia).  The GPU batcher, however, consumes the tree's
+*output* — per-clique variable / factor lists, Gibbs variable classes and tree edges — so this
+module mirrors just enough of the reference to produce that descriptor here (Julia is absent):
+
+  getEliminationOrder      src/services/BayesNet.jl:19-65
+  buildBayesNet!           src/services/BayesNet.jl:139-187
+  buildTree!/newPotential  src/services/JunctionTreeUtils.jl:435-496
+  setCliqPotentials!       src/services/JunctionTreeUtils.jl:1045-1082
+  compCliqAssocMatrices!   src/services/JunctionTreeUtils.jl:1294-1341
+  setCliqMCIDs! and friends  src/services/JunctionTreeUtils.jl:1352-1523
+  upGibbsCliqueDensity     src/services/SolveTree.jl:164-239
+  solveCliqDownFrontalProducts!  src/CliqueStateMachine/services/CliqStateMachineUtils.jl:479-571
+  CSM up/down message flow src/CliqueStateMachine/services/CliqueStateMachine.jl:212-966
+
+The lowering turns every `propagateBelief` of the pass into an iif_prop_op on clique-local
+belief slots and levelises them into waves of mutually independent ops (slot hazards), which
+libiifb200 captures as one CUDA graph.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _abi as A
+from . import compile as CP
+from . import graph as G
+
+
+# ------------------------------------------------------------------ elimination order
+def getEliminationOrder(fg: G.FactorGraph, ordering: str = "qr") -> List[str]:
+    """BayesNet.jl:19-65.  `qr`: column-pivoted QR of the biadjacency matrix, reversed.
+    `natural`: insertion order.  `nd`: nested dissection on the variable adjacency graph
+    (a user-supplied `eliminationOrder`, SolverAPI.jl:338, that makes chain trees bushy)."""
+    labels = list(fg.variables)
+    if ordering == "natural":
+        return labels
+    if ordering == "nd":
+        return nested_dissection_order(fg)
+    if ordering == "qr":
+        import scipy.linalg
+        facs = list(fg.factors.values())
+        Amat = np.zeros((len(facs), len(labels)))
+        col = {l: i for i, l in enumerate(labels)}
+        for r, f in enumerate(facs):
+            for v in f.variables:
+                Amat[r, col[v]] = 1.0
+        _, _, p = scipy.linalg.qr(Amat, pivoting=True, mode="economic")
+        return [labels[i] for i in p[::-1]]
+    raise ValueError(f"unknown ordering {ordering}")
+
+
+def nested_dissection_order(fg: G.FactorGraph) -> List[str]:
+    """Recursive bisection by BFS level sets; separators are eliminated last."""
+    adj: Dict[str, set] = {l: set() for l in fg.variables}
+    for f in fg.factors.values():
+        for a in f.variables:
+            for b in f.variables:
+                if a != b:
+                    adj[a].add(b)
+    order: List[str] = []
+
+    def bfs_far(nodes, start):
+        seen, frontier, last = {start}, [start], start
+        while frontier:
+            nxt = []
+            for u in frontier:
+                for w in adj[u]:
+                    if w in nodes and w not in seen:
+                        seen.add(w)
+                        nxt.append(w)
+            if nxt:
+                last = nxt[-1]
+            frontier = nxt
+        return last, seen
+
+    def levels(nodes, start):
+        lev, seen, frontier = [], {start}, [start]
+        while frontier:
+            lev.append(frontier)
+            nxt = []
+            for u in frontier:
+                for w in adj[u]:
+                    if w in nodes and w not in seen:
+                        seen.add(w)
+                        nxt.append(w)
+            frontier = nxt
+        return lev, seen
+
+    def rec(nodes: set):
+        # iterative over connected components / recursion depth O(log n)
+        if len(nodes) <= 2:
+            order.extend(sorted(nodes, key=lambda l: fg.variables[l].index))
+            return
+        start = min(nodes, key=lambda l: fg.variables[l].index)
+        far, comp = bfs_far(nodes, start)
+        if len(comp) < len(nodes):           # disconnected: handle components separately
+            rec(comp)
+            rec(nodes - comp)
+            return
+        lev, _ = levels(nodes, far)
+        if len(lev) < 3:
+            order.extend(sorted(nodes, key=lambda l: fg.variables[l].index))
+            return
+        half, acc, cut = len(nodes) / 2, 0, len(lev) // 2
+        for i, l in enumerate(lev):
+            acc += len(l)
+            if acc >= half:
+                cut = min(max(i, 1), len(lev) - 2)
+                break
+        sep = set(lev[cut])
+        left = set().union(*lev[:cut])
+        right = set().union(*lev[cut + 1:])
+        rec(left)
+        rec(right)
+        order.extend(sorted(sep, key=lambda l: fg.variables[l].index))
+
+    rec(set(fg.variables))
+    return order
+
+
+# ------------------------------------------------------------------ Bayes tree
+@dataclass
+class TreeClique:
+    id: int
+    frontals: List[str]
+    separators: List[str]
+    parent: Optional[int] = None
+    children: List[int] = field(default_factory=list)
+    potentials: List[str] = field(default_factory=list)      # factor labels (up solve)
+    inmsgIDs: List[str] = field(default_factory=list)        # separator vars of the children (with repeats)
+    directFrtlMsgIDs: List[str] = field(default_factory=list)
+    msgskipIDs: List[str] = field(default_factory=list)
+    itervarIDs: List[str] = field(default_factory=list)
+    directPriorMsgIDs: List[str] = field(default_factory=list)
+
+    @property
+    def allvars(self):
+        return self.frontals + self.separators
+
+
+@dataclass
+class BayesTree:
+    cliques: List[TreeClique]
+    frontal_of: Dict[str, int]
+    eliminationOrder: List[str]
+
+    @property
+    def roots(self):
+        return [c.id for c in self.cliques if c.parent is None]
+
+    def depth(self):
+        d = {}
+        for c in self.cliques:   # parents are created before children (reverse elimination order)
+            d[c.id] = 0 if c.parent is None else d[c.parent] + 1
+        return d
+
+
+def buildBayesNet(fg: G.FactorGraph, order: List[str]) -> Dict[str, List[str]]:
+    """Symbolic elimination -> conditional p(v | separator)  (BayesNet.jl:139-187)."""
+    pos = {v: i for i, v in enumerate(order)}
+    # active "factors" as variable sets; chain-rule marginals are added as eliminated vars go
+    live = [set(f.variables) for f in fg.factors.values()]
+    sep: Dict[str, List[str]] = {}
+    for v in order:
+        touching = [s for s in live if v in s]
+        Si: List[str] = []
+        for s in touching:
+            for w in sorted(s, key=lambda x: fg.variables[x].index):
+                if w != v and w not in Si:
+                    Si.append(w)
+        live = [s for s in live if v not in s]
+        sep[v] = Si if v != order[-1] else []
+        if Si:
+            live.append(set(Si))
+    del pos
+    return sep
+
+
+def buildTree(fg: G.FactorGraph, order: List[str]) -> BayesTree:
+    """buildTree!/newPotential (JunctionTreeUtils.jl:435-496; Kaess et al. Bayes tree Alg. 2)."""
+    sep = buildBayesNet(fg, order)
+    pos = {v: i for i, v in enumerate(order)}
+    cliques: List[TreeClique] = []
+    frontal_of: Dict[str, int] = {}
+    for var in reversed(order):
+        Sj = sep[var]
+        if not Sj:
+            c = TreeClique(len(cliques), [var], [])
+            cliques.append(c)
+            frontal_of[var] = c.id
+            continue
+        first = min(Sj, key=lambda s: pos[s])          # first eliminated separator variable
+        cp = cliques[frontal_of[first]]
+        if sorted(cp.frontals + cp.separators) == sorted(Sj):
+            cp.frontals.append(var)                    # appendClique!: add as a frontal
+            frontal_of[var] = cp.id
+        else:
+            c = TreeClique(len(cliques), [var], list(Sj), parent=cp.id)   # newChildClique!
+            cp.children.append(c.id)
+            cliques.append(c)
+            frontal_of[var] = c.id
+    tree = BayesTree(cliques, frontal_of, list(order))
+    _buildCliquePotentials(fg, tree)
+    return tree
+
+
+def _postorder(tree: BayesTree) -> List[int]:
+    out, stack = [], [(r, False) for r in reversed(tree.roots)]
+    while stack:
+        cid, done = stack.pop()
+        if done:
+            out.append(cid)
+            continue
+        stack.append((cid, True))
+        for ch in reversed(tree.cliques[cid].children):
+            stack.append((ch, False))
+    return out
+
+
+def _buildCliquePotentials(fg: G.FactorGraph, tree: BayesTree):
+    """buildCliquePotentials (post-order): setCliqPotentials! + assoc matrices + setCliqMCIDs!."""
+    used = set()
+    for cid in _postorder(tree):
+        c = tree.cliques[cid]
+        allv = set(c.allvars)
+        pots = []
+        for f in fg.factors.values():                 # getFactorsAmongVariablesOnly(unused) ∩ frontal factors
+            if f.label in used:
+                continue
+            if set(f.variables) <= allv and any(v in c.frontals for v in f.variables):
+                pots.append(f.label)
+        c.potentials = pots
+        used.update(pots)
+        c.inmsgIDs = [s for ch in c.children for s in tree.cliques[ch].separators]   # collectSeparators
+        _setCliqMCIDs(fg, c)
+
+
+def _setCliqMCIDs(fg: G.FactorGraph, c: TreeClique):
+    """JunctionTreeUtils.jl:1352-1523."""
+    cols = c.allvars
+    nf = len(c.frontals)
+    assoc = np.zeros((len(c.potentials), len(cols)), dtype=int)
+    for i, fl in enumerate(c.potentials):
+        for v in fg.factors[fl].variables:
+            if v in cols:
+                assoc[i, cols.index(v)] = 1
+    msg = np.zeros((len(c.inmsgIDs), len(cols)), dtype=int)
+    for i, v in enumerate(c.inmsgIDs):
+        if v in cols:
+            msg[i, cols.index(v)] = 1
+    mat = np.vstack([assoc, msg]) if len(cols) else np.zeros((0, 0), dtype=int)
+    colsum = mat.sum(axis=0) if mat.size else np.zeros(len(cols), dtype=int)
+    # directPriorMsgIDs :1368-1382: columns whose every row is a singleton row
+    sing_rows = mat.sum(axis=1) == 1 if mat.size else np.zeros(0, dtype=bool)
+    sums_sing = mat[sing_rows].sum(axis=0) if mat.size else colsum
+    c.directPriorMsgIDs = [cols[j] for j in range(len(cols)) if sums_sing[j] - colsum[j] == 0]
+    # directAssignmentIDs :1394-1409
+    asum, msum = assoc.sum(axis=0), msg.sum(axis=0)
+    directvars = [cols[j] for j in range(len(cols)) if colsum[j] == 1 and asum[j] == 1]
+    # mcmcIterationIDs :1411-1431
+    multi = [cols[j] for j in range(len(cols)) if colsum[j] > 1]
+    alliter = [v for v in _union(directvars, multi) if v not in c.directPriorMsgIDs]
+    # ordering :1448-1484: non-singleton vars first (ascending factor count), then singleton vars
+    upmsg = [cols[j] for j in range(len(cols)) if msum[j] >= 1]
+    prior_rows = assoc.sum(axis=1) == 1
+    prior_vars = [cols[j] for j in range(len(cols)) if assoc[prior_rows][:, j].sum() > 0] if len(c.potentials) else []
+    # NB getCliqVarIdsPriors(cliq, allids, partials=true) masks prior rows with `partialpotential`, i.e.
+    # only *partial* priors count as singletons there; full priors are not in `allsings`.
+    partial_prior_vars = []
+    for i, fl in enumerate(c.potentials):
+        if prior_rows[i] and isinstance(fg.factors[fl].fnc, G.PartialPrior):
+            partial_prior_vars += [cols[j] for j in range(len(cols)) if assoc[i, j]]
+    del prior_vars
+    allsings = _union(upmsg, partial_prior_vars)
+    singl = [v for v in alliter if v in allsings]
+    nons = [v for v in alliter if v not in singl]
+    key = lambda v: colsum[cols.index(v)]  # noqa: E731
+    c.itervarIDs = sorted(nons, key=key) + sorted(singl, key=key)     # sortperm is stable
+    # skipThroughMsgsIDs :1343-1355 (separator columns with exactly one row, and it is a message)
+    c.msgskipIDs = [cols[j] for j in range(nf, len(cols)) if colsum[j] == 1 and msum[j] == 1]
+    # directFrtlMsgIDs :1384-1392
+    c.directFrtlMsgIDs = [cols[j] for j in range(nf) if colsum[j] == 1 and msum[j] == 1]
+
+
+def _union(a, b):
+    out = list(a)
+    for x in b:
+        if x not in out:
+            out.append(x)
+    return out
+
+
+# ------------------------------------------------------------------ lowering to a wave schedule
+@dataclass
+class SolvePlan:
+    tables: CP.Tables
+    frozen: dict
+    props: list                       # prop op spec dicts
+    sched: list                       # (kind, a, b) in program order
+    wave_off: List[int]
+    sched_waved: list                 # (kind, a, b) sorted by wave
+    var_slot: Dict[str, int]          # global (main-graph) slot of each variable
+    n_conv: int
+    n_prod: int
+    n_msgs: int
+    up_last_wave: int = 0             # waves [0, up_last_wave) cover init copies + the up pass
+    op_clique: Optional[List[int]] = None    # clique id of every op of `sched_waved`
+    op_wave: Optional[List[int]] = None      # wave of every op of `sched_waved`
+    op_reads: Optional[List[List[int]]] = None   # slots read by every op of `sched_waved`
+    op_writes: Optional[List[List[int]]] = None
+    slot_clique: Optional[Dict[int, int]] = None  # clique-local slot -> clique id (main-graph slots absent)
+
+
+def _levelize(ops, reads, writes):
+    """wave(op) = 1 + max wave of earlier ops it conflicts with (RAW / WAR / WAW on slots)."""
+    last_w: Dict[int, int] = {}
+    last_r: Dict[int, int] = {}
+    waves = []
+    for i in range(len(ops)):
+        w = 0
+        for s in reads[i]:
+            if s in last_w:
+                w = max(w, last_w[s] + 1)
+        for s in writes[i]:
+            if s in last_w:
+                w = max(w, last_w[s] + 1)
+            if s in last_r:
+                w = max(w, last_r[s] + 1)
+        waves.append(w)
+        for s in reads[i]:
+            last_r[s] = max(last_r.get(s, -1), w)
+        for s in writes[i]:
+            last_w[s] = w
+    return waves
+
+
+def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, downsolve: bool = True,
+                  gibbsIters: Optional[int] = None, downIters: int = 3) -> SolvePlan:
+    """Lower one solveTree! (up + down pass, useMsgLikelihoods=false) to slots, props and waves."""
+    sp = fg.solverParams
+    N = N or sp.N
+    iters = gibbsIters or sp.gibbsIters
+    T = CP.Tables()
+    # global slots: the main graph's variables (VariableNodeData)
+    var_slot = {l: T.add_slot(v.vartype, max(N, v.val.shape[0], 1)) for l, v in fg.variables.items()}
+    # clique-local copies (buildCliqSubgraph! deep-copies the clique's variables, CSM step 0b)
+    cslot: Dict[tuple, int] = {}
+    for c in tree.cliques:
+        for v in c.allvars:
+            cslot[(c.id, v)] = T.add_slot(fg.variables[v].vartype, max(N, fg.variables[v].val.shape[0], 1))
+
+    props, sched, reads, writes, opc = [], [], [], [], []
+    nconv = [0]
+    cur = [-1]     # clique whose ops are being emitted
+
+    def add_copy(a, b):
+        sched.append((A.S_COPY, a, b))
+        reads.append([a])
+        writes.append([b])
+        opc.append(cur[0])
+
+    def fac_instance(f: G.DFGFactor, slot_of):
+        return T.add_factor(f.fnc, [slot_of(v) for v in f.variables], f.multihypo, f.nullhypo, f.inflation)
+
+    def add_prop(target_label, target_slot, fac_list, rd_slots):
+        """fac_list: [(factor_table_idx, sfidx, is_multihypo)]"""
+        spec = dict(target_slot=target_slot, out_slot=target_slot, factors=[(fi, sf) for fi, sf, _ in fac_list],
+                    N=N, call_id=16 * len(props), any_multihypo=int(any(m for _, _, m in fac_list)))
+        props.append(spec)
+        sched.append((A.S_PROPAGATE, len(props) - 1, 0))
+        reads.append(sorted(set(rd_slots) | {target_slot}))
+        writes.append([target_slot])
+        opc.append(cur[0])
+        nconv[0] += len(fac_list)
+
+    # ---- step 0: clique sub-graphs start from the main graph's (graph-init) beliefs
+    for c in tree.cliques:
+        cur[0] = c.id
+        for v in c.allvars:
+            add_copy(var_slot[v], cslot[(c.id, v)])
+
+    post = _postorder(tree)
+    n_msgs = 0
+    # ---- up pass (children before parents)
+    for cid in post:
+        c = tree.cliques[cid]
+        cur[0] = cid
+        slot_of = lambda v, cid=cid: cslot[(cid, v)]  # noqa: E731
+        # factors of the clique sub-graph: potentials + MsgPrior per child up-message belief
+        inst = []   # (variables, table idx, multihypo?, read slots)
+        for fl in c.potentials:
+            f = fg.factors[fl]
+            inst.append((f.variables, fac_instance(f, slot_of), G.isMultihypo(f), [slot_of(v) for v in f.variables]))
+        for ch in c.children:
+            for s in tree.cliques[ch].separators:           # addMsgFactors! (TreeMessageUtils.jl:566-575)
+                if s in c.allvars:
+                    src = cslot[(ch, s)]                     # the child's updated separator belief
+                    mp = G.MsgPrior(G.SlotRef(src, fg.variables[s].vartype.dim))
+                    inst.append(([s], T.add_factor(mp, [slot_of(s)], None, 0.0, sp.inflation), False,
+                                 [slot_of(s), src]))
+                    n_msgs += 1
+
+        def propagate(v):
+            fl, rd = [], []
+            for variables, fi, ismh, rds in inst:
+                if v in variables:
+                    fl.append((fi, variables.index(v) + 1, ismh))
+                    rd += rds
+            if fl:
+                add_prop(v, slot_of(v), fl[:A.IIF_MAX_FACTORS], rd)
+
+        def fmcmc(lbls, mciter):                              # SolveTree.jl:89-142
+            if len(lbls) == 1:
+                mciter = 1
+            for _ in range(mciter):
+                for v in lbls:
+                    propagate(v)
+
+        # upGibbsCliqueDensity (SolveTree.jl:193-235)
+        fmcmc(c.directFrtlMsgIDs, 1)
+        if c.msgskipIDs:
+            fmcmc(c.msgskipIDs, 1)
+        if c.itervarIDs:
+            fmcmc(c.itervarIDs, iters)
+        if c.directPriorMsgIDs:
+            fmcmc([v for v in c.directPriorMsgIDs if v not in c.msgskipIDs], 1)
+    n_up_ops = len(sched)
+
+    # ---- down pass (parents before children); the root keeps its up-solve result
+    if downsolve:
+        for cid in reversed(post):
+            c = tree.cliques[cid]
+            if c.parent is None:
+                continue
+            cur[0] = cid
+            p = c.parent
+            # updateSubFgFromDownMsgs!: separators adopt the parent's down-message values
+            for s in c.separators:
+                add_copy(cslot[(p, s)], cslot[(cid, s)])
+                n_msgs += 1
+
+            # addDownVariableFactors!: every factor touching a frontal, with outside variables read
+            # from the main graph (their graph-init beliefs, see DESIGN.md "down pass")
+            def slot_dn(v, cid=cid, c=c):
+                return cslot[(cid, v)] if v in c.allvars else var_slot[v]
+
+            inst = []
+            for f in fg.factors.values():
+                if any(v in c.frontals for v in f.variables):
+                    inst.append((f.variables, fac_instance(f, slot_dn), G.isMultihypo(f),
+                                 [slot_dn(v) for v in f.variables]))
+
+            def local_product(v):
+                fl, rd = [], []
+                for variables, fi, ismh, rds in inst:
+                    if v in variables:
+                        fl.append((fi, variables.index(v) + 1, ismh))
+                        rd += rds
+                if fl:
+                    add_prop(v, cslot[(cid, v)], fl[:A.IIF_MAX_FACTORS], rd)
+
+            # determineCliqVariableDownSequence: frontals sharing a factor iterate MCIters times
+            iterF = []
+            for variables, _, _, _ in inst:
+                fr = [v for v in variables if v in c.frontals]
+                if len(fr) > 1:
+                    iterF = _union(iterF, fr)
+            iterF = [v for v in c.frontals if v in iterF]
+            for v in c.frontals:
+                if v not in iterF:
+                    local_product(v)
+            for _ in range(downIters):
+                for v in iterF:
+                    local_product(v)
+    # ---- step 5: updateFromSubgraph — frontal beliefs go back to the main graph
+    for c in tree.cliques:
+        cur[0] = c.id
+        for v in c.frontals:
+            add_copy(cslot[(c.id, v)], var_slot[v])
+
+    waves = _levelize(sched, reads, writes)
+    nw = max(waves) + 1 if waves else 0
+    order = sorted(range(len(sched)), key=lambda i: (waves[i], i))
+    sched_waved = [sched[i] for i in order]
+    wave_off = [0] * (nw + 1)
+    for i in order:
+        wave_off[waves[i] + 1] += 1
+    for w in range(nw):
+        wave_off[w + 1] += wave_off[w]
+    up_last = max(waves[:n_up_ops]) + 1 if n_up_ops else 0
+    frozen = T.freeze()
+    return SolvePlan(T, frozen, props, sched, wave_off, sched_waved, var_slot, nconv[0], len(props), n_msgs,
+                     up_last, [opc[i] for i in order], [waves[i] for i in order], [reads[i] for i in order],
+                     [writes[i] for i in order], {s: cid for (cid, _), s in cslot.items()})

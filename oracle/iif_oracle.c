@@ -537,6 +537,7 @@ int32_t iifo_conv(const iifo_graph* g, const iif_conv_op* op, const double* meas
   uint64_t seed = g->sp.seed;
   uint32_t call = (uint32_t)op->call_id;
   int nnan = 0;
+#pragma omp atomic
   g_conv_count++;
 
   /* _beforeSolveCCW! (CalcFactor.jl:519-617): dest = deepcopy(X_sf) resized to N, new slots =
@@ -926,22 +927,34 @@ int32_t iifo_schedule_run(iifo_graph* g, int32_t nwaves, const int32_t* wave_off
   if (first_wave < 0) first_wave = 0;
   if (last_wave > nwaves) last_wave = nwaves;
   for (int w = first_wave; w < last_wave; ++w) {
+    /* ops inside a wave are mutually independent (distinct destination slots, no op reads a slot
+     * another op of the wave writes), so the multithreaded CPU baseline may run them concurrently —
+     * the same clique/factor-level parallelism solveTree!(; multithread=true) exposes. */
+    int32_t werr = IIF_OK;
+#pragma omp parallel for schedule(dynamic, 1)
     for (int k = wave_off[w]; k < wave_off[w + 1]; ++k) {
       const iif_sched_op* o = &ops[k];
+      int32_t st = IIF_OK;
       if (o->kind == IIF_S_PROPAGATE) {
-        int32_t st = iifo_propagate(g, &props[o->a]);
-        if (st != IIF_OK) return st;
+        st = iifo_propagate(g, &props[o->a]);
       } else if (o->kind == IIF_S_COPY) {
         const iif_slot_desc* A = &g->slots[o->a];
         const iif_slot_desc* B = &g->slots[o->b];
-        if (A->dim != B->dim || B->cap < g->npts[o->a]) return IIF_ERR_ARG;
-        memcpy(g->pts + B->pts_off, g->pts + A->pts_off, sizeof(double) * (size_t)g->npts[o->a] * A->dim);
-        memcpy(g->bw + o->b * IIF_MAX_DIM, g->bw + o->a * IIF_MAX_DIM, sizeof(double) * IIF_MAX_DIM);
-        memcpy(g->ipc + o->b * IIF_MAX_DIM, g->ipc + o->a * IIF_MAX_DIM, sizeof(double) * IIF_MAX_DIM);
-        g->npts[o->b] = g->npts[o->a];
-        g->flags[o->b] = g->flags[o->a];
-      } else return IIF_ERR_ARG;
+        if (A->dim != B->dim || B->cap < g->npts[o->a]) st = IIF_ERR_ARG;
+        else {
+          memcpy(g->pts + B->pts_off, g->pts + A->pts_off, sizeof(double) * (size_t)g->npts[o->a] * A->dim);
+          memcpy(g->bw + o->b * IIF_MAX_DIM, g->bw + o->a * IIF_MAX_DIM, sizeof(double) * IIF_MAX_DIM);
+          memcpy(g->ipc + o->b * IIF_MAX_DIM, g->ipc + o->a * IIF_MAX_DIM, sizeof(double) * IIF_MAX_DIM);
+          g->npts[o->b] = g->npts[o->a];
+          g->flags[o->b] = g->flags[o->a];
+        }
+      } else st = IIF_ERR_ARG;
+      if (st != IIF_OK) {
+#pragma omp critical
+        werr = st;
+      }
     }
+    if (werr != IIF_OK) return werr;
   }
   return IIF_OK;
 }
