@@ -66,7 +66,7 @@ __device__ __forceinline__ int categorical(const double* p, int np, double u) { 
 }
 
 // _prepareHypoRecipe! structure (scalar, thread 0) — ExplicitDiscreteMarginalizations.jl:142-289
-__device__ void build_recipe(HypoRecipe& R, const iif_factor_desc& f, int sfidx, const int32_t* isinit,
+__device__ __noinline__ void build_recipe(HypoRecipe& R, const iif_factor_desc& f, int sfidx, const int32_t* isinit,
                              double nullhypo) {
   const int lenXi = f.arity;
   R.status = IIF_OK;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void sample_simple(int kind, int dim, const double* p
   }
 }
 
-__device__ int sample_measurement(const DeviceGraph& g, const iif_factor_desc& f, uint32_t call, int n,
+__device__ __noinline__ int sample_measurement(const DeviceGraph& g, const iif_factor_desc& f, uint32_t call, int n,
                                   double* z) {
   const iif_dist_desc D = g.dists[f.dist];
   const double* prm = g.dparams + D.poff;
@@ -232,7 +232,7 @@ __device__ void block_default_mean(const double* pts, int n, int d, int32_t cm, 
 }
 
 // calcStdBasicSpread — VariableStatistics.jl:22-36
-__device__ double block_std_basic_spread(const double* pts, int n, int d, int32_t cm, double* mu_s, double* red,
+__device__ __noinline__ double block_std_basic_spread(const double* pts, int n, int d, int32_t cm, double* mu_s, double* red,
                                          int& parity) {
   if (n < 2) return 1.0;
   block_geodesic_mean(pts, n, d, cm, mu_s, red, parity);
@@ -248,7 +248,7 @@ __device__ double block_std_basic_spread(const double* pts, int n, int d, int32_
 }
 
 // calcVariableDistanceExpectedFractional — EvalFactor.jl:40-92
-__device__ double block_spread_distance(const DeviceGraph& g, const iif_factor_desc& f, int sfidx,
+__device__ __noinline__ double block_spread_distance(const DeviceGraph& g, const iif_factor_desc& f, int sfidx,
                                         const double* dest, int N, const HypoRecipe& R, double kappa,
                                         double* mu_s, double* red, int& parity) {
   const iif_slot_desc Ssf = g.slots[f.slot[sfidx - 1]];
@@ -305,6 +305,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
                 const TreeStruct* __restrict__ trees) {
   __shared__ double dest[IIF_MAX_POINTS * IIF_MAX_DIM];
   __shared__ double xa[IIF_MAX_POINTS], xb[IIF_MAX_POINTS];
+  __shared__ double scr[IIF_LOO_SCRATCH];
   __shared__ double red[IIF_RED_DOUBLES];
   __shared__ double mu_s[IIF_MAX_DIM];
   __shared__ HypoRecipe R;
@@ -476,7 +477,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   }
   // approxConvBelief: manikde!(M, pts; partial) — ApproxConv.jl:31-42
   double bw[IIF_MAX_DIM];
-  block_kde_bandwidth(dest, N, d, cm, trees[N], xa, xb, red, parity, bw);
+  block_kde_bandwidth(dest, N, d, cm, trees[N], xa, xb, scr, red, parity, bw);
   if (n == 0) {
     for (int c = 0; c < IIF_MAX_DIM; ++c) {
       t.out_bw[c] = c < d ? (((pmask >> c) & 1) ? bw[c] : 1.0) : 0.0;

@@ -153,80 +153,174 @@ __device__ __forceinline__ double block_min1(double x, double* red, int& parity)
 }
 
 // ------------------------------------------------------------------------------------------
+// exp(x) for x <= 0 in FP64 (the only use on this path: Gaussian kernel weights).  Cody-Waite
+// range reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor/Horner (truncation 4e-18) with
+// the coefficients taken straight from the constant bank (no 64-bit immediates to materialise),
+// two-step power-of-two scaling so results down to the denormal range stay correct.
+// ------------------------------------------------------------------------------------------
+__constant__ double IIF_EXPC[16] = {
+    1.6059043836821613e-10, 2.08767569878681e-09,  2.505210838544172e-08,  2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05,  1.984126984126984e-04,  1.388888888888889e-03,
+    8.333333333333333e-03,  4.1666666666666664e-02, 1.6666666666666666e-01, 0.5,
+    1.4426950408889634074,  -6.93147180369123816490e-01, -1.90821492927058770002e-10, 6755399441055744.0};
+
+__device__ __forceinline__ double exp_neg(double x) {
+  double t = fma(x, IIF_EXPC[12], IIF_EXPC[15]);
+  const int k = __double2loint(t);
+  t -= IIF_EXPC[15];
+  double r = fma(t, IIF_EXPC[13], x);
+  r = fma(t, IIF_EXPC[14], r);
+  double p = IIF_EXPC[0];
+#pragma unroll
+  for (int c = 1; c < 12; ++c) p = fma(p, r, IIF_EXPC[c]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int k1 = k >> 1, k2 = k - k1;
+  const double s1 = __hiloint2double((k1 + 1023) << 20, 0);
+  const double s2 = __hiloint2double((k2 + 1023) << 20, 0);
+  const double res = (p * s1) * s2;
+  return (x < -746.0) ? 0.0 : res;
+}
+
+// ------------------------------------------------------------------------------------------
 // a14: KDE bandwidth by leave-one-out likelihood cross-validation (AMP.manikde! ->
 // getKDEManifoldBandwidths -> KDE kde!(x) "lcv"; call sites ApproxConv.jl:36-42,
 // GraphProductOperations.jl:53).  Exact O(N^2) evaluation (KDE.setForceEvalDirect!(true),
 // src/IncrementalInference.jl:104).
 //
-// Objective -1/N sum_i log( 1/(N-1) sum_{j!=i} N(x_i - x_j; 0, h^2) ): one warp per row i,
-// lanes stride the columns j, warp-shuffle reduction of the kernel sums, one log per row
-// (lane k keeps the sum of the warp's k-th row), block reduction of the log terms.
+// Objective -1/N sum_i log( 1/(N-1) sum_{j!=i} N(x_i - x_j; 0, h^2) ).  The kernel matrix is
+// symmetric with a zero diagonal, so every unordered pair is evaluated ONCE: row i (one warp per
+// row) covers the circulant half j = i+1 .. i+floor(N/2) (mod N); the lanes stride those columns,
+// the row part is reduced with warp shuffles and the mirrored column part accumulates in the
+// warp's private shared-memory strip (distinct j per lane: no atomics).  Two rows are in flight
+// per warp so that two independent exp chains hide the FP64 latency.  scr layout:
+// [IIF_WARPS][N] column strips, [N] row sums, [IIF_WARPS] dummy cells for inactive lanes.
 // ------------------------------------------------------------------------------------------
-__device__ double loo_nll(const double* __restrict__ x, int N, bool circ, double h, double* red, int& parity) {
+#define IIF_LOO_SCRATCH ((IIF_WARPS + 1) * IIF_MAX_POINTS + IIF_WARPS)
+#define IIF_LOO_SCRATCH_N(N) ((IIF_WARPS + 1) * (N) + IIF_WARPS)
+
+template <bool CIRC>
+__device__ __forceinline__ void loo_rows(const double* __restrict__ x, int N, double ninv2h2, double* col,
+                                         double* rowsum, double* dummy) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = (N - 1) >> 1, hN = N >> 1;
+  const bool even = (N & 1) == 0;
+  const int nq2 = (half + 1 + 63) >> 6;  // uniform trip count, two 32-column chunks per trip
+  for (int i0 = warp; i0 < N; i0 += 2 * IIF_WARPS) {
+    const int i1 = i0 + IIF_WARPS;
+    const bool has1 = i1 < N;
+    const double x0 = x[i0], x1 = has1 ? x[i1] : 0.0;
+    const int nk0 = half + ((even && i0 < hN) ? 1 : 0);
+    const int nk1 = has1 ? half + ((even && i1 < hN) ? 1 : 0) : 0;
+    double s0 = 0.0, s1 = 0.0;
+    for (int q = 0; q < nq2; ++q) {
+      // four independent exp chains per trip (2 rows x 2 chunks): branch-free so that the FP64
+      // dependency chains interleave; inactive lanes add 0 to a column nobody else touches
+      const int ka = 1 + lane + 64 * q, kb = ka + 32;
+      const bool a0 = ka <= nk0, b0 = kb <= nk0, a1 = ka <= nk1, b1 = kb <= nk1;
+      int ja0 = i0 + ka, jb0 = i0 + kb, ja1 = i1 + ka, jb1 = i1 + kb;
+      ja0 -= (ja0 >= N) ? N : 0;
+      jb0 -= (jb0 >= N) ? N : 0;
+      ja1 -= (ja1 >= N) ? N : 0;
+      jb1 -= (jb1 >= N) ? N : 0;
+      ja0 = a0 ? ja0 : i0;  // inactive lanes: any valid x index, their weight is discarded
+      jb0 = b0 ? jb0 : i0;
+      ja1 = a1 ? ja1 : i0;
+      jb1 = b1 ? jb1 : i0;
+      double* pa0 = a0 ? col + ja0 : dummy;
+      double* pb0 = b0 ? col + jb0 : dummy;
+      double* pa1 = a1 ? col + ja1 : dummy;
+      double* pb1 = b1 ? col + jb1 : dummy;
+      const double da0 = mdiff(x0, x[ja0], CIRC), db0 = mdiff(x0, x[jb0], CIRC);
+      const double da1 = mdiff(x1, x[ja1], CIRC), db1 = mdiff(x1, x[jb1], CIRC);
+      double ea0 = exp_neg(da0 * da0 * ninv2h2), eb0 = exp_neg(db0 * db0 * ninv2h2);
+      double ea1 = exp_neg(da1 * da1 * ninv2h2), eb1 = exp_neg(db1 * db1 * ninv2h2);
+      ea0 = a0 ? ea0 : 0.0;
+      eb0 = b0 ? eb0 : 0.0;
+      ea1 = a1 ? ea1 : 0.0;
+      eb1 = b1 ? eb1 : 0.0;
+      s0 += ea0 + eb0;
+      s1 += ea1 + eb1;
+      *pa0 += ea0;       // row i0: the two chunks hit distinct columns
+      *pb0 += eb0;
+      __syncwarp();      // row i1 may hit a column row i0 just updated from another lane
+      *pa1 += ea1;
+      *pb1 += eb1;
+      __syncwarp();
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+      rowsum[i0] = s0;
+      if (has1) rowsum[i1] = s1;
+    }
+  }
+}
+
+__device__ __noinline__ double loo_nll(const double* __restrict__ x, int N, int circ, double h, double* scr,
+                                       double* red, int* parity_io) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double ninv2h2 = -1.0 / (2.0 * h * h);
   const double lognorm = log((double)(N - 1) * sqrt(IIF_TWO_PI) * h);
+  double* col = scr + warp * N;
+  double* rowsum = scr + IIF_WARPS * N;
+  for (int j = lane; j < N; j += 32) col[j] = 0.0;
+  __syncwarp();
+  double* dummy = scr + (IIF_WARPS + 1) * N + warp;
+  if (circ) loo_rows<true>(x, N, ninv2h2, col, rowsum, dummy);
+  else loo_rows<false>(x, N, ninv2h2, col, rowsum, dummy);
+  __syncthreads();
   double acc = 0.0;
-  for (int i0 = warp; i0 < N; i0 += IIF_WARPS * 32) {
-    double mine = 1.0;  // log(1) = 0 for lanes without a row
-    int k = 0;
-    for (int i = i0; i < N && k < 32; i += IIF_WARPS, ++k) {
-      const double xi = x[i];
-      double s = 0.0;
-      for (int j = lane; j < N; j += 32) {
-        double dl = mdiff(xi, x[j], circ);
-        double e = exp(dl * dl * ninv2h2);
-        s += (j == i) ? 0.0 : e;
-      }
-      s = warp_sum(s);
-      if (lane == k) mine = s;
-    }
-    if (lane < k) acc += log(mine) - lognorm;
+  for (int i = threadIdx.x; i < N; i += IIF_THREADS) {
+    double t = rowsum[i];
+#pragma unroll
+    for (int w = 0; w < IIF_WARPS; ++w) t += scr[w * N + i];
+    acc += log(t) - lognorm;
   }
-  double tot = block_sum1(acc, red, parity);
+  int parity = *parity_io;
+  double tot = block_sum1(acc, red, parity);  // its barrier also protects scr for the next call
+  *parity_io = parity;
   return -tot / (double)N;
 }
 
 // Numerical-Recipes golden section as used by KDE `golden(npd, nLOO_LL, ax, bx, cx, tol)`;
 // the search variable scales the base bandwidth h0.  Uniform control flow across the CTA.
 __device__ double golden_nr(const double* x, int N, double h0, double ax, double bx, double cx, double tol,
-                            double* red, int& parity) {
+                            double* scr, double* red, int& parity) {
   const double C = (3.0 - sqrt(5.0)) / 2.0, R = 1.0 - C;
   double x0 = ax, x3 = cx, x1, x2;
   if (fabs(cx - bx) > fabs(bx - ax)) { x1 = bx; x2 = bx + C * (cx - bx); }
   else { x2 = bx; x1 = bx - C * (bx - ax); }
-  double f1 = loo_nll(x, N, false, x1 * h0, red, parity);
-  double f2 = loo_nll(x, N, false, x2 * h0, red, parity);
+  double f1 = loo_nll(x, N, 0, x1 * h0, scr, red, &parity);
+  double f2 = loo_nll(x, N, 0, x2 * h0, scr, red, &parity);
   for (int it = 0; it < 200 && fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2)); ++it) {
-    if (f2 < f1) {
-      x0 = x1; x1 = x2; x2 = R * x1 + C * x3;
-      f1 = f2; f2 = loo_nll(x, N, false, x2 * h0, red, parity);
-    } else {
-      x3 = x2; x2 = x1; x1 = R * x2 + C * x0;
-      f2 = f1; f1 = loo_nll(x, N, false, x1 * h0, red, parity);
-    }
+    const bool right = f2 < f1;
+    double xn;
+    if (right) { x0 = x1; x1 = x2; x2 = R * x1 + C * x3; f1 = f2; xn = x2; }
+    else { x3 = x2; x2 = x1; x1 = R * x2 + C * x0; f2 = f1; xn = x1; }
+    const double fn = loo_nll(x, N, 0, xn * h0, scr, red, &parity);
+    if (right) f2 = fn; else f1 = fn;
   }
   return (f1 < f2) ? x1 : x2;
 }
 
 // Optim.jl GoldenSection on [lo, hi] as used by AMP kde!_CircularNaiveCV
-__device__ double golden_optim(const double* x, int N, double lo, double hi, double rel_tol, double* red,
-                               int& parity) {
+__device__ double golden_optim(const double* x, int N, double lo, double hi, double rel_tol, double* scr,
+                               double* red, int& parity) {
   const double gr = 0.5 * (3.0 - sqrt(5.0));
   const double abs_tol = 2.220446049250313e-16;
   double xm = lo + gr * (hi - lo);
-  double fm = loo_nll(x, N, true, xm, red, parity);
+  double fm = loo_nll(x, N, 1, xm, scr, red, &parity);
   for (int it = 0; it < 200; ++it) {
     double tolx = rel_tol * fabs(xm) + abs_tol;
     double mid = 0.5 * (hi + lo);
     if (fabs(xm - mid) <= 2 * tolx - 0.5 * (hi - lo)) break;
-    if (hi - xm > xm - lo) {
-      double xn = xm + gr * (hi - xm);
-      double fn = loo_nll(x, N, true, xn, red, parity);
+    const bool up = hi - xm > xm - lo;
+    const double xn = up ? xm + gr * (hi - xm) : xm - gr * (xm - lo);
+    const double fn = loo_nll(x, N, 1, xn, scr, red, &parity);
+    if (up) {
       if (fn < fm) { lo = xm; xm = xn; fm = fn; } else hi = xn;
     } else {
-      double xn = xm - gr * (xm - lo);
-      double fn = loo_nll(x, N, true, xn, red, parity);
       if (fn < fm) { hi = xm; xm = xn; fm = fn; } else lo = xn;
     }
   }
@@ -234,15 +328,16 @@ __device__ double golden_optim(const double* x, int N, double lo, double hi, dou
 }
 
 // Per-dimension bandwidth of the N x d points in `pts` (shared or global memory).
-// xa, xb: shared scratch of N doubles each.  Result bw[c] is returned to every thread.
+// xa, xb: shared scratch of N doubles each; scr: IIF_WARPS*N + N doubles.  Result bw[c] is returned
+// to every thread.
 __device__ void block_kde_bandwidth(const double* pts, int N, int d, int32_t circ_mask, const TreeStruct& T,
-                                    double* xa, double* xb, double* red, int& parity, double* bw) {
+                                    double* xa, double* xb, double* scr, double* red, int& parity, double* bw) {
   for (int c = 0; c < d; ++c) {
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += IIF_THREADS) xa[i] = pts[i * d + c];
     __syncthreads();
     if (is_circ(circ_mask, c)) {
-      bw[c] = golden_optim(xa, N, 1e-3, IIF_TWO_PI, 1e-3, red, parity);
+      bw[c] = golden_optim(xa, N, 1e-3, IIF_TWO_PI, 1e-3, scr, red, parity);
     } else {
       // rank sort (ties by index) -> xb ascending
       for (int i = threadIdx.x; i < N; i += IIF_THREADS) {
@@ -265,8 +360,8 @@ __device__ void block_kde_bandwidth(const double* pts, int N, int d, int32_t cir
       double minm = block_min1(m, red, parity);
       if (minm < 1e-6) minm = 1e-6;
       double h0 = 0.5 * (minm + maxm);
-      double a = golden_nr(xb, N, h0, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm), 1e-2, red,
-                           parity);
+      double a = golden_nr(xb, N, h0, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm), 1e-2, scr,
+                           red, parity);
       bw[c] = a * h0;
     }
   }

@@ -38,13 +38,14 @@ struct ProdSmem {
   double* xa;     // N
   double* xb;     // N
   double* red;    // IIF_RED_DOUBLES
+  double* scr;    // IIF_LOO_SCRATCH_N(N)  (leave-one-out scratch)
   double* bwk;    // F*IIF_MAX_DIM kernel bandwidths
   int16_t* perm;  // 2*F*N
 };
 
 __host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn) {
   size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + 2 * (size_t)N + IIF_RED_DOUBLES +
-               (size_t)F * IIF_MAX_DIM;
+               (size_t)F * IIF_MAX_DIM + (size_t)IIF_LOO_SCRATCH_N(N);
   size_t i16 = 2 * (size_t)F * N;
   return dbl * sizeof(double) + ((i16 * sizeof(int16_t) + 7) / 8) * 8;
 }
@@ -98,6 +99,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     sm.xa = p; p += N;
     sm.xb = p; p += N;
     sm.red = p; p += IIF_RED_DOUBLES;
+    sm.scr = p; p += (size_t)IIF_LOO_SCRATCH_N(N);
     sm.bwk = p; p += F * IIF_MAX_DIM;
     sm.perm = reinterpret_cast<int16_t*>(p);
   }
@@ -288,7 +290,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     }
     __syncthreads();
     // ---- 4. re-bandwidth of the posterior (getKDEManifoldBandwidths on the result)
-    block_kde_bandwidth(sm.post, N, d, cm, T, sm.xa, sm.xb, sm.red, parity, bw);
+    block_kde_bandwidth(sm.post, N, d, cm, T, sm.xa, sm.xb, sm.scr, sm.red, parity, bw);
     (void)covered;
   }
 
@@ -339,12 +341,13 @@ __global__ void __launch_bounds__(IIF_THREADS)
 iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restrict__ trees) {
   __shared__ double pts[IIF_MAX_POINTS * IIF_MAX_DIM];
   __shared__ double xa[IIF_MAX_POINTS], xb[IIF_MAX_POINTS];
+  __shared__ double scr[IIF_LOO_SCRATCH];
   __shared__ double red[IIF_RED_DOUBLES];
   const BwTask t = tasks[blockIdx.x];
   int parity = 0;
   for (int i = threadIdx.x; i < t.N * t.dim; i += IIF_THREADS) pts[i] = t.pts[i];
   __syncthreads();
   double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
-  block_kde_bandwidth(pts, t.N, t.dim, t.circ_mask, trees[t.N], xa, xb, red, parity, bw);
+  block_kde_bandwidth(pts, t.N, t.dim, t.circ_mask, trees[t.N], xa, xb, scr, red, parity, bw);
   if (threadIdx.x < IIF_MAX_DIM) t.out_bw[threadIdx.x] = threadIdx.x < t.dim ? bw[threadIdx.x] : 0.0;
 }
