@@ -40,12 +40,14 @@ struct ProdSmem {
   double* red;    // IIF_RED_DOUBLES
   double* scr;    // IIF_LOO_SCRATCH_N(N)  (leave-one-out scratch)
   double* bwk;    // F*IIF_MAX_DIM kernel bandwidths
+  double* wt;     // nn node weights (count / N), shared by all densities
+  double* minvar; // F*(L+1)*d smallest node variance per level
   int16_t* perm;  // 2*F*N
 };
 
-__host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn) {
+__host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn, int L) {
   size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + 2 * (size_t)N + IIF_RED_DOUBLES +
-               (size_t)F * IIF_MAX_DIM + (size_t)IIF_LOO_SCRATCH_N(N);
+               (size_t)F * IIF_MAX_DIM + (size_t)IIF_LOO_SCRATCH_N(N) + (size_t)nn + (size_t)F * (L + 1) * d;
   size_t i16 = 2 * (size_t)F * N;
   return dbl * sizeof(double) + ((i16 * sizeof(int16_t) + 7) / 8) * 8;
 }
@@ -101,6 +103,8 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     sm.red = p; p += IIF_RED_DOUBLES;
     sm.scr = p; p += (size_t)IIF_LOO_SCRATCH_N(N);
     sm.bwk = p; p += F * IIF_MAX_DIM;
+    sm.wt = p; p += nn;
+    sm.minvar = p; p += (size_t)F * (L + 1) * d;
     sm.perm = reinterpret_cast<int16_t*>(p);
   }
   const int32_t fullmask = (1 << d) - 1;
@@ -174,92 +178,149 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         sm.var[(size_t)it * d + c] = h * h + q / cnt;
       }
     }
+    for (int z = tid; z < nn; z += IIF_THREADS) sm.wt[z] = (double)(T.hi[z] - T.lo[z] + 1) / (double)N;
+    __syncthreads();
+    for (int it = tid; it < F * (L + 1) * d; it += IIF_THREADS) {
+      const int c = it % d, l = (it / d) % (L + 1), j = it / (d * (L + 1));
+      double mv = INFINITY;
+      for (int z = T.lev_off[l]; z < T.lev_off[l + 1]; ++z) mv = fmin(mv, sm.var[((size_t)j * nn + z) * d + c]);
+      sm.minvar[it] = mv;
+    }
     __syncthreads();
 
-    // ---- oldPoints for coordinates no proposal informs (GraphProductOperations.jl:37-45)
-    int32_t covered = 0;
-    for (int j = 0; j < F; ++j) covered |= masks[j];
-    // ---- 2./3. multiscale Gibbs: one warp per output sample
+    // ---- 2./3. multiscale Gibbs: G lanes per output sample (G = largest power of two <= threads/N).
+    // Every lane owns a contiguous block of the level's candidate nodes, accumulates its weights in
+    // chunks (kept in registers), a group scan locates the lane and chunk holding the inverse-CDF
+    // crossing and only that chunk is re-evaluated.  Weights are taken relative to an analytic lower
+    // bound of the exponent so a single pass suffices; the exact-minimum form (what the oracle
+    // computes) is the fallback when every weight underflows.
     const int niter = g.sp->gibbsNiter;
     const uint64_t seed = g.sp->seed;
     const uint32_t call = (uint32_t)t.call_id;
-    for (int s = warp; s < N; s += IIF_WARPS) {
+    int G = 1;
+    while (G < 32 && 2 * G * N <= IIF_THREADS) G <<= 1;
+    const int smp = tid / G, gl = tid % G;   // sample, lane within the group
+    const bool live = smp < N;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    // whole warps without a sample skip; partial groups never occur (G divides 32)
+    if (live) {
+      const int s = smp;
       int node[IIF_MAX_FACTORS];
       for (int j = 0; j < F; ++j) node[j] = 0;  // roots
       for (int l = 1; l <= L; ++l) {
-        const int z0 = T.lev_off[l], z1 = T.lev_off[l + 1], nz = z1 - z0;
+        const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
+        const bool leaf = (l == L);
         for (int j = 0; j < F; ++j) node[j] = z0 + T.child[node[j]];  // levelDown
+        const int B = (nz + G - 1) / G;
+        const int zb = gl * B, ze = min(zb + B, nz);
+        const int CH = max(8, (B + 15) >> 4);
         for (int it = 0; it < niter; ++it) {
           for (int j = 0; j < F; ++j) {  // sampleIndex(j)
-            double cmu[IIF_MAX_DIM] = {0, 0, 0, 0}, clam[IIF_MAX_DIM];
-            for (int c = 0; c < d; ++c)
-              clam[c] = ((masks[j] >> c) & 1)
-                            ? cond_gauss(F, sm.mean, sm.var, node, masks, j, nn, d, c, is_circ(cm, c), cmu[c])
-                            : 0.0;
-            const double* mj = sm.mean + (size_t)j * nn * d;
-            const double* vj = sm.var + (size_t)j * nn * d;
-            double pz[IIF_MAX_POINTS / 32];
-            double pmin = INFINITY;
-#pragma unroll
-            for (int q = 0; q < IIF_MAX_POINTS / 32; ++q) {
-              const int zz = lane + 32 * q;
-              double p = INFINITY;
-              if (zz < nz) {
-                p = 0;
-                for (int c = 0; c < d; ++c) {
-                  if (!(clam[c] > 0)) continue;
-                  double dl = mdiff(mj[(z0 + zz) * d + c], cmu[c], is_circ(cm, c));
-                  double v = vj[(z0 + zz) * d + c] + 1.0 / clam[c];
+            double cmu[IIF_MAX_DIM] = {0, 0, 0, 0}, cvar[IIF_MAX_DIM] = {0, 0, 0, 0};
+            bool has[IIF_MAX_DIM] = {false, false, false, false};
+            for (int c = 0; c < d; ++c) {
+              if (!((masks[j] >> c) & 1)) continue;
+              const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, j, nn, d, c, is_circ(cm, c), cmu[c]);
+              has[c] = lam > 0;
+              cvar[c] = has[c] ? 1.0 / lam : 0.0;
+            }
+            const double* mj = sm.mean + ((size_t)j * nn + z0) * d;
+            const double* vj = sm.var + ((size_t)j * nn + z0) * d;
+            const double* wj = sm.wt + z0;
+            // exponent p_z = sum_c dl^2 / v + log v ; bound: leaf level v is the same for every
+            // candidate (kernel variance), internal levels use the level's smallest node variance
+            double iv[IIF_MAX_DIM] = {0, 0, 0, 0};
+            double Lb = 0.0;
+            for (int c = 0; c < d; ++c) {
+              if (!has[c]) continue;
+              if (leaf) iv[c] = 1.0 / (vj[c] + cvar[c]);
+              else Lb += log(sm.minvar[((size_t)j * (L + 1) + l) * d + c] + cvar[c]);
+            }
+            auto expo = [&](int z) -> double {  // p_z - (leaf ? sum log v : 0)
+              double p = 0.0;
+              for (int c = 0; c < d; ++c) {
+                if (!has[c]) continue;
+                const double dl = mdiff(mj[z * d + c], cmu[c], is_circ(cm, c));
+                if (leaf) p = fma(dl * dl, iv[c], p);
+                else {
+                  const double v = vj[z * d + c] + cvar[c];
                   p += dl * dl / v + log(v);
                 }
               }
-              pz[q] = p;
-              pmin = fmin(pmin, p);
-            }
-            pmin = warp_min(pmin);
-            double tot = 0;
+              return p;
+            };
+            double ct[16];
+            double Tl = 0.0, off = 0.0, tot = 0.0, base = leaf ? 0.0 : Lb;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+              Tl = 0.0;
 #pragma unroll
-            for (int q = 0; q < IIF_MAX_POINTS / 32; ++q) {
-              const int zz = lane + 32 * q;
-              double w = 0;
-              if (zz < nz) {
-                const int lo = T.lo[z0 + zz], hi = T.hi[z0 + zz];
-                w = exp(-0.5 * (pz[q] - pmin)) * ((double)(hi - lo + 1) / (double)N);
+              for (int ch = 0; ch < 16; ++ch) {
+                const int cb = zb + ch * CH;
+                double sacc = 0.0;
+                if (cb < ze) {
+                  const int ce = min(cb + CH, ze);
+                  for (int z = cb; z < ce; ++z) sacc += exp_neg(fmin(-0.5 * (expo(z) - base), 0.0)) * wj[z];
+                }
+                ct[ch] = sacc;
+                Tl += sacc;
               }
-              pz[q] = w;
-              tot += w;
+              // inclusive scan over the group's lanes
+              double inc = Tl;
+              for (int o = 1; o < G; o <<= 1) {
+                const double y = __shfl_up_sync(gmask, inc, o, G);
+                if (gl >= o) inc += y;
+              }
+              off = inc - Tl;
+              tot = __shfl_sync(gmask, inc, G - 1, G);
+              if (tot > 1e-280 || attempt == 1) break;
+              // every weight underflowed: redo relative to the exact minimum exponent
+              double pm = INFINITY;
+              for (int z = zb; z < ze; ++z) pm = fmin(pm, expo(z));
+              for (int o = G >> 1; o > 0; o >>= 1) pm = fmin(pm, __shfl_xor_sync(gmask, pm, o, G));
+              base = pm;
             }
-            tot = warp_sum(tot);
             const uint32_t idx = (uint32_t)(((s * L + (l - 1)) * niter + it) * F + j);
             const double u = (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx]
                                                                     : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
             const double thr = u * tot;
-            int pick = nz - 1;
-            double carry = 0;
+            const bool mine = (zb < ze) && (thr >= off) && (thr < off + Tl);
+            const unsigned hit = __ballot_sync(gmask, mine) & gmask;
+            int pick = nz - 1;  // rounding left thr >= total: the oracle falls back to the last candidate
+            if (hit) {
+              const int owner = __ffs(hit) - 1;  // lane index within the warp
+              if (lane == owner) {
+                double run = off;
+                pick = ze - 1;
+                bool found = false;
 #pragma unroll
-            for (int q = 0; q < IIF_MAX_POINTS / 32; ++q) {
-              if (32 * q >= nz) break;
-              // inclusive warp scan of this chunk's weights (z ascending == lane ascending)
-              double c = pz[q];
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                double y = __shfl_up_sync(0xffffffffu, c, o);
-                if (lane >= o) c += y;
+                for (int ch = 0; ch < 16; ++ch) {
+                  const int cb = zb + ch * CH;
+                  if (!found && cb < ze) {
+                    if (thr < run + ct[ch]) {
+                      const int ce = min(cb + CH, ze);
+                      double cum = run;
+                      pick = ce - 1;
+                      for (int z = cb; z < ce; ++z) {
+                        cum += exp_neg(fmin(-0.5 * (expo(z) - base), 0.0)) * wj[z];
+                        if (thr < cum) { pick = z; break; }
+                      }
+                      found = true;
+                    }
+                    run += ct[ch];
+                  }
+                }
               }
-              c += carry;
-              const unsigned hit = __ballot_sync(0xffffffffu, (lane + 32 * q < nz) && (thr < c));
-              if (hit) { pick = 32 * q + __ffs(hit) - 1; break; }
-              carry = __shfl_sync(0xffffffffu, c, 31);
+              pick = __shfl_sync(gmask, pick, owner & (G - 1), G);
             }
             node[j] = z0 + pick;
           }
         }
       }
       // samplePoint: draw from the product of the selected leaf kernels
-      for (int c = 0; c < d; ++c) {
-        double mu = 0;
-        const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, -1, nn, d, c, is_circ(cm, c), mu);
-        if (lane == 0) {
+      if (gl == 0) {
+        for (int c = 0; c < d; ++c) {
+          double mu = 0;
+          const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, -1, nn, d, c, is_circ(cm, c), mu);
           double x;
           if (lam > 0) {
             const uint32_t idx = (uint32_t)(s * d + c);
@@ -267,6 +328,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
                                                                     : rs_normal(seed, call, IIF_RS_GIBBS_N, idx);
             x = madd(mu, sqrt(1.0 / lam) * e, is_circ(cm, c));
           } else if (t.target_slot >= 0) {
+            // coordinates no proposal informs keep oldPoints (GraphProductOperations.jl:37-45)
             const iif_slot_desc S = g.slots[t.target_slot];
             const int len = g.npts[t.target_slot];
             if (s < len) x = g.pts[S.pts_off + s * d + c];
@@ -281,17 +343,13 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
           }
           sm.post[s * d + c] = x;
         }
-      }
-      if (t.out_labels != nullptr && lane < F) {
-        int nj = 0;
-        for (int j = 0; j < F; ++j) if (j == lane) nj = node[j];
-        t.out_labels[s * F + lane] = permA[lane * N + T.lo[nj]];
+        if (t.out_labels != nullptr)
+          for (int j = 0; j < F; ++j) t.out_labels[s * F + j] = permA[j * N + T.lo[node[j]]];
       }
     }
     __syncthreads();
     // ---- 4. re-bandwidth of the posterior (getKDEManifoldBandwidths on the result)
     block_kde_bandwidth(sm.post, N, d, cm, T, sm.xa, sm.xb, sm.scr, sm.red, parity, bw);
-    (void)covered;
   }
 
   // ---- outputs: explicit buffers and / or setBelief! into the destination slot

@@ -531,7 +531,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
     const int L = ctx->trees[o.N].L;
     if (o.randu_off >= 0) n_u = std::max<int64_t>(n_u, o.randu_off + (int64_t)o.N * L * ctx->sp.gibbsNiter * o.nfactors);
     if (o.randn_off >= 0) n_n = std::max<int64_t>(n_n, o.randn_off + (int64_t)o.N * o.dim);
-    smem = std::max(smem, prod_smem_bytes(o.nfactors, o.N, o.dim, ctx->trees[o.N].nn));
+    smem = std::max(smem, prod_smem_bytes(o.nfactors, o.N, o.dim, ctx->trees[o.N].nn, ctx->trees[o.N].L));
   }
   if ((n_u && !randU) || (n_n && !randN)) return fail(ctx, IIF_ERR_ARG, "product_batch: explicit stream offset given but array is NULL");
   if ((int)smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "product op exceeds the shared-memory budget (F*N*d too large)");
@@ -702,7 +702,7 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
         t.conv_status = s->d_status + cidx[o.a];
         t.out_status = s->d_status + s->nconv + o.a;
         pt.push_back(t);
-        W.prod_smem = std::max(W.prod_smem, prod_smem_bytes(P.nfactors, P.N, S.dim, ctx->trees[P.N].nn));
+        W.prod_smem = std::max(W.prod_smem, prod_smem_bytes(P.nfactors, P.N, S.dim, ctx->trees[P.N].nn, ctx->trees[P.N].L));
       } else return fail(ctx, IIF_ERR_ARG, "schedule: unknown op kind");
     }
     W.nconv = (int)ct.size() - W.conv0; W.nprod = (int)pt.size() - W.prod0; W.ncopy = (int)cp.size() / 2 - W.copy0;
