@@ -35,6 +35,10 @@ struct ConvTask {
   int32_t* out_status; // 1 or NULL (device-side error code for this task)
 };
 
+__host__ __device__ inline size_t conv_smem_bytes(int N) {
+  return sizeof(double) * ((size_t)N * IIF_MAX_DIM + 2 * (size_t)N + (size_t)loo_scratch_doubles(N));
+}
+
 struct HypoRecipe {  // HypoRecipe, src/entities/HypoRecipe.jl:4-9 (elements are implicit: mhidx == hyp)
   int32_t nb;
   int32_t hyp[IIF_MAX_ARITY + 2];
@@ -299,13 +303,12 @@ __device__ __forceinline__ bool is_prior_kind(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR;
 }
 
-__global__ void __launch_bounds__(IIF_THREADS)
+__global__ void __launch_bounds__(IIF_THREADS, 2)
 iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double* __restrict__ meas,
                 const int32_t* __restrict__ mhidx_in, const double* __restrict__ uinf,
                 const TreeStruct* __restrict__ trees) {
-  __shared__ double dest[IIF_MAX_POINTS * IIF_MAX_DIM];
-  __shared__ double xa[IIF_MAX_POINTS], xb[IIF_MAX_POINTS];
-  __shared__ double scr[IIF_LOO_SCRATCH];
+  // dynamic shared memory, sized by the host for the launch's largest N (conv_smem_bytes)
+  extern __shared__ __align__(16) double conv_smem[];
   __shared__ double red[IIF_RED_DOUBLES];
   __shared__ double mu_s[IIF_MAX_DIM];
   __shared__ HypoRecipe R;
@@ -316,6 +319,10 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   const iif_conv_op op = t.op;
   const int n = threadIdx.x;
   int parity = 0;
+  double* dest = conv_smem;                         // N * IIF_MAX_DIM
+  double* xa = dest + (size_t)op.N * IIF_MAX_DIM;   // N
+  double* xb = xa + op.N;                           // N
+  double* scr = xb + op.N;                          // loo_scratch_doubles(N)
   if (n == 0) {
     f = g.factors[op.factor];
     s_status = IIF_OK;

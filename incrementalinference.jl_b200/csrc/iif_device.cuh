@@ -9,7 +9,7 @@
 
 #include "../../include/iifb200.h"
 
-#define IIF_THREADS 256
+#define IIF_THREADS 512
 #define IIF_WARPS (IIF_THREADS / 32)
 #define IIF_PI 3.14159265358979323846
 #define IIF_TWO_PI 6.28318530717958647692
@@ -175,11 +175,49 @@ __device__ __forceinline__ double exp_neg(double x) {
   for (int c = 1; c < 12; ++c) p = fma(p, r, IIF_EXPC[c]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  const int k1 = k >> 1, k2 = k - k1;
+  // 2^k in two normal-range factors; k clamped so that anything below the denormal range is 0
+  const int kc = max(k, -1100), k1 = kc >> 1, k2 = kc - k1;
   const double s1 = __hiloint2double((k1 + 1023) << 20, 0);
   const double s2 = __hiloint2double((k2 + 1023) << 20, 0);
-  const double res = (p * s1) * s2;
-  return (x < -746.0) ? 0.0 : res;
+  return (p * s1) * s2;
+}
+
+// Four exponentials in lockstep: every polynomial step is issued for all four arguments before the
+// next one, so the four FP64 dependency chains interleave and each coefficient is fetched once.
+__device__ __forceinline__ void exp_neg4(const double (&x)[4], double (&out)[4]) {
+  const double L2E = IIF_EXPC[12], LN2H = IIF_EXPC[13], LN2L = IIF_EXPC[14], MAGIC = IIF_EXPC[15];
+  double t[4], r[4], p[4];
+  int k[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) t[u] = fma(x[u], L2E, MAGIC);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { k[u] = __double2loint(t[u]); t[u] -= MAGIC; }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) r[u] = fma(t[u], LN2H, x[u]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) r[u] = fma(t[u], LN2L, r[u]);
+  {
+    const double c0 = IIF_EXPC[0], c1 = IIF_EXPC[1];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = fma(c0, r[u], c1);
+  }
+#pragma unroll
+  for (int c = 2; c < 12; ++c) {
+    const double cc = IIF_EXPC[c];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = fma(p[u], r[u], cc);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) p[u] = fma(p[u], r[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) p[u] = fma(p[u], r[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int kc = max(k[u], -1100), k1 = kc >> 1, k2 = kc - k1;
+    const double s1 = __hiloint2double((k1 + 1023) << 20, 0);
+    const double s2 = __hiloint2double((k2 + 1023) << 20, 0);
+    out[u] = (p[u] * s1) * s2;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -188,97 +226,137 @@ __device__ __forceinline__ double exp_neg(double x) {
 // GraphProductOperations.jl:53).  Exact O(N^2) evaluation (KDE.setForceEvalDirect!(true),
 // src/IncrementalInference.jl:104).
 //
-// Objective -1/N sum_i log( 1/(N-1) sum_{j!=i} N(x_i - x_j; 0, h^2) ).  The kernel matrix is
-// symmetric with a zero diagonal, so every unordered pair is evaluated ONCE: row i (one warp per
-// row) covers the circulant half j = i+1 .. i+floor(N/2) (mod N); the lanes stride those columns,
-// the row part is reduced with warp shuffles and the mirrored column part accumulates in the
-// warp's private shared-memory strip (distinct j per lane: no atomics).  Two rows are in flight
-// per warp so that two independent exp chains hide the FP64 latency.  scr layout:
-// [IIF_WARPS][N] column strips, [N] row sums, [IIF_WARPS] dummy cells for inactive lanes.
+// Objective -1/N sum_i log( 1/(N-1) sum_{j!=i} N(x_i - x_j; 0, h^2) ).
+// Thread layout: lane <-> row i, the G = threads/roundup(N,32) thread segments split the columns,
+// four independent exp chains per thread hide the FP64 latency, no shuffles in the hot loop.
+//  * symmetric form (N <= IIF_LOO_SYM_MAX): the kernel matrix is symmetric with a zero diagonal,
+//    so every unordered pair is evaluated ONCE: row i covers the circulant half j = i+1..i+N/2
+//    (mod N), keeps its row part in a register and stores e(i,k) to the shared tile E[k][i]; after
+//    one barrier thread j gathers the mirrored column part sum_k E[k][j-k].  Plain stores and
+//    loads only (conflict-free: consecutive lanes touch consecutive addresses).
+//  * full form (larger N, tile would not fit): every thread sums its share of row i directly.
+// scr layout: part[IIF_LOO_PARTS][N] segment partials, then the E tile (symmetric form only).
 // ------------------------------------------------------------------------------------------
-#define IIF_LOO_SCRATCH ((IIF_WARPS + 1) * IIF_MAX_POINTS + IIF_WARPS)
-#define IIF_LOO_SCRATCH_N(N) ((IIF_WARPS + 1) * (N) + IIF_WARPS)
+#define IIF_LOO_SYM_MAX 160
+#define IIF_LOO_PARTS 8
+__host__ __device__ inline bool loo_sym(int N) { return N <= IIF_LOO_SYM_MAX; }
+__host__ __device__ inline int loo_scratch_doubles(int N) {
+  return IIF_LOO_PARTS * N + (loo_sym(N) ? ((N >> 1) + 1) * N : 0);
+}
+#define IIF_LOO_SCRATCH_N(N) loo_scratch_doubles(N)
 
 template <bool CIRC>
-__device__ __forceinline__ void loo_rows(const double* __restrict__ x, int N, double ninv2h2, double* col,
-                                         double* rowsum, double* dummy) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = (N - 1) >> 1, hN = N >> 1;
-  const bool even = (N & 1) == 0;
-  const int nq2 = (half + 1 + 63) >> 6;  // uniform trip count, two 32-column chunks per trip
-  for (int i0 = warp; i0 < N; i0 += 2 * IIF_WARPS) {
-    const int i1 = i0 + IIF_WARPS;
-    const bool has1 = i1 < N;
-    const double x0 = x[i0], x1 = has1 ? x[i1] : 0.0;
-    const int nk0 = half + ((even && i0 < hN) ? 1 : 0);
-    const int nk1 = has1 ? half + ((even && i1 < hN) ? 1 : 0) : 0;
-    double s0 = 0.0, s1 = 0.0;
-    for (int q = 0; q < nq2; ++q) {
-      // four independent exp chains per trip (2 rows x 2 chunks): branch-free so that the FP64
-      // dependency chains interleave; inactive lanes add 0 to a column nobody else touches
-      const int ka = 1 + lane + 64 * q, kb = ka + 32;
-      const bool a0 = ka <= nk0, b0 = kb <= nk0, a1 = ka <= nk1, b1 = kb <= nk1;
-      int ja0 = i0 + ka, jb0 = i0 + kb, ja1 = i1 + ka, jb1 = i1 + kb;
-      ja0 -= (ja0 >= N) ? N : 0;
-      jb0 -= (jb0 >= N) ? N : 0;
-      ja1 -= (ja1 >= N) ? N : 0;
-      jb1 -= (jb1 >= N) ? N : 0;
-      ja0 = a0 ? ja0 : i0;  // inactive lanes: any valid x index, their weight is discarded
-      jb0 = b0 ? jb0 : i0;
-      ja1 = a1 ? ja1 : i0;
-      jb1 = b1 ? jb1 : i0;
-      double* pa0 = a0 ? col + ja0 : dummy;
-      double* pb0 = b0 ? col + jb0 : dummy;
-      double* pa1 = a1 ? col + ja1 : dummy;
-      double* pb1 = b1 ? col + jb1 : dummy;
-      const double da0 = mdiff(x0, x[ja0], CIRC), db0 = mdiff(x0, x[jb0], CIRC);
-      const double da1 = mdiff(x1, x[ja1], CIRC), db1 = mdiff(x1, x[jb1], CIRC);
-      double ea0 = exp_neg(da0 * da0 * ninv2h2), eb0 = exp_neg(db0 * db0 * ninv2h2);
-      double ea1 = exp_neg(da1 * da1 * ninv2h2), eb1 = exp_neg(db1 * db1 * ninv2h2);
-      ea0 = a0 ? ea0 : 0.0;
-      eb0 = b0 ? eb0 : 0.0;
-      ea1 = a1 ? ea1 : 0.0;
-      eb1 = b1 ? eb1 : 0.0;
-      s0 += ea0 + eb0;
-      s1 += ea1 + eb1;
-      *pa0 += ea0;       // row i0: the two chunks hit distinct columns
-      *pb0 += eb0;
-      __syncwarp();      // row i1 may hit a column row i0 just updated from another lane
-      *pa1 += ea1;
-      *pb1 += eb1;
-      __syncwarp();
+__device__ __forceinline__ double loo_thread_sum(const double* __restrict__ x, int N, double c, double* E,
+                                                 int i, int seg, int G, bool active) {
+  double acc = 0.0;
+  if (!active) return acc;
+  const double xi = x[i];
+  if (loo_sym(N)) {
+    const int hN = N >> 1;
+    const bool even = (N & 1) == 0;
+    const int nk = ((N - 1) >> 1) + (even ? 1 : 0);  // k = 1..nk ; k == N/2 (even N) only for i < N/2
+    const int per = (nk + G - 1) / G;
+    const int k0 = 1 + seg * per, k1 = min(nk, (seg + 1) * per);
+    // the antipodal column (even N, k == N/2) counts once: rows i >= N/2 store and add 0 there
+    const bool cut = even && k1 == hN && i >= hN;
+    int k = k0;
+    for (; k + 3 <= k1; k += 4) {  // full groups: no per-element checks except the antipodal one
+      double a[4], e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int j = i + k + u;
+        j -= (j >= N) ? N : 0;
+        const double dl = mdiff(xi, x[j], CIRC);
+        a[u] = dl * dl * c;
+      }
+      exp_neg4(a, e);
+      if (cut && k + 3 == k1) e[3] = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc += e[u];
+        E[(k + u - 1) * N + i] = e[u];
+      }
     }
-    s0 = warp_sum(s0);
-    s1 = warp_sum(s1);
-    if (lane == 0) {
-      rowsum[i0] = s0;
-      if (has1) rowsum[i1] = s1;
+    for (; k <= k1; ++k) {  // tail (< 4 columns)
+      int j = i + k;
+      j -= (j >= N) ? N : 0;
+      const double dl = mdiff(xi, x[j], CIRC);
+      double e = exp_neg(dl * dl * c);
+      if (cut && k == k1) e = 0.0;
+      acc += e;
+      E[(k - 1) * N + i] = e;
+    }
+  } else {
+    const int per = (N + G - 1) / G;
+    const int j0 = seg * per, j1 = min(N, (seg + 1) * per) - 1;
+    for (int j = j0; j <= j1; j += 4) {
+      double a[4], e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = min(j + u, j1);
+        const double dl = mdiff(xi, x[jj], CIRC);
+        a[u] = dl * dl * c;
+      }
+      exp_neg4(a, e);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += ((j + u <= j1) && (j + u != i)) ? e[u] : 0.0;
     }
   }
+  return acc;
 }
 
 __device__ __noinline__ double loo_nll(const double* __restrict__ x, int N, int circ, double h, double* scr,
                                        double* red, int* parity_io) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double ninv2h2 = -1.0 / (2.0 * h * h);
+  const double c = -1.0 / (2.0 * h * h);
   const double lognorm = log((double)(N - 1) * sqrt(IIF_TWO_PI) * h);
-  double* col = scr + warp * N;
-  double* rowsum = scr + IIF_WARPS * N;
-  for (int j = lane; j < N; j += 32) col[j] = 0.0;
-  __syncwarp();
-  double* dummy = scr + (IIF_WARPS + 1) * N + warp;
-  if (circ) loo_rows<true>(x, N, ninv2h2, col, rowsum, dummy);
-  else loo_rows<false>(x, N, ninv2h2, col, rowsum, dummy);
-  __syncthreads();
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < N; i += IIF_THREADS) {
-    double t = rowsum[i];
-#pragma unroll
-    for (int w = 0; w < IIF_WARPS; ++w) t += scr[w * N + i];
-    acc += log(t) - lognorm;
+  const int Npad = (N + 31) & ~31;
+  int G = IIF_THREADS / Npad;
+  G = G > IIF_LOO_PARTS ? IIF_LOO_PARTS : G;
+  const int seg = threadIdx.x / Npad, i = threadIdx.x - seg * Npad;
+  const bool active = (seg < G) && (i < N);
+  double* part = scr;
+  double* E = scr + IIF_LOO_PARTS * N;
+  double acc = circ ? loo_thread_sum<true>(x, N, c, E, i, seg, G, active)
+                    : loo_thread_sum<false>(x, N, c, E, i, seg, G, active);
+  if (loo_sym(N)) {
+    __syncthreads();
+    if (active) {  // mirrored column part: sum_k E[k][j - k], same k-range as this thread's row part
+      const int hN = N >> 1;
+      const int nk = ((N - 1) >> 1) + (((N & 1) == 0) ? 1 : 0);
+      const int per = (nk + G - 1) / G;
+      const int k0 = 1 + seg * per, k1 = min(nk, (seg + 1) * per);
+      double a0 = 0.0, a1 = 0.0;
+      int k = k0;
+      for (; k + 1 <= k1; k += 2) {
+        int r0 = i - k, r1 = i - k - 1;
+        r0 += (r0 < 0) ? N : 0;
+        r1 += (r1 < 0) ? N : 0;
+        a0 += E[(k - 1) * N + r0];
+        a1 += E[k * N + r1];
+      }
+      if (k <= k1) {
+        int r0 = i - k;
+        r0 += (r0 < 0) ? N : 0;
+        a0 += E[(k - 1) * N + r0];
+      }
+      acc += a0 + a1;
+      (void)hN;
+    }
+  }
+  double term = 0.0;
+  if (G > 1) {
+    if (active) part[seg * N + i] = acc;
+    __syncthreads();
+    if (seg == 0 && i < N) {
+      double t = 0.0;
+      for (int g = 0; g < G; ++g) t += part[g * N + i];
+      term = log(t) - lognorm;
+    }
+  } else if (active) {
+    term = log(acc) - lognorm;
   }
   int parity = *parity_io;
-  double tot = block_sum1(acc, red, parity);  // its barrier also protects scr for the next call
+  const double tot = block_sum1(term, red, parity);  // its barrier also protects scr for the next call
   *parity_io = parity;
   return -tot / (double)N;
 }

@@ -397,12 +397,14 @@ struct BwTask {
 };
 __global__ void __launch_bounds__(IIF_THREADS)
 iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restrict__ trees) {
-  __shared__ double pts[IIF_MAX_POINTS * IIF_MAX_DIM];
-  __shared__ double xa[IIF_MAX_POINTS], xb[IIF_MAX_POINTS];
-  __shared__ double scr[IIF_LOO_SCRATCH];
+  extern __shared__ __align__(16) double bw_smem[];  // conv_smem_bytes(N)
   __shared__ double red[IIF_RED_DOUBLES];
   const BwTask t = tasks[blockIdx.x];
   int parity = 0;
+  double* pts = bw_smem;
+  double* xa = pts + (size_t)t.N * IIF_MAX_DIM;
+  double* xb = xa + t.N;
+  double* scr = xb + t.N;
   for (int i = threadIdx.x; i < t.N * t.dim; i += IIF_THREADS) pts[i] = t.pts[i];
   __syncthreads();
   double bw[IIF_MAX_DIM] = {0, 0, 0, 0};

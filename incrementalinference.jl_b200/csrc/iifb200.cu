@@ -25,7 +25,7 @@ struct TreeHost {
 
 struct Wave {
   int conv0 = 0, nconv = 0, prod0 = 0, nprod = 0, copy0 = 0, ncopy = 0;
-  size_t prod_smem = 0;
+  size_t prod_smem = 0, conv_smem = 0;
 };
 
 struct Schedule {
@@ -180,6 +180,12 @@ int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
   if ((e = cudaFuncSetAttribute(iif_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ctx->max_smem_optin - 4096)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(product smem)", e);
+  if ((e = cudaFuncSetAttribute(iif_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(conv smem)", e);
+  if ((e = cudaFuncSetAttribute(iif_bandwidth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(bandwidth smem)", e);
   *ctx_out = ctx;
   return IIF_OK;
 }
@@ -445,9 +451,11 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
   std::vector<ConvTask> tasks(K);
   std::vector<int64_t> poff(K + 1, 0), noff(K + 1, 0);
   int64_t n_meas = 0, n_lab = 0, n_uinf = 0;
+  size_t csmem = 0;
   for (int k = 0; k < K; ++k) {
     int32_t st = validate_conv(ctx, ops[k]);
     if (st != IIF_OK) return st;
+    csmem = std::max(csmem, conv_smem_bytes(ops[k].N));
     const iif_factor_desc& F = ctx->factors[ops[k].factor];
     const int d = ctx->slots[F.slot[ops[k].sfidx - 1]].dim;
     poff[k + 1] = poff[k] + (int64_t)ops[k].N * d;
@@ -483,7 +491,7 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ConvTask) * K, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_conv_kernel<<<K, IIF_THREADS, 0, ctx->stream>>>(ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
+  iif_conv_kernel<<<K, IIF_THREADS, csmem, ctx->stream>>>(ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -594,10 +602,12 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   if (K < 1 || !N || !dim || !circ_mask || !pts || !out_bw) return fail(ctx, IIF_ERR_ARG, "kde_bandwidth: bad arguments");
   CK(cudaSetDevice(ctx->device));
   std::vector<int64_t> off(K + 1, 0);
+  size_t bsmem = 0;
   for (int k = 0; k < K; ++k) {
     if (dim[k] < 1 || dim[k] > IIF_MAX_DIM) return fail(ctx, IIF_ERR_ARG, "kde_bandwidth: dim out of range");
     int32_t st = ensure_tree(ctx, N[k]);
     if (st != IIF_OK) return st;
+    bsmem = std::max(bsmem, conv_smem_bytes(N[k]));
     off[k + 1] = off[k] + (int64_t)N[k] * dim[k];
   }
   double *d_pts = nullptr, *d_bw = nullptr;
@@ -610,7 +620,7 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   CK(cudaMemcpyAsync(d_pts, pts, sizeof(double) * off[K], cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_t, t.data(), sizeof(BwTask) * K, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_bandwidth_kernel<<<K, IIF_THREADS, 0, ctx->stream>>>(d_t, ctx->d_trees);
+  iif_bandwidth_kernel<<<K, IIF_THREADS, bsmem, ctx->stream>>>(d_t, ctx->d_trees);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -702,6 +712,7 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
         t.conv_status = s->d_status + cidx[o.a];
         t.out_status = s->d_status + s->nconv + o.a;
         pt.push_back(t);
+        W.conv_smem = std::max(W.conv_smem, conv_smem_bytes(P.N));
         W.prod_smem = std::max(W.prod_smem, prod_smem_bytes(P.nfactors, P.N, S.dim, ctx->trees[P.N].nn, ctx->trees[P.N].L));
       } else return fail(ctx, IIF_ERR_ARG, "schedule: unknown op kind");
     }
@@ -743,7 +754,7 @@ static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int*
       ++k;
     }
     if (W.nconv) {
-      iif_conv_kernel<<<W.nconv, IIF_THREADS, 0, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      iif_conv_kernel<<<W.nconv, IIF_THREADS, W.conv_smem, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
       ++k;
     }
     if (W.nprod) {
@@ -812,7 +823,7 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
     }
     if (W.nconv) {
       mark();
-      iif_conv_kernel<<<W.nconv, IIF_THREADS, 0, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      iif_conv_kernel<<<W.nconv, IIF_THREADS, W.conv_smem, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(0); blocks[0] += W.nconv;
     }
     if (W.nprod) {
