@@ -1,0 +1,100 @@
+# IIFB200.jl — reference-side binding of libiifb200.so (cannot be executed in the build image: no Julia).
+#
+# Drop-in boundary B3 (SURVEY.md §8b): overrides IncrementalInference.propagateBelief for graphs whose
+# SolverParams.devParams[:backend] == "b200" and forwards to the C-ABI declared in include/iifb200.h.
+# Everything above (factor graph, Bayes tree, CliqueStateMachine, solveTree!) is unchanged Julia.
+module IIFB200
+
+using IncrementalInference
+using DistributedFactorGraphs
+import IncrementalInference: propagateBelief
+const IIF = IncrementalInference
+const AMP = IIF.ApproxManifoldProducts
+
+const LIB = get(ENV, "IIFB200_LIB", joinpath(@__DIR__, "..", "incrementalinference.jl_b200", "csrc", "libiifb200.so"))
+
+# ---- mirrors of the C structs (include/iifb200.h) -------------------------------------------------
+const MAX_DIM, MAX_ARITY, MAX_FACTORS = 4, 6, 8
+struct SlotDesc;   dim::Int32; circ_mask::Int32; cap::Int32; pts_off::Int32; end
+struct DistDesc;   kind::Int32; dim::Int32; ncomp::Int32; comp_kind::Int32; slot::Int32; poff::Int32; end
+struct FactorDesc
+  kind::Int32; arity::Int32; zdim::Int32; dist::Int32
+  slot::NTuple{MAX_ARITY,Int32}; nmh::Int32; partial_mask::Int32
+  mh::NTuple{MAX_ARITY,Float64}; nullhypo::Float64; inflation::Float64
+end
+struct SolverParamsC; spreadNH::Float64; nullSurplusAdd::Float64; inflateCycles::Int32; gibbsNiter::Int32; seed::UInt64; end
+struct PropOp
+  target_slot::Int32; out_slot::Int32; nfactors::Int32; N::Int32
+  factor::NTuple{MAX_FACTORS,Int32}; sfidx::NTuple{MAX_FACTORS,Int32}; call_id::Int32; any_multihypo::Int32
+end
+
+check(ctx, st, what) = st == 0 || error("iifb200 $what failed ($st): " *
+        unsafe_string(ccall((:iifb200_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
+
+function init(device::Integer = 0)
+  ctx = Ref{Ptr{Cvoid}}(C_NULL)
+  st = ccall((:iifb200_init, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, ctx)
+  st == 0 || error("iifb200_init failed: " * unsafe_string(ccall((:iifb200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+  return ctx[]
+end
+
+# factor kind / distribution lowering: only the built-in residual library runs on the device
+factorkind(::Prior) = Int32(1); factorkind(::LinearRelative) = Int32(2)
+factorkind(::PriorCircular) = Int32(3); factorkind(::CircularCircular) = Int32(4)
+factorkind(::EuclidDistance) = Int32(5); factorkind(::IIF.MsgPrior) = Int32(6)
+factorkind(f) = error("IIFB200: factor $(typeof(f)) has no device residual (no CPU fallback on the b200 backend)")
+
+circmask(::Type{<:IIF.Circular}) = Int32(1)
+circmask(::Any) = Int32(0)
+
+"""
+    propagateBelief(dfg, destvar, factors; N, ...)   — GraphProductOperations.jl:16-64
+
+b200 backend: lowers the destination variable, its factors and their variables to the descriptor
+tables, uploads the particle blocks (zero-copy for `Vector{SVector{d,Float64}}`; `Circular`'s
+`Vector{Vector{Float64}}` is packed), runs iifb200_propagate_batch (F convolutions + KDE product) and
+rebuilds the ManifoldKernelDensity from the returned points and bandwidths.
+"""
+function propagateBelief(dfg::AbstractDFG, destvar::DFGVariable, factors::AbstractVector;
+                         solveKey::Symbol = :default, N::Integer = getSolverParams(dfg).N, kw...)
+  get(getSolverParams(dfg).devParams, :backend, "") == "b200" ||
+    return invoke(propagateBelief, Tuple{AbstractDFG, DFGVariable, AbstractVector}, dfg, destvar, factors; solveKey, N, kw...)
+  ctx = _ctx()
+  vars, slotof = _collect_variables(dfg, destvar, factors)           # labels -> slot index
+  slots   = [SlotDesc(getDimension(v), circmask(getVariableType(v)), max(N, length(getVal(v; solveKey))), 0) for v in vars]
+  dists, dparams, fdescs = _lower_factors(dfg, factors, slotof)       # Normal / MvNormal / Mixture / MsgPrior(MKD)
+  sp = getSolverParams(dfg)
+  spc = Ref(SolverParamsC(sp.spreadNH, sp.nullSurplusAdd, sp.inflateCycles, 1, rand(UInt64)))
+  GC.@preserve slots dists dparams fdescs begin
+    check(ctx, ccall((:iifb200_set_graph, LIB), Int32,
+          (Ptr{Cvoid}, Int32, Ptr{SlotDesc}, Int32, Ptr{FactorDesc}, Int32, Ptr{DistDesc}, Int32, Ptr{Float64}, Ref{SolverParamsC}, Ptr{Cvoid}),
+          ctx, length(slots), slots, length(fdescs), fdescs, length(dists), dists, length(dparams), dparams, spc, C_NULL), "set_graph")
+    for (i, v) in enumerate(vars)
+      pts = _packpoints(getVal(v; solveKey))                         # reinterpret(Float64, val) when contiguous
+      bw  = getBW(v; solveKey)[:, 1]
+      check(ctx, ccall((:iifb200_upload_belief, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32),
+            ctx, i - 1, size(pts, 2), pts, bw, isInitialized(v, solveKey)), "upload_belief")
+    end
+    dest = slotof[getLabel(destvar)]
+    op = Ref(PropOp(dest, dest, length(fdescs), N,
+                    ntuple(i -> i <= length(fdescs) ? Int32(i - 1) : Int32(0), MAX_FACTORS),
+                    ntuple(i -> i <= length(fdescs) ? Int32(findfirst(==(getLabel(destvar)), getVariableOrder(factors[i]))) : Int32(0), MAX_FACTORS),
+                    0, any(IIF.isMultihypo.(factors))))
+    # blocking ccall on a dedicated thread so the other cliques' Tasks keep running (SolverAPI.jl:59-96)
+    st = @threadcall((:iifb200_propagate_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{PropOp}), ctx, 1, op)
+    check(ctx, st, "propagate_batch")
+    d = getDimension(destvar)
+    pts = Matrix{Float64}(undef, d, N); bw = zeros(d); ipc = zeros(d); npts = Ref{Int32}(0)
+    check(ctx, ccall((:iifb200_download_belief, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+          ctx, dest, npts, pts, bw, ipc), "download_belief")
+  end
+  M = getManifold(getVariableType(destvar))
+  mkd = AMP.manikde!(M, _unpackpoints(getVariableType(destvar), pts); bw)   # bw given => no re-selection (FGOSUtils.jl:118-128)
+  return mkd, ipc
+end
+
+# throughput mode (boundary B4): IIF.upGibbsCliqueDensity / localProductAndUpdate! are lowered per tree by
+# iifb200_schedule_build and replayed by iifb200_schedule_run; see incrementalinference.jl_b200/tree.py for
+# the lowering that a Julia implementation mirrors 1:1 (same descriptor structs).
+
+end # module
