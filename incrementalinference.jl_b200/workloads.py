@@ -131,3 +131,34 @@ def chain_nd_order(n):
         remaining = [k for k in remaining if k not in es]
     order += remaining
     return [f"x{k}" for k in order]
+
+
+def generateGraph_Kaess(N=100, seed=42, graphinit=False):
+    """CanonicalGraphExamples.jl:15-37 (Kaess et al. example; all Normal())."""
+    fg = G.initfg(G.SolverParams(N=N, seed=seed, graphinit=graphinit))
+    G.addVariable(fg, "x1", G.ContinuousScalar)
+    G.addFactor(fg, ["x1"], G.Prior(G.Normal()))
+    G.addVariable(fg, "x2", G.ContinuousScalar)
+    G.addFactor(fg, ["x1", "x2"], G.LinearRelative(G.Normal()))
+    G.addVariable(fg, "x3", G.ContinuousScalar)
+    G.addFactor(fg, ["x2", "x3"], G.LinearRelative(G.Normal()))
+    G.addVariable(fg, "l1", G.ContinuousScalar)
+    G.addFactor(fg, ["x1", "l1"], G.LinearRelative(G.Normal()))
+    G.addFactor(fg, ["x2", "l1"], G.LinearRelative(G.Normal()))
+    G.addVariable(fg, "l2", G.ContinuousScalar)
+    G.addFactor(fg, ["x3", "l2"], G.LinearRelative(G.Normal()))
+    return fg
+
+
+def generateGraph_CaesarRing1D(N=100, seed=42, graphinit=False):
+    """CanonicalGraphExamples.jl:123-150."""
+    fg = G.initfg(G.SolverParams(N=N, seed=seed, graphinit=graphinit))
+    for k in range(7):
+        G.addVariable(fg, f"x{k}", G.ContinuousScalar)
+    G.addFactor(fg, ["x0"], G.Prior(G.Normal()))
+    for k in range(6):
+        G.addFactor(fg, [f"x{k}", f"x{k+1}"], G.LinearRelative(G.Normal()))
+    G.addVariable(fg, "l1", G.ContinuousScalar)
+    G.addFactor(fg, ["x0", "l1"], G.LinearRelative(G.Normal()))
+    G.addFactor(fg, ["x6", "l1"], G.LinearRelative(G.Normal()))
+    return fg

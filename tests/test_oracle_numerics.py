@@ -1,0 +1,222 @@
+"""CPU tests that pin the oracle (test infrastructure) before it is trusted as the GPU's checker:
+known-answer vectors, the reference's own deterministic tests and analytic roots."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle as O
+import parity_cases as PC
+from iifb200 import _abi as A
+from iifb200 import compile as CP
+from iifb200 import graph as G
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors for philox4x32-10 (Salmon et al., SC'11)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    out = (C.c_uint32 * 4)()
+    for ctr, key, exp in kat:
+        O.lib().iifo_philox4x32(*ctr, *key, out)
+        assert tuple(out) == exp
+
+
+def test_stream_uniform_and_normal_moments():
+    u = np.array([O.uniform(42, 7, 3, i) for i in range(20000)])
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005
+    z = np.array([O.normal(42, 7, 1, i) for i in range(20000)])
+    assert abs(z.mean()) < 0.03 and abs(z.std() - 1) < 0.03
+    # streams are independent of each other and reproducible
+    assert O.uniform(42, 7, 3, 5) == O.uniform(42, 7, 3, 5) != O.uniform(42, 8, 3, 5)
+
+
+def test_residual_known_answer_testApproxConv():
+    """calcFactorResidualTemporary(lr3, ..., [0;0;0.5], (zeros(3), [0;0;1.0])): sum(abs(res)) ≈ 0.5
+    (test/testApproxConv.jl:26-32) and _getZDim == 3 (:24)."""
+    res = O.residual(A.F_LINEAR_RELATIVE, [0, 0, 0.5], [np.zeros(3), np.array([0, 0, 1.0])])
+    assert len(res) == 3 and abs(np.abs(res).sum() - 0.5) < 1e-10
+
+
+def test_residual_library_values():
+    assert np.allclose(O.residual(A.F_PRIOR, [2.0], [np.array([0.5])]), [1.5])
+    assert np.allclose(O.residual(A.F_EUCLID_DISTANCE, [5.0], [np.zeros(2), np.array([3.0, 4.0])]), [0.0])
+    # circular: z=0.2, p=3.1, q=-3.1 => qhat = wrap(3.3) = -2.983..; log_q(qhat) = 0.1168..
+    r = O.residual(A.F_CIRCULAR_CIRCULAR, [0.2], [np.array([3.1]), np.array([-3.1])], circ_mask=1)
+    assert np.allclose(r, [(3.1 + 0.2 - 2 * np.pi) + 3.1])
+    r = O.residual(A.F_PRIOR_CIRCULAR, [3.1], [np.array([-3.1])], circ_mask=1)
+    assert np.allclose(r, [6.2 - 2 * np.pi])
+
+
+def test_std_basic_spread():
+    R = np.random.default_rng(0)
+    x = R.normal(3, 2, (100, 1))
+    assert np.isclose(O.std_basic_spread(x), x.std(ddof=1))                    # VariableStatistics.jl:30-31
+    x2 = R.normal(0, 1, (50, 2))
+    mu = x2.mean(axis=0)
+    assert np.isclose(O.std_basic_spread(x2), np.sqrt(((x2 - mu) ** 2).sum() / 49))  # distance-based std
+    assert O.std_basic_spread(np.full((10, 1), 4.0)) == 1.0                    # :34 sigma < 1e-10 -> 1.0
+    assert O.std_basic_spread(np.zeros((1, 1))) == 1.0
+    th = PC.wrap(R.normal(np.pi, 0.2, (80, 1)))                               # straddles the +-pi cut
+    assert abs(O.std_basic_spread(th, 1) - 0.2) < 0.05
+
+
+def test_loo_objective_matches_brute_force_and_golden_is_a_minimum():
+    R = np.random.default_rng(1)
+    x = R.normal(0, 1, 60)
+    for h in (0.05, 0.3, 2.0):
+        d = x[:, None] - x[None, :]
+        K = np.exp(-d * d / (2 * h * h)) / (np.sqrt(2 * np.pi) * h)
+        np.fill_diagonal(K, 0.0)
+        ref = -np.mean(np.log(K.sum(axis=1) / (len(x) - 1)))
+        assert np.isclose(O.loo_nll(x, h), ref, rtol=1e-12)
+    bw = O.kde_bandwidth(x)[0]
+    f0 = O.loo_nll(x, bw)
+    assert f0 <= O.loo_nll(x, bw * 1.1) and f0 <= O.loo_nll(x, bw / 1.1)
+    assert 0.5 < bw / (1.06 * x.std() * len(x) ** -0.2) < 2.0                  # same ballpark as Silverman
+    # per-dimension independence and scale equivariance
+    x2 = np.stack([x, 10 * x], axis=1)
+    b2 = O.kde_bandwidth(x2)
+    assert np.isclose(b2[0], bw) and np.isclose(b2[1], 10 * bw, rtol=1e-9)
+
+
+def _two_var(N=100, nullhypo=0.0, seed=3):
+    R = np.random.default_rng(seed)
+    P = PC.Problem(seed=seed)
+    x0 = P.slot(G.ContinuousScalar, N, R.normal(0, 1, (N, 1)))
+    x1 = P.slot(G.ContinuousScalar, N, R.normal(5, 3, (N, 1)))
+    f = P.factor(G.LinearRelative(G.Normal(10.0, 1.0)), [x0, x1], nullhypo=nullhypo)
+    return P.freeze(), x0, x1, f
+
+
+def test_unique_root_is_analytic_and_independent_of_the_inflated_start():
+    """for LinearRelative the proposal is x_s[n] + z[n] exactly."""
+    P, x0, x1, f = _two_var()
+    meas = np.random.default_rng(5).normal(10, 1, 100)
+    op = CP.make_conv_ops([dict(factor=f, sfidx=2, N=100, call_id=1, meas_off=0)])[0]
+    pts, bw, ipc, lab, nan = P.oracle().conv(op, meas=meas)
+    src = P.arena.get(x0)[0][:, 0]
+    assert np.abs(pts[:, 0] - (src + meas)).max() < 1e-12 and nan == 0 and np.all(ipc == 1.0)
+    op = CP.make_conv_ops([dict(factor=f, sfidx=1, N=100, call_id=2, meas_off=0)])[0]
+    pts, *_ = P.oracle().conv(op, meas=meas)
+    assert np.abs(pts[:, 0] - (P.arena.get(x1)[0][:, 0] - meas)).max() < 1e-12
+
+
+def test_point_count_contract_and_no_aliasing():
+    """approxConv(...; N=101) returns 101 points (testVariousNSolveSize.jl:18-25) and never mutates
+    the target variable (testMultiHypo3Door.jl:59-90)."""
+    R = np.random.default_rng(2)
+    P = PC.Problem()
+    x0 = P.slot(G.ContinuousScalar, 128, R.normal(0, 1, (100, 1)))
+    x1 = P.slot(G.ContinuousScalar, 128, R.normal(0, 1, (100, 1)))
+    f = P.factor(G.LinearRelative(G.Normal(1.0, 0.1)), [x0, x1])
+    P.freeze()
+    before = P.arena.copy()
+    orc = P.oracle(P.arena)
+    pts, *_ = orc.conv(CP.make_conv_ops([dict(factor=f, sfidx=2, N=101, call_id=1)])[0])
+    assert pts.shape == (101, 1)
+    assert np.array_equal(before.pts, P.arena.pts) and np.array_equal(before.bw, P.arena.bw)
+
+
+def test_nan_solve_leaves_particle_unchanged():
+    """NumericalCalculations.jl:348-351."""
+    P, x0, x1, f = _two_var()
+    s = P.frozen["slots"][x0]
+    P.arena.pts[s.pts_off + 7] = np.nan
+    op = CP.make_conv_ops([dict(factor=f, sfidx=2, N=100, call_id=1)])[0]
+    pts, bw, ipc, lab, nan = P.oracle().conv(op)
+    assert nan == 3  # inflateCycles solves on that particle
+    assert np.isfinite(pts).all()
+
+
+# ---- statistical acceptance bands ported from the reference's tests (>= 20 seeds each) -------------
+def _posterior_of_priors(mus, seed):
+    R = np.random.default_rng(seed)
+    P = PC.Problem(seed=seed)
+    x0 = P.slot(G.ContinuousScalar, 100, R.normal(np.mean(mus), 1.0, (100, 1)))
+    fs = [P.factor(G.Prior(G.Normal(m, 1.0)), [x0]) for m in mus]
+    P.freeze()
+    orc = P.oracle()
+    orc.propagate(CP.make_prop_ops([dict(target_slot=x0, factors=[(f, 1) for f in fs], N=100, call_id=16)])[0])
+    return orc.arena.get(x0)[0][:, 0]
+
+
+@pytest.mark.parametrize("mus,mean_tol,lo,hi", [
+    ([0.0], 0.5, 0.3, 1.9),              # testBasicGraphs.jl:44-47
+    ([0.0, 0.0], 0.4, 0.3, 1.0),         # :86-92  (two identical priors)
+    ([0.0, 0.0, 0.0], 0.4, 0.1, 0.75),   # :107-113 (three identical priors)
+    ([-1.0, 1.0], 0.8, 0.2, 1.5),        # :128-134
+    ([-1001.0, -999.0], 0.6, 0.2, 1.1),  # :149-155 (offset by -1000)
+])
+def test_prior_product_bands_testBasicGraphs(mus, mean_tol, lo, hi):
+    ok = 0
+    for seed in range(20):
+        p = _posterior_of_priors(mus, seed)
+        ok += (abs(p.mean() - np.mean(mus)) < mean_tol) and (lo < p.var(ddof=1) < hi)
+    assert ok >= 19   # the reference allows a retry for stochastic flakiness (testVariousNSolveSize.jl:17)
+
+
+def test_nullhypo_prior_band_testnullhypothesis():
+    """Prior(Normal(10,1)), nullhypo=0.5 (test/testnullhypothesis.jl:27-41): about half the mass stays
+    near the previous belief, half moves to the prior."""
+    ok = 0
+    for seed in range(20):
+        R = np.random.default_rng(seed)
+        P = PC.Problem(seed=seed)
+        x0 = P.slot(G.ContinuousScalar, 100, R.normal(0, 1, (100, 1)))
+        f = P.factor(G.Prior(G.Normal(10.0, 1.0)), [x0], nullhypo=0.5)
+        P.freeze()
+        pts, bw, ipc, lab, _ = P.oracle().conv(CP.make_conv_ops([dict(factor=f, sfidx=1, N=100, call_id=3)])[0])
+        a = ((-15 < pts) & (pts < 4)).sum()
+        b = ((4 < pts) & (pts < 16)).sum()
+        ok += (10 < a < 60) and (30 < b < 85)
+    assert ok >= 19
+
+
+def test_nullhypo_relative_band():
+    """LinearRelative(Normal(10,1)), nullhypo=0.5 (testnullhypothesis.jl:60-66)."""
+    ok = 0
+    for seed in range(20):
+        R = np.random.default_rng(seed)
+        P = PC.Problem(seed=seed)
+        x0 = P.slot(G.ContinuousScalar, 100, R.normal(0, 1, (100, 1)))
+        x1 = P.slot(G.ContinuousScalar, 100, R.normal(0, 1, (100, 1)))
+        f = P.factor(G.LinearRelative(G.Normal(10.0, 1.0)), [x0, x1], nullhypo=0.5)
+        P.freeze()
+        pts, *_ = P.oracle().conv(CP.make_conv_ops([dict(factor=f, sfidx=2, N=100, call_id=3)])[0])
+        ok += (20 < (pts < 5).sum()) and (20 < ((5 < pts) & (pts < 15)).sum())
+    assert ok >= 19
+
+
+def test_multihypo_bimodal_band_testmultihypothesisapi():
+    """x --(10)--> {la @ -30 | lb @ 40} with multihypo [1, .5, .5]: solving for x gives two modes near
+    la-10 and lb-10 (test/testmultihypothesisapi.jl:87-102 analogue)."""
+    ok = 0
+    for seed in range(20):
+        R = np.random.default_rng(seed)
+        P = PC.Problem(seed=seed)
+        x = P.slot(G.ContinuousScalar, 100, R.normal(0, 1, (100, 1)))
+        la = P.slot(G.ContinuousScalar, 100, R.normal(-30, 1, (100, 1)))
+        lb = P.slot(G.ContinuousScalar, 100, R.normal(40, 1, (100, 1)))
+        f = P.factor(G.LinearRelative(G.Normal(10.0, 1.0)), [x, la, lb], mh=[1.0, 0.5, 0.5])
+        P.freeze()
+        pts, bw, ipc, lab, _ = P.oracle().conv(CP.make_conv_ops([dict(factor=f, sfidx=1, N=100, call_id=9)])[0])
+        m1, m2 = (np.abs(pts + 40) < 6).sum(), (np.abs(pts - 30) < 6).sum()
+        ok += (m1 > 20) and (m2 > 20) and (m1 + m2 >= 95) and set(np.unique(lab)) <= {2, 3}
+    assert ok >= 19
+
+
+def test_mixture_prior_band_testMixtureLinearConditional():
+    """Mixture prior: >= 20 % of the points in each mode, < 10 % elsewhere
+    (test/testMixtureLinearConditional.jl:15-67 style)."""
+    R = np.random.default_rng(0)
+    P = PC.Problem()
+    x0 = P.slot(G.ContinuousScalar, 200, R.normal(0, 1, (200, 1)))
+    doors = G.Mixture(G.Prior, [G.Normal(-5, 1), G.Normal(5, 1)], [0.5, 0.5])
+    f = P.factor(doors, [x0])
+    P.freeze()
+    pts, *_ = P.oracle().conv(CP.make_conv_ops([dict(factor=f, sfidx=1, N=200, call_id=2)])[0])
+    lo, hi = (np.abs(pts + 5) < 3).mean(), (np.abs(pts - 5) < 3).mean()
+    assert lo > 0.2 and hi > 0.2 and 1 - lo - hi < 0.1
