@@ -210,7 +210,10 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
       for (int l = 1; l <= L; ++l) {
         const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
         const bool leaf = (l == L);
-        for (int j = 0; j < F; ++j) node[j] = z0 + T.child[node[j]];  // levelDown
+        for (int j = 0; j < F; ++j) {  // levelDown: follow the last child (KDE.jl levelDown!), leaves stay
+          const int nd = node[j];
+          node[j] = z0 + T.child[nd] + (T.hi[nd] > T.lo[nd] ? 1 : 0);
+        }
         const int B = (nz + G - 1) / G;
         const int zb = gl * B, ze = min(zb + B, nz);
         const int CH = max(8, (B + 15) >> 4);

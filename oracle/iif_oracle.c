@@ -800,8 +800,13 @@ int32_t iifo_product(int32_t d, int32_t cm, int32_t F, int32_t N, const double* 
     int node[IIF_MAX_FACTORS];
     for (int j = 0; j < F; ++j) node[j] = 0;                 /* levelInit / initIndices: roots */
     for (int l = 1; l <= L; ++l) {
-      /* levelDown: every density moves to level l; the selected label follows its first child */
-      for (int j = 0; j < F; ++j) node[j] = T[j].lev_off[l] + T[j].child[node[j]];
+      /* levelDown: every density moves to level l; the selected label follows the LAST child pushed
+       * (KDE.jl levelDown!: `ind[j] = levelListNew[j, z-1]`, "make sure ind points to a child of the
+       * old ind"), i.e. the right child of an internal node, the node itself for a leaf */
+      for (int j = 0; j < F; ++j) {
+        int nd = node[j];
+        node[j] = T[j].lev_off[l] + T[j].child[nd] + (T[j].hi[nd] > T[j].lo[nd] ? 1 : 0);
+      }
       for (int it = 0; it < niter; ++it) {
         for (int j = 0; j < F; ++j) {                        /* sampleIndex(j) */
           double cmu[IIF_MAX_DIM] = {0}, clam[IIF_MAX_DIM];
