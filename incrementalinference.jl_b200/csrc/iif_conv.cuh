@@ -204,7 +204,7 @@ __device__ __noinline__ int sample_measurement(const DeviceGraph& g, const iif_f
 __device__ void block_geodesic_mean(const double* pts, int n, int d, int32_t cm, double* mu_s, double* red,
                                     int& parity) {
   double s[IIF_MAX_DIM] = {0, 0, 0, 0};
-  for (int i = threadIdx.x; i < n; i += IIF_THREADS)
+  for (int i = threadIdx.x; i < n; i += IIF_NT)
     for (int c = 0; c < d; ++c) s[c] += pts[i * d + c];
   block_sum<IIF_MAX_DIM>(s, red, parity);
   if (threadIdx.x == 0) {
@@ -225,7 +225,7 @@ __device__ void block_geodesic_mean(const double* pts, int n, int d, int32_t cm,
 __device__ void block_default_mean(const double* pts, int n, int d, int32_t cm, double* mu, double* red,
                                    int& parity) {
   double s[2 * IIF_MAX_DIM] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < n; i += IIF_THREADS)
+  for (int i = threadIdx.x; i < n; i += IIF_NT)
     for (int c = 0; c < d; ++c) {
       double v = pts[i * d + c];
       if (is_circ(cm, c)) { s[c] += sin(v); s[IIF_MAX_DIM + c] += cos(v); } else s[c] += v;
@@ -241,7 +241,7 @@ __device__ __noinline__ double block_std_basic_spread(const double* pts, int n, 
   if (n < 2) return 1.0;
   block_geodesic_mean(pts, n, d, cm, mu_s, red, parity);
   double acc = 0;
-  for (int i = threadIdx.x; i < n; i += IIF_THREADS)
+  for (int i = threadIdx.x; i < n; i += IIF_NT)
     for (int c = 0; c < d; ++c) {
       double v = mdiff(pts[i * d + c], mu_s[c], is_circ(cm, c));
       acc += v * v;
@@ -303,7 +303,7 @@ __device__ __forceinline__ bool is_prior_kind(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR;
 }
 
-__global__ void __launch_bounds__(IIF_THREADS, 2)
+__global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
 iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double* __restrict__ meas,
                 const int32_t* __restrict__ mhidx_in, const double* __restrict__ uinf,
                 const TreeStruct* __restrict__ trees) {
@@ -484,7 +484,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   }
   // approxConvBelief: manikde!(M, pts; partial) — ApproxConv.jl:31-42
   double bw[IIF_MAX_DIM];
-  block_kde_bandwidth(dest, N, d, cm, trees[N], xa, xb, scr, red, parity, bw);
+  block_kde_bandwidth<0>(dest, N, d, cm, trees[N], xa, xb, scr, red, parity, bw);
   if (n == 0) {
     for (int c = 0; c < IIF_MAX_DIM; ++c) {
       t.out_bw[c] = c < d ? (((pmask >> c) & 1) ? bw[c] : 1.0) : 0.0;

@@ -1,7 +1,7 @@
 // iif_device.cuh — device-side building blocks shared by the convolution and product kernels.
 //
 // Everything here is FP64 (the reference path is Float64 end to end) and written for one CTA
-// of IIF_THREADS threads working on one belief (N <= IIF_MAX_POINTS particles resident in
+// of IIF_NT threads working on one belief (N <= IIF_MAX_POINTS particles resident in
 // shared memory).  Reference citations are to IncrementalInference.jl v0.35.6.
 #pragma once
 #include <cuda_runtime.h>
@@ -9,12 +9,16 @@
 
 #include "../../include/iifb200.h"
 
-#define IIF_THREADS 512
-#define IIF_WARPS (IIF_THREADS / 32)
+// CTAs are launched with 128..512 threads (the host picks per wave: small CTAs for wide, throughput-bound
+// waves, large CTAs for narrow, latency-bound ones); device code reads the size from blockDim.
+#define IIF_MAX_THREADS 512
+#define IIF_MAX_WARPS (IIF_MAX_THREADS / 32)
+#define IIF_NT ((int)blockDim.x)
+#define IIF_NW ((int)(blockDim.x >> 5))
 #define IIF_PI 3.14159265358979323846
 #define IIF_TWO_PI 6.28318530717958647692
 #define IIF_RED_KMAX 8
-#define IIF_RED_DOUBLES (2 * IIF_WARPS * IIF_RED_KMAX)
+#define IIF_RED_DOUBLES (2 * IIF_MAX_WARPS * IIF_RED_KMAX)
 
 // random-stream ids: Philox4x32-10 counter word 1 (same constants as the test oracle)
 enum {
@@ -118,7 +122,7 @@ __device__ __forceinline__ double warp_max(double v) {
 template <int K>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* red, int& parity) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* buf = red + parity * (IIF_WARPS * IIF_RED_KMAX);
+  double* buf = red + parity * (IIF_MAX_WARPS * IIF_RED_KMAX);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double s = warp_sum(v[k]);
@@ -128,8 +132,7 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* red, int& pari
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double s = 0;
-#pragma unroll
-    for (int w = 0; w < IIF_WARPS; ++w) s += buf[w * K + k];
+    for (int w = 0; w < IIF_NW; ++w) s += buf[w * K + k];
     v[k] = s;
   }
   parity ^= 1;
@@ -141,13 +144,12 @@ __device__ __forceinline__ double block_sum1(double x, double* red, int& parity)
 }
 __device__ __forceinline__ double block_min1(double x, double* red, int& parity) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* buf = red + parity * (IIF_WARPS * IIF_RED_KMAX);
+  double* buf = red + parity * (IIF_MAX_WARPS * IIF_RED_KMAX);
   double s = warp_min(x);
   if (lane == 0) buf[warp] = s;
   __syncthreads();
   double m = buf[0];
-#pragma unroll
-  for (int w = 1; w < IIF_WARPS; ++w) m = fmin(m, buf[w]);
+  for (int w = 1; w < IIF_NW; ++w) m = fmin(m, buf[w]);
   parity ^= 1;
   return m;
 }
@@ -305,12 +307,14 @@ __device__ __forceinline__ double loo_thread_sum(const double* __restrict__ x, i
   return acc;
 }
 
+// KTAG gives every kernel its own instantiation (and register budget) of the noinline search code.
+template <int KTAG>
 __device__ __noinline__ double loo_nll(const double* __restrict__ x, int N, int circ, double h, double* scr,
                                        double* red, int* parity_io) {
   const double c = -1.0 / (2.0 * h * h);
   const double lognorm = log((double)(N - 1) * sqrt(IIF_TWO_PI) * h);
   const int Npad = (N + 31) & ~31;
-  int G = IIF_THREADS / Npad;
+  int G = IIF_NT / Npad;
   G = G > IIF_LOO_PARTS ? IIF_LOO_PARTS : G;
   const int seg = threadIdx.x / Npad, i = threadIdx.x - seg * Npad;
   const bool active = (seg < G) && (i < N);
@@ -363,39 +367,41 @@ __device__ __noinline__ double loo_nll(const double* __restrict__ x, int N, int 
 
 // Numerical-Recipes golden section as used by KDE `golden(npd, nLOO_LL, ax, bx, cx, tol)`;
 // the search variable scales the base bandwidth h0.  Uniform control flow across the CTA.
+template <int KTAG>
 __device__ double golden_nr(const double* x, int N, double h0, double ax, double bx, double cx, double tol,
                             double* scr, double* red, int& parity) {
   const double C = (3.0 - sqrt(5.0)) / 2.0, R = 1.0 - C;
   double x0 = ax, x3 = cx, x1, x2;
   if (fabs(cx - bx) > fabs(bx - ax)) { x1 = bx; x2 = bx + C * (cx - bx); }
   else { x2 = bx; x1 = bx - C * (bx - ax); }
-  double f1 = loo_nll(x, N, 0, x1 * h0, scr, red, &parity);
-  double f2 = loo_nll(x, N, 0, x2 * h0, scr, red, &parity);
+  double f1 = loo_nll<KTAG>(x, N, 0, x1 * h0, scr, red, &parity);
+  double f2 = loo_nll<KTAG>(x, N, 0, x2 * h0, scr, red, &parity);
   for (int it = 0; it < 200 && fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2)); ++it) {
     const bool right = f2 < f1;
     double xn;
     if (right) { x0 = x1; x1 = x2; x2 = R * x1 + C * x3; f1 = f2; xn = x2; }
     else { x3 = x2; x2 = x1; x1 = R * x2 + C * x0; f2 = f1; xn = x1; }
-    const double fn = loo_nll(x, N, 0, xn * h0, scr, red, &parity);
+    const double fn = loo_nll<KTAG>(x, N, 0, xn * h0, scr, red, &parity);
     if (right) f2 = fn; else f1 = fn;
   }
   return (f1 < f2) ? x1 : x2;
 }
 
 // Optim.jl GoldenSection on [lo, hi] as used by AMP kde!_CircularNaiveCV
+template <int KTAG>
 __device__ double golden_optim(const double* x, int N, double lo, double hi, double rel_tol, double* scr,
                                double* red, int& parity) {
   const double gr = 0.5 * (3.0 - sqrt(5.0));
   const double abs_tol = 2.220446049250313e-16;
   double xm = lo + gr * (hi - lo);
-  double fm = loo_nll(x, N, 1, xm, scr, red, &parity);
+  double fm = loo_nll<KTAG>(x, N, 1, xm, scr, red, &parity);
   for (int it = 0; it < 200; ++it) {
     double tolx = rel_tol * fabs(xm) + abs_tol;
     double mid = 0.5 * (hi + lo);
     if (fabs(xm - mid) <= 2 * tolx - 0.5 * (hi - lo)) break;
     const bool up = hi - xm > xm - lo;
     const double xn = up ? xm + gr * (hi - xm) : xm - gr * (xm - lo);
-    const double fn = loo_nll(x, N, 1, xn, scr, red, &parity);
+    const double fn = loo_nll<KTAG>(x, N, 1, xn, scr, red, &parity);
     if (up) {
       if (fn < fm) { lo = xm; xm = xn; fm = fn; } else hi = xn;
     } else {
@@ -406,19 +412,20 @@ __device__ double golden_optim(const double* x, int N, double lo, double hi, dou
 }
 
 // Per-dimension bandwidth of the N x d points in `pts` (shared or global memory).
-// xa, xb: shared scratch of N doubles each; scr: IIF_WARPS*N + N doubles.  Result bw[c] is returned
+// xa, xb: shared scratch of N doubles each; scr: IIF_NW*N + N doubles.  Result bw[c] is returned
 // to every thread.
+template <int KTAG>
 __device__ void block_kde_bandwidth(const double* pts, int N, int d, int32_t circ_mask, const TreeStruct& T,
                                     double* xa, double* xb, double* scr, double* red, int& parity, double* bw) {
   for (int c = 0; c < d; ++c) {
     __syncthreads();
-    for (int i = threadIdx.x; i < N; i += IIF_THREADS) xa[i] = pts[i * d + c];
+    for (int i = threadIdx.x; i < N; i += IIF_NT) xa[i] = pts[i * d + c];
     __syncthreads();
     if (is_circ(circ_mask, c)) {
-      bw[c] = golden_optim(xa, N, 1e-3, IIF_TWO_PI, 1e-3, scr, red, parity);
+      bw[c] = golden_optim<KTAG>(xa, N, 1e-3, IIF_TWO_PI, 1e-3, scr, red, parity);
     } else {
       // rank sort (ties by index) -> xb ascending
-      for (int i = threadIdx.x; i < N; i += IIF_THREADS) {
+      for (int i = threadIdx.x; i < N; i += IIF_NT) {
         double xi = xa[i];
         int r = 0;
         for (int k = 0; k < N; ++k) {
@@ -431,14 +438,14 @@ __device__ void block_kde_bandwidth(const double* pts, int N, int d, int32_t cir
       // KDE neighborMinMax: root ball diameter and smallest internal ball diameter (>= 1e-6)
       double maxm = xb[N - 1] - xb[0];
       double m = maxm;
-      for (int z = threadIdx.x; z < T.nn; z += IIF_THREADS) {
+      for (int z = threadIdx.x; z < T.nn; z += IIF_NT) {
         int lo = T.lo[z], hi = T.hi[z];
         if (hi > lo) m = fmin(m, xb[hi] - xb[lo]);
       }
       double minm = block_min1(m, red, parity);
       if (minm < 1e-6) minm = 1e-6;
       double h0 = 0.5 * (minm + maxm);
-      double a = golden_nr(xb, N, h0, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm), 1e-2, scr,
+      double a = golden_nr<KTAG>(xb, N, h0, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm), 1e-2, scr,
                            red, parity);
       bw[c] = a * h0;
     }

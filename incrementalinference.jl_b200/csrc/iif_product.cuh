@@ -69,7 +69,7 @@ __device__ __forceinline__ double cond_gauss(int F, const double* mean, const do
   return lam;
 }
 
-__global__ void __launch_bounds__(IIF_THREADS)
+__global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
 iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const double* __restrict__ randU,
                    const double* __restrict__ randN, const TreeStruct* __restrict__ trees) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -110,26 +110,26 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
   const int32_t fullmask = (1 << d) - 1;
   __shared__ int32_t masks[IIF_MAX_FACTORS];
   if (tid < F) masks[tid] = t.mask[tid] ? t.mask[tid] : fullmask;
-  for (int i = tid; i < F * N * d; i += IIF_THREADS) sm.P[i] = t.dens_pts[i];
-  for (int i = tid; i < F * IIF_MAX_DIM; i += IIF_THREADS) sm.bwk[i] = t.dens_bw[i];
+  for (int i = tid; i < F * N * d; i += IIF_NT) sm.P[i] = t.dens_pts[i];
+  for (int i = tid; i < F * IIF_MAX_DIM; i += IIF_NT) sm.bwk[i] = t.dens_bw[i];
   __syncthreads();
 
   double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
   const bool passthrough = (F == 1 && masks[0] == fullmask);
   if (passthrough) {
     // manifoldProduct of one density returns it unchanged (no Gibbs, no re-bandwidth)
-    for (int i = tid; i < N * d; i += IIF_THREADS) sm.post[i] = sm.P[i];
+    for (int i = tid; i < N * d; i += IIF_NT) sm.post[i] = sm.P[i];
     for (int c = 0; c < d; ++c) bw[c] = sm.bwk[c];
-    if (t.out_labels) for (int s = tid; s < N; s += IIF_THREADS) t.out_labels[s] = s;
+    if (t.out_labels) for (int s = tid; s < N; s += IIF_NT) t.out_labels[s] = s;
     __syncthreads();
   } else {
     // ---- 1. ball trees: per level, rank-sort every node along its most-spread coordinate
     int16_t* permA = sm.perm;
     int16_t* permB = sm.perm + F * N;
-    for (int i = tid; i < F * N; i += IIF_THREADS) permA[i] = (int16_t)(i % N);
+    for (int i = tid; i < F * N; i += IIF_NT) permA[i] = (int16_t)(i % N);
     __syncthreads();
     for (int l = 0; l < L; ++l) {
-      for (int it = tid; it < F * N; it += IIF_THREADS) {
+      for (int it = tid; it < F * N; it += IIF_NT) {
         const int j = it / N, pos = it - j * N;
         const int z = T.lev_off[l] + T.node_at[l * N + pos];
         const int lo = T.lo[z], hi = T.hi[z];
@@ -161,31 +161,50 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
       __syncthreads();
       int16_t* tmp = permA; permA = permB; permB = tmp;
     }
-    // ---- node statistics: mean and (kernel variance + member spread) per level-list entry
-    for (int it = tid; it < F * nn; it += IIF_THREADS) {
-      const int j = it / nn, z = it - j * nn;
-      const int lo = T.lo[z], hi = T.hi[z], cnt = hi - lo + 1;
-      const int16_t* pj = permA + j * N;
-      const double* Pj = sm.P + (size_t)j * N * d;
-      for (int c = 0; c < d; ++c) {
-        double s = 0;
-        for (int i = lo; i <= hi; ++i) s += Pj[pj[i] * d + c];
-        const double m = s / cnt;
+    // ---- node statistics: mean and (kernel variance + member spread) per level-list entry.
+    // Two-pass mean / squared deviation; nodes with more than 32 members are reduced by a whole warp
+    // (lanes stride the members), the rest by one thread each.
+    {
+      const int nbig = (nn > 0) ? min(nn, 8) : 0;  // candidates: the first entries of the list are the large nodes
+      // warp tasks: (density, big node, coordinate)
+      for (int task = warp; task < F * nbig * d; task += IIF_NW) {
+        const int c = task % d, z = (task / d) % nbig, j = task / (d * nbig);
+        const int lo = T.lo[z], hi = T.hi[z], cnt = hi - lo + 1;
+        if (cnt <= 32) continue;
+        const int16_t* pj = permA + j * N;
+        const double* Pj = sm.P + (size_t)j * N * d;
+        double s1 = 0;
+        for (int i = lo + lane; i <= hi; i += 32) s1 += Pj[pj[i] * d + c];
+        s1 = warp_sum(s1);
+        const double m = s1 / cnt;
         double q = 0;
-        for (int i = lo; i <= hi; ++i) { double e = Pj[pj[i] * d + c] - m; q += e * e; }
-        const double h = sm.bwk[j * IIF_MAX_DIM + c];
-        sm.mean[(size_t)it * d + c] = m;
-        sm.var[(size_t)it * d + c] = h * h + q / cnt;
+        for (int i = lo + lane; i <= hi; i += 32) { double e = Pj[pj[i] * d + c] - m; q += e * e; }
+        q = warp_sum(q);
+        if (lane == 0) {
+          const double h = sm.bwk[j * IIF_MAX_DIM + c];
+          sm.mean[((size_t)j * nn + z) * d + c] = m;
+          sm.var[((size_t)j * nn + z) * d + c] = h * h + q / cnt;
+        }
+      }
+      for (int it = tid; it < F * nn; it += IIF_NT) {
+        const int j = it / nn, z = it - j * nn;
+        const int lo = T.lo[z], hi = T.hi[z], cnt = hi - lo + 1;
+        if (z < nbig && cnt > 32) continue;  // done by a warp above
+        const int16_t* pj = permA + j * N;
+        const double* Pj = sm.P + (size_t)j * N * d;
+        for (int c = 0; c < d; ++c) {
+          double s1 = 0;
+          for (int i = lo; i <= hi; ++i) s1 += Pj[pj[i] * d + c];
+          const double m = s1 / cnt;
+          double q = 0;
+          for (int i = lo; i <= hi; ++i) { double e = Pj[pj[i] * d + c] - m; q += e * e; }
+          const double h = sm.bwk[j * IIF_MAX_DIM + c];
+          sm.mean[(size_t)it * d + c] = m;
+          sm.var[(size_t)it * d + c] = h * h + q / cnt;
+        }
       }
     }
-    for (int z = tid; z < nn; z += IIF_THREADS) sm.wt[z] = (double)(T.hi[z] - T.lo[z] + 1) / (double)N;
-    __syncthreads();
-    for (int it = tid; it < F * (L + 1) * d; it += IIF_THREADS) {
-      const int c = it % d, l = (it / d) % (L + 1), j = it / (d * (L + 1));
-      double mv = INFINITY;
-      for (int z = T.lev_off[l]; z < T.lev_off[l + 1]; ++z) mv = fmin(mv, sm.var[((size_t)j * nn + z) * d + c]);
-      sm.minvar[it] = mv;
-    }
+    for (int z = tid; z < nn; z += IIF_NT) sm.wt[z] = (double)(T.hi[z] - T.lo[z] + 1) / (double)N;
     __syncthreads();
 
     // ---- 2./3. multiscale Gibbs: G lanes per output sample (G = largest power of two <= threads/N).
@@ -198,7 +217,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     const uint64_t seed = g.sp->seed;
     const uint32_t call = (uint32_t)t.call_id;
     int G = 1;
-    while (G < 32 && 2 * G * N <= IIF_THREADS) G <<= 1;
+    while (G < 32 && 2 * G * N <= IIF_NT) G <<= 1;  // small CTAs (wide waves): G = 1, least total work
     const int smp = tid / G, gl = tid % G;   // sample, lane within the group
     const bool live = smp < N;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
@@ -230,30 +249,35 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
             const double* mj = sm.mean + ((size_t)j * nn + z0) * d;
             const double* vj = sm.var + ((size_t)j * nn + z0) * d;
             const double* wj = sm.wt + z0;
-            // exponent p_z = sum_c dl^2 / v + log v ; bound: leaf level v is the same for every
-            // candidate (kernel variance), internal levels use the level's smallest node variance
+            // weight_z = wt_z * prod_c rsqrt(v) * exp(-1/2 sum_c dl^2 / v),  v = var_z + cvar  (the oracle's
+            // exp(-(p_z - min p)/2) with p_z = sum dl^2/v + log v, up to the common factor).  At the leaf
+            // level v is the same for every candidate, so 1/v is hoisted and rsqrt(v) cancels.
             double iv[IIF_MAX_DIM] = {0, 0, 0, 0};
-            double Lb = 0.0;
-            for (int c = 0; c < d; ++c) {
-              if (!has[c]) continue;
-              if (leaf) iv[c] = 1.0 / (vj[c] + cvar[c]);
-              else Lb += log(sm.minvar[((size_t)j * (L + 1) + l) * d + c] + cvar[c]);
-            }
-            auto expo = [&](int z) -> double {  // p_z - (leaf ? sum log v : 0)
+            for (int c = 0; c < d; ++c)
+              if (has[c] && leaf) iv[c] = 1.0 / (vj[c] + cvar[c]);
+            // returns the exponent (>= 0) and the prefactor of candidate z
+            auto cand = [&](int z, double& pre) -> double {
               double p = 0.0;
+              pre = wj[z];
               for (int c = 0; c < d; ++c) {
                 if (!has[c]) continue;
                 const double dl = mdiff(mj[z * d + c], cmu[c], is_circ(cm, c));
                 if (leaf) p = fma(dl * dl, iv[c], p);
                 else {
-                  const double v = vj[z * d + c] + cvar[c];
-                  p += dl * dl / v + log(v);
+                  const double rs = rsqrt(vj[z * d + c] + cvar[c]);
+                  p = fma(dl * dl, rs * rs, p);
+                  pre *= rs;
                 }
               }
               return p;
             };
+            auto weight = [&](int z, double base) -> double {
+              double pre;
+              const double p = cand(z, pre);
+              return exp_neg(fmin(-0.5 * (p - base), 0.0)) * pre;
+            };
             double ct[16];
-            double Tl = 0.0, off = 0.0, tot = 0.0, base = leaf ? 0.0 : Lb;
+            double Tl = 0.0, off = 0.0, tot = 0.0, base = 0.0;
             for (int attempt = 0; attempt < 2; ++attempt) {
               Tl = 0.0;
 #pragma unroll
@@ -262,7 +286,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
                 double sacc = 0.0;
                 if (cb < ze) {
                   const int ce = min(cb + CH, ze);
-                  for (int z = cb; z < ce; ++z) sacc += exp_neg(fmin(-0.5 * (expo(z) - base), 0.0)) * wj[z];
+                  for (int z = cb; z < ce; ++z) sacc += weight(z, base);
                 }
                 ct[ch] = sacc;
                 Tl += sacc;
@@ -278,7 +302,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
               if (tot > 1e-280 || attempt == 1) break;
               // every weight underflowed: redo relative to the exact minimum exponent
               double pm = INFINITY;
-              for (int z = zb; z < ze; ++z) pm = fmin(pm, expo(z));
+              for (int z = zb; z < ze; ++z) { double pre; pm = fmin(pm, cand(z, pre)); }
               for (int o = G >> 1; o > 0; o >>= 1) pm = fmin(pm, __shfl_xor_sync(gmask, pm, o, G));
               base = pm;
             }
@@ -304,7 +328,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
                       double cum = run;
                       pick = ce - 1;
                       for (int z = cb; z < ce; ++z) {
-                        cum += exp_neg(fmin(-0.5 * (expo(z) - base), 0.0)) * wj[z];
+                        cum += weight(z, base);
                         if (thr < cum) { pick = z; break; }
                       }
                       found = true;
@@ -352,16 +376,16 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     }
     __syncthreads();
     // ---- 4. re-bandwidth of the posterior (getKDEManifoldBandwidths on the result)
-    block_kde_bandwidth(sm.post, N, d, cm, T, sm.xa, sm.xb, sm.scr, sm.red, parity, bw);
+    block_kde_bandwidth<1>(sm.post, N, d, cm, T, sm.xa, sm.xb, sm.scr, sm.red, parity, bw);
   }
 
   // ---- outputs: explicit buffers and / or setBelief! into the destination slot
   if (t.out_pts != nullptr)
-    for (int i = tid; i < N * d; i += IIF_THREADS) t.out_pts[i] = sm.post[i];
+    for (int i = tid; i < N * d; i += IIF_NT) t.out_pts[i] = sm.post[i];
   if (t.out_bw != nullptr && tid < IIF_MAX_DIM) t.out_bw[tid] = tid < d ? bw[tid] : 0.0;
   if (t.out_slot >= 0) {
     const iif_slot_desc O = g.slots[t.out_slot];
-    for (int i = tid; i < N * d; i += IIF_THREADS) g.pts[O.pts_off + i] = sm.post[i];
+    for (int i = tid; i < N * d; i += IIF_NT) g.pts[O.pts_off + i] = sm.post[i];
     if (tid < IIF_MAX_DIM) {
       g.bw[t.out_slot * IIF_MAX_DIM + tid] = tid < d ? bw[tid] : 0.0;
       g.ipc[t.out_slot * IIF_MAX_DIM + tid] = tid < d ? (double)F : 0.0;  // ApproxConv.jl:296-300
@@ -398,7 +422,7 @@ struct BwTask {
   double* out_bw;
   int32_t N, dim, circ_mask, _pad;
 };
-__global__ void __launch_bounds__(IIF_THREADS)
+__global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
 iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restrict__ trees) {
   extern __shared__ __align__(16) double bw_smem[];  // conv_smem_bytes(N)
   __shared__ double red[IIF_RED_DOUBLES];
@@ -408,9 +432,9 @@ iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restr
   double* xa = pts + (size_t)t.N * IIF_MAX_DIM;
   double* xb = xa + t.N;
   double* scr = xb + t.N;
-  for (int i = threadIdx.x; i < t.N * t.dim; i += IIF_THREADS) pts[i] = t.pts[i];
+  for (int i = threadIdx.x; i < t.N * t.dim; i += IIF_NT) pts[i] = t.pts[i];
   __syncthreads();
   double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
-  block_kde_bandwidth(pts, t.N, t.dim, t.circ_mask, trees[t.N], xa, xb, scr, red, parity, bw);
+  block_kde_bandwidth<2>(pts, t.N, t.dim, t.circ_mask, trees[t.N], xa, xb, scr, red, parity, bw);
   if (threadIdx.x < IIF_MAX_DIM) t.out_bw[threadIdx.x] = threadIdx.x < t.dim ? bw[threadIdx.x] : 0.0;
 }

@@ -26,6 +26,7 @@ struct TreeHost {
 struct Wave {
   int conv0 = 0, nconv = 0, prod0 = 0, nprod = 0, copy0 = 0, ncopy = 0;
   size_t prod_smem = 0, conv_smem = 0;
+  int maxN = 2;
 };
 
 struct Schedule {
@@ -66,6 +67,7 @@ struct iifb200_ctx {
   std::vector<Schedule*> schedules;
   int64_t launches = 0;
   int max_smem_optin = 0;
+  int num_sms = 148;
 };
 
 #define CK(call)                                                                       \
@@ -177,6 +179,7 @@ int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
   if ((e = cudaMemcpy(ctx->d_sp, &ctx->sp, sizeof(iif_solver_params), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
   ctx->dg.sp = ctx->d_sp;
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_ordinal);
+  cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device_ordinal);
   if ((e = cudaFuncSetAttribute(iif_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ctx->max_smem_optin - 4096)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(product smem)", e);
@@ -428,6 +431,14 @@ int32_t iifb200_slot_device_ptr(iifb200_ctx* ctx, int32_t slot, void** pts_ptr, 
 }
 
 // ---- helpers -------------------------------------------------------------------------------
+// CTA size of a launch: wide (throughput-bound) launches use the smallest CTA that still gives every
+// particle its own thread, so several CTAs share an SM and no warp idles in the per-particle stages;
+// narrow (latency-bound) launches use 512 threads to split each belief's work further.
+static int pick_threads(iifb200_ctx* ctx, int grid, int maxN, int small_min = 128) {
+  int small = std::max(small_min, (maxN + 31) / 32 * 32);
+  return (grid >= 2 * ctx->num_sms) ? small : IIF_MAX_THREADS;
+}
+
 static bool is_prior_kind_h(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR;
 }
@@ -452,10 +463,12 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
   std::vector<int64_t> poff(K + 1, 0), noff(K + 1, 0);
   int64_t n_meas = 0, n_lab = 0, n_uinf = 0;
   size_t csmem = 0;
+  int cmaxN = 2;
   for (int k = 0; k < K; ++k) {
     int32_t st = validate_conv(ctx, ops[k]);
     if (st != IIF_OK) return st;
     csmem = std::max(csmem, conv_smem_bytes(ops[k].N));
+    cmaxN = std::max(cmaxN, (int)ops[k].N);
     const iif_factor_desc& F = ctx->factors[ops[k].factor];
     const int d = ctx->slots[F.slot[ops[k].sfidx - 1]].dim;
     poff[k + 1] = poff[k] + (int64_t)ops[k].N * d;
@@ -491,7 +504,7 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ConvTask) * K, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_conv_kernel<<<K, IIF_THREADS, csmem, ctx->stream>>>(ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
+  iif_conv_kernel<<<K, pick_threads(ctx, K, cmaxN), csmem, ctx->stream>>>(ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -526,6 +539,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
   std::vector<int64_t> doff(V + 1, 0), foff(V + 1, 0), ooff(V + 1, 0), loff(V + 1, 0);
   int64_t n_u = 0, n_n = 0;
   size_t smem = 0;
+  int pmaxN = 2;
   for (int v = 0; v < V; ++v) {
     const iif_product_op& o = ops[v];
     if (o.dim < 1 || o.dim > IIF_MAX_DIM || o.nfactors < 1 || o.nfactors > IIF_MAX_FACTORS)
@@ -540,6 +554,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
     if (o.randu_off >= 0) n_u = std::max<int64_t>(n_u, o.randu_off + (int64_t)o.N * L * ctx->sp.gibbsNiter * o.nfactors);
     if (o.randn_off >= 0) n_n = std::max<int64_t>(n_n, o.randn_off + (int64_t)o.N * o.dim);
     smem = std::max(smem, prod_smem_bytes(o.nfactors, o.N, o.dim, ctx->trees[o.N].nn, ctx->trees[o.N].L));
+    pmaxN = std::max(pmaxN, (int)o.N);
   }
   if ((n_u && !randU) || (n_n && !randN)) return fail(ctx, IIF_ERR_ARG, "product_batch: explicit stream offset given but array is NULL");
   if ((int)smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "product op exceeds the shared-memory budget (F*N*d too large)");
@@ -581,7 +596,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ProdTask) * V, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_product_kernel<<<V, IIF_THREADS, smem, ctx->stream>>>(ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
+  iif_product_kernel<<<V, IIF_MAX_THREADS, smem, ctx->stream>>>(ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -603,11 +618,13 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   CK(cudaSetDevice(ctx->device));
   std::vector<int64_t> off(K + 1, 0);
   size_t bsmem = 0;
+  int bmaxN = 2;
   for (int k = 0; k < K; ++k) {
     if (dim[k] < 1 || dim[k] > IIF_MAX_DIM) return fail(ctx, IIF_ERR_ARG, "kde_bandwidth: dim out of range");
     int32_t st = ensure_tree(ctx, N[k]);
     if (st != IIF_OK) return st;
     bsmem = std::max(bsmem, conv_smem_bytes(N[k]));
+    bmaxN = std::max(bmaxN, (int)N[k]);
     off[k + 1] = off[k] + (int64_t)N[k] * dim[k];
   }
   double *d_pts = nullptr, *d_bw = nullptr;
@@ -620,7 +637,7 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   CK(cudaMemcpyAsync(d_pts, pts, sizeof(double) * off[K], cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_t, t.data(), sizeof(BwTask) * K, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_bandwidth_kernel<<<K, IIF_THREADS, bsmem, ctx->stream>>>(d_t, ctx->d_trees);
+  iif_bandwidth_kernel<<<K, pick_threads(ctx, K, bmaxN), bsmem, ctx->stream>>>(d_t, ctx->d_trees);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -713,6 +730,7 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
         t.out_status = s->d_status + s->nconv + o.a;
         pt.push_back(t);
         W.conv_smem = std::max(W.conv_smem, conv_smem_bytes(P.N));
+        W.maxN = std::max(W.maxN, P.N);
         W.prod_smem = std::max(W.prod_smem, prod_smem_bytes(P.nfactors, P.N, S.dim, ctx->trees[P.N].nn, ctx->trees[P.N].L));
       } else return fail(ctx, IIF_ERR_ARG, "schedule: unknown op kind");
     }
@@ -754,11 +772,11 @@ static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int*
       ++k;
     }
     if (W.nconv) {
-      iif_conv_kernel<<<W.nconv, IIF_THREADS, W.conv_smem, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      iif_conv_kernel<<<W.nconv, pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
       ++k;
     }
     if (W.nprod) {
-      iif_product_kernel<<<W.nprod, IIF_THREADS, W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      iif_product_kernel<<<W.nprod, IIF_MAX_THREADS, W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
       ++k;
     }
   }
@@ -823,12 +841,12 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
     }
     if (W.nconv) {
       mark();
-      iif_conv_kernel<<<W.nconv, IIF_THREADS, W.conv_smem, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      iif_conv_kernel<<<W.nconv, pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(0); blocks[0] += W.nconv;
     }
     if (W.nprod) {
       mark();
-      iif_product_kernel<<<W.nprod, IIF_THREADS, W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      iif_product_kernel<<<W.nprod, IIF_MAX_THREADS, W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(1); blocks[1] += W.nprod;
     }
   }
