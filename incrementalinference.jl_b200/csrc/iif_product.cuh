@@ -45,9 +45,17 @@ struct ProdSmem {
   int16_t* perm;  // 2*F*N
 };
 
+// F == 2 products tabulate the level's pair-weight matrix (N^2 doubles at the leaf level) in the scratch
+// region shared with the leave-one-out tile
+#define IIF_GIBBS_TAB_MAX 150
+__host__ __device__ inline bool gibbs_tab(int N) { return N <= IIF_GIBBS_TAB_MAX; }
+
 __host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn, int L) {
   size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + 2 * (size_t)N + IIF_RED_DOUBLES +
-               (size_t)F * IIF_MAX_DIM + (size_t)IIF_LOO_SCRATCH_N(N) + (size_t)nn + (size_t)F * (L + 1) * d;
+               (size_t)F * IIF_MAX_DIM + (size_t)nn + (size_t)F * (L + 1) * d;
+  size_t scr = (size_t)IIF_LOO_SCRATCH_N(N);
+  if (F == 2 && gibbs_tab(N) && (size_t)N * N > scr) scr = (size_t)N * N;
+  dbl += scr;
   size_t i16 = 2 * (size_t)F * N;
   return dbl * sizeof(double) + ((i16 * sizeof(int16_t) + 7) / 8) * 8;
 }
@@ -101,10 +109,15 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     sm.xa = p; p += N;
     sm.xb = p; p += N;
     sm.red = p; p += IIF_RED_DOUBLES;
-    sm.scr = p; p += (size_t)IIF_LOO_SCRATCH_N(N);
     sm.bwk = p; p += F * IIF_MAX_DIM;
     sm.wt = p; p += nn;
     sm.minvar = p; p += (size_t)F * (L + 1) * d;
+    sm.scr = p;  // last: loo scratch, aliased by the F == 2 pair-weight matrix (sized by prod_smem_bytes)
+    {
+      size_t scrn = (size_t)IIF_LOO_SCRATCH_N(N);
+      if (F == 2 && gibbs_tab(N) && (size_t)N * N > scrn) scrn = (size_t)N * N;
+      p += scrn;
+    }
     sm.perm = reinterpret_cast<int16_t*>(p);
   }
   const int32_t fullmask = (1 << d) - 1;
@@ -222,10 +235,103 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     const bool live = smp < N;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     // whole warps without a sample skip; partial groups never occur (G divides 32)
-    if (live) {
-      const int s = smp;
-      int node[IIF_MAX_FACTORS];
-      for (int j = 0; j < F; ++j) node[j] = 0;  // roots
+    const int s = smp;
+    int node[IIF_MAX_FACTORS];
+    for (int j = 0; j < F; ++j) node[j] = 0;  // roots
+    const bool tab = (F == 2) && gibbs_tab(N);
+    if (tab) {
+      // ---- F == 2: the conditional of one density depends only on the node selected in the other, so the
+      // level's pair-weight matrix K[a][b] = prod_c rsqrt(va+vb) exp(-(ma-mb)^2 / 2(va+vb)) is tabulated ONCE
+      // per level by the whole CTA (shared with the leave-one-out tile) and every sample's two label draws
+      // become a weighted column / row scan of K — no transcendental per sample.
+      double* K = sm.scr;
+      const int32_t both = masks[0] & masks[1];
+      const double* m0 = sm.mean;
+      const double* m1 = sm.mean + (size_t)nn * d;
+      const double* v0 = sm.var;
+      const double* v1 = sm.var + (size_t)nn * d;
+      for (int l = 1; l <= L; ++l) {
+        const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
+        for (int j = 0; j < 2; ++j) {  // levelDown: follow the last child, leaves stay
+          const int nd = node[j];
+          node[j] = z0 + T.child[nd] + (T.hi[nd] > T.lo[nd] ? 1 : 0);
+        }
+        __syncthreads();  // the previous level's K is no longer read
+        for (int idx = tid; idx < nz * nz; idx += IIF_NT) {
+          const int a = idx / nz, b = idx - a * nz;
+          double pexp = 0.0, pre = 1.0;
+          for (int c = 0; c < d; ++c) {
+            if (!((both >> c) & 1)) continue;
+            const double dl = mdiff(m0[(z0 + a) * d + c], m1[(z0 + b) * d + c], is_circ(cm, c));
+            const double rs = rsqrt(v0[(z0 + a) * d + c] + v1[(z0 + b) * d + c]);
+            pexp = fma(dl * dl, rs * rs, pexp);
+            pre *= rs;
+          }
+          K[idx] = exp_neg(-0.5 * pexp) * pre;
+        }
+        __syncthreads();
+        if (live) {
+          const double* wl = sm.wt + z0;
+          const int B = (nz + G - 1) / G;
+          const int zb = gl * B, ze = min(zb + B, nz);
+          for (int it = 0; it < niter; ++it) {
+            for (int j = 0; j < 2; ++j) {
+              // density 0 scans column b of K (stride nz), density 1 scans row a (stride 1)
+              const int other = node[1 - j] - z0;
+              const double* Kb = (j == 0) ? K + other : K + (size_t)other * nz;
+              const int stride = (j == 0) ? nz : 1;
+              double Tl = 0.0;
+              for (int z = zb; z < ze; ++z) Tl += wl[z] * Kb[(size_t)z * stride];
+              double inc = Tl;
+              for (int o = 1; o < G; o <<= 1) {
+                const double y = __shfl_up_sync(gmask, inc, o, G);
+                if (gl >= o) inc += y;
+              }
+              const double off = inc - Tl;
+              const double tot = __shfl_sync(gmask, inc, G - 1, G);
+              const uint32_t idx = (uint32_t)(((s * L + (l - 1)) * niter + it) * 2 + j);
+              const double u = (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx]
+                                                                      : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
+              int pick;
+              if (tot > 1e-290) {
+                const double thr = u * tot;
+                int mypick = -1;
+                if ((zb < ze) && (thr >= off) && (thr < off + Tl)) {
+                  double cum = off;
+                  mypick = ze - 1;
+                  for (int z = zb; z < ze; ++z) {
+                    cum += wl[z] * Kb[(size_t)z * stride];
+                    if (thr < cum) { mypick = z; break; }
+                  }
+                }
+                const unsigned hit = __ballot_sync(gmask, mypick >= 0) & gmask;
+                pick = nz - 1;
+                if (hit) pick = __shfl_sync(gmask, mypick, (__ffs(hit) - 1) & (G - 1), G);
+              } else {
+                // every pair weight underflowed: relative to the smallest exponent (what the oracle does) the
+                // closest candidate carries all the mass
+                double best = INFINITY;
+                int bz = 0;
+                for (int z = 0; z < nz; ++z) {
+                  const int a = (j == 0) ? z : other, b = (j == 0) ? other : z;
+                  double pexp = 0.0;
+                  for (int c = 0; c < d; ++c) {
+                    if (!((both >> c) & 1)) continue;
+                    const double dl = mdiff(m0[(z0 + a) * d + c], m1[(z0 + b) * d + c], is_circ(cm, c));
+                    const double v = v0[(z0 + a) * d + c] + v1[(z0 + b) * d + c];
+                    pexp += dl * dl / v + log(v);
+                  }
+                  if (pexp < best) { best = pexp; bz = z; }
+                }
+                pick = bz;
+              }
+              node[j] = z0 + pick;
+            }
+          }
+        }
+      }
+      __syncthreads();  // K (aliases the leave-one-out scratch) is dead from here on
+    } else if (live) {
       for (int l = 1; l <= L; ++l) {
         const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
         const bool leaf = (l == L);
@@ -235,7 +341,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         }
         const int B = (nz + G - 1) / G;
         const int zb = gl * B, ze = min(zb + B, nz);
-        const int CH = max(8, (B + 15) >> 4);
+        const int CH = (B + 15) >> 4;  // <= 16 chunks per lane; CH == 1 (B <= 16) needs no re-evaluation
         for (int it = 0; it < niter; ++it) {
           for (int j = 0; j < F; ++j) {  // sampleIndex(j)
             double cmu[IIF_MAX_DIM] = {0, 0, 0, 0}, cvar[IIF_MAX_DIM] = {0, 0, 0, 0};
@@ -310,39 +416,41 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
             const double u = (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx]
                                                                     : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
             const double thr = u * tot;
-            const bool mine = (zb < ze) && (thr >= off) && (thr < off + Tl);
-            const unsigned hit = __ballot_sync(gmask, mine) & gmask;
-            int pick = nz - 1;  // rounding left thr >= total: the oracle falls back to the last candidate
-            if (hit) {
-              const int owner = __ffs(hit) - 1;  // lane index within the warp
-              if (lane == owner) {
-                double run = off;
-                pick = ze - 1;
-                bool found = false;
+            // every lane searches its own chunks (no divergent owner path); exactly one lane finds the crossing
+            int mypick = -1;
+            if ((zb < ze) && (thr >= off) && (thr < off + Tl)) {
+              double run = off;
+              mypick = ze - 1;
+              bool found = false;
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch) {
-                  const int cb = zb + ch * CH;
-                  if (!found && cb < ze) {
-                    if (thr < run + ct[ch]) {
-                      const int ce = min(cb + CH, ze);
+              for (int ch = 0; ch < 16; ++ch) {
+                const int cb = zb + ch * CH;
+                if (!found && cb < ze) {
+                  if (thr < run + ct[ch]) {
+                    const int ce = min(cb + CH, ze);
+                    mypick = ce - 1;
+                    if (CH > 1) {
                       double cum = run;
-                      pick = ce - 1;
                       for (int z = cb; z < ce; ++z) {
                         cum += weight(z, base);
-                        if (thr < cum) { pick = z; break; }
+                        if (thr < cum) { mypick = z; break; }
                       }
-                      found = true;
                     }
-                    run += ct[ch];
+                    found = true;
                   }
+                  run += ct[ch];
                 }
               }
-              pick = __shfl_sync(gmask, pick, owner & (G - 1), G);
             }
+            const unsigned hit = __ballot_sync(gmask, mypick >= 0) & gmask;
+            int pick = nz - 1;  // rounding left thr >= total: the oracle falls back to the last candidate
+            if (hit) pick = __shfl_sync(gmask, mypick, (__ffs(hit) - 1) & (G - 1), G);
             node[j] = z0 + pick;
           }
         }
       }
+    }
+    if (live) {
       // samplePoint: draw from the product of the selected leaf kernels
       if (gl == 0) {
         for (int c = 0; c < d; ++c) {
