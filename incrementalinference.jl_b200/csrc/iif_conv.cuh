@@ -33,6 +33,9 @@ struct ConvTask {
   int32_t* out_mhidx;  // N or NULL
   int32_t* out_nan;    // 1 or NULL
   int32_t* out_status; // 1 or NULL (device-side error code for this task)
+  int32_t out_slot;    // >= 0: single-factor propagateBelief — the proposal IS the posterior (manifoldProduct of
+                       // one density is a pass-through), so it is written straight into this belief slot
+  int32_t _pad;
 };
 
 __host__ __device__ inline size_t conv_smem_bytes(int N) {
@@ -489,6 +492,19 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
     for (int c = 0; c < IIF_MAX_DIM; ++c) {
       t.out_bw[c] = c < d ? (((pmask >> c) & 1) ? bw[c] : 1.0) : 0.0;
       t.out_ipc[c] = c < d ? (((pmask >> c) & 1) ? 1.0 : 0.0) : 0.0;
+    }
+  }
+  if (t.out_slot >= 0) {  // setBelief! of a one-factor propagateBelief (SolveTree.jl:74)
+    const iif_slot_desc O = g.slots[t.out_slot];
+    if (active)
+      for (int c = 0; c < d; ++c) g.pts[O.pts_off + n * d + c] = dest[n * d + c];
+    if (n < IIF_MAX_DIM) {
+      g.bw[t.out_slot * IIF_MAX_DIM + n] = n < d ? bw[n] : 0.0;
+      g.ipc[t.out_slot * IIF_MAX_DIM + n] = n < d ? 1.0 : 0.0;
+    }
+    if (n == 0) {
+      g.npts[t.out_slot] = N;
+      g.flags[t.out_slot] |= 1;
     }
   }
 }

@@ -501,6 +501,7 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
     t.out_mhidx = d_lab + noff[k];
     t.out_nan = d_misc + k;
     t.out_status = d_misc + K + k;
+    t.out_slot = -1;
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ConvTask) * K, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -718,9 +719,14 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
           c.out_ipc = bwbase + (int64_t)(P.nfactors + f) * IIF_MAX_DIM;
           c.out_mhidx = nullptr; c.out_nan = nullptr;
           c.out_status = s->d_status + cidx[o.a] + f;
+          // one full-dimension factor: the convolution writes the posterior itself, no product task
+          c.out_slot = (P.nfactors == 1 && F.partial_mask == 0) ? P.out_slot : -1;
           ct.push_back(c);
           t.mask[f] = F.partial_mask;
         }
+        W.conv_smem = std::max(W.conv_smem, conv_smem_bytes(P.N));
+        W.maxN = std::max(W.maxN, P.N);
+        if (P.nfactors == 1 && ctx->factors[P.factor[0]].partial_mask == 0) continue;
         t.dim = S.dim; t.circ_mask = S.circ_mask; t.F = P.nfactors; t.N = P.N;
         t.call_id = P.call_id; t.randu_off = t.randn_off = -1;
         t.target_slot = P.target_slot; t.out_slot = P.out_slot;
@@ -729,8 +735,6 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
         t.conv_status = s->d_status + cidx[o.a];
         t.out_status = s->d_status + s->nconv + o.a;
         pt.push_back(t);
-        W.conv_smem = std::max(W.conv_smem, conv_smem_bytes(P.N));
-        W.maxN = std::max(W.maxN, P.N);
         W.prod_smem = std::max(W.prod_smem, prod_smem_bytes(P.nfactors, P.N, S.dim, ctx->trees[P.N].nn, ctx->trees[P.N].L));
       } else return fail(ctx, IIF_ERR_ARG, "schedule: unknown op kind");
     }

@@ -82,7 +82,8 @@ def test_schedule_parity_gauss_seidel(built):
     eng.download_arena(ag)
     n_launch = eng.launch_count()
     eng.close()
-    assert n_launch == 2 * len(sched)
+    # one conv kernel per wave + one product kernel per wave that holds a multi-factor propagate
+    assert len(sched) <= n_launch <= 2 * len(sched)
     PC.assert_arena_equal("schedule", orc.arena, ag, P.frozen, xs)
 
 
