@@ -39,7 +39,7 @@ struct ConvTask {
 };
 
 __host__ __device__ inline size_t conv_smem_bytes(int N) {
-  return sizeof(double) * ((size_t)N * IIF_MAX_DIM + 2 * (size_t)N + (size_t)loo_scratch_doubles(N));
+  return sizeof(double) * ((size_t)N * IIF_MAX_DIM + (size_t)N + (size_t)loo_x2_doubles(N) + (size_t)loo_scratch_doubles(N));
 }
 
 struct HypoRecipe {  // HypoRecipe, src/entities/HypoRecipe.jl:4-9 (elements are implicit: mhidx == hyp)
@@ -324,8 +324,8 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   int parity = 0;
   double* dest = conv_smem;                         // N * IIF_MAX_DIM
   double* xa = dest + (size_t)op.N * IIF_MAX_DIM;   // N
-  double* xb = xa + op.N;                           // N
-  double* scr = xb + op.N;                          // loo_scratch_doubles(N)
+  double* xb = xa + op.N;                           // loo_x2_doubles(N)
+  double* scr = xb + loo_x2_doubles(op.N);          // loo_scratch_doubles(N)
   if (n == 0) {
     f = g.factors[op.factor];
     s_status = IIF_OK;
@@ -487,7 +487,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   }
   // approxConvBelief: manikde!(M, pts; partial) — ApproxConv.jl:31-42
   double bw[IIF_MAX_DIM];
-  block_kde_bandwidth<0>(dest, N, d, cm, trees[N], xa, xb, scr, red, parity, bw);
+  block_kde_bandwidth<0>(dest, N, d, cm, &trees[N], xa, xb, scr, red, &parity, bw);
   if (n == 0) {
     for (int c = 0; c < IIF_MAX_DIM; ++c) {
       t.out_bw[c] = c < d ? (((pmask >> c) & 1) ? bw[c] : 1.0) : 0.0;

@@ -20,6 +20,41 @@
 #define IIF_RED_KMAX 8
 #define IIF_RED_DOUBLES (2 * IIF_MAX_WARPS * IIF_RED_KMAX)
 
+// Phase clocks for kernel development (profiles/phase_probe.py builds a copy of the library with
+// -DIIF_PHASES; compiled out of the product library): thread IIF_PHASE_TID of block 0 accumulates the
+// clock64() time between consecutive marks.
+#ifdef IIF_PHASES
+#ifndef IIF_PHASE_TID
+#define IIF_PHASE_TID 0
+#endif
+__device__ long long g_iif_phase[16];
+__shared__ long long s_iif_phase[16];  // shared accumulators: a mark costs one LDS/STS round trip, not a global one
+#define IIF_PHASE_BEGIN() long long ph_t_ = clock64()
+#define IIF_PHASE(k)                                             \
+  do {                                                           \
+    if (threadIdx.x == IIF_PHASE_TID && blockIdx.x == 0) {       \
+      const long long t_ = clock64();                            \
+      s_iif_phase[k] += t_ - ph_t_;                              \
+      ph_t_ = clock64();                                         \
+    }                                                            \
+  } while (0)
+#define IIF_PHASE_ZERO()                                                                        \
+  do {                                                                                          \
+    if (threadIdx.x == IIF_PHASE_TID && blockIdx.x == 0)                                        \
+      for (int k_ = 0; k_ < 16; ++k_) s_iif_phase[k_] = 0;                                      \
+  } while (0)
+#define IIF_PHASE_FLUSH()                                                                       \
+  do {                                                                                          \
+    if (threadIdx.x == IIF_PHASE_TID && blockIdx.x == 0)                                        \
+      for (int k_ = 0; k_ < 16; ++k_) g_iif_phase[k_] += s_iif_phase[k_];                       \
+  } while (0)
+#else
+#define IIF_PHASE_BEGIN()
+#define IIF_PHASE(k)
+#define IIF_PHASE_ZERO()
+#define IIF_PHASE_FLUSH()
+#endif
+
 // random-stream ids: Philox4x32-10 counter word 1 (same constants as the test oracle)
 enum {
   IIF_RS_MEAS = 1,
@@ -155,70 +190,134 @@ __device__ __forceinline__ double block_min1(double x, double* red, int& parity)
 }
 
 // ------------------------------------------------------------------------------------------
-// exp(x) for x <= 0 in FP64 (the only use on this path: Gaussian kernel weights).  Cody-Waite
-// range reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor/Horner (truncation 4e-18) with
-// the coefficients taken straight from the constant bank (no 64-bit immediates to materialise),
-// two-step power-of-two scaling so results down to the denormal range stay correct.
+// exp(x) for x <= 0 in FP64 (the only use on this path: Gaussian kernel weights).
+//   x = k ln2 + r, |r| <= ln2/2 (one FMA against the double nearest ln2: the reduction error
+//   |k| 2.3e-17 is below one ulp of the result wherever the result matters), degree-11 minimax
+//   polynomial 1 + r + r^2 q(r) (approximation error 1.3e-17, coefficients below from a Chebyshev fit
+//   of (e^r - 1 - r)/r^2, read straight from the constant bank), and 2^k applied by an integer add
+//   on the exponent field.  Arguments below -708 (subnormal results), -inf and NaN take the careful
+//   path (two-step power-of-two scaling, exact gradual underflow like libm).
 // ------------------------------------------------------------------------------------------
 __constant__ double IIF_EXPC[16] = {
-    1.6059043836821613e-10, 2.08767569878681e-09,  2.505210838544172e-08,  2.755731922398589e-07,
-    2.7557319223985893e-06, 2.48015873015873e-05,  1.984126984126984e-04,  1.388888888888889e-03,
-    8.333333333333333e-03,  4.1666666666666664e-02, 1.6666666666666666e-01, 0.5,
-    1.4426950408889634074,  -6.93147180369123816490e-01, -1.90821492927058770002e-10, 6755399441055744.0};
+    2.510037583256132e-08,  2.762007587998348e-07,  2.7557268480310024e-06, 2.4801521322368692e-05,
+    1.9841269863040545e-04, 1.3888888917196719e-03, 8.333333333330065e-03,  4.1666666666624164e-02,
+    1.6666666666666669e-01, 5.000000000000001e-01,  0.0,                    0.0,
+    1.4426950408889634074,  -6.931471805599453094e-01, 0.0,                 6755399441055744.0};
+#define IIF_EXP_NQ 10  // coefficients of q, highest degree first
 
-__device__ __forceinline__ double exp_neg(double x) {
-  double t = fma(x, IIF_EXPC[12], IIF_EXPC[15]);
-  const int k = __double2loint(t);
-  t -= IIF_EXPC[15];
-  double r = fma(t, IIF_EXPC[13], x);
-  r = fma(t, IIF_EXPC[14], r);
-  double p = IIF_EXPC[0];
-#pragma unroll
-  for (int c = 1; c < 12; ++c) p = fma(p, r, IIF_EXPC[c]);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  // 2^k in two normal-range factors; k clamped so that anything below the denormal range is 0
+__device__ __forceinline__ double exp_scale2(double p, int k) {  // p * 2^k, any k <= 0, gradual underflow
   const int kc = max(k, -1100), k1 = kc >> 1, k2 = kc - k1;
   const double s1 = __hiloint2double((k1 + 1023) << 20, 0);
   const double s2 = __hiloint2double((k2 + 1023) << 20, 0);
   return (p * s1) * s2;
 }
 
-// Four exponentials in lockstep: every polynomial step is issued for all four arguments before the
-// next one, so the four FP64 dependency chains interleave and each coefficient is fetched once.
-__device__ __forceinline__ void exp_neg4(const double (&x)[4], double (&out)[4]) {
-  const double L2E = IIF_EXPC[12], LN2H = IIF_EXPC[13], LN2L = IIF_EXPC[14], MAGIC = IIF_EXPC[15];
-  double t[4], r[4], p[4];
-  int k[4];
+__device__ __forceinline__ double exp_neg(double x) {  // careful scalar form
+  if (x < -1000.0) return 0.0;                         // also -inf; NaN falls through and propagates
+  double t = fma(x, IIF_EXPC[12], IIF_EXPC[15]);
+  const int k = __double2loint(t);
+  t -= IIF_EXPC[15];
+  const double r = fma(t, IIF_EXPC[13], x);
+  double p = IIF_EXPC[0];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) t[u] = fma(x[u], L2E, MAGIC);
+  for (int c = 1; c < IIF_EXP_NQ; ++c) p = fma(p, r, IIF_EXPC[c]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return exp_scale2(p, k);
+}
+
+// U exponentials in lockstep: every step is issued for all U arguments before the next one, so the U
+// FP64 dependency chains interleave and each coefficient is fetched once.
+template <int U>
+__device__ __forceinline__ void exp_negU(const double (&x)[U], double (&out)[U]) {
+  const double L2E = IIF_EXPC[12], NLN2 = IIF_EXPC[13], MAGIC = IIF_EXPC[15];
+  double t[U], r[U], p[U];
+  unsigned worst = 0u;  // largest high word: negative arguments sort by magnitude as unsigned
 #pragma unroll
-  for (int u = 0; u < 4; ++u) { k[u] = __double2loint(t[u]); t[u] -= MAGIC; }
+  for (int u = 0; u < U; ++u) worst = max(worst, (unsigned)__double2hiint(x[u]));
 #pragma unroll
-  for (int u = 0; u < 4; ++u) r[u] = fma(t[u], LN2H, x[u]);
+  for (int u = 0; u < U; ++u) t[u] = fma(x[u], L2E, MAGIC);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) r[u] = fma(t[u], LN2L, r[u]);
+  for (int u = 0; u < U; ++u) r[u] = t[u] - MAGIC;
+#pragma unroll
+  for (int u = 0; u < U; ++u) r[u] = fma(r[u], NLN2, x[u]);
   {
     const double c0 = IIF_EXPC[0], c1 = IIF_EXPC[1];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) p[u] = fma(c0, r[u], c1);
+    for (int u = 0; u < U; ++u) p[u] = fma(c0, r[u], c1);
   }
 #pragma unroll
-  for (int c = 2; c < 12; ++c) {
+  for (int c = 2; c < IIF_EXP_NQ; ++c) {
     const double cc = IIF_EXPC[c];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) p[u] = fma(p[u], r[u], cc);
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], cc);
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) p[u] = fma(p[u], r[u], 1.0);
+  for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.0);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) p[u] = fma(p[u], r[u], 1.0);
+  for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.0);
+  if (worst < 0xC0862000u) {  // every argument in (-708, +0]: 2^k is a plain exponent-field add
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int kc = max(k[u], -1100), k1 = kc >> 1, k2 = kc - k1;
-    const double s1 = __hiloint2double((k1 + 1023) << 20, 0);
-    const double s2 = __hiloint2double((k2 + 1023) << 20, 0);
-    out[u] = (p[u] * s1) * s2;
+    for (int u = 0; u < U; ++u)
+      out[u] = __hiloint2double(__double2hiint(p[u]) + (int)((unsigned)__double2loint(t[u]) << 20), __double2loint(p[u]));
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) out[u] = exp_neg(x[u]);
+  }
+}
+
+// Gaussian kernel values exp(-z^2 ln2/16) for U scaled differences z (z = delta * sqrt(8 log2 e) / h gives
+// exp(-delta^2 / 2h^2)), in lockstep.  -z^2 = n + f with n = round(-z^2) taken by the magic-number FMA
+// straight from the exact product, f = fma(-z, z, -n) in [-1/2, 1/2] (single rounding), and
+//   2^((n + f)/16) = 2^(n >> 4) * T[n & 15] * P(f),   T[j] = 2^(j/16) (16-entry shared table: every entry
+// has its own bank pair, so the lookup is conflict-free), P = degree-6 minimax of 2^(f/16) (error 2.8e-17).
+// 13 FP64 instructions per kernel value including the difference and the accumulation (libm-style exp: 20+).
+// Values below 2^-1020 (and inf / NaN arguments) take the careful scalar path.
+__constant__ double IIF_G16C[8] = {9.181315729667637e-12, 1.2716049516907036e-09, 1.4676100322318454e-07,
+                                   1.3550807778387664e-05, 9.383847928089872e-04,  4.332169878499658e-02,
+                                   6755399441055744.0,     0.0};
+__constant__ double IIF_EXP2TAB[16] = {
+    1.0,                1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721,  1.241857812073484,
+    1.2968395546510096, 1.3542555469368927, 1.4142135623730951, 1.4768261459394993, 1.5422108254079407, 1.6104903319492543,
+    1.681792830507429,  1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+#define IIF_GSCALE 3.3972872011520763  // sqrt(8 log2(e))
+
+template <int U>
+__device__ __forceinline__ void gauss_negU(const double (&z)[U], const double* __restrict__ tab, double (&out)[U]) {
+  const double MAGIC = IIF_G16C[6];
+  double t[U], f[U], p[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) t[u] = fma(-z[u], z[u], MAGIC);
+#pragma unroll
+  for (int u = 0; u < U; ++u) f[u] = t[u] - MAGIC;  // n as a double (<= 0)
+  unsigned worst = 0u;  // largest high word of n: negative values sort by magnitude as unsigned
+#pragma unroll
+  for (int u = 0; u < U; ++u) worst = max(worst, (unsigned)__double2hiint(f[u]));
+#pragma unroll
+  for (int u = 0; u < U; ++u) f[u] = fma(-z[u], z[u], -f[u]);
+  {
+    const double c0 = IIF_G16C[0], c1 = IIF_G16C[1];
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(c0, f[u], c1);
+  }
+#pragma unroll
+  for (int c = 2; c < 6; ++c) {
+    const double cc = IIF_G16C[c];
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], f[u], cc);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) p[u] = fma(p[u], f[u], 1.0);
+  if (worst <= (unsigned)__double2hiint(-16320.0)) {  // every value >= 2^-1020: 2^(n>>4) is an exponent-field add
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int n = __double2loint(t[u]);
+      const double v = p[u] * tab[n & 15];
+      out[u] = __hiloint2double(__double2hiint(v) + (int)((unsigned)(n >> 4) << 20), __double2loint(v));
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) out[u] = exp_neg(-(z[u] * z[u]) * 4.332169878499658e-02);
   }
 }
 
@@ -229,180 +328,257 @@ __device__ __forceinline__ void exp_neg4(const double (&x)[4], double (&out)[4])
 // src/IncrementalInference.jl:104).
 //
 // Objective -1/N sum_i log( 1/(N-1) sum_{j!=i} N(x_i - x_j; 0, h^2) ).
-// Thread layout: lane <-> row i, the G = threads/roundup(N,32) thread segments split the columns,
-// four independent exp chains per thread hide the FP64 latency, no shuffles in the hot loop.
-//  * symmetric form (N <= IIF_LOO_SYM_MAX): the kernel matrix is symmetric with a zero diagonal,
-//    so every unordered pair is evaluated ONCE: row i covers the circulant half j = i+1..i+N/2
-//    (mod N), keeps its row part in a register and stores e(i,k) to the shared tile E[k][i]; after
-//    one barrier thread j gathers the mirrored column part sum_k E[k][j-k].  Plain stores and
-//    loads only (conflict-free: consecutive lanes touch consecutive addresses).
-//  * full form (larger N, tile would not fit): every thread sums its share of row i directly.
-// scr layout: part[IIF_LOO_PARTS][N] segment partials, then the E tile (symmetric form only).
+// The kernel matrix is symmetric with a zero diagonal, so every unordered pair is evaluated ONCE:
+// row i covers the circulant half j = i+1..i+N/2 (mod N).  Thread t owns row i = t mod N and the
+// column segment seg = t / N (G = threads/N segments, columns split evenly so that only a thread's
+// last lock-step group can hold padding).  It reads its partners from a doubled copy of the
+// coordinates (x2[i+k], no index wrap), keeps its row part in a register and stores e(i,k) to the
+// shared tile E[k][i]; after one barrier the same thread gathers the mirrored column part
+// sum_k E[k][i-k] (a stride N-1 walk with one wrap).  Plain conflict-free loads and stores only.
+// For even N the antipodal column k = N/2 is evaluated by both of its rows and never stored.
+// Beliefs whose half matrix exceeds the tile are processed in column chunks.
+// Everything that depends only on (N, thread) is computed once per belief (LooThread), outside the
+// ~16 objective evaluations of the golden-section search.
+// scr layout: part[IIF_LOO_PARTS][N] segment partials, then the E tile of loo_tile_rows(N) rows.
 // ------------------------------------------------------------------------------------------
-#define IIF_LOO_SYM_MAX 160
 #define IIF_LOO_PARTS 8
-__host__ __device__ inline bool loo_sym(int N) { return N <= IIF_LOO_SYM_MAX; }
-__host__ __device__ inline int loo_scratch_doubles(int N) {
-  return IIF_LOO_PARTS * N + (loo_sym(N) ? ((N >> 1) + 1) * N : 0);
+#define IIF_LOO_TILE_DOUBLES 12800  // 100 KB: the whole half matrix up to N = 160
+#define IIF_LOO_XPAD 8              // slack behind the doubled coordinates (padding lanes of the last group)
+__host__ __device__ inline int loo_nk(int N) { return ((N - 1) >> 1) + (((N & 1) == 0) ? 1 : 0); }
+__host__ __device__ inline int loo_chunks(int N) {
+  const int nk = loo_nk(N), cap = IIF_LOO_TILE_DOUBLES / N;
+  return (nk + cap - 1) / cap;
 }
+__host__ __device__ inline int loo_tile_rows(int N) {  // equal-sized column chunks
+  const int nc = loo_chunks(N);
+  return (loo_nk(N) + nc - 1) / nc;
+}
+__host__ __device__ inline int loo_scratch_doubles(int N) { return IIF_LOO_PARTS * N + loo_tile_rows(N) * N; }
+__host__ __device__ inline int loo_x2_doubles(int N) { return 2 * N + IIF_LOO_XPAD; }
 #define IIF_LOO_SCRATCH_N(N) loo_scratch_doubles(N)
 
-template <bool CIRC>
-__device__ __forceinline__ double loo_thread_sum(const double* __restrict__ x, int N, double c, double* E,
-                                                 int i, int seg, int G, bool active) {
-  double acc = 0.0;
-  if (!active) return acc;
-  const double xi = x[i];
-  if (loo_sym(N)) {
-    const int hN = N >> 1;
-    const bool even = (N & 1) == 0;
-    const int nk = ((N - 1) >> 1) + (even ? 1 : 0);  // k = 1..nk ; k == N/2 (even N) only for i < N/2
-    const int per = (nk + G - 1) / G;
-    const int k0 = 1 + seg * per, k1 = min(nk, (seg + 1) * per);
-    // the antipodal column (even N, k == N/2) counts once: rows i >= N/2 store and add 0 there
-    const bool cut = even && k1 == hN && i >= hN;
-    int k = k0;
-    for (; k + 3 <= k1; k += 4) {  // full groups: no per-element checks except the antipodal one
-      double a[4], e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        int j = i + k + u;
-        j -= (j >= N) ? N : 0;
-        const double dl = mdiff(xi, x[j], CIRC);
-        a[u] = dl * dl * c;
-      }
-      exp_neg4(a, e);
-      if (cut && k + 3 == k1) e[3] = 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc += e[u];
-        E[(k + u - 1) * N + i] = e[u];
-      }
-    }
-    for (; k <= k1; ++k) {  // tail (< 4 columns)
-      int j = i + k;
-      j -= (j >= N) ? N : 0;
-      const double dl = mdiff(xi, x[j], CIRC);
-      double e = exp_neg(dl * dl * c);
-      if (cut && k == k1) e = 0.0;
-      acc += e;
-      E[(k - 1) * N + i] = e;
-    }
-  } else {
-    const int per = (N + G - 1) / G;
-    const int j0 = seg * per, j1 = min(N, (seg + 1) * per) - 1;
-    for (int j = j0; j <= j1; j += 4) {
-      double a[4], e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int jj = min(j + u, j1);
-        const double dl = mdiff(xi, x[jj], CIRC);
-        a[u] = dl * dl * c;
-      }
-      exp_neg4(a, e);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) acc += ((j + u <= j1) && (j + u != i)) ? e[u] : 0.0;
-    }
-  }
-  return acc;
+struct LooCfg {  // per belief size N and CTA size (uniform)
+  int N, nk, nks, Kc, nchunks, G, U, nrw;
+};
+
+__device__ __forceinline__ LooCfg loo_config(int N) {
+  LooCfg L;
+  L.N = N;
+  L.nk = loo_nk(N);
+  L.nks = (N - 1) >> 1;  // stored (mirrored) columns: all but the antipodal one
+  L.Kc = loo_tile_rows(N);
+  L.nchunks = loo_chunks(N);
+  int G = IIF_NT / N;
+  G = G > IIF_LOO_PARTS ? IIF_LOO_PARTS : G;
+  G = G > L.Kc ? L.Kc : G;
+  L.G = G < 1 ? 1 : G;
+  const int per = (L.Kc + L.G - 1) / L.G;
+  // lock-step width: least padded work among 4, 5, 6 (ties: the widest, more independent chains)
+  int best = 4, cost = ((per + 3) / 4) * 4;
+  if (((per + 4) / 5) * 5 <= cost) { best = 5; cost = ((per + 4) / 5) * 5; }
+  if (((per + 5) / 6) * 6 <= cost) { best = 6; cost = ((per + 5) / 6) * 6; }
+  L.U = best;
+  L.nrw = (N + 31) >> 5;
+  return L;
 }
 
-// KTAG gives every kernel its own instantiation (and register budget) of the noinline search code.
-template <int KTAG>
-__device__ __noinline__ double loo_nll(const double* __restrict__ x, int N, int circ, double h, double* scr,
-                                       double* red, int* parity_io) {
-  const double c = -1.0 / (2.0 * h * h);
-  const double lognorm = log((double)(N - 1) * sqrt(IIF_TWO_PI) * h);
-  const int Npad = (N + 31) & ~31;
-  int G = IIF_NT / Npad;
-  G = G > IIF_LOO_PARTS ? IIF_LOO_PARTS : G;
-  const int seg = threadIdx.x / Npad, i = threadIdx.x - seg * Npad;
-  const bool active = (seg < G) && (i < N);
+struct LooThread {  // this thread's share of one column chunk
+  int cnt;          // columns evaluated
+  int cnts;         // columns stored and gathered (<= cnt)
+  int wrap;         // column (0-based within the thread) at which the partner row index i + k wraps
+  int xoff;         // x2 offset of the first partner: i + kb
+  int soff;         // tile offset of the first store:  (kb - cf) * N + (i + kb)  [- N once wrapped]
+  int goff;         // tile offset of the first gather: (kb - cf) * N + i
+};
+
+__device__ __forceinline__ LooThread loo_thread(const LooCfg& L, int seg, int i, int ch) {
+  LooThread T;
+  const int cf = 1 + ch * L.Kc;
+  const int cols = min(L.Kc, L.nk - cf + 1);
+  const int kb = cf + (seg * cols) / L.G, ke = cf + ((seg + 1) * cols) / L.G - 1;
+  const bool on = seg < L.G && kb <= ke;
+  T.cnt = on ? ke - kb + 1 : 0;
+  T.cnts = on ? max(min(ke, L.nks) - kb + 1, 0) : 0;
+  T.wrap = L.N - (i + kb);              // < 0: wrapped from the first column on
+  T.xoff = i + kb;
+  T.soff = (kb - cf) * L.N + (i + kb) - (T.wrap < 0 ? L.N : 0);
+  T.goff = (kb - cf) * L.N + i;
+  return T;
+}
+
+// row part: sum_k e(i, i+k) over this thread's columns; e(i, i+k) is stored to tile row k at the position
+// of the partner row j = (i + k) mod N, so that the gather below is a plain stride-N walk
+template <int U, bool CIRC>
+__device__ __forceinline__ double loo_rows(const double* __restrict__ xp, double xi, double sc,
+                                           const double* __restrict__ tab, double* __restrict__ ep, int N, int cnt,
+                                           int cnts, int wrap) {
+  double acc0 = 0.0, acc1 = 0.0;
+  int done = 0;
+  for (; done + U <= cnts; done += U) {  // full groups: every column valid and stored
+    double a[U], e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = mdiff(xi, xp[u], CIRC) * sc;
+    gauss_negU<U>(a, tab, e);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u & 1) acc1 += e[u]; else acc0 += e[u];
+      if (done + u == wrap) ep -= N;
+      *ep = e[u];
+      ep += N + 1;
+    }
+    xp += U;
+  }
+  if (done < cnt) {  // last group: padding lanes are dropped, the antipodal column is not stored
+    double a[U], e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = mdiff(xi, xp[u], CIRC) * sc;
+    gauss_negU<U>(a, tab, e);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (done + u < cnt) acc0 += e[u];
+      if (done + u == wrap) ep -= N;
+      if (done + u < cnts) *ep = e[u];
+      ep += N + 1;
+    }
+  }
+  return acc0 + acc1;
+}
+
+// mirrored column part: sum_k E[k][i] over the stored columns of this thread
+__device__ __forceinline__ double loo_gather(const double* __restrict__ gp, int N, int cnts) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int m = 0;
+#pragma unroll 1
+  for (; m + 3 < cnts; m += 4) {
+    a0 += gp[0];
+    a1 += gp[N];
+    a2 += gp[2 * N];
+    a3 += gp[3 * N];
+    gp += 4 * N;
+  }
+#pragma unroll 1
+  for (; m < cnts; ++m) { a0 += gp[0]; gp += N; }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// one objective evaluation; x2 = doubled coordinates in shared memory.  invK = 1 / ((N-1) sqrt(2 pi)).
+template <int U, bool CIRC>
+__device__ __forceinline__ double loo_nll(const double* __restrict__ x2, const LooCfg& L, const LooThread& T0, int seg,
+                                          int i, double xi, double h, double invK, double negInvN,
+                                          const double* __restrict__ tab, double* scr, double* red, int& parity) {
+  const int N = L.N;
+  IIF_PHASE_BEGIN();
+  const double rh = 1.0 / h;
+  const double sc = IIF_GSCALE * rh;  // exp(-delta^2 / 2h^2) = 2^(-(delta sc)^2 / 16)
+  const double norm = rh * invK;  // row sums are normalised before the log: one log per row, none for the constant
   double* part = scr;
   double* E = scr + IIF_LOO_PARTS * N;
-  double acc = circ ? loo_thread_sum<true>(x, N, c, E, i, seg, G, active)
-                    : loo_thread_sum<false>(x, N, c, E, i, seg, G, active);
-  if (loo_sym(N)) {
+  double acc = 0.0;
+  for (int ch = 0; ch < L.nchunks; ++ch) {
+    LooThread T = T0;
+    if (ch > 0) {
+      T = loo_thread(L, seg, i, ch);
+      __syncthreads();  // the previous chunk's tile is no longer read
+    }
+    if (T.cnt > 0) acc += loo_rows<U, CIRC>(x2 + T.xoff, xi, sc, tab, E + T.soff, N, T.cnt, T.cnts, T.wrap);
+    IIF_PHASE(0);
     __syncthreads();
-    if (active) {  // mirrored column part: sum_k E[k][j - k], same k-range as this thread's row part
-      const int hN = N >> 1;
-      const int nk = ((N - 1) >> 1) + (((N & 1) == 0) ? 1 : 0);
-      const int per = (nk + G - 1) / G;
-      const int k0 = 1 + seg * per, k1 = min(nk, (seg + 1) * per);
-      double a0 = 0.0, a1 = 0.0;
-      int k = k0;
-      for (; k + 1 <= k1; k += 2) {
-        int r0 = i - k, r1 = i - k - 1;
-        r0 += (r0 < 0) ? N : 0;
-        r1 += (r1 < 0) ? N : 0;
-        a0 += E[(k - 1) * N + r0];
-        a1 += E[k * N + r1];
+    IIF_PHASE(1);
+    if (T.cnts > 0) acc += loo_gather(E + T.goff, N, T.cnts);
+    IIF_PHASE(2);
+  }
+  if (L.G > 1) {
+    if (seg < L.G) part[seg * N + i] = acc;
+    __syncthreads();
+    IIF_PHASE(3);
+    if (threadIdx.x < N) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int g = 0; g < IIF_LOO_PARTS; g += 2) {
+        if (g < L.G) s0 += part[g * N + threadIdx.x];
+        if (g + 1 < L.G) s1 += part[(g + 1) * N + threadIdx.x];
       }
-      if (k <= k1) {
-        int r0 = i - k;
-        r0 += (r0 < 0) ? N : 0;
-        a0 += E[(k - 1) * N + r0];
-      }
-      acc += a0 + a1;
-      (void)hN;
+      acc = s0 + s1;
     }
   }
-  double term = 0.0;
-  if (G > 1) {
-    if (active) part[seg * N + i] = acc;
-    __syncthreads();
-    if (seg == 0 && i < N) {
-      double t = 0.0;
-      for (int g = 0; g < G; ++g) t += part[g * N + i];
-      term = log(t) - lognorm;
-    }
-  } else if (active) {
-    term = log(acc) - lognorm;
+  // rows live in the first ceil(N/32) warps: sum their log terms
+  double* buf = red + parity * (IIF_MAX_WARPS * IIF_RED_KMAX);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < L.nrw) {
+    double term = (threadIdx.x < N) ? log(acc * norm) : 0.0;
+    term = warp_sum(term);
+    if (lane == 0) buf[warp] = term;
   }
-  int parity = *parity_io;
-  const double tot = block_sum1(term, red, parity);  // its barrier also protects scr for the next call
-  *parity_io = parity;
-  return -tot / (double)N;
+  IIF_PHASE(4);
+  __syncthreads();  // also protects scr for the next evaluation
+  IIF_PHASE(5);
+  double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+  for (int w = 0; w < IIF_MAX_POINTS / 32; w += 2) {
+    if (w < L.nrw) t0 += buf[w];
+    if (w + 1 < L.nrw) t1 += buf[w + 1];
+  }
+  parity ^= 1;
+  IIF_PHASE(6);
+  return (t0 + t1) * negInvN;
 }
 
-// Numerical-Recipes golden section as used by KDE `golden(npd, nLOO_LL, ax, bx, cx, tol)`;
-// the search variable scales the base bandwidth h0.  Uniform control flow across the CTA.
-template <int KTAG>
-__device__ double golden_nr(const double* x, int N, double h0, double ax, double bx, double cx, double tol,
-                            double* scr, double* red, int& parity) {
+// Numerical-Recipes golden section as used by KDE `golden(npd, nLOO_LL, ax, bx, cx, tol)`; the search
+// variable scales the base bandwidth h0.  Uniform control flow across the CTA; the objective has ONE
+// call site (iterations -2 and -1 are the two initial evaluations) so that it is inlined once.
+template <int U>
+__device__ __forceinline__ double golden_nr(const double* x2, const LooCfg& L, const LooThread& T0, int seg, int i,
+                                            double h0, double ax, double bx, double cx, double tol,
+                                            const double* tab, double* scr, double* red, int& parity) {
   const double C = (3.0 - sqrt(5.0)) / 2.0, R = 1.0 - C;
-  double x0 = ax, x3 = cx, x1, x2;
-  if (fabs(cx - bx) > fabs(bx - ax)) { x1 = bx; x2 = bx + C * (cx - bx); }
-  else { x2 = bx; x1 = bx - C * (bx - ax); }
-  double f1 = loo_nll<KTAG>(x, N, 0, x1 * h0, scr, red, &parity);
-  double f2 = loo_nll<KTAG>(x, N, 0, x2 * h0, scr, red, &parity);
-  for (int it = 0; it < 200 && fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2)); ++it) {
-    const bool right = f2 < f1;
+  const double xi = x2[i];
+  const double invK = 1.0 / ((double)(L.N - 1) * sqrt(IIF_TWO_PI)), negInvN = -1.0 / (double)L.N;
+  double x0 = ax, x3 = cx, x1, x2v;
+  if (fabs(cx - bx) > fabs(bx - ax)) { x1 = bx; x2v = bx + C * (cx - bx); }
+  else { x2v = bx; x1 = bx - C * (bx - ax); }
+  double f1 = 0.0, f2 = 0.0;
+  bool right = false;
+  for (int it = -2; it < 200; ++it) {
     double xn;
-    if (right) { x0 = x1; x1 = x2; x2 = R * x1 + C * x3; f1 = f2; xn = x2; }
-    else { x3 = x2; x2 = x1; x1 = R * x2 + C * x0; f2 = f1; xn = x1; }
-    const double fn = loo_nll<KTAG>(x, N, 0, xn * h0, scr, red, &parity);
-    if (right) f2 = fn; else f1 = fn;
+    if (it >= 0) {
+      if (!(fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2v)))) break;
+      right = f2 < f1;
+      if (right) { x0 = x1; x1 = x2v; x2v = R * x1 + C * x3; f1 = f2; xn = x2v; }
+      else { x3 = x2v; x2v = x1; x1 = R * x2v + C * x0; f2 = f1; xn = x1; }
+    } else {
+      xn = (it == -2) ? x1 : x2v;
+    }
+    const double fn = loo_nll<U, false>(x2, L, T0, seg, i, xi, xn * h0, invK, negInvN, tab, scr, red, parity);
+    if (it == -2) f1 = fn;
+    else if (it == -1 || right) f2 = fn;
+    else f1 = fn;
   }
-  return (f1 < f2) ? x1 : x2;
+  return (f1 < f2) ? x1 : x2v;
 }
 
-// Optim.jl GoldenSection on [lo, hi] as used by AMP kde!_CircularNaiveCV
-template <int KTAG>
-__device__ double golden_optim(const double* x, int N, double lo, double hi, double rel_tol, double* scr,
-                               double* red, int& parity) {
+// Optim.jl GoldenSection on [lo, hi] as used by AMP kde!_CircularNaiveCV (same single call site)
+template <int U>
+__device__ __forceinline__ double golden_optim(const double* x2, const LooCfg& L, const LooThread& T0, int seg, int i,
+                                               double lo, double hi, double rel_tol, const double* tab, double* scr,
+                                               double* red, int& parity) {
   const double gr = 0.5 * (3.0 - sqrt(5.0));
   const double abs_tol = 2.220446049250313e-16;
-  double xm = lo + gr * (hi - lo);
-  double fm = loo_nll<KTAG>(x, N, 1, xm, scr, red, &parity);
-  for (int it = 0; it < 200; ++it) {
-    double tolx = rel_tol * fabs(xm) + abs_tol;
-    double mid = 0.5 * (hi + lo);
-    if (fabs(xm - mid) <= 2 * tolx - 0.5 * (hi - lo)) break;
-    const bool up = hi - xm > xm - lo;
-    const double xn = up ? xm + gr * (hi - xm) : xm - gr * (xm - lo);
-    const double fn = loo_nll<KTAG>(x, N, 1, xn, scr, red, &parity);
-    if (up) {
+  const double xi = x2[i];
+  const double invK = 1.0 / ((double)(L.N - 1) * sqrt(IIF_TWO_PI)), negInvN = -1.0 / (double)L.N;
+  double xm = lo + gr * (hi - lo), fm = 0.0;
+  bool up = false;
+  for (int it = -1; it < 200; ++it) {
+    double xn = xm;
+    if (it >= 0) {
+      const double tolx = rel_tol * fabs(xm) + abs_tol;
+      const double mid = 0.5 * (hi + lo);
+      if (fabs(xm - mid) <= 2 * tolx - 0.5 * (hi - lo)) break;
+      up = hi - xm > xm - lo;
+      xn = up ? xm + gr * (hi - xm) : xm - gr * (xm - lo);
+    }
+    const double fn = loo_nll<U, true>(x2, L, T0, seg, i, xi, xn, invK, negInvN, tab, scr, red, parity);
+    if (it < 0) fm = fn;
+    else if (up) {
       if (fn < fm) { lo = xm; xm = xn; fm = fn; } else hi = xn;
     } else {
       if (fn < fm) { hi = xm; xm = xn; fm = fn; } else lo = xn;
@@ -411,43 +587,69 @@ __device__ double golden_optim(const double* x, int N, double lo, double hi, dou
   return xm;
 }
 
+// bandwidth of one coordinate; xa = the N coordinates, xb = loo_x2_doubles(N) scratch
+template <int U>
+__device__ __forceinline__ double coord_bandwidth(bool circ, const LooCfg& L, const LooThread& T0, int seg, int i,
+                                                  const TreeStruct& T, const double* xa, double* xb,
+                                                  const double* tab, double* scr, double* red, int& parity) {
+  const int N = L.N;
+  if (circ) {
+    for (int m = threadIdx.x; m < 2 * N + IIF_LOO_XPAD; m += IIF_NT) xb[m] = xa[m % N];
+    __syncthreads();
+    return golden_optim<U>(xb, L, T0, seg, i, 1e-3, IIF_TWO_PI, 1e-3, tab, scr, red, parity);
+  }
+  // rank sort (ties by index) -> xb ascending, doubled
+  for (int m = threadIdx.x; m < N; m += IIF_NT) {
+    const double xi = xa[m];
+    int r = 0;
+    for (int k = 0; k < N; ++k) {
+      const double xk = xa[k];
+      r += (xk < xi) || (xk == xi && k < m);
+    }
+    xb[r] = xi;
+    xb[r + N] = xi;
+    if (r < IIF_LOO_XPAD) xb[r + 2 * N] = xi;
+  }
+  __syncthreads();
+  // KDE neighborMinMax: root ball diameter and smallest internal ball diameter (>= 1e-6)
+  const double maxm = xb[N - 1] - xb[0];
+  double m = maxm;
+  for (int z = threadIdx.x; z < T.nn; z += IIF_NT) {
+    const int lo = T.lo[z], hi = T.hi[z];
+    if (hi > lo) m = fmin(m, xb[hi] - xb[lo]);
+  }
+  double minm = block_min1(m, red, parity);
+  if (minm < 1e-6) minm = 1e-6;
+  const double h0 = 0.5 * (minm + maxm);
+  const double a = golden_nr<U>(xb, L, T0, seg, i, h0, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm),
+                                1e-2, tab, scr, red, parity);
+  return a * h0;
+}
+
 // Per-dimension bandwidth of the N x d points in `pts` (shared or global memory).
-// xa, xb: shared scratch of N doubles each; scr: IIF_NW*N + N doubles.  Result bw[c] is returned
-// to every thread.
+// xa: N doubles, xb: loo_x2_doubles(N) doubles, scr: loo_scratch_doubles(N) doubles of shared scratch.
+// Result bw[c] is returned to every thread.  KTAG gives every kernel its own instantiation.
 template <int KTAG>
-__device__ void block_kde_bandwidth(const double* pts, int N, int d, int32_t circ_mask, const TreeStruct& T,
-                                    double* xa, double* xb, double* scr, double* red, int& parity, double* bw) {
+__device__ __noinline__ void block_kde_bandwidth(const double* pts, int N, int d, int32_t circ_mask,
+                                                 const TreeStruct* Tp, double* xa, double* xb, double* scr,
+                                                 double* red, int* parity_io, double* bw) {
+  const TreeStruct T = *Tp;
+  const LooCfg L = loo_config(N);
+  const int seg = threadIdx.x / N, i = threadIdx.x - seg * N;
+  const LooThread T0 = loo_thread(L, seg, i, 0);
+  int parity = *parity_io;
+  __shared__ double tab[16];  // 2^(j/16), see gauss_negU
+  if (threadIdx.x < 16) tab[threadIdx.x] = IIF_EXP2TAB[threadIdx.x];
+  IIF_PHASE_ZERO();
   for (int c = 0; c < d; ++c) {
     __syncthreads();
-    for (int i = threadIdx.x; i < N; i += IIF_NT) xa[i] = pts[i * d + c];
+    for (int m = threadIdx.x; m < N; m += IIF_NT) xa[m] = pts[m * d + c];
     __syncthreads();
-    if (is_circ(circ_mask, c)) {
-      bw[c] = golden_optim<KTAG>(xa, N, 1e-3, IIF_TWO_PI, 1e-3, scr, red, parity);
-    } else {
-      // rank sort (ties by index) -> xb ascending
-      for (int i = threadIdx.x; i < N; i += IIF_NT) {
-        double xi = xa[i];
-        int r = 0;
-        for (int k = 0; k < N; ++k) {
-          double xk = xa[k];
-          r += (xk < xi) || (xk == xi && k < i);
-        }
-        xb[r] = xi;
-      }
-      __syncthreads();
-      // KDE neighborMinMax: root ball diameter and smallest internal ball diameter (>= 1e-6)
-      double maxm = xb[N - 1] - xb[0];
-      double m = maxm;
-      for (int z = threadIdx.x; z < T.nn; z += IIF_NT) {
-        int lo = T.lo[z], hi = T.hi[z];
-        if (hi > lo) m = fmin(m, xb[hi] - xb[lo]);
-      }
-      double minm = block_min1(m, red, parity);
-      if (minm < 1e-6) minm = 1e-6;
-      double h0 = 0.5 * (minm + maxm);
-      double a = golden_nr<KTAG>(xb, N, h0, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm), 1e-2, scr,
-                           red, parity);
-      bw[c] = a * h0;
-    }
+    const bool circ = is_circ(circ_mask, c);
+    bw[c] = (L.U == 4)   ? coord_bandwidth<4>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity)
+            : (L.U == 5) ? coord_bandwidth<5>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity)
+                         : coord_bandwidth<6>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity);
   }
+  IIF_PHASE_FLUSH();
+  *parity_io = parity;
 }

@@ -36,7 +36,7 @@ struct ProdSmem {
   double* var;    // F*nn*d
   double* post;   // N*d
   double* xa;     // N
-  double* xb;     // N
+  double* xb;     // loo_x2_doubles(N)
   double* red;    // IIF_RED_DOUBLES
   double* scr;    // IIF_LOO_SCRATCH_N(N)  (leave-one-out scratch)
   double* bwk;    // F*IIF_MAX_DIM kernel bandwidths
@@ -51,7 +51,7 @@ struct ProdSmem {
 __host__ __device__ inline bool gibbs_tab(int N) { return N <= IIF_GIBBS_TAB_MAX; }
 
 __host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn, int L) {
-  size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + 2 * (size_t)N + IIF_RED_DOUBLES +
+  size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + (size_t)N + (size_t)loo_x2_doubles(N) + IIF_RED_DOUBLES +
                (size_t)F * IIF_MAX_DIM + (size_t)nn + (size_t)F * (L + 1) * d;
   size_t scr = (size_t)IIF_LOO_SCRATCH_N(N);
   if (F == 2 && gibbs_tab(N) && (size_t)N * N > scr) scr = (size_t)N * N;
@@ -107,7 +107,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     sm.var = p; p += (size_t)F * nn * d;
     sm.post = p; p += (size_t)N * d;
     sm.xa = p; p += N;
-    sm.xb = p; p += N;
+    sm.xb = p; p += loo_x2_doubles(N);
     sm.red = p; p += IIF_RED_DOUBLES;
     sm.bwk = p; p += F * IIF_MAX_DIM;
     sm.wt = p; p += nn;
@@ -484,7 +484,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     }
     __syncthreads();
     // ---- 4. re-bandwidth of the posterior (getKDEManifoldBandwidths on the result)
-    block_kde_bandwidth<1>(sm.post, N, d, cm, T, sm.xa, sm.xb, sm.scr, sm.red, parity, bw);
+    block_kde_bandwidth<1>(sm.post, N, d, cm, &trees[N], sm.xa, sm.xb, sm.scr, sm.red, &parity, bw);
   }
 
   // ---- outputs: explicit buffers and / or setBelief! into the destination slot
@@ -539,10 +539,10 @@ iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restr
   double* pts = bw_smem;
   double* xa = pts + (size_t)t.N * IIF_MAX_DIM;
   double* xb = xa + t.N;
-  double* scr = xb + t.N;
+  double* scr = xb + loo_x2_doubles(t.N);
   for (int i = threadIdx.x; i < t.N * t.dim; i += IIF_NT) pts[i] = t.pts[i];
   __syncthreads();
   double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
-  block_kde_bandwidth<2>(pts, t.N, t.dim, t.circ_mask, trees[t.N], xa, xb, scr, red, parity, bw);
+  block_kde_bandwidth<2>(pts, t.N, t.dim, t.circ_mask, &trees[t.N], xa, xb, scr, red, &parity, bw);
   if (threadIdx.x < IIF_MAX_DIM) t.out_bw[threadIdx.x] = threadIdx.x < t.dim ? bw[threadIdx.x] : 0.0;
 }

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -434,9 +435,20 @@ int32_t iifb200_slot_device_ptr(iifb200_ctx* ctx, int32_t slot, void** pts_ptr, 
 // CTA size of a launch: wide (throughput-bound) launches use the smallest CTA that still gives every
 // particle its own thread, so several CTAs share an SM and no warp idles in the per-particle stages;
 // narrow (latency-bound) launches use 512 threads to split each belief's work further.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 static int pick_threads(iifb200_ctx* ctx, int grid, int maxN, int small_min = 128) {
-  int small = std::max(small_min, (maxN + 31) / 32 * 32);
+  static const int wide = env_int("IIFB200_WIDE_THREADS", 0);  // tuning knob: CTA size of wide launches
+  int small = std::max(wide > 0 ? wide : small_min, (maxN + 31) / 32 * 32);
+  small = std::min(small, IIF_MAX_THREADS);
   return (grid >= 2 * ctx->num_sms) ? small : IIF_MAX_THREADS;
+}
+static int pick_threads_prod(iifb200_ctx* ctx, int grid, int maxN) {
+  static const int wide = env_int("IIFB200_PROD_WIDE_THREADS", 0);
+  if (wide <= 0 || grid < 2 * ctx->num_sms) return IIF_MAX_THREADS;
+  return std::min(IIF_MAX_THREADS, std::max(wide, (maxN + 31) / 32 * 32));
 }
 
 static bool is_prior_kind_h(int k) {
@@ -597,7 +609,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ProdTask) * V, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_product_kernel<<<V, IIF_MAX_THREADS, smem, ctx->stream>>>(ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
+  iif_product_kernel<<<V, pick_threads_prod(ctx, V, pmaxN), smem, ctx->stream>>>(ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -780,7 +792,7 @@ static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int*
       ++k;
     }
     if (W.nprod) {
-      iif_product_kernel<<<W.nprod, IIF_MAX_THREADS, W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      iif_product_kernel<<<W.nprod, pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
       ++k;
     }
   }
@@ -850,7 +862,7 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
     }
     if (W.nprod) {
       mark();
-      iif_product_kernel<<<W.nprod, IIF_MAX_THREADS, W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      iif_product_kernel<<<W.nprod, pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(1); blocks[1] += W.nprod;
     }
   }
@@ -934,6 +946,13 @@ int32_t iifb200_set_stream(iifb200_ctx* ctx, void* stream) {
   return IIF_OK;
 }
 void* iifb200_stream(iifb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+#ifdef IIF_PHASES
+// development only (profiles/phase_probe.py): read and optionally reset the phase clocks
+void iifb200_debug_phases(long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, g_iif_phase, sizeof(long long) * 16);
+  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_iif_phase, z, sizeof(z)); }
+}
+#endif
 float iifb200_last_elapsed_ms(iifb200_ctx* ctx) {
   if (!ctx || !ctx->timed) return -1.0f;
   float ms = -1.0f;
