@@ -209,7 +209,9 @@ __device__ void block_geodesic_mean(const double* pts, int n, int d, int32_t cm,
   double s[IIF_MAX_DIM] = {0, 0, 0, 0};
   for (int i = threadIdx.x; i < n; i += IIF_NT)
     for (int c = 0; c < d; ++c) s[c] += pts[i * d + c];
-  block_sum<IIF_MAX_DIM>(s, red, parity);
+  const int nwa = (n + 31) >> 5;
+  if (d == 1) s[0] = block_sum1(s[0], red, parity, nwa);
+  else block_sum<IIF_MAX_DIM>(s, red, parity, nwa);
   if (threadIdx.x == 0) {
     for (int c = 0; c < d; ++c) {
       if (!is_circ(cm, c)) { mu_s[c] = n > 0 ? s[c] / n : 0.0; continue; }
@@ -233,7 +235,7 @@ __device__ void block_default_mean(const double* pts, int n, int d, int32_t cm, 
       double v = pts[i * d + c];
       if (is_circ(cm, c)) { s[c] += sin(v); s[IIF_MAX_DIM + c] += cos(v); } else s[c] += v;
     }
-  block_sum<2 * IIF_MAX_DIM>(s, red, parity);
+  block_sum<2 * IIF_MAX_DIM>(s, red, parity, (n + 31) >> 5);
   for (int c = 0; c < d; ++c)
     mu[c] = n > 0 ? (is_circ(cm, c) ? atan2(s[c], s[IIF_MAX_DIM + c]) : s[c] / n) : 0.0;
 }
@@ -249,7 +251,7 @@ __device__ __noinline__ double block_std_basic_spread(const double* pts, int n, 
       double v = mdiff(pts[i * d + c], mu_s[c], is_circ(cm, c));
       acc += v * v;
     }
-  acc = block_sum1(acc, red, parity);
+  acc = block_sum1(acc, red, parity, (n + 31) >> 5);
   double sigma = sqrt(acc / (double)(n - 1));
   return (1e-10 < sigma) ? sigma : 1.0;
 }
@@ -318,6 +320,8 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   __shared__ iif_factor_desc f;
   __shared__ int s_status;
 
+  IIF_PHASE_ZERO();
+  IIF_PHASE_BEGIN();
   const ConvTask t = tasks[blockIdx.x];
   const iif_conv_op op = t.op;
   const int n = threadIdx.x;
@@ -351,6 +355,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
       }
     }
   }
+  IIF_PHASE(8);
   // fresh measurements (CalcFactor.jl:578)
   double z[IIF_MAX_DIM] = {0, 0, 0, 0};
   if (active) {
@@ -381,6 +386,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   const int32_t pmask = f.partial_mask ? f.partial_mask : fullmask;
   const int C = g.sp->inflateCycles;
   int nnan = 0;
+  IIF_PHASE(9);
 
   auto inflate_u = [&](int cyc, int c) -> double {
     uint32_t idx = (uint32_t)((cyc * N + n) * d + c);
@@ -420,47 +426,48 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
       const bool sfincer = in_list(R.cert, R.ncert, sfidx);
       for (int b = 0; b < R.nb; ++b) {
         const int hyp = R.hyp[b];
+        // a bucket without elements changes nothing (its spread would only feed its own entropy): skip it
+        const int nel = __syncthreads_count(active && label == hyp);
+        if (nel == 0) continue;
         if ((sfincer && hyp != 0) || in_list(R.cert, R.ncert, hyp) || hyp == sfidx) {
-          const int nel = __syncthreads_count(active && label == hyp);
-          int other = -1;
-          bool sf_second = false;
-          if (nel > 0) {
-            if (R.nv[b] != 2 || !in_list(R.vars[b], 2, sfidx)) {
-              if (n == 0) s_status = IIF_ERR_UNSUPPORTED;
-              break;
+          if (R.nv[b] != 2 || !in_list(R.vars[b], 2, sfidx)) {
+            if (n == 0) s_status = IIF_ERR_UNSUPPORTED;
+            break;
+          }
+          const int other = (R.vars[b][0] == sfidx) ? R.vars[b][1] : R.vars[b][0];
+          const bool sf_second = (R.vars[b][1] == sfidx);
+          // the partner particle of this sample does not change between the inflation cycles: fetch it once
+          double o[IIF_MAX_DIM] = {0, 0, 0, 0};
+          bool ok = false;
+          if (active && label == hyp) {
+            const int oslot = f.slot[other - 1];
+            const iif_slot_desc So = g.slots[oslot];
+            const int lo = g.npts[oslot];
+            int m = n;  // _getindex_anyn, NumericalCalculations.jl:377-381
+            ok = true;
+            if (n >= lo) {
+              if (lo <= 0) { s_status = IIF_ERR_STATE; ok = false; }
+              else {
+                double u = rs_uniform(seed, call, IIF_RS_ANYN, (uint32_t)((other - 1) * N + n));
+                m = min((int)(u * lo), lo - 1);
+              }
             }
-            other = (R.vars[b][0] == sfidx) ? R.vars[b][1] : R.vars[b][0];
-            sf_second = (R.vars[b][1] == sfidx);
+            if (ok)
+              for (int c = 0; c < So.dim; ++c) o[c] = g.pts[So.pts_off + m * So.dim + c];
           }
           for (int cyc = 0; cyc < C; ++cyc) {
             __syncthreads();
             double sp = block_spread_distance(g, f, sfidx, dest, N, R, f.inflation, mu_s, red, parity);
             add_entropy(hyp, pmask, sp, cyc);
-            if (nel == 0) continue;
-            if (active && label == hyp) {
-              const int oslot = f.slot[other - 1];
-              const iif_slot_desc So = g.slots[oslot];
-              const int lo = g.npts[oslot];
-              int m = n;  // _getindex_anyn, NumericalCalculations.jl:377-381
-              bool ok = true;
-              if (n >= lo) {
-                if (lo <= 0) { s_status = IIF_ERR_STATE; ok = false; }
-                else {
-                  double u = rs_uniform(seed, call, IIF_RS_ANYN, (uint32_t)((other - 1) * N + n));
-                  m = min((int)(u * lo), lo - 1);
-                }
-              }
-              if (ok) {
-                double o[IIF_MAX_DIM], r[IIF_MAX_DIM];
-                for (int c = 0; c < So.dim; ++c) o[c] = g.pts[So.pts_off + m * So.dim + c];
-                solve_binary(f.kind, d, cm, z, o, sf_second, my, r);
-                bool bad = false;
-                for (int c = 0; c < d; ++c) bad |= isnan(r[c]);
-                if (bad) nnan++;  // NumericalCalculations.jl:348-351: particle left unchanged
-                else
-                  for (int c = 0; c < d; ++c)
-                    if ((pmask >> c) & 1) { my[c] = r[c]; dest[n * d + c] = r[c]; }
-              }
+            if (ok) {
+              double r[IIF_MAX_DIM];
+              solve_binary(f.kind, d, cm, z, o, sf_second, my, r);
+              bool bad = false;
+              for (int c = 0; c < d; ++c) bad |= isnan(r[c]);
+              if (bad) nnan++;  // NumericalCalculations.jl:348-351: particle left unchanged
+              else
+                for (int c = 0; c < d; ++c)
+                  if ((pmask >> c) & 1) { my[c] = r[c]; dest[n * d + c] = r[c]; }
             }
           }
         } else {
@@ -473,6 +480,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
     }
   }
   __syncthreads();
+  IIF_PHASE(10);
   const int status = s_status;
   if (t.out_status != nullptr && n == 0) *t.out_status = status;
   if (status != IIF_OK) return;
@@ -487,7 +495,9 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   }
   // approxConvBelief: manikde!(M, pts; partial) — ApproxConv.jl:31-42
   double bw[IIF_MAX_DIM];
+  IIF_PHASE(11);
   block_kde_bandwidth<0>(dest, N, d, cm, &trees[N], xa, xb, scr, red, &parity, bw);
+  IIF_PHASE(12);
   if (n == 0) {
     for (int c = 0; c < IIF_MAX_DIM; ++c) {
       t.out_bw[c] = c < d ? (((pmask >> c) & 1) ? bw[c] : 1.0) : 0.0;
@@ -507,4 +517,6 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
       g.flags[t.out_slot] |= 1;
     }
   }
+  IIF_PHASE(13);
+  IIF_PHASE_FLUSH();
 }

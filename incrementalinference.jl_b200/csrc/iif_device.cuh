@@ -154,27 +154,32 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// `nwa`: warps that can hold a non-zero contribution (items 0..n-1 dealt to threads round-robin occupy the
+// first ceil(n/32) warps); the others skip the shuffles and are not read back.
 template <int K>
-__device__ __forceinline__ void block_sum(double (&v)[K], double* red, int& parity) {
+__device__ __forceinline__ void block_sum(double (&v)[K], double* red, int& parity, int nwa = IIF_MAX_WARPS) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* buf = red + parity * (IIF_MAX_WARPS * IIF_RED_KMAX);
+  nwa = min(nwa, IIF_NW);
+  if (warp < nwa) {
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    double s = warp_sum(v[k]);
-    if (lane == 0) buf[warp * K + k] = s;
+    for (int k = 0; k < K; ++k) {
+      double s = warp_sum(v[k]);
+      if (lane == 0) buf[warp * K + k] = s;
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double s = 0;
-    for (int w = 0; w < IIF_NW; ++w) s += buf[w * K + k];
+    for (int w = 0; w < nwa; ++w) s += buf[w * K + k];
     v[k] = s;
   }
   parity ^= 1;
 }
-__device__ __forceinline__ double block_sum1(double x, double* red, int& parity) {
+__device__ __forceinline__ double block_sum1(double x, double* red, int& parity, int nwa = IIF_MAX_WARPS) {
   double v[1] = {x};
-  block_sum<1>(v, red, parity);
+  block_sum<1>(v, red, parity, nwa);
   return v[0];
 }
 __device__ __forceinline__ double block_min1(double x, double* red, int& parity) {
@@ -313,7 +318,7 @@ __device__ __forceinline__ void gauss_negU(const double (&z)[U], const double* _
     for (int u = 0; u < U; ++u) {
       const int n = __double2loint(t[u]);
       const double v = p[u] * tab[n & 15];
-      out[u] = __hiloint2double(__double2hiint(v) + (int)((unsigned)(n >> 4) << 20), __double2loint(v));
+      out[u] = __hiloint2double(__double2hiint(v) + (n >> 4) * 1048576, __double2loint(v));
     }
   } else {
 #pragma unroll
@@ -640,7 +645,6 @@ __device__ __noinline__ void block_kde_bandwidth(const double* pts, int N, int d
   int parity = *parity_io;
   __shared__ double tab[16];  // 2^(j/16), see gauss_negU
   if (threadIdx.x < 16) tab[threadIdx.x] = IIF_EXP2TAB[threadIdx.x];
-  IIF_PHASE_ZERO();
   for (int c = 0; c < d; ++c) {
     __syncthreads();
     for (int m = threadIdx.x; m < N; m += IIF_NT) xa[m] = pts[m * d + c];
@@ -650,6 +654,5 @@ __device__ __noinline__ void block_kde_bandwidth(const double* pts, int N, int d
             : (L.U == 5) ? coord_bandwidth<5>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity)
                          : coord_bandwidth<6>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity);
   }
-  IIF_PHASE_FLUSH();
   *parity_io = parity;
 }

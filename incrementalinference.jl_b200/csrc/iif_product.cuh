@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
 iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const double* __restrict__ randU,
                    const double* __restrict__ randN, const TreeStruct* __restrict__ trees) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  IIF_PHASE_ZERO();
+  IIF_PHASE_BEGIN();
   const ProdTask t = tasks[blockIdx.x];
   const int F = t.F, N = t.N, d = t.dim;
   const int32_t cm = t.circ_mask;
@@ -136,12 +138,16 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     if (t.out_labels) for (int s = tid; s < N; s += IIF_NT) t.out_labels[s] = s;
     __syncthreads();
   } else {
+    IIF_PHASE(8);
     // ---- 1. ball trees: per level, rank-sort every node along its most-spread coordinate
     int16_t* permA = sm.perm;
     int16_t* permB = sm.perm + F * N;
     for (int i = tid; i < F * N; i += IIF_NT) permA[i] = (int16_t)(i % N);
     __syncthreads();
-    for (int l = 0; l < L; ++l) {
+    // one coordinate: the root's rank sort already orders every descendant node (same key, same tie-break),
+    // so the deeper levels would be identity permutations
+    const int Lsort = (d == 1) ? 1 : L;
+    for (int l = 0; l < Lsort; ++l) {
       for (int it = tid; it < F * N; it += IIF_NT) {
         const int j = it / N, pos = it - j * N;
         const int z = T.lev_off[l] + T.node_at[l * N + pos];
@@ -150,9 +156,9 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         const double* Pj = sm.P + (size_t)j * N * d;
         const int me = pj[pos];
         if (lo == hi) { permB[j * N + pos] = (int16_t)me; continue; }
-        int best = -1;
+        int best = (d == 1) ? 0 : -1;
         double bs = -1.0;
-        for (int c = 0; c < d; ++c) {
+        for (int c = 0; c < d && d > 1; ++c) {
           if (!((masks[j] >> c) & 1)) continue;
           double mn = INFINITY, mx = -INFINITY;
           for (int i = lo; i <= hi; ++i) {
@@ -174,6 +180,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
       __syncthreads();
       int16_t* tmp = permA; permA = permB; permB = tmp;
     }
+    IIF_PHASE(9);
     // ---- node statistics: mean and (kernel variance + member spread) per level-list entry.
     // Two-pass mean / squared deviation; nodes with more than 32 members are reduced by a whole warp
     // (lanes stride the members), the rest by one thread each.
@@ -220,6 +227,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     for (int z = tid; z < nn; z += IIF_NT) sm.wt[z] = (double)(T.hi[z] - T.lo[z] + 1) / (double)N;
     __syncthreads();
 
+    IIF_PHASE(10);
     // ---- 2./3. multiscale Gibbs: G lanes per output sample (G = largest power of two <= threads/N).
     // Every lane owns a contiguous block of the level's candidate nodes, accumulates its weights in
     // chunks (kept in registers), a group scan locates the lane and chunk holding the inverse-CDF
@@ -270,6 +278,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
           K[idx] = exp_neg(-0.5 * pexp) * pre;
         }
         __syncthreads();
+        IIF_PHASE(7);
         if (live) {
           const double* wl = sm.wt + z0;
           const int B = (nz + G - 1) / G;
@@ -329,6 +338,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
             }
           }
         }
+        IIF_PHASE(15);
       }
       __syncthreads();  // K (aliases the leave-one-out scratch) is dead from here on
     } else if (live) {
@@ -450,6 +460,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         }
       }
     }
+    IIF_PHASE(11);
     if (live) {
       // samplePoint: draw from the product of the selected leaf kernels
       if (gl == 0) {
@@ -483,8 +494,10 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
       }
     }
     __syncthreads();
+    IIF_PHASE(12);
     // ---- 4. re-bandwidth of the posterior (getKDEManifoldBandwidths on the result)
     block_kde_bandwidth<1>(sm.post, N, d, cm, &trees[N], sm.xa, sm.xb, sm.scr, sm.red, &parity, bw);
+    IIF_PHASE(13);
   }
 
   // ---- outputs: explicit buffers and / or setBelief! into the destination slot
@@ -504,6 +517,8 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     }
   }
   if (tid == 0 && t.out_status) *t.out_status = IIF_OK;
+  IIF_PHASE(14);
+  IIF_PHASE_FLUSH();
 }
 
 // separator-message adoption: slot b := slot a (updateSubFgFromDownMsgs!, TreeMessageUtils.jl:66)
@@ -540,9 +555,14 @@ iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restr
   double* xa = pts + (size_t)t.N * IIF_MAX_DIM;
   double* xb = xa + t.N;
   double* scr = xb + loo_x2_doubles(t.N);
+  IIF_PHASE_ZERO();
+  IIF_PHASE_BEGIN();
   for (int i = threadIdx.x; i < t.N * t.dim; i += IIF_NT) pts[i] = t.pts[i];
   __syncthreads();
+  IIF_PHASE(8);
   double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
   block_kde_bandwidth<2>(pts, t.N, t.dim, t.circ_mask, &trees[t.N], xa, xb, scr, red, &parity, bw);
   if (threadIdx.x < IIF_MAX_DIM) t.out_bw[threadIdx.x] = threadIdx.x < t.dim ? bw[threadIdx.x] : 0.0;
+  IIF_PHASE(13);
+  IIF_PHASE_FLUSH();
 }

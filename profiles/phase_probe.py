@@ -1,7 +1,6 @@
 """Kernel-development probe: builds a copy of the library with -DIIF_PHASES (clock64 marks inside the
-leave-one-out objective), runs single-belief bandwidth searches and prints cycles per phase and per
-objective evaluation for an on-critical-path thread (tid 0) and an off-path one.
-usage (GPU box): python profiles/phase_probe.py [N] [threads-independent]"""
+kernels), runs ONE belief through the bandwidth, convolution and product kernels and prints the cycles
+per phase seen by one thread.  usage (GPU box): python profiles/phase_probe.py [N] [tid ...]"""
 import ctypes as C
 import os
 import subprocess
@@ -14,34 +13,59 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 CSRC = os.path.join(ROOT, "incrementalinference.jl_b200", "csrc")
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-NAMES = ["rows(hot loop)", "barrier1", "gather", "part+barrier2", "partsum+log+warpsum", "barrier3", "tot",
-         "-", "-", "-"]
-for tid in (0, 160, 480):
+TIDS = [int(a) for a in sys.argv[2:]] or [0, 160]
+LOO = ["loo rows (hot loop)", "loo barrier1", "loo gather", "loo part+barrier2", "loo partsum+log+warpsum",
+       "loo barrier3", "loo tot", "-"]
+KER = {"bandwidth": {8: "load", 13: "search+write"},
+       "conv": {8: "setup/load", 9: "measurements+recipe+labels", 10: "inflate/solve", 11: "write proposal",
+                12: "bandwidth (all)", 13: "write bw/slot"},
+       "product": {8: "load", 9: "ball trees", 10: "node stats", 7: "gibbs: pair-weight tables", 15: "gibbs: label draws",
+                   11: "gibbs: rest", 12: "sample", 13: "bandwidth (all)", 14: "write"}}
+from iifb200 import _abi as A, compile as CP  # noqa: E402
+import parity_cases as PC  # noqa: E402
+
+for tid in TIDS:
     lib = os.path.join(CSRC, f"libiifb200_ph{tid}.so")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                            "-shared", "-DIIF_PHASES", f"-DIIF_PHASE_TID={tid}", "-o", lib, os.path.join(CSRC, "iifb200.cu")])
-    import importlib
-    from iifb200 import _abi as A
     A._lib = None
     L = A.load_library(lib)
     L.iifb200_debug_phases.argtypes = [C.POINTER(C.c_longlong), C.c_int]
-    import parity_cases as PC
-    P, xs, fs = PC.chain_problem(n=3, N=100, seed=1)
+    P, xs, fs = PC.chain_problem(n=3, N=N, seed=1)
     eng = P.engine()
     R = np.random.default_rng(0)
+    buf = (C.c_longlong * 16)()
+
+    def report(name, run):
+        for rep in range(3):
+            L.iifb200_debug_phases(buf, 1)
+            run()
+            ms = eng.last_elapsed_ms()
+        L.iifb200_debug_phases(buf, 0)
+        v = np.array(list(buf), dtype=np.float64)
+        print(f"--- {name} kernel, one belief, N={N}, tid {tid}: {ms*1e3:.1f} us (events around the launch)")
+        for k, nm in KER[name].items():
+            print(f"   {nm:28s} {v[k]:9.0f} cyc  {v[k]/1.965e3:6.1f} us")
+        print("   inside the bandwidth search:")
+        for k in range(7):
+            if name == "product" and k == 7:
+                continue
+            print(f"      {LOO[k]:25s} {v[k]:9.0f} cyc  {v[k]/1.965e3:6.1f} us")
+
     pts = R.normal(0, 1, (1, N, 1))
     Ns = np.full(1, N, dtype=np.int32); Ds = np.ones(1, dtype=np.int32); Ms = np.zeros(1, dtype=np.int32)
     out = np.zeros(4)
-    buf = (C.c_longlong * 16)()
-    for rep in range(3):
-        L.iifb200_debug_phases(buf, 1)
-        eng._check(L.iifb200_kde_bandwidth(eng.ctx, 1, A.as_ip(Ns), A.as_ip(Ds), A.as_ip(Ms), A.as_dp(pts), A.as_dp(out)), "bw")
-        ms = eng.last_elapsed_ms()
-    L.iifb200_debug_phases(buf, 0)
-    v = np.array(list(buf), dtype=np.float64)
-    print(f"tid {tid}: kernel {ms*1e3:.1f} us, bw {out[0]:.6f}; cycles per phase (total over the search): ")
-    for k in range(7):
-        print(f"   {NAMES[k]:22s} {v[k]:10.0f}")
-    print(f"   sum {v[:7].sum():.0f} cycles = {v[:7].sum()/1.965e3:.1f} us at 1965 MHz")
+    report("bandwidth", lambda: eng._check(L.iifb200_kde_bandwidth(eng.ctx, 1, A.as_ip(Ns), A.as_ip(Ds), A.as_ip(Ms),
+                                                                    A.as_dp(pts), A.as_dp(out)), "bw"))
+    ops = CP.make_conv_ops([dict(factor=fs[1], sfidx=2, N=N, call_id=16)])
+    report("conv", lambda: eng.conv_batch(ops, 1))
+    a = R.normal(0, 1, (1, 2, N, 1))
+    bws = np.zeros((2, 4)); bws[:, 0] = 0.4
+    pop = (A.ProductOp * 1)()
+    pop[0].dim, pop[0].circ_mask, pop[0].nfactors, pop[0].N, pop[0].call_id = 1, 0, 2, N, 16
+    pop[0].randu_off = pop[0].randn_off = -1
+    o2 = np.zeros((1, N, 1)); obw = np.zeros(4)
+    report("product", lambda: eng._check(L.iifb200_product_batch(eng.ctx, 1, pop, A.as_dp(a), A.as_dp(bws), None, None, None,
+                                                                  None, A.as_dp(o2), A.as_dp(obw), None), "prod"))
     eng.close()
     os.remove(lib)
