@@ -27,8 +27,8 @@
 #ifndef IIF_PHASE_TID
 #define IIF_PHASE_TID 0
 #endif
-__device__ long long g_iif_phase[16];
-__shared__ long long s_iif_phase[16];  // shared accumulators: a mark costs one LDS/STS round trip, not a global one
+__device__ long long g_iif_phase[32];
+__shared__ long long s_iif_phase[32];  // shared accumulators: a mark costs one LDS/STS round trip, not a global one
 #define IIF_PHASE_BEGIN() long long ph_t_ = clock64()
 #define IIF_PHASE(k)                                             \
   do {                                                           \
@@ -41,12 +41,12 @@ __shared__ long long s_iif_phase[16];  // shared accumulators: a mark costs one 
 #define IIF_PHASE_ZERO()                                                                        \
   do {                                                                                          \
     if (threadIdx.x == IIF_PHASE_TID && blockIdx.x == 0)                                        \
-      for (int k_ = 0; k_ < 16; ++k_) s_iif_phase[k_] = 0;                                      \
+      for (int k_ = 0; k_ < 32; ++k_) s_iif_phase[k_] = 0;                                      \
   } while (0)
 #define IIF_PHASE_FLUSH()                                                                       \
   do {                                                                                          \
     if (threadIdx.x == IIF_PHASE_TID && blockIdx.x == 0)                                        \
-      for (int k_ = 0; k_ < 16; ++k_) g_iif_phase[k_] += s_iif_phase[k_];                       \
+      for (int k_ = 0; k_ < 32; ++k_) g_iif_phase[k_] += s_iif_phase[k_];                       \
   } while (0)
 #else
 #define IIF_PHASE_BEGIN()
@@ -525,6 +525,8 @@ __device__ __forceinline__ double loo_nll(const double* __restrict__ x2, const L
   }
   parity ^= 1;
   IIF_PHASE(6);
+  IIF_PHASE(30);
+  IIF_PHASE(31);
   return (t0 + t1) * negInvN;
 }
 

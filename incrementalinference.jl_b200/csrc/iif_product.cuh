@@ -265,17 +265,33 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
           node[j] = z0 + T.child[nd] + (T.hi[nd] > T.lo[nd] ? 1 : 0);
         }
         __syncthreads();  // the previous level's K is no longer read
-        for (int idx = tid; idx < nz * nz; idx += IIF_NT) {
-          const int a = idx / nz, b = idx - a * nz;
-          double pexp = 0.0, pre = 1.0;
-          for (int c = 0; c < d; ++c) {
-            if (!((both >> c) & 1)) continue;
-            const double dl = mdiff(m0[(z0 + a) * d + c], m1[(z0 + b) * d + c], is_circ(cm, c));
-            const double rs = rsqrt(v0[(z0 + a) * d + c] + v1[(z0 + b) * d + c]);
-            pexp = fma(dl * dl, rs * rs, pexp);
-            pre *= rs;
+        {
+          // four table entries per thread in lockstep (independent rsqrt / exp chains)
+          const int nzz = nz * nz;
+          const float invnz = 1.0f / (float)nz;
+          for (int base = tid; base < nzz; base += 4 * IIF_NT) {
+            double arg[4], pre[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = min(base + u * IIF_NT, nzz - 1);
+              const int a = (int)(((float)idx + 0.5f) * invnz), b = idx - a * nz;  // exact: nz <= 256
+              double pexp = 0.0, pr = 1.0;
+              for (int c = 0; c < d; ++c) {
+                if (!((both >> c) & 1)) continue;
+                const double dl = mdiff(m0[(z0 + a) * d + c], m1[(z0 + b) * d + c], is_circ(cm, c));
+                const double rs = rsqrt(v0[(z0 + a) * d + c] + v1[(z0 + b) * d + c]);
+                pexp = fma(dl * dl, rs * rs, pexp);
+                pr *= rs;
+              }
+              arg[u] = -0.5 * pexp;
+              pre[u] = pr;
+            }
+            double e[4];
+            exp_negU<4>(arg, e);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (base + u * IIF_NT < nzz) K[base + u * IIF_NT] = e[u] * pre[u];
           }
-          K[idx] = exp_neg(-0.5 * pexp) * pre;
         }
         __syncthreads();
         IIF_PHASE(7);
@@ -283,14 +299,28 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
           const double* wl = sm.wt + z0;
           const int B = (nz + G - 1) / G;
           const int zb = gl * B, ze = min(zb + B, nz);
+          const int CHL = (B + 7) >> 3;  // every lane splits its block into <= 8 chunks of CHL candidates
           for (int it = 0; it < niter; ++it) {
             for (int j = 0; j < 2; ++j) {
               // density 0 scans column b of K (stride nz), density 1 scans row a (stride 1)
               const int other = node[1 - j] - z0;
               const double* Kb = (j == 0) ? K + other : K + (size_t)other * nz;
               const int stride = (j == 0) ? nz : 1;
-              double Tl = 0.0;
-              for (int z = zb; z < ze; ++z) Tl += wl[z] * Kb[(size_t)z * stride];
+              const uint32_t idx = (uint32_t)(((s * L + (l - 1)) * niter + it) * 2 + j);
+              const double u = (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx]
+                                                                      : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
+              IIF_PHASE(16);
+              // chunk sums: eight independent accumulation chains
+              double ct[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              for (int e = 0; e < CHL; ++e) {
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                  const int z = zb + ch * CHL + e;
+                  if (z < ze) ct[ch] = fma(wl[z], Kb[(size_t)z * stride], ct[ch]);
+                }
+              }
+              const double Tl = ((ct[0] + ct[1]) + (ct[2] + ct[3])) + ((ct[4] + ct[5]) + (ct[6] + ct[7]));
+              IIF_PHASE(17);
               double inc = Tl;
               for (int o = 1; o < G; o <<= 1) {
                 const double y = __shfl_up_sync(gmask, inc, o, G);
@@ -298,18 +328,27 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
               }
               const double off = inc - Tl;
               const double tot = __shfl_sync(gmask, inc, G - 1, G);
-              const uint32_t idx = (uint32_t)(((s * L + (l - 1)) * niter + it) * 2 + j);
-              const double u = (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx]
-                                                                      : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
+              IIF_PHASE(18);
               int pick;
               if (tot > 1e-290) {
                 const double thr = u * tot;
                 int mypick = -1;
                 if ((zb < ze) && (thr >= off) && (thr < off + Tl)) {
-                  double cum = off;
-                  mypick = ze - 1;
-                  for (int z = zb; z < ze; ++z) {
-                    cum += wl[z] * Kb[(size_t)z * stride];
+                  // the chunk holding the crossing, then only that chunk is walked again
+                  double run = off;
+                  int cb = zb;
+                  bool go = true;
+#pragma unroll
+                  for (int ch = 0; ch < 7; ++ch) {
+                    go = go && (thr >= run + ct[ch]) && (cb + CHL < ze);
+                    run += go ? ct[ch] : 0.0;
+                    cb += go ? CHL : 0;
+                  }
+                  const int ce = min(cb + CHL, ze);
+                  mypick = ce - 1;
+                  double cum = run;
+                  for (int z = cb; z < ce; ++z) {
+                    cum = fma(wl[z], Kb[(size_t)z * stride], cum);
                     if (thr < cum) { mypick = z; break; }
                   }
                 }
@@ -334,6 +373,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
                 }
                 pick = bz;
               }
+              IIF_PHASE(20);
               node[j] = z0 + pick;
             }
           }

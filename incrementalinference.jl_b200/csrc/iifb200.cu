@@ -948,9 +948,9 @@ int32_t iifb200_set_stream(iifb200_ctx* ctx, void* stream) {
 void* iifb200_stream(iifb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 #ifdef IIF_PHASES
 // development only (profiles/phase_probe.py): read and optionally reset the phase clocks
-void iifb200_debug_phases(long long* out16, int reset) {
-  if (out16) cudaMemcpyFromSymbol(out16, g_iif_phase, sizeof(long long) * 16);
-  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_iif_phase, z, sizeof(z)); }
+void iifb200_debug_phases(long long* out32, int reset) {
+  if (out32) cudaMemcpyFromSymbol(out32, g_iif_phase, sizeof(long long) * 32);
+  if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(g_iif_phase, z, sizeof(z)); }
 }
 #endif
 float iifb200_last_elapsed_ms(iifb200_ctx* ctx) {

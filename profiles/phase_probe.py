@@ -20,6 +20,7 @@ KER = {"bandwidth": {8: "load", 13: "search+write"},
        "conv": {8: "setup/load", 9: "measurements+recipe+labels", 10: "inflate/solve", 11: "write proposal",
                 12: "bandwidth (all)", 13: "write bw/slot"},
        "product": {8: "load", 9: "ball trees", 10: "node stats", 7: "gibbs: pair-weight tables", 15: "gibbs: label draws",
+                   16: "  draw: uniform+misc", 17: "  draw: chunk sums", 18: "  draw: group scan", 20: "  draw: pick",
                    11: "gibbs: rest", 12: "sample", 13: "bandwidth (all)", 14: "write"}}
 from iifb200 import _abi as A, compile as CP  # noqa: E402
 import parity_cases as PC  # noqa: E402
@@ -34,7 +35,7 @@ for tid in TIDS:
     P, xs, fs = PC.chain_problem(n=3, N=N, seed=1)
     eng = P.engine()
     R = np.random.default_rng(0)
-    buf = (C.c_longlong * 16)()
+    buf = (C.c_longlong * 32)()
 
     def report(name, run):
         for rep in range(3):
@@ -46,6 +47,7 @@ for tid in TIDS:
         print(f"--- {name} kernel, one belief, N={N}, tid {tid}: {ms*1e3:.1f} us (events around the launch)")
         for k, nm in KER[name].items():
             print(f"   {nm:28s} {v[k]:9.0f} cyc  {v[k]/1.965e3:6.1f} us")
+        print(f"   [cost of one phase mark: {v[31] / max(v[30] and 18, 1):.0f} cycles if 18 evaluations; raw {v[30]:.0f} {v[31]:.0f}]")
         print("   inside the bandwidth search:")
         for k in range(7):
             if name == "product" and k == 7:
