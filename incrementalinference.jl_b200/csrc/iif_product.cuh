@@ -42,6 +42,7 @@ struct ProdSmem {
   double* bwk;    // F*IIF_MAX_DIM kernel bandwidths
   double* wt;     // nn node weights (count / N), shared by all densities
   double* minvar; // F*(L+1)*d smallest node variance per level
+  const double* tab;  // 16-entry 2^(j/16) table
   int16_t* perm;  // 2*F*N
 };
 
@@ -56,7 +57,7 @@ __host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn, i
   size_t scr = (size_t)IIF_LOO_SCRATCH_N(N);
   if (F == 2 && gibbs_tab(N) && (size_t)N * N > scr) scr = (size_t)N * N;
   dbl += scr;
-  size_t i16 = 2 * (size_t)F * N;
+  size_t i16 = 2 * (size_t)F * N + (size_t)(L + 2) + 3 * (size_t)nn + (size_t)L * N;  // permutations + tree structure
   return dbl * sizeof(double) + ((i16 * sizeof(int16_t) + 7) / 8) * 8;
 }
 
@@ -86,7 +87,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
   const ProdTask t = tasks[blockIdx.x];
   const int F = t.F, N = t.N, d = t.dim;
   const int32_t cm = t.circ_mask;
-  const TreeStruct T = trees[N];
+  TreeStruct T = trees[N];
   const int nn = T.nn, L = T.L;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int parity = 0;
@@ -122,8 +123,24 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     }
     sm.perm = reinterpret_cast<int16_t*>(p);
   }
+  {
+    // the tree structure (level lists, node ranges, children) is walked at every level by every thread: stage
+    // the whole blob (lev_off | lo | hi | child | node_at, contiguous in global memory) in shared memory
+    int16_t* ts = sm.perm + 2 * (size_t)F * N;
+    const int16_t* gsrc = T.lev_off;
+    const int tot = (L + 2) + 3 * nn + L * N;
+    for (int i = tid; i < tot; i += IIF_NT) ts[i] = gsrc[i];
+    T.lev_off = ts;
+    T.lo = ts + (L + 2);
+    T.hi = T.lo + nn;
+    T.child = T.hi + nn;
+    T.node_at = T.child + nn;
+  }
   const int32_t fullmask = (1 << d) - 1;
   __shared__ int32_t masks[IIF_MAX_FACTORS];
+  __shared__ double gtab[16];  // 2^(j/16) for gauss_negU
+  if (tid < 16) gtab[tid] = IIF_EXP2TAB[tid];
+  sm.tab = gtab;
   if (tid < F) masks[tid] = t.mask[tid] ? t.mask[tid] : fullmask;
   for (int i = tid; i < F * N * d; i += IIF_NT) sm.P[i] = t.dens_pts[i];
   for (int i = tid; i < F * IIF_MAX_DIM; i += IIF_NT) sm.bwk[i] = t.dens_bw[i];
@@ -265,7 +282,27 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
           node[j] = z0 + T.child[nd] + (T.hi[nd] > T.lo[nd] ? 1 : 0);
         }
         __syncthreads();  // the previous level's K is no longer read
-        {
+        if (l == L && d == 1 && !is_circ(cm, 0)) {
+          // leaf level, one Euclid coordinate: every node is a single kernel of variance h_j^2, so the table is
+          // the Gaussian kernel matrix between the two point sets: rs exp(-(ma - mb)^2 rs^2 / 2), rs constant
+          const int nzz = nz * nz;
+          const float invnz = 1.0f / (float)nz;
+          const double rs = rsqrt(v0[z0] + v1[z0]);
+          const double sc = IIF_GSCALE * rs;
+          for (int base = tid; base < nzz; base += 4 * IIF_NT) {
+            double zz[4], e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = min(base + u * IIF_NT, nzz - 1);
+              const int a = (int)(((float)idx + 0.5f) * invnz), b = idx - a * nz;
+              zz[u] = (m0[z0 + a] - m1[z0 + b]) * sc;
+            }
+            gauss_negU<4>(zz, sm.tab, e);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (base + u * IIF_NT < nzz) K[base + u * IIF_NT] = e[u] * rs;
+          }
+        } else {
           // four table entries per thread in lockstep (independent rsqrt / exp chains)
           const int nzz = nz * nz;
           const float invnz = 1.0f / (float)nz;
@@ -536,7 +573,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     __syncthreads();
     IIF_PHASE(12);
     // ---- 4. re-bandwidth of the posterior (getKDEManifoldBandwidths on the result)
-    block_kde_bandwidth<1>(sm.post, N, d, cm, &trees[N], sm.xa, sm.xb, sm.scr, sm.red, &parity, bw);
+    block_kde_bandwidth<1>(sm.post, N, d, cm, &T, sm.xa, sm.xb, sm.scr, sm.red, &parity, bw);
     IIF_PHASE(13);
   }
 

@@ -445,8 +445,10 @@ static int pick_threads(iifb200_ctx* ctx, int grid, int maxN, int small_min = 12
   small = std::min(small, IIF_MAX_THREADS);
   return (grid >= 2 * ctx->num_sms) ? small : IIF_MAX_THREADS;
 }
+// product kernel: 256-thread CTAs in wide launches put two CTAs on an SM (shared memory allows two), so one
+// CTA's barrier and latency stalls are covered by the other; narrow launches split each product 512 ways.
 static int pick_threads_prod(iifb200_ctx* ctx, int grid, int maxN) {
-  static const int wide = env_int("IIFB200_PROD_WIDE_THREADS", 0);
+  static const int wide = env_int("IIFB200_PROD_WIDE_THREADS", 256);
   if (wide <= 0 || grid < 2 * ctx->num_sms) return IIF_MAX_THREADS;
   return std::min(IIF_MAX_THREADS, std::max(wide, (maxN + 31) / 32 * 32));
 }
