@@ -81,6 +81,21 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic_per_block():
+    """DRAM bytes per convolution (CTA) of iif_conv_kernel from the committed `ncu --set full` capture
+    (profiles/r01_kernels.json, written by profiles/summarise.py); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r01_kernels.json")
+    if not os.path.exists(p):
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for name, d in json.load(open(p)).items():
+        if "iif_conv_kernel" in d.get("kernel", "") and "dram__bytes_read.sum" in d:
+            rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+            tot = float(rd[0]) * unit.get(rd[1], 1.0) + float(wr[0]) * unit.get(wr[1], 1.0)
+            return tot / max(float(d["launch__grid_size"][0]), 1.0), name
+    return None, None
+
+
 def conv_bytes(plan):
     """algorithmic HBM bytes of every convolution of the plan, device-RNG mode:
     8*N*[(a-1)*P + P] (sources + target init) + 4*N (labels) + 8*N*P + 16*d (proposal, bw, ipc)."""
@@ -312,12 +327,28 @@ def run_b200(args, rank, world, local_rank):
         cms, cl, cb = prof["conv"]
         byts = conv_bytes(plan) * (my_conv / max(total_conv, 1))
         ach = byts / (cms * 1e-3) / 1e9 if cms > 0 else 0.0
+        tpb, tsrc = ncu_traffic_per_block()
+        # FP64-pipe view of the same kernel: 13 FP64 instructions per Gaussian kernel value, N(N-1)/2 values per
+        # objective evaluation, ~18 evaluations per bandwidth search; the pipe retires one
+        # warp instruction per 2 cycles per SM sub-partition (profiles/ubench/fp64_pipe.cu, measured).
+        n_eval, fp64_per_pair = 18, 13
+        pairs = NPART * (NPART - 1) // 2
+        sm_hz = 1e6 * float(pk.get("sm_max_mhz", 1965.0))
+        floor_s = cb * pairs * n_eval * fp64_per_pair / 32.0 * 2.0 / 4.0 / sm_hz / 148.0
         roof = {"bound": "hbm", "kernel": "iif_conv_kernel", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": ach / pk["hbm_gbs"],
+                "traffic": (tpb * cb / max(cl, 1)) if tpb is not None else None,
+                "traffic_source": (f"profiles/{tsrc}.ncu-rep summary in profiles/r01_kernels.json: dram bytes per CTA x "
+                                   f"average CTAs per launch") if tpb is not None else None,
+                "algorithmic_bytes_per_launch": byts / max(cl, 1),
+                "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)",
                 "launch_ms_avg": cms / max(cl, 1), "launches": cl, "blocks": cb,
                 "kernel_ms": {k: v[0] for k, v in prof.items()},
-                "note": "FP64-issue bound, not HBM bound: the exact O(N^2) leave-one-out bandwidth search "
-                        "dominates (see DESIGN.md); traffic: see profiles/"}
+                "fp64_pipe": {"floor_ms": 1e3 * floor_s, "frac_of_floor": (1e3 * floor_s) / cms if cms > 0 else None,
+                              "model": "13 FP64 instr/pair x N(N-1)/2 pairs x 18 evaluations, 2 cycles per warp "
+                                       "instruction per SM sub-partition, 148 SMs"},
+                "note": "FP64-pipe / issue bound, not HBM bound: the exact O(N^2) leave-one-out bandwidth search "
+                        "dominates (DESIGN.md section 4); the HBM fraction is reported because the metric asks for it"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -439,17 +439,21 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
+// CTA size of a launch.  A belief's work can be split over 128..512 threads; registers (126 per thread)
+// allow 65536 / (126 * threads) CTAs per SM, shared memory caps the convolution at 4 and the product at 2.
+// The largest CTA whose launch still fits in ONE round of resident CTAs wins (per-belief latency is what a
+// narrow wave costs); launches beyond that use the smallest CTA (most beliefs in flight per SM).
 static int pick_threads(iifb200_ctx* ctx, int grid, int maxN, int small_min = 128) {
   static const int wide = env_int("IIFB200_WIDE_THREADS", 0);  // tuning knob: CTA size of wide launches
-  int small = std::max(wide > 0 ? wide : small_min, (maxN + 31) / 32 * 32);
-  small = std::min(small, IIF_MAX_THREADS);
-  return (grid >= 2 * ctx->num_sms) ? small : IIF_MAX_THREADS;
+  const int fit = (maxN + 31) / 32 * 32;
+  int small = std::min(std::max(wide > 0 ? wide : small_min, fit), IIF_MAX_THREADS);
+  if (grid <= ctx->num_sms) return IIF_MAX_THREADS;
+  if (grid <= 2 * ctx->num_sms) return std::min(IIF_MAX_THREADS, std::max(256, fit));
+  return small;
 }
-// product kernel: 256-thread CTAs in wide launches put two CTAs on an SM (shared memory allows two), so one
-// CTA's barrier and latency stalls are covered by the other; narrow launches split each product 512 ways.
 static int pick_threads_prod(iifb200_ctx* ctx, int grid, int maxN) {
   static const int wide = env_int("IIFB200_PROD_WIDE_THREADS", 256);
-  if (wide <= 0 || grid < 2 * ctx->num_sms) return IIF_MAX_THREADS;
+  if (wide <= 0 || grid <= ctx->num_sms) return IIF_MAX_THREADS;
   return std::min(IIF_MAX_THREADS, std::max(wide, (maxN + 31) / 32 * 32));
 }
 
