@@ -24,6 +24,7 @@
  *                               localProductAndUpdate!      src/services/GraphProductOperations.jl:136-155
  *                               solveCliqDownFrontalProducts! src/CliqueStateMachine/services/CliqStateMachineUtils.jl:479-571
  *   iifb200_kde_bandwidth    <- AMP.manikde! bandwidth (call sites ApproxConv.jl:38-41, FGOSUtils.jl:118-128)
+ *   iifb200_ppe_batch        <- calcPPE / setPPE!           src/services/FGOSUtils.jl:237-278
  *   belief slots             <- VariableNodeData.val/.bw, TreeBelief   src/entities/BeliefTypes.jl:47-57
  *   iif_factor_desc          <- CommonConvWrapper           src/entities/FactorOperationalMemory.jl:21-70
  *   iif_solver_params        <- SolverParams                src/entities/SolverParams.jl:12-75
@@ -225,6 +226,13 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
 int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, const int32_t* dim,
                               const int32_t* circ_mask, const double* pts /* packed */,
                               double* out_bw /* K x IIF_MAX_DIM */);
+
+/* Point estimates of V device-resident beliefs (calcPPE, src/services/FGOSUtils.jl:237-278; setPPE! at CSM
+ * step 5, CliqueStateMachine.jl:933-939): out_mean = calcMean, out_max = getKDEMax (per coordinate, first
+ * maximum of the marginal KDE on a 200-point grid over the 10 %-extended point range).  Outputs are HOST
+ * buffers of V x IIF_MAX_DIM doubles (coordinates; the "suggested" estimate is the mean). */
+int32_t iifb200_ppe_batch(iifb200_ctx* ctx, int32_t V, const int32_t* slots, double* out_mean,
+                          double* out_max);
 
 /* V independent propagateBelief calls on device-resident slots (one launch sequence).
  * Posteriors are written into out_slot on the device; nothing is copied to the host. */

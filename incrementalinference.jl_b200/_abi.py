@@ -94,6 +94,7 @@ SYMBOLS = {
     "iifb200_product_batch": (C.c_int32, [_vp, C.c_int32, P(ProductOp), _dp, _dp, _ip, _dp, _dp, _dp,
                                           _dp, _dp, _ip]),
     "iifb200_kde_bandwidth": (C.c_int32, [_vp, C.c_int32, _ip, _ip, _ip, _dp, _dp]),
+    "iifb200_ppe_batch": (C.c_int32, [_vp, C.c_int32, _ip, _dp, _dp]),
     "iifb200_propagate_batch": (C.c_int32, [_vp, C.c_int32, P(PropOp)]),
     "iifb200_schedule_build": (C.c_int32, [_vp, C.c_int32, _ip, C.c_int32, P(SchedOp), C.c_int32,
                                            P(PropOp), _ip]),

@@ -13,6 +13,7 @@
 #include <utility>
 #include <vector>
 
+#include "iif_ppe.cuh"
 #include "iif_product.cuh"
 
 #define IIFB200_VERSION 100
@@ -664,6 +665,37 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   CK(cudaMemcpyAsync(out_bw, d_bw, sizeof(double) * K * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_pts); cudaFree(d_bw); cudaFree(d_t);
+  return IIF_OK;
+}
+
+// ---- point estimates of V device-resident beliefs (calcPPE, FGOSUtils.jl:237-278) ------------------------
+int32_t iifb200_ppe_batch(iifb200_ctx* ctx, int32_t V, const int32_t* slots, double* out_mean, double* out_max) {
+  NEED_GRAPH();
+  if (V < 1 || !slots || !out_mean || !out_max) return fail(ctx, IIF_ERR_ARG, "ppe_batch: bad arguments");
+  for (int v = 0; v < V; ++v)
+    if (slots[v] < 0 || slots[v] >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "ppe_batch: slot out of range");
+  CK(cudaSetDevice(ctx->device));
+  double* d_out = nullptr;
+  PpeTask* d_t = nullptr;
+  CK(cudaMalloc(&d_out, sizeof(double) * 2 * V * IIF_MAX_DIM));
+  CK(cudaMalloc(&d_t, sizeof(PpeTask) * V));
+  std::vector<PpeTask> t(V);
+  for (int v = 0; v < V; ++v) {
+    t[v].slot = slots[v]; t[v]._pad = 0;
+    t[v].out_mean = d_out + (int64_t)v * IIF_MAX_DIM;
+    t[v].out_max = d_out + (int64_t)(V + v) * IIF_MAX_DIM;
+  }
+  CK(cudaMemcpyAsync(d_t, t.data(), sizeof(PpeTask) * V, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  iif_ppe_kernel<<<V, IIF_PPE_THREADS, 0, ctx->stream>>>(ctx->dg, d_t);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(out_mean, d_out, sizeof(double) * V * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_max, d_out + (int64_t)V * IIF_MAX_DIM, sizeof(double) * V * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_out); cudaFree(d_t);
   return IIF_OK;
 }
 

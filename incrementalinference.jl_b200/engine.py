@@ -163,6 +163,14 @@ class Engine:
                                                    A.as_dp(bw)), "kde_bandwidth")
         return bw[:d].copy()
 
+    def ppe_batch(self, slots):
+        """calcPPE of device-resident beliefs -> (mean, max) arrays of shape (V, IIF_MAX_DIM)"""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        V = len(sl)
+        mean, mx = np.zeros((V, A.IIF_MAX_DIM)), np.zeros((V, A.IIF_MAX_DIM))
+        self._check(self.lib.iifb200_ppe_batch(self.ctx, V, A.as_ip(sl), A.as_dp(mean), A.as_dp(mx)), "ppe_batch")
+        return mean, mx
+
     def propagate_batch(self, prop_ops, V):
         self._check(self.lib.iifb200_propagate_batch(self.ctx, V, prop_ops), "propagate_batch")
 

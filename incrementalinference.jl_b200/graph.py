@@ -188,6 +188,16 @@ class DFGVariable:
     infoPerCoord: np.ndarray
     initialized: bool = False
     index: int = -1
+    ppeDict: dict = field(default_factory=dict)   # solveKey -> MeanMaxPPE (getPPEDict)
+
+
+@dataclass
+class MeanMaxPPE:
+    """MeanMaxPPE (DFG): suggested / max / mean coordinates of a belief — calcPPE, FGOSUtils.jl:237-278"""
+    solveKey: str
+    suggested: np.ndarray
+    max: np.ndarray
+    mean: np.ndarray
 
 
 @dataclass

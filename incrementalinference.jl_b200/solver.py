@@ -171,6 +171,37 @@ def localProductAndUpdate(fg: G.FactorGraph, sym: str, setkde: bool = True):
     return mkd, ipc, lbl
 
 
+# --------------------------------------------------------------------------- §8f-3: point estimates
+def calcPPE(fg: G.FactorGraph, label: str, solveKey: str = "default") -> G.MeanMaxPPE:
+    """calcPPE(dfg, label) — FGOSUtils.jl:237-296: suggested = mean = calcMean(P), max = getKDEMax(P)."""
+    return calcPPEs(fg, [label], solveKey)[0]
+
+
+def calcPPEs(fg: G.FactorGraph, labels: Sequence[str], solveKey: str = "default") -> List[G.MeanMaxPPE]:
+    """calcPPE of several variables in one kernel launch (one CTA per belief)."""
+    ge = _engine(fg)
+    for l in labels:
+        if fg.variables[l].val.shape[0] < 1:
+            raise A.IIFB200Error(f"calcPPE: variable {l} has no belief points")
+    mean, mx = ge.eng.ppe_batch([ge.var_slot[l] for l in labels])
+    out = []
+    for k, l in enumerate(labels):
+        d = fg.variables[l].vartype.dim
+        out.append(G.MeanMaxPPE(solveKey, mean[k, :d].copy(), mx[k, :d].copy(), mean[k, :d].copy()))
+    return out
+
+
+def setPPE(fg: G.FactorGraph, label: str, solveKey: str = "default") -> G.MeanMaxPPE:
+    """setPPE!(dfg, label) — FGOSUtils.jl:546-570: calcPPE and store it in the variable's ppeDict."""
+    ppe = calcPPE(fg, label, solveKey)
+    fg.variables[label].ppeDict[solveKey] = ppe
+    return ppe
+
+
+def getPPE(fg: G.FactorGraph, label: str, solveKey: str = "default") -> G.MeanMaxPPE:
+    return fg.variables[label].ppeDict[solveKey]
+
+
 # --------------------------------------------------------------------------- §8f-1: graph init
 def factorCanInitFromOtherVars(fg: G.FactorGraph, fct: str, lbl: str) -> bool:
     """GraphInit.jl:39-103: every other variable of the factor is initialised (priors always can;
@@ -195,14 +226,68 @@ def doautoinit(fg: G.FactorGraph, lbl: str, singles: bool = True) -> bool:
     return True
 
 
-def initAll(fg: G.FactorGraph) -> None:
-    """initAll! — GraphInit.jl:495-556: sweep until nothing new can be initialised."""
+def initAll(fg: G.FactorGraph, batched: bool = True) -> None:
+    """initAll! — GraphInit.jl:495-556: sweep until nothing new can be initialised.
+
+    `batched`: the sequential sweep of doautoinit! calls is replayed on the
+    initialisation flags only, every propagateBelief it would run is recorded in order, the list is
+    levelised by slot hazards into waves of independent initialisations and executed as ONE schedule
+    (CUDA graph) on the device-resident graph; beliefs come back to the host once at the end.  Order,
+    factor selection and Philox call ids are those of the sequential sweep."""
+    if not batched:
+        for _ in range(len(fg.variables) + 1):
+            did = False
+            for l in fg.variables:
+                did |= doautoinit(fg, l)
+            if not did:
+                break
+        return
+    ge = _engine(fg)
+    N = fg.solverParams.N
+    init = {l: v.initialized for l, v in fg.variables.items()}
+    specs, order, reads, writes = [], [], [], []
     for _ in range(len(fg.variables) + 1):
         did = False
         for l in fg.variables:
-            did |= doautoinit(fg, l)
+            if init[l]:
+                continue
+            use = [f for f in fg.listNeighbors(l)
+                   if all(init[v] for v in fg.factors[f].variables if v != l)]        # factorCanInitFromOtherVars
+            if not use:
+                continue
+            use = use[:A.IIF_MAX_FACTORS]
+            slot = ge.var_slot[l]
+            specs.append(dict(target_slot=slot, out_slot=slot,
+                              factors=[(ge.fac_idx[f], fg.factors[f].variables.index(l) + 1) for f in use],
+                              N=N, call_id=ge.next_call(),
+                              any_multihypo=int(any(G.isMultihypo(fg.factors[f]) for f in use))))
+            order.append(l)
+            reads.append(sorted({ge.var_slot[v] for f in use for v in fg.factors[f].variables}))
+            writes.append([slot])
+            init[l] = True
+            did = True
         if not did:
             break
+    if not specs:
+        return
+    sched = [(A.S_PROPAGATE, k, 0) for k in range(len(specs))]
+    waves = TR._levelize(sched, reads, writes)
+    idx = sorted(range(len(sched)), key=lambda i: (waves[i], i))
+    nw = max(waves) + 1
+    wave_off = [0] * (nw + 1)
+    for i in idx:
+        wave_off[waves[i] + 1] += 1
+    for w in range(nw):
+        wave_off[w + 1] += wave_off[w]
+    sid = ge.eng.schedule_build(wave_off, CP.make_sched_ops([sched[i] for i in idx]), len(sched),
+                                CP.make_prop_ops(specs), len(specs))
+    ge.eng.schedule_run(sid)
+    ge.eng.sync()
+    for l in order:
+        pts, bw, ipc = ge.eng.download_belief(ge.var_slot[l])
+        v = fg.variables[l]
+        v.val, v.bw, v.infoPerCoord, v.initialized = pts, bw, ipc, True      # setValKDE!; the device copy is current
+    ge.eng.lib.iifb200_schedule_free(ge.eng.ctx, sid)
 
 
 # --------------------------------------------------------------------------- solveTree!
@@ -238,10 +323,20 @@ class TreeSolver:
         self.eng.sync()
         self.eng.download_arena(self.arena)
 
-    def store_to_graph(self):
-        for l in self.fg.variables:
+    def store_to_graph(self, ppe: bool = True):
+        """updateFromSubgraph (CSM step 5, CliqueStateMachine.jl:928-966): beliefs and point estimates go back
+        to the graph; the PPEs of all variables come from one iifb200_ppe_batch launch on the device-resident
+        posteriors."""
+        labels = list(self.fg.variables)
+        for l in labels:
             pts, bw, ipc = self.arena.get(self.plan.var_slot[l])
             G.setValKDE(self.fg, l, G.ManifoldKernelDensity(self.fg.variables[l].vartype, pts, bw), True, ipc)
+        if ppe:
+            mean, mx = self.eng.ppe_batch([self.plan.var_slot[l] for l in labels])
+            for k, l in enumerate(labels):
+                d = self.fg.variables[l].vartype.dim
+                self.fg.variables[l].ppeDict["default"] = G.MeanMaxPPE("default", mean[k, :d].copy(), mx[k, :d].copy(),
+                                                                       mean[k, :d].copy())
 
     def close(self):
         self.eng.close()

@@ -367,6 +367,44 @@ static int32_t sample_measurement(const iifo_graph* g, const iif_factor_desc* f,
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* point estimates — calcPPE (src/services/FGOSUtils.jl:237-278): mean = calcMean(P),   */
+/* max = getKDEMax(P).  getKDEMax / getKDERange live in KernelDensityEstimate.jl (un-vendored,     */
+/* PARITY UNPINNED): per coordinate, the marginal KDE is evaluated on a 200-point grid over the    */
+/* point range extended by 10 % on both sides and the first grid point of maximal density is taken. */
+/* ------------------------------------------------------------------------------------ */
+#define IIFO_PPE_GRID 200
+int32_t iifo_ppe(const double* pts, int32_t n, int32_t d, int32_t cm, const double* bw,
+                 double* mean_out, double* max_out) {
+  if (n < 1 || d < 1 || d > IIF_MAX_DIM) return IIF_ERR_ARG;
+  for (int c = 0; c < d; ++c) {
+    const int circ = is_circ(cm, c);
+    double s = 0, sn = 0, cs = 0, lo = pts[c], hi = pts[c];
+    for (int i = 0; i < n; ++i) {
+      double v = pts[i * d + c];
+      if (circ) { sn += sin(v); cs += cos(v); } else s += v;
+      if (v < lo) lo = v;
+      if (v > hi) hi = v;
+    }
+    mean_out[c] = circ ? atan2(sn, cs) : s / (double)n;
+    const double dr = 0.1 * (hi - lo);
+    const double a = lo - dr, b = hi + dr, step = (b - a) / (double)(IIFO_PPE_GRID - 1);
+    const double inv2h2 = 1.0 / (2.0 * bw[c] * bw[c]);
+    double best = -1.0, xbest = a;
+    for (int gi = 0; gi < IIFO_PPE_GRID; ++gi) {
+      const double X = a + step * (double)gi;
+      double y = 0;
+      for (int i = 0; i < n; ++i) {
+        double dl = mdiff(X, pts[i * d + c], circ);
+        y += exp(-dl * dl * inv2h2);
+      }
+      if (y > best) { best = y; xbest = X; }
+    }
+    max_out[c] = circ ? wrap_pi(xbest) : xbest;
+  }
+  return IIF_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* a14: KDE bandwidth — AMP.manikde! -> getKDEManifoldBandwidths -> KDE.kde!(x) "lcv"      */
 /* PARITY UNPINNED (upstream packages not vendored).                                       */
 /* ------------------------------------------------------------------------------------ */

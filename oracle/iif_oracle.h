@@ -87,6 +87,9 @@ int32_t iifo_residual(int32_t kind, int32_t d, int32_t circ_mask, int32_t zdim, 
 double iifo_std_basic_spread(const double* pts, int32_t n, int32_t d, int32_t circ_mask);
 
 /* a14: per-dimension leave-one-out likelihood bandwidth (manikde! with bw === nothing) */
+/* calcPPE (FGOSUtils.jl:237-278): mean and KDE-max point estimates of one belief */
+int32_t iifo_ppe(const double* pts, int32_t n, int32_t d, int32_t cm, const double* bw,
+                 double* mean_out, double* max_out);
 int32_t iifo_kde_bandwidth(const double* pts, int32_t n, int32_t d, int32_t circ_mask,
                            double* bw_out);
 /* LOO objective (negative average log likelihood) of one coordinate at bandwidth h */

@@ -153,6 +153,23 @@ def kde_bandwidth(pts, circ_mask=0):
     return bw[:d]
 
 
+def ppe(pts, bw, circ_mask=0):
+    """calcPPE: (mean, max) coordinates of one belief"""
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    if pts.ndim == 1:
+        pts = pts.reshape(-1, 1)
+    n, d = pts.shape
+    b = np.zeros(A.IIF_MAX_DIM)
+    b[:d] = np.asarray(bw, dtype=np.float64)[:d]
+    mean, mx = np.zeros(A.IIF_MAX_DIM), np.zeros(A.IIF_MAX_DIM)
+    L = lib()
+    L.iifo_ppe.restype = C.c_int32
+    L.iifo_ppe.argtypes = [_dp(pts).__class__, C.c_int32, C.c_int32, C.c_int32, _dp(b).__class__, _dp(mean).__class__,
+                           _dp(mx).__class__]
+    _check(L.iifo_ppe(_dp(pts), n, d, circ_mask, _dp(b), _dp(mean), _dp(mx)), "ppe")
+    return mean[:d], mx[:d]
+
+
 def loo_nll(x, h, circular=0):
     x = np.ascontiguousarray(x, dtype=np.float64)
     return lib().iifo_loo_nll(_dp(x), len(x), circular, h)

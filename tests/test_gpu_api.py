@@ -151,3 +151,53 @@ def test_unsupported_variable_dim_fails_loudly():
     fg = G.initfg(G.SolverParams(graphinit=False))
     with pytest.raises(AssertionError):
         G.addVariable(fg, "p", G.Position(7))
+
+
+def test_calcPPE_after_solveTree(built):
+    """setPPE! at CSM step 5 (CliqueStateMachine.jl:933-939): after solveTree every variable carries a
+    MeanMaxPPE; on the 4-variable chain of testBasicGraphs.jl:325-343 the estimates sit at 0, 1, 2, 3."""
+    fg = G.initfg(G.SolverParams(seed=3))
+    for k in range(4):
+        G.addVariable(fg, f"x{k}", G.ContinuousScalar)
+    G.addFactor(fg, ["x0"], G.Prior(G.Normal(0.0, 1.0)))
+    for k in range(3):
+        G.addFactor(fg, [f"x{k}", f"x{k + 1}"], G.LinearRelative(G.Normal(1.0, 0.01)))
+    SV.solveTree(fg)
+    for k in range(4):
+        ppe = SV.getPPE(fg, f"x{k}")
+        assert abs(ppe.suggested[0] - _pts(fg, f"x{k}").mean()) < 1e-9
+        assert abs(ppe.suggested[0] - k) < 0.75 and abs(ppe.max[0] - k) < 1.0
+    one = SV.calcPPE(fg, "x2")
+    assert np.allclose(one.mean, SV.getPPE(fg, "x2").mean) and np.allclose(one.max, SV.getPPE(fg, "x2").max)
+
+
+def test_initAll_batched_matches_sequential(built):
+    """the wavefront (one CUDA-graph schedule) form of initAll! reproduces the sequential
+    doautoinit! sweep (same order, factors and Philox call ids) on a chain and on a grid with loop closures."""
+    def chain(seed):
+        fg = G.initfg(G.SolverParams(seed=seed))
+        for k in range(12):
+            G.addVariable(fg, f"x{k}", G.ContinuousScalar)
+        G.addFactor(fg, ["x0"], G.Prior(G.Normal(0.0, 0.1)))
+        for k in range(11):
+            G.addFactor(fg, [f"x{k}", f"x{k + 1}"], G.LinearRelative(G.Normal(1.0, 0.1)))
+        return fg
+
+    def kaess(seed):
+        return W.generateGraph_Kaess(N=100, seed=seed, graphinit=False)
+
+    for make in (chain, kaess):
+        a, b = make(21), make(21)
+        SV.initAll(a, batched=False)
+        SV.initAll(b, batched=True)
+        for l in a.variables:
+            assert a.variables[l].initialized and b.variables[l].initialized
+            pa, pb = a.variables[l].val, b.variables[l].val
+            assert pa.shape == pb.shape
+            # identical streams; only the CTA size of a launch (hence a summation order) may differ
+            assert np.allclose(pa, pb, rtol=0, atol=1e-9), l
+            assert np.allclose(a.variables[l].bw, b.variables[l].bw, rtol=1e-7)
+    # the batched form leaves the graph solvable
+    c = chain(5)
+    SV.solveTree(c)
+    assert abs(_pts(c, "x11").mean() - 11.0) < 1.5

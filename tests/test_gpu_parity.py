@@ -109,3 +109,31 @@ def test_unsupported_and_bad_arguments_fail_loudly(built):
     with pytest.raises(IIFB200Error):
         eng.conv_batch(CP.make_conv_ops([dict(factor=fs[1], sfidx=2, N=1000, call_id=1)]), 1)
     eng.close()
+
+
+def test_ppe_parity(built):
+    """calcPPE: device mean / KDE-max of resident beliefs against the oracle.  The grid is
+    identical on both sides, so the max agrees exactly unless two grid points tie to the last ulp."""
+    import oracle as O
+    from iifb200 import graph as G
+    R = np.random.default_rng(12)
+    P = PC.Problem()
+    cases = [(G.ContinuousScalar, R.normal(3, 1, (100, 1))),
+             (G.ContinuousScalar, np.concatenate([R.normal(-2, 0.3, (30, 1)), R.normal(4, 0.3, (70, 1))])),
+             (G.Position(2), R.normal([1.0, -5.0], [0.5, 2.0], (150, 2))),
+             (G.Circular, PC.wrap(R.normal(3.0, 0.3, (200, 1)))),
+             (G.ContinuousScalar, R.normal(0, 1e-3, (17, 1)) + 1000.0)]
+    slots = [P.slot(vt, len(x), x) for vt, x in cases]
+    P.freeze()
+    eng = P.engine()
+    mean, mx = eng.ppe_batch(slots)
+    eng.close()
+    step_tol = 1.2 / 199
+    for k, (vt, x) in enumerate(cases):
+        s = slots[k]
+        bw = P.arena.bw[4 * s:4 * s + vt.dim]
+        om, ox = O.ppe(x, bw, vt.circ_mask)
+        assert np.allclose(mean[k, :vt.dim], om, rtol=0, atol=1e-11 * max(1.0, np.abs(x).max())), (k, mean[k], om)
+        rng_ = x.max(axis=0) - x.min(axis=0)
+        assert np.all(np.abs(mx[k, :vt.dim] - ox) <= 1e-12 + 0 * rng_) or \
+            np.all(np.abs(mx[k, :vt.dim] - ox) <= step_tol * rng_ * 1.0001), (k, mx[k], ox)

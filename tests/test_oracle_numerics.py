@@ -220,3 +220,26 @@ def test_mixture_prior_band_testMixtureLinearConditional():
     pts, *_ = P.oracle().conv(CP.make_conv_ops([dict(factor=f, sfidx=1, N=200, call_id=2)])[0])
     lo, hi = (np.abs(pts + 5) < 3).mean(), (np.abs(pts - 5) < 3).mean()
     assert lo > 0.2 and hi > 0.2 and 1 - lo - hi < 0.1
+
+
+def test_ppe_oracle_known_answers():
+    """calcPPE restatement (FGOSUtils.jl:237-278; getKDEMax from KDE.jl, parity unpinned): a hand-computable
+    two-kernel case, a bimodal case and the circular wrap."""
+    # kernels at 0, 0 and 1, h = 0.1: grid [-0.1, 1.1] with 200 points, the density peaks at the grid point
+    # nearest to 0
+    mean, mx = O.ppe(np.array([[0.0], [0.0], [1.0]]), [0.1])
+    step = 1.2 / 199
+    assert abs(mean[0] - 1.0 / 3.0) < 1e-15
+    assert abs(mx[0] - (-0.1 + round(0.1 / step) * step)) < 1e-12
+    R = np.random.default_rng(3)
+    x = np.concatenate([R.normal(-2, 0.3, (30, 1)), R.normal(4, 0.3, (70, 1))])
+    mean, mx = O.ppe(x, [0.2])
+    assert abs(mean[0] - x.mean()) < 1e-12 and abs(mx[0] - 4.0) < 0.3      # the heavier mode
+    # circular coordinate: points around +-pi; the mean is the extrinsic (atan2) mean, the max stays in [-pi, pi)
+    th = PC.wrap(R.normal(np.pi, 0.2, (80, 1)))
+    mean, mx = O.ppe(th, [0.1], circ_mask=1)
+    assert abs(abs(mean[0]) - np.pi) < 0.1 and -np.pi <= mx[0] < np.pi
+    # two coordinates are treated independently (marginals)
+    y = R.normal([1.0, -5.0], [0.5, 2.0], (100, 2))
+    mean, mx = O.ppe(y, [0.2, 0.8])
+    assert np.allclose(mean, y.mean(axis=0)) and abs(mx[0] - 1.0) < 0.5 and abs(mx[1] + 5.0) < 2.0
