@@ -201,3 +201,39 @@ def test_initAll_batched_matches_sequential(built):
     c = chain(5)
     SV.solveTree(c)
     assert abs(_pts(c, "x11").mean() - 11.0) < 1.5
+
+
+def test_c2_full_size_chain_properties(built):
+    """BASELINE configs[1] at FULL size (1000 poses, N=100, nested-dissection order): size-independent
+    properties of the posterior — every belief complete and finite, located at its pose index within the
+    accumulated odometry noise, bandwidths positive, same seed => bit-identical run, new seed => new samples,
+    convolution count of the plan as derived in SURVEY.md A.9 (~10 per pose with this order)."""
+    n = 1000
+    fg = W.scalar_chain(n, N=100, seed=42)
+    ts = SV.TreeSolver(fg, W.chain_nd_order(n))
+    assert 9 * n < ts.plan.n_conv < 13 * n and ts.plan.n_prod > 5 * n
+
+    def run(seed):
+        from iifb200 import compile as CP
+        ts.eng.set_solver_params(CP.solver_params_c(fg.solverParams, seed))
+        ts.load_from_graph()
+        ts.upload()
+        ts.run()
+        ts.download()
+        nv = len(fg.variables)
+        pts = np.stack([ts.arena.get(ts.plan.var_slot[f"x{k}"])[0][:, 0] for k in range(nv)])
+        bw = np.array([ts.arena.get(ts.plan.var_slot[f"x{k}"])[1][0] for k in range(nv)])
+        return pts, bw
+
+    p1, b1 = run(7)
+    p2, b2 = run(7)
+    p3, _ = run(8)
+    assert p1.shape == (n, 100) and np.isfinite(p1).all() and (b1 > 0).all()
+    assert np.array_equal(p1, p2) and np.array_equal(b1, b2)          # deterministic replay of the CUDA graph
+    assert not np.array_equal(p1, p3)
+    mean_err = np.abs(p1.mean(axis=1) - np.arange(n))
+    sigma = 0.1 * np.sqrt(np.arange(n) + 1.0)                          # prior 0.1, odometry 0.1 per step
+    assert (mean_err < 6.0 * sigma + 0.5).all(), float(mean_err.max())
+    spread = p1.std(axis=1)
+    assert (spread < 4.0 * sigma + 0.5).all() and (spread > 0.01).all()
+    ts.close()
