@@ -322,7 +322,11 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
 
   IIF_PHASE_ZERO();
   IIF_PHASE_BEGIN();
-  const ConvTask t = tasks[blockIdx.x];
+  // narrow launches give every convolution a cluster of CTAs that run redundantly and share the bandwidth
+  // search (iif_device.cuh, "cluster-speculative"); only rank 0 writes
+  const int cC = (int)cooperative_groups::this_cluster().num_blocks();
+  const bool wr = cooperative_groups::this_cluster().block_rank() == 0;
+  const ConvTask t = tasks[blockIdx.x / cC];
   const iif_conv_op op = t.op;
   const int n = threadIdx.x;
   int parity = 0;
@@ -482,22 +486,23 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   __syncthreads();
   IIF_PHASE(10);
   const int status = s_status;
-  if (t.out_status != nullptr && n == 0) *t.out_status = status;
+  if (t.out_status != nullptr && n == 0 && wr) *t.out_status = status;
   if (status != IIF_OK) return;
 
   // proposal points out
-  if (active)
+  if (active && wr)
     for (int c = 0; c < d; ++c) t.out_pts[n * d + c] = dest[n * d + c];
-  if (t.out_mhidx != nullptr && active) t.out_mhidx[n] = label;
+  if (t.out_mhidx != nullptr && active && wr) t.out_mhidx[n] = label;
   if (t.out_nan != nullptr) {
     double tot = block_sum1((double)nnan, red, parity);
-    if (n == 0) *t.out_nan = (int32_t)tot;
+    if (n == 0 && wr) *t.out_nan = (int32_t)tot;
   }
   // approxConvBelief: manikde!(M, pts; partial) — ApproxConv.jl:31-42
   double bw[IIF_MAX_DIM];
   IIF_PHASE(11);
   block_kde_bandwidth<0>(dest, N, d, cm, &trees[N], xa, xb, scr, red, &parity, bw);
   IIF_PHASE(12);
+  if (!wr) return;
   if (n == 0) {
     for (int c = 0; c < IIF_MAX_DIM; ++c) {
       t.out_bw[c] = c < d ? (((pmask >> c) & 1) ? bw[c] : 1.0) : 0.0;

@@ -4,6 +4,7 @@
 // of IIF_NT threads working on one belief (N <= IIF_MAX_POINTS particles resident in
 // shared memory).  Reference citations are to IncrementalInference.jl v0.35.6.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -530,80 +531,203 @@ __device__ __forceinline__ double loo_nll(const double* __restrict__ x2, const L
   return (t0 + t1) * negInvN;
 }
 
+// ------------------------------------------------------------------------------------------
+// Golden-section searches, sequential and cluster-speculative.
+//
+// A search is ~18 strictly sequential objective evaluations, so a lone CTA pays 18 evaluation latencies.
+// In narrow launches (tree top: fewer beliefs than SMs / 3) every belief is given a thread-block CLUSTER of
+// three CTAs that run the kernel redundantly (same inputs, same Philox streams => identical state) and split
+// the search speculatively: rank 0 evaluates the next point, ranks 1 and 2 the two points the step after
+// could ask for (they depend only on the outcome of one comparison).  One value per CTA is exchanged per
+// round through distributed shared memory + a cluster barrier, and every CTA advances the search by two
+// steps.  The evaluated-and-used points and all comparisons are those of the sequential search, so the
+// result is bit-identical; only rank 0 writes outputs.
+// ------------------------------------------------------------------------------------------
+#define IIF_SPEC_CLUSTER 3
+struct ClusterCtx {
+  int C, rank;   // cluster size (1 or IIF_SPEC_CLUSTER) and this CTA's rank
+  double* fx;    // shared exchange buffer [2][8]
+  int xpar;      // round parity (double buffering)
+};
+
+__device__ __forceinline__ void cluster_exchange(ClusterCtx& cc, double f, double (&F)[IIF_SPEC_CLUSTER]) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  if (threadIdx.x == 0) {
+    for (int p = 0; p < cc.C; ++p) {
+      double* remote = cl.map_shared_rank(cc.fx, p);
+      remote[cc.xpar * 8 + cc.rank] = f;
+    }
+  }
+  cl.sync();
+#pragma unroll
+  for (int k = 0; k < IIF_SPEC_CLUSTER; ++k) F[k] = cc.fx[cc.xpar * 8 + k];
+  cc.xpar ^= 1;
+}
+
 // Numerical-Recipes golden section as used by KDE `golden(npd, nLOO_LL, ax, bx, cx, tol)`; the search
-// variable scales the base bandwidth h0.  Uniform control flow across the CTA; the objective has ONE
-// call site (iterations -2 and -1 are the two initial evaluations) so that it is inlined once.
+// variable scales the base bandwidth h0.  Uniform control flow across the CTA (and the cluster); the
+// objective has ONE call site per variant so that it is inlined once.
+struct GoldenNR {
+  double x0, x1, x2, x3, f1, f2;
+};
+__device__ __forceinline__ bool gnr_done(const GoldenNR& s, double tol) {
+  return !(fabs(s.x3 - s.x0) > tol * (fabs(s.x1) + fabs(s.x2)));
+}
+__device__ __forceinline__ double gnr_advance(GoldenNR& s, bool right) {  // new evaluation point
+  const double C = (3.0 - sqrt(5.0)) / 2.0, R = 1.0 - C;
+  if (right) { s.x0 = s.x1; s.x1 = s.x2; s.x2 = R * s.x1 + C * s.x3; s.f1 = s.f2; return s.x2; }
+  s.x3 = s.x2; s.x2 = s.x1; s.x1 = R * s.x2 + C * s.x0; s.f2 = s.f1;
+  return s.x1;
+}
+__device__ __forceinline__ void gnr_set(GoldenNR& s, bool right, double fn) {
+  if (right) s.f2 = fn; else s.f1 = fn;
+}
+
 template <int U>
 __device__ __forceinline__ double golden_nr(const double* x2, const LooCfg& L, const LooThread& T0, int seg, int i,
                                             double h0, double ax, double bx, double cx, double tol,
-                                            const double* tab, double* scr, double* red, int& parity) {
-  const double C = (3.0 - sqrt(5.0)) / 2.0, R = 1.0 - C;
+                                            const double* tab, double* scr, double* red, int& parity,
+                                            ClusterCtx& cc) {
+  const double C = (3.0 - sqrt(5.0)) / 2.0;
   const double xi = x2[i];
   const double invK = 1.0 / ((double)(L.N - 1) * sqrt(IIF_TWO_PI)), negInvN = -1.0 / (double)L.N;
-  double x0 = ax, x3 = cx, x1, x2v;
-  if (fabs(cx - bx) > fabs(bx - ax)) { x1 = bx; x2v = bx + C * (cx - bx); }
-  else { x2v = bx; x1 = bx - C * (bx - ax); }
-  double f1 = 0.0, f2 = 0.0;
-  bool right = false;
-  for (int it = -2; it < 200; ++it) {
-    double xn;
-    if (it >= 0) {
-      if (!(fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2v)))) break;
-      right = f2 < f1;
-      if (right) { x0 = x1; x1 = x2v; x2v = R * x1 + C * x3; f1 = f2; xn = x2v; }
-      else { x3 = x2v; x2v = x1; x1 = R * x2v + C * x0; f2 = f1; xn = x1; }
-    } else {
-      xn = (it == -2) ? x1 : x2v;
+  GoldenNR s;
+  s.x0 = ax; s.x3 = cx; s.f1 = 0.0; s.f2 = 0.0;
+  if (fabs(cx - bx) > fabs(bx - ax)) { s.x1 = bx; s.x2 = bx + C * (cx - bx); }
+  else { s.x2 = bx; s.x1 = bx - C * (bx - ax); }
+  if (cc.C < IIF_SPEC_CLUSTER) {  // ---- sequential (iterations -2 and -1 are the two initial evaluations)
+    bool right = false;
+    for (int it = -2; it < 200; ++it) {
+      double xn;
+      if (it >= 0) {
+        if (gnr_done(s, tol)) break;
+        right = s.f2 < s.f1;
+        xn = gnr_advance(s, right);
+      } else {
+        xn = (it == -2) ? s.x1 : s.x2;
+      }
+      const double fn = loo_nll<U, false>(x2, L, T0, seg, i, xi, xn * h0, invK, negInvN, tab, scr, red, parity);
+      if (it == -2) s.f1 = fn;
+      else if (it == -1) s.f2 = fn;
+      else gnr_set(s, right, fn);
     }
-    const double fn = loo_nll<U, false>(x2, L, T0, seg, i, xi, xn * h0, invK, negInvN, tab, scr, red, parity);
-    if (it == -2) f1 = fn;
-    else if (it == -1 || right) f2 = fn;
-    else f1 = fn;
+  } else {  // ---- cluster-speculative: two steps per round
+    bool right = false, stop = false;
+    GoldenNR sA = s;
+    for (int round = -1; round < 100 && !stop; ++round) {
+      double xe;
+      if (round < 0) {
+        xe = (cc.rank == 0) ? s.x1 : s.x2;
+      } else {
+        if (gnr_done(s, tol)) break;
+        right = s.f2 < s.f1;
+        sA = s;
+        const double xA = gnr_advance(sA, right);
+        GoldenNR sT = sA, sF = sA;
+        const double xT = gnr_advance(sT, true), xF = gnr_advance(sF, false);
+        xe = (cc.rank == 0) ? xA : (cc.rank == 1) ? xT : xF;
+      }
+      const double fn = loo_nll<U, false>(x2, L, T0, seg, i, xi, xe * h0, invK, negInvN, tab, scr, red, parity);
+      double F[IIF_SPEC_CLUSTER];
+      cluster_exchange(cc, fn, F);
+      if (round < 0) { s.f1 = F[0]; s.f2 = F[1]; continue; }
+      s = sA;
+      gnr_set(s, right, F[0]);
+      if (gnr_done(s, tol)) { stop = true; continue; }
+      const bool right2 = s.f2 < s.f1;
+      gnr_advance(s, right2);
+      gnr_set(s, right2, right2 ? F[1] : F[2]);
+    }
   }
-  return (f1 < f2) ? x1 : x2v;
+  return (s.f1 < s.f2) ? s.x1 : s.x2;
 }
 
-// Optim.jl GoldenSection on [lo, hi] as used by AMP kde!_CircularNaiveCV (same single call site)
+// Optim.jl GoldenSection on [lo, hi] as used by AMP kde!_CircularNaiveCV
+struct GoldenOptim {
+  double lo, hi, xm, fm;
+};
+__device__ __forceinline__ bool gop_done(const GoldenOptim& s, double rel_tol) {
+  const double abs_tol = 2.220446049250313e-16;
+  const double tolx = rel_tol * fabs(s.xm) + abs_tol;
+  const double mid = 0.5 * (s.hi + s.lo);
+  return fabs(s.xm - mid) <= 2 * tolx - 0.5 * (s.hi - s.lo);
+}
+__device__ __forceinline__ double gop_next(const GoldenOptim& s, bool& up) {
+  const double gr = 0.5 * (3.0 - sqrt(5.0));
+  up = s.hi - s.xm > s.xm - s.lo;
+  return up ? s.xm + gr * (s.hi - s.xm) : s.xm - gr * (s.xm - s.lo);
+}
+__device__ __forceinline__ void gop_apply(GoldenOptim& s, bool up, double xn, bool less, double fn) {
+  if (up) {
+    if (less) { s.lo = s.xm; s.xm = xn; s.fm = fn; } else s.hi = xn;
+  } else {
+    if (less) { s.hi = s.xm; s.xm = xn; s.fm = fn; } else s.lo = xn;
+  }
+}
+
 template <int U>
 __device__ __forceinline__ double golden_optim(const double* x2, const LooCfg& L, const LooThread& T0, int seg, int i,
                                                double lo, double hi, double rel_tol, const double* tab, double* scr,
-                                               double* red, int& parity) {
+                                               double* red, int& parity, ClusterCtx& cc) {
   const double gr = 0.5 * (3.0 - sqrt(5.0));
-  const double abs_tol = 2.220446049250313e-16;
   const double xi = x2[i];
   const double invK = 1.0 / ((double)(L.N - 1) * sqrt(IIF_TWO_PI)), negInvN = -1.0 / (double)L.N;
-  double xm = lo + gr * (hi - lo), fm = 0.0;
-  bool up = false;
-  for (int it = -1; it < 200; ++it) {
-    double xn = xm;
-    if (it >= 0) {
-      const double tolx = rel_tol * fabs(xm) + abs_tol;
-      const double mid = 0.5 * (hi + lo);
-      if (fabs(xm - mid) <= 2 * tolx - 0.5 * (hi - lo)) break;
-      up = hi - xm > xm - lo;
-      xn = up ? xm + gr * (hi - xm) : xm - gr * (xm - lo);
+  GoldenOptim s;
+  s.lo = lo; s.hi = hi; s.xm = lo + gr * (hi - lo); s.fm = 0.0;
+  if (cc.C < IIF_SPEC_CLUSTER) {  // ---- sequential (iteration -1 is the initial evaluation)
+    bool up = false;
+    for (int it = -1; it < 200; ++it) {
+      double xn = s.xm;
+      if (it >= 0) {
+        if (gop_done(s, rel_tol)) break;
+        xn = gop_next(s, up);
+      }
+      const double fn = loo_nll<U, true>(x2, L, T0, seg, i, xi, xn, invK, negInvN, tab, scr, red, parity);
+      if (it < 0) s.fm = fn;
+      else gop_apply(s, up, xn, fn < s.fm, fn);
     }
-    const double fn = loo_nll<U, true>(x2, L, T0, seg, i, xi, xn, invK, negInvN, tab, scr, red, parity);
-    if (it < 0) fm = fn;
-    else if (up) {
-      if (fn < fm) { lo = xm; xm = xn; fm = fn; } else hi = xn;
-    } else {
-      if (fn < fm) { hi = xm; xm = xn; fm = fn; } else lo = xn;
+  } else {  // ---- cluster-speculative: the step after next depends only on whether fn < fm
+    bool up = false, stop = false;
+    double xA = s.xm, xT = s.xm, xF = s.xm;
+    bool upT = false, upF = false;
+    for (int round = -1; round < 100 && !stop; ++round) {
+      double xe = s.xm;
+      if (round >= 0) {
+        if (gop_done(s, rel_tol)) break;
+        xA = gop_next(s, up);
+        GoldenOptim sT = s, sF = s;
+        gop_apply(sT, up, xA, true, 0.0);
+        gop_apply(sF, up, xA, false, 0.0);
+        xT = gop_next(sT, upT);
+        xF = gop_next(sF, upF);
+        xe = (cc.rank == 0) ? xA : (cc.rank == 1) ? xT : xF;
+      }
+      const double fn = loo_nll<U, true>(x2, L, T0, seg, i, xi, xe, invK, negInvN, tab, scr, red, parity);
+      double F[IIF_SPEC_CLUSTER];
+      cluster_exchange(cc, fn, F);
+      if (round < 0) { s.fm = F[0]; continue; }
+      const bool less = F[0] < s.fm;
+      gop_apply(s, up, xA, less, F[0]);
+      if (gop_done(s, rel_tol)) { stop = true; continue; }
+      if (less) gop_apply(s, upT, xT, F[1] < s.fm, F[1]);
+      else gop_apply(s, upF, xF, F[2] < s.fm, F[2]);
     }
   }
-  return xm;
+  return s.xm;
 }
 
 // bandwidth of one coordinate; xa = the N coordinates, xb = loo_x2_doubles(N) scratch
 template <int U>
 __device__ __forceinline__ double coord_bandwidth(bool circ, const LooCfg& L, const LooThread& T0, int seg, int i,
                                                   const TreeStruct& T, const double* xa, double* xb,
-                                                  const double* tab, double* scr, double* red, int& parity) {
+                                                  const double* tab, double* scr, double* red, int& parity,
+                                                  ClusterCtx& cc) {
   const int N = L.N;
   if (circ) {
     for (int m = threadIdx.x; m < 2 * N + IIF_LOO_XPAD; m += IIF_NT) xb[m] = xa[m % N];
     __syncthreads();
-    return golden_optim<U>(xb, L, T0, seg, i, 1e-3, IIF_TWO_PI, 1e-3, tab, scr, red, parity);
+    return golden_optim<U>(xb, L, T0, seg, i, 1e-3, IIF_TWO_PI, 1e-3, tab, scr, red, parity, cc);
   }
   // rank sort (ties by index) -> xb ascending, doubled
   for (int m = threadIdx.x; m < N; m += IIF_NT) {
@@ -629,7 +753,7 @@ __device__ __forceinline__ double coord_bandwidth(bool circ, const LooCfg& L, co
   if (minm < 1e-6) minm = 1e-6;
   const double h0 = 0.5 * (minm + maxm);
   const double a = golden_nr<U>(xb, L, T0, seg, i, h0, 2.0 * minm / (minm + maxm), 1.0, 2.0 * maxm / (minm + maxm),
-                                1e-2, tab, scr, red, parity);
+                                1e-2, tab, scr, red, parity, cc);
   return a * h0;
 }
 
@@ -646,15 +770,24 @@ __device__ __noinline__ void block_kde_bandwidth(const double* pts, int N, int d
   const LooThread T0 = loo_thread(L, seg, i, 0);
   int parity = *parity_io;
   __shared__ double tab[16];  // 2^(j/16), see gauss_negU
+  __shared__ double fx[16];   // cluster exchange buffer (speculative search)
   if (threadIdx.x < 16) tab[threadIdx.x] = IIF_EXP2TAB[threadIdx.x];
+  ClusterCtx cc;
+  {
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    cc.C = (int)cl.num_blocks();
+    cc.rank = (int)cl.block_rank();
+    cc.fx = fx;
+    cc.xpar = 0;
+  }
   for (int c = 0; c < d; ++c) {
     __syncthreads();
     for (int m = threadIdx.x; m < N; m += IIF_NT) xa[m] = pts[m * d + c];
     __syncthreads();
     const bool circ = is_circ(circ_mask, c);
-    bw[c] = (L.U == 4)   ? coord_bandwidth<4>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity)
-            : (L.U == 5) ? coord_bandwidth<5>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity)
-                         : coord_bandwidth<6>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity);
+    bw[c] = (L.U == 4)   ? coord_bandwidth<4>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity, cc)
+            : (L.U == 5) ? coord_bandwidth<5>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity, cc)
+                         : coord_bandwidth<6>(circ, L, T0, seg, i, T, xa, xb, tab, scr, red, parity, cc);
   }
   *parity_io = parity;
 }

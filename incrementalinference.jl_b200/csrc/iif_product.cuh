@@ -84,7 +84,10 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IIF_PHASE_ZERO();
   IIF_PHASE_BEGIN();
-  const ProdTask t = tasks[blockIdx.x];
+  // narrow launches: a cluster of CTAs per product runs redundantly and shares the bandwidth search; rank 0 writes
+  const int cC = (int)cooperative_groups::this_cluster().num_blocks();
+  const bool wr = cooperative_groups::this_cluster().block_rank() == 0;
+  const ProdTask t = tasks[blockIdx.x / cC];
   const int F = t.F, N = t.N, d = t.dim;
   const int32_t cm = t.circ_mask;
   TreeStruct T = trees[N];
@@ -97,7 +100,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     int st = IIF_OK;
     for (int j = 0; j < F; ++j) if (t.conv_status[j] != IIF_OK) st = t.conv_status[j];
     if (st != IIF_OK) {
-      if (tid == 0 && t.out_status) *t.out_status = st;
+      if (tid == 0 && t.out_status && wr) *t.out_status = st;
       return;
     }
   }
@@ -152,7 +155,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     // manifoldProduct of one density returns it unchanged (no Gibbs, no re-bandwidth)
     for (int i = tid; i < N * d; i += IIF_NT) sm.post[i] = sm.P[i];
     for (int c = 0; c < d; ++c) bw[c] = sm.bwk[c];
-    if (t.out_labels) for (int s = tid; s < N; s += IIF_NT) t.out_labels[s] = s;
+    if (t.out_labels && wr) for (int s = tid; s < N; s += IIF_NT) t.out_labels[s] = s;
     __syncthreads();
   } else {
     IIF_PHASE(8);
@@ -256,7 +259,10 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     const uint32_t call = (uint32_t)t.call_id;
     int G = 1;
     while (G < 32 && 2 * G * N <= IIF_NT) G <<= 1;  // small CTAs (wide waves): G = 1, least total work
-    const int smp = tid / G, gl = tid % G;   // sample, lane within the group
+    // in a cluster launch the output samples are dealt round-robin to the ranks (every rank builds the same
+    // trees and tables, draws only its own samples and broadcasts their points before the bandwidth search)
+    const int crank = (int)cooperative_groups::this_cluster().block_rank();
+    const int smp = (tid / G) * cC + crank, gl = tid % G;   // sample, lane within the group
     const bool live = smp < N;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     // whole warps without a sample skip; partial groups never occur (G divides 32)
@@ -564,13 +570,18 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
           } else {
             x = t.old_pts ? t.old_pts[s * d + c] : 0.0;
           }
-          sm.post[s * d + c] = x;
+          if (cC > 1) {
+            for (int r = 0; r < cC; ++r) cooperative_groups::this_cluster().map_shared_rank(sm.post, r)[s * d + c] = x;
+          } else {
+            sm.post[s * d + c] = x;
+          }
         }
-        if (t.out_labels != nullptr)
+        if (t.out_labels != nullptr)   // every sample belongs to exactly one rank
           for (int j = 0; j < F; ++j) t.out_labels[s * F + j] = permA[j * N + T.lo[node[j]]];
       }
     }
-    __syncthreads();
+    if (cC > 1) cooperative_groups::this_cluster().sync();   // all ranks hold all posterior samples
+    else __syncthreads();
     IIF_PHASE(12);
     // ---- 4. re-bandwidth of the posterior (getKDEManifoldBandwidths on the result)
     block_kde_bandwidth<1>(sm.post, N, d, cm, &T, sm.xa, sm.xb, sm.scr, sm.red, &parity, bw);
@@ -578,6 +589,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
   }
 
   // ---- outputs: explicit buffers and / or setBelief! into the destination slot
+  if (!wr) return;
   if (t.out_pts != nullptr)
     for (int i = tid; i < N * d; i += IIF_NT) t.out_pts[i] = sm.post[i];
   if (t.out_bw != nullptr && tid < IIF_MAX_DIM) t.out_bw[tid] = tid < d ? bw[tid] : 0.0;
@@ -626,7 +638,9 @@ __global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
 iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restrict__ trees) {
   extern __shared__ __align__(16) double bw_smem[];  // conv_smem_bytes(N)
   __shared__ double red[IIF_RED_DOUBLES];
-  const BwTask t = tasks[blockIdx.x];
+  const int cC = (int)cooperative_groups::this_cluster().num_blocks();
+  const bool wr = cooperative_groups::this_cluster().block_rank() == 0;
+  const BwTask t = tasks[blockIdx.x / cC];
   int parity = 0;
   double* pts = bw_smem;
   double* xa = pts + (size_t)t.N * IIF_MAX_DIM;
@@ -639,7 +653,7 @@ iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restr
   IIF_PHASE(8);
   double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
   block_kde_bandwidth<2>(pts, t.N, t.dim, t.circ_mask, &trees[t.N], xa, xb, scr, red, &parity, bw);
-  if (threadIdx.x < IIF_MAX_DIM) t.out_bw[threadIdx.x] = threadIdx.x < t.dim ? bw[threadIdx.x] : 0.0;
+  if (threadIdx.x < IIF_MAX_DIM && wr) t.out_bw[threadIdx.x] = threadIdx.x < t.dim ? bw[threadIdx.x] : 0.0;
   IIF_PHASE(13);
   IIF_PHASE_FLUSH();
 }

@@ -143,6 +143,27 @@ static int32_t ensure_tree(iifb200_ctx* ctx, int N) {
   return IIF_OK;
 }
 
+// launch with an optional thread-block cluster dimension (cluster == 1: a plain launch)
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), int tasks, int cluster, int threads, size_t smem, cudaStream_t st,
+                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(tasks * cluster));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (cluster > 1) {
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);  // errors surface through cudaGetLastError at the call site
+}
+
 // =============================================================================================
 extern "C" {
 
@@ -458,6 +479,13 @@ static int pick_threads_prod(iifb200_ctx* ctx, int grid, int maxN) {
   return std::min(IIF_MAX_THREADS, std::max(wide, (maxN + 31) / 32 * 32));
 }
 
+// Narrow launches (fewer beliefs than SMs / 3, i.e. the top of the tree) give every belief a thread-block
+// cluster of IIF_SPEC_CLUSTER CTAs that share the golden-section bandwidth search speculatively
+// (iif_device.cuh); everything else launches plain CTAs.
+static int pick_cluster(iifb200_ctx* ctx, int grid) {
+  static const int want = env_int("IIFB200_CLUSTER", IIF_SPEC_CLUSTER);
+  return (want == IIF_SPEC_CLUSTER && grid * IIF_SPEC_CLUSTER <= ctx->num_sms) ? IIF_SPEC_CLUSTER : 1;
+}
 static bool is_prior_kind_h(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR;
 }
@@ -524,7 +552,7 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ConvTask) * K, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_conv_kernel<<<K, pick_threads(ctx, K, cmaxN), csmem, ctx->stream>>>(ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
+  launch_k(iif_conv_kernel, K, pick_cluster(ctx, K), pick_threads(ctx, K, cmaxN), csmem, ctx->stream, ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -616,7 +644,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ProdTask) * V, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_product_kernel<<<V, pick_threads_prod(ctx, V, pmaxN), smem, ctx->stream>>>(ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
+  launch_k(iif_product_kernel, V, pick_cluster(ctx, V), pick_threads_prod(ctx, V, pmaxN), smem, ctx->stream, ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -657,7 +685,7 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   CK(cudaMemcpyAsync(d_pts, pts, sizeof(double) * off[K], cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_t, t.data(), sizeof(BwTask) * K, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  iif_bandwidth_kernel<<<K, pick_threads(ctx, K, bmaxN), bsmem, ctx->stream>>>(d_t, ctx->d_trees);
+  launch_k(iif_bandwidth_kernel, K, pick_cluster(ctx, K), pick_threads(ctx, K, bmaxN), bsmem, ctx->stream, d_t, ctx->d_trees);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -826,11 +854,11 @@ static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int*
       ++k;
     }
     if (W.nconv) {
-      iif_conv_kernel<<<W.nconv, pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      launch_k(iif_conv_kernel, W.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream, ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
       ++k;
     }
     if (W.nprod) {
-      iif_product_kernel<<<W.nprod, pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      launch_k(iif_product_kernel, W.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream, ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
       ++k;
     }
   }
@@ -895,12 +923,12 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
     }
     if (W.nconv) {
       mark();
-      iif_conv_kernel<<<W.nconv, pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream>>>(ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      launch_k(iif_conv_kernel, W.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream, ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(0); blocks[0] += W.nconv;
     }
     if (W.nprod) {
       mark();
-      iif_product_kernel<<<W.nprod, pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream>>>(ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      launch_k(iif_product_kernel, W.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream, ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(1); blocks[1] += W.nprod;
     }
   }
