@@ -39,7 +39,7 @@ struct ConvTask {
 };
 
 __host__ __device__ inline size_t conv_smem_bytes(int N) {
-  return sizeof(double) * ((size_t)N * IIF_MAX_DIM + (size_t)N + (size_t)loo_x2_doubles(N) + (size_t)loo_scratch_doubles(N));
+  return sizeof(double) * ((size_t)N * IIF_MAX_DIM + (size_t)loo_xa_doubles(N) + (size_t)loo_x2_doubles(N) + (size_t)loo_scratch_doubles(N));
 }
 
 struct HypoRecipe {  // HypoRecipe, src/entities/HypoRecipe.jl:4-9 (elements are implicit: mhidx == hyp)
@@ -326,13 +326,14 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   // search (iif_device.cuh, "cluster-speculative"); only rank 0 writes
   const int cC = (int)cooperative_groups::this_cluster().num_blocks();
   const bool wr = cooperative_groups::this_cluster().block_rank() == 0;
+  if (cC > 1) cooperative_groups::this_cluster().sync();  // every rank is resident before any remote shared-memory access
   const ConvTask t = tasks[blockIdx.x / cC];
   const iif_conv_op op = t.op;
   const int n = threadIdx.x;
   int parity = 0;
   double* dest = conv_smem;                         // N * IIF_MAX_DIM
   double* xa = dest + (size_t)op.N * IIF_MAX_DIM;   // N
-  double* xb = xa + op.N;                           // loo_x2_doubles(N)
+  double* xb = xa + loo_xa_doubles(op.N);           // loo_x2_doubles(N)
   double* scr = xb + loo_x2_doubles(op.N);          // loo_scratch_doubles(N)
   if (n == 0) {
     f = g.factors[op.factor];

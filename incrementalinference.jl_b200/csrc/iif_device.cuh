@@ -361,6 +361,9 @@ __host__ __device__ inline int loo_tile_rows(int N) {  // equal-sized column chu
 }
 __host__ __device__ inline int loo_scratch_doubles(int N) { return IIF_LOO_PARTS * N + loo_tile_rows(N) * N; }
 __host__ __device__ inline int loo_x2_doubles(int N) { return 2 * N + IIF_LOO_XPAD; }
+// the coordinate buffer `xa` in front of it: the compiler vectorises the rank sort's reads of xa (LDS.128, eight
+// values per trip) and may read up to 7 values past xa[N-1]; they are discarded, the slack keeps them off xb
+__host__ __device__ inline int loo_xa_doubles(int N) { return N + 8; }
 #define IIF_LOO_SCRATCH_N(N) loo_scratch_doubles(N)
 
 struct LooCfg {  // per belief size N and CTA size (uniform)

@@ -52,7 +52,7 @@ struct ProdSmem {
 __host__ __device__ inline bool gibbs_tab(int N) { return N <= IIF_GIBBS_TAB_MAX; }
 
 __host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn, int L) {
-  size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + (size_t)N + (size_t)loo_x2_doubles(N) + IIF_RED_DOUBLES +
+  size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + (size_t)loo_xa_doubles(N) + (size_t)loo_x2_doubles(N) + IIF_RED_DOUBLES +
                (size_t)F * IIF_MAX_DIM + (size_t)nn + (size_t)F * (L + 1) * d;
   size_t scr = (size_t)IIF_LOO_SCRATCH_N(N);
   if (F == 2 && gibbs_tab(N) && (size_t)N * N > scr) scr = (size_t)N * N;
@@ -87,6 +87,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
   // narrow launches: a cluster of CTAs per product runs redundantly and shares the bandwidth search; rank 0 writes
   const int cC = (int)cooperative_groups::this_cluster().num_blocks();
   const bool wr = cooperative_groups::this_cluster().block_rank() == 0;
+  if (cC > 1) cooperative_groups::this_cluster().sync();  // every rank is resident before any remote shared-memory access
   const ProdTask t = tasks[blockIdx.x / cC];
   const int F = t.F, N = t.N, d = t.dim;
   const int32_t cm = t.circ_mask;
@@ -112,7 +113,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     sm.mean = p; p += (size_t)F * nn * d;
     sm.var = p; p += (size_t)F * nn * d;
     sm.post = p; p += (size_t)N * d;
-    sm.xa = p; p += N;
+    sm.xa = p; p += loo_xa_doubles(N);
     sm.xb = p; p += loo_x2_doubles(N);
     sm.red = p; p += IIF_RED_DOUBLES;
     sm.bwk = p; p += F * IIF_MAX_DIM;
@@ -640,11 +641,12 @@ iif_bandwidth_kernel(const BwTask* __restrict__ tasks, const TreeStruct* __restr
   __shared__ double red[IIF_RED_DOUBLES];
   const int cC = (int)cooperative_groups::this_cluster().num_blocks();
   const bool wr = cooperative_groups::this_cluster().block_rank() == 0;
+  if (cC > 1) cooperative_groups::this_cluster().sync();  // every rank is resident before any remote shared-memory access
   const BwTask t = tasks[blockIdx.x / cC];
   int parity = 0;
   double* pts = bw_smem;
   double* xa = pts + (size_t)t.N * IIF_MAX_DIM;
-  double* xb = xa + t.N;
+  double* xb = xa + loo_xa_doubles(t.N);
   double* scr = xb + loo_x2_doubles(t.N);
   IIF_PHASE_ZERO();
   IIF_PHASE_BEGIN();
