@@ -25,6 +25,8 @@
  *                               solveCliqDownFrontalProducts! src/CliqueStateMachine/services/CliqStateMachineUtils.jl:479-571
  *   iifb200_kde_bandwidth    <- AMP.manikde! bandwidth (call sites ApproxConv.jl:38-41, FGOSUtils.jl:118-128)
  *   iifb200_ppe_batch        <- calcPPE / setPPE!           src/services/FGOSUtils.jl:237-278
+ *   iifb200_deconv_batch     <- approxDeconv                src/services/DeconvUtils.jl:32-162
+ *   iifb200_mmd              <- mmd (AMP.mmd!)              src/services/SolverUtilities.jl:25-47
  *   belief slots             <- VariableNodeData.val/.bw, TreeBelief   src/entities/BeliefTypes.jl:47-57
  *   iif_factor_desc          <- CommonConvWrapper           src/entities/FactorOperationalMemory.jl:21-70
  *   iif_solver_params        <- SolverParams                src/entities/SolverParams.jl:12-75
@@ -233,6 +235,19 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
  * buffers of V x IIF_MAX_DIM doubles (coordinates; the "suggested" estimate is the mean). */
 int32_t iifb200_ppe_batch(iifb200_ctx* ctx, int32_t V, const int32_t* slots, double* out_mean,
                           double* out_max);
+
+/* approxDeconv of K factors on device-resident beliefs (src/services/DeconvUtils.jl:32-162): for sample n the
+ * factor residual is solved for the measurement given particle n of every variable (closed form for the
+ * built-in residuals; multihypo factors are unsupported, as in the reference :22).  Outputs are HOST buffers
+ * packed per factor, N_k x zdim_k doubles each: out_pred = predicted, out_meas = sampled measurements. */
+int32_t iifb200_deconv_batch(iifb200_ctx* ctx, int32_t K, const int32_t* factors, const int32_t* N,
+                             const int32_t* call_ids, double* out_pred, double* out_meas);
+
+/* mmd kernel-embedding distance of K pairs of HOST point sets (src/services/SolverUtilities.jl:25-47 ->
+ * AMP.mmd!): sum k(a,a)/Na^2 - 2 sum k(a,b)/(Na Nb) + sum k(b,b)/Nb^2, k(p,q) = exp(-bw dist(p,q)^2)
+ * (bw = 0.001 in the reference).  a / b are packed Na_k x dim_k / Nb_k x dim_k; out holds K doubles. */
+int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_t* nb, const int32_t* dim,
+                    const int32_t* circ_mask, const double* a, const double* b, double bw, double* out);
 
 /* V independent propagateBelief calls on device-resident slots (one launch sequence).
  * Posteriors are written into out_slot on the device; nothing is copied to the host. */

@@ -95,6 +95,8 @@ SYMBOLS = {
                                           _dp, _dp, _ip]),
     "iifb200_kde_bandwidth": (C.c_int32, [_vp, C.c_int32, _ip, _ip, _ip, _dp, _dp]),
     "iifb200_ppe_batch": (C.c_int32, [_vp, C.c_int32, _ip, _dp, _dp]),
+    "iifb200_deconv_batch": (C.c_int32, [_vp, C.c_int32, _ip, _ip, _ip, _dp, _dp]),
+    "iifb200_mmd": (C.c_int32, [_vp, C.c_int32, _ip, _ip, _ip, _ip, _dp, _dp, C.c_double, _dp]),
     "iifb200_propagate_batch": (C.c_int32, [_vp, C.c_int32, P(PropOp)]),
     "iifb200_schedule_build": (C.c_int32, [_vp, C.c_int32, _ip, C.c_int32, P(SchedOp), C.c_int32,
                                            P(PropOp), _ip]),

@@ -1,0 +1,130 @@
+// iif_deconv.cuh — SURVEY.md §8f-2: approxDeconv (src/services/DeconvUtils.jl:32-162) and the mmd
+// kernel-embedding distance that pins it (SolverUtilities.jl:25-47 -> AMP.mmd!; test/testDefaultDeconv.jl:10-45).
+//
+// approxDeconv is the inverse of the convolution: for every sample n, solve the factor residual for the
+// MEASUREMENT given particle n of every variable (first hypothesis only, DeconvUtils.jl:76,139), starting from a
+// sampled measurement; it returns (predicted, sampled).  The built-in residuals are linear in z, so the root is
+// closed form (prior z = x1, LinearRelative z = x2 - x1, CircularCircular z = wrap(x2 - x1), EuclidDistance
+// z = |x2 - x1|).  One CTA per factor, one thread per sample.
+#pragma once
+#include "iif_conv.cuh"
+
+struct DeconvTask {
+  int32_t factor, N, call_id, _pad;
+  double* out_pred;    // N * zdim
+  double* out_meas;    // N * zdim
+  int32_t* out_status;
+};
+
+__global__ void iif_deconv_kernel(DeviceGraph g, const DeconvTask* __restrict__ tasks) {
+  const DeconvTask t = tasks[blockIdx.x];
+  const iif_factor_desc f = g.factors[t.factor];
+  const int zd = f.zdim;
+  __shared__ int s_status;
+  if (threadIdx.x == 0) s_status = (f.nmh != 0 || f.arity > 2) ? IIF_ERR_UNSUPPORTED : IIF_OK;
+  __syncthreads();
+  const iif_slot_desc S1 = g.slots[f.slot[0]];
+  for (int n = threadIdx.x; n < t.N && s_status == IIF_OK; n += blockDim.x) {
+    double z[IIF_MAX_DIM] = {0, 0, 0, 0};
+    int st = sample_measurement(g, f, (uint32_t)t.call_id, n, z);
+    if (st != IIF_OK) { s_status = st; break; }
+    for (int c = 0; c < zd; ++c) t.out_meas[n * zd + c] = z[c];
+    double x[2][IIF_MAX_DIM];
+    bool ok = true;
+    for (int v = 0; v < f.arity; ++v) {  // _getindex_anyn, NumericalCalculations.jl:377-381
+      const iif_slot_desc S = g.slots[f.slot[v]];
+      const int len = g.npts[f.slot[v]];
+      if (len <= 0) { s_status = IIF_ERR_STATE; ok = false; break; }
+      int m = n;
+      if (n >= len) {
+        const double u = rs_uniform(g.sp->seed, (uint32_t)t.call_id, IIF_RS_ANYN, (uint32_t)(v * t.N + n));
+        m = min((int)(u * len), len - 1);
+      }
+      for (int c = 0; c < S.dim; ++c) x[v][c] = g.pts[S.pts_off + m * S.dim + c];
+    }
+    if (!ok) break;
+    double* p = t.out_pred + (size_t)n * zd;
+    switch (f.kind) {
+      case IIF_F_PRIOR:
+      case IIF_F_MSG_PRIOR:
+        for (int c = 0; c < zd; ++c) p[c] = x[0][c];
+        break;
+      case IIF_F_PRIOR_CIRCULAR: p[0] = wrap_pi(x[0][0]); break;
+      case IIF_F_PARTIAL_PRIOR: {
+        int k = 0;
+        for (int c = 0; c < S1.dim; ++c)
+          if ((f.partial_mask >> c) & 1) p[k++] = x[0][c];
+        break;
+      }
+      case IIF_F_LINEAR_RELATIVE:
+      case IIF_F_CIRCULAR_CIRCULAR:
+        for (int c = 0; c < zd; ++c) p[c] = mdiff(x[1][c], x[0][c], is_circ(S1.circ_mask, c));
+        break;
+      case IIF_F_EUCLID_DISTANCE: {
+        double s = 0;
+        for (int c = 0; c < S1.dim; ++c) s += (x[1][c] - x[0][c]) * (x[1][c] - x[0][c]);
+        p[0] = sqrt(s);
+        break;
+      }
+      default: s_status = IIF_ERR_UNSUPPORTED;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && t.out_status) *t.out_status = s_status;
+}
+
+// mmd: sum k(a,a)/Na^2 - 2 sum k(a,b)/(Na Nb) + sum k(b,b)/Nb^2 with k(p,q) = exp(-bw dist(p,q)^2).
+// One CTA per pair of point sets; thread i owns row i of each of the three kernel matrices; Gaussian kernel
+// values four at a time by exp_negU.
+struct MmdTask {
+  const double* a;
+  const double* b;
+  int32_t na, nb, dim, circ_mask;
+  double bw;
+  double* out;
+};
+
+__device__ __forceinline__ double mmd_rows(const double* __restrict__ P, int np, const double* __restrict__ Q, int nq,
+                                           int d, int32_t cm, double bw) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    double pi[IIF_MAX_DIM];
+    for (int c = 0; c < d; ++c) pi[c] = P[i * d + c];
+    for (int j = 0; j < nq; j += 4) {
+      double a[4], e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = min(j + u, nq - 1);
+        double d2 = 0.0;
+        for (int c = 0; c < d; ++c) {
+          const double dl = mdiff(pi[c], Q[jj * d + c], is_circ(cm, c));
+          d2 = fma(dl, dl, d2);
+        }
+        a[u] = -bw * d2;
+      }
+      exp_negU<4>(a, e);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += (j + u < nq) ? e[u] : 0.0;
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256, 1) iif_mmd_kernel(const MmdTask* __restrict__ tasks) {
+  extern __shared__ __align__(16) double mmd_smem[];  // a (na*d) then b (nb*d)
+  __shared__ double red[IIF_RED_DOUBLES];
+  const MmdTask t = tasks[blockIdx.x];
+  double* A_ = mmd_smem;
+  double* B_ = mmd_smem + (size_t)t.na * t.dim;
+  for (int i = threadIdx.x; i < t.na * t.dim; i += blockDim.x) A_[i] = t.a[i];
+  for (int i = threadIdx.x; i < t.nb * t.dim; i += blockDim.x) B_[i] = t.b[i];
+  __syncthreads();
+  int parity = 0;
+  double v[3];
+  v[0] = mmd_rows(A_, t.na, A_, t.na, t.dim, t.circ_mask, t.bw);
+  v[1] = mmd_rows(A_, t.na, B_, t.nb, t.dim, t.circ_mask, t.bw);
+  v[2] = mmd_rows(B_, t.nb, B_, t.nb, t.dim, t.circ_mask, t.bw);
+  block_sum<3>(v, red, parity);
+  if (threadIdx.x == 0)
+    *t.out = v[0] / ((double)t.na * t.na) - 2.0 * v[1] / ((double)t.na * t.nb) + v[2] / ((double)t.nb * t.nb);
+}

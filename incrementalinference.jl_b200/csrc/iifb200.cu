@@ -13,6 +13,7 @@
 #include <utility>
 #include <vector>
 
+#include "iif_deconv.cuh"
 #include "iif_ppe.cuh"
 #include "iif_product.cuh"
 
@@ -724,6 +725,89 @@ int32_t iifb200_ppe_batch(iifb200_ctx* ctx, int32_t V, const int32_t* slots, dou
   CK(cudaMemcpyAsync(out_max, d_out + (int64_t)V * IIF_MAX_DIM, sizeof(double) * V * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_out); cudaFree(d_t);
+  return IIF_OK;
+}
+
+// ---- approxDeconv of K factors on device-resident beliefs (DeconvUtils.jl:32-162) ----------------------------
+int32_t iifb200_deconv_batch(iifb200_ctx* ctx, int32_t K, const int32_t* factors, const int32_t* N,
+                             const int32_t* call_ids, double* out_pred, double* out_meas) {
+  NEED_GRAPH();
+  if (K < 1 || !factors || !N || !call_ids || !out_pred || !out_meas) return fail(ctx, IIF_ERR_ARG, "deconv_batch: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<int64_t> off(K + 1, 0);
+  for (int k = 0; k < K; ++k) {
+    if (factors[k] < 0 || factors[k] >= (int)ctx->factors.size()) return fail(ctx, IIF_ERR_ARG, "deconv_batch: factor index out of range");
+    if (N[k] < 1 || N[k] > IIF_MAX_POINTS) return fail(ctx, IIF_ERR_ARG, "deconv_batch: N out of range");
+    off[k + 1] = off[k] + (int64_t)N[k] * ctx->factors[factors[k]].zdim;
+  }
+  double* d_out = nullptr;
+  int32_t* d_st = nullptr;
+  DeconvTask* d_t = nullptr;
+  CK(cudaMalloc(&d_out, sizeof(double) * 2 * off[K]));
+  CK(cudaMalloc(&d_st, sizeof(int32_t) * K));
+  CK(cudaMalloc(&d_t, sizeof(DeconvTask) * K));
+  std::vector<DeconvTask> t(K);
+  for (int k = 0; k < K; ++k) {
+    t[k].factor = factors[k]; t[k].N = N[k]; t[k].call_id = call_ids[k]; t[k]._pad = 0;
+    t[k].out_pred = d_out + off[k];
+    t[k].out_meas = d_out + off[K] + off[k];
+    t[k].out_status = d_st + k;
+  }
+  CK(cudaMemcpyAsync(d_t, t.data(), sizeof(DeconvTask) * K, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  iif_deconv_kernel<<<K, 128, 0, ctx->stream>>>(ctx->dg, d_t);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->launches += 1;
+  std::vector<int32_t> st(K);
+  CK(cudaMemcpyAsync(out_pred, d_out, sizeof(double) * off[K], cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_meas, d_out + off[K], sizeof(double) * off[K], cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(st.data(), d_st, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_out); cudaFree(d_st); cudaFree(d_t);
+  for (int k = 0; k < K; ++k)
+    if (st[k] != IIF_OK) return fail(ctx, st[k], std::string("deconv_batch: device reported '") + status_name(st[k]) + "'");
+  return IIF_OK;
+}
+
+// ---- mmd kernel-embedding distance of K pairs of point sets (SolverUtilities.jl:25-47 / AMP.mmd!) ---------------
+int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_t* nb, const int32_t* dim,
+                    const int32_t* circ_mask, const double* a, const double* b, double bw, double* out) {
+  if (!ctx) return IIF_ERR_ARG;
+  if (K < 1 || !na || !nb || !dim || !circ_mask || !a || !b || !out) return fail(ctx, IIF_ERR_ARG, "mmd: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<int64_t> oa(K + 1, 0), ob(K + 1, 0);
+  size_t smem = 0;
+  for (int k = 0; k < K; ++k) {
+    if (dim[k] < 1 || dim[k] > IIF_MAX_DIM || na[k] < 1 || nb[k] < 1) return fail(ctx, IIF_ERR_ARG, "mmd: bad sizes");
+    oa[k + 1] = oa[k] + (int64_t)na[k] * dim[k];
+    ob[k + 1] = ob[k] + (int64_t)nb[k] * dim[k];
+    smem = std::max(smem, sizeof(double) * (size_t)(na[k] + nb[k]) * dim[k]);
+  }
+  if ((int)smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "mmd: point sets exceed the shared-memory budget");
+  double *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
+  MmdTask* d_t = nullptr;
+  CK(cudaMalloc(&d_a, sizeof(double) * oa[K]));
+  CK(cudaMalloc(&d_b, sizeof(double) * ob[K]));
+  CK(cudaMalloc(&d_o, sizeof(double) * K));
+  CK(cudaMalloc(&d_t, sizeof(MmdTask) * K));
+  std::vector<MmdTask> t(K);
+  for (int k = 0; k < K; ++k) {
+    t[k].a = d_a + oa[k]; t[k].b = d_b + ob[k];
+    t[k].na = na[k]; t[k].nb = nb[k]; t[k].dim = dim[k]; t[k].circ_mask = circ_mask[k];
+    t[k].bw = bw; t[k].out = d_o + k;
+  }
+  CK(cudaMemcpyAsync(d_a, a, sizeof(double) * oa[K], cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_b, b, sizeof(double) * ob[K], cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_t, t.data(), sizeof(MmdTask) * K, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaFuncSetAttribute(iif_mmd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - 4096));
+  iif_mmd_kernel<<<K, 256, smem, ctx->stream>>>(d_t);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(out, d_o, sizeof(double) * K, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_o); cudaFree(d_t);
   return IIF_OK;
 }
 

@@ -171,6 +171,25 @@ class Engine:
         self._check(self.lib.iifb200_ppe_batch(self.ctx, V, A.as_ip(sl), A.as_dp(mean), A.as_dp(mx)), "ppe_batch")
         return mean, mx
 
+    def deconv(self, factor, N, call_id):
+        """approxDeconv of one factor -> (predicted N x z, sampled N x z)"""
+        zd = self.frozen["factors"][factor].zdim
+        pred, meas = np.zeros((N, zd)), np.zeros((N, zd))
+        f, n, c = (np.array([x], dtype=np.int32) for x in (factor, N, call_id))
+        self._check(self.lib.iifb200_deconv_batch(self.ctx, 1, A.as_ip(f), A.as_ip(n), A.as_ip(c), A.as_dp(pred),
+                                                  A.as_dp(meas)), "deconv_batch")
+        return pred, meas
+
+    def mmd(self, a, b, circ_mask=0, bw=0.001):
+        """AMP.mmd kernel-embedding distance between two point sets"""
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(len(a), -1)
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(len(b), -1)
+        na, nb, d, cm = (np.array([x], dtype=np.int32) for x in (a.shape[0], b.shape[0], a.shape[1], circ_mask))
+        out = np.zeros(1)
+        self._check(self.lib.iifb200_mmd(self.ctx, 1, A.as_ip(na), A.as_ip(nb), A.as_ip(d), A.as_ip(cm), A.as_dp(a),
+                                         A.as_dp(b), float(bw), A.as_dp(out)), "mmd")
+        return float(out[0])
+
     def propagate_batch(self, prop_ops, V):
         self._check(self.lib.iifb200_propagate_batch(self.ctx, V, prop_ops), "propagate_batch")
 

@@ -171,6 +171,23 @@ def localProductAndUpdate(fg: G.FactorGraph, sym: str, setkde: bool = True):
     return mkd, ipc, lbl
 
 
+# --------------------------------------------------------------------------- §8f-2: deconvolution
+def approxDeconv(fg: G.FactorGraph, fctsym: str, N: Optional[int] = None):
+    """approxDeconv(dfg, fctsym) — DeconvUtils.jl:32-202: (predicted, sampled) measurement values of a factor,
+    N = number of points of its first variable (:194-196)."""
+    ge = _engine(fg)
+    f = fg.factors[fctsym]
+    if G.isMultihypo(f):
+        raise A.IIFB200Error("approxDeconv: multihypo factors are not supported (as in the reference, #1096)")
+    N = N or fg.variables[f.variables[0]].val.shape[0] or fg.solverParams.N
+    return ge.eng.deconv(ge.fac_idx[fctsym], N, ge.next_call())
+
+
+def mmd(fg: G.FactorGraph, p1, p2, vartype: G.InferenceVariable = None, bw: float = 0.001) -> float:
+    """mmd(p1, p2, varType; bw=[0.001]) — SolverUtilities.jl:25-47 (AMP.mmd!)."""
+    return _engine(fg).eng.mmd(p1, p2, vartype.circ_mask if vartype is not None else 0, bw)
+
+
 # --------------------------------------------------------------------------- §8f-3: point estimates
 def calcPPE(fg: G.FactorGraph, label: str, solveKey: str = "default") -> G.MeanMaxPPE:
     """calcPPE(dfg, label) — FGOSUtils.jl:237-296: suggested = mean = calcMean(P), max = getKDEMax(P)."""

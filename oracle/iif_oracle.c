@@ -509,6 +509,92 @@ int32_t iifo_kde_bandwidth(const double* pts, int32_t n, int32_t d, int32_t cm, 
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* approxDeconv (src/services/DeconvUtils.jl:32-162) — the inverse of the convolution:  */
+/* for every sample n solve the factor residual for the MEASUREMENT given particle n of every        */
+/* variable (first hypothesis only, :76,:139), starting from a sampled measurement.  Returns          */
+/* (predicted, sampled) measurements.  The built-in residuals are linear in z, so the root is closed  */
+/* form: prior z = x1, LinearRelative z = x2 - x1, CircularCircular z = wrap(x2 - x1), EuclidDistance */
+/* z = |x2 - x1|.  Multihypo factors are not supported by the reference either (:22, #1096).          */
+/* ------------------------------------------------------------------------------------ */
+int32_t iifo_deconv(const iifo_graph* g, int32_t factor, int32_t N, int32_t call_id,
+                    double* out_pred, double* out_meas) {
+  if (factor < 0 || factor >= g->nfactors || N < 1) return IIF_ERR_ARG;
+  const iif_factor_desc* f = &g->factors[factor];
+  if (f->nmh != 0) return IIF_ERR_UNSUPPORTED;
+  if (!(f->arity == 1 || f->arity == 2)) return IIF_ERR_UNSUPPORTED;
+  const int zd = f->zdim;
+  const iif_slot_desc* S1 = &g->slots[f->slot[0]];
+  const iif_slot_desc* S2 = f->arity == 2 ? &g->slots[f->slot[1]] : NULL;
+  for (int n = 0; n < N; ++n) {
+    double z[IIF_MAX_DIM] = {0, 0, 0, 0};
+    int32_t st = sample_measurement(g, f, (uint32_t)call_id, n, z);
+    if (st != IIF_OK) return st;
+    for (int c = 0; c < zd; ++c) out_meas[n * zd + c] = z[c];
+    const double* x[2] = {NULL, NULL};
+    for (int v = 0; v < f->arity; ++v) {       /* _getindex_anyn, NumericalCalculations.jl:377-381 */
+      const iif_slot_desc* S = v == 0 ? S1 : S2;
+      int len = g->npts[f->slot[v]];
+      if (len <= 0) return IIF_ERR_STATE;
+      int m = n;
+      if (n >= len) {
+        double u = iifo_uniform(g->sp.seed, (uint32_t)call_id, IIF_RS_ANYN, (uint32_t)(v * N + n));
+        m = (int)(u * len);
+        if (m >= len) m = len - 1;
+      }
+      x[v] = g->pts + S->pts_off + (size_t)m * S->dim;
+    }
+    double* p = out_pred + (size_t)n * zd;
+    switch (f->kind) {
+      case IIF_F_PRIOR: case IIF_F_MSG_PRIOR:
+        for (int c = 0; c < zd; ++c) p[c] = x[0][c];
+        break;
+      case IIF_F_PRIOR_CIRCULAR:
+        p[0] = wrap_pi(x[0][0]);
+        break;
+      case IIF_F_PARTIAL_PRIOR: {
+        int k = 0;
+        for (int c = 0; c < S1->dim; ++c) if ((f->partial_mask >> c) & 1) p[k++] = x[0][c];
+        break;
+      }
+      case IIF_F_LINEAR_RELATIVE: case IIF_F_CIRCULAR_CIRCULAR:
+        for (int c = 0; c < zd; ++c) p[c] = mdiff(x[1][c], x[0][c], is_circ(S1->circ_mask, c));
+        break;
+      case IIF_F_EUCLID_DISTANCE: {
+        double s = 0;
+        for (int c = 0; c < S1->dim; ++c) s += (x[1][c] - x[0][c]) * (x[1][c] - x[0][c]);
+        p[0] = sqrt(s);
+        break;
+      }
+      default: return IIF_ERR_UNSUPPORTED;
+    }
+  }
+  return IIF_OK;
+}
+
+/* mmd (src/services/SolverUtilities.jl:25-47 -> AMP.mmd!, un-vendored, PARITY UNPINNED): kernel-embedding */
+/* distance with ker(p,q) = exp(-bw * dist(p,q)^2):  sum k(a,a)/Na^2 - 2 sum k(a,b)/(Na Nb) + sum k(b,b)/Nb^2 */
+double iifo_mmd(const double* a, int32_t na, const double* b, int32_t nb, int32_t d, int32_t cm, double bw) {
+  double saa = 0, sab = 0, sbb = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    const double* P = pass == 2 ? b : a;
+    const double* Q = pass == 0 ? a : b;
+    const int np = pass == 2 ? nb : na, nq = pass == 0 ? na : nb;
+    double s = 0;
+    for (int i = 0; i < np; ++i)
+      for (int j = 0; j < nq; ++j) {
+        double d2 = 0;
+        for (int c = 0; c < d; ++c) {
+          double dl = mdiff(P[i * d + c], Q[j * d + c], is_circ(cm, c));
+          d2 += dl * dl;
+        }
+        s += exp(-bw * d2);
+      }
+    if (pass == 0) saa = s; else if (pass == 1) sab = s; else sbb = s;
+  }
+  return saa / ((double)na * na) - 2.0 * sab / ((double)na * nb) + sbb / ((double)nb * nb);
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* a3/a4/a5: approxConvBelief -> evalFactor -> evalPotentialSpecific                        */
 /* ------------------------------------------------------------------------------------ */
 static int is_prior_kind(int k) {

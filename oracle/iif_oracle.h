@@ -87,6 +87,11 @@ int32_t iifo_residual(int32_t kind, int32_t d, int32_t circ_mask, int32_t zdim, 
 double iifo_std_basic_spread(const double* pts, int32_t n, int32_t d, int32_t circ_mask);
 
 /* a14: per-dimension leave-one-out likelihood bandwidth (manikde! with bw === nothing) */
+/* approxDeconv (DeconvUtils.jl:32-162): predicted and sampled measurements, N x zdim each */
+int32_t iifo_deconv(const iifo_graph* g, int32_t factor, int32_t N, int32_t call_id,
+                    double* out_pred, double* out_meas);
+/* mmd (SolverUtilities.jl:25-47 / AMP.mmd!): kernel-embedding distance of two point sets */
+double iifo_mmd(const double* a, int32_t na, const double* b, int32_t nb, int32_t d, int32_t cm, double bw);
 /* calcPPE (FGOSUtils.jl:237-278): mean and KDE-max point estimates of one belief */
 int32_t iifo_ppe(const double* pts, int32_t n, int32_t d, int32_t cm, const double* bw,
                  double* mean_out, double* max_out);

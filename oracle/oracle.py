@@ -125,6 +125,16 @@ class Oracle:
         _check(st, "conv")
         return pts, bw[:d], ipc[:d], lab, nan.value
 
+    def deconv(self, factor, N, call_id):
+        """approxDeconv of one factor -> (predicted N x z, sampled N x z)"""
+        zd = self.frozen["factors"][factor].zdim
+        pred, meas = np.zeros((N, zd)), np.zeros((N, zd))
+        L = lib()
+        L.iifo_deconv.restype = C.c_int32
+        _check(L.iifo_deconv(C.byref(self.g), C.c_int32(factor), C.c_int32(N), C.c_int32(call_id), _dp(pred), _dp(meas)),
+               "deconv")
+        return pred, meas
+
     def propagate(self, op):
         _check(lib().iifo_propagate(C.byref(self.g), C.byref(op)), "propagate")
 
@@ -168,6 +178,16 @@ def ppe(pts, bw, circ_mask=0):
                            _dp(mx).__class__]
     _check(L.iifo_ppe(_dp(pts), n, d, circ_mask, _dp(b), _dp(mean), _dp(mx)), "ppe")
     return mean[:d], mx[:d]
+
+
+def mmd(a, b, circ_mask=0, bw=0.001):
+    """AMP.mmd kernel-embedding distance between two point sets (N x d each)"""
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(len(a), -1)
+    b = np.ascontiguousarray(b, dtype=np.float64).reshape(len(b), -1)
+    L = lib()
+    L.iifo_mmd.restype = C.c_double
+    return float(L.iifo_mmd(_dp(a), C.c_int32(a.shape[0]), _dp(b), C.c_int32(b.shape[0]), C.c_int32(a.shape[1]),
+                            C.c_int32(circ_mask), C.c_double(bw)))
 
 
 def loo_nll(x, h, circular=0):

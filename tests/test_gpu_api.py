@@ -237,3 +237,16 @@ def test_c2_full_size_chain_properties(built):
     spread = p1.std(axis=1)
     assert (spread < 4.0 * sigma + 0.5).all() and (spread > 0.01).all()
     ts.close()
+
+
+def test_approxDeconv_reference_bands(built):
+    """test/testDefaultDeconv.jl:10-31: after solving a 3-pose line, the predicted measurements of the prior and
+    of an odometry factor agree with fresh factor samples in the mmd sense (< 1e-8 resp. < 1e-3 there; the prior
+    band is taken at 1e-6 because x0 here is a solved posterior, not the prior's own samples)."""
+    fg = W.scalar_chain(3, N=100, seed=9)
+    SV.solveTree(fg)
+    pred, meas = SV.approxDeconv(fg, "x0f1")
+    assert pred.shape == (100, 1) and SV.mmd(fg, pred, meas, G.ContinuousScalar) < 1e-6
+    pred, meas = SV.approxDeconv(fg, "x0x1f1")
+    assert SV.mmd(fg, pred, meas, G.ContinuousScalar) < 1e-3
+    assert abs(pred.mean() - 1.0) < 0.2 and abs(meas.mean() - 1.0) < 0.05

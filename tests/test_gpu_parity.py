@@ -137,3 +137,36 @@ def test_ppe_parity(built):
         rng_ = x.max(axis=0) - x.min(axis=0)
         assert np.all(np.abs(mx[k, :vt.dim] - ox) <= 1e-12 + 0 * rng_) or \
             np.all(np.abs(mx[k, :vt.dim] - ox) <= step_tol * rng_ * 1.0001), (k, mx[k], ox)
+
+
+def test_deconv_and_mmd_parity(built):
+    """approxDeconv and mmd on the device against the oracle (same Philox streams)."""
+    import oracle as O
+    from iifb200 import graph as G
+    R = np.random.default_rng(31)
+    P = PC.Problem()
+    N = 100
+    x0 = P.slot(G.ContinuousScalar, N, R.normal(0, 1, (N, 1)))
+    x1 = P.slot(G.ContinuousScalar, N, R.normal(1, 1, (N, 1)))
+    c0 = P.slot(G.Circular, N, PC.wrap(R.normal(3.0, 0.5, (N, 1))))
+    c1 = P.slot(G.Circular, N, PC.wrap(R.normal(-2.5, 0.5, (N, 1))))
+    p0 = P.slot(G.Position(2), 60, R.normal(0, 1, (60, 2)))          # shorter than N: random partner (_getindex_anyn)
+    p1 = P.slot(G.Position(2), N, R.normal(5, 1, (N, 2)))
+    fs = [P.factor(G.Prior(G.Normal(0.0, 1.0)), [x0]),
+          P.factor(G.LinearRelative(G.Normal(1.0, 0.1)), [x0, x1]),
+          P.factor(G.CircularCircular(G.Normal(0.5, 0.1)), [c0, c1]),
+          P.factor(G.PriorCircular(G.Normal(3.0, 0.1)), [c0]),
+          P.factor(G.LinearRelative(G.MvNormal([5.0, 5.0], np.diag([0.1, 0.2]))), [p0, p1]),
+          P.factor(G.EuclidDistance(G.Normal(7.0, 0.1)), [p0, p1])]
+    P.freeze()
+    orc, eng = P.oracle(), P.engine()
+    for k, f in enumerate(fs):
+        po, mo = orc.deconv(f, N, 900 + k)
+        pg, mg = eng.deconv(f, N, 900 + k)
+        assert np.allclose(pg, po, rtol=0, atol=1e-12), k
+        assert np.allclose(mg, mo, rtol=0, atol=1e-12), k
+        cm = 1 if k in (2, 3) else 0
+        assert abs(eng.mmd(pg, mg, cm) - O.mmd(po, mo, cm)) < 1e-12
+    a, b = R.normal(0, 2, (200, 3)), R.normal(0.5, 2, (150, 3))
+    assert abs(eng.mmd(a, b, 0b010, 0.01) - O.mmd(a, b, 0b010, 0.01)) < 1e-12
+    eng.close()

@@ -243,3 +243,37 @@ def test_ppe_oracle_known_answers():
     y = R.normal([1.0, -5.0], [0.5, 2.0], (100, 2))
     mean, mx = O.ppe(y, [0.2, 0.8])
     assert np.allclose(mean, y.mean(axis=0)) and abs(mx[0] - 1.0) < 0.5 and abs(mx[1] + 5.0) < 2.0
+
+
+def test_deconv_and_mmd_oracle_known_answers():
+    """approxDeconv restatement (DeconvUtils.jl:32-162) and mmd (SolverUtilities.jl:25-47 / AMP.mmd!)."""
+    # mmd: identical sets -> 0; two single points at distance D -> 2 (1 - exp(-bw D^2))
+    R = np.random.default_rng(2)
+    a = R.normal(0, 1, (50, 1))
+    assert abs(O.mmd(a, a)) < 1e-15
+    assert abs(O.mmd(np.array([[0.0]]), np.array([[3.0]]), bw=0.5) - 2 * (1 - np.exp(-0.5 * 9.0))) < 1e-15
+    assert O.mmd(a, a + 100.0) > O.mmd(a, a + 1.0) > 0
+    # circular distance: points at +-(pi - 0.01) are 0.02 apart on the circle
+    assert O.mmd(np.array([[np.pi - 0.01]]), np.array([[-np.pi + 0.01]]), circ_mask=1, bw=1.0) < 1e-3
+    # deconv: prior -> the variable's own particles; relative -> particle differences; sampled = factor samples
+    P, xs, fs = PC.chain_problem(n=3, N=100, seed=4)
+    orc = P.oracle()
+    pred, meas = orc.deconv(fs[0], 100, 77)
+    x0 = P.arena.get(xs[0])[0]
+    assert np.array_equal(pred, x0) and meas.shape == (100, 1) and abs(meas.std() - 0.1) < 0.05
+    pred, meas = orc.deconv(fs[1], 100, 78)
+    x1 = P.arena.get(xs[1])[0]
+    assert np.allclose(pred, x1 - x0, rtol=0, atol=1e-15) and abs(meas.mean() - 1.0) < 0.05
+    # the reference's own bands (test/testDefaultDeconv.jl:18-31) on beliefs consistent with the factors
+    x0s = R.normal(0.0, 0.1, (100, 1))
+    Q = PC.Problem()
+    from iifb200 import graph as G
+    a0 = Q.slot(G.ContinuousScalar, 100, x0s)
+    a1 = Q.slot(G.ContinuousScalar, 100, x0s + R.normal(1.0, 0.1, (100, 1)))
+    fp = Q.factor(G.Prior(G.Normal(0.0, 0.1)), [a0])
+    fr = Q.factor(G.LinearRelative(G.Normal(1.0, 0.1)), [a0, a1])
+    orc = Q.freeze().oracle()
+    pred, meas = orc.deconv(fp, 100, 5)
+    assert O.mmd(pred, meas) < 1e-6
+    pred, meas = orc.deconv(fr, 100, 6)
+    assert O.mmd(pred, meas) < 1e-3
