@@ -93,6 +93,40 @@ function propagateBelief(dfg::AbstractDFG, destvar::DFGVariable, factors::Abstra
   return mkd, ipc
 end
 
+"""
+    calcPPE(var, varType; solveKey)   — FGOSUtils.jl:237-278 (setPPE! at CSM step 5 funnels through it)
+
+b200 backend: mean and KDE-max of a belief that is resident on the device (`slot` = its slot index in the
+tables uploaded by the enclosing clique solve) from one `iifb200_ppe_batch` launch.
+"""
+function calcPPE_b200(slots::Vector{Int32})
+  ctx = _ctx(); V = length(slots)
+  mean = zeros(4, V); mx = zeros(4, V)
+  check(ctx, ccall((:iifb200_ppe_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+        ctx, V, slots, mean, mx), "ppe_batch")
+  return mean, mx      # column v: coordinates of belief v; MeanMaxPPE(suggested = mean, max = mx, mean = mean)
+end
+
+"""
+    approxDeconv(dfg, fctsym)   — DeconvUtils.jl:176-202,  mmd(p1, p2, varType) — SolverUtilities.jl:25-47
+"""
+function approxDeconv_b200(factor::Integer, N::Integer, zdim::Integer)
+  ctx = _ctx()
+  pred = zeros(zdim, N); meas = zeros(zdim, N)
+  check(ctx, ccall((:iifb200_deconv_batch, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ptr{Float64}, Ptr{Float64}),
+        ctx, 1, Int32(factor), Int32(N), Int32(rand(0:2^30)), pred, meas), "deconv_batch")
+  return pred, meas
+end
+
+function mmd_b200(a::Matrix{Float64}, b::Matrix{Float64}; circmask::Integer = 0, bw::Float64 = 0.001)
+  ctx = _ctx(); out = Ref(0.0)
+  check(ctx, ccall((:iifb200_mmd, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}),
+        ctx, 1, Int32(size(a, 2)), Int32(size(b, 2)), Int32(size(a, 1)), Int32(circmask), a, b, bw, out), "mmd")
+  return out[]
+end
+
 # throughput mode (boundary B4): IIF.upGibbsCliqueDensity / localProductAndUpdate! are lowered per tree by
 # iifb200_schedule_build and replayed by iifb200_schedule_run; see incrementalinference.jl_b200/tree.py for
 # the lowering that a Julia implementation mirrors 1:1 (same descriptor structs).
