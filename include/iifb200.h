@@ -37,6 +37,10 @@
  * plus `dim` bandwidths and `dim` infoPerCoord values.  Points are stored as
  * coordinates at the group identity (TranslationGroup(d), RealCircleGroup and their
  * products: point representation == coordinates; circular coordinates live in [-pi,pi)).
+ * SpecialEuclidean(2) points ArrayPartition(t, R) are stored as (t1, t2, atan2(R21, R11)) with
+ * dim = 3, circ_mask = 0b100 (vee(log(M, eps, p)) in the hybrid tangent representation the reference
+ * tests use, test/testSpecialEuclidean2Mani.jl:14); KDE bandwidth / product / statistics work on these
+ * coordinates, only the relative residual (IIF_F_SE2_RELATIVE) composes on the group.
  */
 #ifndef IIFB200_H
 #define IIFB200_H
@@ -67,7 +71,14 @@ enum iif_factor_kind {
   IIF_F_CIRCULAR_CIRCULAR = 4, /* CircularCircular Circular.jl:13,24  vee(log(q, exp(p,X)))      */
   IIF_F_EUCLID_DISTANCE = 5,   /* EuclidDistance   EuclidDistance.jl:9,20    z - norm(x2 - x1)   */
   IIF_F_MSG_PRIOR = 6,         /* MsgPrior         MsgPrior.jl:10,36         z - x1              */
-  IIF_F_PARTIAL_PRIOR = 7      /* PartialPrior     PartialPrior.jl:11-21  (prior on partial_mask dims) */
+  IIF_F_PARTIAL_PRIOR = 7,     /* PartialPrior     PartialPrior.jl:11-21  (prior on partial_mask dims) */
+  /* generic-manifold factors (src/Factors/GenericFunctions.jl) on groups whose point coordinates
+   * are (Euclid..., angle...): TranslationGroup(d), RealCircleGroup, SpecialEuclidean(2) as (x, y, theta). */
+  IIF_F_MANIFOLD_PRIOR = 8,    /* ManifoldPrior :163-214 / ManifoldPriorPartial :288-303: sample = retract(M, p, hat(Z))
+                                  = p (+) Z coordinate-wise (angles wrapped); p is folded into Z's mean by the host;
+                                  partial_mask != 0 selects the informed coordinates */
+  IIF_F_SE2_RELATIVE = 9       /* ManifoldFactor{SpecialEuclidean(2)} :64-100 with distanceTangent2Point :39-44:
+                                  qhat = p o exp(eps, X), residual vee(log(q, qhat)); X = (dx, dy, dtheta) in p's frame */
 };
 
 /* measurement distributions (SamplableBelief) */

@@ -17,6 +17,7 @@ IIF_OK, IIF_ERR_ARG, IIF_ERR_CUDA, IIF_ERR_UNSUPPORTED, IIF_ERR_STATE = 0, -1, -
 # iif_factor_kind
 F_PRIOR, F_LINEAR_RELATIVE, F_PRIOR_CIRCULAR, F_CIRCULAR_CIRCULAR = 1, 2, 3, 4
 F_EUCLID_DISTANCE, F_MSG_PRIOR, F_PARTIAL_PRIOR = 5, 6, 7
+F_MANIFOLD_PRIOR, F_SE2_RELATIVE = 8, 9
 # iif_dist_kind
 D_NORMAL, D_MVNORMAL, D_MIXTURE, D_KDE, D_UNIFORM = 1, 2, 3, 4, 5
 # iif_sched_kind

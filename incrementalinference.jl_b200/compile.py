@@ -63,7 +63,7 @@ class Tables:
         d = self.add_dist(Z)
         zdim = self.dists[d][1]
         partial_mask = 0
-        if isinstance(fnc, G.PartialPrior):
+        if isinstance(fnc, (G.PartialPrior, G.ManifoldPriorPartial)):
             for c in fnc.partial:
                 partial_mask |= 1 << (int(c) - 1)
         self.factors.append(dict(kind=fnc.kind, arity=len(slots), zdim=zdim, dist=d, slot=list(slots),

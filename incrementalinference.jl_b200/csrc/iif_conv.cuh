@@ -292,6 +292,16 @@ __device__ __forceinline__ void solve_binary(int kind, int d, int32_t cm, const 
                                              bool sf_second, const double* u0, double* out) {
   if (kind == IIF_F_LINEAR_RELATIVE || kind == IIF_F_CIRCULAR_CIRCULAR) {
     for (int c = 0; c < d; ++c) out[c] = madd(other[c], sf_second ? z[c] : -z[c], is_circ(cm, c));
+  } else if (kind == IIF_F_SE2_RELATIVE) {
+    // ManifoldFactor{SpecialEuclidean(2)}: q = p o exp(eps, X)  (GenericFunctions.jl:39-44, hybrid tangent
+    // representation: exp(eps, X) = (X_t, R(X_theta))).  Solving q: theta_q = theta_p + X_theta,
+    // t_q = t_p + R(theta_p) X_t; solving p: theta_p = theta_q - X_theta, t_p = t_q - R(theta_p) X_t.
+    const double th = sf_second ? other[2] : wrap_pi(other[2] - z[2]);
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    const double rx = cs * z[0] - sn * z[1], ry = sn * z[0] + cs * z[1];
+    if (sf_second) { out[0] = other[0] + rx; out[1] = other[1] + ry; out[2] = wrap_pi(other[2] + z[2]); }
+    else { out[0] = other[0] - rx; out[1] = other[1] - ry; out[2] = th; }
   } else {
     double dir[IIF_MAX_DIM], nrm = 0;
     for (int c = 0; c < d; ++c) { dir[c] = u0[c] - other[c]; nrm += dir[c] * dir[c]; }
@@ -305,7 +315,8 @@ __device__ __forceinline__ void solve_binary(int kind, int d, int32_t cm, const 
 }
 
 __device__ __forceinline__ bool is_prior_kind(int k) {
-  return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR;
+  return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR ||
+         k == IIF_F_MANIFOLD_PRIOR;
 }
 
 __global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
@@ -413,13 +424,17 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
     if (is_prior_kind(f.kind)) {
       // evalPotentialSpecific (AbstractPrior) — EvalFactor.jl:400-542
       double spreadDist = g.sp->spreadNH * block_std_basic_spread(dest, N, d, cm, mu_s, red, parity);  // :464
-      const bool wrap = (f.kind == IIF_F_PRIOR_CIRCULAR || f.kind == IIF_F_MSG_PRIOR);
+      const bool wrap = (f.kind == IIF_F_PRIOR_CIRCULAR || f.kind == IIF_F_MSG_PRIOR || f.kind == IIF_F_MANIFOLD_PRIOR);
       if (active && label == 1) {
         if (!f.partial_mask) {
           for (int c = 0; c < d; ++c) my[c] = (wrap && is_circ(cm, c)) ? wrap_pi(z[c]) : z[c];
         } else {
           int k = 0;
-          for (int c = 0; c < d; ++c) if ((pmask >> c) & 1) my[c] = z[k++];
+          for (int c = 0; c < d; ++c)
+            if ((pmask >> c) & 1) {
+              const double v = z[k++];
+              my[c] = (f.kind == IIF_F_MANIFOLD_PRIOR && is_circ(cm, c)) ? wrap_pi(v) : v;
+            }
         }
         for (int c = 0; c < d; ++c) dest[n * d + c] = my[c];
       }

@@ -56,6 +56,21 @@ __global__ void iif_deconv_kernel(DeviceGraph g, const DeconvTask* __restrict__ 
           if ((f.partial_mask >> c) & 1) p[k++] = x[0][c];
         break;
       }
+      case IIF_F_MANIFOLD_PRIOR: {  // the sampled measurement IS a point: z = x1 (on the informed coordinates)
+        int k = 0;
+        for (int c = 0; c < S1.dim; ++c)
+          if (!f.partial_mask || ((f.partial_mask >> c) & 1)) p[k++] = is_circ(S1.circ_mask, c) ? wrap_pi(x[0][c]) : x[0][c];
+        break;
+      }
+      case IIF_F_SE2_RELATIVE: {    // X = vee(log(eps, p^-1 o q)): X_t = R(theta_p)^T (t_q - t_p), X_theta = theta_q - theta_p
+        double sn, cs;
+        sincos(x[0][2], &sn, &cs);
+        const double dx = x[1][0] - x[0][0], dy = x[1][1] - x[0][1];
+        p[0] = cs * dx + sn * dy;
+        p[1] = -sn * dx + cs * dy;
+        p[2] = wrap_pi(x[1][2] - x[0][2]);
+        break;
+      }
       case IIF_F_LINEAR_RELATIVE:
       case IIF_F_CIRCULAR_CIRCULAR:
         for (int c = 0; c < zd; ++c) p[c] = mdiff(x[1][c], x[0][c], is_circ(S1.circ_mask, c));

@@ -34,6 +34,28 @@ def Position(n: int) -> InferenceVariable:  # DefaultVariables.jl:9-24
 ContinuousEuclid = Position
 ContinuousScalar = Position(1)              # DefaultVariables.jl:32
 Circular = InferenceVariable("Circular", 1, 1)  # DefaultVariables.jl:52  RealCircleGroup
+# @defVariable SpecialEuclidean2 SpecialEuclidean(2; vectors=HybridTangentRepresentation()) (test/testSpecialEuclidean2Mani.jl:14):
+# device points are the coordinates (x, y, theta) = vee(log(M, eps, p)); theta is circular
+SpecialEuclidean2 = InferenceVariable("SpecialEuclidean2", 3, 0b100)
+
+
+def TranslationGroup(n: int) -> InferenceVariable:
+    return Position(n)
+
+
+RealCircleGroup = Circular
+
+
+def se2_point_to_coords(t, R) -> np.ndarray:
+    """ArrayPartition(t, R) -> (x, y, theta): AMP.makeCoordsFromPoint for SpecialEuclidean(2)."""
+    R = np.asarray(R, dtype=np.float64)
+    return np.array([t[0], t[1], np.arctan2(R[1, 0], R[0, 0])])
+
+
+def se2_coords_to_point(c):
+    """(x, y, theta) -> (t, R): AMP.makePointFromCoords for SpecialEuclidean(2)."""
+    cs, sn = np.cos(c[2]), np.sin(c[2])
+    return np.array([c[0], c[1]]), np.array([[cs, -sn], [sn, cs]])
 
 
 # ---------------------------------------------------------------- SamplableBelief
@@ -138,6 +160,51 @@ class EuclidDistance:      # EuclidDistance.jl:9
     Z: object
     kind = A.F_EUCLID_DISTANCE
     is_prior = False
+
+
+class ManifoldPrior:
+    """ManifoldPrior(M, p, Z) — GenericFunctions.jl:163-214: Z is a tangent-coordinate distribution at the point
+    `p`; a sample is retract(M, p, hat(M, p, rand(Z))), which for TranslationGroup / RealCircleGroup /
+    SpecialEuclidean(2) (hybrid representation) is p (+) Z coordinate-wise, so `p` (coordinates) is folded
+    into Z's mean when the factor is lowered."""
+    kind = A.F_MANIFOLD_PRIOR
+    is_prior = True
+
+    def __init__(self, M: InferenceVariable, p, Z):
+        self.M, self.p, self.Z0 = M, np.atleast_1d(np.asarray(p, dtype=np.float64)), Z
+        assert self.p.shape[0] == M.dim, "p must be given in coordinates (see se2_point_to_coords)"
+        if isinstance(Z, MvNormal):
+            self.Z = MvNormal(Z.mu + self.p, Z.cov)
+        elif isinstance(Z, Normal):
+            self.Z = Normal(Z.mu + float(self.p[0]), Z.sigma)
+        else:
+            raise A.IIFB200Error(f"ManifoldPrior: distribution {type(Z).__name__} has no device sampler")
+
+
+class ManifoldPriorPartial:
+    """ManifoldPriorPartial(M, Z, partial) — GenericFunctions.jl:288-303: Xc[partial] = rand(Z) at the identity."""
+    kind = A.F_MANIFOLD_PRIOR
+    is_prior = True
+
+    def __init__(self, M: InferenceVariable, Z, partial: Sequence[int]):
+        self.M, self.Z, self.partial = M, Z, tuple(int(c) for c in partial)
+
+
+class ManifoldFactor:
+    """ManifoldFactor(M, Z) — GenericFunctions.jl:64-100: relative factor with the measurement a tangent at the
+    identity; residual distanceTangent2Point (:39-52).  Lowered to the residual of the group M."""
+    is_prior = False
+
+    def __init__(self, M: InferenceVariable, Z):
+        self.M, self.Z = M, Z
+        if M.name == "SpecialEuclidean2":
+            self.kind = A.F_SE2_RELATIVE
+        elif M.circ_mask == 0:
+            self.kind = A.F_LINEAR_RELATIVE           # TranslationGroup: exp(p, X) = p + X
+        elif M.dim == 1 and M.circ_mask == 1:
+            self.kind = A.F_CIRCULAR_CIRCULAR         # RealCircleGroup
+        else:
+            raise A.IIFB200Error(f"ManifoldFactor on {M.name} has no device residual (no CPU fallback)")
 
 
 class Mixture:

@@ -271,7 +271,7 @@ def _setCliqMCIDs(fg: G.FactorGraph, c: TreeClique):
     # only *partial* priors count as singletons there; full priors are not in `allsings`.
     partial_prior_vars = []
     for i, fl in enumerate(c.potentials):
-        if prior_rows[i] and isinstance(fg.factors[fl].fnc, G.PartialPrior):
+        if prior_rows[i] and isinstance(fg.factors[fl].fnc, (G.PartialPrior, G.ManifoldPriorPartial)):
             partial_prior_vars += [cols[j] for j in range(len(cols)) if assoc[i, j]]
     del prior_vars
     allsings = _union(upmsg, partial_prior_vars)

@@ -277,6 +277,21 @@ int32_t iifo_residual(int32_t kind, int32_t d, int32_t cm, int32_t zdim, const d
       res[0] = z[0] - sqrt(s);
       return IIF_OK;
     }
+    case IIF_F_MANIFOLD_PRIOR: /* GenericFunctions.jl:209-214  vee(M, p, log(M, p, m)) in (Euclid.., angle..) coords */
+      for (int c = 0; c < zdim; ++c) res[c] = mdiff(z[c], x[c], is_circ(cm, c));
+      return IIF_OK;
+    case IIF_F_SE2_RELATIVE: { /* GenericFunctions.jl:39-44: qhat = compose(p, exp(M, eps, X)); vee(M, q, log(M, q, qhat));
+                                  hybrid tangent representation (testSpecialEuclidean2Mani.jl:14): exp(eps, X) = (X_t, R(X_th)),
+                                  log(q, qhat) = (t_qhat - t_q, th_qhat - th_q) */
+      if (arity != 2 || d != 3) return IIF_ERR_ARG;
+      const double* p = x; const double* q = x + d;
+      double sn = sin(p[2]), cs = cos(p[2]);
+      double qh0 = p[0] + cs * z[0] - sn * z[1], qh1 = p[1] + sn * z[0] + cs * z[1];
+      res[0] = qh0 - q[0];
+      res[1] = qh1 - q[1];
+      res[2] = wrap_pi(wrap_pi(p[2] + z[2]) - q[2]);
+      return IIF_OK;
+    }
     default: return IIF_ERR_UNSUPPORTED;
   }
 }
@@ -294,6 +309,14 @@ static void solve_binary(int kind, int d, int32_t cm, const double* z, const dou
       int circ = is_circ(cm, c);
       out[c] = sf_second ? madd(other[c], z[c], circ) : madd(other[c], -z[c], circ);
     }
+  } else if (kind == IIF_F_SE2_RELATIVE) {
+    /* unique root of the residual above: solving q: q = p o (X_t, R(X_th)); solving p: th_p = th_q - X_th,
+     * t_p = t_q - R(th_p) X_t */
+    double th = sf_second ? other[2] : wrap_pi(other[2] - z[2]);
+    double sn = sin(th), cs = cos(th);
+    double rx = cs * z[0] - sn * z[1], ry = sn * z[0] + cs * z[1];
+    if (sf_second) { out[0] = other[0] + rx; out[1] = other[1] + ry; out[2] = wrap_pi(other[2] + z[2]); }
+    else { out[0] = other[0] - rx; out[1] = other[1] - ry; out[2] = th; }
   } else { /* IIF_F_EUCLID_DISTANCE */
     double dir[IIF_MAX_DIM], nrm = 0;
     for (int c = 0; c < d; ++c) { dir[c] = u0[c] - other[c]; nrm += dir[c] * dir[c]; }
@@ -556,6 +579,21 @@ int32_t iifo_deconv(const iifo_graph* g, int32_t factor, int32_t N, int32_t call
         for (int c = 0; c < S1->dim; ++c) if ((f->partial_mask >> c) & 1) p[k++] = x[0][c];
         break;
       }
+      case IIF_F_MANIFOLD_PRIOR: {
+        int k = 0;
+        for (int c = 0; c < S1->dim; ++c)
+          if (!f->partial_mask || ((f->partial_mask >> c) & 1))
+            p[k++] = is_circ(S1->circ_mask, c) ? wrap_pi(x[0][c]) : x[0][c];
+        break;
+      }
+      case IIF_F_SE2_RELATIVE: { /* X = vee(log(eps, p^-1 o q)) */
+        double sn = sin(x[0][2]), cs = cos(x[0][2]);
+        double dx = x[1][0] - x[0][0], dy = x[1][1] - x[0][1];
+        p[0] = cs * dx + sn * dy;
+        p[1] = -sn * dx + cs * dy;
+        p[2] = wrap_pi(x[1][2] - x[0][2]);
+        break;
+      }
       case IIF_F_LINEAR_RELATIVE: case IIF_F_CIRCULAR_CIRCULAR:
         for (int c = 0; c < zd; ++c) p[c] = mdiff(x[1][c], x[0][c], is_circ(S1->circ_mask, c));
         break;
@@ -598,7 +636,8 @@ double iifo_mmd(const double* a, int32_t na, const double* b, int32_t nb, int32_
 /* a3/a4/a5: approxConvBelief -> evalFactor -> evalPotentialSpecific                        */
 /* ------------------------------------------------------------------------------------ */
 static int is_prior_kind(int k) {
-  return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR;
+  return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR ||
+         k == IIF_F_MANIFOLD_PRIOR;
 }
 
 static double inflate_u(const iifo_graph* g, const iif_conv_op* op, const double* uinf, int cyc,
@@ -706,7 +745,7 @@ int32_t iifo_conv(const iifo_graph* g, const iif_conv_op* op, const double* meas
   if (is_prior_kind(f->kind)) {
     /* evalPotentialSpecific, AbstractPrior — EvalFactor.jl:400-542 */
     double spreadDist = g->sp.spreadNH * iifo_std_basic_spread(dest, N, d, cm); /* :464 */
-    int wrap = (f->kind == IIF_F_PRIOR_CIRCULAR || f->kind == IIF_F_MSG_PRIOR);
+    int wrap = (f->kind == IIF_F_PRIOR_CIRCULAR || f->kind == IIF_F_MSG_PRIOR || f->kind == IIF_F_MANIFOLD_PRIOR);
     for (int n = 0; n < N; ++n) {
       if (mhidx[n] != 1) continue;                           /* ahmask :438 */
       if (!f->partial_mask) {                                /* setPointsMani! :469-474 */
@@ -717,7 +756,10 @@ int32_t iifo_conv(const iifo_graph* g, const iif_conv_op* op, const double* meas
       } else {                                               /* setPointPartial! :505-515 */
         int k = 0;
         for (int c = 0; c < d; ++c)
-          if ((pmask >> c) & 1) dest[n * d + c] = z[n * IIF_MAX_DIM + (k++)];
+          if ((pmask >> c) & 1) {
+            double v = z[n * IIF_MAX_DIM + (k++)];   /* ManifoldPriorPartial: point = exp(eps, hat(Xc)) => angles wrapped */
+            dest[n * d + c] = (f->kind == IIF_F_MANIFOLD_PRIOR && is_circ(cm, c)) ? wrap_pi(v) : v;
+          }
       }
     }
     /* null-hypothesis elements get entropy (:476 full, :531 partial dims only) */

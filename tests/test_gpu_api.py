@@ -250,3 +250,42 @@ def test_approxDeconv_reference_bands(built):
     pred, meas = SV.approxDeconv(fg, "x0x1f1")
     assert SV.mmd(fg, pred, meas, G.ContinuousScalar) < 1e-3
     assert abs(pred.mean() - 1.0) < 0.2 and abs(meas.mean() - 1.0) < 0.05
+
+
+def test_se2_solveTree_testSpecialEuclidean2Mani(built):
+    """SURVEY 8f-4, test/testSpecialEuclidean2Mani.jl:35-88: ManifoldPrior at the identity + ManifoldFactor
+    MvNormal([1, 2, pi/4], 0.01) chain on SpecialEuclidean(2); means within atol 0.1 after doautoinit! and after
+    solveTree!; :113-123 a PartialPrior on the translation gives a partial belief with 3 infoPerCoord."""
+    se = G.SpecialEuclidean2
+    fg = G.initfg(G.SolverParams(seed=17))
+    G.addVariable(fg, "x0", se)
+    G.addFactor(fg, ["x0"], G.ManifoldPrior(se, G.se2_point_to_coords([0.0, 0.0], np.eye(2)),
+                                            G.MvNormal([0, 0, 0], np.diag([1e-4] * 3))))
+    SV.doautoinit(fg, "x0")
+    assert np.abs(fg.variables["x0"].val.mean(axis=0)).max() < 0.1
+    G.addVariable(fg, "x1", se)
+    G.addFactor(fg, ["x0", "x1"], G.ManifoldFactor(se, G.MvNormal([1.0, 2.0, np.pi / 4], np.diag([0.01] * 3))))
+    SV.doautoinit(fg, "x1")
+
+    def mean(l):
+        p = fg.variables[l].val
+        return np.array([p[:, 0].mean(), p[:, 1].mean(), np.arctan2(np.sin(p[:, 2]).mean(), np.cos(p[:, 2]).mean())])
+
+    assert np.abs(mean("x1") - [1.0, 2.0, np.pi / 4]).max() < 0.1
+    SV.solveTree(fg)
+    assert np.abs(mean("x0")).max() < 0.1 and np.abs(mean("x1") - [1.0, 2.0, np.pi / 4]).max() < 0.1
+    t, Rm = G.se2_coords_to_point(mean("x1"))
+    assert np.allclose(Rm, [[0.7071, -0.7071], [0.7071, 0.7071]], atol=0.1) and np.allclose(t, [1.0, 2.0], atol=0.1)
+    G.addVariable(fg, "x2", se)
+    G.addFactor(fg, ["x1", "x2"], G.ManifoldFactor(se, G.MvNormal([1.0, 2.0, np.pi / 4], np.diag([0.01] * 3))))
+    SV.solveTree(fg)
+    c = np.sqrt(0.5)
+    assert np.abs(mean("x2") - [1.0 - c, 2.0 + 3 * c, np.pi / 2]).max() < 0.25
+    ppe = SV.getPPE(fg, "x2")
+    assert np.abs(ppe.suggested - mean("x2")).max() < 1e-9
+    # partial prior on an SE(2) variable
+    fg = G.initfg(G.SolverParams(seed=3, graphinit=False))
+    G.addVariable(fg, "x0", se)
+    G.addFactor(fg, ["x0"], G.PartialPrior(G.MvNormal([0.01, 0.01], np.eye(2) * 1e-4), (1, 2)))
+    pbel = SV.approxConvBelief(fg, "x0f1", "x0")
+    assert pbel.partial == [1, 2] and len(pbel.infoPerCoord) == 3

@@ -152,12 +152,17 @@ def test_deconv_and_mmd_parity(built):
     c1 = P.slot(G.Circular, N, PC.wrap(R.normal(-2.5, 0.5, (N, 1))))
     p0 = P.slot(G.Position(2), 60, R.normal(0, 1, (60, 2)))          # shorter than N: random partner (_getindex_anyn)
     p1 = P.slot(G.Position(2), N, R.normal(5, 1, (N, 2)))
+    se = G.SpecialEuclidean2
+    e0 = P.slot(se, N, np.column_stack([R.normal(0, 1, (N, 2)), PC.wrap(R.normal(3.0, 0.5, N))]))
+    e1 = P.slot(se, N, np.column_stack([R.normal(2, 1, (N, 2)), PC.wrap(R.normal(-2.0, 0.5, N))]))
     fs = [P.factor(G.Prior(G.Normal(0.0, 1.0)), [x0]),
           P.factor(G.LinearRelative(G.Normal(1.0, 0.1)), [x0, x1]),
           P.factor(G.CircularCircular(G.Normal(0.5, 0.1)), [c0, c1]),
           P.factor(G.PriorCircular(G.Normal(3.0, 0.1)), [c0]),
           P.factor(G.LinearRelative(G.MvNormal([5.0, 5.0], np.diag([0.1, 0.2]))), [p0, p1]),
-          P.factor(G.EuclidDistance(G.Normal(7.0, 0.1)), [p0, p1])]
+          P.factor(G.EuclidDistance(G.Normal(7.0, 0.1)), [p0, p1]),
+          P.factor(G.ManifoldFactor(se, G.MvNormal([1.0, 2.0, 0.7], np.diag([0.01] * 3))), [e0, e1]),
+          P.factor(G.ManifoldPrior(se, [0.1, 0.2, 3.0], G.MvNormal([0, 0, 0], np.diag([0.01] * 3))), [e0])]
     P.freeze()
     orc, eng = P.oracle(), P.engine()
     for k, f in enumerate(fs):
@@ -165,7 +170,7 @@ def test_deconv_and_mmd_parity(built):
         pg, mg = eng.deconv(f, N, 900 + k)
         assert np.allclose(pg, po, rtol=0, atol=1e-12), k
         assert np.allclose(mg, mo, rtol=0, atol=1e-12), k
-        cm = 1 if k in (2, 3) else 0
+        cm = 1 if k in (2, 3) else (4 if k in (6, 7) else 0)
         assert abs(eng.mmd(pg, mg, cm) - O.mmd(po, mo, cm)) < 1e-12
     a, b = R.normal(0, 2, (200, 3)), R.normal(0.5, 2, (150, 3))
     assert abs(eng.mmd(a, b, 0b010, 0.01) - O.mmd(a, b, 0b010, 0.01)) < 1e-12

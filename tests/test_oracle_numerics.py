@@ -277,3 +277,89 @@ def test_deconv_and_mmd_oracle_known_answers():
     assert O.mmd(pred, meas) < 1e-6
     pred, meas = orc.deconv(fr, 100, 6)
     assert O.mmd(pred, meas) < 1e-3
+
+
+def test_se2_residual_and_root_known_answers():
+    """SURVEY 8f-4.  ManifoldFactor{SpecialEuclidean(2)} residual (GenericFunctions.jl:39-44, hybrid tangent
+    representation as in test/testSpecialEuclidean2Mani.jl:14): p = identity, X = (1, 2, pi/4) puts q at
+    t = (1, 2), R(pi/4) (the values the reference test asserts, :62-63); composing once more from there gives
+    t = (1,2) + R(pi/4)(1,2), theta = pi/2."""
+    X = [1.0, 2.0, np.pi / 4]
+    e = np.zeros(3)
+    q1 = np.array([1.0, 2.0, np.pi / 4])
+    assert np.allclose(O.residual(A.F_SE2_RELATIVE, X, [e, q1], circ_mask=4), 0, atol=1e-15)
+    c = np.sqrt(0.5)
+    q2 = np.array([1.0 + c * 1 - c * 2, 2.0 + c * 1 + c * 2, np.pi / 2])
+    assert np.allclose(O.residual(A.F_SE2_RELATIVE, X, [q1, q2], circ_mask=4), 0, atol=1e-15)
+    # a displaced q gives (t_qhat - t_q, wrapped angle difference)
+    r = O.residual(A.F_SE2_RELATIVE, X, [e, q1 + [0.1, -0.2, 0.3]], circ_mask=4)
+    assert np.allclose(r, [-0.1, 0.2, -0.3])
+    # the angle residual wraps across the seam
+    r = O.residual(A.F_SE2_RELATIVE, [0, 0, 0.2], [np.array([0, 0, 3.1]), np.array([0, 0, -3.1])], circ_mask=4)
+    assert np.allclose(r, [0, 0, (3.3 - 2 * np.pi) + 3.1])
+    # ManifoldPrior residual: log(p, m) in coordinates
+    r = O.residual(A.F_MANIFOLD_PRIOR, [1.0, 2.0, 3.1], [np.array([0.5, 0.5, -3.1])], circ_mask=4)
+    assert np.allclose(r, [0.5, 1.5, 6.2 - 2 * np.pi])
+
+
+def test_se2_proposals_are_roots_and_deconv_inverts():
+    """Every proposal of the SE(2) convolution is a root of the residual for the sample's own measurement (both
+    solve directions), and approxDeconv recovers the measurement that was used."""
+    R = np.random.default_rng(8)
+    N = 64
+    se = G.SpecialEuclidean2
+    P = PC.Problem()
+    a = np.column_stack([R.normal(0, 2, N), R.normal(0, 2, N), PC.wrap(R.normal(3.0, 1.0, N))])
+    b = np.column_stack([R.normal(0, 2, N), R.normal(0, 2, N), PC.wrap(R.normal(-1.0, 1.0, N))])
+    s0, s1 = P.slot(se, N, a), P.slot(se, N, b)
+    f = P.factor(G.ManifoldFactor(se, G.MvNormal([1.0, 2.0, np.pi / 4], np.diag([0.04, 0.04, 0.01]))), [s0, s1])
+    P.freeze()
+    meas = R.normal([1.0, 2.0, 0.8], [0.2, 0.2, 0.1], (N, 3))
+    orc = P.oracle()
+    op = CP.make_conv_ops([dict(factor=f, sfidx=2, N=N, call_id=3, meas_off=0),
+                           dict(factor=f, sfidx=1, N=N, call_id=4, meas_off=0)])
+    q, *_ = orc.conv(op[0], meas.reshape(-1))
+    p, *_ = orc.conv(op[1], meas.reshape(-1))
+    for n in range(N):
+        assert np.allclose(O.residual(A.F_SE2_RELATIVE, meas[n], [a[n], q[n]], circ_mask=4), 0, atol=1e-12)
+        assert np.allclose(O.residual(A.F_SE2_RELATIVE, meas[n], [p[n], b[n]], circ_mask=4), 0, atol=1e-12)
+    assert np.all(np.abs(q[:, 2]) <= np.pi) and np.all(np.abs(p[:, 2]) <= np.pi)
+    # deconv on (a, q): predicted == the measurements (angles modulo 2 pi)
+    orc.arena.set(s1, q, None, True)
+    pred, _ = orc.deconv(f, N, 5)
+    d = pred - meas
+    d[:, 2] = PC.wrap(d[:, 2])
+    assert np.abs(d).max() < 1e-12
+
+
+def test_se2_reference_bands_testSpecialEuclidean2Mani():
+    """test/testSpecialEuclidean2Mani.jl:35-63 on the oracle: ManifoldPrior at the identity (sigma 0.01) initialises
+    x0 near the identity; ManifoldFactor MvNormal([1,2,pi/4], 0.01) initialises x1 near (1, 2, R(pi/4)); atol 0.1.
+    :113-123: a PartialPrior on dims (1,2) of an SE(2) variable gives a partial belief with 3 infoPerCoord."""
+    se = G.SpecialEuclidean2
+    N = 100
+    ok = 0
+    for seed in range(20):
+        P = PC.Problem(seed=seed)
+        x0 = P.slot(se, N, np.zeros((0, 3)), initialized=False)
+        x1 = P.slot(se, N, np.zeros((0, 3)), initialized=False)
+        fp = P.factor(G.ManifoldPrior(se, [0.0, 0.0, 0.0], G.MvNormal([0, 0, 0], np.diag([1e-4] * 3))), [x0])
+        ff = P.factor(G.ManifoldFactor(se, G.MvNormal([1.0, 2.0, np.pi / 4], np.diag([0.01] * 3))), [x0, x1])
+        P.freeze()
+        orc = P.oracle()
+        pr = CP.make_prop_ops([dict(target_slot=x0, out_slot=x0, factors=[(fp, 1)], N=N, call_id=16),
+                               dict(target_slot=x1, out_slot=x1, factors=[(ff, 2)], N=N, call_id=32)])
+        orc.propagate(pr[0])
+        orc.propagate(pr[1])
+        a, _, _ = orc.arena.get(x0)
+        b, bw, ipc = orc.arena.get(x1)
+        m1 = np.array([b[:, 0].mean(), b[:, 1].mean(), np.arctan2(np.sin(b[:, 2]).mean(), np.cos(b[:, 2]).mean())])
+        ok += (np.abs(a.mean(axis=0)).max() < 0.1) and (np.abs(m1 - [1.0, 2.0, np.pi / 4]).max() < 0.1) \
+            and np.all(bw > 0) and np.array_equal(ipc, [1.0, 1.0, 1.0])
+    assert ok == 20
+    P = PC.Problem()
+    x0 = P.slot(se, N, np.zeros((0, 3)), initialized=False)
+    fpp = P.factor(G.PartialPrior(G.MvNormal([0.01, 0.01], np.eye(2) * 1e-4), (1, 2)), [x0])
+    P.freeze()
+    pts, bw, ipc, _, _ = P.oracle().conv(CP.make_conv_ops([dict(factor=fpp, sfidx=1, N=N, call_id=1)])[0])
+    assert np.array_equal(ipc, [1.0, 1.0, 0.0]) and np.all(pts[:, 2] == 0.0) and abs(pts[:, 0].mean() - 0.01) < 0.01
