@@ -184,6 +184,15 @@ def conv_cases():
     fpp = P.factor(G.PartialPrior(G.Normal(-20.0, 1.0), (2,)), [q0])
     yield "partial_prior", P.freeze(), [dict(factor=fpp, sfidx=1, N=N, call_id=98)], None
 
+    # 12. extreme sizes: N=2 (minimum) and N=256 (IIF_MAX_POINTS)
+    for Nx in (2, 3, 256):
+        P = Problem()
+        a = P.slot(G.ContinuousScalar, Nx, R.normal(0, 1, (Nx, 1)), bw=[0.5])
+        b = P.slot(G.ContinuousScalar, Nx, R.normal(0, 1, (Nx, 1)), bw=[0.5])
+        fr = P.factor(G.LinearRelative(G.Normal(1.0, 0.1)), [a, b])
+        yield f"size_{Nx}", P.freeze(), [dict(factor=fr, sfidx=2, N=Nx, call_id=99)], None
+
+
     # 13. SpecialEuclidean(2) (testSpecialEuclidean2Mani.jl): ManifoldPrior, ManifoldFactor solved both
     # ways, a partial prior on the translation and on the angle, nullhypo entropy on the manifold
     P = Problem()
@@ -200,14 +209,6 @@ def conv_cases():
     yield "se2_circ", P.freeze(), [dict(factor=fmp, sfidx=1, N=N, call_id=110), dict(factor=fmf, sfidx=2, N=N, call_id=111),
                                    dict(factor=fmf, sfidx=1, N=N, call_id=112), dict(factor=fmn, sfidx=2, N=N, call_id=113),
                                    dict(factor=fpt, sfidx=1, N=N, call_id=114), dict(factor=fpa, sfidx=1, N=N, call_id=115)], None
-
-    # 12. extreme sizes: N=2 (minimum) and N=256 (IIF_MAX_POINTS)
-    for Nx in (2, 3, 256):
-        P = Problem()
-        a = P.slot(G.ContinuousScalar, Nx, R.normal(0, 1, (Nx, 1)), bw=[0.5])
-        b = P.slot(G.ContinuousScalar, Nx, R.normal(0, 1, (Nx, 1)), bw=[0.5])
-        fr = P.factor(G.LinearRelative(G.Normal(1.0, 0.1)), [a, b])
-        yield f"size_{Nx}", P.freeze(), [dict(factor=fr, sfidx=2, N=Nx, call_id=99)], None
 
 
 def wrap(a):
@@ -270,10 +271,6 @@ def product_cases():
     yield "partial_mask", dict(dens_pts=a, dens_bw=bws(a), dim=2, dens_mask=[0, 2], old_pts=R.normal(9, 1, (N, 2)), call_id=11)
     a = np.stack([R.normal(0, 1, (N, 2)), R.normal(5, 1, (N, 2))])
     yield "partial_uncovered_dim", dict(dens_pts=a, dens_bw=bws(a), dim=2, dens_mask=[2, 2], old_pts=R.normal(9, 1, (N, 2)), call_id=12)
-    # SpecialEuclidean(2) coordinates (x, y, theta): two Euclid + one circular coordinate across the +-pi seam
-    a = np.stack([np.column_stack([R.normal(1, 0.3, N), R.normal(2, 0.3, N), wrap(R.normal(3.1, 0.2, N))]),
-                  np.column_stack([R.normal(1.1, 0.4, N), R.normal(1.9, 0.2, N), wrap(R.normal(-3.1, 0.3, N))])])
-    yield "se2_circ_product", dict(dens_pts=a, dens_bw=bws(a, 4), dim=3, circ_mask=4, call_id=17)
     a = np.stack([R.normal(0, 1, (N, 1))])
     yield "single_passthrough", dict(dens_pts=a, dens_bw=bws(a), dim=1, call_id=13)
     a = np.stack([R.normal(0, 1, (256, 1)), R.normal(0.2, 1, (256, 1))])
@@ -284,6 +281,11 @@ def product_cases():
     a = np.stack([R.normal(0, 1, (N, 1)), R.normal(0.5, 1, (N, 1))])
     yield "explicit_gibbs_streams", dict(dens_pts=a, dens_bw=bws(a), dim=1, call_id=16,
                                          randU=R.random(N * 7 * 2), randN=R.normal(0, 1, N))
+
+    # SpecialEuclidean(2) coordinates (x, y, theta): two Euclid + one circular coordinate across the +-pi seam
+    a = np.stack([np.column_stack([R.normal(1, 0.3, N), R.normal(2, 0.3, N), wrap(R.normal(3.1, 0.2, N))]),
+                  np.column_stack([R.normal(1.1, 0.4, N), R.normal(1.9, 0.2, N), wrap(R.normal(-3.1, 0.3, N))])])
+    yield "se2_circ_product", dict(dens_pts=a, dens_bw=bws(a, 4), dim=3, circ_mask=4, call_id=17)
 
 
 def run_product_case(case, engine):
