@@ -26,6 +26,7 @@
  *   iifb200_kde_bandwidth    <- AMP.manikde! bandwidth (call sites ApproxConv.jl:38-41, FGOSUtils.jl:118-128)
  *   iifb200_ppe_batch        <- calcPPE / setPPE!           src/services/FGOSUtils.jl:237-278
  *   iifb200_deconv_batch     <- approxDeconv                src/services/DeconvUtils.jl:32-162
+ *   IIF_S_DECONV ops         <- addLikelihoodsDifferentialCHILD!  src/services/TreeMessageUtils.jl:279-335
  *   iifb200_mmd              <- mmd (AMP.mmd!)              src/services/SolverUtilities.jl:25-47
  *   belief slots             <- VariableNodeData.val/.bw, TreeBelief   src/entities/BeliefTypes.jl:47-57
  *   iif_factor_desc          <- CommonConvWrapper           src/entities/FactorOperationalMemory.jl:21-70
@@ -160,8 +161,23 @@ typedef struct {
 /* schedule op kinds (one clique solve = a few of these; one wave = independent ops) */
 enum iif_sched_kind {
   IIF_S_PROPAGATE = 1, /* propagateBelief + setBelief!  (SolveTree.jl:63-74)                */
-  IIF_S_COPY = 2       /* slot := slot (separator message adoption, TreeMessageUtils.jl:66) */
+  IIF_S_COPY = 2,      /* slot := slot (separator message adoption, TreeMessageUtils.jl:66) */
+  IIF_S_DECONV = 3     /* differential likelihood of an up message (useMsgLikelihoods=true):
+                          slot := manikde!(exp(M, eps, approxDeconv(dummy factor)))
+                          addLikelihoodsDifferentialCHILD!, TreeMessageUtils.jl:279-335            */
 };
+
+/* One differential-likelihood construction (TreeMessageUtils.jl:314-321): approxDeconv of the (dummy)
+ * relative factor `factor` over two separator beliefs, the predicted measurements mapped to points
+ * (exp at the identity: angles wrapped) and written, with their KDE bandwidth, into `out_slot`
+ * (dim == the factor's zdim).  The belief in out_slot then serves as the measurement density
+ * (IIF_D_KDE) of the relative factor the parent clique adds (`_sft(newBel)`, :321-324). */
+typedef struct {
+  int32_t factor;   /* index into the factor table: binary relative factor, no multihypo */
+  int32_t out_slot; /* belief slot receiving N points of dim zdim (+ bw, ipc = 1, initialized) */
+  int32_t N;        /* samples (approxDeconv uses the point count of the first variable, DeconvUtils.jl:194-196) */
+  int32_t call_id;  /* Philox call id (partner draws for short beliefs, measurement start samples) */
+} iif_deconv_op;
 
 typedef struct iifb200_ctx iifb200_ctx;
 
@@ -270,13 +286,18 @@ int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* 
  * The schedule is captured once into a CUDA graph and replayed by iifb200_schedule_run. */
 typedef struct {
   int32_t kind; /* iif_sched_kind */
-  int32_t a;    /* PROPAGATE: index into props;  COPY: source slot */
+  int32_t a;    /* PROPAGATE: index into props;  COPY: source slot;  DECONV: index into deconvs */
   int32_t b;    /* COPY: destination slot */
   int32_t _pad;
 } iif_sched_op;
 int32_t iifb200_schedule_build(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off,
                                int32_t nops, const iif_sched_op* ops, int32_t nprops,
                                const iif_prop_op* props, int32_t* schedule_id_out);
+/* same, with IIF_S_DECONV ops (tree solves with SolverParams.useMsgLikelihoods = true) */
+int32_t iifb200_schedule_build_ex(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off,
+                                  int32_t nops, const iif_sched_op* ops, int32_t nprops,
+                                  const iif_prop_op* props, int32_t ndeconvs,
+                                  const iif_deconv_op* deconvs, int32_t* schedule_id_out);
 /* Runs schedule asynchronously on the ctx stream; `first_wave,last_wave` select a wave range
  * (multi-GPU: run to a cut level, exchange separator messages with NCCL, continue). */
 int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t first_wave,

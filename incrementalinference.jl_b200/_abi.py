@@ -21,7 +21,7 @@ F_MANIFOLD_PRIOR, F_SE2_RELATIVE = 8, 9
 # iif_dist_kind
 D_NORMAL, D_MVNORMAL, D_MIXTURE, D_KDE, D_UNIFORM = 1, 2, 3, 4, 5
 # iif_sched_kind
-S_PROPAGATE, S_COPY = 1, 2
+S_PROPAGATE, S_COPY, S_DECONV = 1, 2, 3
 
 
 class DistDesc(C.Structure):
@@ -65,6 +65,10 @@ class ProductOp(C.Structure):
                 ("randn_off", C.c_int32), ("_pad", C.c_int32)]
 
 
+class DeconvOp(C.Structure):
+    _fields_ = [("factor", C.c_int32), ("out_slot", C.c_int32), ("N", C.c_int32), ("call_id", C.c_int32)]
+
+
 class SchedOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("_pad", C.c_int32)]
 
@@ -101,6 +105,8 @@ SYMBOLS = {
     "iifb200_propagate_batch": (C.c_int32, [_vp, C.c_int32, P(PropOp)]),
     "iifb200_schedule_build": (C.c_int32, [_vp, C.c_int32, _ip, C.c_int32, P(SchedOp), C.c_int32,
                                            P(PropOp), _ip]),
+    "iifb200_schedule_build_ex": (C.c_int32, [_vp, C.c_int32, _ip, C.c_int32, P(SchedOp), C.c_int32,
+                                              P(PropOp), C.c_int32, P(DeconvOp), _ip]),
     "iifb200_schedule_run": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32]),
     "iifb200_schedule_free": (C.c_int32, [_vp, C.c_int32]),
     "iifb200_schedule_profile": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, P(C.c_float), _ip,

@@ -177,6 +177,14 @@ def make_prop_ops(specs):
     return ops
 
 
+def make_deconv_ops(specs):
+    """specs: list of dicts(factor, out_slot, N, call_id) -> iif_deconv_op array (IIF_S_DECONV)."""
+    ops = (A.DeconvOp * max(len(specs), 1))()
+    for i, s in enumerate(specs):
+        ops[i].factor, ops[i].out_slot, ops[i].N, ops[i].call_id = s["factor"], s["out_slot"], s["N"], s["call_id"]
+    return ops
+
+
 def make_sched_ops(ops_list):
     """ops_list: list of (kind, a, b)."""
     ops = (A.SchedOp * max(len(ops_list), 1))()

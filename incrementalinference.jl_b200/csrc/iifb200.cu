@@ -27,8 +27,9 @@ struct TreeHost {
 };
 
 struct Wave {
-  int conv0 = 0, nconv = 0, prod0 = 0, nprod = 0, copy0 = 0, ncopy = 0;
-  size_t prod_smem = 0, conv_smem = 0;
+  int conv0 = 0, nconv = 0, prod0 = 0, nprod = 0, copy0 = 0, ncopy = 0, dcv0 = 0, ndcv = 0;
+  size_t prod_smem = 0, conv_smem = 0, dcv_smem = 0;
+  int dcv_maxN = 2;
   int maxN = 2;
 };
 
@@ -37,9 +38,11 @@ struct Schedule {
   ConvTask* d_conv = nullptr;
   ProdTask* d_prod = nullptr;
   int32_t* d_copy = nullptr;
+  DeconvSlotTask* d_dcv = nullptr;
   double* d_scratch = nullptr;
-  int32_t* d_status = nullptr;
-  int nconv = 0, nprod = 0;
+  int32_t* d_status = nullptr;  // nconv + nprod + ndcv device-side status codes
+  int nconv = 0, nprod = 0, ndcv = 0;
+  int nstatus() const { return nconv + nprod + ndcv; }
   std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int>> graphs;  // (exec, kernel nodes)
 };
 
@@ -213,6 +216,9 @@ int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
   if ((e = cudaFuncSetAttribute(iif_bandwidth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ctx->max_smem_optin - 4096)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(bandwidth smem)", e);
+  if ((e = cudaFuncSetAttribute(iif_deconv_slot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(deconv smem)", e);
   *ctx_out = ctx;
   return IIF_OK;
 }
@@ -220,7 +226,7 @@ int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
 static void free_schedule(Schedule* s) {
   if (!s) return;
   for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second.first);
-  cudaFree(s->d_conv); cudaFree(s->d_prod); cudaFree(s->d_copy); cudaFree(s->d_scratch); cudaFree(s->d_status);
+  cudaFree(s->d_conv); cudaFree(s->d_prod); cudaFree(s->d_copy); cudaFree(s->d_dcv); cudaFree(s->d_scratch); cudaFree(s->d_status);
   delete s;
 }
 
@@ -820,7 +826,20 @@ int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_
 
 // ---- schedules: propagateBelief waves captured as a CUDA graph -----------------------------------
 static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
-                              const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, Schedule** out) {
+                              const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, int32_t ndeconvs,
+                              const iif_deconv_op* deconvs, Schedule** out) {
+  for (int k = 0; k < ndeconvs; ++k) {
+    const iif_deconv_op& D = deconvs[k];
+    if (D.factor < 0 || D.factor >= (int)ctx->factors.size() || D.out_slot < 0 || D.out_slot >= (int)ctx->slots.size())
+      return fail(ctx, IIF_ERR_ARG, "deconv op: factor / slot out of range");
+    const iif_factor_desc& F = ctx->factors[D.factor];
+    if (F.arity != 2 || F.nmh != 0 || is_prior_kind_h(F.kind))
+      return fail(ctx, IIF_ERR_UNSUPPORTED, "deconv op: needs a binary relative factor without multihypo");
+    if (ctx->slots[D.out_slot].dim != F.zdim || ctx->slots[D.out_slot].cap < D.N)
+      return fail(ctx, IIF_ERR_ARG, "deconv op: out slot must hold N points of the factor's measurement dimension");
+    int32_t st = ensure_tree(ctx, D.N);
+    if (st != IIF_OK) return st;
+  }
   // per-prop scratch layout: proposals F*N*d doubles, then bw F*4, ipc F*4 (ipc unused downstream)
   std::vector<int64_t> soff(nprops + 1, 0);
   std::vector<int> cidx(nprops + 1, 0);
@@ -847,16 +866,19 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
   *out = s;
   s->nconv = cidx[nprops];
   s->nprod = nprops;
+  s->ndcv = ndeconvs;
   std::vector<ConvTask> ct;
   std::vector<ProdTask> pt;
   std::vector<int32_t> cp;
+  std::vector<DeconvSlotTask> dt;
+  std::vector<char> dused(std::max(ndeconvs, 1), 0);
   CK(cudaMalloc(&s->d_scratch, sizeof(double) * std::max<int64_t>(soff[nprops], 1)));
-  CK(cudaMalloc(&s->d_status, sizeof(int32_t) * std::max(s->nconv + s->nprod, 1)));
-  CK(cudaMemsetAsync(s->d_status, 0, sizeof(int32_t) * std::max(s->nconv + s->nprod, 1), ctx->stream));
+  CK(cudaMalloc(&s->d_status, sizeof(int32_t) * std::max(s->nstatus(), 1)));
+  CK(cudaMemsetAsync(s->d_status, 0, sizeof(int32_t) * std::max(s->nstatus(), 1), ctx->stream));
   std::vector<char> used(nprops, 0);
   for (int w = 0; w < nwaves; ++w) {
     Wave W;
-    W.conv0 = (int)ct.size(); W.prod0 = (int)pt.size(); W.copy0 = (int)cp.size() / 2;
+    W.conv0 = (int)ct.size(); W.prod0 = (int)pt.size(); W.copy0 = (int)cp.size() / 2; W.dcv0 = (int)dt.size();
     if (wave_off[w] < 0 || wave_off[w + 1] > nops || wave_off[w] > wave_off[w + 1]) return fail(ctx, IIF_ERR_ARG, "schedule: bad wave offsets");
     for (int k = wave_off[w]; k < wave_off[w + 1]; ++k) {
       const iif_sched_op& o = ops[k];
@@ -864,6 +886,16 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
         if (o.a < 0 || o.a >= (int)ctx->slots.size() || o.b < 0 || o.b >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "schedule: copy slot out of range");
         if (ctx->slots[o.a].dim != ctx->slots[o.b].dim || ctx->slots[o.b].cap < ctx->slots[o.a].cap) return fail(ctx, IIF_ERR_ARG, "schedule: copy slots incompatible");
         cp.push_back(o.a); cp.push_back(o.b);
+      } else if (o.kind == IIF_S_DECONV) {
+        if (o.a < 0 || o.a >= ndeconvs) return fail(ctx, IIF_ERR_ARG, "schedule: deconv index out of range");
+        if (dused[o.a]) return fail(ctx, IIF_ERR_ARG, "schedule: a deconv op may appear once");
+        dused[o.a] = 1;
+        DeconvSlotTask t;
+        t.op = deconvs[o.a];
+        t.out_status = s->d_status + s->nconv + s->nprod + o.a;
+        dt.push_back(t);
+        W.dcv_smem = std::max(W.dcv_smem, conv_smem_bytes(t.op.N));
+        W.dcv_maxN = std::max(W.dcv_maxN, (int)t.op.N);
       } else if (o.kind == IIF_S_PROPAGATE) {
         if (o.a < 0 || o.a >= nprops) return fail(ctx, IIF_ERR_ARG, "schedule: prop index out of range");
         if (used[o.a]) return fail(ctx, IIF_ERR_ARG, "schedule: a prop op may appear once (its Philox call ids are unique)");
@@ -908,6 +940,7 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
       } else return fail(ctx, IIF_ERR_ARG, "schedule: unknown op kind");
     }
     W.nconv = (int)ct.size() - W.conv0; W.nprod = (int)pt.size() - W.prod0; W.ncopy = (int)cp.size() / 2 - W.copy0;
+    W.ndcv = (int)dt.size() - W.dcv0;
     if ((int)W.prod_smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "schedule: product exceeds the shared-memory budget");
     s->waves.push_back(W);
   }
@@ -917,6 +950,8 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
   if (!ct.empty()) CK(cudaMemcpyAsync(s->d_conv, ct.data(), sizeof(ConvTask) * ct.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (!pt.empty()) CK(cudaMemcpyAsync(s->d_prod, pt.data(), sizeof(ProdTask) * pt.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (!cp.empty()) CK(cudaMemcpyAsync(s->d_copy, cp.data(), sizeof(int32_t) * cp.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMalloc(&s->d_dcv, sizeof(DeconvSlotTask) * std::max<size_t>(dt.size(), 1)));
+  if (!dt.empty()) CK(cudaMemcpyAsync(s->d_dcv, dt.data(), sizeof(DeconvSlotTask) * dt.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
 }
@@ -924,11 +959,18 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
 int32_t iifb200_schedule_build(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
                                const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props,
                                int32_t* schedule_id_out) {
+  return iifb200_schedule_build_ex(ctx, nwaves, wave_off, nops, ops, nprops, props, 0, nullptr, schedule_id_out);
+}
+
+int32_t iifb200_schedule_build_ex(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
+                                  const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, int32_t ndeconvs,
+                                  const iif_deconv_op* deconvs, int32_t* schedule_id_out) {
   NEED_GRAPH();
-  if (nwaves < 1 || !wave_off || nops < 0 || !ops || nprops < 0 || !schedule_id_out) return fail(ctx, IIF_ERR_ARG, "schedule_build: bad arguments");
+  if (nwaves < 1 || !wave_off || nops < 0 || !ops || nprops < 0 || ndeconvs < 0 || (ndeconvs > 0 && !deconvs) || !schedule_id_out)
+    return fail(ctx, IIF_ERR_ARG, "schedule_build: bad arguments");
   CK(cudaSetDevice(ctx->device));
   Schedule* s = nullptr;
-  int32_t st = build_schedule(ctx, nwaves, wave_off, nops, ops, nprops, props, &s);
+  int32_t st = build_schedule(ctx, nwaves, wave_off, nops, ops, nprops, props, ndeconvs, deconvs, &s);
   if (st != IIF_OK) { free_schedule(s); return st; }
   ctx->schedules.push_back(s);
   *schedule_id_out = (int32_t)ctx->schedules.size() - 1;
@@ -942,6 +984,10 @@ static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int*
     const Wave& W = s->waves[w];
     if (W.ncopy) {
       iif_copy_kernel<<<W.ncopy, 128, 0, ctx->stream>>>(ctx->dg, s->d_copy + 2 * W.copy0, W.ncopy);
+      ++k;
+    }
+    if (W.ndcv) {
+      launch_k(iif_deconv_slot_kernel, W.ndcv, pick_cluster(ctx, W.ndcv), pick_threads(ctx, W.ndcv, W.dcv_maxN), W.dcv_smem, ctx->stream, ctx->dg, s->d_dcv + W.dcv0, ctx->d_trees);
       ++k;
     }
     if (W.nconv) {
@@ -1012,6 +1058,11 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
       iif_copy_kernel<<<W.ncopy, 128, 0, ctx->stream>>>(ctx->dg, s->d_copy + 2 * W.copy0, W.ncopy);
       mark(); kind.push_back(2); blocks[2] += W.ncopy;
     }
+    if (W.ndcv) {  // differential-likelihood construction is accounted with the copy (message) kernels
+      mark();
+      launch_k(iif_deconv_slot_kernel, W.ndcv, pick_cluster(ctx, W.ndcv), pick_threads(ctx, W.ndcv, W.dcv_maxN), W.dcv_smem, ctx->stream, ctx->dg, s->d_dcv + W.dcv0, ctx->d_trees);
+      mark(); kind.push_back(2); blocks[2] += W.ndcv;
+    }
     if (W.nconv) {
       mark();
       launch_k(iif_conv_kernel, W.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream, ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
@@ -1055,7 +1106,7 @@ int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* 
   for (int v = 0; v < V; ++v) { so[v].kind = IIF_S_PROPAGATE; so[v].a = v; so[v].b = 0; so[v]._pad = 0; }
   int32_t wo[2] = {0, V};
   Schedule* s = nullptr;
-  int32_t st = build_schedule(ctx, 1, wo, V, so.data(), V, ops, &s);
+  int32_t st = build_schedule(ctx, 1, wo, V, so.data(), V, ops, 0, nullptr, &s);
   if (st != IIF_OK) { free_schedule(s); return st; }
   int nk = 0;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1064,7 +1115,7 @@ int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* 
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->timed = true;
     ctx->launches += nk;
-    std::vector<int32_t> stat(s->nconv + s->nprod);
+    std::vector<int32_t> stat(s->nstatus());
     cudaError_t e = cudaMemcpyAsync(stat.data(), s->d_status, sizeof(int32_t) * stat.size(), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { free_schedule(s); return fail(ctx, IIF_ERR_CUDA, std::string("propagate_batch: ") + cudaGetErrorString(e)); }
@@ -1082,7 +1133,7 @@ int32_t iifb200_sync(iifb200_ctx* ctx) {
   // surface device-side failures of schedule runs
   for (auto* s : ctx->schedules) {
     if (!s) continue;
-    std::vector<int32_t> stat(s->nconv + s->nprod);
+    std::vector<int32_t> stat(s->nstatus());
     if (stat.empty()) continue;
     CK(cudaMemcpy(stat.data(), s->d_status, sizeof(int32_t) * stat.size(), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < stat.size(); ++i)

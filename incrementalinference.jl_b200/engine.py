@@ -194,11 +194,16 @@ class Engine:
         self._check(self.lib.iifb200_propagate_batch(self.ctx, V, prop_ops), "propagate_batch")
 
     # ---- schedules
-    def schedule_build(self, wave_off, sched_ops, nops, prop_ops, nprops):
+    def schedule_build(self, wave_off, sched_ops, nops, prop_ops, nprops, deconv_ops=None, ndeconvs=0):
         wo = np.ascontiguousarray(wave_off, dtype=np.int32)
         sid = C.c_int32(-1)
-        self._check(self.lib.iifb200_schedule_build(self.ctx, len(wo) - 1, A.as_ip(wo), nops, sched_ops, nprops,
-                                                    prop_ops, C.cast(C.byref(sid), A._ip)), "schedule_build")
+        if ndeconvs:
+            self._check(self.lib.iifb200_schedule_build_ex(self.ctx, len(wo) - 1, A.as_ip(wo), nops, sched_ops, nprops,
+                                                           prop_ops, ndeconvs, deconv_ops,
+                                                           C.cast(C.byref(sid), A._ip)), "schedule_build_ex")
+        else:
+            self._check(self.lib.iifb200_schedule_build(self.ctx, len(wo) - 1, A.as_ip(wo), nops, sched_ops, nprops,
+                                                        prop_ops, C.cast(C.byref(sid), A._ip)), "schedule_build")
         return sid.value
 
     def schedule_run(self, sid, first=0, last=-1):

@@ -79,7 +79,7 @@ class ShardedTreeSolver:
         self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
         self.fg = fg
         self.tree = TR.buildTree(fg, list(order))
-        self.plan = TR.compile_solve(fg, self.tree)
+        self.plan = TR.compile_solve(fg, self.tree, useMsgLikelihoods=False)   # sharded solves exchange plain separator beliefs
         self.owner = clique_owner(fg, self.tree, world)
         self.op_rank, self.transfers = partition_plan(self.plan, self.owner, world)
         my_ops, my_wave_off = rank_schedule(self.plan, self.op_rank, rank)

@@ -322,8 +322,10 @@ class TreeSolver:
         self.eng = Engine(self.plan.frozen, self.sp_c, device, ext_arena_ptr)
         self.props_c = CP.make_prop_ops(self.plan.props)
         self.sched_c = CP.make_sched_ops(self.plan.sched_waved)
+        self.deconvs_c = CP.make_deconv_ops(self.plan.deconvs or [])
         self.sid = self.eng.schedule_build(self.plan.wave_off, self.sched_c, len(self.plan.sched_waved),
-                                           self.props_c, len(self.plan.props))
+                                           self.props_c, len(self.plan.props), self.deconvs_c,
+                                           len(self.plan.deconvs or []))
         self.arena = CP.HostArena(self.plan.frozen)
 
     def load_from_graph(self):

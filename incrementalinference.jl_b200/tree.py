@@ -312,6 +312,7 @@ class SolvePlan:
     op_reads: Optional[List[List[int]]] = None   # slots read by every op of `sched_waved`
     op_writes: Optional[List[List[int]]] = None
     slot_clique: Optional[Dict[int, int]] = None  # clique-local slot -> clique id (main-graph slots absent)
+    deconvs: Optional[list] = None    # IIF_S_DECONV specs (useMsgLikelihoods=true): factor, out_slot, N, call_id
 
 
 def _levelize(ops, reads, writes):
@@ -337,12 +338,66 @@ def _levelize(ops, reads, writes):
     return waves
 
 
+def selectFactorType(t1: G.InferenceVariable, t2: G.InferenceVariable):
+    """selectFactorType — src/services/DefaultNodeTypes.jl:12-31: the default relative factor between two
+    variable types (Position{N} -> LinearRelative{N}; otherwise getfield(Module, Symbol(T1, T2)), which exists
+    for Circular -> CircularCircular).  Returns (type name, default-constructed factor) or None."""
+    if t1.circ_mask == 0 and t2.circ_mask == 0 and t1.dim == t2.dim and t1.name.startswith("Position"):
+        d = t1.dim
+        Z = G.Normal(0.0, 1.0) if d == 1 else G.MvNormal(np.zeros(d), np.eye(d))   # LinearRelative{N}() default
+        return "LinearRelative", G.LinearRelative(Z)
+    if t1.name == "Circular" and t2.name == "Circular":
+        return "CircularCircular", G.CircularCircular(G.Normal(0.0, 0.1))
+    return None
+
+
+def _shortest_path_factor_types(inst, src: str, dst: str, only_type: Optional[str] = None):
+    """findShortestPathDijkstra(dfg, from, to; typeFactors) on the bipartite variable/factor graph of a clique
+    sub-graph (DFG, un-vendored; unit edge weights => BFS, neighbours in insertion order): the factor type names
+    along the path, or None when the two variables are not connected."""
+    if src == dst:
+        return []
+    prev = {src: None}
+    frontier = [src]
+    while frontier:
+        nxt = []
+        for u in frontier:
+            for k, e in enumerate(inst):
+                if u not in e["variables"] or (only_type is not None and e["type"] != only_type):
+                    continue
+                for w in e["variables"]:
+                    if w not in prev:
+                        prev[w] = (u, k)
+                        nxt.append(w)
+        if dst in prev:
+            break
+        frontier = nxt
+    if dst not in prev:
+        return None
+    types, w = [], dst
+    while prev[w] is not None:
+        u, k = prev[w]
+        types.append(inst[k]["type"])
+        w = u
+    return types[::-1]
+
+
 def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, downsolve: bool = True,
-                  gibbsIters: Optional[int] = None, downIters: int = 3) -> SolvePlan:
-    """Lower one solveTree! (up + down pass, useMsgLikelihoods=false) to slots, props and waves."""
+                  gibbsIters: Optional[int] = None, downIters: int = 3,
+                  useMsgLikelihoods: Optional[bool] = None) -> SolvePlan:
+    """Lower one solveTree! (up + down pass) to slots, props and waves.
+
+    useMsgLikelihoods=false (SolverParams default): up messages are one MsgPrior per separator variable.
+    useMsgLikelihoods=true (test/fourdoortest.jl:19, testCircular.jl:12): a child sends the joint of
+    its separators as *differential* relative factors + at most one MsgPrior per connected class
+    (prepCliqueMsgUp -> _generateMsgJointRelativesPriors, TreeMessageUtils.jl:417-446); every differential is one
+    IIF_S_DECONV op (approxDeconv + manikde! on the device) whose belief slot is the measurement density of the
+    relative factor the parent adds; differentials stay in the sub-graph for the down solve, which then does not
+    merge extra graph factors (CliqueStateMachine.jl:825-834)."""
     sp = fg.solverParams
     N = N or sp.N
     iters = gibbsIters or sp.gibbsIters
+    uml = sp.useMsgLikelihoods if useMsgLikelihoods is None else bool(useMsgLikelihoods)
     T = CP.Tables()
     # global slots: the main graph's variables (VariableNodeData)
     var_slot = {l: T.add_slot(v.vartype, max(N, v.val.shape[0], 1)) for l, v in fg.variables.items()}
@@ -353,6 +408,9 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
             cslot[(c.id, v)] = T.add_slot(fg.variables[v].vartype, max(N, fg.variables[v].val.shape[0], 1))
 
     props, sched, reads, writes, opc = [], [], [], [], []
+    deconvs = []                     # IIF_S_DECONV specs (useMsgLikelihoods)
+    upmsg: Dict[int, dict] = {}      # child clique id -> joint up message (relatives, priors, hasPriors)
+    kept_diffs: Dict[int, list] = {}  # clique id -> differential factor instances kept for the down solve
     nconv = [0]
     cur = [-1]     # clique whose ops are being emitted
 
@@ -390,25 +448,46 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
         cur[0] = cid
         slot_of = lambda v, cid=cid: cslot[(cid, v)]  # noqa: E731
         # factors of the clique sub-graph: potentials + MsgPrior per child up-message belief
-        inst = []   # (variables, table idx, multihypo?, read slots)
+        inst = []   # factor instances of the clique sub-graph
         for fl in c.potentials:
             f = fg.factors[fl]
-            inst.append((f.variables, fac_instance(f, slot_of), G.isMultihypo(f), [slot_of(v) for v in f.variables]))
+            inst.append(dict(variables=f.variables, fi=fac_instance(f, slot_of), mh=G.isMultihypo(f),
+                             rd=[slot_of(v) for v in f.variables], type=type(f.fnc).__name__, prior=f.is_prior,
+                             tag="pot"))
+
+        def add_msg_prior(s, src):
+            mp = G.MsgPrior(G.SlotRef(src, fg.variables[s].vartype.dim))
+            inst.append(dict(variables=[s], fi=T.add_factor(mp, [slot_of(s)], None, 0.0, sp.inflation), mh=False,
+                             rd=[slot_of(s), src], type="MsgPrior", prior=True, tag="common"))
+
         for ch in c.children:
-            for s in tree.cliques[ch].separators:           # addMsgFactors! (TreeMessageUtils.jl:566-575)
-                if s in c.allvars:
-                    src = cslot[(ch, s)]                     # the child's updated separator belief
-                    mp = G.MsgPrior(G.SlotRef(src, fg.variables[s].vartype.dim))
-                    inst.append(([s], T.add_factor(mp, [slot_of(s)], None, 0.0, sp.inflation), False,
-                                 [slot_of(s), src]))
+            if not uml:
+                for s in tree.cliques[ch].separators:       # addMsgFactors! (TreeMessageUtils.jl:566-575)
+                    if s in c.allvars:
+                        add_msg_prior(s, cslot[(ch, s)])     # the child's updated separator belief
+                        n_msgs += 1
+                continue
+            msg = upmsg[ch]
+            # addLikelihoodsDifferential! (TreeMessageUtils.jl:225-233): the relatives of the joint message
+            for rel in msg["relatives"]:
+                fnc = type(rel["sft"])(G.SlotRef(rel["slot"], rel["zdim"]))            # _sft(newBel), :321
+                inst.append(dict(variables=list(rel["variables"]),
+                                 fi=T.add_factor(fnc, [slot_of(v) for v in rel["variables"]], None, 0.0, sp.inflation),
+                                 mh=False, rd=[slot_of(v) for v in rel["variables"]] + [rel["slot"]],
+                                 type=rel["type"], prior=False, tag="diff"))
+                n_msgs += 1
+            # addLikelihoodPriorCommon! (TreeMessageUtils.jl:454-469)
+            for lbl, src in msg["priors"]:
+                if msg["hasPriors"] or not any(lbl in e["variables"] for e in inst):
+                    add_msg_prior(lbl, src)
                     n_msgs += 1
 
         def propagate(v):
             fl, rd = [], []
-            for variables, fi, ismh, rds in inst:
-                if v in variables:
-                    fl.append((fi, variables.index(v) + 1, ismh))
-                    rd += rds
+            for e in inst:
+                if v in e["variables"]:
+                    fl.append((e["fi"], e["variables"].index(v) + 1, e["mh"]))
+                    rd += e["rd"]
             if fl:
                 add_prop(v, slot_of(v), fl[:A.IIF_MAX_FACTORS], rd)
 
@@ -427,6 +506,10 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
             fmcmc(c.itervarIDs, iters)
         if c.directPriorMsgIDs:
             fmcmc([v for v in c.directPriorMsgIDs if v not in c.msgskipIDs], 1)
+        if uml:
+            kept_diffs[cid] = [e for e in inst if e["tag"] == "diff"]       # only UPWARD_COMMON is deleted (CSM :559-563)
+            if c.parent is not None:
+                upmsg[cid] = _joint_up_message(fg, c, inst, slot_of, T, N, deconvs, sched, reads, writes, opc, cur)
     n_up_ops = len(sched)
 
     # ---- down pass (parents before children); the root keeps its up-solve result
@@ -448,10 +531,21 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
                 return cslot[(cid, v)] if v in c.allvars else var_slot[v]
 
             inst = []
-            for f in fg.factors.values():
-                if any(v in c.frontals for v in f.variables):
+            if uml:
+                # the clique sub-graph as the up solve left it: potentials + the children's differentials; no
+                # addDownVariableFactors! (CliqueStateMachine.jl:825-834).  The DOWNWARD_COMMON MsgPriors sit on
+                # separators only and never enter a frontal's product.
+                for fl in c.potentials:
+                    f = fg.factors[fl]
                     inst.append((f.variables, fac_instance(f, slot_dn), G.isMultihypo(f),
                                  [slot_dn(v) for v in f.variables]))
+                for e in kept_diffs.get(cid, []):
+                    inst.append((e["variables"], e["fi"], False, e["rd"]))
+            else:
+                for f in fg.factors.values():
+                    if any(v in c.frontals for v in f.variables):
+                        inst.append((f.variables, fac_instance(f, slot_dn), G.isMultihypo(f),
+                                     [slot_dn(v) for v in f.variables]))
 
             def local_product(v):
                 fl, rd = [], []
@@ -494,4 +588,73 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
     frozen = T.freeze()
     return SolvePlan(T, frozen, props, sched, wave_off, sched_waved, var_slot, nconv[0], len(props), n_msgs,
                      up_last, [opc[i] for i in order], [waves[i] for i in order], [reads[i] for i in order],
-                     [writes[i] for i in order], {s: cid for (cid, _), s in cslot.items()})
+                     [writes[i] for i in order], {s: cid for (cid, _), s in cslot.items()}, deconvs)
+
+
+def _joint_up_message(fg, c: TreeClique, inst, slot_of, T, N, deconvs, sched, reads, writes, opc, cur):
+    """prepCliqueMsgUp with useMsgLikelihoods (TreeMessageUtils.jl:667-703) ->
+    _generateMsgJointRelativesPriors (:417-446): differentials between separator pairs
+    (addLikelihoodsDifferentialCHILD!, :279-335), connected classes (_findSubgraphsFactorType, :118-205) and one
+    candidate MsgPrior per class (_generateSubgraphMsgPriors / _calcCandidatePriorBest, :339-412).
+
+    Each differential becomes one IIF_S_DECONV schedule op writing a fresh measurement slot."""
+    seps = list(c.separators)
+    dims = [fg.variables[s].vartype.dim for s in seps]
+    dec = [seps[i] for i in sorted(range(len(seps)), key=lambda i: -dims[i])]      # sortperm(listDims; rev=true), stable
+    acc = dec[::-1]
+    relatives, already = [], []
+    for s1 in dec:
+        already.append(s1)
+        for s2 in [v for v in acc if v not in already]:
+            types = _shortest_path_factor_types(inst, s1, s2)                       # isPathFactorsHomogeneous (DFG)
+            if not types or len(set(types)) != 1:
+                continue
+            sel = selectFactorType(fg.variables[s1].vartype, fg.variables[s2].vartype)
+            if sel is None or sel[0] != types[0]:
+                continue
+            name, sft = sel
+            vt = fg.variables[s1].vartype
+            mslot = T.add_slot(vt, N)                                               # newBel = manikde!(sft, pts)
+            dummy = T.add_factor(sft, [slot_of(s1), slot_of(s2)], None, 0.0, 5.0)   # tfg dummy factor, :314
+            deconvs.append(dict(factor=dummy, out_slot=mslot, N=N, call_id=(1 << 24) + 16 * len(deconvs)))
+            sched.append((A.S_DECONV, len(deconvs) - 1, 0))
+            reads.append(sorted({slot_of(s1), slot_of(s2)}))
+            writes.append([mslot])
+            opc.append(cur[0])
+            relatives.append(dict(variables=[s1, s2], type=name, sft=sft, slot=mslot, zdim=vt.dim))
+    # _findSubgraphsFactorType: classes of separators connected through the default relative type
+    count = {s: 0 for s in seps}
+    for r in relatives:
+        for v in r["variables"]:
+            count[v] += 1
+    cls: Dict[str, int] = {}
+    ncls = 0
+    for s in seps:
+        if count[s] == 0:
+            ncls += 1
+            cls[s] = ncls
+    for k1 in [s for s in seps if s not in cls]:
+        if k1 not in cls:
+            ncls += 1
+            cls[k1] = ncls
+        for k2 in [s for s in seps if s not in cls]:
+            sel = selectFactorType(fg.variables[k1].vartype, fg.variables[k2].vartype)
+            pth = _shortest_path_factor_types(inst, k1, k2, sel[0]) if sel is not None else None
+            if not pth:
+                ncls += 1
+                cls[k2] = ncls
+            else:
+                cls[k2] = cls[k1]
+    classes: Dict[int, List[str]] = {}
+    for s in seps:
+        classes.setdefault(cls[s], []).append(s)
+    pot_has_prior = any(e["prior"] for e in inst if e["tag"] == "pot")              # :431
+    priors = []
+    for syms in classes.values():
+        if len(syms) == 1 or pot_has_prior:                                         # :402-408
+            md = max(fg.variables[v].vartype.dim for v in syms)
+            cand = [v for v in syms if fg.variables[v].vartype.dim == md]
+            adj = [sum(1 for e in inst if v in e["variables"]) for v in cand]
+            best = cand[max(range(len(cand)), key=lambda i: (adj[i], -i))]          # sortperm(mdAdj; rev=true)[1]
+            priors.append((best, slot_of(best)))
+    return dict(relatives=relatives, priors=priors, hasPriors=any(e["prior"] for e in inst))   # :681

@@ -1091,10 +1091,47 @@ int32_t iifo_propagate(iifo_graph* g, const iif_prop_op* op) {
   return st;
 }
 
+/* IIF_S_DECONV — addLikelihoodsDifferentialCHILD! (src/services/TreeMessageUtils.jl:314-321):
+ *   pred_X, = approxDeconv(tfg, afc.label); pts = exp.(M, e0, pred_X); newBel = manikde!(sft, pts)
+ * the belief lands in `out_slot` (a measurement density the parent's relative factor samples from). */
+int32_t iifo_deconv_to_slot(iifo_graph* g, const iif_deconv_op* op) {
+  if (op->factor < 0 || op->factor >= g->nfactors || op->out_slot < 0 || op->out_slot >= g->nslots) return IIF_ERR_ARG;
+  const iif_factor_desc* f = &g->factors[op->factor];
+  const iif_slot_desc* O = &g->slots[op->out_slot];
+  const int N = op->N, d = O->dim;
+  if (f->nmh != 0 || f->arity != 2 || f->zdim != d || O->cap < N) return IIF_ERR_UNSUPPORTED;
+  double* pred = (double*)malloc(sizeof(double) * 2 * (size_t)N * d);
+  double* meas = pred + (size_t)N * d;
+  int32_t st = iifo_deconv(g, op->factor, N, op->call_id, pred, meas);
+  if (st != IIF_OK) { free(pred); return st; }
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < d; ++c) {
+      double v = pred[n * d + c];
+      g->pts[O->pts_off + n * d + c] = is_circ(O->circ_mask, c) ? wrap_pi(v) : v;   /* exp(M, eps, X) */
+    }
+  free(pred);
+  double bw[IIF_MAX_DIM] = {0, 0, 0, 0};
+  st = iifo_kde_bandwidth(g->pts + O->pts_off, N, d, O->circ_mask, bw);
+  if (st != IIF_OK) return st;
+  for (int c = 0; c < IIF_MAX_DIM; ++c) {
+    g->bw[op->out_slot * IIF_MAX_DIM + c] = c < d ? bw[c] : 0.0;
+    g->ipc[op->out_slot * IIF_MAX_DIM + c] = c < d ? 1.0 : 0.0;
+  }
+  g->npts[op->out_slot] = N;
+  g->flags[op->out_slot] |= 1;
+  return IIF_OK;
+}
+
 /* a16: clique Gibbs sweeps expressed as a wave schedule (fmcmc! SolveTree.jl:89-142 etc.) */
 int32_t iifo_schedule_run(iifo_graph* g, int32_t nwaves, const int32_t* wave_off,
                           const iif_sched_op* ops, const iif_prop_op* props, int32_t first_wave,
                           int32_t last_wave) {
+  return iifo_schedule_run_ex(g, nwaves, wave_off, ops, props, NULL, first_wave, last_wave);
+}
+
+int32_t iifo_schedule_run_ex(iifo_graph* g, int32_t nwaves, const int32_t* wave_off,
+                             const iif_sched_op* ops, const iif_prop_op* props, const iif_deconv_op* deconvs,
+                             int32_t first_wave, int32_t last_wave) {
   if (first_wave < 0) first_wave = 0;
   if (last_wave > nwaves) last_wave = nwaves;
   for (int w = first_wave; w < last_wave; ++w) {
@@ -1119,6 +1156,8 @@ int32_t iifo_schedule_run(iifo_graph* g, int32_t nwaves, const int32_t* wave_off
           g->npts[o->b] = g->npts[o->a];
           g->flags[o->b] = g->flags[o->a];
         }
+      } else if (o->kind == IIF_S_DECONV && deconvs) {
+        st = iifo_deconv_to_slot(g, &deconvs[o->a]);
       } else st = IIF_ERR_ARG;
       if (st != IIF_OK) {
 #pragma omp critical

@@ -120,6 +120,11 @@ int32_t iifo_propagate(iifo_graph* g, const iif_prop_op* op);
 int32_t iifo_schedule_run(iifo_graph* g, int32_t nwaves, const int32_t* wave_off,
                           const iif_sched_op* ops, const iif_prop_op* props, int32_t first_wave,
                           int32_t last_wave);
+int32_t iifo_schedule_run_ex(iifo_graph* g, int32_t nwaves, const int32_t* wave_off,
+                             const iif_sched_op* ops, const iif_prop_op* props, const iif_deconv_op* deconvs,
+                             int32_t first_wave, int32_t last_wave);
+/* IIF_S_DECONV: differential likelihood of an up message (TreeMessageUtils.jl:314-321) into a belief slot */
+int32_t iifo_deconv_to_slot(iifo_graph* g, const iif_deconv_op* op);
 
 /* counters for the CPU baseline */
 int64_t iifo_conv_count(void);

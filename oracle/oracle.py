@@ -79,6 +79,11 @@ def lib():
         L.iifo_schedule_run.restype = C.c_int32
         L.iifo_schedule_run.argtypes = [C.POINTER(OracleGraph), C.c_int32, ip, C.POINTER(A.SchedOp),
                                         C.POINTER(A.PropOp), C.c_int32, C.c_int32]
+        L.iifo_schedule_run_ex.restype = C.c_int32
+        L.iifo_schedule_run_ex.argtypes = [C.POINTER(OracleGraph), C.c_int32, ip, C.POINTER(A.SchedOp),
+                                           C.POINTER(A.PropOp), C.POINTER(A.DeconvOp), C.c_int32, C.c_int32]
+        L.iifo_deconv_to_slot.restype = C.c_int32
+        L.iifo_deconv_to_slot.argtypes = [C.POINTER(OracleGraph), C.POINTER(A.DeconvOp)]
         L.iifo_conv_count.restype = C.c_int64
         _lib = L
     return _lib
@@ -138,11 +143,15 @@ class Oracle:
     def propagate(self, op):
         _check(lib().iifo_propagate(C.byref(self.g), C.byref(op)), "propagate")
 
-    def schedule_run(self, wave_off, ops, props, first=0, last=None):
+    def schedule_run(self, wave_off, ops, props, first=0, last=None, deconvs=None):
         nw = len(wave_off) - 1
         wo = np.asarray(wave_off, dtype=np.int32)
-        _check(lib().iifo_schedule_run(C.byref(self.g), nw, _ip(wo), ops, props, first,
-                                       nw if last is None else last), "schedule_run")
+        _check(lib().iifo_schedule_run_ex(C.byref(self.g), nw, _ip(wo), ops, props, deconvs, first,
+                                          nw if last is None else last), "schedule_run")
+
+    def deconv_to_slot(self, op):
+        """IIF_S_DECONV: differential likelihood of an up message into a belief slot"""
+        _check(lib().iifo_deconv_to_slot(C.byref(self.g), C.byref(op)), "deconv_to_slot")
 
 
 def uniform(seed, call, stream, idx):
