@@ -60,6 +60,9 @@ def nested_dissection_order(fg: G.FactorGraph) -> List[str]:
             for b in f.variables:
                 if a != b:
                     adj[a].add(b)
+    # neighbour lists in variable order: set iteration order depends on the process' string-hash seed and would make
+    # the elimination order (hence the tree and the plan) differ from run to run
+    adj = {l: sorted(ns, key=lambda x: fg.variables[x].index) for l, ns in adj.items()}
     order: List[str] = []
 
     def bfs_far(nodes, start):

@@ -289,3 +289,60 @@ def test_se2_solveTree_testSpecialEuclidean2Mani(built):
     G.addFactor(fg, ["x0"], G.PartialPrior(G.MvNormal([0.01, 0.01], np.eye(2) * 1e-4), (1, 2)))
     pbel = SV.approxConvBelief(fg, "x0f1", "x0")
     assert pbel.partial == [1, 2] and len(pbel.infoPerCoord) == 3
+
+
+def _solve_twice(ts, fg, seed):
+    from iifb200 import compile as CP
+    out = []
+    for _ in range(2):
+        ts.eng.set_solver_params(CP.solver_params_c(fg.solverParams, seed))
+        ts.load_from_graph()
+        ts.upload()
+        ts.run()
+        ts.download()
+        out.append({l: ts.arena.get(ts.plan.var_slot[l]) for l in fg.variables})
+    return out
+
+
+def test_c4_full_size_circular_chain_properties(built):
+    """BASELINE configs[3] at FULL size on one GPU (500 Circular poses, N=150, testCircular.jl:14-16 scaled):
+    every belief complete, in [-pi, pi), located at rem2pi(k) within the accumulated odometry noise (prior 0.1,
+    0.1 rad per step), bandwidths positive, deterministic replay."""
+    n = 500
+    fg = W.circular_chain(n=n, N=150, seed=42)
+    ts = SV.TreeSolver(fg, W.chain_nd_order(n))
+    assert 9 * n < ts.plan.n_conv < 13 * n
+    a, b = _solve_twice(ts, fg, 11)
+    for k in range(n):
+        p, bw, ipc = a[f"x{k}"]
+        assert p.shape == (150, 1) and np.isfinite(p).all() and (-np.pi <= p).all() and (p < np.pi).all() and bw[0] > 0
+        assert np.array_equal(p, b[f"x{k}"][0])
+        mu = np.arctan2(np.sin(p).mean(), np.cos(p).mean())
+        err = abs((mu - k + np.pi) % (2 * np.pi) - np.pi)
+        assert err < 0.15 + 0.1 * np.sqrt(k + 1.0), (k, mu, err)
+    ts.close()
+
+
+def test_c5_full_size_grid_properties(built):
+    """BASELINE configs[4] at FULL size on one GPU (5000 Position{2} poses on a 50 x 100 boustrophedon grid with
+    loop closures every 5th column, N=100, nested-dissection order: ~4200 cliques, separators up to ~100
+    variables, ~79 k convolutions): beliefs complete and finite, every pose located on its grid node (mean error
+    < 0.4 on average, < 2.5 anywhere - the loop closures bound the drift), deterministic replay."""
+    rows, cols = 50, 100
+    fg = W.euclid2_grid(rows=rows, cols=cols, N=100, seed=42, closure_every=5)
+    ts = SV.TreeSolver(fg, TR.getEliminationOrder(fg, "nd"))
+    assert ts.plan.n_conv > 10 * rows * cols and max(len(c.separators) for c in ts.tree.cliques) >= 50
+    a, b = _solve_twice(ts, fg, 5)
+    pos = []
+    for r in range(rows):
+        for c in (range(cols) if r % 2 == 0 else range(cols - 1, -1, -1)):
+            pos.append((float(c), float(r)))
+    pos = np.array(pos)
+    mean = np.stack([a[f"x{k}"][0].mean(axis=0) for k in range(rows * cols)])
+    for k in range(rows * cols):
+        p, bw, _ = a[f"x{k}"]
+        assert p.shape == (100, 2) and np.isfinite(p).all() and (bw > 0).all()
+    assert all(np.array_equal(a[l][0], b[l][0]) for l in fg.variables)
+    err = np.abs(mean - pos).max(axis=1)
+    assert err.mean() < 0.4 and err.max() < 2.5, (float(err.mean()), float(err.max()))
+    ts.close()
