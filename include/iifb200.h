@@ -288,7 +288,10 @@ typedef struct {
   int32_t kind; /* iif_sched_kind */
   int32_t a;    /* PROPAGATE: index into props;  COPY: source slot;  DECONV: index into deconvs */
   int32_t b;    /* COPY: destination slot */
-  int32_t _pad;
+  int32_t lane; /* 0: no lane (a wave holding such an op is a barrier).  1..8: independent sub-tree ("lane") the op
+                   belongs to.  Ops of different lanes never touch a common slot unless a barrier wave lies between
+                   them (the caller guarantees it); inside the captured CUDA graph every lane is its own branch, so a
+                   lane's next wave starts as soon as ITS previous wave has drained. */
 } iif_sched_op;
 int32_t iifb200_schedule_build(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off,
                                int32_t nops, const iif_sched_op* ops, int32_t nprops,

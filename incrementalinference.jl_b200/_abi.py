@@ -70,7 +70,7 @@ class DeconvOp(C.Structure):
 
 
 class SchedOp(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("lane", C.c_int32)]
 
 
 P = C.POINTER

@@ -185,9 +185,10 @@ def make_deconv_ops(specs):
     return ops
 
 
-def make_sched_ops(ops_list):
-    """ops_list: list of (kind, a, b)."""
+def make_sched_ops(ops_list, lanes=None):
+    """ops_list: list of (kind, a, b); lanes: optional lane id per op (0 = none / barrier)."""
     ops = (A.SchedOp * max(len(ops_list), 1))()
     for i, (k, a, b) in enumerate(ops_list):
         ops[i].kind, ops[i].a, ops[i].b = k, a, b
+        ops[i].lane = 0 if lanes is None else int(lanes[i])
     return ops

@@ -26,8 +26,18 @@ struct TreeHost {
   int16_t* d_blob = nullptr;
 };
 
-struct Wave {
+#define IIF_MAX_LANES 8
+// One wave = the independent ops of one dependency level.  A wave whose ops all carry a lane id (iif_sched_op.lane
+// != 0) is split into per-lane segments that are launched on per-lane streams inside the captured CUDA graph: lanes
+// are independent sub-trees, so one lane's kernels need not wait for another lane's wave to drain.  A wave that holds
+// any lane-0 op is a full barrier (one segment, main stream).
+struct Seg {
+  int lane = 0;
   int conv0 = 0, nconv = 0, prod0 = 0, nprod = 0, copy0 = 0, ncopy = 0, dcv0 = 0, ndcv = 0;
+};
+struct Wave {
+  std::vector<Seg> segs;
+  int nconv = 0, nprod = 0, ncopy = 0, ndcv = 0;  // wave totals: CTA size / cluster choice follow the whole wave's width
   size_t prod_smem = 0, conv_smem = 0, dcv_smem = 0;
   int dcv_maxN = 2;
   int maxN = 2;
@@ -44,12 +54,14 @@ struct Schedule {
   int nconv = 0, nprod = 0, ndcv = 0;
   int nstatus() const { return nconv + nprod + ndcv; }
   std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int>> graphs;  // (exec, kernel nodes)
+  std::vector<cudaEvent_t> events;  // fork / join events of the captured graphs
 };
 
 struct iifb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t lane_stream[IIF_MAX_LANES + 1] = {};  // created on first use (schedules with lanes)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   std::string err;
@@ -226,6 +238,7 @@ int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
 static void free_schedule(Schedule* s) {
   if (!s) return;
   for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second.first);
+  for (auto e : s->events) cudaEventDestroy(e);
   cudaFree(s->d_conv); cudaFree(s->d_prod); cudaFree(s->d_copy); cudaFree(s->d_dcv); cudaFree(s->d_scratch); cudaFree(s->d_status);
   delete s;
 }
@@ -252,6 +265,7 @@ void iifb200_free(iifb200_ctx* ctx) {
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->own_stream);
+  for (auto st : ctx->lane_stream) if (st) cudaStreamDestroy(st);
   delete ctx;
 }
 
@@ -878,10 +892,25 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
   std::vector<char> used(nprops, 0);
   for (int w = 0; w < nwaves; ++w) {
     Wave W;
-    W.conv0 = (int)ct.size(); W.prod0 = (int)pt.size(); W.copy0 = (int)cp.size() / 2; W.dcv0 = (int)dt.size();
     if (wave_off[w] < 0 || wave_off[w + 1] > nops || wave_off[w] > wave_off[w + 1]) return fail(ctx, IIF_ERR_ARG, "schedule: bad wave offsets");
+    // lanes present in this wave; any lane-0 op makes the wave a barrier (single segment)
+    std::vector<int> lanes;
+    bool barrier = false;
+    for (int k = wave_off[w]; k < wave_off[w + 1]; ++k) {
+      const int ln = ops[k].lane;
+      if (ln < 0 || ln > IIF_MAX_LANES) return fail(ctx, IIF_ERR_ARG, "schedule: lane out of range");
+      if (ln == 0) barrier = true;
+      if (std::find(lanes.begin(), lanes.end(), ln) == lanes.end()) lanes.push_back(ln);
+    }
+    if (barrier || lanes.empty()) lanes.assign(1, 0);
+    std::sort(lanes.begin(), lanes.end());
+   for (size_t li = 0; li < lanes.size(); ++li) {
+    Seg G;
+    G.lane = lanes[li];
+    G.conv0 = (int)ct.size(); G.prod0 = (int)pt.size(); G.copy0 = (int)cp.size() / 2; G.dcv0 = (int)dt.size();
     for (int k = wave_off[w]; k < wave_off[w + 1]; ++k) {
       const iif_sched_op& o = ops[k];
+      if (!barrier && o.lane != G.lane) continue;
       if (o.kind == IIF_S_COPY) {
         if (o.a < 0 || o.a >= (int)ctx->slots.size() || o.b < 0 || o.b >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "schedule: copy slot out of range");
         if (ctx->slots[o.a].dim != ctx->slots[o.b].dim || ctx->slots[o.b].cap < ctx->slots[o.a].cap) return fail(ctx, IIF_ERR_ARG, "schedule: copy slots incompatible");
@@ -939,8 +968,11 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
         W.prod_smem = std::max(W.prod_smem, prod_smem_bytes(P.nfactors, P.N, S.dim, ctx->trees[P.N].nn, ctx->trees[P.N].L));
       } else return fail(ctx, IIF_ERR_ARG, "schedule: unknown op kind");
     }
-    W.nconv = (int)ct.size() - W.conv0; W.nprod = (int)pt.size() - W.prod0; W.ncopy = (int)cp.size() / 2 - W.copy0;
-    W.ndcv = (int)dt.size() - W.dcv0;
+    G.nconv = (int)ct.size() - G.conv0; G.nprod = (int)pt.size() - G.prod0; G.ncopy = (int)cp.size() / 2 - G.copy0;
+    G.ndcv = (int)dt.size() - G.dcv0;
+    W.nconv += G.nconv; W.nprod += G.nprod; W.ncopy += G.ncopy; W.ndcv += G.ndcv;
+    W.segs.push_back(G);
+   }
     if ((int)W.prod_smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "schedule: product exceeds the shared-memory budget");
     s->waves.push_back(W);
   }
@@ -977,28 +1009,71 @@ int32_t iifb200_schedule_build_ex(iifb200_ctx* ctx, int32_t nwaves, const int32_
   return IIF_OK;
 }
 
-// enqueue waves [w0, w1) on the ctx stream; returns the number of kernels launched
-static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int* nk) {
+// launches of one segment of a wave on stream `st`; CTA size and cluster choice follow the whole wave's width
+static int enqueue_seg(iifb200_ctx* ctx, Schedule* s, const Wave& W, const Seg& G, cudaStream_t st) {
   int k = 0;
+  if (G.ncopy) {
+    iif_copy_kernel<<<G.ncopy, 128, 0, st>>>(ctx->dg, s->d_copy + 2 * G.copy0, G.ncopy);
+    ++k;
+  }
+  if (G.ndcv) {
+    launch_k(iif_deconv_slot_kernel, G.ndcv, pick_cluster(ctx, W.ndcv), pick_threads(ctx, W.ndcv, W.dcv_maxN), W.dcv_smem, st, ctx->dg, s->d_dcv + G.dcv0, ctx->d_trees);
+    ++k;
+  }
+  if (G.nconv) {
+    launch_k(iif_conv_kernel, G.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, st, ctx->dg, s->d_conv + G.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+    ++k;
+  }
+  if (G.nprod) {
+    launch_k(iif_product_kernel, G.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, st, ctx->dg, s->d_prod + G.prod0, nullptr, nullptr, ctx->d_trees);
+    ++k;
+  }
+  return k;
+}
+
+// enqueue waves [w0, w1); returns the number of kernels launched.  `lanes` (only inside a stream capture): lane
+// segments go to per-lane streams forked from / joined into the ctx stream with events, so the captured graph
+// carries the lanes as parallel branches.  Without `lanes` everything is issued on the ctx stream in wave order.
+static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int* nk, bool lanes) {
+  int k = 0;
+  bool active[IIF_MAX_LANES + 1] = {};
+  auto new_event = [&](cudaEvent_t* e) {
+    cudaError_t err = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    if (err == cudaSuccess) s->events.push_back(*e);
+    return err;
+  };
+  auto join_all = [&]() -> cudaError_t {
+    for (int l = 1; l <= IIF_MAX_LANES; ++l) {
+      if (!active[l]) continue;
+      cudaEvent_t e;
+      cudaError_t err = new_event(&e);
+      if (err == cudaSuccess) err = cudaEventRecord(e, ctx->lane_stream[l]);
+      if (err == cudaSuccess) err = cudaStreamWaitEvent(ctx->stream, e, 0);
+      if (err != cudaSuccess) return err;
+      active[l] = false;
+    }
+    return cudaSuccess;
+  };
   for (int w = w0; w < w1; ++w) {
     const Wave& W = s->waves[w];
-    if (W.ncopy) {
-      iif_copy_kernel<<<W.ncopy, 128, 0, ctx->stream>>>(ctx->dg, s->d_copy + 2 * W.copy0, W.ncopy);
-      ++k;
-    }
-    if (W.ndcv) {
-      launch_k(iif_deconv_slot_kernel, W.ndcv, pick_cluster(ctx, W.ndcv), pick_threads(ctx, W.ndcv, W.dcv_maxN), W.dcv_smem, ctx->stream, ctx->dg, s->d_dcv + W.dcv0, ctx->d_trees);
-      ++k;
-    }
-    if (W.nconv) {
-      launch_k(iif_conv_kernel, W.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream, ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
-      ++k;
-    }
-    if (W.nprod) {
-      launch_k(iif_product_kernel, W.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream, ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
-      ++k;
+    for (const Seg& G : W.segs) {
+      if (!lanes || G.lane == 0) {
+        if (lanes) CK(join_all());
+        k += enqueue_seg(ctx, s, W, G, ctx->stream);
+        continue;
+      }
+      if (!ctx->lane_stream[G.lane]) CK(cudaStreamCreateWithFlags(&ctx->lane_stream[G.lane], cudaStreamNonBlocking));
+      if (!active[G.lane]) {  // fork: the lane continues from the ctx stream's current point
+        cudaEvent_t e;
+        CK(new_event(&e));
+        CK(cudaEventRecord(e, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->lane_stream[G.lane], e, 0));
+        active[G.lane] = true;
+      }
+      k += enqueue_seg(ctx, s, W, G, ctx->lane_stream[G.lane]);
     }
   }
+  if (lanes) CK(join_all());
   CK(cudaGetLastError());
   *nk = k;
   return IIF_OK;
@@ -1019,7 +1094,7 @@ int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t firs
     cudaGraph_t graph = nullptr;
     int nk = 0;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    int32_t st = enqueue_waves(ctx, s, first_wave, last_wave, &nk);
+    int32_t st = enqueue_waves(ctx, s, first_wave, last_wave, &nk, true);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (st != IIF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
     if (e != cudaSuccess) return fail(ctx, IIF_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
@@ -1055,22 +1130,22 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
     const Wave& W = s->waves[w];
     if (W.ncopy) {
       mark();
-      iif_copy_kernel<<<W.ncopy, 128, 0, ctx->stream>>>(ctx->dg, s->d_copy + 2 * W.copy0, W.ncopy);
+      iif_copy_kernel<<<W.ncopy, 128, 0, ctx->stream>>>(ctx->dg, s->d_copy + 2 * W.segs[0].copy0, W.ncopy);
       mark(); kind.push_back(2); blocks[2] += W.ncopy;
     }
     if (W.ndcv) {  // differential-likelihood construction is accounted with the copy (message) kernels
       mark();
-      launch_k(iif_deconv_slot_kernel, W.ndcv, pick_cluster(ctx, W.ndcv), pick_threads(ctx, W.ndcv, W.dcv_maxN), W.dcv_smem, ctx->stream, ctx->dg, s->d_dcv + W.dcv0, ctx->d_trees);
+      launch_k(iif_deconv_slot_kernel, W.ndcv, pick_cluster(ctx, W.ndcv), pick_threads(ctx, W.ndcv, W.dcv_maxN), W.dcv_smem, ctx->stream, ctx->dg, s->d_dcv + W.segs[0].dcv0, ctx->d_trees);
       mark(); kind.push_back(2); blocks[2] += W.ndcv;
     }
     if (W.nconv) {
       mark();
-      launch_k(iif_conv_kernel, W.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream, ctx->dg, s->d_conv + W.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      launch_k(iif_conv_kernel, W.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream, ctx->dg, s->d_conv + W.segs[0].conv0, nullptr, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(0); blocks[0] += W.nconv;
     }
     if (W.nprod) {
       mark();
-      launch_k(iif_product_kernel, W.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream, ctx->dg, s->d_prod + W.prod0, nullptr, nullptr, ctx->d_trees);
+      launch_k(iif_product_kernel, W.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream, ctx->dg, s->d_prod + W.segs[0].prod0, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(1); blocks[1] += W.nprod;
     }
   }
@@ -1103,14 +1178,14 @@ int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* 
   if (V < 1 || !ops) return fail(ctx, IIF_ERR_ARG, "propagate_batch: bad arguments");
   CK(cudaSetDevice(ctx->device));
   std::vector<iif_sched_op> so(V);
-  for (int v = 0; v < V; ++v) { so[v].kind = IIF_S_PROPAGATE; so[v].a = v; so[v].b = 0; so[v]._pad = 0; }
+  for (int v = 0; v < V; ++v) { so[v].kind = IIF_S_PROPAGATE; so[v].a = v; so[v].b = 0; so[v].lane = 0; }
   int32_t wo[2] = {0, V};
   Schedule* s = nullptr;
   int32_t st = build_schedule(ctx, 1, wo, V, so.data(), V, ops, 0, nullptr, &s);
   if (st != IIF_OK) { free_schedule(s); return st; }
   int nk = 0;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  st = enqueue_waves(ctx, s, 0, 1, &nk);
+  st = enqueue_waves(ctx, s, 0, 1, &nk, false);
   if (st == IIF_OK) {
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->timed = true;

@@ -8,6 +8,7 @@ Names, argument meaning and error behaviour follow the reference (`!` dropped):
   solveTree / solveGraph          src/services/SolverAPI.jl:326-446
 Every numeric step is a kernel launch in libiifb200.so (Engine); nothing here computes beliefs.
 """
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -312,16 +313,18 @@ class TreeSolver:
     """Compiled solveTree!: one device arena with clique-local slots + one CUDA-graph schedule."""
 
     def __init__(self, fg: G.FactorGraph, eliminationOrder: Optional[Sequence[str]] = None, ordering: str = "qr",
-                 device: int = 0, ext_arena_ptr=None, downsolve: Optional[bool] = None):
+                 device: int = 0, ext_arena_ptr=None, downsolve: Optional[bool] = None, lanes: Optional[int] = None):
         self.fg = fg
         order = list(eliminationOrder) if eliminationOrder is not None else TR.getEliminationOrder(fg, ordering)
         self.tree = TR.buildTree(fg, order)
         ds = fg.solverParams.downsolve if downsolve is None else downsolve
-        self.plan = TR.compile_solve(fg, self.tree, downsolve=ds)
+        # independent sub-trees become parallel branches ("lanes") of the captured CUDA graph (tree.assign_lanes)
+        lanes = int(os.environ.get("IIFB200_LANES", "4")) if lanes is None else lanes
+        self.plan = TR.compile_solve(fg, self.tree, downsolve=ds, lanes=lanes)
         self.sp_c = CP.solver_params_c(fg.solverParams)
         self.eng = Engine(self.plan.frozen, self.sp_c, device, ext_arena_ptr)
         self.props_c = CP.make_prop_ops(self.plan.props)
-        self.sched_c = CP.make_sched_ops(self.plan.sched_waved)
+        self.sched_c = CP.make_sched_ops(self.plan.sched_waved, self.plan.op_lane)
         self.deconvs_c = CP.make_deconv_ops(self.plan.deconvs or [])
         self.sid = self.eng.schedule_build(self.plan.wave_off, self.sched_c, len(self.plan.sched_waved),
                                            self.props_c, len(self.plan.props), self.deconvs_c,

@@ -316,6 +316,7 @@ class SolvePlan:
     op_writes: Optional[List[List[int]]] = None
     slot_clique: Optional[Dict[int, int]] = None  # clique-local slot -> clique id (main-graph slots absent)
     deconvs: Optional[list] = None    # IIF_S_DECONV specs (useMsgLikelihoods=true): factor, out_slot, N, call_id
+    op_lane: Optional[List[int]] = None   # lane of every op of `sched_waved` (0 = none), see assign_lanes
 
 
 def _levelize(ops, reads, writes):
@@ -385,9 +386,92 @@ def _shortest_path_factor_types(inst, src: str, dst: str, only_type: Optional[st
     return types[::-1]
 
 
+def assign_lanes(tree: BayesTree, op_clique, op_weight, waves, reads, writes, nlanes: int) -> List[int]:
+    """Lane (1..nlanes) of every op, 0 = none.  Lanes are groups of disjoint sub-trees of the Bayes tree: cliques in
+    disjoint sub-trees are independent until their common ancestor (CliqueStateMachine.jl:221-234 waits only on own
+    children), so the device may run one lane's next wave while another lane's wave is still draining.  The top of the
+    tree (the "cap") stays lane 0; a wave that holds a lane-0 op is a barrier.
+
+    1. split the heaviest sub-tree at its root until there are ~2*nlanes sub-trees, pack them into lanes (LPT);
+    2. hazard check on the slots: an op that conflicts (RAW / WAR / WAW) with an earlier op of a DIFFERENT lane with no
+       barrier wave in between is demoted to lane 0 (e.g. the write-back copies into the main graph)."""
+    n = len(op_clique)
+    if nlanes < 2 or n == 0:
+        return [0] * n
+    cl = tree.cliques
+    w_cl = [0.0] * len(cl)
+    for i in range(n):
+        if op_clique[i] >= 0:
+            w_cl[op_clique[i]] += op_weight[i]
+    sub = list(w_cl)                                     # sub-tree weights (children are created after parents)
+    for c in reversed(cl):
+        if c.parent is not None:
+            sub[c.parent] += sub[c.id]
+    frontier = list(tree.roots)
+    cap = set()
+    while len(frontier) < 2 * nlanes:
+        cand = [c for c in frontier if cl[c].children]
+        if not cand:
+            break
+        big = max(cand, key=lambda c: sub[c])
+        frontier.remove(big)
+        cap.add(big)
+        frontier += cl[big].children
+    load = [0.0] * (nlanes + 1)
+    lane_of_clique = [0] * len(cl)
+    for r in sorted(frontier, key=lambda c: -sub[c]):
+        ln = min(range(1, nlanes + 1), key=lambda k: load[k])
+        load[ln] += sub[r]
+        stack = [r]
+        while stack:
+            c = stack.pop()
+            lane_of_clique[c] = ln
+            stack += cl[c].children
+    lane = [lane_of_clique[op_clique[i]] if op_clique[i] >= 0 else 0 for i in range(n)]
+    # hazard check in wave order; barrier waves (any lane-0 op) separate everything before from everything after
+    order = sorted(range(n), key=lambda i: (waves[i], i))
+    for _ in range(n):                                   # demotions create new barrier waves: iterate to a fixed point
+        barrier = sorted({waves[i] for i in range(n) if lane[i] == 0})
+        import bisect
+
+        def separated(wa, wb):                          # a barrier wave in (wa, wb], or wa itself a barrier
+            k = bisect.bisect_left(barrier, wa)
+            return k < len(barrier) and barrier[k] <= wb
+        last_w: Dict[int, tuple] = {}
+        last_r: Dict[int, list] = {}
+        changed = False
+        for i in order:
+            li, wi = lane[i], waves[i]
+            conflict = False
+            if li != 0:
+                for s_ in reads[i]:
+                    a = last_w.get(s_)
+                    if a and a[0] != li and a[0] != 0 and not separated(a[1], wi):
+                        conflict = True
+                for s_ in writes[i]:
+                    a = last_w.get(s_)
+                    if a and a[0] != li and a[0] != 0 and not separated(a[1], wi):
+                        conflict = True
+                    for (lr, wr) in last_r.get(s_, []):
+                        if lr != li and lr != 0 and not separated(wr, wi):
+                            conflict = True
+            if conflict:
+                lane[i] = 0
+                changed = True
+                break
+            for s_ in writes[i]:
+                last_w[s_] = (li, wi)
+                last_r[s_] = []
+            for s_ in reads[i]:
+                last_r.setdefault(s_, []).append((li, wi))
+        if not changed:
+            break
+    return lane
+
+
 def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, downsolve: bool = True,
                   gibbsIters: Optional[int] = None, downIters: int = 3,
-                  useMsgLikelihoods: Optional[bool] = None) -> SolvePlan:
+                  useMsgLikelihoods: Optional[bool] = None, lanes: int = 0) -> SolvePlan:
     """Lower one solveTree! (up + down pass) to slots, props and waves.
 
     useMsgLikelihoods=false (SolverParams default): up messages are one MsgPrior per separator variable.
@@ -588,10 +672,14 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
     for w in range(nw):
         wave_off[w + 1] += wave_off[w]
     up_last = max(waves[:n_up_ops]) + 1 if n_up_ops else 0
+    wt = [float(len(props[a]["factors"]) + 1) if k == A.S_PROPAGATE else (1.0 if k == A.S_DECONV else 0.05)
+          for (k, a, _) in sched]
+    lane = assign_lanes(tree, opc, wt, waves, reads, writes, lanes)
     frozen = T.freeze()
     return SolvePlan(T, frozen, props, sched, wave_off, sched_waved, var_slot, nconv[0], len(props), n_msgs,
                      up_last, [opc[i] for i in order], [waves[i] for i in order], [reads[i] for i in order],
-                     [writes[i] for i in order], {s: cid for (cid, _), s in cslot.items()}, deconvs)
+                     [writes[i] for i in order], {s: cid for (cid, _), s in cslot.items()}, deconvs,
+                     [lane[i] for i in order])
 
 
 def _joint_up_message(fg, c: TreeClique, inst, slot_of, T, N, deconvs, sched, reads, writes, opc, cur):

@@ -346,3 +346,28 @@ def test_c5_full_size_grid_properties(built):
     err = np.abs(mean - pos).max(axis=1)
     assert err.mean() < 0.4 and err.max() < 2.5, (float(err.mean()), float(err.max()))
     ts.close()
+
+
+def test_lanes_do_not_change_results(built):
+    """Lanes only add parallel branches to the captured CUDA graph: the posterior of every variable is bit-identical
+    with 0, 2 and 4 lanes (chain with differential messages off and on, and a grid)."""
+    cases = [(W.scalar_chain(120, N=100, seed=4), W.chain_nd_order(120), False),
+             (W.scalar_chain(60, N=64, seed=4), W.chain_nd_order(60), True),
+             (W.euclid2_grid(rows=5, cols=8, N=64, seed=4, closure_every=2), None, False)]
+    for fg, order, uml in cases:
+        fg.solverParams.useMsgLikelihoods = uml
+        order = order or TR.getEliminationOrder(fg, "nd")
+        res = []
+        for lanes in (0, 2, 4):
+            ts = SV.TreeSolver(fg, order, lanes=lanes)
+            assert (max(ts.plan.op_lane) > 0) == (lanes > 0)
+            ts.load_from_graph()
+            ts.upload()
+            ts.run()
+            ts.run()                                    # replay of the cached graph
+            ts.download()
+            res.append({l: ts.arena.get(ts.plan.var_slot[l]) for l in fg.variables})
+            ts.close()
+        for l in fg.variables:
+            for r in res[1:]:
+                assert np.array_equal(res[0][l][0], r[l][0]) and np.array_equal(res[0][l][1], r[l][1]), l

@@ -138,3 +138,35 @@ def test_nested_dissection_orders_are_permutations():
         q = TR.getEliminationOrder(fg, "qr")
         assert sorted(q) == sorted(fg.variables)
     assert sorted(W.chain_nd_order(37)) == sorted(f"x{k}" for k in range(37))
+
+
+def test_lanes_are_hazard_free():
+    """tree.assign_lanes: ops of different lanes never conflict on a slot unless a barrier wave (one holding a
+    lane-0 op) separates them; lanes carry the bulk of the work and are balanced."""
+    for fg, order, L in ((W.scalar_chain(200, N=8), W.chain_nd_order(200), 4),
+                         (W.euclid2_grid(8, 10, N=8), None, 3),
+                         (W.scalar_chain(40, N=8), TR.getEliminationOrder(W.scalar_chain(40, N=8), "natural"), 4)):
+        order = order or TR.getEliminationOrder(fg, "nd")
+        tree = TR.buildTree(fg, order)
+        plan = TR.compile_solve(fg, tree, lanes=L)
+        ln, wv = plan.op_lane, plan.op_wave
+        assert len(ln) == len(plan.sched_waved) and set(ln) <= set(range(L + 1))
+        barrier = sorted({w for l, w in zip(ln, wv) if l == 0})
+
+        def separated(wa, wb):
+            return any(wa <= b <= wb for b in barrier)
+        touched = {}
+        for i, (rd, wr) in enumerate(zip(plan.op_reads, plan.op_writes)):
+            for s_ in set(rd) | set(wr):
+                for j, j_writes in touched.get(s_, []):
+                    if (j_writes or s_ in wr) and ln[i] != ln[j] and ln[i] != 0 and ln[j] != 0:
+                        assert separated(wv[j], wv[i]), (i, j, s_)
+                touched.setdefault(s_, []).append((i, s_ in wr))
+        plain = TR.compile_solve(fg, tree)
+        assert plain.sched_waved == plan.sched_waved and plain.wave_off == plan.wave_off   # lanes only annotate
+        assert set(plain.op_lane) == {0}
+    # on the nested-dissection chain most of the work sits in lanes and the lanes are balanced
+    fg = W.scalar_chain(200, N=8)
+    plan = TR.compile_solve(fg, TR.buildTree(fg, W.chain_nd_order(200)), lanes=4)
+    cnt = [sum(1 for l in plan.op_lane if l == k) for k in range(5)]
+    assert cnt[0] < 0.2 * sum(cnt) and min(cnt[1:]) > 0.6 * max(cnt[1:])
