@@ -471,7 +471,8 @@ def assign_lanes(tree: BayesTree, op_clique, op_weight, waves, reads, writes, nl
 
 def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, downsolve: bool = True,
                   gibbsIters: Optional[int] = None, downIters: int = 3,
-                  useMsgLikelihoods: Optional[bool] = None, lanes: int = 0) -> SolvePlan:
+                  useMsgLikelihoods: Optional[bool] = None, lanes: int = 0,
+                  forward_copies: bool = True) -> SolvePlan:
     """Lower one solveTree! (up + down pass) to slots, props and waves.
 
     useMsgLikelihoods=false (SolverParams default): up messages are one MsgPrior per separator variable.
@@ -501,11 +502,25 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
     nconv = [0]
     cur = [-1]     # clique whose ops are being emitted
 
+    # copy forwarding: a separator value travels down the tree through a chain of slot copies (parent -> child ->
+    # grandchild ...).  A copy whose source was itself filled by a copy from X, with X unchanged since, reads X
+    # directly: same value, but the chain no longer serialises one wave per tree level.
+    version: Dict[int, int] = {}
+    prov: Dict[int, tuple] = {}
+
+    def wrote(slot):
+        version[slot] = version.get(slot, 0) + 1
+        prov.pop(slot, None)
+
     def add_copy(a, b):
+        if forward_copies and a in prov and version.get(prov[a][0], 0) == prov[a][1]:
+            a = prov[a][0]
         sched.append((A.S_COPY, a, b))
         reads.append([a])
         writes.append([b])
         opc.append(cur[0])
+        wrote(b)
+        prov[b] = (a, version.get(a, 0))
 
     def fac_instance(f: G.DFGFactor, slot_of):
         return T.add_factor(f.fnc, [slot_of(v) for v in f.variables], f.multihypo, f.nullhypo, f.inflation)
@@ -520,6 +535,7 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
         writes.append([target_slot])
         opc.append(cur[0])
         nconv[0] += len(fac_list)
+        wrote(target_slot)
 
     # ---- step 0: clique sub-graphs start from the main graph's (graph-init) beliefs
     for c in tree.cliques:
