@@ -70,6 +70,17 @@ def rank_schedule(plan: TR.SolvePlan, op_rank: List[int], rank: int):
     return [o for o, _ in ops], wave_off
 
 
+def rank_lanes(plan: TR.SolvePlan, tree: TR.BayesTree, op_rank: List[int], rank: int, nlanes: int) -> List[int]:
+    """Lane of every op of `rank` (same order as rank_schedule): tree.assign_lanes restricted to the rank's own
+    ops, so barrier waves and hazards are those this device sees.  Beliefs arriving from other ranks are written
+    between two graph launches (wave-range boundaries), where every lane has joined."""
+    idx = [i for i, r in enumerate(op_rank) if r == rank]
+    wt = [float(len(plan.props[plan.sched_waved[i][1]]["factors"]) + 1) if plan.sched_waved[i][0] == A.S_PROPAGATE else 0.05
+          for i in idx]
+    return TR.assign_lanes(tree, [plan.op_clique[i] for i in idx], wt, [plan.op_wave[i] for i in idx],
+                           [plan.op_reads[i] for i in idx], [plan.op_writes[i] for i in idx], nlanes)
+
+
 class ShardedTreeSolver:
     """One rank's share of a tree solve.  `dist` is torch.distributed (nccl on GPUs)."""
 
@@ -100,7 +111,9 @@ class ShardedTreeSolver:
         self.eng = Engine(fz, self.sp_c, local_rank, self.arena_t.data_ptr())
         self.eng.set_stream(self.stream.cuda_stream)
         self.props_c = CP.make_prop_ops(self.plan.props)
-        self.sched_c = CP.make_sched_ops(my_ops)
+        import os
+        self.lanes = rank_lanes(self.plan, self.tree, self.op_rank, rank, int(os.environ.get("IIFB200_LANES", "4")))
+        self.sched_c = CP.make_sched_ops(my_ops, self.lanes)
         self.sid = self.eng.schedule_build(my_wave_off, self.sched_c, len(my_ops), self.props_c, len(self.plan.props))
         self.arena = CP.HostArena(fz)
         # every rank knows the size of every clique-local belief (remote replicas are receive buffers)

@@ -27,6 +27,8 @@ struct PropOp
   target_slot::Int32; out_slot::Int32; nfactors::Int32; N::Int32
   factor::NTuple{MAX_FACTORS,Int32}; sfidx::NTuple{MAX_FACTORS,Int32}; call_id::Int32; any_multihypo::Int32
 end
+struct SchedOp;  kind::Int32; a::Int32; b::Int32; lane::Int32; end      # kind: 1 PROPAGATE, 2 COPY, 3 DECONV
+struct DeconvOp; factor::Int32; out_slot::Int32; N::Int32; call_id::Int32; end
 
 check(ctx, st, what) = st == 0 || error("iifb200 $what failed ($st): " *
         unsafe_string(ccall((:iifb200_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
@@ -42,10 +44,21 @@ end
 factorkind(::Prior) = Int32(1); factorkind(::LinearRelative) = Int32(2)
 factorkind(::PriorCircular) = Int32(3); factorkind(::CircularCircular) = Int32(4)
 factorkind(::EuclidDistance) = Int32(5); factorkind(::IIF.MsgPrior) = Int32(6)
+factorkind(::IIF.PartialPrior) = Int32(7)
+factorkind(::ManifoldPrior) = Int32(8); factorkind(::IIF.ManifoldPriorPartial) = Int32(8)   # p is folded into Z's mean by _lower_factors
+factorkind(f::ManifoldFactor) = _manifoldfactorkind(f.M)
+_manifoldfactorkind(::Manifolds.SpecialEuclidean{2}) = Int32(9)     # hybrid tangent representation (testSpecialEuclidean2Mani.jl:14)
+_manifoldfactorkind(::Manifolds.TranslationGroup) = Int32(2)
+_manifoldfactorkind(::Manifolds.RealCircleGroup) = Int32(4)
+_manifoldfactorkind(M) = error("IIFB200: ManifoldFactor on $(M) has no device residual")
 factorkind(f) = error("IIFB200: factor $(typeof(f)) has no device residual (no CPU fallback on the b200 backend)")
 
+# circular-coordinate mask of a variable type; SpecialEuclidean(2) points ArrayPartition(t, R) travel as (t1, t2, theta)
 circmask(::Type{<:IIF.Circular}) = Int32(1)
+circmask(::Type{T}) where {T <: InferenceVariable} = getManifold(T) isa Manifolds.SpecialEuclidean{2} ? Int32(0b100) : Int32(0)
 circmask(::Any) = Int32(0)
+se2coords(p) = (p.x[1][1], p.x[1][2], atan(p.x[2][2, 1], p.x[2][1, 1]))           # AMP.makeCoordsFromPoint
+se2point(c)  = ArrayPartition(SA[c[1], c[2]], SA[cos(c[3]) -sin(c[3]); sin(c[3]) cos(c[3])])   # AMP.makePointFromCoords
 
 """
     propagateBelief(dfg, destvar, factors; N, ...)   — GraphProductOperations.jl:16-64
@@ -126,6 +139,23 @@ function mmd_b200(a::Matrix{Float64}, b::Matrix{Float64}; circmask::Integer = 0,
         ctx, 1, Int32(size(a, 2)), Int32(size(b, 2)), Int32(size(a, 1)), Int32(circmask), a, b, bw, out), "mmd")
   return out[]
 end
+
+"""
+    schedule(ctx, wave_off, ops, props, deconvs) -> id     — boundary B4 (whole clique / whole tree per replay)
+
+`ops` in wave order (`wave_off[w]:wave_off[w+1]` are mutually independent), `props` the propagateBelief descriptors,
+`deconvs` the differential-likelihood constructions of `useMsgLikelihoods=true` up messages
+(addLikelihoodsDifferentialCHILD!, TreeMessageUtils.jl:279-335).  `SchedOp.lane` marks independent sub-trees that
+the captured CUDA graph runs as parallel branches (0 = none).
+"""
+function schedule(ctx, wave_off::Vector{Int32}, ops::Vector{SchedOp}, props::Vector{PropOp}, deconvs::Vector{DeconvOp} = DeconvOp[])
+  id = Ref{Int32}(-1)
+  check(ctx, ccall((:iifb200_schedule_build_ex, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{SchedOp}, Int32, Ptr{PropOp}, Int32, Ptr{DeconvOp}, Ref{Int32}),
+        ctx, length(wave_off) - 1, wave_off, length(ops), ops, length(props), props, length(deconvs), deconvs, id), "schedule_build_ex")
+  return id[]
+end
+run!(ctx, id; first = 0, last = -1) = check(ctx, ccall((:iifb200_schedule_run, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), ctx, id, first, last), "schedule_run")
 
 # throughput mode (boundary B4): IIF.upGibbsCliqueDensity / localProductAndUpdate! are lowered per tree by
 # iifb200_schedule_build and replayed by iifb200_schedule_run; see incrementalinference.jl_b200/tree.py for

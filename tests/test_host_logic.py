@@ -169,4 +169,4 @@ def test_lanes_are_hazard_free():
     fg = W.scalar_chain(200, N=8)
     plan = TR.compile_solve(fg, TR.buildTree(fg, W.chain_nd_order(200)), lanes=4)
     cnt = [sum(1 for l in plan.op_lane if l == k) for k in range(5)]
-    assert cnt[0] < 0.2 * sum(cnt) and min(cnt[1:]) > 0.6 * max(cnt[1:])
+    assert cnt[0] < 0.2 * sum(cnt) and min(cnt[1:]) > 0.5 * max(cnt[1:])

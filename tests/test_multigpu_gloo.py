@@ -123,3 +123,32 @@ def test_partition_properties():
             assert woff[-1] == len(ops) and len(woff) == len(plan.wave_off)
             tot += len(ops)
         assert tot == len(plan.sched_waved)
+
+
+def test_rank_lanes_are_hazard_free():
+    """Per-rank lanes (multigpu.rank_lanes): among one rank's ops, conflicting ops of different lanes are separated
+    by one of THAT rank's barrier waves; beliefs received from other ranks land between graph launches."""
+    import iifb200  # noqa: F401
+    from iifb200 import multigpu as MG
+    from iifb200 import tree as TR
+    from iifb200 import workloads as W
+    fg = W.scalar_chain(128, N=16)
+    tree = TR.buildTree(fg, W.chain_nd_order(128))
+    plan = TR.compile_solve(fg, tree, useMsgLikelihoods=False)
+    for world in (2, 4):
+        owner = MG.clique_owner(fg, tree, world)
+        op_rank, transfers = MG.partition_plan(plan, owner, world)
+        for r in range(world):
+            idx = [i for i, q in enumerate(op_rank) if q == r]
+            ln = MG.rank_lanes(plan, tree, op_rank, r, 4)
+            assert len(ln) == len(idx) and max(ln) > 0
+            wv = [plan.op_wave[i] for i in idx]
+            barrier = sorted({w for l, w in zip(ln, wv) if l == 0})
+            touched = {}
+            for k, i in enumerate(idx):
+                rd, wr = plan.op_reads[i], plan.op_writes[i]
+                for s_ in set(rd) | set(wr):
+                    for j, j_writes in touched.get(s_, []):
+                        if (j_writes or s_ in wr) and ln[k] != ln[j] and ln[k] != 0 and ln[j] != 0:
+                            assert any(wv[j] <= b <= wv[k] for b in barrier), (r, k, j, s_)
+                    touched.setdefault(s_, []).append((k, s_ in wr))
