@@ -34,15 +34,16 @@ def test_struct_sizes_match_header(built):
     prog = textwrap.dedent("""
         #include <stdio.h>
         #include "iifb200.h"
-        int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(iif_dist_desc), sizeof(iif_slot_desc),
+        int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(iif_dist_desc), sizeof(iif_slot_desc),
           sizeof(iif_factor_desc), sizeof(iif_solver_params), sizeof(iif_conv_op), sizeof(iif_prop_op),
-          sizeof(iif_product_op), sizeof(iif_sched_op)); return 0;}""")
+          sizeof(iif_product_op), sizeof(iif_sched_op), sizeof(iif_deconv_op)); return 0;}""")
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(prog)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
         out = subprocess.check_output([os.path.join(d, "s")]).split()
     sizes = [int(x) for x in out]
-    mirrors = [A.DistDesc, A.SlotDesc, A.FactorDesc, A.SolverParamsC, A.ConvOp, A.PropOp, A.ProductOp, A.SchedOp]
+    mirrors = [A.DistDesc, A.SlotDesc, A.FactorDesc, A.SolverParamsC, A.ConvOp, A.PropOp, A.ProductOp, A.SchedOp,
+               A.DeconvOp]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 
