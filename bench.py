@@ -363,6 +363,8 @@ def run_b200(args, rank, world, local_rank):
                                f"one solveTree pass = {total_conv} convolutions + {plan.n_prod} products",
                    "poses": n_poses, "N": NPART, "elimination_order": args.order, "waves": len(plan.wave_off) - 1,
                    "l2": "flushed between timed steps (256 MiB write)", "rng": "device Philox4x32-10, new seed every step",
+                   "schedule": f"one CUDA graph per pass, {max(plan.op_lane) if runner is None else max(runner.lanes)} lanes "
+                               "(independent sub-trees as parallel graph branches), separator copies forwarded",
                    "sharding": "1 GPU" if world == 1 else f"{world} contiguous 1000-pose segments, NCCL separator messages"},
         "e2e": {"value": total_conv * args.steps / e2e_s, "unit": "conv/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
