@@ -84,8 +84,9 @@ class ClockSampler:
 def ncu_traffic_per_block():
     """DRAM bytes per convolution (CTA) of iif_conv_kernel from the committed `ncu --set full` capture
     (profiles/r01_kernels.json, written by profiles/summarise.py); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r01_kernels.json")
-    if not os.path.exists(p):
+    p = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r01b_kernels.json", "r01_kernels.json"))
+              if os.path.exists(q)), None)
+    if p is None:
         return None, None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for name, d in json.load(open(p)).items():
@@ -338,7 +339,7 @@ def run_b200(args, rank, world, local_rank):
         roof = {"bound": "hbm", "kernel": "iif_conv_kernel", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"],
                 "traffic": (tpb * cb / max(cl, 1)) if tpb is not None else None,
-                "traffic_source": (f"profiles/{tsrc}.ncu-rep summary in profiles/r01_kernels.json: dram bytes per CTA x "
+                "traffic_source": (f"profiles/{tsrc}.ncu-rep summary in profiles/r01b_kernels.json: dram bytes per CTA x "
                                    f"average CTAs per launch") if tpb is not None else None,
                 "algorithmic_bytes_per_launch": byts / max(cl, 1),
                 "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)",

@@ -1034,13 +1034,15 @@ static int enqueue_seg(iifb200_ctx* ctx, Schedule* s, const Wave& W, const Seg& 
 // enqueue waves [w0, w1); returns the number of kernels launched.  `lanes` (only inside a stream capture): lane
 // segments go to per-lane streams forked from / joined into the ctx stream with events, so the captured graph
 // carries the lanes as parallel branches.  Without `lanes` everything is issued on the ctx stream in wave order.
-static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int* nk, bool lanes) {
+static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int* nk, bool lanes,
+                             const std::vector<cudaEvent_t>* pool = nullptr) {
   int k = 0;
+  size_t used = 0;
   bool active[IIF_MAX_LANES + 1] = {};
-  auto new_event = [&](cudaEvent_t* e) {
-    cudaError_t err = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
-    if (err == cudaSuccess) s->events.push_back(*e);
-    return err;
+  auto new_event = [&](cudaEvent_t* e) {  // events come from a pool created BEFORE the capture began
+    if (!pool || used >= pool->size()) return cudaErrorInvalidValue;
+    *e = (*pool)[used++];
+    return cudaSuccess;
   };
   auto join_all = [&]() -> cudaError_t {
     for (int l = 1; l <= IIF_MAX_LANES; ++l) {
@@ -1062,7 +1064,6 @@ static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int*
         k += enqueue_seg(ctx, s, W, G, ctx->stream);
         continue;
       }
-      if (!ctx->lane_stream[G.lane]) CK(cudaStreamCreateWithFlags(&ctx->lane_stream[G.lane], cudaStreamNonBlocking));
       if (!active[G.lane]) {  // fork: the lane continues from the ctx stream's current point
         cudaEvent_t e;
         CK(new_event(&e));
@@ -1093,8 +1094,24 @@ int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t firs
   if (it == s->graphs.end()) {
     cudaGraph_t graph = nullptr;
     int nk = 0;
+    // lane streams and the fork / join events are created before the capture begins (no resource creation inside it)
+    std::vector<cudaEvent_t> pool;
+    {
+      size_t need = 0;
+      for (int w = first_wave; w < last_wave; ++w)
+        for (const Seg& G : s->waves[w].segs) {
+          if (G.lane == 0) continue;
+          if (!ctx->lane_stream[G.lane]) CK(cudaStreamCreateWithFlags(&ctx->lane_stream[G.lane], cudaStreamNonBlocking));
+          need += 2;  // at most one fork and one join per lane segment
+        }
+      pool.resize(need);
+      for (auto& e : pool) {
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->events.push_back(e);
+      }
+    }
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    int32_t st = enqueue_waves(ctx, s, first_wave, last_wave, &nk, true);
+    int32_t st = enqueue_waves(ctx, s, first_wave, last_wave, &nk, true, &pool);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (st != IIF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
     if (e != cudaSuccess) return fail(ctx, IIF_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
