@@ -17,6 +17,23 @@ import parity_cases as PC  # noqa: E402
 from iifb200 import compile as CP  # noqa: E402
 
 
+def uml_case():
+    """13-pose scalar chain, N=64, nested-dissection order, useMsgLikelihoods=true, solved by the oracle"""
+    import oracle as O
+    from iifb200 import tree as TR
+    from iifb200 import workloads as W
+    fg, order = W.scalar_chain(13, N=64, seed=3), W.chain_nd_order(13)
+    fg.solverParams.useMsgLikelihoods = True
+    plan = TR.compile_solve(fg, TR.buildTree(fg, order))
+    arena = CP.HostArena(plan.frozen)
+    for l, v in fg.variables.items():
+        arena.set(plan.var_slot[l], v.val, v.bw, True, v.infoPerCoord)
+    orc = O.Oracle(plan.frozen, arena, CP.solver_params_c(fg.solverParams))
+    orc.schedule_run(plan.wave_off, CP.make_sched_ops(plan.sched_waved), CP.make_prop_ops(plan.props),
+                     deconvs=CP.make_deconv_ops(plan.deconvs or []))
+    return fg, order, plan, arena
+
+
 def main():
     out = {}
     for name, P, specs, streams in PC.conv_cases():
@@ -46,6 +63,14 @@ def main():
     for k, x in enumerate(xs):
         pts, bw, ipc = orc.arena.get(x)
         out[f"schedule/chain4/x{k}/pts"], out[f"schedule/chain4/x{k}/bw"] = pts, bw
+    # a whole tree solve with differential messages (useMsgLikelihoods=true), incl. the IIF_S_DECONV slots
+    fg, order, plan, arena = uml_case()
+    for l in fg.variables:
+        pts, bw, _ = arena.get(plan.var_slot[l])
+        out[f"uml/chain13/{l}/pts"], out[f"uml/chain13/{l}/bw"] = pts, bw
+    for k, dc in enumerate(plan.deconvs):
+        pts, bw, _ = arena.get(dc["out_slot"])
+        out[f"uml/chain13/diff{k}/pts"], out[f"uml/chain13/diff{k}/bw"] = pts, bw
     np.savez_compressed(os.path.join(HERE, "hotpath_golden.npz"), **out)
     print("wrote", len(out), "arrays")
 
