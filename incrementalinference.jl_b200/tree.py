@@ -19,6 +19,7 @@ The lowering turns every `propagateBelief` of the pass into an iif_prop_op on cl
 belief slots and levelises them into waves of mutually independent ops (slot hazards), which
 libiifb200 captures as one CUDA graph.
 """
+import bisect
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -432,7 +433,6 @@ def assign_lanes(tree: BayesTree, op_clique, op_weight, waves, reads, writes, nl
     order = sorted(range(n), key=lambda i: (waves[i], i))
     for _ in range(n):                                   # demotions create new barrier waves: iterate to a fixed point
         barrier = sorted({waves[i] for i in range(n) if lane[i] == 0})
-        import bisect
 
         def separated(wa, wb):                          # a barrier wave in (wa, wb], or wa itself a barrier
             k = bisect.bisect_left(barrier, wa)
