@@ -35,6 +35,29 @@ def scalar_chain(n=4, N=100, seed=42, prior_sigma=0.1, odo=1.0, odo_sigma=0.1):
     return fg
 
 
+def scalar_chain_sessions(sessions=4, n=1000, N=100, seed=42, prior_sigma=0.1, odo=1.0, odo_sigma=0.1):
+    """`sessions` independent C2-style chains s{b}x0..s{b}x{n-1} in ONE factor graph (a forest): several robots /
+    sessions solved by one solveTree pass.  The Bayes tree has one root per session, so every wave of the pass holds
+    the independent work of all sessions."""
+    sp = G.SolverParams(N=N, seed=seed, graphinit=False)
+    fg = G.initfg(sp)
+    R = np.random.default_rng(seed)
+    for b in range(sessions):
+        for k in range(n):
+            G.addVariable(fg, f"s{b}x{k}", G.ContinuousScalar)
+        G.addFactor(fg, [f"s{b}x0"], G.Prior(G.Normal(10.0 * b, prior_sigma)))
+        for k in range(n - 1):
+            G.addFactor(fg, [f"s{b}x{k}", f"s{b}x{k+1}"], G.LinearRelative(G.Normal(odo, odo_sigma)))
+        for k in range(n):
+            _init(fg, f"s{b}x{k}", R.normal(10.0 * b + odo * k, odo_sigma * np.sqrt(k + 1.0), (N, 1)))
+    return fg
+
+
+def sessions_nd_order(sessions, n):
+    """nested-dissection order of every session's chain, one after the other"""
+    return [f"s{b}{x}" for b in range(sessions) for x in chain_nd_order(n)]
+
+
 def four_door(N=200, seed=42):
     """C3: test/fourdoortest.jl:9-54 (Mixture priors = four doors) with useMsgLikelihoods=false."""
     sp = G.SolverParams(N=N, seed=seed, graphinit=False)

@@ -371,3 +371,16 @@ def test_lanes_do_not_change_results(built):
         for l in fg.variables:
             for r in res[1:]:
                 assert np.array_equal(res[0][l][0], r[l][0]) and np.array_equal(res[0][l][1], r[l][1]), l
+
+
+def test_independent_sessions_in_one_pass(built):
+    """Several independent graphs in one factor graph (a forest: one Bayes-tree root per session) are solved by one
+    pass; every session is localised as when solved alone (priors at 0, 10, 20; unit odometry)."""
+    B, n = 3, 24
+    fg = W.scalar_chain_sessions(B, n, N=100, seed=6)
+    ts = SV.solveTree(fg, eliminationOrder=W.sessions_nd_order(B, n))
+    assert len(ts.tree.roots) == B
+    for b in range(B):
+        for k in (0, n // 2, n - 1):
+            p = _pts(fg, f"s{b}x{k}")
+            assert abs(p.mean() - (10.0 * b + k)) < 0.35 + 0.15 * np.sqrt(k + 1.0), (b, k, p.mean())
