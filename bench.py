@@ -120,11 +120,54 @@ def build_workload(n_poses, order_kind):
 
 
 # ----------------------------------------------------------------------------- reference arm
+def run_reference_julia(args):
+    """The reference's own solveTree! through baseline/ref_solve.jl — only where a Julia toolchain with
+    IncrementalInference installed exists (not in the build image nor on its GPU boxes; then None)."""
+    import shutil
+    julia = shutil.which("julia")
+    if julia is None:
+        return None
+    try:
+        ok = subprocess.run([julia, "-e", "using IncrementalInference"], capture_output=True, timeout=600).returncode == 0
+    except Exception:
+        ok = False
+    if not ok:
+        return None
+    cores = os.cpu_count() or 1
+    n_sample = 100
+    from iifb200 import tree as TR
+    fg, order = build_workload(n_sample, args.order)
+    n_conv = TR.compile_solve(fg, TR.buildTree(fg, order)).n_conv      # the unit count both arms are divided into
+    env = dict(os.environ, JULIA_NUM_THREADS=str(cores))
+    try:
+        out = subprocess.run([julia, os.path.join(ROOT, "baseline", "ref_solve.jl"), str(n_sample), str(NPART),
+                              str(max(args.steps, 1)), "true", str(n_conv)],
+                             capture_output=True, text=True, timeout=3000, env=env)
+        r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception:
+        return None
+    val = float(r["conv_per_s"])
+    sample = f"{r['solves']} solveTree! calls on a {n_sample}-pose chain of the same kind ({r['convolutions']} convolutions each)"
+    return {"impl": "reference", "metric": "clique belief convolutions/sec (N=100 particles)", "value": val,
+            "unit": "conv/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(r["seconds"]) / max(int(r["solves"]), 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{POSES_PER_GPU}-pose ContinuousScalar odometry chain, N={NPART} (bounded sample: {n_sample} poses)",
+                       "elimination_order": args.order, "N": NPART},
+            "cpu_baseline": {"value": val, "unit": "conv/s", "cores": int(r["threads"]), "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": "conv/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "note": "unmodified IncrementalInference.jl solveTree!(; multithread=true) via baseline/ref_solve.jl"}
+
+
 def run_reference(args, rank, world):
     """CPU reference arm.  The reference is pure Julia and no Julia toolchain exists in this image
     (DESIGN.md), so this times the oracle port of the same path with all host threads (OpenMP over
     the independent ops of a wave) on a bounded sample of the same workload."""
     if rank != 0:
+        return
+    ref = run_reference_julia(args)
+    if ref is not None:
+        print(json.dumps(ref))
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ctypes

@@ -1,0 +1,52 @@
+# dump_golden.jl — golden vectors from the reference itself, to PIN sample-level parity (SURVEY.md §8c item 5).
+#
+# NOT EXECUTED IN THE BUILD IMAGE (no Julia).  Run it wherever IncrementalInference.jl is installed, commit the output
+# under tests/golden/julia/ and compare through the host-stream inputs of the C-ABI (`meas`, `mhidx`, `uinf` of
+# iifb200_conv_batch; `randU`, `randN` of iifb200_product_batch): with the reference's own random draws passed in,
+# hypothesis labels must match bit for bit and proposals within 1e-6 (1-D BFGS) / 1e-3 (Nelder-Mead).
+#
+# usage: julia julia/dump_golden.jl out_dir
+# writes, per case, CSV files: <case>_src.csv (source particles), <case>_meas.csv, <case>_mhidx.csv,
+# <case>_proposal.csv, <case>_bw.csv  (one row per particle / coordinate)
+using IncrementalInference, Random, DelimitedFiles
+const IIF = IncrementalInference
+out = length(ARGS) > 0 ? ARGS[1] : "golden_julia"
+mkpath(out)
+Random.seed!(42)
+N = 100
+
+function dump_case(name, fg, fct::Symbol, target::Symbol)
+  fc = getFactor(fg, fct)
+  ccw = IIF._getCCW(fc)
+  # the reference's own draws: fresh measurements and the hypothesis recipe for this convolution
+  IIF.sampleFactor!(ccw, N)
+  m0 = deepcopy(ccw.measurement)
+  meas = [collect(Float64, m) for m in m0]
+  # pass the drawn measurements explicitly so that the convolution uses exactly the dumped ones
+  # (approxConvBelief(dfg, fc, target, measurement; N), ApproxConv.jl:4-12)
+  bel = approxConvBelief(fg, fct, target, m0; N = N)
+  pts = getPoints(bel, false)
+  writedlm(joinpath(out, "$(name)_meas.csv"), reduce(hcat, meas)', ',')
+  writedlm(joinpath(out, "$(name)_proposal.csv"), reduce(hcat, [collect(Float64, p) for p in pts])', ',')
+  writedlm(joinpath(out, "$(name)_bw.csv"), getBW(bel)[:, 1], ',')
+  for v in getVariableOrder(fc)
+    vals = getVal(fg, v)
+    writedlm(joinpath(out, "$(name)_src_$(v).csv"), reduce(hcat, [collect(Float64, p) for p in vals])', ',')
+  end
+end
+
+# case 1: scalar prior + relative (tests/parity_cases.py "scalar_prior_and_relative")
+fg = initfg(); getSolverParams(fg).N = N
+addVariable!(fg, :x0, ContinuousScalar); addVariable!(fg, :x1, ContinuousScalar)
+addFactor!(fg, [:x0], Prior(Normal(0.0, 1.0)))
+addFactor!(fg, [:x0, :x1], LinearRelative(Normal(1.0, 0.1)))
+initAll!(fg)
+dump_case("scalar_prior", fg, :x0f1, :x0)
+dump_case("scalar_relative_fwd", fg, :x0x1f1, :x1)
+dump_case("scalar_relative_bwd", fg, :x0x1f1, :x0)
+
+# case 2: product of two proposals with the Gibbs streams AMP consumed (manifoldProduct is called by propagateBelief)
+mkd, ipc = propagateBelief(fg, :x0, :)
+writedlm(joinpath(out, "product_x0_posterior.csv"), reduce(hcat, [collect(Float64, p) for p in getPoints(mkd, false)])', ',')
+writedlm(joinpath(out, "product_x0_bw.csv"), getBW(mkd)[:, 1], ',')
+println("wrote golden vectors to ", out)
