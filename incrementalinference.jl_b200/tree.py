@@ -227,19 +227,40 @@ def _postorder(tree: BayesTree) -> List[int]:
 def _buildCliquePotentials(fg: G.FactorGraph, tree: BayesTree):
     """buildCliquePotentials (post-order): setCliqPotentials! + assoc matrices + setCliqMCIDs!."""
     used = set()
+    by_var = _factors_by_variable(fg)
     for cid in _postorder(tree):
         c = tree.cliques[cid]
         allv = set(c.allvars)
         pots = []
-        for f in fg.factors.values():                 # getFactorsAmongVariablesOnly(unused) ∩ frontal factors
+        for f in _factors_touching(fg, by_var, c.frontals):   # getFactorsAmongVariablesOnly(unused) ∩ frontal factors
             if f.label in used:
                 continue
-            if set(f.variables) <= allv and any(v in c.frontals for v in f.variables):
+            if set(f.variables) <= allv:
                 pots.append(f.label)
         c.potentials = pots
         used.update(pots)
         c.inmsgIDs = [s for ch in c.children for s in tree.cliques[ch].separators]   # collectSeparators
         _setCliqMCIDs(fg, c)
+
+
+def _factors_by_variable(fg: G.FactorGraph) -> Dict[str, list]:
+    by_var: Dict[str, list] = {l: [] for l in fg.variables}
+    for f in fg.factors.values():
+        for v in f.variables:
+            by_var[v].append(f)
+    return by_var
+
+
+def _factors_touching(fg: G.FactorGraph, by_var, variables):
+    """factors with at least one of `variables`, in graph (insertion) order, each once"""
+    seen, out = set(), []
+    for v in variables:
+        for f in by_var[v]:
+            if f.label not in seen:
+                seen.add(f.label)
+                out.append(f)
+    out.sort(key=lambda f: f.index)
+    return out
 
 
 def _setCliqMCIDs(fg: G.FactorGraph, c: TreeClique):
@@ -544,6 +565,7 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
             add_copy(var_slot[v], cslot[(c.id, v)])
 
     post = _postorder(tree)
+    by_var = _factors_by_variable(fg)
     n_msgs = 0
     # ---- up pass (children before parents)
     for cid in post:
@@ -645,10 +667,9 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
                 for e in kept_diffs.get(cid, []):
                     inst.append((e["variables"], e["fi"], False, e["rd"]))
             else:
-                for f in fg.factors.values():
-                    if any(v in c.frontals for v in f.variables):
-                        inst.append((f.variables, fac_instance(f, slot_dn), G.isMultihypo(f),
-                                     [slot_dn(v) for v in f.variables]))
+                for f in _factors_touching(fg, by_var, c.frontals):
+                    inst.append((f.variables, fac_instance(f, slot_dn), G.isMultihypo(f),
+                                 [slot_dn(v) for v in f.variables]))
 
             def local_product(v):
                 fl, rd = [], []
