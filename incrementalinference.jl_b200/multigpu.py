@@ -95,7 +95,9 @@ class ShardedTreeSolver:
         self.op_rank, self.transfers = partition_plan(self.plan, self.owner, world)
         my_ops, my_wave_off = rank_schedule(self.plan, self.op_rank, rank)
         self.my_conv = sum(len(self.plan.props[a]["factors"]) for k, a, _ in my_ops if k == A.S_PROPAGATE)
-        self.comm_waves = sorted({t[0] for t in self.transfers})
+        # this rank splits its graph only at the waves where IT sends or receives (point-to-point exchanges involve
+        # nobody else); waves where other pairs exchange do not interrupt its graph
+        self.comm_waves = sorted({t[0] for t in self.transfers if rank in (t[2], t[3])})
         self.by_wave = defaultdict(list)
         for w, s, a, b in self.transfers:
             if rank in (a, b):
