@@ -170,3 +170,28 @@ def test_lanes_are_hazard_free():
     plan = TR.compile_solve(fg, TR.buildTree(fg, W.chain_nd_order(200)), lanes=4)
     cnt = [sum(1 for l in plan.op_lane if l == k) for k in range(5)]
     assert cnt[0] < 0.2 * sum(cnt) and min(cnt[1:]) > 0.5 * max(cnt[1:])
+
+
+def test_tree_structure_known_answer_testTreeMessageUtils():
+    """test/testTreeMessageUtils.jl:6-39: LineStep(8) ring through lm0 with a fixed elimination order.  The reference
+    asserts: up messages exist for cliques 2..8; clique 2's message carries [:x0, :x4]; the variables that appear in
+    messages are [:lm0, :x0, :x2, :x4, :x6, :x7]; x0 is in 3 messages; x4 is in the messages of cliques
+    4 => depth 2, 6 => 3, 2 => 1, 8 => 1; clique 7 is a child of clique 3.  (Clique ids are 1-based there.)"""
+    fg = G.initfg(G.SolverParams(graphinit=False))
+    for i in range(9):
+        G.addVariable(fg, f"x{i}", G.ContinuousScalar)
+        if i == 0:
+            G.addFactor(fg, ["x0"], G.Prior(G.Normal(0.0, 0.1)))
+            G.addVariable(fg, "lm0", G.ContinuousScalar)
+        else:
+            G.addFactor(fg, [f"x{i - 1}", f"x{i}"], G.LinearRelative(G.Normal(1.0, 0.1)))
+    G.addFactor(fg, ["x0", "lm0"], G.LinearRelative(G.Normal(0.0, 0.1)))
+    G.addFactor(fg, ["x8", "lm0"], G.LinearRelative(G.Normal(-8.0, 0.1)))
+    tree = TR.buildTree(fg, ["x3", "x8", "x5", "x1", "x6", "lm0", "x7", "x4", "x2", "x0"])
+    depth = tree.depth()
+    assert len(tree.cliques) == 8 and [c.id + 1 for c in tree.cliques if c.parent is not None] == list(range(2, 9))
+    assert set(tree.cliques[1].separators) == {"x0", "x4"}
+    assert set().union(*[c.separators for c in tree.cliques]) == {"lm0", "x0", "x2", "x4", "x6", "x7"}
+    assert sum(1 for c in tree.cliques if "x0" in c.separators) == 3
+    assert {(c.id + 1, depth[c.id]) for c in tree.cliques if "x4" in c.separators} == {(4, 2), (6, 3), (2, 1), (8, 1)}
+    assert tree.cliques[6].parent == 2          # clique 7 -> clique 3

@@ -131,6 +131,86 @@ def test_oracle_solve_bands_with_msg_likelihoods(circular):
         assert bw[0] > 0 and pts.shape[0] == 64 and np.isfinite(m)
 
 
+def _caesar_ring():
+    """generateGraph_CaesarRing1D — CanonicalGraphExamples.jl:123-147"""
+    fg = G.initfg(G.SolverParams(graphinit=False, N=32))
+    for k in range(7):
+        G.addVariable(fg, f"x{k}", G.ContinuousScalar)
+    G.addFactor(fg, ["x0"], G.Prior(G.Normal()))
+    for k in range(6):
+        G.addFactor(fg, [f"x{k}", f"x{k + 1}"], G.LinearRelative(G.Normal()))
+    G.addVariable(fg, "l1", G.ContinuousScalar)
+    G.addFactor(fg, ["x0", "l1"], G.LinearRelative(G.Normal()))
+    G.addFactor(fg, ["x6", "l1"], G.LinearRelative(G.Normal()))
+    R = np.random.default_rng(0)
+    for l, v in fg.variables.items():
+        v.val, v.bw, v.initialized = R.normal(0, 1, (32, 1)), np.array([0.5]), True
+    return fg
+
+
+def test_joint_message_known_answer_testUseMsgLikelihoods():
+    """test/testUseMsgLikelihoods.jl:41-78: CaesarRing1D, eliminationOrder [x3,x5,l1,x1,x6,x4,x2,x0].  Clique 2 has
+    3 variables and no factor of its own; after addMsgFactors! of the up messages of cliques 4 and 5 it holds exactly
+    2 factors, one of them :x0x6f1, a LinearRelative whose Z is a ManifoldKernelDensity (no MsgPrior is added: neither
+    child holds a prior)."""
+    fg = _caesar_ring()
+    tree = TR.buildTree(fg, ["x3", "x5", "l1", "x1", "x6", "x4", "x2", "x0"])
+    c2, c4, c5 = tree.cliques[1], tree.cliques[3], tree.cliques[4]
+    assert len(c2.allvars) == 3 and not c2.potentials and c2.children == [3, 4]
+    assert set(c4.frontals) == {"l1"} and set(c4.separators) == {"x0", "x6"} and set(c5.separators) == {"x4", "x6"}
+    plan = TR.compile_solve(fg, tree, useMsgLikelihoods=True, downsolve=False)
+    fz = plan.frozen
+    slot_var = {}
+    idx = len(fg.variables)
+    for c in tree.cliques:                       # clique-local slots are allocated in clique order, variable order
+        for v in c.allvars:
+            slot_var[idx] = (c.id, v)
+            idx += 1
+    on_c2 = []
+    dummies = {dc["factor"] for dc in plan.deconvs}      # the tfg dummy factors of addLikelihoodsDifferentialCHILD!
+    for i in range(fz["nfactors"]):
+        if i in dummies:
+            continue
+        f = fz["factors"][i]
+        owners = {slot_var.get(f.slot[k], (None, None))[0] for k in range(f.arity)}
+        if owners == {1}:
+            on_c2.append((f.kind, fz["dists"][f.dist].kind, tuple(slot_var[f.slot[k]][1] for k in range(f.arity))))
+    assert len(on_c2) == 2, on_c2
+    assert all(k == A.F_LINEAR_RELATIVE and dk == A.D_KDE for k, dk, _ in on_c2)
+    assert {frozenset(v) for _, _, v in on_c2} == {frozenset(("x0", "x6")), frozenset(("x4", "x6"))}
+    assert len(plan.deconvs) >= 2
+
+
+def test_hasPriors913_band_oracle():
+    """test/testHasPriors913.jl:9-47: line x0..x4 closed through lm0, every belief initialised WRONG (around 5 + i), the
+    correct prior Normal(0, 0.01) on x0, useMsgLikelihoods=true; after three consecutive solves every PPE is within
+    0.7 of i (the message priors must carry the gauge up and down the tree)."""
+    sp = G.SolverParams(graphinit=False, N=64, useMsgLikelihoods=True, seed=7)
+    fg = G.initfg(sp)
+    for i in range(5):
+        G.addVariable(fg, f"x{i}", G.ContinuousScalar)
+        if i == 0:
+            G.addVariable(fg, "lm0", G.ContinuousScalar)
+        else:
+            G.addFactor(fg, [f"x{i - 1}", f"x{i}"], G.LinearRelative(G.Normal(1.0, 0.1)))
+    G.addFactor(fg, ["x0", "lm0"], G.LinearRelative(G.Normal(0.0, 0.1)))
+    G.addFactor(fg, ["x4", "lm0"], G.LinearRelative(G.Normal(-4.0, 0.1)))
+    G.addFactor(fg, ["x0"], G.Prior(G.Normal(0.0, 0.01)))
+    R = np.random.default_rng(1)
+    for l, v in fg.variables.items():
+        c = 5.0 + (int(l[1:]) if l.startswith("x") else 0.0)
+        v.val, v.initialized = R.normal(c, 0.1, (64, 1)), True
+        v.bw = O.kde_bandwidth(v.val)
+    order = TR.getEliminationOrder(fg, "qr")
+    for it in range(3):
+        fg.solverParams.seed = 7 + it
+        tree, plan, arena = _oracle_solve(fg, order)
+        for l, v in fg.variables.items():
+            v.val, v.bw, _ = arena.get(plan.var_slot[l])
+    for i in range(5):
+        assert abs(fg.variables[f"x{i}"].val.mean() - i) < 0.7, (i, fg.variables[f"x{i}"].val.mean())
+
+
 # ------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_deconv_slot_op_parity(built):
