@@ -377,3 +377,59 @@ def run_smoke():
     assert eng.launch_count() >= 2
     eng.close()
     assert_arena_equal("smoke", orc.arena, ag, P.frozen, [xs[0]])
+
+
+# ------------------------------------------------------------------------------ oracle-backed host flows (CPU tests)
+def oracle_initAll(fg):
+    """initAll! (GraphInit.jl:495-556) with the ORACLE as compute: the sequential doautoinit! sweep of
+    iifb200.solver.initAll(batched=False), for CPU tests of the reference's acceptance bands."""
+    import oracle as O
+    T = CP.Tables()
+    N = fg.solverParams.N
+    var_slot = {l: T.add_slot(v.vartype, max(N, v.val.shape[0], 1)) for l, v in fg.variables.items()}
+    fac_idx = {l: T.add_factor(f.fnc, [var_slot[v] for v in f.variables], f.multihypo, f.nullhypo, f.inflation)
+               for l, f in fg.factors.items()}
+    frozen = T.freeze()
+    arena = CP.HostArena(frozen)
+    for l, v in fg.variables.items():
+        if v.initialized:
+            arena.set(var_slot[l], v.val, v.bw, True, v.infoPerCoord)
+    orc = O.Oracle(frozen, arena, CP.solver_params_c(fg.solverParams))
+    call = 0
+    for _ in range(len(fg.variables) + 1):
+        did = False
+        for l, v in fg.variables.items():
+            if v.initialized:
+                continue
+            use = [f for f in fg.listNeighbors(l)
+                   if all(fg.variables[w].initialized for w in fg.factors[f].variables if w != l)]
+            if not use:
+                continue
+            spec = dict(target_slot=var_slot[l], out_slot=var_slot[l], N=N, call_id=call,
+                        factors=[(fac_idx[f], fg.factors[f].variables.index(l) + 1) for f in use],
+                        any_multihypo=int(any(G.isMultihypo(fg.factors[f]) for f in use)))
+            call += 16
+            orc.propagate(CP.make_prop_ops([spec])[0])
+            v.val, v.bw, v.infoPerCoord = arena.get(var_slot[l])
+            v.initialized = True
+            did = True
+        if not did:
+            break
+
+
+def oracle_solveTree(fg, order=None, ordering="qr", **kw):
+    """solveTree! with the ORACLE as compute (same plan the device runs); posteriors are written back to `fg`."""
+    import oracle as O
+    from iifb200 import tree as TR
+    order = order or TR.getEliminationOrder(fg, ordering)
+    tree = TR.buildTree(fg, order)
+    plan = TR.compile_solve(fg, tree, **kw)
+    arena = CP.HostArena(plan.frozen)
+    for l, v in fg.variables.items():
+        arena.set(plan.var_slot[l], v.val, v.bw, True, v.infoPerCoord)
+    orc = O.Oracle(plan.frozen, arena, CP.solver_params_c(fg.solverParams))
+    orc.schedule_run(plan.wave_off, CP.make_sched_ops(plan.sched_waved), CP.make_prop_ops(plan.props),
+                     deconvs=CP.make_deconv_ops(plan.deconvs or []))
+    for l, v in fg.variables.items():
+        v.val, v.bw, v.infoPerCoord = arena.get(plan.var_slot[l])
+    return tree, plan, arena

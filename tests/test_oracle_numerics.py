@@ -363,3 +363,97 @@ def test_se2_reference_bands_testSpecialEuclidean2Mani():
     P.freeze()
     pts, bw, ipc, _, _ = P.oracle().conv(CP.make_conv_ops([dict(factor=fpp, sfidx=1, N=N, call_id=1)])[0])
     assert np.array_equal(ipc, [1.0, 1.0, 0.0]) and np.all(pts[:, 2] == 0.0) and abs(pts[:, 0].mean() - 0.01) < 0.01
+
+
+def test_chain_solve_bands_testProductReproducable():
+    """test/testProductReproducable.jl:10-41: a..e with Prior(Normal()) and LinearRelative(Normal(10, 1)); after
+    initAll! + solveTree! the means sit at 0, 10, .., 40 (|err| < 3, 4, 4, 5, 5) and the spreads stay inside
+    (0.3, 2), (0.5, 4), (0.9, 6), (1.2, 7), (1.5, 8).  >= 19 of 20 seeds."""
+    ok = 0
+    for seed in range(20):
+        fg = G.initfg(G.SolverParams(graphinit=False, seed=seed))
+        for l in "abcde":
+            G.addVariable(fg, l, G.ContinuousScalar)
+        G.addFactor(fg, ["a"], G.Prior(G.Normal()))
+        for u, v in zip("abcd", "bcde"):
+            G.addFactor(fg, [u, v], G.LinearRelative(G.Normal(10.0, 1.0)))
+        PC.oracle_initAll(fg)
+        PC.oracle_solveTree(fg)
+        good = True
+        for k, (l, em, lo, hi) in enumerate(zip("abcde", (3, 4, 4, 5, 5), (0.3, 0.5, 0.9, 1.2, 1.5), (2, 4, 6, 7, 8))):
+            p = fg.variables[l].val[:, 0]
+            good &= abs(p.mean() - 10.0 * k) < em and lo < p.std(ddof=1) < hi
+        ok += good
+    assert ok >= 19, ok
+
+
+def test_back_and_forth_convolution_spreads_testProductReproducable():
+    """test/testProductReproducable.jl:52-98: ten rounds of approxConv a -> b -> a over LinearRelative(Normal(10, 1)):
+    the means stay put (|a| < 2, |b - 10| < 2) and the spreads grow beyond 3."""
+    R = np.random.default_rng(4)
+    P = PC.Problem()
+    a = P.slot(G.ContinuousScalar, 100, R.normal(0, 1, (100, 1)))
+    b = P.slot(G.ContinuousScalar, 100, R.normal(10, 1, (100, 1)))
+    f = P.factor(G.LinearRelative(G.Normal(10.0, 1.0)), [a, b])
+    P.freeze()
+    orc = P.oracle()
+    A0, B0 = orc.arena.get(a)[0].copy(), orc.arena.get(b)[0].copy()
+    for i in range(10):
+        for sf, slot in ((2, b), (1, a)):
+            pts, bw, *_ = orc.conv(CP.make_conv_ops([dict(factor=f, sfidx=sf, N=100, call_id=100 + 2 * i + sf)])[0])
+            orc.arena.set(slot, pts, bw, True)               # initVariable!(fg, :b, manikde!(pts))
+    A1, B1 = orc.arena.get(a)[0], orc.arena.get(b)[0]
+    assert abs(A0.mean()) < 1 and abs(A1.mean()) < 2 and abs(B0.mean() - 10) < 1 and abs(B1.mean() - 10) < 2
+    assert A0.std(ddof=1) < 2 and 3 < A1.std(ddof=1) and B0.std(ddof=1) < 2 and 3 < B1.std(ddof=1)
+
+
+def test_forward_convolve_testBasicForwardConvolve():
+    """test/testBasicForwardConvolve.jl:13-66 (#477): X0 ~ N(0, 0.1) -> LinearRelative(Normal(11, 1)) -> product with a
+    measurement belief N(9.5, 0.75) -> LinearRelative(Normal(8, 2)); 100 points, 15 < mean < 25."""
+    ok = 0
+    for seed in range(20):
+        R = np.random.default_rng(seed)
+        P = PC.Problem(seed=seed)
+        x0 = P.slot(G.ContinuousScalar, 100, R.normal(0, 0.1, (100, 1)))
+        x1 = P.slot(G.ContinuousScalar, 100, np.zeros((0, 1)), initialized=False)
+        x2 = P.slot(G.ContinuousScalar, 100, np.zeros((0, 1)), initialized=False)
+        f1 = P.factor(G.LinearRelative(G.Normal(11.0, 1.0)), [x0, x1])
+        f2 = P.factor(G.LinearRelative(G.Normal(8.0, 2.0)), [x1, x2])
+        P.freeze()
+        orc = P.oracle()
+        X1_, bw1, *_ = orc.conv(CP.make_conv_ops([dict(factor=f1, sfidx=2, N=100, call_id=1)])[0])
+        meas = R.normal(9.5, 0.75, (100, 1))
+        X1, bwp, _ = O.product(np.stack([X1_, meas]), np.stack([bw1, O.kde_bandwidth(meas)]), 1, seed=seed, call_id=2)
+        orc.arena.set(x1, X1, bwp, True)
+        X2, *_ = orc.conv(CP.make_conv_ops([dict(factor=f2, sfidx=2, N=100, call_id=3)])[0])
+        ok += X2.shape == (100, 1) and 15 < X2.mean() < 25
+    assert ok == 20
+
+
+def test_euclid_distance_bands_testEuclidDistance():
+    """test/testEuclidDistance.jl:10-77: x0 with a unit prior, x1 tied by EuclidDistance(Normal(10, 1)).
+    1-D: the solve-for belief is two-sided (> 30 % beyond +5, > 30 % below -5, < 10 % in between);
+    2-D: more than half of the points on the ring 7 < |x1| < 13; x0's estimate stays within 1 of the origin."""
+    ok1 = ok2 = 0
+    for seed in range(20):
+        fg = G.initfg(G.SolverParams(graphinit=False, seed=seed))
+        G.addVariable(fg, "x0", G.ContinuousScalar)
+        G.addFactor(fg, ["x0"], G.Prior(G.Normal()))
+        G.addVariable(fg, "x1", G.ContinuousScalar)
+        G.addFactor(fg, ["x0", "x1"], G.EuclidDistance(G.Normal(10.0, 1.0)))
+        PC.oracle_initAll(fg)
+        PC.oracle_solveTree(fg)
+        p = fg.variables["x1"].val[:, 0]
+        n = len(p)
+        ok1 += abs(fg.variables["x0"].val.mean()) < 1 and (p > 5).sum() > 0.3 * n and (p < -5).sum() > 0.3 * n \
+            and ((p > -5) & (p < 5)).sum() < 0.1 * n
+        fg = G.initfg(G.SolverParams(graphinit=False, seed=seed))
+        G.addVariable(fg, "x0", G.Position(2))
+        G.addFactor(fg, ["x0"], G.Prior(G.MvNormal(np.zeros(2), np.eye(2))))
+        G.addVariable(fg, "x1", G.Position(2))
+        G.addFactor(fg, ["x0", "x1"], G.EuclidDistance(G.Normal(10.0, 1.0)))
+        PC.oracle_initAll(fg)
+        PC.oracle_solveTree(fg)
+        r = np.linalg.norm(fg.variables["x1"].val, axis=1)
+        ok2 += np.abs(fg.variables["x0"].val.mean(axis=0)).max() < 1 and ((r > 7) & (r < 13)).sum() > 0.5 * len(r)
+    assert ok1 >= 18 and ok2 >= 18, (ok1, ok2)
