@@ -380,6 +380,24 @@ def addFactor(fg: FactorGraph, variables: Sequence[str], fnc, multihypo=None, nu
     return f
 
 
+def factorCanInitFromOtherVars(fg: "FactorGraph", fct: str, loovar: str, isinit=None) -> bool:
+    """factorCanInitFromOtherVars — GraphInit.jl:62-116: priors always; n-ary factors when `loovar` is the only
+    uninitialised variable; multihypo carve-out (#427, isLeastOneHypoAvailable FactorGraph.jl:772-784): solving a
+    certain variable needs at least one initialised hypothesis, solving an uncertain one needs all certain ones.
+    `isinit` (label -> bool) overrides the variables' own flags (used when a sweep is replayed on flags only)."""
+    f = fg.factors[fct]
+    init = [(fg.variables[v].initialized if isinit is None else isinit[v]) for v in f.variables]
+    fail = [v for v, i in zip(f.variables, init) if not i]
+    canuse = len(f.variables) == 1 or (len(fail) == 1 and loovar in fail)
+    if not canuse and isMultihypo(f):
+        sfidx = f.variables.index(loovar)
+        certain = [i for i, p in enumerate(f.multihypo) if p == 0.0]     # parseusermultihypo: certain -> 0.0
+        uncertn = [i for i, p in enumerate(f.multihypo) if p > 0.0]
+        canuse = (sfidx in certain and any(init[i] for i in uncertn)) or \
+                 (sfidx in uncertn and all(init[i] for i in certain))
+    return canuse
+
+
 def isInitialized(fg_or_var, lbl=None) -> bool:
     v = fg_or_var if lbl is None else fg_or_var.variables[lbl]
     return v.initialized

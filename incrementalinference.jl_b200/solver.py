@@ -221,11 +221,7 @@ def getPPE(fg: G.FactorGraph, label: str, solveKey: str = "default") -> G.MeanMa
 
 
 # --------------------------------------------------------------------------- §8f-1: graph init
-def factorCanInitFromOtherVars(fg: G.FactorGraph, fct: str, lbl: str) -> bool:
-    """GraphInit.jl:39-103: every other variable of the factor is initialised (priors always can;
-    multihypo factors need at least the certain ones — simplified to `all others`)."""
-    f = fg.factors[fct]
-    return all(fg.variables[v].initialized for v in f.variables if v != lbl)
+factorCanInitFromOtherVars = G.factorCanInitFromOtherVars      # GraphInit.jl:62-116 incl. the multihypo carve-out
 
 
 def doautoinit(fg: G.FactorGraph, lbl: str, singles: bool = True) -> bool:
@@ -269,8 +265,7 @@ def initAll(fg: G.FactorGraph, batched: bool = True) -> None:
         for l in fg.variables:
             if init[l]:
                 continue
-            use = [f for f in fg.listNeighbors(l)
-                   if all(init[v] for v in fg.factors[f].variables if v != l)]        # factorCanInitFromOtherVars
+            use = [f for f in fg.listNeighbors(l) if G.factorCanInitFromOtherVars(fg, f, l, init)]
             if not use:
                 continue
             use = use[:A.IIF_MAX_FACTORS]

@@ -401,8 +401,7 @@ def oracle_initAll(fg):
         for l, v in fg.variables.items():
             if v.initialized:
                 continue
-            use = [f for f in fg.listNeighbors(l)
-                   if all(fg.variables[w].initialized for w in fg.factors[f].variables if w != l)]
+            use = [f for f in fg.listNeighbors(l) if G.factorCanInitFromOtherVars(fg, f, l)]
             if not use:
                 continue
             spec = dict(target_slot=var_slot[l], out_slot=var_slot[l], N=N, call_id=call,

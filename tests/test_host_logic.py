@@ -195,3 +195,19 @@ def test_tree_structure_known_answer_testTreeMessageUtils():
     assert sum(1 for c in tree.cliques if "x0" in c.separators) == 3
     assert {(c.id + 1, depth[c.id]) for c in tree.cliques if "x4" in c.separators} == {(4, 2), (6, 3), (2, 1), (8, 1)}
     assert tree.cliques[6].parent == 2          # clique 7 -> clique 3
+
+
+def test_factorCanInitFromOtherVars_multihypo_carve_out():
+    """GraphInit.jl:62-116 with isLeastOneHypoAvailable (FactorGraph.jl:772-784); the cases listed in the source:
+    multihypo=[1;0.5;0.5]: sfidx=1, isinit=[0,1,0] -> true; sfidx=1, isinit=[0,0,1] -> true; sfidx=2|3, isinit=[1,0,0] -> true."""
+    fg = G.initfg(G.SolverParams(graphinit=False))
+    for l in ("x", "a", "b", "y"):
+        G.addVariable(fg, l, G.ContinuousScalar)
+    G.addFactor(fg, ["x"], G.Prior(G.Normal()), label="p")
+    G.addFactor(fg, ["x", "a", "b"], G.LinearRelative(G.Normal()), multihypo=[1.0, 0.5, 0.5], label="mh")
+    G.addFactor(fg, ["x", "y"], G.LinearRelative(G.Normal()), label="xy")
+    can = lambda f, l, **init: G.factorCanInitFromOtherVars(fg, f, l, dict(dict(x=False, a=False, b=False, y=False), **init))  # noqa: E731
+    assert can("p", "x")                                            # priors always
+    assert can("mh", "x", a=True) and can("mh", "x", b=True) and not can("mh", "x")
+    assert can("mh", "a", x=True) and can("mh", "b", x=True) and not can("mh", "a", b=True)
+    assert can("xy", "y", x=True) and not can("xy", "y") and not can("xy", "y", x=True, y=True)
