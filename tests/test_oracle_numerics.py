@@ -457,3 +457,38 @@ def test_euclid_distance_bands_testEuclidDistance():
         r = np.linalg.norm(fg.variables["x1"].val, axis=1)
         ok2 += np.abs(fg.variables["x0"].val.mean(axis=0)).max() < 1 and ((r > 7) & (r < 13)).sum() > 0.5 * len(r)
     assert ok1 >= 18 and ok2 >= 18, (ok1, ok2)
+
+
+def test_partial_prior_bands_testpartialconstraint():
+    """test/testpartialconstraint.jl:53-124: x1 in R^2 with a full prior N(0, 0.01 I) and a partial prior on
+    coordinate 1 ~ N(2, 1).  The full prior's proposal has mean[1] within 0.3 of 0; the partial proposal moves
+    coordinate 1 (mean within 0.75 of 2, far from the current values) and leaves coordinate 2 EXACTLY at the current
+    values, without touching the variable; the belief is partial; solving the graph keeps both coordinates within 0.4
+    of 0."""
+    ok = 0
+    for seed in range(20):
+        fg = G.initfg(G.SolverParams(graphinit=False, seed=seed))
+        G.addVariable(fg, "x1", G.Position(2))
+        G.addFactor(fg, ["x1"], G.Prior(G.MvNormal([0.0, 0.0], np.diag([0.01, 0.01]))), label="x1f1")
+        PC.oracle_initAll(fg)                                     # doautoinit! before the partial factor exists (:63-65)
+        G.addFactor(fg, ["x1"], G.PartialPrior(G.Normal(2.0, 1.0), (1,)), label="x1f2")
+        P = PC.Problem(sp=fg.solverParams, seed=seed)
+        X1 = fg.variables["x1"].val.copy()
+        s1 = P.slot(G.Position(2), 100, X1, fg.variables["x1"].bw)
+        f1 = P.factor(fg.factors["x1f1"].fnc, [s1])
+        f2 = P.factor(fg.factors["x1f2"].fnc, [s1])
+        P.freeze()
+        orc = P.oracle()
+        ops = CP.make_conv_ops([dict(factor=f1, sfidx=1, N=100, call_id=1), dict(factor=f2, sfidx=1, N=100, call_id=2)])
+        full, *_ = orc.conv(ops[0])
+        part, bw, ipc, _, _ = orc.conv(ops[1])
+        good = full.shape == (100, 2) and abs(full[:, 0].mean()) < 0.3
+        good &= abs(part[:, 0].mean() - 2.0) < 0.75 and np.linalg.norm(X1[:, 0] - part[:, 0]) > 2.0
+        good &= np.linalg.norm(X1[:, 1] - part[:, 1]) < 1e-10                 # untouched coordinate
+        good &= np.array_equal(orc.arena.get(s1)[0], X1)                      # the variable itself is not modified
+        good &= np.array_equal(ipc, [1.0, 0.0])                               # isPartial(X1_)
+        PC.oracle_solveTree(fg)
+        m = fg.variables["x1"].val.mean(axis=0)
+        good &= abs(m[0]) < 0.4 and abs(m[1]) < 0.4
+        ok += bool(good)
+    assert ok >= 19, ok
