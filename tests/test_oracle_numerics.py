@@ -492,3 +492,22 @@ def test_partial_prior_bands_testpartialconstraint():
         good &= abs(m[0]) < 0.4 and abs(m[1]) < 0.4
         ok += bool(good)
     assert ok >= 19, ok
+
+
+def test_mixture_prior_balance_testMixturePrior():
+    """test/testMixturePrior.jl:11-68 (#605): Mixture(Prior, [Normal(-5, 1), Normal(0, 1)], [0.5; 0.5]) — the proposal and
+    the solved marginal keep both modes in balance: |#(x < -2.5) - #(x > -2.5)| < 0.35 N.  (The reference's last variant
+    swaps the second component for an AliasingScalarSampler, which has no device sampler.)"""
+    ok = 0
+    for seed in range(20):
+        fg = G.initfg(G.SolverParams(graphinit=False, seed=seed, N=100))
+        G.addVariable(fg, "x0", G.ContinuousScalar)
+        G.addFactor(fg, ["x0"], G.Mixture(G.Prior, [G.Normal(-5.0, 1.0), G.Normal(0.0, 1.0)], [0.5, 0.5]))
+        PC.oracle_initAll(fg)                                              # approxConv(fg, :x0f1, :x0)
+        p = fg.variables["x0"].val[:, 0]
+        good = abs(int((p < -2.5).sum()) - int((p > -2.5).sum())) < 35
+        PC.oracle_solveTree(fg)
+        q = fg.variables["x0"].val[:, 0]
+        good &= abs(int((q < -2.5).sum()) - int((q > -2.5).sum())) < 35
+        ok += bool(good)
+    assert ok >= 19, ok
