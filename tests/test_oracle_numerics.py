@@ -511,3 +511,24 @@ def test_mixture_prior_balance_testMixturePrior():
         good &= abs(int((q < -2.5).sum()) - int((q > -2.5).sum())) < 35
         ok += bool(good)
     assert ok >= 19, ok
+
+
+@pytest.mark.parametrize("nullhypo", [0.0, 0.2])
+def test_n_dimensional_partials_testPartialNH(nullhypo):
+    """test/testPartialNH.jl:9-90: x0, x1 in R^3; PartialPrior on coordinates (2, 3) of x0 ~ N(0, I), PartialPrior on
+    coordinate 1 of x1 ~ N(10, 1), LinearRelative(MvNormal([10, 0, 0], I)); with and without nullhypo = 0.2 on the x0
+    prior and the relative.  After initAll! + solveTree!: x0 within 1 of [0, 0, 0], x1 within 1 (2 with nullhypo) of
+    [10, 0, 0].  The products mix full and partial proposals (coordinates nobody informs keep their old values)."""
+    ok = 0
+    for seed in range(20):
+        fg = G.initfg(G.SolverParams(graphinit=False, seed=seed, N=100))
+        G.addVariable(fg, "x0", G.Position(3))
+        G.addFactor(fg, ["x0"], G.PartialPrior(G.MvNormal(np.zeros(2), np.eye(2)), (2, 3)), nullhypo=nullhypo)
+        G.addVariable(fg, "x1", G.Position(3))
+        G.addFactor(fg, ["x1"], G.PartialPrior(G.Normal(10.0, 1.0), (1,)))
+        G.addFactor(fg, ["x0", "x1"], G.LinearRelative(G.MvNormal([10.0, 0.0, 0.0], np.eye(3))), nullhypo=nullhypo)
+        PC.oracle_initAll(fg)
+        PC.oracle_solveTree(fg)
+        m0, m1 = fg.variables["x0"].val.mean(axis=0), fg.variables["x1"].val.mean(axis=0)
+        ok += np.abs(m0).max() < 1 and np.abs(m1 - [10.0, 0.0, 0.0]).max() < (1 if nullhypo == 0 else 2)
+    assert ok >= 18, ok
