@@ -532,3 +532,20 @@ def test_n_dimensional_partials_testPartialNH(nullhypo):
         m0, m1 = fg.variables["x0"].val.mean(axis=0), fg.variables["x1"].val.mean(axis=0)
         ok += np.abs(m0).max() < 1 and np.abs(m1 - [10.0, 0.0, 0.0]).max() < (1 if nullhypo == 0 else 2)
     assert ok >= 18, ok
+
+
+def test_translation_group_manifold_factors_testTranslationMani():
+    """test/testTranslationMani.jl:7-38 (a smoke test there): ManifoldPrior(TranslationGroup(2), [10, 20], MvNormal([1, 1]))
+    and ManifoldFactor(TranslationGroup(2), MvNormal([1, 2], [0.1, 0.1])) initialise and solve; here also located:
+    x0 near [10, 20], x1 near [11, 22]."""
+    M = G.TranslationGroup(2)
+    fg = G.initfg(G.SolverParams(graphinit=False, seed=2))
+    G.addVariable(fg, "x0", M)
+    G.addVariable(fg, "x1", M)
+    G.addFactor(fg, ["x0"], G.ManifoldPrior(M, [10.0, 20.0], G.MvNormal([0.0, 0.0], np.eye(2))))
+    f = G.addFactor(fg, ["x0", "x1"], G.ManifoldFactor(M, G.MvNormal([1.0, 2.0], np.diag([0.1, 0.1]))))
+    assert f.fnc.kind == A.F_LINEAR_RELATIVE and fg.factors["x0f1"].fnc.kind == A.F_MANIFOLD_PRIOR
+    PC.oracle_initAll(fg)
+    PC.oracle_solveTree(fg)
+    assert np.abs(fg.variables["x0"].val.mean(axis=0) - [10.0, 20.0]).max() < 0.5
+    assert np.abs(fg.variables["x1"].val.mean(axis=0) - [11.0, 22.0]).max() < 0.7
