@@ -39,6 +39,16 @@ Circular = InferenceVariable("Circular", 1, 1)  # DefaultVariables.jl:52  RealCi
 SpecialEuclidean2 = InferenceVariable("SpecialEuclidean2", 3, 0b100)
 
 
+# @defVariable SpecialOrthogonal2 SpecialOrthogonal(2) (test/testSpecialOrthogonalMani.jl:19): a rotation matrix is its
+# angle atan2(R21, R11) on the device — the same single circular coordinate as Circular / RealCircleGroup
+SpecialOrthogonal2 = InferenceVariable("SpecialOrthogonal2", 1, 1)
+
+
+def so2_point_to_coords(R) -> np.ndarray:
+    R = np.asarray(R, dtype=np.float64)
+    return np.array([np.arctan2(R[1, 0], R[0, 0])])
+
+
 def TranslationGroup(n: int) -> InferenceVariable:
     return Position(n)
 

@@ -549,3 +549,25 @@ def test_translation_group_manifold_factors_testTranslationMani():
     PC.oracle_solveTree(fg)
     assert np.abs(fg.variables["x0"].val.mean(axis=0) - [10.0, 20.0]).max() < 0.5
     assert np.abs(fg.variables["x1"].val.mean(axis=0) - [11.0, 22.0]).max() < 0.7
+
+
+def test_special_orthogonal2_testSpecialOrthogonalMani():
+    """test/testSpecialOrthogonalMani.jl:12-58: ManifoldPrior(SpecialOrthogonal(2), I, MvNormal([0.01])) initialises x0
+    at the identity (atol 0.1); ManifoldFactor(SpecialOrthogonal(2), MvNormal([pi], [0.01])) puts x1 half a turn away;
+    the tree solve runs.  SO(2) points are carried as their angle."""
+    M = G.SpecialOrthogonal2
+    fg = G.initfg(G.SolverParams(graphinit=False, seed=4))
+    G.addVariable(fg, "x0", M)
+    G.addFactor(fg, ["x0"], G.ManifoldPrior(M, G.so2_point_to_coords(np.eye(2)), G.Normal(0.0, 0.01)))
+    PC.oracle_initAll(fg)
+    th = fg.variables["x0"].val[:, 0]
+    Rm = np.array([[np.cos(th).mean(), -np.sin(th).mean()], [np.sin(th).mean(), np.cos(th).mean()]])
+    assert np.allclose(Rm, np.eye(2), atol=0.1)
+    G.addVariable(fg, "x1", M)
+    f = G.addFactor(fg, ["x0", "x1"], G.ManifoldFactor(M, G.Normal(np.pi, 0.1)))
+    assert f.fnc.kind == A.F_CIRCULAR_CIRCULAR
+    PC.oracle_initAll(fg)
+    PC.oracle_solveTree(fg)
+    t0, t1 = fg.variables["x0"].val[:, 0], fg.variables["x1"].val[:, 0]
+    assert np.all(np.abs(t1) <= np.pi) and abs(np.arctan2(np.sin(t0).mean(), np.cos(t0).mean())) < 0.1
+    assert np.cos(t1).mean() < -0.9                                   # x1 sits at +-pi (the seam)
