@@ -42,7 +42,7 @@ def _worker(rank, world, port, n, ret):
     orc = O.Oracle(plan.frozen, arena, sp)
     props, ops = CP.make_prop_ops(plan.props), CP.make_sched_ops(my_ops)
     nw = len(plan.wave_off) - 1
-    comm = sorted({t[0] for t in transfers})
+    comm = sorted({t[0] for t in transfers if rank in (t[2], t[3])})     # as ShardedTreeSolver: own exchange waves only
     slots = plan.frozen["slots"]
 
     def exchange(w):
@@ -99,6 +99,18 @@ def test_sharded_solve_matches_single_process(built, n):
         assert ret["nvars"] == n
         assert 0 < ret["ntransfers"] <= 16      # only the cut's separator messages cross ranks
         assert min(ret["split"]) > 0.3 * max(ret["split"])   # both ranks carry a real share
+
+
+def test_sharded_solve_world4_matches_single_process(built):
+    """four ranks: some exchange waves involve only two of them, the others must not wait there"""
+    import torch.multiprocessing as mp
+    n = 96
+    port = 29500 + (os.getpid() + 7 * n) % 1000
+    with mp.Manager() as man:
+        ret = man.dict()
+        mp.spawn(_worker, args=(4, port, n, ret), nprocs=4, join=True)
+        assert ret["ok"], "sharded solve differs from the single-process solve"
+        assert ret["nvars"] == n and min(ret["split"]) > 0
 
 
 def test_partition_properties():
