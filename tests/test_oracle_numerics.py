@@ -571,3 +571,24 @@ def test_special_orthogonal2_testSpecialOrthogonalMani():
     t0, t1 = fg.variables["x0"].val[:, 0], fg.variables["x1"].val[:, 0]
     assert np.all(np.abs(t1) <= np.pi) and abs(np.arctan2(np.sin(t0).mean(), np.cos(t0).mean())) < 0.1
     assert np.cos(t1).mean() < -0.9                                   # x1 sits at +-pi (the seam)
+
+
+def test_four_equal_peaks_testMultiHypo3Door():
+    """test/testMultiHypo3Door.jl:40-99: x0 sees one of four doors (landmarks at 0, 10, 20, 40, sigma 0.01) through a
+    5-ary LinearRelative(Normal(0, 0.25)) with multihypo = [1, 1/4, 1/4, 1/4, 1/4], N = 200: the proposal has four
+    peaks, its KDE exceeds 0.1 at every door (:96-99), and the convolution leaves x0 itself untouched (:80-90)."""
+    def dens(pts, bw, x):
+        return np.mean(np.exp(-0.5 * ((x - pts) / bw) ** 2) / (np.sqrt(2 * np.pi) * bw))
+    ok = 0
+    for seed in range(20):
+        R = np.random.default_rng(seed)
+        P = PC.Problem(sp=G.SolverParams(N=200), seed=seed)
+        ls = [P.slot(G.ContinuousScalar, 200, R.normal(m, 0.01, (200, 1))) for m in (0.0, 10.0, 20.0, 40.0)]
+        x0 = P.slot(G.ContinuousScalar, 200, np.zeros((0, 1)), initialized=False)
+        f = P.factor(G.LinearRelative(G.Normal(0.0, 0.25)), [x0] + ls, mh=[1.0, 0.25, 0.25, 0.25, 0.25])
+        P.freeze()
+        orc = P.oracle()
+        pts, bw, ipc, lab, _ = orc.conv(CP.make_conv_ops([dict(factor=f, sfidx=1, N=200, call_id=3)])[0])
+        ok += all(dens(pts[:, 0], bw[0], l) > 0.1 for l in (0.0, 10.0, 20.0, 40.0)) and orc.arena.npts[x0] == 0 \
+            and set(np.unique(lab)) == {2, 3, 4, 5}
+    assert ok >= 19, ok
