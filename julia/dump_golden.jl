@@ -49,4 +49,20 @@ dump_case("scalar_relative_bwd", fg, :x0x1f1, :x0)
 mkd, ipc = propagateBelief(fg, :x0, :)
 writedlm(joinpath(out, "product_x0_posterior.csv"), reduce(hcat, [collect(Float64, p) for p in getPoints(mkd, false)])', ',')
 writedlm(joinpath(out, "product_x0_bw.csv"), getBW(mkd)[:, 1], ',')
+# case 3: separated modes (test/testMultiHypo3Door.jl:40-124) - does the one-sweep multiscale Gibbs product lock onto
+# node pairs that only overlap at a coarse level?  Dump both proposals of x1 and the posterior of their product.
+fg3 = initfg(); getSolverParams(fg3).N = 200; getSolverParams(fg3).graphinit = false
+for (k, l) in enumerate((0.0, 10.0, 20.0, 40.0))
+  addVariable!(fg3, Symbol("l$(k-1)"), ContinuousScalar)
+  addFactor!(fg3, [Symbol("l$(k-1)")], Prior(Normal(l, 0.01)))
+end
+addVariable!(fg3, :x0, ContinuousScalar); addVariable!(fg3, :x1, ContinuousScalar)
+addFactor!(fg3, [:x0; :l0; :l1; :l2; :l3], LinearRelative(Normal(0, 0.25)), multihypo = [1.0; 0.25; 0.25; 0.25; 0.25])
+addFactor!(fg3, [:x0; :x1], LinearRelative(Normal(10.0, 0.1)))
+addFactor!(fg3, [:x1; :l0; :l1; :l2; :l3], LinearRelative(Normal(0, 0.25)), multihypo = [1.0; 0.25; 0.25; 0.25; 0.25])
+initAll!(fg3)
+dump_case("door_odometry_to_x1", fg3, :x0x1f1, :x1)
+dump_case("door_multihypo_to_x1", fg3, :x1l0l1l2l3f1, :x1)
+mkd3, = propagateBelief(fg3, :x1, :)
+writedlm(joinpath(out, "door_x1_posterior.csv"), reduce(hcat, [collect(Float64, p) for p in getPoints(mkd3, false)])', ',')
 println("wrote golden vectors to ", out)
