@@ -84,7 +84,7 @@ class ClockSampler:
 def ncu_traffic_per_block():
     """DRAM bytes per convolution (CTA) of iif_conv_kernel from the committed `ncu --set full` capture
     (profiles/r01_kernels.json, written by profiles/summarise.py); None when no capture is committed."""
-    p = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r01b_kernels.json", "r01_kernels.json"))
+    p = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r02_kernels.json", "r01b_kernels.json", "r01_kernels.json"))
               if os.path.exists(q)), None)
     if p is None:
         return None, None
@@ -111,6 +111,20 @@ def conv_bytes(plan):
     return tot
 
 
+def make_config(n_poses, world, order_kind, plan, lanes):
+    """the workload both arms run (identical dict in the b200 and the reference line)"""
+    return {"workload": f"{n_poses}-pose ContinuousScalar odometry chain (Prior + LinearRelative), N={NPART}, "
+                        f"one solveTree pass = {plan.n_conv} convolutions + {plan.n_prod} products",
+            "poses": n_poses, "N": NPART, "elimination_order": order_kind, "waves": len(plan.wave_off) - 1,
+            "l2": "b200 arm: flushed between timed steps (256 MiB write); reference arm: host caches, not flushed",
+            "rng": "Philox4x32-10 streams, new seed every step (device-drawn in the b200 arm)",
+            "schedule": f"b200 arm: one CUDA graph per pass, {lanes} lanes (independent sub-trees as parallel graph "
+                        "branches), separator copies forwarded; reference arm: the same plan, OpenMP over the "
+                        "independent ops of a wave",
+            "sharding": "1 GPU" if world == 1 else f"{world} contiguous {POSES_PER_GPU}-pose segments, separator "
+                                                    "messages between ranks"}
+
+
 def build_workload(n_poses, order_kind):
     import iifb200  # noqa: F401
     from iifb200 import workloads as W
@@ -134,7 +148,7 @@ def run_reference_julia(args):
     if not ok:
         return None
     cores = os.cpu_count() or 1
-    n_sample = 100
+    n_sample = POSES_PER_GPU          # the metric's configuration, not a reduced one
     from iifb200 import tree as TR
     fg, order = build_workload(n_sample, args.order)
     n_conv = TR.compile_solve(fg, TR.buildTree(fg, order)).n_conv      # the unit count both arms are divided into
@@ -152,8 +166,7 @@ def run_reference_julia(args):
             "unit": "conv/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(r["seconds"]) / max(int(r["solves"]), 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{POSES_PER_GPU}-pose ContinuousScalar odometry chain, N={NPART} (bounded sample: {n_sample} poses)",
-                       "elimination_order": args.order, "N": NPART},
+            "config": make_config(POSES_PER_GPU, 1, args.order, TR.compile_solve(fg, TR.buildTree(fg, order), lanes=4), 4),
             "cpu_baseline": {"value": val, "unit": "conv/s", "cores": int(r["threads"]), "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": "conv/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "note": "unmodified IncrementalInference.jl solveTree!(; multithread=true) via baseline/ref_solve.jl"}
@@ -179,10 +192,17 @@ def run_reference(args, rank, world):
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
     except OSError:
         cores = 1
-    n_sample = 100  # poses in the bounded sample (same chain kind, same N, same elimination-order kind)
-    fg, order = build_workload(n_sample, args.order)
+    # The metric's configuration itself: the full 1000-pose chain, same nested-dissection order, same plan (waves of
+    # independent ops) the device runs, all host threads.  Under torchrun (N > 1) the b200 arm solves an N x 1000-pose
+    # chain; the CPU arm times one 1000-pose segment per step (conv/s on the CPU does not depend on the chain length).
+    n_poses = POSES_PER_GPU
+    fg, order = build_workload(n_poses, args.order)
     tree = TR.buildTree(fg, order)
-    plan = TR.compile_solve(fg, tree)
+    plan = TR.compile_solve(fg, tree, lanes=4)
+    cfg_plan = plan
+    if world > 1:
+        fgN, orderN = build_workload(POSES_PER_GPU * world, args.order)
+        cfg_plan = TR.compile_solve(fgN, TR.buildTree(fgN, orderN), lanes=4)
     base = CP.HostArena(plan.frozen)
     for l, v in fg.variables.items():
         base.set(plan.var_slot[l], v.val, v.bw, True)
@@ -198,14 +218,14 @@ def run_reference(args, rank, world):
             times.append(dt)
     tot = sum(times)
     val = plan.n_conv * len(times) / tot
-    sample = f"{len(times)} solves of a {n_sample}-pose chain of the same kind ({plan.n_conv} convolutions each)"
+    sample = (f"{len(times)} full solves of the {n_poses}-pose chain ({plan.n_conv} convolutions + {plan.n_prod} products "
+              f"each), {cores} OpenMP threads" + ("" if world == 1 else f"; one {n_poses}-pose segment of the {world}-GPU workload per step"))
     out = {
         "impl": "reference", "metric": "clique belief convolutions/sec (N=100 particles)", "value": val,
         "unit": "conv/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{POSES_PER_GPU}-pose ContinuousScalar odometry chain, N={NPART} (bounded sample: {n_sample} poses)",
-                   "elimination_order": args.order, "N": NPART},
+        "config": make_config(POSES_PER_GPU * world, world, args.order, cfg_plan, 4),
         "cpu_baseline": {"value": val, "unit": "conv/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "conv/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -216,30 +236,62 @@ def run_reference(args, rank, world):
 
 # ----------------------------------------------------------------------------- b200 arm
 def cpu_baseline_sample(order_kind):
-    """oracle port, 1 thread, bounded sample (rank 0, N=1 only)"""
+    """oracle port on the host cores of the GPU box: full solves of the metric's 1000-pose chain (same plan the
+    device runs), all OpenMP threads, repeated for >= 10 s (rank 0, N=1 only)"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ctypes
     import oracle as O
     from iifb200 import compile as CP
     from iifb200 import tree as TR
+    cores = os.cpu_count() or 1
     try:
-        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(1)
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
     except OSError:
-        pass
-    n_sample = 100
-    fg, order = build_workload(n_sample, order_kind)
-    plan = TR.compile_solve(fg, TR.buildTree(fg, order))
+        cores = 1
+    fg, order = build_workload(POSES_PER_GPU, order_kind)
+    plan = TR.compile_solve(fg, TR.buildTree(fg, order), lanes=4)
+    base = CP.HostArena(plan.frozen)
+    for l, v in fg.variables.items():
+        base.set(plan.var_slot[l], v.val, v.bw, True)
+    ops, props = CP.make_sched_ops(plan.sched_waved), CP.make_prop_ops(plan.props)
+    nrep, spent = 0, 0.0
+    while spent < 10.0:
+        orc = O.Oracle(plan.frozen, base.copy(), CP.solver_params_c(fg.solverParams, 42 + nrep))
+        t0 = time.perf_counter()
+        orc.schedule_run(plan.wave_off, ops, props)
+        spent += time.perf_counter() - t0
+        nrep += 1
+    return {"value": plan.n_conv * nrep / spent, "unit": "conv/s", "cores": cores, "kind": "port",
+            "sample": f"{nrep} full solves of the {POSES_PER_GPU}-pose chain ({plan.n_conv} convolutions + {plan.n_prod} "
+                      f"products each), {cores} OpenMP threads, {spent:.1f} s"}
+
+
+def posterior_check(fg, plan, seed, gpu_pts):
+    """parity and sanity of the LAST end-to-end step, inside the bench: the oracle runs the same plan with the same
+    seed (checker, not measured) and the posterior means are compared with the analytic pose positions"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from iifb200 import compile as CP
+    n = len(fg.variables)
     ar = CP.HostArena(plan.frozen)
     for l, v in fg.variables.items():
         ar.set(plan.var_slot[l], v.val, v.bw, True)
-    orc = O.Oracle(plan.frozen, ar, CP.solver_params_c(fg.solverParams))
-    nrep, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < 12.0:
-        orc.schedule_run(plan.wave_off, CP.make_sched_ops(plan.sched_waved), CP.make_prop_ops(plan.props))
-        nrep += 1
-    dt = time.perf_counter() - t0
-    return {"value": plan.n_conv * nrep / dt, "unit": "conv/s", "cores": 1, "kind": "port",
-            "sample": f"{nrep} solves of a {n_sample}-pose chain of the same kind ({plan.n_conv} convolutions each), 1 thread"}
+    orc = O.Oracle(plan.frozen, ar, CP.solver_params_c(fg.solverParams, seed))
+    orc.schedule_run(plan.wave_off, CP.make_sched_ops(plan.sched_waved), CP.make_prop_ops(plan.props))
+    op = ar.pts[:n * NPART].reshape(n, NPART)
+    gp = gpu_pts.reshape(n, NPART)
+    same = np.abs(op - gp) <= 1e-9 * np.maximum(1.0, np.abs(op))
+    err = gp.mean(axis=1) - np.arange(n)
+    sig = 0.1 * np.sqrt(np.arange(n) + 1.0)          # analytic marginal: prior 0.1, odometry 0.1 per step
+    worst = np.argsort(-np.abs(err))[:3]
+    return {"vs_oracle": {"points_within_1e-9": float(same.mean()), "poses_all_points_equal": int(same.all(axis=1).sum()),
+                          "max_abs_mean_diff": float(np.abs(op.mean(axis=1) - gp.mean(axis=1)).max())},
+            "vs_analytic": {"mean_abs_err_median": float(np.median(np.abs(err))), "mean_abs_err_max": float(np.abs(err).max()),
+                            "max_err_over_sigma": float((np.abs(err) / sig).max()),
+                            "worst_poses": [[int(k), float(err[k]), float(gp[k].std()), float(sig[k])] for k in worst],
+                            "columns": "pose, mean error, posterior std, analytic std",
+                            "note": "useMsgLikelihoods=false (the default): separator messages are plain priors, so "
+                                    "beliefs far from the x0 prior are over-confident relative to the analytic marginal"}}
 
 
 def run_b200(args, rank, world, local_rank):
@@ -353,6 +405,8 @@ def run_b200(args, rank, world, local_rank):
         e2e_s += time.perf_counter() - t0
     clocks = sampler.stop()
     post_mean_err = float(np.abs(hp.reshape(nvars, NPART).mean(axis=1) - np.arange(nvars)).max())
+    last_pts = hp.copy()
+    last_seed = 42 + 100 + args.steps - 1
 
     # max over ranks
     if dist is not None:
@@ -403,13 +457,7 @@ def run_b200(args, rank, world, local_rank):
         "metric": "clique belief convolutions/sec (N=100 particles)", "value": val, "unit": "conv/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n_poses}-pose ContinuousScalar odometry chain (Prior + LinearRelative), N={NPART}, "
-                               f"one solveTree pass = {total_conv} convolutions + {plan.n_prod} products",
-                   "poses": n_poses, "N": NPART, "elimination_order": args.order, "waves": len(plan.wave_off) - 1,
-                   "l2": "flushed between timed steps (256 MiB write)", "rng": "device Philox4x32-10, new seed every step",
-                   "schedule": f"one CUDA graph per pass, {max(plan.op_lane) if runner is None else max(runner.lanes)} lanes "
-                               "(independent sub-trees as parallel graph branches), separator copies forwarded",
-                   "sharding": "1 GPU" if world == 1 else f"{world} contiguous 1000-pose segments, NCCL separator messages"},
+        "config": make_config(n_poses, world, args.order, plan, max(plan.op_lane) if runner is None else max(runner.lanes)),
         "e2e": {"value": total_conv * args.steps / e2e_s, "unit": "conv/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
@@ -418,6 +466,8 @@ def run_b200(args, rank, world, local_rank):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
+    if world == 1 and not args.no_cpu_baseline:
+        out["posterior_check"] = posterior_check(fg, plan, last_seed, last_pts)
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -54,7 +54,7 @@ extern "C" {
 
 #define IIF_MAX_DIM 4           /* max variable dimension handled by the kernels */
 #define IIF_MAX_ARITY 6         /* max variables per factor (four-door multihypo uses 5) */
-#define IIF_MAX_FACTORS 8       /* max factors contributing to one propagateBelief */
+#define IIF_MAX_FACTORS 16      /* max factors contributing to one propagateBelief (more: IIF_ERR_ARG, never truncated) */
 #define IIF_MAX_POINTS 256      /* max particles per belief (kernel shared-memory budget) */
 
 /* status codes */
@@ -238,7 +238,11 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops,
 /* V independent KDE products (AMP.manifoldProduct).  Inputs HOST buffers:
  *   dens_pts  packed F_v x N x d proposals per product, dens_bw F_v x IIF_MAX_DIM,
  *   dens_mask F_v partial masks (0 = full), old_pts N x d,
- *   randU / randN optional explicit Gibbs streams (NULL => Philox from call_id). */
+ *   randU / randN optional explicit Gibbs streams (NULL => Philox from call_id), the analogue of AMP.manifoldProduct's
+ *   `_randU` / `_randN` keyword vectors.  With L = floor(log2(N) + 1) levels and Niter Gibbs sweeps per level, output
+ *   sample s owns randU[s*F*(1 + L*(Niter+1)) ...]: F uniforms for initIndices, then per level F for sampleIndices
+ *   (labels given the point) and Niter*F for sampleIndex (labels given the other densities' labels); and
+ *   randN[s*d*(L+1) ...]: d normals for the samplePoint of every level and d for the final sample. */
 typedef struct {
   int32_t dim, circ_mask, nfactors, N;
   int32_t call_id;

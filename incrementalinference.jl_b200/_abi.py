@@ -9,7 +9,7 @@ import os
 
 IIF_MAX_DIM = 4
 IIF_MAX_ARITY = 6
-IIF_MAX_FACTORS = 8
+IIF_MAX_FACTORS = 16
 IIF_MAX_POINTS = 256
 
 IIF_OK, IIF_ERR_ARG, IIF_ERR_CUDA, IIF_ERR_UNSUPPORTED, IIF_ERR_STATE = 0, -1, -2, -3, -4

@@ -271,6 +271,134 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     int node[IIF_MAX_FACTORS];
     for (int j = 0; j < F; ++j) node[j] = 0;  // roots
     const bool tab = (F == 2) && gibbs_tab(N);
+    // Random-stream layout (AMP.manifoldProduct `_randU` / `_randN`; KDE.jl sizes them Np*Ndens*(Niter+2)*Nlevels and
+    // Ndim*Np*(Nlevels+1)): per output sample the uniforms go to initIndices (F), then per level to sampleIndices (F)
+    // and Niter sweeps of sampleIndex (F each); the normals are the Nlevels+1 samplePoint draws (d each).
+    const uint32_t ublk = (uint32_t)(F * (1 + L * (niter + 1))), nblk = (uint32_t)(d * (L + 1));
+    auto gibbs_u = [&](uint32_t idx) -> double {
+      return (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx] : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
+    };
+    auto gibbs_n = [&](uint32_t idx) -> double {
+      return (randN != nullptr && t.randn_off >= 0) ? randN[t.randn_off + idx] : rs_normal(seed, call, IIF_RS_GIBBS_N, idx);
+    };
+    // samplePoint: a point from the product of the currently selected Gaussians (every lane of a group computes it)
+    auto sample_point = [&](int l, double* X) {
+      for (int c = 0; c < d; ++c) {
+        double mu = 0;
+        const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, -1, nn, d, c, is_circ(cm, c), mu);
+        X[c] = lam > 0 ? madd(mu, sqrt(1.0 / lam) * gibbs_n((uint32_t)s * nblk + (uint32_t)((l - 1) * d + c)), is_circ(cm, c)) : 0.0;
+      }
+    };
+    // Label draw of density j at level l given a Gaussian (cmu, cvar) per coordinate (`has[c]`: coordinate takes part):
+    // weight_z = wt_z * prod_c rsqrt(v) * exp(-1/2 sum_c dl^2 / v),  v = var_z + cvar  (the oracle's
+    // exp(-(p_z - min p)/2) with p_z = sum dl^2/v + log v, up to the common factor).  sampleIndex(j) passes the product
+    // of the other densities' selected nodes, sampleIndices passes the point X with cvar = 0.  The G lanes of the
+    // sample's group own contiguous blocks of candidates, accumulate chunk sums in registers, a group scan locates the
+    // lane and chunk holding the inverse-CDF crossing and only that chunk is re-evaluated.  Weights are relative to an
+    // analytic lower bound of the exponent (single pass); exact-minimum fallback when every weight underflows.
+    auto draw_label = [&](int j, int l, const double* cmu, const double* cvar, const bool* has, double u) -> int {
+      const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
+      const bool leaf = (l == L);
+      const int B = (nz + G - 1) / G;
+      const int zb = gl * B, ze = min(zb + B, nz);
+      const int CH = (B + 15) >> 4;  // <= 16 chunks per lane; CH == 1 (B <= 16) needs no re-evaluation
+      const double* mj = sm.mean + ((size_t)j * nn + z0) * d;
+      const double* vj = sm.var + ((size_t)j * nn + z0) * d;
+      const double* wj = sm.wt + z0;
+      // at the leaf level v is the same for every candidate, so 1/v is hoisted and rsqrt(v) cancels
+      double iv[IIF_MAX_DIM] = {0, 0, 0, 0};
+      for (int c = 0; c < d; ++c)
+        if (has[c] && leaf) iv[c] = 1.0 / (vj[c] + cvar[c]);
+      auto cand = [&](int z, double& pre) -> double {  // exponent (>= 0) and prefactor of candidate z
+        double p = 0.0;
+        pre = wj[z];
+        for (int c = 0; c < d; ++c) {
+          if (!has[c]) continue;
+          const double dl = mdiff(mj[z * d + c], cmu[c], is_circ(cm, c));
+          if (leaf) p = fma(dl * dl, iv[c], p);
+          else {
+            const double rs = rsqrt(vj[z * d + c] + cvar[c]);
+            p = fma(dl * dl, rs * rs, p);
+            pre *= rs;
+          }
+        }
+        return p;
+      };
+      auto weight = [&](int z, double base) -> double {
+        double pre;
+        const double p = cand(z, pre);
+        return exp_neg(fmin(-0.5 * (p - base), 0.0)) * pre;
+      };
+      double ct[16];
+      double Tl = 0.0, off = 0.0, tot = 0.0, base = 0.0;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        Tl = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          const int cb = zb + ch * CH;
+          double sacc = 0.0;
+          if (cb < ze) {
+            const int ce = min(cb + CH, ze);
+            for (int z = cb; z < ce; ++z) sacc += weight(z, base);
+          }
+          ct[ch] = sacc;
+          Tl += sacc;
+        }
+        double inc = Tl;  // inclusive scan over the group's lanes
+        for (int o = 1; o < G; o <<= 1) {
+          const double y = __shfl_up_sync(gmask, inc, o, G);
+          if (gl >= o) inc += y;
+        }
+        off = inc - Tl;
+        tot = __shfl_sync(gmask, inc, G - 1, G);
+        if (tot > 1e-280 || attempt == 1) break;
+        // every weight underflowed: redo relative to the exact minimum exponent
+        double pm = INFINITY;
+        for (int z = zb; z < ze; ++z) { double pre; pm = fmin(pm, cand(z, pre)); }
+        for (int o = G >> 1; o > 0; o >>= 1) pm = fmin(pm, __shfl_xor_sync(gmask, pm, o, G));
+        base = pm;
+      }
+      const double thr = u * tot;
+      // every lane searches its own chunks (no divergent owner path); exactly one lane finds the crossing
+      int mypick = -1;
+      if ((zb < ze) && (thr >= off) && (thr < off + Tl)) {
+        double run = off;
+        mypick = ze - 1;
+        bool found = false;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          const int cb = zb + ch * CH;
+          if (!found && cb < ze) {
+            if (thr < run + ct[ch]) {
+              const int ce = min(cb + CH, ze);
+              mypick = ce - 1;
+              if (CH > 1) {
+                double cum = run;
+                for (int z = cb; z < ce; ++z) {
+                  cum += weight(z, base);
+                  if (thr < cum) { mypick = z; break; }
+                }
+              }
+              found = true;
+            }
+            run += ct[ch];
+          }
+        }
+      }
+      const unsigned hit = __ballot_sync(gmask, mypick >= 0) & gmask;
+      int pick = nz - 1;  // rounding left thr >= total: the oracle falls back to the last candidate
+      if (hit) pick = __shfl_sync(gmask, mypick, (__ffs(hit) - 1) & (G - 1), G);
+      return z0 + pick;
+    };
+    // sampleIndices(X): the label of every density given the point X, over the whole level list
+    auto sample_indices = [&](int l, const double* X) {
+      const double zero[IIF_MAX_DIM] = {0, 0, 0, 0};
+      for (int j = 0; j < F; ++j) {
+        bool has[IIF_MAX_DIM];
+        for (int c = 0; c < IIF_MAX_DIM; ++c) has[c] = c < d && ((masks[j] >> c) & 1);
+        node[j] = draw_label(j, l, X, zero, has, gibbs_u((uint32_t)s * ublk + (uint32_t)(F + (l - 1) * F * (niter + 1) + j)));
+      }
+    };
     if (tab) {
       // ---- F == 2: the conditional of one density depends only on the node selected in the other, so the
       // level's pair-weight matrix K[a][b] = prod_c rsqrt(va+vb) exp(-(ma-mb)^2 / 2(va+vb)) is tabulated ONCE
@@ -284,10 +412,10 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
       const double* v1 = sm.var + (size_t)nn * d;
       for (int l = 1; l <= L; ++l) {
         const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
-        for (int j = 0; j < 2; ++j) {  // levelDown: follow the last child, leaves stay
-          const int nd = node[j];
-          node[j] = z0 + T.child[nd] + (T.hi[nd] > T.lo[nd] ? 1 : 0);
-        }
+        // samplePoint from the product of the nodes selected at the coarser level; levelDown then replaces every
+        // level list by its children (leaves stay) and sampleIndices re-draws every label over the new list
+        double X[IIF_MAX_DIM] = {0, 0, 0, 0};
+        if (live) sample_point(l, X);
         __syncthreads();  // the previous level's K is no longer read
         if (l == L && d == 1 && !is_circ(cm, 0)) {
           // leaf level, one Euclid coordinate: every node is a single kernel of variance h_j^2, so the table is
@@ -340,6 +468,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         __syncthreads();
         IIF_PHASE(7);
         if (live) {
+          sample_indices(l, X);
           const double* wl = sm.wt + z0;
           const int B = (nz + G - 1) / G;
           const int zb = gl * B, ze = min(zb + B, nz);
@@ -350,9 +479,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
               const int other = node[1 - j] - z0;
               const double* Kb = (j == 0) ? K + other : K + (size_t)other * nz;
               const int stride = (j == 0) ? nz : 1;
-              const uint32_t idx = (uint32_t)(((s * L + (l - 1)) * niter + it) * 2 + j);
-              const double u = (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx]
-                                                                      : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
+              const double u = gibbs_u((uint32_t)s * ublk + (uint32_t)(2 + (l - 1) * 2 * (niter + 1) + 2 + it * 2 + j));
               IIF_PHASE(16);
               // chunk sums: eight independent accumulation chains
               double ct[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -427,17 +554,11 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
       __syncthreads();  // K (aliases the leave-one-out scratch) is dead from here on
     } else if (live) {
       for (int l = 1; l <= L; ++l) {
-        const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
-        const bool leaf = (l == L);
-        for (int j = 0; j < F; ++j) {  // levelDown: follow the last child (KDE.jl levelDown!), leaves stay
-          const int nd = node[j];
-          node[j] = z0 + T.child[nd] + (T.hi[nd] > T.lo[nd] ? 1 : 0);
-        }
-        const int B = (nz + G - 1) / G;
-        const int zb = gl * B, ze = min(zb + B, nz);
-        const int CH = (B + 15) >> 4;  // <= 16 chunks per lane; CH == 1 (B <= 16) needs no re-evaluation
+        double X[IIF_MAX_DIM] = {0, 0, 0, 0};
+        sample_point(l, X);      // samplePoint, then levelDown (implicit) and sampleIndices over the new level list
+        sample_indices(l, X);
         for (int it = 0; it < niter; ++it) {
-          for (int j = 0; j < F; ++j) {  // sampleIndex(j)
+          for (int j = 0; j < F; ++j) {  // sampleIndex(j): label given the other densities' selected nodes
             double cmu[IIF_MAX_DIM] = {0, 0, 0, 0}, cvar[IIF_MAX_DIM] = {0, 0, 0, 0};
             bool has[IIF_MAX_DIM] = {false, false, false, false};
             for (int c = 0; c < d; ++c) {
@@ -446,100 +567,8 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
               has[c] = lam > 0;
               cvar[c] = has[c] ? 1.0 / lam : 0.0;
             }
-            const double* mj = sm.mean + ((size_t)j * nn + z0) * d;
-            const double* vj = sm.var + ((size_t)j * nn + z0) * d;
-            const double* wj = sm.wt + z0;
-            // weight_z = wt_z * prod_c rsqrt(v) * exp(-1/2 sum_c dl^2 / v),  v = var_z + cvar  (the oracle's
-            // exp(-(p_z - min p)/2) with p_z = sum dl^2/v + log v, up to the common factor).  At the leaf
-            // level v is the same for every candidate, so 1/v is hoisted and rsqrt(v) cancels.
-            double iv[IIF_MAX_DIM] = {0, 0, 0, 0};
-            for (int c = 0; c < d; ++c)
-              if (has[c] && leaf) iv[c] = 1.0 / (vj[c] + cvar[c]);
-            // returns the exponent (>= 0) and the prefactor of candidate z
-            auto cand = [&](int z, double& pre) -> double {
-              double p = 0.0;
-              pre = wj[z];
-              for (int c = 0; c < d; ++c) {
-                if (!has[c]) continue;
-                const double dl = mdiff(mj[z * d + c], cmu[c], is_circ(cm, c));
-                if (leaf) p = fma(dl * dl, iv[c], p);
-                else {
-                  const double rs = rsqrt(vj[z * d + c] + cvar[c]);
-                  p = fma(dl * dl, rs * rs, p);
-                  pre *= rs;
-                }
-              }
-              return p;
-            };
-            auto weight = [&](int z, double base) -> double {
-              double pre;
-              const double p = cand(z, pre);
-              return exp_neg(fmin(-0.5 * (p - base), 0.0)) * pre;
-            };
-            double ct[16];
-            double Tl = 0.0, off = 0.0, tot = 0.0, base = 0.0;
-            for (int attempt = 0; attempt < 2; ++attempt) {
-              Tl = 0.0;
-#pragma unroll
-              for (int ch = 0; ch < 16; ++ch) {
-                const int cb = zb + ch * CH;
-                double sacc = 0.0;
-                if (cb < ze) {
-                  const int ce = min(cb + CH, ze);
-                  for (int z = cb; z < ce; ++z) sacc += weight(z, base);
-                }
-                ct[ch] = sacc;
-                Tl += sacc;
-              }
-              // inclusive scan over the group's lanes
-              double inc = Tl;
-              for (int o = 1; o < G; o <<= 1) {
-                const double y = __shfl_up_sync(gmask, inc, o, G);
-                if (gl >= o) inc += y;
-              }
-              off = inc - Tl;
-              tot = __shfl_sync(gmask, inc, G - 1, G);
-              if (tot > 1e-280 || attempt == 1) break;
-              // every weight underflowed: redo relative to the exact minimum exponent
-              double pm = INFINITY;
-              for (int z = zb; z < ze; ++z) { double pre; pm = fmin(pm, cand(z, pre)); }
-              for (int o = G >> 1; o > 0; o >>= 1) pm = fmin(pm, __shfl_xor_sync(gmask, pm, o, G));
-              base = pm;
-            }
-            const uint32_t idx = (uint32_t)(((s * L + (l - 1)) * niter + it) * F + j);
-            const double u = (randU != nullptr && t.randu_off >= 0) ? randU[t.randu_off + idx]
-                                                                    : rs_uniform(seed, call, IIF_RS_GIBBS_U, idx);
-            const double thr = u * tot;
-            // every lane searches its own chunks (no divergent owner path); exactly one lane finds the crossing
-            int mypick = -1;
-            if ((zb < ze) && (thr >= off) && (thr < off + Tl)) {
-              double run = off;
-              mypick = ze - 1;
-              bool found = false;
-#pragma unroll
-              for (int ch = 0; ch < 16; ++ch) {
-                const int cb = zb + ch * CH;
-                if (!found && cb < ze) {
-                  if (thr < run + ct[ch]) {
-                    const int ce = min(cb + CH, ze);
-                    mypick = ce - 1;
-                    if (CH > 1) {
-                      double cum = run;
-                      for (int z = cb; z < ce; ++z) {
-                        cum += weight(z, base);
-                        if (thr < cum) { mypick = z; break; }
-                      }
-                    }
-                    found = true;
-                  }
-                  run += ct[ch];
-                }
-              }
-            }
-            const unsigned hit = __ballot_sync(gmask, mypick >= 0) & gmask;
-            int pick = nz - 1;  // rounding left thr >= total: the oracle falls back to the last candidate
-            if (hit) pick = __shfl_sync(gmask, mypick, (__ffs(hit) - 1) & (G - 1), G);
-            node[j] = z0 + pick;
+            node[j] = draw_label(j, l, cmu, cvar, has,
+                                 gibbs_u((uint32_t)s * ublk + (uint32_t)(F + (l - 1) * F * (niter + 1) + F + it * F + j)));
           }
         }
       }
@@ -553,9 +582,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
           const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, -1, nn, d, c, is_circ(cm, c), mu);
           double x;
           if (lam > 0) {
-            const uint32_t idx = (uint32_t)(s * d + c);
-            const double e = (randN != nullptr && t.randn_off >= 0) ? randN[t.randn_off + idx]
-                                                                    : rs_normal(seed, call, IIF_RS_GIBBS_N, idx);
+            const double e = gibbs_n((uint32_t)s * nblk + (uint32_t)(L * d + c));
             x = madd(mu, sqrt(1.0 / lam) * e, is_circ(cm, c));
           } else if (t.target_slot >= 0) {
             // coordinates no proposal informs keep oldPoints (GraphProductOperations.jl:37-45)

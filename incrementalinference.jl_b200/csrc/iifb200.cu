@@ -627,8 +627,8 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
     ooff[v + 1] = ooff[v] + (int64_t)o.N * o.dim;
     loff[v + 1] = loff[v] + (int64_t)o.N * o.nfactors;
     const int L = ctx->trees[o.N].L;
-    if (o.randu_off >= 0) n_u = std::max<int64_t>(n_u, o.randu_off + (int64_t)o.N * L * ctx->sp.gibbsNiter * o.nfactors);
-    if (o.randn_off >= 0) n_n = std::max<int64_t>(n_n, o.randn_off + (int64_t)o.N * o.dim);
+    if (o.randu_off >= 0) n_u = std::max<int64_t>(n_u, o.randu_off + (int64_t)o.N * o.nfactors * (1 + (int64_t)L * (ctx->sp.gibbsNiter + 1)));
+    if (o.randn_off >= 0) n_n = std::max<int64_t>(n_n, o.randn_off + (int64_t)o.N * o.dim * (L + 1));
     smem = std::max(smem, prod_smem_bytes(o.nfactors, o.N, o.dim, ctx->trees[o.N].nn, ctx->trees[o.N].L));
     pmaxN = std::max(pmaxN, (int)o.N);
   }

@@ -316,6 +316,17 @@ class FactorGraph:
         self.solverParams = solverParams or SolverParams()
         self._engine = None          # lazily-built device engine (solver.Engine)
         self._version = 0            # bumped on structural change
+        self._by_var: Dict[str, List[str]] = {}   # variable -> factor labels (insertion order)
+        # Philox call ids handed out so far.  Every numeric call on this graph (approxConv, propagateBelief, initAll,
+        # solveTree) draws its ids from here, so consecutive calls and consecutive solves see fresh noise, as the
+        # reference's global RNG gives them (a per-engine counter restarted at 0 replayed the same streams).
+        self._call_counter = 0
+
+    def next_call(self, n: int = 16) -> int:
+        """reserve `n` consecutive Philox call ids; returns the first"""
+        c = self._call_counter
+        self._call_counter = (c + int(n)) % (1 << 31)
+        return c
 
     # DFG accessors used by the mirrored API
     def getVariable(self, lbl):
@@ -332,7 +343,7 @@ class FactorGraph:
 
     def listNeighbors(self, lbl):
         if lbl in self.variables:
-            return [f.label for f in self.factors.values() if lbl in f.variables]
+            return list(self._by_var.get(lbl, ()))
         return list(self.factors[lbl].variables)
 
 
@@ -381,6 +392,8 @@ def addFactor(fg: FactorGraph, variables: Sequence[str], fnc, multihypo=None, nu
                   fg.solverParams.inflation if inflation is None else float(inflation),
                   len(fg.factors))
     fg.factors[label] = f
+    for v in dict.fromkeys(variables):
+        fg._by_var.setdefault(v, []).append(label)
     fg._version += 1
     do_init = fg.solverParams.graphinit if graphinit is None else graphinit
     if do_init:

@@ -24,14 +24,17 @@ from .engine import Engine
 class GraphEngine:
     """Device mirror of one FactorGraph: slot i == variable i, factor table == graph factors."""
 
-    def __init__(self, fg: G.FactorGraph, device: int = 0):
+    def __init__(self, fg: G.FactorGraph, device: int = 0, cap: int = 0):
         self.fg = fg
         self.version = fg._version
         T = CP.Tables()
         self.N = fg.solverParams.N
+        # slot capacity is the engine's own business: a call that asks for more points than SolverParams.N grows it
+        # without touching the user's solver parameters
+        self.cap = max(self.N, int(cap))
         self.var_slot = {}
         for l, v in fg.variables.items():
-            self.var_slot[l] = T.add_slot(v.vartype, max(self.N, v.val.shape[0], 1))
+            self.var_slot[l] = T.add_slot(v.vartype, max(self.cap, v.val.shape[0], 1))
         self.fac_idx = {}
         for l, f in fg.factors.items():
             self.fac_idx[l] = T.add_factor(f.fnc, [self.var_slot[v] for v in f.variables], f.multihypo,
@@ -40,7 +43,6 @@ class GraphEngine:
         self.sp_c = CP.solver_params_c(fg.solverParams)
         self.eng = Engine(self.frozen, self.sp_c, device)
         self.dirty = set(fg.variables)
-        self.call_id = 0
 
     def mark_dirty(self, lbl):
         self.dirty.add(lbl)
@@ -52,20 +54,20 @@ class GraphEngine:
         self.dirty.clear()
 
     def next_call(self, n=16):
-        c = self.call_id
-        self.call_id += n
-        return c
+        return self.fg.next_call(n)       # graph-wide counter: no two numeric calls on a graph share Philox streams
 
     def close(self):
         self.eng.close()
 
 
-def _engine(fg: G.FactorGraph) -> GraphEngine:
+def _engine(fg: G.FactorGraph, cap: int = 0) -> GraphEngine:
     ge = fg._engine
-    if ge is None or ge.version != fg._version or ge.N != fg.solverParams.N:
+    if ge is None or ge.version != fg._version or ge.N != fg.solverParams.N or ge.cap < cap:
+        keep = 0
         if ge is not None:
+            keep = ge.cap
             ge.close()
-        ge = GraphEngine(fg)
+        ge = GraphEngine(fg, cap=max(cap, keep))
         fg._engine = ge
     sp_c = CP.solver_params_c(fg.solverParams)
     if bytes(sp_c) != bytes(ge.sp_c):
@@ -96,17 +98,14 @@ def approxConvBelief(fg: G.FactorGraph, fct: str, target: str, measurement=None,
     The target variable is NOT modified (ApproxConv.jl:17).  `measurement`, `mhidx`, `uinf` inject
     host-drawn random streams (Julia-drawn labels stay bit-exact); by default the device draws them.
     """
-    ge = _engine(fg)
     f = fg.factors[fct]
     if target not in f.variables:
         raise KeyError(f"{target} is not a variable of factor {fct}")
     v = fg.variables[target]
     if N is None:
         N = len(measurement) if measurement is not None and len(measurement) else 0
-    N = N if N else (v.val.shape[0] or fg.solverParams.N)     # ApproxConv.jl:15
-    if N > ge.frozen["slots"][ge.var_slot[target]].cap:
-        fg.solverParams.N = max(fg.solverParams.N, N)          # grow slot capacity
-        ge = _engine(fg)
+    N = N if N else (v.val.shape[0] or fg.solverParams.N)     # ApproxConv.jl:15 picks a local N
+    ge = _engine(fg, cap=N)                                    # grows the engine's slots, not SolverParams.N
     spec = dict(factor=ge.fac_idx[fct], sfidx=f.variables.index(target) + 1, N=N, call_id=ge.next_call(),
                 nullSurplus=nullSurplus)
     meas = None
@@ -235,7 +234,7 @@ def doautoinit(fg: G.FactorGraph, lbl: str, singles: bool = True) -> bool:
     use = [f for f in nei if factorCanInitFromOtherVars(fg, f, lbl)]
     if not use:
         return False
-    mkd, ipc = propagateBelief(fg, lbl, use[:A.IIF_MAX_FACTORS])
+    mkd, ipc = propagateBelief(fg, lbl, use)                   # raises beyond IIF_MAX_FACTORS, never truncates
     G.setValKDE(fg, lbl, mkd, True, ipc)
     return True
 
@@ -268,7 +267,8 @@ def initAll(fg: G.FactorGraph, batched: bool = True) -> None:
             use = [f for f in fg.listNeighbors(l) if G.factorCanInitFromOtherVars(fg, f, l, init)]
             if not use:
                 continue
-            use = use[:A.IIF_MAX_FACTORS]
+            if len(use) > A.IIF_MAX_FACTORS:
+                raise A.IIFB200Error(f"initAll: {len(use)} factors on {l} exceed IIF_MAX_FACTORS = {A.IIF_MAX_FACTORS}")
             slot = ge.var_slot[l]
             specs.append(dict(target_slot=slot, out_slot=slot,
                               factors=[(ge.fac_idx[f], fg.factors[f].variables.index(l) + 1) for f in use],
@@ -308,14 +308,21 @@ class TreeSolver:
     """Compiled solveTree!: one device arena with clique-local slots + one CUDA-graph schedule."""
 
     def __init__(self, fg: G.FactorGraph, eliminationOrder: Optional[Sequence[str]] = None, ordering: str = "qr",
-                 device: int = 0, ext_arena_ptr=None, downsolve: Optional[bool] = None, lanes: Optional[int] = None):
+                 device: int = 0, ext_arena_ptr=None, downsolve: Optional[bool] = None, lanes: Optional[int] = None,
+                 forward_copies: bool = True, call_base=0):
+        """`call_base`: first Philox call id of the plan.  0 (default) gives the same streams for the same seed —
+        what parity tests and the bench want; "auto" reserves a fresh range from the graph's counter, so consecutive
+        solveTree calls on one graph see independent noise."""
         self.fg = fg
         order = list(eliminationOrder) if eliminationOrder is not None else TR.getEliminationOrder(fg, ordering)
         self.tree = TR.buildTree(fg, order)
         ds = fg.solverParams.downsolve if downsolve is None else downsolve
         # independent sub-trees become parallel branches ("lanes") of the captured CUDA graph (tree.assign_lanes)
         lanes = int(os.environ.get("IIFB200_LANES", "4")) if lanes is None else lanes
-        self.plan = TR.compile_solve(fg, self.tree, downsolve=ds, lanes=lanes)
+        self.plan = TR.compile_solve(fg, self.tree, downsolve=ds, lanes=lanes, forward_copies=forward_copies)
+        if call_base == "auto":
+            call_base = fg.next_call(TR.plan_call_span(self.plan))
+        TR.rebase_calls(self.plan, int(call_base))
         self.sp_c = CP.solver_params_c(fg.solverParams)
         self.eng = Engine(self.plan.frozen, self.sp_c, device, ext_arena_ptr)
         self.props_c = CP.make_prop_ops(self.plan.props)
@@ -368,7 +375,7 @@ def solveTree(fg: G.FactorGraph, eliminationOrder: Optional[Sequence[str]] = Non
     for l, v in fg.variables.items():
         if not v.initialized:
             raise A.IIFB200Error(f"solveTree: variable {l} could not be initialised")
-    ts = TreeSolver(fg, eliminationOrder, ordering, device)
+    ts = TreeSolver(fg, eliminationOrder, ordering, device, call_base="auto")
     ts.load_from_graph()
     ts.upload()
     ts.run()

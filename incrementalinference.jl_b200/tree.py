@@ -548,6 +548,9 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
 
     def add_prop(target_label, target_slot, fac_list, rd_slots):
         """fac_list: [(factor_table_idx, sfidx, is_multihypo)]"""
+        if len(fac_list) > A.IIF_MAX_FACTORS:     # never truncate: dropped likelihoods / messages lose whole sub-trees
+            raise A.IIFB200Error(f"solve plan: {len(fac_list)} factors and messages on {target_label} in clique "
+                                 f"{cur[0]} exceed IIF_MAX_FACTORS = {A.IIF_MAX_FACTORS}")
         spec = dict(target_slot=target_slot, out_slot=target_slot, factors=[(fi, sf) for fi, sf, _ in fac_list],
                     N=N, call_id=16 * len(props), any_multihypo=int(any(m for _, _, m in fac_list)))
         props.append(spec)
@@ -614,7 +617,7 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
                     fl.append((e["fi"], e["variables"].index(v) + 1, e["mh"]))
                     rd += e["rd"]
             if fl:
-                add_prop(v, slot_of(v), fl[:A.IIF_MAX_FACTORS], rd)
+                add_prop(v, slot_of(v), fl, rd)
 
         def fmcmc(lbls, mciter):                              # SolveTree.jl:89-142
             if len(lbls) == 1:
@@ -678,7 +681,7 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
                         fl.append((fi, variables.index(v) + 1, ismh))
                         rd += rds
                 if fl:
-                    add_prop(v, cslot[(cid, v)], fl[:A.IIF_MAX_FACTORS], rd)
+                    add_prop(v, cslot[(cid, v)], fl, rd)
 
             # determineCliqVariableDownSequence: frontals sharing a factor iterate MCIters times
             iterF = []
@@ -699,6 +702,8 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
         for v in c.frontals:
             add_copy(cslot[(c.id, v)], var_slot[v])
 
+    for k, dc in enumerate(deconvs):               # Philox call ids: props first (16 apart), then the deconvolutions
+        dc["call_id"] = 16 * (len(props) + k)
     waves = _levelize(sched, reads, writes)
     nw = max(waves) + 1 if waves else 0
     order = sorted(range(len(sched)), key=lambda i: (waves[i], i))
@@ -717,6 +722,20 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
                      up_last, [opc[i] for i in order], [waves[i] for i in order], [reads[i] for i in order],
                      [writes[i] for i in order], {s: cid for (cid, _), s in cslot.items()}, deconvs,
                      [lane[i] for i in order])
+
+
+def plan_call_span(plan: SolvePlan) -> int:
+    """number of Philox call ids a plan uses (16 per propagateBelief / deconvolution)"""
+    return 16 * (len(plan.props) + len(plan.deconvs or []))
+
+
+def rebase_calls(plan: SolvePlan, base: int) -> None:
+    """shift every call id of a freshly compiled plan (ids start at 0) by `base`"""
+    if base:
+        for p in plan.props:
+            p["call_id"] += base
+        for dc in plan.deconvs or []:
+            dc["call_id"] += base
 
 
 def _joint_up_message(fg, c: TreeClique, inst, slot_of, T, N, deconvs, sched, reads, writes, opc, cur):
@@ -744,7 +763,7 @@ def _joint_up_message(fg, c: TreeClique, inst, slot_of, T, N, deconvs, sched, re
             vt = fg.variables[s1].vartype
             mslot = T.add_slot(vt, N)                                               # newBel = manikde!(sft, pts)
             dummy = T.add_factor(sft, [slot_of(s1), slot_of(s2)], None, 0.0, 5.0)   # tfg dummy factor, :314
-            deconvs.append(dict(factor=dummy, out_slot=mslot, N=N, call_id=(1 << 24) + 16 * len(deconvs)))
+            deconvs.append(dict(factor=dummy, out_slot=mslot, N=N, call_id=-1))    # ids follow the props', see compile_solve
             sched.append((A.S_DECONV, len(deconvs) - 1, 0))
             reads.append(sorted({slot_of(s1), slot_of(s2)}))
             writes.append([mslot])

@@ -962,19 +962,55 @@ int32_t iifo_product(int32_t d, int32_t cm, int32_t F, int32_t N, const double* 
   for (int j = 0; j < F; ++j)
     tree_build(&T[j], dens_pts + (size_t)j * N * d, dens_bw + j * IIF_MAX_DIM, N, d, masks[j], L);
   double* logw = (double*)malloc(sizeof(double) * N);
+  /* Stream layout (AMP.manifoldProduct keyword vectors `_randU` / `_randN`; KDE.jl sizes them
+   * Np*Ndens*(Niter+2)*Nlevels and Ndim*Np*(Nlevels+1)): per output sample the uniforms are consumed in the order
+   * initIndices (F), then per level sampleIndices (F) and Niter sweeps of sampleIndex (F each); the normals are the
+   * Nlevels+1 samplePoint draws (d each).  Here every sample owns a fixed-size block so that samples are
+   * independent of each other: U block = F*(1 + L*(niter+1)), N block = d*(L+1). */
+  const int ublk = F * (1 + L * (niter + 1)), nblk = d * (L + 1);
   for (int s = 0; s < N; ++s) {
     int node[IIF_MAX_FACTORS];
-    for (int j = 0; j < F; ++j) node[j] = 0;                 /* levelInit / initIndices: roots */
+    uint32_t uc = (uint32_t)(s * ublk), nc = (uint32_t)(s * nblk);
+    /* levelInit / initIndices: every level list holds the root only; the draw is trivial but consumes its uniform */
+    for (int j = 0; j < F; ++j) { node[j] = 0; uc++; }
+    double X[IIF_MAX_DIM];
     for (int l = 1; l <= L; ++l) {
-      /* levelDown: every density moves to level l; the selected label follows the LAST child pushed
-       * (KDE.jl levelDown!: `ind[j] = levelListNew[j, z-1]`, "make sure ind points to a child of the
-       * old ind"), i.e. the right child of an internal node, the node itself for a leaf */
+      /* samplePoint(X): a point from the product of the currently selected (coarse) Gaussians */
+      for (int c = 0; c < d; ++c) {
+        double mu = 0;
+        double lam = cond_gauss(F, T, node, masks, -1, d, c, is_circ(cm, c), &mu);
+        uint32_t idx = nc++;
+        double e = randN ? randN[idx] : iifo_normal(seed, call_id, IIF_RS_GIBBS_N, idx);
+        X[c] = lam > 0 ? madd(mu, sqrt(1.0 / lam) * e, is_circ(cm, c)) : 0.0;
+      }
+      /* levelDown: every density's level list becomes the children of the previous list (a leaf stays).  The label
+       * would follow the last child pushed, but sampleIndices below re-draws every label over the whole new list. */
+      /* sampleIndices(X): label of every density given the point, p(z) ~ w_z N(X; mean_z, var_z) */
       for (int j = 0; j < F; ++j) {
-        int nd = node[j];
-        node[j] = T[j].lev_off[l] + T[j].child[nd] + (T[j].hi[nd] > T[j].lo[nd] ? 1 : 0);
+        int z0 = T[j].lev_off[l], z1 = T[j].lev_off[l + 1], nz = z1 - z0;
+        double best = INFINITY;
+        for (int z = 0; z < nz; ++z) {
+          double p = 0;
+          for (int c = 0; c < d; ++c) {
+            if (!((masks[j] >> c) & 1)) continue;
+            double dl = mdiff(X[c], T[j].mean[(z0 + z) * d + c], is_circ(cm, c));
+            double v = T[j].var[(z0 + z) * d + c];
+            p += dl * dl / v + log(v);
+          }
+          logw[z] = p;
+          if (p < best) best = p;
+        }
+        double tot = 0;
+        for (int z = 0; z < nz; ++z) { logw[z] = exp(-0.5 * (logw[z] - best)) * T[j].wt[z0 + z]; tot += logw[z]; }
+        uint32_t idx = uc++;
+        double u = randU ? randU[idx] : iifo_uniform(seed, call_id, IIF_RS_GIBBS_U, idx);
+        double thr = u * tot, cum = 0;
+        int pick = nz - 1;
+        for (int z = 0; z < nz; ++z) { cum += logw[z]; if (thr < cum) { pick = z; break; } }
+        node[j] = z0 + pick;
       }
       for (int it = 0; it < niter; ++it) {
-        for (int j = 0; j < F; ++j) {                        /* sampleIndex(j) */
+        for (int j = 0; j < F; ++j) {                        /* sampleIndex(j): label | the other densities' labels */
           double cmu[IIF_MAX_DIM] = {0}, clam[IIF_MAX_DIM];
           for (int c = 0; c < d; ++c)
             clam[c] = ((masks[j] >> c) & 1) ? cond_gauss(F, T, node, masks, j, d, c, is_circ(cm, c), &cmu[c]) : 0.0;
@@ -993,7 +1029,7 @@ int32_t iifo_product(int32_t d, int32_t cm, int32_t F, int32_t N, const double* 
           }
           double tot = 0;
           for (int z = 0; z < nz; ++z) { logw[z] = exp(-0.5 * (logw[z] - best)) * T[j].wt[z0 + z]; tot += logw[z]; }
-          uint32_t idx = (uint32_t)(((s * L + (l - 1)) * niter + it) * F + j);
+          uint32_t idx = uc++;
           double u = randU ? randU[idx] : iifo_uniform(seed, call_id, IIF_RS_GIBBS_U, idx);
           double thr = u * tot, cum = 0;
           int pick = nz - 1;
@@ -1002,12 +1038,12 @@ int32_t iifo_product(int32_t d, int32_t cm, int32_t F, int32_t N, const double* 
         }
       }
     }
-    /* samplePoint: draw from the product of the selected leaf kernels */
+    /* final samplePoint: draw from the product of the selected leaf kernels */
     for (int c = 0; c < d; ++c) {
       double mu = 0;
       double lam = cond_gauss(F, T, node, masks, -1, d, c, is_circ(cm, c), &mu);
+      uint32_t idx = nc++;
       if (lam > 0) {
-        uint32_t idx = (uint32_t)(s * d + c);
         double e = randN ? randN[idx] : iifo_normal(seed, call_id, IIF_RS_GIBBS_N, idx);
         out_pts[s * d + c] = madd(mu, sqrt(1.0 / lam) * e, is_circ(cm, c));
       } else {

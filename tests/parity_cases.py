@@ -280,7 +280,7 @@ def product_cases():
     # explicit Gibbs streams (AMP _randU / _randN keyword vectors)
     a = np.stack([R.normal(0, 1, (N, 1)), R.normal(0.5, 1, (N, 1))])
     yield "explicit_gibbs_streams", dict(dens_pts=a, dens_bw=bws(a), dim=1, call_id=16,
-                                         randU=R.random(N * 7 * 2), randN=R.normal(0, 1, N))
+                                         randU=R.random(N * 2 * (1 + 7 * 2)), randN=R.normal(0, 1, N * 8))   # F*(1 + L*(Niter+1)) and d*(L+1) per sample, L = 7
 
     # SpecialEuclidean(2) coordinates (x, y, theta): two Euclid + one circular coordinate across the +-pi seam
     a = np.stack([np.column_stack([R.normal(1, 0.3, N), R.normal(2, 0.3, N), wrap(R.normal(3.1, 0.2, N))]),
@@ -395,7 +395,6 @@ def oracle_initAll(fg):
         if v.initialized:
             arena.set(var_slot[l], v.val, v.bw, True, v.infoPerCoord)
     orc = O.Oracle(frozen, arena, CP.solver_params_c(fg.solverParams))
-    call = 0
     for _ in range(len(fg.variables) + 1):
         did = False
         for l, v in fg.variables.items():
@@ -404,10 +403,9 @@ def oracle_initAll(fg):
             use = [f for f in fg.listNeighbors(l) if G.factorCanInitFromOtherVars(fg, f, l)]
             if not use:
                 continue
-            spec = dict(target_slot=var_slot[l], out_slot=var_slot[l], N=N, call_id=call,
+            spec = dict(target_slot=var_slot[l], out_slot=var_slot[l], N=N, call_id=fg.next_call(),
                         factors=[(fac_idx[f], fg.factors[f].variables.index(l) + 1) for f in use],
                         any_multihypo=int(any(G.isMultihypo(fg.factors[f]) for f in use)))
-            call += 16
             orc.propagate(CP.make_prop_ops([spec])[0])
             v.val, v.bw, v.infoPerCoord = arena.get(var_slot[l])
             v.initialized = True
@@ -423,6 +421,7 @@ def oracle_solveTree(fg, order=None, ordering="qr", **kw):
     order = order or TR.getEliminationOrder(fg, ordering)
     tree = TR.buildTree(fg, order)
     plan = TR.compile_solve(fg, tree, **kw)
+    TR.rebase_calls(plan, fg.next_call(TR.plan_call_span(plan)))     # as solver.solveTree does (call_base="auto")
     arena = CP.HostArena(plan.frozen)
     for l, v in fg.variables.items():
         arena.set(plan.var_slot[l], v.val, v.bw, True, v.infoPerCoord)

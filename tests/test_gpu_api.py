@@ -232,10 +232,13 @@ def test_c2_full_size_chain_properties(built):
     assert np.array_equal(p1, p2) and np.array_equal(b1, b2)          # deterministic replay of the CUDA graph
     assert not np.array_equal(p1, p3)
     mean_err = np.abs(p1.mean(axis=1) - np.arange(n))
-    sigma = 0.1 * np.sqrt(np.arange(n) + 1.0)                          # prior 0.1, odometry 0.1 per step
-    assert (mean_err < 6.0 * sigma + 0.5).all(), float(mean_err.max())
+    sigma = 0.1 * np.sqrt(np.arange(n) + 1.0)                          # analytic marginal: prior 0.1, odometry 0.1 per step
+    # Band derived from the ORACLE on this plan over 20 seeds (round 2): max |mean error| = 0.68 sigma (2.1 absolute,
+    # at the chain end), posterior std between 0.30 and 1.31 sigma.  (Round 1 accepted 6 sigma + 0.5 because its
+    # product sampler carried an upward bias of ~3.5 sigma at x997..x999)
+    assert (mean_err < 1.0 * sigma + 0.3).all(), (int(np.argmax(mean_err / sigma)), float((mean_err / sigma).max()))
     spread = p1.std(axis=1)
-    assert (spread < 4.0 * sigma + 0.5).all() and (spread > 0.01).all()
+    assert (spread < 1.7 * sigma + 0.1).all() and (spread > 0.15 * sigma).all(), (float((spread / sigma).max()), float((spread / sigma).min()))
     ts.close()
 
 
