@@ -312,6 +312,69 @@ int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t firs
 int32_t iifb200_schedule_free(iifb200_ctx* ctx, int32_t schedule_id);
 int32_t iifb200_sync(iifb200_ctx* ctx);
 
+/* ---- tree planner (boundary B4 for a reference-side caller) ------------------------------------------------------
+ * The reference's own offload unit is a CLIQUE: `upGibbsCliqueDensity(dfg, cliq, ...)` (src/services/SolveTree.jl:164-173,
+ * shipped to workers by CliqStateMachineUtils.jl:369-385) and `solveCliqDownFrontalProducts!` (:479-571).  The planner
+ * takes what `tree.bt` and the DFG already hold — per clique: parent, frontals, separators, potentials and the four Gibbs
+ * variable classes of setCliqMCIDs! (JunctionTreeUtils.jl:1352-1523) — and produces the whole pass inside the library:
+ * clique-local belief slots, one iif_prop_op per propagateBelief of every fmcmc! sweep, MsgPrior instances for the up
+ * messages, separator adoption and addDownVariableFactors! for the down pass, the frontal write-back, then waves of
+ * independent ops, copy forwarding and lanes.  Pure host code (no GPU needed); iifb200_plan_upload puts it on a device.
+ * Variables are numbered 0..nvars-1 in graph order and factor descriptors refer to them through `slot[]`; in the plan the
+ * main-graph belief of variable v is slot v. */
+typedef struct {
+  int32_t nvars;
+  const iif_slot_desc* vars;       /* dim, circ_mask, cap (>= current point count) of every graph variable */
+  int32_t nfactors;
+  const iif_factor_desc* factors;  /* graph order (getFactors); slot[k] = variable index */
+  int32_t ndists;
+  const iif_dist_desc* dists;
+  int32_t nparams;
+  const double* dparams;
+} iif_graph_desc;
+
+/* Bayes tree in CSR form; cliques are numbered parents first (parent id < child id, roots have parent -1), children of a
+ * clique are taken in increasing id.  All lists hold variable indices except `potentials` (factor indices). */
+typedef struct {
+  int32_t ncliques;
+  const int32_t* parent;
+  const int32_t *frontal_off, *frontals;               /* getCliqFrontalVarIds */
+  const int32_t *separator_off, *separators;           /* getCliqSeparatorVarIds */
+  const int32_t *potential_off, *potentials;           /* getCliqueData(cliq).potentials */
+  const int32_t *directFrtlMsg_off, *directFrtlMsg;    /* .directFrtlMsgIDs */
+  const int32_t *msgskip_off, *msgskip;                /* .msgskipIDs */
+  const int32_t *itervar_off, *itervar;                /* .itervarIDs */
+  const int32_t *directPriorMsg_off, *directPriorMsg;  /* .directPriorMsgIDs */
+} iif_tree_desc;
+
+typedef struct {
+  int32_t N;                  /* particles per belief */
+  int32_t gibbsIters;         /* SolverParams.gibbsIters (3) */
+  int32_t downIters;          /* MCIters of the down solve (3) */
+  int32_t downsolve;          /* SolverParams.downsolve */
+  int32_t lanes;              /* parallel graph branches for independent sub-trees (0 = none, <= 8) */
+  int32_t forward_copies;     /* collapse separator copy chains */
+  int32_t useMsgLikelihoods;  /* must be 0 here (differential messages are lowered by the host mirror) */
+  int32_t call_base;          /* first Philox call id of the pass (prop k uses call_base + 16 k) */
+  double inflation;           /* SolverParams.inflation, for the message priors */
+} iif_plan_opts;
+
+typedef struct iifb200_plan iifb200_plan;
+int32_t iifb200_plan_tree(const iif_graph_desc* graph, const iif_tree_desc* tree, const iif_plan_opts* opts,
+                          iifb200_plan** plan_out);
+const char* iifb200_plan_error(void); /* message of the last failed iifb200_plan_tree on this thread */
+void iifb200_plan_free(iifb200_plan* plan);
+/* counts[16]: nslots, nfactors, ndists, nparams, nprops, nops, nwaves, n_conv, n_prod, n_msgs, up_last_wave, nvars, 0.. */
+int32_t iifb200_plan_counts(const iifb200_plan* plan, int32_t* counts);
+/* copies the plan's tables into caller arrays sized from iifb200_plan_counts (any pointer may be NULL) */
+int32_t iifb200_plan_export(const iifb200_plan* plan, iif_slot_desc* slots, iif_factor_desc* factors,
+                            iif_dist_desc* dists, double* dparams, iif_prop_op* props, iif_sched_op* ops,
+                            int32_t* wave_off /* nwaves + 1 */);
+/* iifb200_set_graph + iifb200_schedule_build of a plan in one call; beliefs of the graph variables then go to slots
+ * 0..nvars-1 (iifb200_upload_slots), iifb200_schedule_run solves, iifb200_download_slots reads the posteriors. */
+int32_t iifb200_plan_upload(iifb200_ctx* ctx, const iifb200_plan* plan, const iif_solver_params* sp,
+                            void* ext_arena, int32_t* schedule_id_out);
+
 /* ---- instrumentation ---------------------------------------------------------------- */
 /* kernels launched by this ctx since init (for bench.py "gpu_launches") */
 int64_t iifb200_launch_count(const iifb200_ctx* ctx);

@@ -73,6 +73,28 @@ class SchedOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("lane", C.c_int32)]
 
 
+class GraphDesc(C.Structure):
+    _fields_ = [("nvars", C.c_int32), ("vars", C.POINTER(SlotDesc)), ("nfactors", C.c_int32),
+                ("factors", C.POINTER(FactorDesc)), ("ndists", C.c_int32), ("dists", C.POINTER(DistDesc)),
+                ("nparams", C.c_int32), ("dparams", C.POINTER(C.c_double))]
+
+
+_ipt = C.POINTER(C.c_int32)
+
+
+class TreeDesc(C.Structure):
+    _fields_ = [("ncliques", C.c_int32), ("parent", _ipt)] + [
+        (f"{name}{suffix}", _ipt)
+        for name in ("frontal", "separator", "potential", "directFrtlMsg", "msgskip", "itervar", "directPriorMsg")
+        for suffix in ("_off", "s" if name in ("frontal", "separator", "potential") else "")]
+
+
+class PlanOpts(C.Structure):
+    _fields_ = [("N", C.c_int32), ("gibbsIters", C.c_int32), ("downIters", C.c_int32), ("downsolve", C.c_int32),
+                ("lanes", C.c_int32), ("forward_copies", C.c_int32), ("useMsgLikelihoods", C.c_int32),
+                ("call_base", C.c_int32), ("inflation", C.c_double)]
+
+
 P = C.POINTER
 _dp, _ip, _vp = P(C.c_double), P(C.c_int32), C.c_void_p
 
@@ -111,6 +133,12 @@ SYMBOLS = {
     "iifb200_schedule_free": (C.c_int32, [_vp, C.c_int32]),
     "iifb200_schedule_profile": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, P(C.c_float), _ip,
                                              P(C.c_int64)]),
+    "iifb200_plan_tree": (C.c_int32, [P(GraphDesc), P(TreeDesc), P(PlanOpts), P(_vp)]),
+    "iifb200_plan_error": (C.c_char_p, []),
+    "iifb200_plan_free": (None, [_vp]),
+    "iifb200_plan_counts": (C.c_int32, [_vp, _ip]),
+    "iifb200_plan_export": (C.c_int32, [_vp, P(SlotDesc), P(FactorDesc), P(DistDesc), _dp, P(PropOp), P(SchedOp), _ip]),
+    "iifb200_plan_upload": (C.c_int32, [_vp, _vp, P(SolverParamsC), _vp, _ip]),
     "iifb200_sync": (C.c_int32, [_vp]),
     "iifb200_launch_count": (C.c_int64, [_vp]),
     "iifb200_set_stream": (C.c_int32, [_vp, _vp]),

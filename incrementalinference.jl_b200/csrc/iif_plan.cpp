@@ -1,0 +1,459 @@
+// iif_plan.cpp — host-side planner of libiifb200.so: lowers ONE solveTree! pass (up + down clique solves) from the
+// data a Julia caller already holds (the factor graph's descriptor tables and the Bayes tree `tree.bt` with every
+// clique's frontals, separators, potentials and Gibbs variable classes) to belief slots, propagateBelief ops and
+// waves of independent ops, including copy forwarding and lane assignment.  No CUDA here: the planner is a pure
+// function of its inputs (unit-tested without a GPU); iifb200_plan_upload (iifb200.cu) hands the result to the device.
+//
+// Reference call sites this replaces on the caller's side (it does what the CSM would do clique by clique):
+//   buildCliqSubgraph! deep copies                      CliqueStateMachine.jl step 0b
+//   addMsgFactors! (one MsgPrior per separator)         TreeMessageUtils.jl:566-575
+//   upGibbsCliqueDensity / fmcmc! sweeps                SolveTree.jl:89-239
+//   updateSubFgFromDownMsgs!, addDownVariableFactors!   TreeMessageUtils.jl:66, CliqStateMachineUtils.jl:479-571
+//   determineCliqVariableDownSequence / downGibbs       CliqStateMachineUtils.jl:438-571
+//   updateFromSubgraph (frontals back to the graph)     CliqueStateMachine.jl:928-966
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/iifb200.h"
+
+struct iifb200_plan {
+  std::vector<iif_slot_desc> slots;
+  std::vector<iif_factor_desc> factors;
+  std::vector<iif_dist_desc> dists;
+  std::vector<double> dparams;
+  std::vector<iif_prop_op> props;
+  std::vector<iif_sched_op> ops;      // sorted by wave
+  std::vector<int32_t> wave_off;
+  int32_t n_conv = 0, n_prod = 0, n_msgs = 0, up_last_wave = 0, nvars = 0;
+};
+
+static thread_local std::string g_plan_error;
+
+namespace {
+
+struct Op {
+  int kind, a, b, clique;
+  std::vector<int> rd, wr;
+  double weight;
+};
+
+struct Inst {  // one factor instance of a clique sub-graph
+  std::vector<int> vars;
+  std::vector<int> rd;
+  int fi;
+  bool mh;
+};
+
+std::vector<int> csr(const int32_t* off, const int32_t* val, int i) {
+  return std::vector<int>(val + off[i], val + off[i + 1]);
+}
+bool has(const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+
+// wave(op) = 1 + max wave of earlier ops it conflicts with (RAW / WAR / WAW on slots)
+std::vector<int> levelize(const std::vector<Op>& ops) {
+  std::unordered_map<int, int> last_w, last_r;
+  std::vector<int> waves(ops.size());
+  for (size_t i = 0; i < ops.size(); ++i) {
+    int w = 0;
+    for (int s : ops[i].rd) { auto it = last_w.find(s); if (it != last_w.end()) w = std::max(w, it->second + 1); }
+    for (int s : ops[i].wr) {
+      auto it = last_w.find(s); if (it != last_w.end()) w = std::max(w, it->second + 1);
+      auto ir = last_r.find(s); if (ir != last_r.end()) w = std::max(w, ir->second + 1);
+    }
+    waves[i] = w;
+    for (int s : ops[i].rd) { auto ir = last_r.find(s); last_r[s] = (ir == last_r.end()) ? w : std::max(ir->second, w); }
+    for (int s : ops[i].wr) last_w[s] = w;
+  }
+  return waves;
+}
+
+// Lanes: groups of disjoint sub-trees (independent until their common ancestor); the tree top stays lane 0 and any
+// op that conflicts with another lane without a barrier wave in between is demoted to lane 0.
+std::vector<int> assign_lanes(int ncl, const int32_t* parent, const std::vector<std::vector<int>>& children,
+                              const std::vector<Op>& ops, const std::vector<int>& waves, int nlanes) {
+  const int n = (int)ops.size();
+  std::vector<int> lane(n, 0);
+  if (nlanes < 2 || n == 0) return lane;
+  std::vector<double> sub(ncl, 0.0);
+  for (int i = 0; i < n; ++i) if (ops[i].clique >= 0) sub[ops[i].clique] += ops[i].weight;
+  for (int c = ncl - 1; c >= 0; --c) if (parent[c] >= 0) sub[parent[c]] += sub[c];   // children have larger ids
+  std::vector<int> frontier;
+  for (int c = 0; c < ncl; ++c) if (parent[c] < 0) frontier.push_back(c);
+  while ((int)frontier.size() < 2 * nlanes) {
+    int big = -1;
+    for (int c : frontier) if (!children[c].empty() && (big < 0 || sub[c] > sub[big])) big = c;   // first maximum
+    if (big < 0) break;
+    frontier.erase(std::find(frontier.begin(), frontier.end(), big));
+    for (int ch : children[big]) frontier.push_back(ch);
+  }
+  std::vector<double> load(nlanes + 1, 0.0);
+  std::vector<int> lane_of_clique(ncl, 0);
+  std::vector<int> order_f = frontier;
+  std::stable_sort(order_f.begin(), order_f.end(), [&](int a, int b) { return sub[a] > sub[b]; });
+  for (int r : order_f) {
+    int ln = 1;
+    for (int k = 2; k <= nlanes; ++k) if (load[k] < load[ln]) ln = k;
+    load[ln] += sub[r];
+    std::vector<int> stack{r};
+    while (!stack.empty()) {
+      int c = stack.back(); stack.pop_back();
+      lane_of_clique[c] = ln;
+      for (int ch : children[c]) stack.push_back(ch);
+    }
+  }
+  for (int i = 0; i < n; ++i) lane[i] = ops[i].clique >= 0 ? lane_of_clique[ops[i].clique] : 0;
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return waves[a] < waves[b]; });
+  for (int pass = 0; pass < n; ++pass) {   // demotions create new barrier waves: iterate to a fixed point
+    std::vector<int> barrier;
+    for (int i = 0; i < n; ++i) if (lane[i] == 0) barrier.push_back(waves[i]);
+    std::sort(barrier.begin(), barrier.end());
+    barrier.erase(std::unique(barrier.begin(), barrier.end()), barrier.end());
+    auto separated = [&](int wa, int wb) {   // a barrier wave in [wa, wb]
+      auto it = std::lower_bound(barrier.begin(), barrier.end(), wa);
+      return it != barrier.end() && *it <= wb;
+    };
+    std::unordered_map<int, std::pair<int, int>> last_w;
+    std::unordered_map<int, std::vector<std::pair<int, int>>> last_r;
+    bool changed = false;
+    for (int i : order) {
+      const int li = lane[i], wi = waves[i];
+      bool conflict = false;
+      if (li != 0) {
+        for (int s : ops[i].rd) {
+          auto a = last_w.find(s);
+          if (a != last_w.end() && a->second.first != li && a->second.first != 0 && !separated(a->second.second, wi)) conflict = true;
+        }
+        for (int s : ops[i].wr) {
+          auto a = last_w.find(s);
+          if (a != last_w.end() && a->second.first != li && a->second.first != 0 && !separated(a->second.second, wi)) conflict = true;
+          auto r = last_r.find(s);
+          if (r != last_r.end())
+            for (auto& lw : r->second)
+              if (lw.first != li && lw.first != 0 && !separated(lw.second, wi)) conflict = true;
+        }
+      }
+      if (conflict) { lane[i] = 0; changed = true; break; }
+      for (int s : ops[i].wr) { last_w[s] = {li, wi}; last_r[s].clear(); }
+      for (int s : ops[i].rd) last_r[s].push_back({li, wi});
+    }
+    if (!changed) break;
+  }
+  return lane;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* iifb200_plan_error(void) { return g_plan_error.c_str(); }
+
+void iifb200_plan_free(iifb200_plan* p) { delete p; }
+
+int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const iif_plan_opts* o, iifb200_plan** out) {
+  auto fail = [&](int32_t code, const std::string& msg) { g_plan_error = msg; return code; };
+  if (!g || !t || !o || !out) return fail(IIF_ERR_ARG, "plan_tree: null argument");
+  *out = nullptr;
+  if (o->useMsgLikelihoods)
+    return fail(IIF_ERR_UNSUPPORTED, "plan_tree: useMsgLikelihoods = true plans are lowered by the host mirror (tree.compile_solve) "
+                                     "and submitted through iifb200_schedule_build_ex");
+  const int nv = g->nvars, nf = g->nfactors, ncl = t->ncliques, N = o->N;
+  if (nv < 1 || ncl < 1 || N < 2 || N > IIF_MAX_POINTS) return fail(IIF_ERR_ARG, "plan_tree: bad sizes");
+  for (int f = 0; f < nf; ++f) {
+    const iif_factor_desc& F = g->factors[f];
+    if (F.arity < 1 || F.arity > IIF_MAX_ARITY) return fail(IIF_ERR_ARG, "plan_tree: factor arity out of range");
+    for (int k = 0; k < F.arity; ++k)
+      if (F.slot[k] < 0 || F.slot[k] >= nv) return fail(IIF_ERR_ARG, "plan_tree: factor variable index out of range");
+  }
+  for (int c = 0; c < ncl; ++c)
+    if (t->parent[c] >= c) return fail(IIF_ERR_ARG, "plan_tree: cliques must be numbered parents first (parent id < child id)");
+  iifb200_plan* P = new iifb200_plan();
+  P->nvars = nv;
+  P->dists.assign(g->dists, g->dists + g->ndists);
+  P->dparams.assign(g->dparams, g->dparams + g->nparams);
+
+  auto add_slot = [&](int var) {
+    iif_slot_desc s = g->vars[var];
+    s.cap = std::max(std::max(N, s.cap), 1);
+    s.pts_off = 0;
+    P->slots.push_back(s);
+    return (int)P->slots.size() - 1;
+  };
+  for (int v = 0; v < nv; ++v) add_slot(v);   // main graph: slot v == variable v
+  // clique-local copies
+  std::vector<std::vector<int>> fr(ncl), sp(ncl), allv(ncl), children(ncl);
+  std::vector<std::unordered_map<int, int>> cslot(ncl);
+  for (int c = 0; c < ncl; ++c) {
+    fr[c] = csr(t->frontal_off, t->frontals, c);
+    sp[c] = csr(t->separator_off, t->separators, c);
+    allv[c] = fr[c];
+    allv[c].insert(allv[c].end(), sp[c].begin(), sp[c].end());
+    for (int v : allv[c]) {
+      if (v < 0 || v >= nv) { delete P; return fail(IIF_ERR_ARG, "plan_tree: clique variable index out of range"); }
+      cslot[c][v] = add_slot(v);
+    }
+    if (t->parent[c] >= 0) children[t->parent[c]].push_back(c);
+  }
+  // variable -> factors (graph order)
+  std::vector<std::vector<int>> by_var(nv);
+  for (int f = 0; f < nf; ++f)
+    for (int k = 0; k < g->factors[f].arity; ++k) {
+      auto& l = by_var[g->factors[f].slot[k]];
+      if (l.empty() || l.back() != f) l.push_back(f);
+    }
+
+  std::vector<Op> ops;
+  int cur = -1, nconv = 0, n_msgs = 0;
+  std::string err;
+  // copy forwarding (see tree.compile_solve): a copy whose source was itself filled by a copy from X, X unchanged
+  // since, reads X directly
+  std::unordered_map<int, int> version;
+  std::unordered_map<int, std::pair<int, int>> prov;
+  auto ver = [&](int s) { auto it = version.find(s); return it == version.end() ? 0 : it->second; };
+  auto wrote = [&](int s) { version[s] = ver(s) + 1; prov.erase(s); };
+  auto add_copy = [&](int a, int b) {
+    if (o->forward_copies) {
+      auto it = prov.find(a);
+      if (it != prov.end() && ver(it->second.first) == it->second.second) a = it->second.first;
+    }
+    Op op{IIF_S_COPY, a, b, cur, {a}, {b}, 0.05};
+    ops.push_back(op);
+    wrote(b);
+    prov[b] = {a, ver(a)};
+  };
+  auto fac_instance = [&](int f, const std::vector<int>& slots) {
+    iif_factor_desc F = g->factors[f];
+    for (int k = 0; k < F.arity; ++k) F.slot[k] = slots[k];
+    P->factors.push_back(F);
+    return (int)P->factors.size() - 1;
+  };
+  auto add_prop = [&](int target_slot, const std::vector<Inst*>& use, int var) {
+    if ((int)use.size() > IIF_MAX_FACTORS) {
+      err = "plan_tree: " + std::to_string(use.size()) + " factors and messages on variable " + std::to_string(var) +
+            " in clique " + std::to_string(cur) + " exceed IIF_MAX_FACTORS";
+      return;
+    }
+    iif_prop_op p;
+    memset(&p, 0, sizeof(p));
+    p.target_slot = p.out_slot = target_slot;
+    p.nfactors = (int)use.size();
+    p.N = N;
+    std::vector<int> rd{target_slot};
+    bool anymh = false;
+    for (size_t k = 0; k < use.size(); ++k) {
+      const Inst& e = *use[k];
+      p.factor[k] = e.fi;
+      p.sfidx[k] = (int)(std::find(e.vars.begin(), e.vars.end(), var) - e.vars.begin()) + 1;
+      anymh |= e.mh;
+      rd.insert(rd.end(), e.rd.begin(), e.rd.end());
+    }
+    p.call_id = o->call_base + 16 * (int)P->props.size();
+    p.any_multihypo = anymh ? 1 : 0;
+    std::sort(rd.begin(), rd.end());
+    rd.erase(std::unique(rd.begin(), rd.end()), rd.end());
+    P->props.push_back(p);
+    Op op{IIF_S_PROPAGATE, (int)P->props.size() - 1, 0, cur, rd, {target_slot}, (double)use.size() + 1.0};
+    ops.push_back(op);
+    nconv += (int)use.size();
+    wrote(target_slot);
+  };
+
+  // ---- step 0: clique sub-graphs start from the main graph's beliefs
+  for (int c = 0; c < ncl; ++c) {
+    cur = c;
+    for (int v : allv[c]) add_copy(v, cslot[c][v]);
+  }
+  // post-order (children in id order)
+  std::vector<int> post;
+  {
+    std::vector<std::pair<int, bool>> stack;
+    std::vector<int> roots;
+    for (int c = 0; c < ncl; ++c) if (t->parent[c] < 0) roots.push_back(c);
+    for (auto it = roots.rbegin(); it != roots.rend(); ++it) stack.push_back({*it, false});
+    while (!stack.empty()) {
+      auto [c, done] = stack.back();
+      stack.pop_back();
+      if (done) { post.push_back(c); continue; }
+      stack.push_back({c, true});
+      for (auto it = children[c].rbegin(); it != children[c].rend(); ++it) stack.push_back({*it, false});
+    }
+  }
+  // ---- up pass
+  for (int cid : post) {
+    cur = cid;
+    std::vector<Inst> inst;
+    for (int f : csr(t->potential_off, t->potentials, cid)) {
+      if (f < 0 || f >= nf) { delete P; return fail(IIF_ERR_ARG, "plan_tree: potential index out of range"); }
+      const iif_factor_desc& F = g->factors[f];
+      Inst e;
+      for (int k = 0; k < F.arity; ++k) {
+        auto it = cslot[cid].find(F.slot[k]);
+        if (it == cslot[cid].end()) { delete P; return fail(IIF_ERR_ARG, "plan_tree: potential touches a variable outside its clique"); }
+        e.vars.push_back(F.slot[k]);
+        e.rd.push_back(it->second);
+      }
+      e.fi = fac_instance(f, e.rd);
+      e.mh = F.nmh != 0;
+      inst.push_back(e);
+    }
+    for (int ch : children[cid])
+      for (int s : sp[ch]) {   // addMsgFactors!: one MsgPrior per separator variable of the child
+        auto it = cslot[cid].find(s);
+        if (it == cslot[cid].end()) continue;
+        const int src = cslot[ch][s];
+        iif_dist_desc D;
+        memset(&D, 0, sizeof(D));
+        D.kind = IIF_D_KDE; D.dim = g->vars[s].dim; D.slot = src; D.poff = (int)P->dparams.size();
+        P->dists.push_back(D);
+        iif_factor_desc F;
+        memset(&F, 0, sizeof(F));
+        F.kind = IIF_F_MSG_PRIOR; F.arity = 1; F.zdim = D.dim; F.dist = (int)P->dists.size() - 1;
+        F.slot[0] = it->second; F.nullhypo = 0.0; F.inflation = o->inflation;
+        P->factors.push_back(F);
+        Inst e;
+        e.vars = {s}; e.rd = {it->second, src}; e.fi = (int)P->factors.size() - 1; e.mh = false;
+        inst.push_back(e);
+        n_msgs++;
+      }
+    auto propagate = [&](int v) {
+      std::vector<Inst*> use;
+      for (auto& e : inst) if (has(e.vars, v)) use.push_back(&e);
+      if (!use.empty()) add_prop(cslot[cid][v], use, v);
+    };
+    auto fmcmc = [&](const std::vector<int>& lbls, int iters) {
+      if (lbls.size() == 1) iters = 1;
+      for (int it = 0; it < iters; ++it) for (int v : lbls) propagate(v);
+    };
+    const std::vector<int> dfm = csr(t->directFrtlMsg_off, t->directFrtlMsg, cid), skip = csr(t->msgskip_off, t->msgskip, cid),
+                           iter = csr(t->itervar_off, t->itervar, cid), dpm = csr(t->directPriorMsg_off, t->directPriorMsg, cid);
+    fmcmc(dfm, 1);
+    if (!skip.empty()) fmcmc(skip, 1);
+    if (!iter.empty()) fmcmc(iter, o->gibbsIters);
+    if (!dpm.empty()) {
+      std::vector<int> l;
+      for (int v : dpm) if (!has(skip, v)) l.push_back(v);
+      fmcmc(l, 1);
+    }
+    if (!err.empty()) { delete P; return fail(IIF_ERR_ARG, err); }
+  }
+  const size_t n_up_ops = ops.size();
+  // ---- down pass (parents before children); the root keeps its up-solve result
+  if (o->downsolve) {
+    for (auto itc = post.rbegin(); itc != post.rend(); ++itc) {
+      const int cid = *itc, p = t->parent[cid];
+      if (p < 0) continue;
+      cur = cid;
+      for (int s : sp[cid]) {
+        auto ps = cslot[p].find(s);
+        if (ps == cslot[p].end()) { delete P; return fail(IIF_ERR_ARG, "plan_tree: separator missing from the parent clique"); }
+        add_copy(ps->second, cslot[cid][s]);
+        n_msgs++;
+      }
+      // addDownVariableFactors!: every factor touching a frontal; outside variables are read from the main graph
+      std::vector<int> touching;
+      for (int v : fr[cid]) for (int f : by_var[v]) touching.push_back(f);
+      std::sort(touching.begin(), touching.end());
+      touching.erase(std::unique(touching.begin(), touching.end()), touching.end());
+      std::vector<Inst> inst;
+      for (int f : touching) {
+        const iif_factor_desc& F = g->factors[f];
+        Inst e;
+        for (int k = 0; k < F.arity; ++k) {
+          auto it = cslot[cid].find(F.slot[k]);
+          e.vars.push_back(F.slot[k]);
+          e.rd.push_back(it != cslot[cid].end() ? it->second : F.slot[k]);
+        }
+        e.fi = fac_instance(f, e.rd);
+        e.mh = F.nmh != 0;
+        inst.push_back(e);
+      }
+      auto local_product = [&](int v) {
+        std::vector<Inst*> use;
+        for (auto& e : inst) if (has(e.vars, v)) use.push_back(&e);
+        if (!use.empty()) add_prop(cslot[cid][v], use, v);
+      };
+      std::vector<int> iterF;   // frontals sharing a factor iterate downIters times
+      for (auto& e : inst) {
+        std::vector<int> f2;
+        for (int v : e.vars) if (has(fr[cid], v)) f2.push_back(v);
+        if (f2.size() > 1) for (int v : f2) if (!has(iterF, v)) iterF.push_back(v);
+      }
+      std::vector<int> iterO;
+      for (int v : fr[cid]) if (has(iterF, v)) iterO.push_back(v);
+      for (int v : fr[cid]) if (!has(iterO, v)) local_product(v);
+      for (int it = 0; it < o->downIters; ++it) for (int v : iterO) local_product(v);
+      if (!err.empty()) { delete P; return fail(IIF_ERR_ARG, err); }
+    }
+  }
+  // ---- step 5: frontal beliefs go back to the main graph
+  for (int c = 0; c < ncl; ++c) {
+    cur = c;
+    for (int v : fr[c]) add_copy(cslot[c][v], v);
+  }
+  // ---- waves, lanes
+  std::vector<int> waves = levelize(ops);
+  int nw = 0;
+  for (int w : waves) nw = std::max(nw, w + 1);
+  std::vector<int> lane = assign_lanes(ncl, t->parent, children, ops, waves, o->lanes);
+  std::vector<int> order(ops.size());
+  for (size_t i = 0; i < ops.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return waves[a] < waves[b]; });
+  P->wave_off.assign(nw + 1, 0);
+  for (int i : order) P->wave_off[waves[i] + 1]++;
+  for (int w = 0; w < nw; ++w) P->wave_off[w + 1] += P->wave_off[w];
+  for (int i : order) {
+    iif_sched_op so;
+    so.kind = ops[i].kind; so.a = ops[i].a; so.b = ops[i].b; so.lane = lane[i];
+    P->ops.push_back(so);
+  }
+  int up_last = 0;
+  for (size_t i = 0; i < n_up_ops; ++i) up_last = std::max(up_last, waves[i] + 1);
+  P->up_last_wave = up_last;
+  P->n_conv = nconv;
+  P->n_prod = (int)P->props.size();
+  P->n_msgs = n_msgs;
+  int64_t off = 0;
+  for (auto& s : P->slots) { s.pts_off = (int32_t)off; off += (int64_t)s.cap * s.dim; }
+  *out = P;
+  return IIF_OK;
+}
+
+int32_t iifb200_plan_counts(const iifb200_plan* p, int32_t* c) {
+  if (!p || !c) return IIF_ERR_ARG;
+  c[0] = (int32_t)p->slots.size(); c[1] = (int32_t)p->factors.size(); c[2] = (int32_t)p->dists.size();
+  c[3] = (int32_t)p->dparams.size(); c[4] = (int32_t)p->props.size(); c[5] = (int32_t)p->ops.size();
+  c[6] = (int32_t)p->wave_off.size() - 1; c[7] = p->n_conv; c[8] = p->n_prod; c[9] = p->n_msgs;
+  c[10] = p->up_last_wave; c[11] = p->nvars;
+  for (int k = 12; k < 16; ++k) c[k] = 0;
+  return IIF_OK;
+}
+
+int32_t iifb200_plan_export(const iifb200_plan* p, iif_slot_desc* slots, iif_factor_desc* factors, iif_dist_desc* dists,
+                            double* dparams, iif_prop_op* props, iif_sched_op* ops, int32_t* wave_off) {
+  if (!p) return IIF_ERR_ARG;
+  if (slots) std::copy(p->slots.begin(), p->slots.end(), slots);
+  if (factors) std::copy(p->factors.begin(), p->factors.end(), factors);
+  if (dists) std::copy(p->dists.begin(), p->dists.end(), dists);
+  if (dparams) std::copy(p->dparams.begin(), p->dparams.end(), dparams);
+  if (props) std::copy(p->props.begin(), p->props.end(), props);
+  if (ops) std::copy(p->ops.begin(), p->ops.end(), ops);
+  if (wave_off) std::copy(p->wave_off.begin(), p->wave_off.end(), wave_off);
+  return IIF_OK;
+}
+
+}  // extern "C"
+
+// accessors for iifb200.cu (iifb200_plan_upload)
+const std::vector<iif_slot_desc>& iif_plan_slots(const iifb200_plan* p) { return p->slots; }
+const std::vector<iif_factor_desc>& iif_plan_factors(const iifb200_plan* p) { return p->factors; }
+const std::vector<iif_dist_desc>& iif_plan_dists(const iifb200_plan* p) { return p->dists; }
+const std::vector<double>& iif_plan_dparams(const iifb200_plan* p) { return p->dparams; }
+const std::vector<iif_prop_op>& iif_plan_props(const iifb200_plan* p) { return p->props; }
+const std::vector<iif_sched_op>& iif_plan_ops(const iifb200_plan* p) { return p->ops; }
+const std::vector<int32_t>& iif_plan_wave_off(const iifb200_plan* p) { return p->wave_off; }

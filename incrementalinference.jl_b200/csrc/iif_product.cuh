@@ -34,6 +34,11 @@ struct ProdSmem {
   double* P;      // F*N*d proposals
   double* mean;   // F*nn*d
   double* var;    // F*nn*d
+  double* irs;    // F*nn*d  rsqrt(var)
+  double* cm;     // N*d  per-sample conditional mean of the current label draw
+  double* cv;     // N*d  per-sample conditional variance
+  double* us;     // N*IIF_GIBBS_RND_PHASES  the level's uniforms of every owned sample (two-density products)
+  double* zs;     // N*d  normals of the next samplePoint
   double* post;   // N*d
   double* xa;     // N
   double* xb;     // loo_x2_doubles(N)
@@ -46,17 +51,21 @@ struct ProdSmem {
   int16_t* perm;  // 2*F*N
 };
 
-// F == 2 products tabulate the level's pair-weight matrix (N^2 doubles at the leaf level) in the scratch
-// region shared with the leave-one-out tile
-#define IIF_GIBBS_TAB_MAX 150
-__host__ __device__ inline bool gibbs_tab(int N) { return N <= IIF_GIBBS_TAB_MAX; }
+// the label draws keep one total per piece of four candidates and output sample in the scratch region that the
+// leave-one-out search uses afterwards
+#define IIF_GIBBS_FUSED_MAX 150  // largest N whose four tables of piece totals fit in shared memory
+__host__ __device__ inline bool gibbs_fused(int F, int N) { return F == 2 && N <= IIF_GIBBS_FUSED_MAX; }
+#define IIF_GIBBS_RND_PHASES 6   // staged uniforms per sample and level: F (1 + Niter) <= 6 for two densities, Niter <= 2
+__host__ __device__ inline size_t prod_scratch_doubles(int F, int N) {
+  // two densities build the level's four tables of piece totals at once
+  const size_t loo = (size_t)IIF_LOO_SCRATCH_N(N), pt = (size_t)(gibbs_fused(F, N) ? 4 : 1) * N * (size_t)((N + 3) >> 2);
+  return loo > pt ? loo : pt;
+}
 
 __host__ __device__ inline size_t prod_smem_bytes(int F, int N, int d, int nn, int L) {
-  size_t dbl = (size_t)F * N * d + 2 * (size_t)F * nn * d + (size_t)N * d + (size_t)loo_xa_doubles(N) + (size_t)loo_x2_doubles(N) + IIF_RED_DOUBLES +
-               (size_t)F * IIF_MAX_DIM + (size_t)nn + (size_t)F * (L + 1) * d;
-  size_t scr = (size_t)IIF_LOO_SCRATCH_N(N);
-  if (F == 2 && gibbs_tab(N) && (size_t)N * N > scr) scr = (size_t)N * N;
-  dbl += scr;
+  size_t dbl = (size_t)F * N * d + 3 * (size_t)F * nn * d + 4 * (size_t)N * d + (size_t)N * IIF_GIBBS_RND_PHASES + (size_t)loo_xa_doubles(N) +
+               (size_t)loo_x2_doubles(N) + IIF_RED_DOUBLES + (size_t)F * IIF_MAX_DIM + (size_t)nn + (size_t)F * (L + 1) * d;
+  dbl += prod_scratch_doubles(F, N);
   size_t i16 = 2 * (size_t)F * N + (size_t)(L + 2) + 3 * (size_t)nn + (size_t)L * N;  // permutations + tree structure
   return dbl * sizeof(double) + ((i16 * sizeof(int16_t) + 7) / 8) * 8;
 }
@@ -76,6 +85,147 @@ __device__ __forceinline__ double cond_gauss(int F, const double* mean, const do
   }
   if (lam > 0) mu = circ ? atan2(sn, cs) : a / lam;
   return lam;
+}
+
+// |a| clamped to 127 by integer min on the high word (the low word keeps its bits: |result| < 127.00001).  The Gaussian
+// kernel value of a clamped argument is below 1e-300, i.e. nothing, and the lock-step evaluation stays on its fast path.
+__device__ __forceinline__ double clamp_abs127(double a) {
+  return __hiloint2double(min(__double2hiint(a) & 0x7fffffff, 0x405FC000), __double2loint(a));
+}
+
+// Weights of the four candidate nodes [zb, zb+4) of one density at one level given a Gaussian (m, cv) per coordinate
+// (see the Gibbs section of the kernel).  mean / var / irs / wt point at the level's first node.  POINT: cv == 0
+// (sampleIndices), the stored rsqrt(var) is used; LEAF: every candidate has the same variance, the conditional rsqrt
+// is hoisted.  One-coordinate Euclid beliefs (the chain benchmark):
+template <bool POINT, bool LEAF>
+__device__ __forceinline__ void gibbs_piece_d1(const double* __restrict__ mean, const double* __restrict__ var,
+                                               const double* __restrict__ irs, const double* __restrict__ wt, int nz,
+                                               int zb, double m0, double cv0, const double* __restrict__ tab,
+                                               double (&w)[4]) {
+  double a[4], pre[4], e[4];
+  const double rsl = (!POINT && LEAF) ? rsqrt(var[0] + cv0) : 0.0;
+  if (zb + 4 <= nz) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int z = zb + u;
+      const double rs = POINT ? irs[z] : LEAF ? rsl : rsqrt(var[z] + cv0);
+      a[u] = clamp_abs127((mean[z] - m0) * (rs * IIF_GSCALE));
+      pre[u] = wt[z] * rs;
+    }
+  } else {  // last piece of the level: clamp the index, padding lanes weigh nothing
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int z = min(zb + u, nz - 1);
+      const double rs = POINT ? irs[z] : LEAF ? rsl : rsqrt(var[z] + cv0);
+      a[u] = clamp_abs127((mean[z] - m0) * (rs * IIF_GSCALE));
+      pre[u] = (zb + u < nz) ? wt[z] * rs : 0.0;
+    }
+  }
+  gauss_negU<4>(a, tab, e);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) w[u] = e[u] * pre[u];
+}
+
+// general form: several coordinates, circular coordinates, partial masks
+__device__ __forceinline__ void gibbs_piece_nd(const double* __restrict__ mean, const double* __restrict__ var,
+                                               const double* __restrict__ irs, const double* __restrict__ wt, int nz, int zb,
+                                               int d, int32_t cmask, int32_t hasmask, bool point, bool leaf,
+                                               const double* __restrict__ m, const double* __restrict__ cv, double (&w)[4]) {
+  double rsl[IIF_MAX_DIM] = {0, 0, 0, 0};
+  if (!point && leaf)
+    for (int c = 0; c < d; ++c) rsl[c] = rsqrt(var[c] + cv[c]);
+  double arg[4], pre[4], e[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int z = min(zb + u, nz - 1);
+    double q = 0.0, pr = (zb + u < nz) ? wt[z] : 0.0;
+    for (int c = 0; c < d; ++c) {
+      if (!((hasmask >> c) & 1)) continue;
+      const double rs = point ? irs[z * d + c] : leaf ? rsl[c] : rsqrt(var[z * d + c] + cv[c]);
+      const double tq = mdiff(mean[z * d + c], m[c], is_circ(cmask, c)) * rs;
+      q = fma(tq, tq, q);
+      pr *= rs;
+    }
+    arg[u] = fmax(-0.5 * q, -700.0);
+    pre[u] = pr;
+  }
+  exp_negU<4>(arg, e);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) w[u] = e[u] * pre[u];
+}
+
+// runtime dispatch of one piece
+__device__ __forceinline__ void gibbs_piece(bool d1, const double* mean, const double* var, const double* irs,
+                                            const double* wt, int nz, int zb, int d, int32_t cmask, int32_t hasmask,
+                                            bool point, bool leaf, const double* m, const double* cv, const double* tab,
+                                            double (&w)[4]) {
+  if (d1 && (hasmask & 1)) {
+    if (point) gibbs_piece_d1<true, false>(mean, var, irs, wt, nz, zb, m[0], 0.0, tab, w);
+    else if (leaf) gibbs_piece_d1<false, true>(mean, var, irs, wt, nz, zb, m[0], cv[0], tab, w);
+    else gibbs_piece_d1<false, false>(mean, var, irs, wt, nz, zb, m[0], cv[0], tab, w);
+  } else {
+    gibbs_piece_nd(mean, var, irs, wt, nz, zb, d, cmask, hasmask, point, leaf, m, cv, w);
+  }
+}
+
+// piece totals of `rows` rows x np pieces into PT (row stride NPs); row r has the conditional Gaussian
+// (mrow + r * mstride, cvrow + r * mstride).  All threads of the CTA; the mode is uniform, so the loop is specialised.
+template <bool POINT, bool LEAF>
+__device__ __forceinline__ void gibbs_build_d1(const double* mean, const double* var, const double* irs, const double* wt,
+                                               int nz, int np, int rows, const double* mrow, const double* cvrow,
+                                               int mstride, const double* tab, double* PT, int NPs) {
+  const float inv_np = 1.0f / (float)np;
+  for (int p = threadIdx.x; p < rows * np; p += IIF_NT) {
+    const int row = (int)(((float)p + 0.5f) * inv_np), pc = p - row * np;   // exact: p < 2^14
+    double w[4];
+    gibbs_piece_d1<POINT, LEAF>(mean, var, irs, wt, nz, pc << 2, mrow[row * mstride], POINT ? 0.0 : cvrow[row * mstride], tab, w);
+    PT[row * NPs + pc] = (w[0] + w[1]) + (w[2] + w[3]);
+  }
+}
+__device__ __forceinline__ void gibbs_build(bool d1, const double* mean, const double* var, const double* irs,
+                                            const double* wt, int nz, int np, int rows, int d, int32_t cmask,
+                                            int32_t hasmask, bool point, bool leaf, const double* mrow,
+                                            const double* cvrow, const double* tab, double* PT, int NPs) {
+  if (d1 && (hasmask & 1)) {
+    if (point) gibbs_build_d1<true, false>(mean, var, irs, wt, nz, np, rows, mrow, cvrow, 1, tab, PT, NPs);
+    else if (leaf) gibbs_build_d1<false, true>(mean, var, irs, wt, nz, np, rows, mrow, cvrow, 1, tab, PT, NPs);
+    else gibbs_build_d1<false, false>(mean, var, irs, wt, nz, np, rows, mrow, cvrow, 1, tab, PT, NPs);
+    return;
+  }
+  const float inv_np = 1.0f / (float)np;
+  for (int p = threadIdx.x; p < rows * np; p += IIF_NT) {
+    const int row = (int)(((float)p + 0.5f) * inv_np), pc = p - row * np;
+    double w[4];
+    gibbs_piece_nd(mean, var, irs, wt, nz, pc << 2, d, cmask, hasmask, point, leaf, mrow + row * d, cvrow + row * d, w);
+    PT[row * NPs + pc] = (w[0] + w[1]) + (w[2] + w[3]);
+  }
+}
+
+// Label pick when every weight of a draw underflowed: p_z = sum_c dl^2 / v + log v, weights exp(-(p_z - min p)/2) wt_z,
+// sequential inverse CDF — the form the oracle always uses.  Rare (a sample hundreds of bandwidths from every node).
+__device__ __noinline__ int gibbs_pick_exact(const double* mean, const double* var, const double* wt, int nz, int d,
+                                             int32_t cmask, int32_t hasmask, const double* m, const double* cv, double u) {
+  auto expo = [&](int z) {
+    double p = 0.0;
+    for (int c = 0; c < d; ++c) {
+      if (!((hasmask >> c) & 1)) continue;
+      const double dl = mdiff(mean[z * d + c], m[c], is_circ(cmask, c));
+      const double v = var[z * d + c] + cv[c];
+      p += dl * dl / v + log(v);
+    }
+    return p;
+  };
+  double best = INFINITY;
+  for (int z = 0; z < nz; ++z) best = fmin(best, expo(z));
+  double tot = 0.0;
+  for (int z = 0; z < nz; ++z) tot += exp(-0.5 * (expo(z) - best)) * wt[z];
+  const double thr = u * tot;
+  double cum = 0.0;
+  for (int z = 0; z < nz; ++z) {
+    cum += exp(-0.5 * (expo(z) - best)) * wt[z];
+    if (thr < cum) return z;
+  }
+  return nz - 1;
 }
 
 __global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
@@ -112,6 +262,11 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     sm.P = p; p += (size_t)F * N * d;
     sm.mean = p; p += (size_t)F * nn * d;
     sm.var = p; p += (size_t)F * nn * d;
+    sm.irs = p; p += (size_t)F * nn * d;
+    sm.cm = p; p += (size_t)N * d;
+    sm.cv = p; p += (size_t)N * d;
+    sm.us = p; p += (size_t)N * IIF_GIBBS_RND_PHASES;
+    sm.zs = p; p += (size_t)N * d;
     sm.post = p; p += (size_t)N * d;
     sm.xa = p; p += loo_xa_doubles(N);
     sm.xb = p; p += loo_x2_doubles(N);
@@ -119,12 +274,8 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     sm.bwk = p; p += F * IIF_MAX_DIM;
     sm.wt = p; p += nn;
     sm.minvar = p; p += (size_t)F * (L + 1) * d;
-    sm.scr = p;  // last: loo scratch, aliased by the F == 2 pair-weight matrix (sized by prod_smem_bytes)
-    {
-      size_t scrn = (size_t)IIF_LOO_SCRATCH_N(N);
-      if (F == 2 && gibbs_tab(N) && (size_t)N * N > scrn) scrn = (size_t)N * N;
-      p += scrn;
-    }
+    sm.scr = p;  // last: leave-one-out scratch, used for the label draws' piece totals before
+    p += prod_scratch_doubles(F, N);
     sm.perm = reinterpret_cast<int16_t*>(p);
   }
   {
@@ -248,29 +399,31 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     for (int z = tid; z < nn; z += IIF_NT) sm.wt[z] = (double)(T.hi[z] - T.lo[z] + 1) / (double)N;
     __syncthreads();
 
+    // reciprocal standard deviations of every node (the label draws below multiply instead of dividing)
+    for (int i = tid; i < F * nn * d; i += IIF_NT) sm.irs[i] = rsqrt(sm.var[i]);
+    __syncthreads();
     IIF_PHASE(10);
-    // ---- 2./3. multiscale Gibbs: G lanes per output sample (G = largest power of two <= threads/N).
-    // Every lane owns a contiguous block of the level's candidate nodes, accumulates its weights in
-    // chunks (kept in registers), a group scan locates the lane and chunk holding the inverse-CDF
-    // crossing and only that chunk is re-evaluated.  Weights are taken relative to an analytic lower
-    // bound of the exponent so a single pass suffices; the exact-minimum form (what the oracle
-    // computes) is the fallback when every weight underflows.
+    // ---- 2./3. multiscale Gibbs (KDE.jl gibbs1; Ihler, Sudderth, Freeman & Willsky 2003), per output sample:
+    //   labels := roots; for every level: X = samplePoint(product of the selected nodes), levelDown,
+    //   sampleIndices(X) = every density's label given X, then Niter sweeps of sampleIndex(j) = label of density j
+    //   given the other densities' selected nodes; the sample is samplePoint(selected leaf kernels).
+    // Every label draw is an inverse-CDF pick over the nz candidate nodes of the level with weights
+    //   w_z = wt_z prod_c rsqrt(v_zc) exp(-1/2 sum_c (mean_zc - m_c)^2 / v_zc),   v_zc = var_zc + cv_c,
+    // (m, cv) = (X, 0) for sampleIndices and the product Gaussian of the other densities' nodes for sampleIndex.
+    // Mapping: thread i < nloc OWNS output sample s (labels in registers, the random draws, the pick).  The N x nz
+    // weight evaluations of a draw — the expensive part — are dealt flat to ALL threads of the CTA in pieces of four
+    // candidates (one lock-step gauss_negU / exp_negU group); only the piece totals are stored (in the idle
+    // leave-one-out scratch).  The owner walks its row of totals, finds the piece holding u * total and re-evaluates
+    // that piece alone.  In a cluster launch the output samples are dealt round-robin to the ranks.
     const int niter = g.sp->gibbsNiter;
     const uint64_t seed = g.sp->seed;
     const uint32_t call = (uint32_t)t.call_id;
-    int G = 1;
-    while (G < 32 && 2 * G * N <= IIF_NT) G <<= 1;  // small CTAs (wide waves): G = 1, least total work
-    // in a cluster launch the output samples are dealt round-robin to the ranks (every rank builds the same
-    // trees and tables, draws only its own samples and broadcasts their points before the bandwidth search)
     const int crank = (int)cooperative_groups::this_cluster().block_rank();
-    const int smp = (tid / G) * cC + crank, gl = tid % G;   // sample, lane within the group
-    const bool live = smp < N;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    // whole warps without a sample skip; partial groups never occur (G divides 32)
-    const int s = smp;
+    const int nloc = (N - crank + cC - 1) / cC;
+    const bool own = tid < nloc;
+    const int s = tid * cC + crank;
     int node[IIF_MAX_FACTORS];
-    for (int j = 0; j < F; ++j) node[j] = 0;  // roots
-    const bool tab = (F == 2) && gibbs_tab(N);
+    for (int j = 0; j < F; ++j) node[j] = 0;  // levelInit / initIndices: roots (their uniforms are skipped)
     // Random-stream layout (AMP.manifoldProduct `_randU` / `_randN`; KDE.jl sizes them Np*Ndens*(Niter+2)*Nlevels and
     // Ndim*Np*(Nlevels+1)): per output sample the uniforms go to initIndices (F), then per level to sampleIndices (F)
     // and Niter sweeps of sampleIndex (F each); the normals are the Nlevels+1 samplePoint draws (d each).
@@ -281,332 +434,200 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     auto gibbs_n = [&](uint32_t idx) -> double {
       return (randN != nullptr && t.randn_off >= 0) ? randN[t.randn_off + idx] : rs_normal(seed, call, IIF_RS_GIBBS_N, idx);
     };
-    // samplePoint: a point from the product of the currently selected Gaussians (every lane of a group computes it)
-    auto sample_point = [&](int l, double* X) {
-      for (int c = 0; c < d; ++c) {
-        double mu = 0;
-        const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, -1, nn, d, c, is_circ(cm, c), mu);
-        X[c] = lam > 0 ? madd(mu, sqrt(1.0 / lam) * gibbs_n((uint32_t)s * nblk + (uint32_t)((l - 1) * d + c)), is_circ(cm, c)) : 0.0;
-      }
-    };
-    // Label draw of density j at level l given a Gaussian (cmu, cvar) per coordinate (`has[c]`: coordinate takes part):
-    // weight_z = wt_z * prod_c rsqrt(v) * exp(-1/2 sum_c dl^2 / v),  v = var_z + cvar  (the oracle's
-    // exp(-(p_z - min p)/2) with p_z = sum dl^2/v + log v, up to the common factor).  sampleIndex(j) passes the product
-    // of the other densities' selected nodes, sampleIndices passes the point X with cvar = 0.  The G lanes of the
-    // sample's group own contiguous blocks of candidates, accumulate chunk sums in registers, a group scan locates the
-    // lane and chunk holding the inverse-CDF crossing and only that chunk is re-evaluated.  Weights are relative to an
-    // analytic lower bound of the exponent (single pass); exact-minimum fallback when every weight underflows.
-    auto draw_label = [&](int j, int l, const double* cmu, const double* cvar, const bool* has, double u) -> int {
-      const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
-      const bool leaf = (l == L);
-      const int B = (nz + G - 1) / G;
-      const int zb = gl * B, ze = min(zb + B, nz);
-      const int CH = (B + 15) >> 4;  // <= 16 chunks per lane; CH == 1 (B <= 16) needs no re-evaluation
-      const double* mj = sm.mean + ((size_t)j * nn + z0) * d;
-      const double* vj = sm.var + ((size_t)j * nn + z0) * d;
-      const double* wj = sm.wt + z0;
-      // at the leaf level v is the same for every candidate, so 1/v is hoisted and rsqrt(v) cancels
-      double iv[IIF_MAX_DIM] = {0, 0, 0, 0};
-      for (int c = 0; c < d; ++c)
-        if (has[c] && leaf) iv[c] = 1.0 / (vj[c] + cvar[c]);
-      auto cand = [&](int z, double& pre) -> double {  // exponent (>= 0) and prefactor of candidate z
-        double p = 0.0;
-        pre = wj[z];
-        for (int c = 0; c < d; ++c) {
-          if (!has[c]) continue;
-          const double dl = mdiff(mj[z * d + c], cmu[c], is_circ(cm, c));
-          if (leaf) p = fma(dl * dl, iv[c], p);
-          else {
-            const double rs = rsqrt(vj[z * d + c] + cvar[c]);
-            p = fma(dl * dl, rs * rs, p);
-            pre *= rs;
-          }
-        }
-        return p;
-      };
-      auto weight = [&](int z, double base) -> double {
-        double pre;
-        const double p = cand(z, pre);
-        return exp_neg(fmin(-0.5 * (p - base), 0.0)) * pre;
-      };
-      double ct[16];
-      double Tl = 0.0, off = 0.0, tot = 0.0, base = 0.0;
-      for (int attempt = 0; attempt < 2; ++attempt) {
-        Tl = 0.0;
-#pragma unroll
-        for (int ch = 0; ch < 16; ++ch) {
-          const int cb = zb + ch * CH;
-          double sacc = 0.0;
-          if (cb < ze) {
-            const int ce = min(cb + CH, ze);
-            for (int z = cb; z < ce; ++z) sacc += weight(z, base);
-          }
-          ct[ch] = sacc;
-          Tl += sacc;
-        }
-        double inc = Tl;  // inclusive scan over the group's lanes
-        for (int o = 1; o < G; o <<= 1) {
-          const double y = __shfl_up_sync(gmask, inc, o, G);
-          if (gl >= o) inc += y;
-        }
-        off = inc - Tl;
-        tot = __shfl_sync(gmask, inc, G - 1, G);
-        if (tot > 1e-280 || attempt == 1) break;
-        // every weight underflowed: redo relative to the exact minimum exponent
-        double pm = INFINITY;
-        for (int z = zb; z < ze; ++z) { double pre; pm = fmin(pm, cand(z, pre)); }
-        for (int o = G >> 1; o > 0; o >>= 1) pm = fmin(pm, __shfl_xor_sync(gmask, pm, o, G));
-        base = pm;
-      }
-      const double thr = u * tot;
-      // every lane searches its own chunks (no divergent owner path); exactly one lane finds the crossing
-      int mypick = -1;
-      if ((zb < ze) && (thr >= off) && (thr < off + Tl)) {
-        double run = off;
-        mypick = ze - 1;
-        bool found = false;
-#pragma unroll
-        for (int ch = 0; ch < 16; ++ch) {
-          const int cb = zb + ch * CH;
-          if (!found && cb < ze) {
-            if (thr < run + ct[ch]) {
-              const int ce = min(cb + CH, ze);
-              mypick = ce - 1;
-              if (CH > 1) {
-                double cum = run;
-                for (int z = cb; z < ce; ++z) {
-                  cum += weight(z, base);
-                  if (thr < cum) { mypick = z; break; }
-                }
-              }
-              found = true;
-            }
-            run += ct[ch];
-          }
-        }
-      }
-      const unsigned hit = __ballot_sync(gmask, mypick >= 0) & gmask;
-      int pick = nz - 1;  // rounding left thr >= total: the oracle falls back to the last candidate
-      if (hit) pick = __shfl_sync(gmask, mypick, (__ffs(hit) - 1) & (G - 1), G);
-      return z0 + pick;
-    };
-    // sampleIndices(X): the label of every density given the point X, over the whole level list
-    auto sample_indices = [&](int l, const double* X) {
-      const double zero[IIF_MAX_DIM] = {0, 0, 0, 0};
-      for (int j = 0; j < F; ++j) {
-        bool has[IIF_MAX_DIM];
-        for (int c = 0; c < IIF_MAX_DIM; ++c) has[c] = c < d && ((masks[j] >> c) & 1);
-        node[j] = draw_label(j, l, X, zero, has, gibbs_u((uint32_t)s * ublk + (uint32_t)(F + (l - 1) * F * (niter + 1) + j)));
-      }
-    };
-    if (tab) {
-      // ---- F == 2: the conditional of one density depends only on the node selected in the other, so the
-      // level's pair-weight matrix K[a][b] = prod_c rsqrt(va+vb) exp(-(ma-mb)^2 / 2(va+vb)) is tabulated ONCE
-      // per level by the whole CTA (shared with the leave-one-out tile) and every sample's two label draws
-      // become a weighted column / row scan of K — no transcendental per sample.
-      double* K = sm.scr;
-      const int32_t both = masks[0] & masks[1];
-      const double* m0 = sm.mean;
-      const double* m1 = sm.mean + (size_t)nn * d;
-      const double* v0 = sm.var;
-      const double* v1 = sm.var + (size_t)nn * d;
-      for (int l = 1; l <= L; ++l) {
-        const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0;
-        // samplePoint from the product of the nodes selected at the coarser level; levelDown then replaces every
-        // level list by its children (leaves stay) and sampleIndices re-draws every label over the new list
-        double X[IIF_MAX_DIM] = {0, 0, 0, 0};
-        if (live) sample_point(l, X);
-        __syncthreads();  // the previous level's K is no longer read
-        if (l == L && d == 1 && !is_circ(cm, 0)) {
-          // leaf level, one Euclid coordinate: every node is a single kernel of variance h_j^2, so the table is
-          // the Gaussian kernel matrix between the two point sets: rs exp(-(ma - mb)^2 rs^2 / 2), rs constant
-          const int nzz = nz * nz;
-          const float invnz = 1.0f / (float)nz;
-          const double rs = rsqrt(v0[z0] + v1[z0]);
-          const double sc = IIF_GSCALE * rs;
-          for (int base = tid; base < nzz; base += 4 * IIF_NT) {
-            double zz[4], e[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int idx = min(base + u * IIF_NT, nzz - 1);
-              const int a = (int)(((float)idx + 0.5f) * invnz), b = idx - a * nz;
-              zz[u] = (m0[z0 + a] - m1[z0 + b]) * sc;
-            }
-            gauss_negU<4>(zz, sm.tab, e);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (base + u * IIF_NT < nzz) K[base + u * IIF_NT] = e[u] * rs;
-          }
-        } else {
-          // four table entries per thread in lockstep (independent rsqrt / exp chains)
-          const int nzz = nz * nz;
-          const float invnz = 1.0f / (float)nz;
-          for (int base = tid; base < nzz; base += 4 * IIF_NT) {
-            double arg[4], pre[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int idx = min(base + u * IIF_NT, nzz - 1);
-              const int a = (int)(((float)idx + 0.5f) * invnz), b = idx - a * nz;  // exact: nz <= 256
-              double pexp = 0.0, pr = 1.0;
-              for (int c = 0; c < d; ++c) {
-                if (!((both >> c) & 1)) continue;
-                const double dl = mdiff(m0[(z0 + a) * d + c], m1[(z0 + b) * d + c], is_circ(cm, c));
-                const double rs = rsqrt(v0[(z0 + a) * d + c] + v1[(z0 + b) * d + c]);
-                pexp = fma(dl * dl, rs * rs, pexp);
-                pr *= rs;
-              }
-              arg[u] = -0.5 * pexp;
-              pre[u] = pr;
-            }
-            double e[4];
-            exp_negU<4>(arg, e);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (base + u * IIF_NT < nzz) K[base + u * IIF_NT] = e[u] * pre[u];
-          }
-        }
-        __syncthreads();
-        IIF_PHASE(7);
-        if (live) {
-          sample_indices(l, X);
-          const double* wl = sm.wt + z0;
-          const int B = (nz + G - 1) / G;
-          const int zb = gl * B, ze = min(zb + B, nz);
-          const int CHL = (B + 7) >> 3;  // every lane splits its block into <= 8 chunks of CHL candidates
-          for (int it = 0; it < niter; ++it) {
-            for (int j = 0; j < 2; ++j) {
-              // density 0 scans column b of K (stride nz), density 1 scans row a (stride 1)
-              const int other = node[1 - j] - z0;
-              const double* Kb = (j == 0) ? K + other : K + (size_t)other * nz;
-              const int stride = (j == 0) ? nz : 1;
-              const double u = gibbs_u((uint32_t)s * ublk + (uint32_t)(2 + (l - 1) * 2 * (niter + 1) + 2 + it * 2 + j));
-              IIF_PHASE(16);
-              // chunk sums: eight independent accumulation chains
-              double ct[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-              for (int e = 0; e < CHL; ++e) {
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                  const int z = zb + ch * CHL + e;
-                  if (z < ze) ct[ch] = fma(wl[z], Kb[(size_t)z * stride], ct[ch]);
-                }
-              }
-              const double Tl = ((ct[0] + ct[1]) + (ct[2] + ct[3])) + ((ct[4] + ct[5]) + (ct[6] + ct[7]));
-              IIF_PHASE(17);
-              double inc = Tl;
-              for (int o = 1; o < G; o <<= 1) {
-                const double y = __shfl_up_sync(gmask, inc, o, G);
-                if (gl >= o) inc += y;
-              }
-              const double off = inc - Tl;
-              const double tot = __shfl_sync(gmask, inc, G - 1, G);
-              IIF_PHASE(18);
-              int pick;
-              if (tot > 1e-290) {
-                const double thr = u * tot;
-                int mypick = -1;
-                if ((zb < ze) && (thr >= off) && (thr < off + Tl)) {
-                  // the chunk holding the crossing, then only that chunk is walked again
-                  double run = off;
-                  int cb = zb;
-                  bool go = true;
-#pragma unroll
-                  for (int ch = 0; ch < 7; ++ch) {
-                    go = go && (thr >= run + ct[ch]) && (cb + CHL < ze);
-                    run += go ? ct[ch] : 0.0;
-                    cb += go ? CHL : 0;
-                  }
-                  const int ce = min(cb + CHL, ze);
-                  mypick = ce - 1;
-                  double cum = run;
-                  for (int z = cb; z < ce; ++z) {
-                    cum = fma(wl[z], Kb[(size_t)z * stride], cum);
-                    if (thr < cum) { mypick = z; break; }
-                  }
-                }
-                const unsigned hit = __ballot_sync(gmask, mypick >= 0) & gmask;
-                pick = nz - 1;
-                if (hit) pick = __shfl_sync(gmask, mypick, (__ffs(hit) - 1) & (G - 1), G);
-              } else {
-                // every pair weight underflowed: relative to the smallest exponent (what the oracle does) the
-                // closest candidate carries all the mass
-                double best = INFINITY;
-                int bz = 0;
-                for (int z = 0; z < nz; ++z) {
-                  const int a = (j == 0) ? z : other, b = (j == 0) ? other : z;
-                  double pexp = 0.0;
-                  for (int c = 0; c < d; ++c) {
-                    if (!((both >> c) & 1)) continue;
-                    const double dl = mdiff(m0[(z0 + a) * d + c], m1[(z0 + b) * d + c], is_circ(cm, c));
-                    const double v = v0[(z0 + a) * d + c] + v1[(z0 + b) * d + c];
-                    pexp += dl * dl / v + log(v);
-                  }
-                  if (pexp < best) { best = pexp; bz = z; }
-                }
-                pick = bz;
-              }
-              IIF_PHASE(20);
-              node[j] = z0 + pick;
-            }
-          }
-        }
-        IIF_PHASE(15);
-      }
-      __syncthreads();  // K (aliases the leave-one-out scratch) is dead from here on
-    } else if (live) {
-      for (int l = 1; l <= L; ++l) {
-        double X[IIF_MAX_DIM] = {0, 0, 0, 0};
-        sample_point(l, X);      // samplePoint, then levelDown (implicit) and sampleIndices over the new level list
-        sample_indices(l, X);
-        for (int it = 0; it < niter; ++it) {
-          for (int j = 0; j < F; ++j) {  // sampleIndex(j): label given the other densities' selected nodes
-            double cmu[IIF_MAX_DIM] = {0, 0, 0, 0}, cvar[IIF_MAX_DIM] = {0, 0, 0, 0};
-            bool has[IIF_MAX_DIM] = {false, false, false, false};
-            for (int c = 0; c < d; ++c) {
-              if (!((masks[j] >> c) & 1)) continue;
-              const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, j, nn, d, c, is_circ(cm, c), cmu[c]);
-              has[c] = lam > 0;
-              cvar[c] = has[c] ? 1.0 / lam : 0.0;
-            }
-            node[j] = draw_label(j, l, cmu, cvar, has,
-                                 gibbs_u((uint32_t)s * ublk + (uint32_t)(F + (l - 1) * F * (niter + 1) + F + it * F + j)));
-          }
-        }
-      }
+    const int NP = (N + 3) >> 2;     // row stride of the piece totals
+    const bool d1 = (d == 1) && !is_circ(cm, 0);
+    int32_t anyother[IIF_MAX_FACTORS];  // coordinates some OTHER density informs (uniform over the samples)
+    for (int j = 0; j < F; ++j) {
+      int32_t m = 0;
+      for (int k = 0; k < F; ++k) if (k != j) m |= masks[k];
+      anyother[j] = m;
     }
-    IIF_PHASE(11);
-    if (live) {
-      // samplePoint: draw from the product of the selected leaf kernels
-      if (gl == 0) {
+    // inverse-CDF pick in a row of piece totals: four interleaved partial sums locate the quarter, a short walk the
+    // piece, `eval` re-evaluates that piece's four weights (same function, same arguments => same bits as the build)
+    auto pick_row = [&](const double* rowp, int np, int nz, double u, auto&& eval, auto&& exact) -> int {
+      const int ch = (np + 3) >> 2;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int k = 0; k < ch; ++k) {
+        s0 += rowp[k];
+        if (k + ch < np) s1 += rowp[k + ch];
+        if (k + 2 * ch < np) s2 += rowp[k + 2 * ch];
+        if (k + 3 * ch < np) s3 += rowp[k + 3 * ch];
+      }
+      const double c1 = s0 + s1, c2 = c1 + s2, tot = c2 + s3;
+      if (!(tot > 1e-280)) return exact();   // every weight underflowed (or NaN): the oracle's exact form
+      const double thr = u * tot;
+      double run = 0.0;
+      int pc = 0;
+      if (thr >= s0) { run = s0; pc = ch; }
+      if (thr >= c1) { run = c1; pc = 2 * ch; }
+      if (thr >= c2) { run = c2; pc = 3 * ch; }
+      pc = min(pc, np - 1);
+      for (; pc < np - 1; ++pc) {
+        const double nx = run + rowp[pc];
+        if (thr < nx) break;
+        run = nx;
+      }
+      double w[4];
+      eval(pc << 2, w);
+      int pick = min((pc << 2) + 3, nz - 1);  // rounding left thr >= total: the last candidate (as the oracle does)
+      double cum = run;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        cum += w[q];
+        if ((pc << 2) + q < nz && thr < cum) { pick = (pc << 2) + q; break; }
+      }
+      return pick;
+    };
+    // per-level random numbers of the owned sample, drawn by ALL threads during the build pass
+    const int nph = F * (1 + niter);
+    const bool fused = gibbs_fused(F, N);
+    const bool rnd_staged = fused && nph <= IIF_GIBBS_RND_PHASES;
+    if (rnd_staged) {
+      for (int r = tid; r < nloc * d; r += IIF_NT) {  // normals of the first samplePoint
+        const int i = r / d, c = r - i * d;
+        sm.zs[r] = gibbs_n((uint32_t)(i * cC + crank) * nblk + (uint32_t)c);
+      }
+      __syncthreads();
+    }
+    for (int l = 1; l <= L; ++l) {
+      const int z0 = T.lev_off[l], nz = T.lev_off[l + 1] - z0, np = (nz + 3) >> 2;
+      const bool leaf = (l == L);
+      if (own) {  // samplePoint from the product of the nodes selected at the coarser level
         for (int c = 0; c < d; ++c) {
           double mu = 0;
           const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, -1, nn, d, c, is_circ(cm, c), mu);
-          double x;
-          if (lam > 0) {
-            const double e = gibbs_n((uint32_t)s * nblk + (uint32_t)(L * d + c));
-            x = madd(mu, sqrt(1.0 / lam) * e, is_circ(cm, c));
-          } else if (t.target_slot >= 0) {
-            // coordinates no proposal informs keep oldPoints (GraphProductOperations.jl:37-45)
-            const iif_slot_desc S = g.slots[t.target_slot];
-            const int len = g.npts[t.target_slot];
-            if (s < len) x = g.pts[S.pts_off + s * d + c];
-            else if (len > 0) {
-              double uu = rs_uniform(seed, call, IIF_RS_OLDPAD, (uint32_t)(s * (d + 1)));
-              int k = min((int)(uu * len), len - 1);
-              double e = rs_normal(seed, call, IIF_RS_OLDPAD, (uint32_t)(s * (d + 1) + 1 + c));
-              x = madd(g.pts[S.pts_off + k * d + c], g.bw[t.target_slot * IIF_MAX_DIM + c] * e, is_circ(cm, c));
-            } else x = 0.0;
-          } else {
-            x = t.old_pts ? t.old_pts[s * d + c] : 0.0;
+          const double e = rnd_staged ? sm.zs[tid * d + c] : gibbs_n((uint32_t)s * nblk + (uint32_t)((l - 1) * d + c));
+          sm.cm[tid * d + c] = lam > 0 ? madd(mu, sqrt(1.0 / lam) * e, is_circ(cm, c)) : 0.0;
+          sm.cv[tid * d + c] = 0.0;
+        }
+      }
+      IIF_PHASE(20);
+      // levelDown: the level lists become the children of the previous lists (leaves stay); every label is re-drawn
+      if (fused) {
+        // ---- two densities: none of the level's four weight tables depends on a label drawn at this level — the
+        // sampleIndices rows are the samples (given X), the sampleIndex rows of density j are the nz candidate nodes of
+        // the OTHER density (its selected node is the whole condition) — so all piece totals are built in one flat
+        // pass between two barriers, together with the level's uniforms and the next samplePoint's normals.
+        __syncthreads();  // X of every sample visible; the previous level's picks are done
+        IIF_PHASE(17);
+        double* PTq[4] = {sm.scr, sm.scr + (size_t)N * NP, sm.scr + 2 * (size_t)N * NP, sm.scr + 3 * (size_t)N * NP};
+        for (int q = 0; q < 4; ++q) {
+          const int j = q & 1;
+          const bool point = q < 2;
+          const int32_t hasmask = masks[j] & (point ? fullmask : anyother[j]);
+          const size_t bj = ((size_t)j * nn + z0) * d, bo = ((size_t)(1 - j) * nn + z0) * d;
+          gibbs_build(d1, sm.mean + bj, sm.var + bj, sm.irs + bj, sm.wt + z0, nz, np, point ? nloc : nz, d, cm, hasmask, point,
+                      leaf, point ? sm.cm : sm.mean + bo, point ? sm.cv : sm.var + bo, sm.tab, PTq[q], NP);
+        }
+        if (rnd_staged) {
+          for (int r = tid; r < nloc * nph; r += IIF_NT) {
+            const int i = r / nph, ph = r - i * nph;
+            sm.us[r] = gibbs_u((uint32_t)(i * cC + crank) * ublk + (uint32_t)(F + (l - 1) * nph + ph));
           }
-          if (cC > 1) {
-            for (int r = 0; r < cC; ++r) cooperative_groups::this_cluster().map_shared_rank(sm.post, r)[s * d + c] = x;
-          } else {
-            sm.post[s * d + c] = x;
+          for (int r = tid; r < nloc * d; r += IIF_NT) {
+            const int i = r / d, c = r - i * d;
+            sm.zs[r] = gibbs_n((uint32_t)(i * cC + crank) * nblk + (uint32_t)(l * d + c));
           }
         }
-        if (t.out_labels != nullptr)   // every sample belongs to exactly one rank
-          for (int j = 0; j < F; ++j) t.out_labels[s * F + j] = permA[j * N + T.lo[node[j]]];
+        IIF_PHASE(7);
+        __syncthreads();
+        IIF_PHASE(18);
+        if (own) {
+          for (int phase = 0; phase < nph; ++phase) {
+            const int j = phase & 1;
+            const bool point = phase < 2;
+            const int32_t hasmask = masks[j] & (point ? fullmask : anyother[j]);
+            const size_t bj = ((size_t)j * nn + z0) * d;
+            const double* mj = sm.mean + bj;
+            const double* vj = sm.var + bj;
+            const double* rj = sm.irs + bj;
+            const double* wl = sm.wt + z0;
+            const int row = point ? tid : node[1 - j] - z0;
+            const double* mrow = point ? sm.cm + tid * d : sm.mean + (size_t)node[1 - j] * d + (size_t)(1 - j) * nn * d;
+            const double* cvrow = point ? sm.cv + tid * d : sm.var + (size_t)node[1 - j] * d + (size_t)(1 - j) * nn * d;
+            const double u = rnd_staged ? sm.us[tid * nph + phase] : gibbs_u((uint32_t)s * ublk + (uint32_t)(F + (l - 1) * nph + phase));
+            const int pick = pick_row(
+                PTq[point ? j : 2 + j] + (size_t)row * NP, np, nz, u,
+                [&](int zb, double (&w)[4]) { gibbs_piece(d1, mj, vj, rj, wl, nz, zb, d, cm, hasmask, point, leaf, mrow, cvrow, sm.tab, w); },
+                [&]() { return gibbs_pick_exact(mj, vj, wl, nz, d, cm, hasmask, mrow, cvrow, u); });
+            node[j] = z0 + pick;
+          }
+        }
+        IIF_PHASE(15);
+        continue;
       }
+      // ---- any number of densities: one draw after the other; the conditional of sampleIndex(j) (product of the
+      // other densities' selected nodes) is per sample, staged in shared memory by the owner
+      double* PT = sm.scr;
+      for (int phase = 0; phase < nph; ++phase) {
+        const int j = phase % F;
+        const bool point = phase < F;   // sampleIndices (given X) first, then the sampleIndex sweeps
+        const int32_t hasmask = masks[j] & (point ? fullmask : anyother[j]);
+        if (!point && own) {
+          for (int c = 0; c < d; ++c) {
+            double mu = 0;
+            const double lam = ((hasmask >> c) & 1) ? cond_gauss(F, sm.mean, sm.var, node, masks, j, nn, d, c, is_circ(cm, c), mu) : 0.0;
+            sm.cm[tid * d + c] = mu;
+            sm.cv[tid * d + c] = lam > 0 ? 1.0 / lam : 0.0;
+          }
+        }
+        IIF_PHASE(16);
+        __syncthreads();  // (cm, cv) of every sample visible; the previous draw's totals are no longer read
+        IIF_PHASE(17);
+        const size_t bj = ((size_t)j * nn + z0) * d;
+        const double* mj = sm.mean + bj;
+        const double* vj = sm.var + bj;
+        const double* rj = sm.irs + bj;
+        const double* wl = sm.wt + z0;
+        gibbs_build(d1, mj, vj, rj, wl, nz, np, nloc, d, cm, hasmask, point, leaf, sm.cm, sm.cv, sm.tab, PT, NP);
+        IIF_PHASE(7);
+        __syncthreads();
+        IIF_PHASE(18);
+        if (own) {
+          const double u = gibbs_u((uint32_t)s * ublk + (uint32_t)(F + (l - 1) * nph + phase));
+          const double* mrow = sm.cm + tid * d;
+          const double* cvrow = sm.cv + tid * d;
+          const int pick = pick_row(
+              PT + (size_t)tid * NP, np, nz, u,
+              [&](int zb, double (&w)[4]) { gibbs_piece(d1, mj, vj, rj, wl, nz, zb, d, cm, hasmask, point, leaf, mrow, cvrow, sm.tab, w); },
+              [&]() { return gibbs_pick_exact(mj, vj, wl, nz, d, cm, hasmask, mrow, cvrow, u); });
+          node[j] = z0 + pick;
+        }
+        IIF_PHASE(15);
+      }
+    }
+    IIF_PHASE(11);
+    if (own) {
+      // final samplePoint: draw from the product of the selected leaf kernels
+      for (int c = 0; c < d; ++c) {
+        double mu = 0;
+        const double lam = cond_gauss(F, sm.mean, sm.var, node, masks, -1, nn, d, c, is_circ(cm, c), mu);
+        double x;
+        if (lam > 0) {
+          const double e = rnd_staged ? sm.zs[tid * d + c] : gibbs_n((uint32_t)s * nblk + (uint32_t)(L * d + c));
+          x = madd(mu, sqrt(1.0 / lam) * e, is_circ(cm, c));
+        } else if (t.target_slot >= 0) {
+          // coordinates no proposal informs keep oldPoints (GraphProductOperations.jl:37-45)
+          const iif_slot_desc S = g.slots[t.target_slot];
+          const int len = g.npts[t.target_slot];
+          if (s < len) x = g.pts[S.pts_off + s * d + c];
+          else if (len > 0) {
+            double uu = rs_uniform(seed, call, IIF_RS_OLDPAD, (uint32_t)(s * (d + 1)));
+            int k = min((int)(uu * len), len - 1);
+            double e = rs_normal(seed, call, IIF_RS_OLDPAD, (uint32_t)(s * (d + 1) + 1 + c));
+            x = madd(g.pts[S.pts_off + k * d + c], g.bw[t.target_slot * IIF_MAX_DIM + c] * e, is_circ(cm, c));
+          } else x = 0.0;
+        } else {
+          x = t.old_pts ? t.old_pts[s * d + c] : 0.0;
+        }
+        if (cC > 1) {
+          for (int r = 0; r < cC; ++r) cooperative_groups::this_cluster().map_shared_rank(sm.post, r)[s * d + c] = x;
+        } else {
+          sm.post[s * d + c] = x;
+        }
+      }
+      if (t.out_labels != nullptr)   // every sample belongs to exactly one rank
+        for (int j = 0; j < F; ++j) t.out_labels[s * F + j] = permA[j * N + T.lo[node[j]]];
     }
     if (cC > 1) cooperative_groups::this_cluster().sync();   // all ranks hold all posterior samples
     else __syncthreads();

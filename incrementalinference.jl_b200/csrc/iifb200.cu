@@ -17,7 +17,16 @@
 #include "iif_ppe.cuh"
 #include "iif_product.cuh"
 
-#define IIFB200_VERSION 100
+#define IIFB200_VERSION 200
+
+// iif_plan.cpp (host planner)
+const std::vector<iif_slot_desc>& iif_plan_slots(const iifb200_plan* p);
+const std::vector<iif_factor_desc>& iif_plan_factors(const iifb200_plan* p);
+const std::vector<iif_dist_desc>& iif_plan_dists(const iifb200_plan* p);
+const std::vector<double>& iif_plan_dparams(const iifb200_plan* p);
+const std::vector<iif_prop_op>& iif_plan_props(const iifb200_plan* p);
+const std::vector<iif_sched_op>& iif_plan_ops(const iifb200_plan* p);
+const std::vector<int32_t>& iif_plan_wave_off(const iifb200_plan* p);
 
 static std::string g_init_error;
 
@@ -502,6 +511,8 @@ static int pick_threads(iifb200_ctx* ctx, int grid, int maxN, int small_min = 12
 }
 static int pick_threads_prod(iifb200_ctx* ctx, int grid, int maxN) {
   static const int wide = env_int("IIFB200_PROD_WIDE_THREADS", 256);
+  static const int force = env_int("IIFB200_FORCE_PROD_THREADS", 0);  // development: probe a lone product in its wide-wave shape
+  if (force > 0) return std::min(IIF_MAX_THREADS, std::max(force, (maxN + 31) / 32 * 32));
   if (wide <= 0 || grid <= ctx->num_sms) return IIF_MAX_THREADS;
   return std::min(IIF_MAX_THREADS, std::max(wide, (maxN + 31) / 32 * 32));
 }
@@ -1216,6 +1227,24 @@ int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* 
   }
   free_schedule(s);
   return st;
+}
+
+int32_t iifb200_plan_upload(iifb200_ctx* ctx, const iifb200_plan* plan, const iif_solver_params* sp, void* ext_arena,
+                            int32_t* schedule_id_out) {
+  if (!ctx) return IIF_ERR_ARG;
+  if (!plan || !sp || !schedule_id_out) return fail(ctx, IIF_ERR_ARG, "plan_upload: bad arguments");
+  std::vector<iif_slot_desc> slots = iif_plan_slots(plan);   // set_graph fills pts_off in place
+  const auto& F = iif_plan_factors(plan);
+  const auto& D = iif_plan_dists(plan);
+  const auto& prm = iif_plan_dparams(plan);
+  int32_t st = iifb200_set_graph(ctx, (int32_t)slots.size(), slots.data(), (int32_t)F.size(), F.data(), (int32_t)D.size(),
+                                 D.data(), (int32_t)prm.size(), prm.data(), sp, ext_arena);
+  if (st != IIF_OK) return st;
+  const auto& wo = iif_plan_wave_off(plan);
+  const auto& ops = iif_plan_ops(plan);
+  const auto& props = iif_plan_props(plan);
+  return iifb200_schedule_build(ctx, (int32_t)wo.size() - 1, wo.data(), (int32_t)ops.size(), ops.data(),
+                                (int32_t)props.size(), props.data(), schedule_id_out);
 }
 
 int32_t iifb200_sync(iifb200_ctx* ctx) {

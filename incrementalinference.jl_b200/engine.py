@@ -12,7 +12,7 @@ from . import _abi as A
 
 
 class Engine:
-    def __init__(self, frozen, sp_c, device=0, ext_arena_ptr=None):
+    def __init__(self, frozen, sp_c, device=0, ext_arena_ptr=None, _plan_handle=None):
         self.lib = A.load_library()
         self.frozen = frozen
         self.sp_c = sp_c
@@ -21,10 +21,23 @@ class Engine:
         if st != A.IIF_OK:
             raise A.IIFB200Error(f"iifb200_init failed ({st}): {self.lib.iifb200_last_error(None).decode()}")
         self.ctx = ctx
+        if _plan_handle is not None:      # iifb200_plan_upload: set_graph + schedule_build inside the library
+            sid = C.c_int32(-1)
+            self._check(self.lib.iifb200_plan_upload(ctx, _plan_handle, C.byref(sp_c),
+                                                     C.c_void_p(ext_arena_ptr) if ext_arena_ptr else None,
+                                                     C.cast(C.byref(sid), A._ip)), "plan_upload")
+            self.plan_sid = sid.value
+            return
         self._check(self.lib.iifb200_set_graph(
             ctx, frozen["nslots"], frozen["slots"], frozen["nfactors"], frozen["factors"], frozen["ndists"],
             frozen["dists"], frozen["nparams"], A.as_dp(frozen["dparams"]), C.byref(sp_c),
             C.c_void_p(ext_arena_ptr) if ext_arena_ptr else None), "set_graph")
+
+    @classmethod
+    def from_plan(cls, frozen, plan_handle, sp_c, device=0, ext_arena_ptr=None):
+        """engine + schedule from a plan made by iifb200_plan_tree -> (Engine, schedule id)"""
+        e = cls(frozen, sp_c, device, ext_arena_ptr, _plan_handle=plan_handle)
+        return e, e.plan_sid
 
     # ---- plumbing
     def _check(self, st, what):

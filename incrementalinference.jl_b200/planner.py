@@ -1,0 +1,98 @@
+"""Python binding of the tree planner in libiifb200.so (iifb200_plan_tree): packs the factor graph's descriptor
+tables and the Bayes tree's per-clique lists into the C structs of include/iifb200.h — exactly what the Julia shim
+does with `getCliqueData(cliq)` — and wraps the returned plan as a tree.SolvePlan."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from . import compile as CP
+from . import graph as G
+from . import tree as TR
+
+
+def _csr(lists):
+    off = np.zeros(len(lists) + 1, dtype=np.int32)
+    for i, l in enumerate(lists):
+        off[i + 1] = off[i] + len(l)
+    flat = np.asarray([x for l in lists for x in l] or [0], dtype=np.int32)
+    return off, flat
+
+
+def graph_tables(fg: G.FactorGraph, N: int):
+    """iif_graph_desc content: slot v == variable v, factor table in graph order"""
+    T = CP.Tables()
+    var_idx = {}
+    for l, v in fg.variables.items():
+        var_idx[l] = T.add_slot(v.vartype, max(N, v.val.shape[0], 1))
+    fac_idx = {}
+    for l, f in fg.factors.items():
+        fac_idx[l] = T.add_factor(f.fnc, [var_idx[v] for v in f.variables], f.multihypo, f.nullhypo, f.inflation)
+    return T.freeze(), var_idx, fac_idx
+
+
+class CPlan:
+    """owner of an iifb200_plan handle"""
+
+    def __init__(self, handle, lib):
+        self.handle, self.lib = handle, lib
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.iifb200_plan_free(self.handle)
+            self.handle = None
+
+
+def plan_tree(fg: G.FactorGraph, tree: TR.BayesTree, N=None, downsolve=True, gibbsIters=None, downIters=3,
+              useMsgLikelihoods=False, lanes=0, forward_copies=True, call_base=0) -> TR.SolvePlan:
+    lib = A.load_library()
+    sp = fg.solverParams
+    N = N or sp.N
+    frozen, var_idx, fac_idx = graph_tables(fg, min(N, A.IIF_MAX_POINTS))
+    gd = A.GraphDesc(frozen["nslots"], frozen["slots"], frozen["nfactors"], frozen["factors"], frozen["ndists"],
+                     frozen["dists"], frozen["nparams"], A.as_dp(frozen["dparams"]))
+    cl = tree.cliques
+    keep = []
+
+    def lists(get, idx):
+        off, flat = _csr([[idx[x] for x in get(c)] for c in cl])
+        keep.extend((off, flat))
+        return A.as_ip(off), A.as_ip(flat)
+    parent = np.asarray([-1 if c.parent is None else c.parent for c in cl], dtype=np.int32)
+    td = A.TreeDesc()
+    td.ncliques, td.parent = len(cl), A.as_ip(parent)
+    td.frontal_off, td.frontals = lists(lambda c: c.frontals, var_idx)
+    td.separator_off, td.separators = lists(lambda c: c.separators, var_idx)
+    td.potential_off, td.potentials = lists(lambda c: c.potentials, fac_idx)
+    td.directFrtlMsg_off, td.directFrtlMsg = lists(lambda c: c.directFrtlMsgIDs, var_idx)
+    td.msgskip_off, td.msgskip = lists(lambda c: c.msgskipIDs, var_idx)
+    td.itervar_off, td.itervar = lists(lambda c: c.itervarIDs, var_idx)
+    td.directPriorMsg_off, td.directPriorMsg = lists(lambda c: c.directPriorMsgIDs, var_idx)
+    po = A.PlanOpts(int(N), int(gibbsIters or sp.gibbsIters), int(downIters), int(bool(downsolve)), int(lanes),
+                    int(bool(forward_copies)), int(bool(useMsgLikelihoods)), int(call_base), float(sp.inflation))
+    h = C.c_void_p()
+    st = lib.iifb200_plan_tree(C.byref(gd), C.byref(td), C.byref(po), C.byref(h))
+    if st != A.IIF_OK:
+        raise A.IIFB200Error(f"iifb200_plan_tree failed ({st}): {lib.iifb200_plan_error().decode()}")
+    cnt = np.zeros(16, dtype=np.int32)
+    lib.iifb200_plan_counts(h, A.as_ip(cnt))
+    ns, nf, nd, npar, nprops, nops, nw, n_conv, n_prod, n_msgs, up_last, nvars = (int(x) for x in cnt[:12])
+    slots = (A.SlotDesc * max(ns, 1))()
+    factors = (A.FactorDesc * max(nf, 1))()
+    dists = (A.DistDesc * max(nd, 1))()
+    dparams = np.zeros(max(npar, 1))
+    props = (A.PropOp * max(nprops, 1))()
+    ops = (A.SchedOp * max(nops, 1))()
+    wave_off = np.zeros(nw + 1, dtype=np.int32)
+    lib.iifb200_plan_export(h, slots, factors, dists, A.as_dp(dparams), props, ops, A.as_ip(wave_off))
+    total = slots[ns - 1].pts_off + slots[ns - 1].cap * slots[ns - 1].dim
+    fz = dict(nslots=ns, slots=slots, nfactors=nf, factors=factors, ndists=nd, dists=dists, nparams=npar,
+              dparams=dparams, total_doubles=total)
+    pspecs = [dict(target_slot=p.target_slot, out_slot=p.out_slot,
+                   factors=[(p.factor[k], p.sfidx[k]) for k in range(p.nfactors)], N=p.N, call_id=p.call_id,
+                   any_multihypo=p.any_multihypo) for p in props[:nprops]]
+    sched = [(o.kind, o.a, o.b) for o in ops[:nops]]
+    plan = TR.SolvePlan(None, fz, pspecs, sched, [int(x) for x in wave_off], sched, dict(var_idx), n_conv, n_prod,
+                        n_msgs, up_last, None, None, None, None, None, [], [o.lane for o in ops[:nops]])
+    plan.c_plan = CPlan(h, lib)
+    return plan

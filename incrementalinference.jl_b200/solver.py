@@ -309,7 +309,7 @@ class TreeSolver:
 
     def __init__(self, fg: G.FactorGraph, eliminationOrder: Optional[Sequence[str]] = None, ordering: str = "qr",
                  device: int = 0, ext_arena_ptr=None, downsolve: Optional[bool] = None, lanes: Optional[int] = None,
-                 forward_copies: bool = True, call_base=0):
+                 forward_copies: bool = True, call_base=0, planner: Optional[str] = None):
         """`call_base`: first Philox call id of the plan.  0 (default) gives the same streams for the same seed —
         what parity tests and the bench want; "auto" reserves a fresh range from the graph's counter, so consecutive
         solveTree calls on one graph see independent noise."""
@@ -319,18 +319,35 @@ class TreeSolver:
         ds = fg.solverParams.downsolve if downsolve is None else downsolve
         # independent sub-trees become parallel branches ("lanes") of the captured CUDA graph (tree.assign_lanes)
         lanes = int(os.environ.get("IIFB200_LANES", "4")) if lanes is None else lanes
-        self.plan = TR.compile_solve(fg, self.tree, downsolve=ds, lanes=lanes, forward_copies=forward_copies)
-        if call_base == "auto":
-            call_base = fg.next_call(TR.plan_call_span(self.plan))
-        TR.rebase_calls(self.plan, int(call_base))
+        # `planner`: "c" = iifb200_plan_tree inside libiifb200.so (what a Julia caller uses: the clique table goes in,
+        # the schedule comes out), "python" = the mirror in tree.py (also lowers useMsgLikelihoods = true).  Both give
+        # the same plan bit for bit (tests/test_plan_abi.py); default: the library's planner whenever it applies.
+        uml = bool(fg.solverParams.useMsgLikelihoods)
+        planner = planner or os.environ.get("IIFB200_PLANNER") or ("python" if uml else "c")
         self.sp_c = CP.solver_params_c(fg.solverParams)
-        self.eng = Engine(self.plan.frozen, self.sp_c, device, ext_arena_ptr)
-        self.props_c = CP.make_prop_ops(self.plan.props)
-        self.sched_c = CP.make_sched_ops(self.plan.sched_waved, self.plan.op_lane)
-        self.deconvs_c = CP.make_deconv_ops(self.plan.deconvs or [])
-        self.sid = self.eng.schedule_build(self.plan.wave_off, self.sched_c, len(self.plan.sched_waved),
-                                           self.props_c, len(self.plan.props), self.deconvs_c,
-                                           len(self.plan.deconvs or []))
+        self.plan_handle = None
+        if planner == "c":
+            from . import planner as PL
+            self.plan = PL.plan_tree(fg, self.tree, downsolve=ds, lanes=lanes, forward_copies=forward_copies)
+            if call_base == "auto":
+                call_base = fg.next_call(TR.plan_call_span(self.plan))
+            if call_base:       # ids are baked into the library's plan: plan again with the base
+                self.plan = PL.plan_tree(fg, self.tree, downsolve=ds, lanes=lanes, forward_copies=forward_copies,
+                                         call_base=int(call_base))
+            self.plan_handle = self.plan.c_plan
+            self.eng, self.sid = Engine.from_plan(self.plan.frozen, self.plan_handle.handle, self.sp_c, device, ext_arena_ptr)
+        else:
+            self.plan = TR.compile_solve(fg, self.tree, downsolve=ds, lanes=lanes, forward_copies=forward_copies)
+            if call_base == "auto":
+                call_base = fg.next_call(TR.plan_call_span(self.plan))
+            TR.rebase_calls(self.plan, int(call_base))
+            self.eng = Engine(self.plan.frozen, self.sp_c, device, ext_arena_ptr)
+            self.props_c = CP.make_prop_ops(self.plan.props)
+            self.sched_c = CP.make_sched_ops(self.plan.sched_waved, self.plan.op_lane)
+            self.deconvs_c = CP.make_deconv_ops(self.plan.deconvs or [])
+            self.sid = self.eng.schedule_build(self.plan.wave_off, self.sched_c, len(self.plan.sched_waved),
+                                               self.props_c, len(self.plan.props), self.deconvs_c,
+                                               len(self.plan.deconvs or []))
         self.arena = CP.HostArena(self.plan.frozen)
 
     def load_from_graph(self):

@@ -339,6 +339,7 @@ class SolvePlan:
     slot_clique: Optional[Dict[int, int]] = None  # clique-local slot -> clique id (main-graph slots absent)
     deconvs: Optional[list] = None    # IIF_S_DECONV specs (useMsgLikelihoods=true): factor, out_slot, N, call_id
     op_lane: Optional[List[int]] = None   # lane of every op of `sched_waved` (0 = none), see assign_lanes
+    c_plan: object = None             # planner.CPlan when the plan was made by iifb200_plan_tree (libiifb200.so)
 
 
 def _levelize(ops, reads, writes):

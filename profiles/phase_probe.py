@@ -19,16 +19,17 @@ LOO = ["loo rows (hot loop)", "loo barrier1", "loo gather", "loo part+barrier2",
 KER = {"bandwidth": {8: "load", 13: "search+write"},
        "conv": {8: "setup/load", 9: "measurements+recipe+labels", 10: "inflate/solve", 11: "write proposal",
                 12: "bandwidth (all)", 13: "write bw/slot"},
-       "product": {8: "load", 9: "ball trees", 10: "node stats", 7: "gibbs: pair-weight tables", 15: "gibbs: label draws",
-                   16: "  draw: uniform+misc", 17: "  draw: chunk sums", 18: "  draw: group scan", 20: "  draw: pick",
-                   11: "gibbs: rest", 12: "sample", 13: "bandwidth (all)", 14: "write"}}
+       "product": {8: "load", 9: "ball trees", 10: "node stats + rsqrt", 20: "gibbs: samplePoint per level",
+                   16: "gibbs: conditional setup", 17: "gibbs: barrier before build", 7: "gibbs: flat weight build",
+                   18: "gibbs: barrier after build", 15: "gibbs: owner pick", 11: "gibbs: rest",
+                   12: "final sample", 13: "bandwidth (all)", 14: "write"}}
 from iifb200 import _abi as A, compile as CP  # noqa: E402
 import parity_cases as PC  # noqa: E402
 
 for tid in TIDS:
     lib = os.path.join(CSRC, f"libiifb200_ph{tid}.so")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-                           "-shared", "-DIIF_PHASES", f"-DIIF_PHASE_TID={tid}", "-o", lib, os.path.join(CSRC, "iifb200.cu")])
+                           "-shared", "-DIIF_PHASES", f"-DIIF_PHASE_TID={tid}", "-o", lib, os.path.join(CSRC, "iifb200.cu"), os.path.join(CSRC, "iif_plan.cpp")])
     A._lib = None
     L = A.load_library(lib)
     L.iifb200_debug_phases.argtypes = [C.POINTER(C.c_longlong), C.c_int]

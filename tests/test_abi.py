@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = C.CDLL(A.LIB_PATH)
     for name in _declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/iifb200.h but not exported"
-    assert A.load_library().iifb200_version() == 100
+    assert A.load_library().iifb200_version() == 200
 
 
 def test_struct_sizes_match_header(built):
@@ -34,16 +34,17 @@ def test_struct_sizes_match_header(built):
     prog = textwrap.dedent("""
         #include <stdio.h>
         #include "iifb200.h"
-        int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(iif_dist_desc), sizeof(iif_slot_desc),
+        int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(iif_dist_desc), sizeof(iif_slot_desc),
           sizeof(iif_factor_desc), sizeof(iif_solver_params), sizeof(iif_conv_op), sizeof(iif_prop_op),
-          sizeof(iif_product_op), sizeof(iif_sched_op), sizeof(iif_deconv_op)); return 0;}""")
+          sizeof(iif_product_op), sizeof(iif_sched_op), sizeof(iif_deconv_op), sizeof(iif_graph_desc),
+          sizeof(iif_tree_desc), sizeof(iif_plan_opts)); return 0;}""")
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(prog)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
         out = subprocess.check_output([os.path.join(d, "s")]).split()
     sizes = [int(x) for x in out]
     mirrors = [A.DistDesc, A.SlotDesc, A.FactorDesc, A.SolverParamsC, A.ConvOp, A.PropOp, A.ProductOp, A.SchedOp,
-               A.DeconvOp]
+               A.DeconvOp, A.GraphDesc, A.TreeDesc, A.PlanOpts]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 
@@ -66,6 +67,6 @@ def test_product_package_never_imports_oracle():
     pkg = os.path.join(ROOT, "incrementalinference.jl_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "iif_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, f

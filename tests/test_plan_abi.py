@@ -1,0 +1,115 @@
+"""The tree planner inside libiifb200.so (iifb200_plan_tree, include/iifb200.h): a raw clique table — what a Julia
+caller reads off `tree.bt` — goes through the C-ABI and must reproduce the Python mirror's plan (tree.compile_solve)
+bit for bit: slots, factor instances, props (targets, factor lists, solve-for indices, Philox call ids, multihypo
+flags), schedule ops, waves and lanes.  No GPU needed: the planner is host code."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import parity_cases as PC
+from iifb200 import _abi as A
+from iifb200 import compile as CP
+from iifb200 import planner as PL
+from iifb200 import tree as TR
+from iifb200 import workloads as W
+from test_tree_parity import three_door_graph
+
+
+def graphs():
+    yield "chain_nd", W.scalar_chain(37, N=32, seed=1), W.chain_nd_order(37), {}
+    yield "chain_natural", W.scalar_chain(9, N=16, seed=1), [f"x{k}" for k in range(9)], {}
+    fg = W.euclid2_grid(rows=4, cols=7, N=24, seed=2, closure_every=2)
+    yield "grid_nd", fg, TR.getEliminationOrder(fg, "nd"), {}
+    fg = W.generateGraph_Kaess(N=20)
+    yield "kaess_qr", fg, TR.getEliminationOrder(fg, "qr"), {}
+    fg = W.generateGraph_CaesarRing1D(N=20)
+    yield "caesar_ring_no_down", fg, TR.getEliminationOrder(fg, "qr"), dict(downsolve=False)
+    fg = W.scalar_chain_sessions(3, 12, N=16)
+    yield "forest", fg, W.sessions_nd_order(3, 12), {}
+    fg = three_door_graph(1, poses=3, N=50)
+    yield "multihypo", fg, TR.getEliminationOrder(fg, "qr"), {}
+    fg = W.circular_chain(n=15, N=40)
+    yield "circular_no_forwarding", fg, W.chain_nd_order(15), dict(forward_copies=False)
+    fg = W.four_door(N=64)
+    yield "mixture_priors", fg, TR.getEliminationOrder(fg, "qr"), dict(gibbsIters=5)
+
+
+def _factor_tuple(frozen, i):
+    f = frozen["factors"][i]
+    D = frozen["dists"][f.dist]
+    prm = frozen["dparams"]
+    if D.kind == A.D_KDE:
+        dist = ("kde", D.dim, D.slot)
+    elif D.kind == A.D_MIXTURE:
+        blk = 2 if D.comp_kind != A.D_MVNORMAL else D.dim + D.dim * D.dim
+        dist = ("mix", D.dim, D.ncomp, D.comp_kind, tuple(prm[D.poff:D.poff + D.ncomp * (1 + blk)]))
+    else:
+        n = {A.D_NORMAL: 2, A.D_UNIFORM: 2}.get(D.kind, D.dim + D.dim * D.dim)
+        dist = (D.kind, D.dim, tuple(prm[D.poff:D.poff + n]))
+    return (f.kind, f.arity, f.zdim, tuple(f.slot[k] for k in range(f.arity)), f.nmh, f.partial_mask,
+            tuple(f.mh[k] for k in range(f.nmh)), f.nullhypo, f.inflation, dist)
+
+
+@pytest.mark.parametrize("case", list(graphs()), ids=lambda c: c[0])
+def test_c_planner_reproduces_python_plan(built, case):
+    name, fg, order, kw = case
+    tree = TR.buildTree(fg, order)
+    for lanes in (0, 4):
+        ref = TR.compile_solve(fg, tree, lanes=lanes, useMsgLikelihoods=False, **kw)
+        got = PL.plan_tree(fg, tree, lanes=lanes, **kw)
+        a, b = ref.frozen, got.frozen
+        assert a["nslots"] == b["nslots"] and a["nfactors"] == b["nfactors"]
+        for i in range(a["nslots"]):
+            sa, sb = a["slots"][i], b["slots"][i]
+            assert (sa.dim, sa.circ_mask, sa.cap, sa.pts_off) == (sb.dim, sb.circ_mask, sb.cap, sb.pts_off), i
+        for i in range(a["nfactors"]):
+            assert _factor_tuple(a, i) == _factor_tuple(b, i), (name, i)
+        assert ref.props == got.props
+        assert ref.sched_waved == got.sched_waved
+        assert list(ref.wave_off) == list(got.wave_off)
+        assert list(ref.op_lane) == list(got.op_lane)
+        assert (ref.n_conv, ref.n_prod, ref.n_msgs, ref.up_last_wave) == (got.n_conv, got.n_prod, got.n_msgs, got.up_last_wave)
+        assert ref.var_slot == got.var_slot
+
+
+def test_c_planner_runs_on_the_oracle(built):
+    """a plan made by the library drives the oracle to the same posteriors as the Python-made plan"""
+    import oracle as O
+    fg, order = W.scalar_chain(21, N=32, seed=4), W.chain_nd_order(21)
+    tree = TR.buildTree(fg, order)
+    res = []
+    for plan in (TR.compile_solve(fg, tree, lanes=4), PL.plan_tree(fg, tree, lanes=4)):
+        ar = CP.HostArena(plan.frozen)
+        for l, v in fg.variables.items():
+            ar.set(plan.var_slot[l], v.val, v.bw, True)
+        orc = O.Oracle(plan.frozen, ar, CP.solver_params_c(fg.solverParams))
+        orc.schedule_run(plan.wave_off, CP.make_sched_ops(plan.sched_waved), CP.make_prop_ops(plan.props))
+        res.append(ar)
+    assert np.array_equal(res[0].pts, res[1].pts) and np.array_equal(res[0].bw, res[1].bw)
+
+
+def test_c_planner_errors(built):
+    fg, order = W.scalar_chain(5, N=16), W.chain_nd_order(5)
+    tree = TR.buildTree(fg, order)
+    with pytest.raises(A.IIFB200Error, match="useMsgLikelihoods"):
+        PL.plan_tree(fg, tree, useMsgLikelihoods=True)
+    with pytest.raises(A.IIFB200Error):
+        PL.plan_tree(fg, tree, N=100000)
+
+
+@pytest.mark.gpu
+def test_plan_upload_solves_like_the_python_path(built):
+    """iifb200_plan_upload (set_graph + schedule_build inside the library) followed by upload_slots / schedule_run /
+    download_slots — the whole B4 sequence a reference-side caller makes — gives the TreeSolver's posteriors."""
+    from iifb200 import solver as SV
+    fg, order = W.scalar_chain(64, N=100, seed=3), W.chain_nd_order(64)
+    ts = SV.TreeSolver(fg, order, planner="python")
+    ts.load_from_graph(); ts.upload(); ts.run(); ts.download()
+    tc = SV.TreeSolver(fg, order, planner="c")
+    assert tc.plan_handle is not None
+    tc.load_from_graph(); tc.upload(); tc.run(); tc.download()
+    for l in fg.variables:
+        for x, y in zip(ts.arena.get(ts.plan.var_slot[l]), tc.arena.get(tc.plan.var_slot[l])):
+            assert np.array_equal(x, y), l
+    ts.close(); tc.close()
