@@ -53,12 +53,12 @@ struct ProdSmem {
 
 // the label draws keep one total per piece of four candidates and output sample in the scratch region that the
 // leave-one-out search uses afterwards
-#define IIF_GIBBS_FUSED_MAX 150  // largest N whose four tables of piece totals fit in shared memory
+#define IIF_GIBBS_FUSED_MAX 128  // largest N whose four tables of piece totals fit in shared memory
 __host__ __device__ inline bool gibbs_fused(int F, int N) { return F == 2 && N <= IIF_GIBBS_FUSED_MAX; }
 #define IIF_GIBBS_RND_PHASES 6   // staged uniforms per sample and level: F (1 + Niter) <= 6 for two densities, Niter <= 2
 __host__ __device__ inline size_t prod_scratch_doubles(int F, int N) {
   // two densities build the level's four tables of piece totals at once
-  const size_t loo = (size_t)IIF_LOO_SCRATCH_N(N), pt = (size_t)(gibbs_fused(F, N) ? 4 : 1) * N * (size_t)((N + 3) >> 2);
+  const size_t loo = (size_t)IIF_LOO_SCRATCH_N(N), pt = (size_t)(gibbs_fused(F, N) ? 4 : 1) * N * (size_t)(((N + 3) >> 2) | 1);
   return loo > pt ? loo : pt;
 }
 
@@ -174,9 +174,11 @@ template <bool POINT, bool LEAF>
 __device__ __forceinline__ void gibbs_build_d1(const double* mean, const double* var, const double* irs, const double* wt,
                                                int nz, int np, int rows, const double* mrow, const double* cvrow,
                                                int mstride, const double* tab, double* PT, int NPs) {
-  const float inv_np = 1.0f / (float)np;
+  // consecutive lanes take consecutive ROWS of the same piece: the candidates' node data is a broadcast read, the
+  // rows' conditional parameters are contiguous, and the totals land on distinct banks (odd row stride)
+  const float inv_rows = 1.0f / (float)rows;
   for (int p = threadIdx.x; p < rows * np; p += IIF_NT) {
-    const int row = (int)(((float)p + 0.5f) * inv_np), pc = p - row * np;   // exact: p < 2^14
+    const int pc = (int)(((float)p + 0.5f) * inv_rows), row = p - pc * rows;   // exact: p < 2^14
     double w[4];
     gibbs_piece_d1<POINT, LEAF>(mean, var, irs, wt, nz, pc << 2, mrow[row * mstride], POINT ? 0.0 : cvrow[row * mstride], tab, w);
     PT[row * NPs + pc] = (w[0] + w[1]) + (w[2] + w[3]);
@@ -192,9 +194,9 @@ __device__ __forceinline__ void gibbs_build(bool d1, const double* mean, const d
     else gibbs_build_d1<false, false>(mean, var, irs, wt, nz, np, rows, mrow, cvrow, 1, tab, PT, NPs);
     return;
   }
-  const float inv_np = 1.0f / (float)np;
+  const float inv_rows = 1.0f / (float)rows;
   for (int p = threadIdx.x; p < rows * np; p += IIF_NT) {
-    const int row = (int)(((float)p + 0.5f) * inv_np), pc = p - row * np;
+    const int pc = (int)(((float)p + 0.5f) * inv_rows), row = p - pc * rows;
     double w[4];
     gibbs_piece_nd(mean, var, irs, wt, nz, pc << 2, d, cmask, hasmask, point, leaf, mrow + row * d, cvrow + row * d, w);
     PT[row * NPs + pc] = (w[0] + w[1]) + (w[2] + w[3]);
@@ -434,7 +436,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
     auto gibbs_n = [&](uint32_t idx) -> double {
       return (randN != nullptr && t.randn_off >= 0) ? randN[t.randn_off + idx] : rs_normal(seed, call, IIF_RS_GIBBS_N, idx);
     };
-    const int NP = (N + 3) >> 2;     // row stride of the piece totals
+    const int NP = ((N + 3) >> 2) | 1;   // row stride of the piece totals (odd: rows on distinct banks)
     const bool d1 = (d == 1) && !is_circ(cm, 0);
     int32_t anyother[IIF_MAX_FACTORS];  // coordinates some OTHER density informs (uniform over the samples)
     for (int j = 0; j < F; ++j) {
@@ -510,14 +512,14 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         // pass between two barriers, together with the level's uniforms and the next samplePoint's normals.
         __syncthreads();  // X of every sample visible; the previous level's picks are done
         IIF_PHASE(17);
-        double* PTq[4] = {sm.scr, sm.scr + (size_t)N * NP, sm.scr + 2 * (size_t)N * NP, sm.scr + 3 * (size_t)N * NP};
+        const size_t ptq = (size_t)N * NP;   // table q at sm.scr + q * ptq
         for (int q = 0; q < 4; ++q) {
           const int j = q & 1;
           const bool point = q < 2;
           const int32_t hasmask = masks[j] & (point ? fullmask : anyother[j]);
           const size_t bj = ((size_t)j * nn + z0) * d, bo = ((size_t)(1 - j) * nn + z0) * d;
           gibbs_build(d1, sm.mean + bj, sm.var + bj, sm.irs + bj, sm.wt + z0, nz, np, point ? nloc : nz, d, cm, hasmask, point,
-                      leaf, point ? sm.cm : sm.mean + bo, point ? sm.cv : sm.var + bo, sm.tab, PTq[q], NP);
+                      leaf, point ? sm.cm : sm.mean + bo, point ? sm.cv : sm.var + bo, sm.tab, sm.scr + q * ptq, NP);
         }
         if (rnd_staged) {
           for (int r = tid; r < nloc * nph; r += IIF_NT) {
@@ -533,6 +535,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         __syncthreads();
         IIF_PHASE(18);
         if (own) {
+          int nd0 = node[0], nd1 = node[1];   // scalars: no dynamically indexed local array in the hot path
           for (int phase = 0; phase < nph; ++phase) {
             const int j = phase & 1;
             const bool point = phase < 2;
@@ -542,16 +545,19 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
             const double* vj = sm.var + bj;
             const double* rj = sm.irs + bj;
             const double* wl = sm.wt + z0;
-            const int row = point ? tid : node[1 - j] - z0;
-            const double* mrow = point ? sm.cm + tid * d : sm.mean + (size_t)node[1 - j] * d + (size_t)(1 - j) * nn * d;
-            const double* cvrow = point ? sm.cv + tid * d : sm.var + (size_t)node[1 - j] * d + (size_t)(1 - j) * nn * d;
+            const int other = j ? nd0 : nd1;
+            const int row = point ? tid : other - z0;
+            const double* mrow = point ? sm.cm + tid * d : sm.mean + (size_t)other * d + (size_t)(1 - j) * nn * d;
+            const double* cvrow = point ? sm.cv + tid * d : sm.var + (size_t)other * d + (size_t)(1 - j) * nn * d;
             const double u = rnd_staged ? sm.us[tid * nph + phase] : gibbs_u((uint32_t)s * ublk + (uint32_t)(F + (l - 1) * nph + phase));
             const int pick = pick_row(
-                PTq[point ? j : 2 + j] + (size_t)row * NP, np, nz, u,
+                sm.scr + (point ? j : 2 + j) * ptq + (size_t)row * NP, np, nz, u,
                 [&](int zb, double (&w)[4]) { gibbs_piece(d1, mj, vj, rj, wl, nz, zb, d, cm, hasmask, point, leaf, mrow, cvrow, sm.tab, w); },
                 [&]() { return gibbs_pick_exact(mj, vj, wl, nz, d, cm, hasmask, mrow, cvrow, u); });
-            node[j] = z0 + pick;
+            if (j) nd1 = z0 + pick; else nd0 = z0 + pick;
           }
+          node[0] = nd0;
+          node[1] = nd1;
         }
         IIF_PHASE(15);
         continue;
