@@ -464,6 +464,23 @@ def run_b200(args, rank, world, local_rank):
         "products_per_s": plan.n_prod * args.steps / (dev_ms * 1e-3),
         "posterior_mean_abs_err_max": post_mean_err,
     }
+    if world == 1 and not args.no_b3:
+        # boundary B3 for comparison: the same pass driven ONE propagateBelief per C-ABI round trip (set_graph on the
+        # mini graph, one upload, propagate, download), the call sequence of julia/IIFB200.jl's propagateBelief
+        b3 = SV.B3Driver(plan, CP.solver_params_c(fg.solverParams, 7))
+        ar = CP.HostArena(plan.frozen)
+        for l, v in fg.variables.items():
+            ar.set(plan.var_slot[l], v.val, v.bw, True)
+        b3.run(ar.copy())                      # warm-up: pools reach their size
+        t0 = time.perf_counter()
+        b3.run(ar)
+        dt = time.perf_counter() - t0
+        out["e2e_b3"] = {"value": total_conv / dt, "unit": "conv/s", "ms_per_step": 1e3 * dt,
+                         "round_trips_per_step": len(plan.props),
+                         "note": "one propagateBelief per call through set_graph / upload_slots / propagate_batch / "
+                                 "download_belief (Python mirror of the Julia shim's B3 sequence; descriptor tables "
+                                 "prebuilt outside the timed region)"}
+        b3.close()
     if cpu is not None:
         out["cpu_baseline"] = cpu
     if world == 1 and not args.no_cpu_baseline:
@@ -481,6 +498,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--order", default="nd", choices=["nd", "natural"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-b3", action="store_true", help="skip the per-call (boundary B3) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

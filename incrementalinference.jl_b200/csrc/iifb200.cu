@@ -53,6 +53,7 @@ struct Wave {
 };
 
 struct Schedule {
+  bool pooled = false;  // device arrays live in the ctx pool (propagate_batch): not freed with the schedule
   std::vector<Wave> waves;
   ConvTask* d_conv = nullptr;
   ProdTask* d_prod = nullptr;
@@ -92,6 +93,11 @@ struct iifb200_ctx {
   TreeStruct h_trees[IIF_MAX_POINTS + 1];
   TreeStruct* d_trees = nullptr;
   std::vector<Schedule*> schedules;
+  // grow-only device scratch of the *_batch entry points and of propagate_batch's one-wave schedule: a call never
+  // pays cudaMalloc / cudaFree once the pools have reached their working size (boundary B3 is one call per belief)
+  void* pool[2] = {nullptr, nullptr};
+  size_t pool_cap[2] = {0, 0};
+  size_t arena_cap = 0, tables_cap = 0;
   int64_t launches = 0;
   int max_smem_optin = 0;
   int num_sms = 148;
@@ -113,6 +119,17 @@ static int32_t fail(iifb200_ctx* ctx, int32_t code, const std::string& msg) {
   ctx->err = msg;
   return code;
 }
+
+struct Carver {   // first pass (base == nullptr) sizes, second pass hands out 256-byte aligned pieces
+  char* base = nullptr;
+  size_t off = 0;
+  template <typename T> T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
 
 static const char* status_name(int st) {
   switch (st) {
@@ -248,24 +265,45 @@ static void free_schedule(Schedule* s) {
   if (!s) return;
   for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second.first);
   for (auto e : s->events) cudaEventDestroy(e);
-  cudaFree(s->d_conv); cudaFree(s->d_prod); cudaFree(s->d_copy); cudaFree(s->d_dcv); cudaFree(s->d_scratch); cudaFree(s->d_status);
+  if (!s->pooled) { cudaFree(s->d_conv); cudaFree(s->d_prod); cudaFree(s->d_copy); cudaFree(s->d_dcv); cudaFree(s->d_scratch); cudaFree(s->d_status); }
   delete s;
 }
 
-static void free_graph(iifb200_ctx* ctx) {
+// schedules go; the arena and the descriptor tables stay allocated (grow-only) unless `release`
+static void free_graph(iifb200_ctx* ctx, bool release) {
   for (auto*& s : ctx->schedules) { free_schedule(s); s = nullptr; }
   ctx->schedules.clear();
-  if (ctx->arena_owned && ctx->arena) cudaFree(ctx->arena);
-  ctx->arena = nullptr;
-  if (ctx->d_tables) cudaFree(ctx->d_tables);
-  ctx->d_tables = nullptr;
+  if (!ctx->arena_owned) { ctx->arena = nullptr; ctx->arena_cap = 0; }
+  if (release) {
+    if (ctx->arena_owned && ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr; ctx->arena_cap = 0;
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    ctx->d_tables = nullptr; ctx->tables_cap = 0;
+    for (int k = 0; k < 2; ++k) { if (ctx->pool[k]) cudaFree(ctx->pool[k]); ctx->pool[k] = nullptr; ctx->pool_cap[k] = 0; }
+  }
+}
+
+// grow-only pool k; the previous contents are not preserved.  Carve with `Carver`.
+static cudaError_t pool_reserve(iifb200_ctx* ctx, int k, size_t bytes, char** base) {
+  if (bytes > ctx->pool_cap[k]) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return e;
+    if (ctx->pool[k]) cudaFree(ctx->pool[k]);
+    ctx->pool[k] = nullptr; ctx->pool_cap[k] = 0;
+    const size_t want = bytes + bytes / 2 + 4096;
+    e = cudaMalloc(&ctx->pool[k], want);
+    if (e != cudaSuccess) return e;
+    ctx->pool_cap[k] = want;
+  }
+  *base = (char*)ctx->pool[k];
+  return cudaSuccess;
 }
 
 void iifb200_free(iifb200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  free_graph(ctx);
+  free_graph(ctx, true);
   for (auto& t : ctx->trees) if (t.d_blob) cudaFree(t.d_blob);
   cudaFree(ctx->d_trees);
   cudaFree(ctx->d_err);
@@ -301,7 +339,7 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
   if (nslots < 1 || !slots || nfactors < 0 || ndists < 0 || !sp) return fail(ctx, IIF_ERR_ARG, "set_graph: bad arguments");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  free_graph(ctx);
+  free_graph(ctx, false);
   for (int s = 0; s < nslots; ++s) {
     if (slots[s].dim < 1 || slots[s].dim > IIF_MAX_DIM) return fail(ctx, IIF_ERR_ARG, "slot dim out of range");
     if (slots[s].cap < 1 || slots[s].cap > IIF_MAX_POINTS) return fail(ctx, IIF_ERR_ARG, "slot capacity out of range");
@@ -334,14 +372,28 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
   ctx->dists.assign(dists, dists + ndists);
   ctx->sp = *sp;
   const int64_t bytes = iifb200_arena_bytes(nslots, slots);
-  if (ext_arena) { ctx->arena = ext_arena; ctx->arena_owned = false; }
-  else { CK(cudaMalloc(&ctx->arena, bytes)); ctx->arena_owned = true; }
+  if (ext_arena) {
+    if (ctx->arena_owned && ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = ext_arena; ctx->arena_owned = false; ctx->arena_cap = 0;
+  } else if (!ctx->arena_owned || !ctx->arena || ctx->arena_cap < (size_t)bytes) {   // grow-only: re-used across set_graph calls
+    if (ctx->arena_owned && ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    const size_t want = (size_t)bytes + (size_t)bytes / 4;
+    CK(cudaMalloc(&ctx->arena, want));
+    ctx->arena_owned = true; ctx->arena_cap = want;
+  }
   CK(cudaMemsetAsync(ctx->arena, 0, bytes, ctx->stream));
   // descriptor tables in one allocation
   const size_t b_slots = sizeof(iif_slot_desc) * nslots, b_fac = sizeof(iif_factor_desc) * std::max(nfactors, 1),
                b_dist = sizeof(iif_dist_desc) * std::max(ndists, 1), b_par = sizeof(double) * std::max(nparams, 1);
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-  CK(cudaMalloc(&ctx->d_tables, al(b_slots) + al(b_fac) + al(b_dist) + al(b_par)));
+  const size_t tb = al(b_slots) + al(b_fac) + al(b_dist) + al(b_par);
+  if (!ctx->d_tables || ctx->tables_cap < tb) {
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    ctx->d_tables = nullptr;
+    CK(cudaMalloc(&ctx->d_tables, tb + tb / 4));
+    ctx->tables_cap = tb + tb / 4;
+  }
   char* p = (char*)ctx->d_tables;
   DeviceGraph& dg = ctx->dg;
   dg.slots = (iif_slot_desc*)p; p += al(b_slots);
@@ -567,17 +619,27 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
   double *d_pts = nullptr, *d_bw = nullptr, *d_meas = nullptr, *d_uinf = nullptr;
   int32_t *d_lab = nullptr, *d_misc = nullptr, *d_labin = nullptr;
   ConvTask* d_tasks = nullptr;
-  auto cleanup = [&]() { cudaFree(d_pts); cudaFree(d_bw); cudaFree(d_meas); cudaFree(d_uinf); cudaFree(d_lab); cudaFree(d_misc); cudaFree(d_labin); cudaFree(d_tasks); };
+  auto cleanup = [&]() {};   // scratch comes from the grow-only pool
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return IIF_ERR_CUDA; } } while (0)
-  CKC(cudaMalloc(&d_pts, sizeof(double) * poff[K]));
-  CKC(cudaMalloc(&d_bw, sizeof(double) * 2 * K * IIF_MAX_DIM));
-  CKC(cudaMalloc(&d_lab, sizeof(int32_t) * noff[K]));
-  CKC(cudaMalloc(&d_misc, sizeof(int32_t) * 2 * K));
-  CKC(cudaMalloc(&d_tasks, sizeof(ConvTask) * K));
+  {
+    Carver cv;
+    for (int pass = 0; pass < 2; ++pass) {
+      cv.off = 0;
+      d_pts = cv.take<double>(poff[K]);
+      d_bw = cv.take<double>(2 * (size_t)K * IIF_MAX_DIM);
+      d_lab = cv.take<int32_t>(noff[K]);
+      d_misc = cv.take<int32_t>(2 * (size_t)K);
+      d_tasks = cv.take<ConvTask>(K);
+      d_meas = n_meas ? cv.take<double>(n_meas) : nullptr;
+      d_labin = n_lab ? cv.take<int32_t>(n_lab) : nullptr;
+      d_uinf = n_uinf ? cv.take<double>(n_uinf) : nullptr;
+      if (pass == 0) CKC(pool_reserve(ctx, 0, cv.off + 256, &cv.base));
+    }
+  }
   CKC(cudaMemsetAsync(d_misc, 0, sizeof(int32_t) * 2 * K, ctx->stream));
-  if (n_meas) { CKC(cudaMalloc(&d_meas, sizeof(double) * n_meas)); CKC(cudaMemcpyAsync(d_meas, meas, sizeof(double) * n_meas, cudaMemcpyHostToDevice, ctx->stream)); }
-  if (n_lab) { CKC(cudaMalloc(&d_labin, sizeof(int32_t) * n_lab)); CKC(cudaMemcpyAsync(d_labin, mhidx, sizeof(int32_t) * n_lab, cudaMemcpyHostToDevice, ctx->stream)); }
-  if (n_uinf) { CKC(cudaMalloc(&d_uinf, sizeof(double) * n_uinf)); CKC(cudaMemcpyAsync(d_uinf, uinf, sizeof(double) * n_uinf, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (n_meas) CKC(cudaMemcpyAsync(d_meas, meas, sizeof(double) * n_meas, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_lab) CKC(cudaMemcpyAsync(d_labin, mhidx, sizeof(int32_t) * n_lab, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_uinf) CKC(cudaMemcpyAsync(d_uinf, uinf, sizeof(double) * n_uinf, cudaMemcpyHostToDevice, ctx->stream));
   for (int k = 0; k < K; ++k) {
     ConvTask& t = tasks[k];
     t.op = ops[k];
@@ -648,21 +710,31 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
   double *d_in = nullptr, *d_bw = nullptr, *d_old = nullptr, *d_u = nullptr, *d_n = nullptr, *d_out = nullptr, *d_obw = nullptr;
   int32_t *d_lab = nullptr, *d_st = nullptr;
   ProdTask* d_tasks = nullptr;
-  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_bw); cudaFree(d_old); cudaFree(d_u); cudaFree(d_n); cudaFree(d_out); cudaFree(d_obw); cudaFree(d_lab); cudaFree(d_st); cudaFree(d_tasks); };
+  auto cleanup = [&]() {};   // scratch comes from the grow-only pool
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return IIF_ERR_CUDA; } } while (0)
-  CKC(cudaMalloc(&d_in, sizeof(double) * doff[V]));
-  CKC(cudaMalloc(&d_bw, sizeof(double) * foff[V] * IIF_MAX_DIM));
-  CKC(cudaMalloc(&d_out, sizeof(double) * ooff[V]));
-  CKC(cudaMalloc(&d_obw, sizeof(double) * V * IIF_MAX_DIM));
-  CKC(cudaMalloc(&d_lab, sizeof(int32_t) * loff[V]));
-  CKC(cudaMalloc(&d_st, sizeof(int32_t) * V));
-  CKC(cudaMalloc(&d_tasks, sizeof(ProdTask) * V));
+  {
+    Carver cv;
+    for (int pass = 0; pass < 2; ++pass) {
+      cv.off = 0;
+      d_in = cv.take<double>(doff[V]);
+      d_bw = cv.take<double>((size_t)foff[V] * IIF_MAX_DIM);
+      d_out = cv.take<double>(ooff[V]);
+      d_obw = cv.take<double>((size_t)V * IIF_MAX_DIM);
+      d_lab = cv.take<int32_t>(loff[V]);
+      d_st = cv.take<int32_t>(V);
+      d_tasks = cv.take<ProdTask>(V);
+      d_old = old_pts ? cv.take<double>(ooff[V]) : nullptr;
+      d_u = n_u ? cv.take<double>(n_u) : nullptr;
+      d_n = n_n ? cv.take<double>(n_n) : nullptr;
+      if (pass == 0) CKC(pool_reserve(ctx, 0, cv.off + 256, &cv.base));
+    }
+  }
   CKC(cudaMemcpyAsync(d_in, dens_pts, sizeof(double) * doff[V], cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(d_bw, dens_bw, sizeof(double) * foff[V] * IIF_MAX_DIM, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemsetAsync(d_st, 0, sizeof(int32_t) * V, ctx->stream));
-  if (old_pts) { CKC(cudaMalloc(&d_old, sizeof(double) * ooff[V])); CKC(cudaMemcpyAsync(d_old, old_pts, sizeof(double) * ooff[V], cudaMemcpyHostToDevice, ctx->stream)); }
-  if (n_u) { CKC(cudaMalloc(&d_u, sizeof(double) * n_u)); CKC(cudaMemcpyAsync(d_u, randU, sizeof(double) * n_u, cudaMemcpyHostToDevice, ctx->stream)); }
-  if (n_n) { CKC(cudaMalloc(&d_n, sizeof(double) * n_n)); CKC(cudaMemcpyAsync(d_n, randN, sizeof(double) * n_n, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (old_pts) CKC(cudaMemcpyAsync(d_old, old_pts, sizeof(double) * ooff[V], cudaMemcpyHostToDevice, ctx->stream));
+  if (n_u) CKC(cudaMemcpyAsync(d_u, randU, sizeof(double) * n_u, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_n) CKC(cudaMemcpyAsync(d_n, randN, sizeof(double) * n_n, cudaMemcpyHostToDevice, ctx->stream));
   std::vector<ProdTask> tasks(V);
   for (int v = 0; v < V; ++v) {
     ProdTask& t = tasks[v];
@@ -716,9 +788,16 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   }
   double *d_pts = nullptr, *d_bw = nullptr;
   BwTask* d_t = nullptr;
-  CK(cudaMalloc(&d_pts, sizeof(double) * off[K]));
-  CK(cudaMalloc(&d_bw, sizeof(double) * K * IIF_MAX_DIM));
-  CK(cudaMalloc(&d_t, sizeof(BwTask) * K));
+  {
+    Carver cv;
+    for (int pass = 0; pass < 2; ++pass) {
+      cv.off = 0;
+      d_pts = cv.take<double>(off[K]);
+      d_bw = cv.take<double>((size_t)K * IIF_MAX_DIM);
+      d_t = cv.take<BwTask>(K);
+      if (pass == 0) CK(pool_reserve(ctx, 0, cv.off + 256, &cv.base));
+    }
+  }
   std::vector<BwTask> t(K);
   for (int k = 0; k < K; ++k) { t[k].pts = d_pts + off[k]; t[k].out_bw = d_bw + (int64_t)k * IIF_MAX_DIM; t[k].N = N[k]; t[k].dim = dim[k]; t[k].circ_mask = circ_mask[k]; t[k]._pad = 0; }
   CK(cudaMemcpyAsync(d_pts, pts, sizeof(double) * off[K], cudaMemcpyHostToDevice, ctx->stream));
@@ -731,7 +810,6 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   ctx->launches += 1;
   CK(cudaMemcpyAsync(out_bw, d_bw, sizeof(double) * K * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_pts); cudaFree(d_bw); cudaFree(d_t);
   return IIF_OK;
 }
 
@@ -744,8 +822,15 @@ int32_t iifb200_ppe_batch(iifb200_ctx* ctx, int32_t V, const int32_t* slots, dou
   CK(cudaSetDevice(ctx->device));
   double* d_out = nullptr;
   PpeTask* d_t = nullptr;
-  CK(cudaMalloc(&d_out, sizeof(double) * 2 * V * IIF_MAX_DIM));
-  CK(cudaMalloc(&d_t, sizeof(PpeTask) * V));
+  {
+    Carver cv;
+    for (int pass = 0; pass < 2; ++pass) {
+      cv.off = 0;
+      d_out = cv.take<double>(2 * (size_t)V * IIF_MAX_DIM);
+      d_t = cv.take<PpeTask>(V);
+      if (pass == 0) CK(pool_reserve(ctx, 0, cv.off + 256, &cv.base));
+    }
+  }
   std::vector<PpeTask> t(V);
   for (int v = 0; v < V; ++v) {
     t[v].slot = slots[v]; t[v]._pad = 0;
@@ -762,7 +847,6 @@ int32_t iifb200_ppe_batch(iifb200_ctx* ctx, int32_t V, const int32_t* slots, dou
   CK(cudaMemcpyAsync(out_mean, d_out, sizeof(double) * V * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(out_max, d_out + (int64_t)V * IIF_MAX_DIM, sizeof(double) * V * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_out); cudaFree(d_t);
   return IIF_OK;
 }
 
@@ -781,9 +865,16 @@ int32_t iifb200_deconv_batch(iifb200_ctx* ctx, int32_t K, const int32_t* factors
   double* d_out = nullptr;
   int32_t* d_st = nullptr;
   DeconvTask* d_t = nullptr;
-  CK(cudaMalloc(&d_out, sizeof(double) * 2 * off[K]));
-  CK(cudaMalloc(&d_st, sizeof(int32_t) * K));
-  CK(cudaMalloc(&d_t, sizeof(DeconvTask) * K));
+  {
+    Carver cv;
+    for (int pass = 0; pass < 2; ++pass) {
+      cv.off = 0;
+      d_out = cv.take<double>(2 * (size_t)off[K]);
+      d_st = cv.take<int32_t>(K);
+      d_t = cv.take<DeconvTask>(K);
+      if (pass == 0) CK(pool_reserve(ctx, 0, cv.off + 256, &cv.base));
+    }
+  }
   std::vector<DeconvTask> t(K);
   for (int k = 0; k < K; ++k) {
     t[k].factor = factors[k]; t[k].N = N[k]; t[k].call_id = call_ids[k]; t[k]._pad = 0;
@@ -803,7 +894,6 @@ int32_t iifb200_deconv_batch(iifb200_ctx* ctx, int32_t K, const int32_t* factors
   CK(cudaMemcpyAsync(out_meas, d_out + off[K], sizeof(double) * off[K], cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(st.data(), d_st, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_out); cudaFree(d_st); cudaFree(d_t);
   for (int k = 0; k < K; ++k)
     if (st[k] != IIF_OK) return fail(ctx, st[k], std::string("deconv_batch: device reported '") + status_name(st[k]) + "'");
   return IIF_OK;
@@ -826,10 +916,17 @@ int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_
   if ((int)smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "mmd: point sets exceed the shared-memory budget");
   double *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
   MmdTask* d_t = nullptr;
-  CK(cudaMalloc(&d_a, sizeof(double) * oa[K]));
-  CK(cudaMalloc(&d_b, sizeof(double) * ob[K]));
-  CK(cudaMalloc(&d_o, sizeof(double) * K));
-  CK(cudaMalloc(&d_t, sizeof(MmdTask) * K));
+  {
+    Carver cv;
+    for (int pass = 0; pass < 2; ++pass) {
+      cv.off = 0;
+      d_a = cv.take<double>(oa[K]);
+      d_b = cv.take<double>(ob[K]);
+      d_o = cv.take<double>(K);
+      d_t = cv.take<MmdTask>(K);
+      if (pass == 0) CK(pool_reserve(ctx, 0, cv.off + 256, &cv.base));
+    }
+  }
   std::vector<MmdTask> t(K);
   for (int k = 0; k < K; ++k) {
     t[k].a = d_a + oa[k]; t[k].b = d_b + ob[k];
@@ -845,14 +942,13 @@ int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_
   ctx->launches += 1;
   CK(cudaMemcpyAsync(out, d_o, sizeof(double) * K, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_a); cudaFree(d_b); cudaFree(d_o); cudaFree(d_t);
   return IIF_OK;
 }
 
 // ---- schedules: propagateBelief waves captured as a CUDA graph -----------------------------------
 static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
                               const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, int32_t ndeconvs,
-                              const iif_deconv_op* deconvs, Schedule** out) {
+                              const iif_deconv_op* deconvs, Schedule** out, bool pooled = false) {
   for (int k = 0; k < ndeconvs; ++k) {
     const iif_deconv_op& D = deconvs[k];
     if (D.factor < 0 || D.factor >= (int)ctx->factors.size() || D.out_slot < 0 || D.out_slot >= (int)ctx->slots.size())
@@ -897,8 +993,23 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
   std::vector<int32_t> cp;
   std::vector<DeconvSlotTask> dt;
   std::vector<char> dused(std::max(ndeconvs, 1), 0);
-  CK(cudaMalloc(&s->d_scratch, sizeof(double) * std::max<int64_t>(soff[nprops], 1)));
-  CK(cudaMalloc(&s->d_status, sizeof(int32_t) * std::max(s->nstatus(), 1)));
+  s->pooled = pooled;
+  if (pooled) {   // one-shot schedule (propagate_batch): every device array comes from the ctx pool
+    Carver cv;
+    for (int pass = 0; pass < 2; ++pass) {
+      cv.off = 0;
+      s->d_scratch = cv.take<double>(std::max<int64_t>(soff[nprops], 1));
+      s->d_status = cv.take<int32_t>(std::max(s->nstatus(), 1));
+      s->d_conv = cv.take<ConvTask>(std::max(s->nconv, 1));
+      s->d_prod = cv.take<ProdTask>(std::max(nprops, 1));
+      s->d_copy = cv.take<int32_t>(2 * (size_t)std::max(nops, 1));
+      s->d_dcv = cv.take<DeconvSlotTask>(std::max(ndeconvs, 1));
+      if (pass == 0) CK(pool_reserve(ctx, 1, cv.off + 256, &cv.base));
+    }
+  } else {
+    CK(cudaMalloc(&s->d_scratch, sizeof(double) * std::max<int64_t>(soff[nprops], 1)));
+    CK(cudaMalloc(&s->d_status, sizeof(int32_t) * std::max(s->nstatus(), 1)));
+  }
   CK(cudaMemsetAsync(s->d_status, 0, sizeof(int32_t) * std::max(s->nstatus(), 1), ctx->stream));
   std::vector<char> used(nprops, 0);
   for (int w = 0; w < nwaves; ++w) {
@@ -987,13 +1098,15 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
     if ((int)W.prod_smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "schedule: product exceeds the shared-memory budget");
     s->waves.push_back(W);
   }
-  CK(cudaMalloc(&s->d_conv, sizeof(ConvTask) * std::max<size_t>(ct.size(), 1)));
-  CK(cudaMalloc(&s->d_prod, sizeof(ProdTask) * std::max<size_t>(pt.size(), 1)));
-  CK(cudaMalloc(&s->d_copy, sizeof(int32_t) * std::max<size_t>(cp.size(), 2)));
+  if (!pooled) {
+    CK(cudaMalloc(&s->d_conv, sizeof(ConvTask) * std::max<size_t>(ct.size(), 1)));
+    CK(cudaMalloc(&s->d_prod, sizeof(ProdTask) * std::max<size_t>(pt.size(), 1)));
+    CK(cudaMalloc(&s->d_copy, sizeof(int32_t) * std::max<size_t>(cp.size(), 2)));
+    CK(cudaMalloc(&s->d_dcv, sizeof(DeconvSlotTask) * std::max<size_t>(dt.size(), 1)));
+  }
   if (!ct.empty()) CK(cudaMemcpyAsync(s->d_conv, ct.data(), sizeof(ConvTask) * ct.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (!pt.empty()) CK(cudaMemcpyAsync(s->d_prod, pt.data(), sizeof(ProdTask) * pt.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (!cp.empty()) CK(cudaMemcpyAsync(s->d_copy, cp.data(), sizeof(int32_t) * cp.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMalloc(&s->d_dcv, sizeof(DeconvSlotTask) * std::max<size_t>(dt.size(), 1)));
   if (!dt.empty()) CK(cudaMemcpyAsync(s->d_dcv, dt.data(), sizeof(DeconvSlotTask) * dt.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
@@ -1209,7 +1322,7 @@ int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* 
   for (int v = 0; v < V; ++v) { so[v].kind = IIF_S_PROPAGATE; so[v].a = v; so[v].b = 0; so[v].lane = 0; }
   int32_t wo[2] = {0, V};
   Schedule* s = nullptr;
-  int32_t st = build_schedule(ctx, 1, wo, V, so.data(), V, ops, 0, nullptr, &s);
+  int32_t st = build_schedule(ctx, 1, wo, V, so.data(), V, ops, 0, nullptr, &s, true);
   if (st != IIF_OK) { free_schedule(s); return st; }
   int nk = 0;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));

@@ -39,6 +39,15 @@ class Engine:
         e = cls(frozen, sp_c, device, ext_arena_ptr, _plan_handle=plan_handle)
         return e, e.plan_sid
 
+    def reset_graph(self, frozen, sp_c=None):
+        """iifb200_set_graph again on the same context (arena, tables and scratch are re-used, grow-only)"""
+        self.frozen = frozen
+        if sp_c is not None:
+            self.sp_c = sp_c
+        self._check(self.lib.iifb200_set_graph(
+            self.ctx, frozen["nslots"], frozen["slots"], frozen["nfactors"], frozen["factors"], frozen["ndists"],
+            frozen["dists"], frozen["nparams"], A.as_dp(frozen["dparams"]), C.byref(self.sp_c), None), "set_graph")
+
     # ---- plumbing
     def _check(self, st, what):
         if st != A.IIF_OK:

@@ -402,3 +402,95 @@ def solveTree(fg: G.FactorGraph, eliminationOrder: Optional[Sequence[str]] = Non
 
 
 solveGraph = solveTree
+
+
+# --------------------------------------------------------------------------- boundary B3 driver
+class B3Driver:
+    """Drives a compiled plan ONE propagateBelief at a time, with the call sequence julia/IIFB200.jl's
+    `propagateBelief` makes per belief update (boundary B3): iifb200_set_graph on the mini graph {destination, its
+    factors' variables, message beliefs}, ONE iifb200_upload_slots of their beliefs, iifb200_propagate_batch(1) and
+    iifb200_download_belief of the posterior.  Beliefs live on the host between calls (as they do in the DFG's
+    VariableNodeData); separator copies are host copies.  Same Philox call ids as the plan => same posteriors as the
+    one-schedule (B4) run; what differs is the cost of 7 000 round trips instead of one."""
+
+    def __init__(self, plan: TR.SolvePlan, sp_c, device: int = 0):
+        self.plan, self.sp_c = plan, sp_c
+        fz = plan.frozen
+        self.calls = []
+        for spec in plan.props:
+            order, loc = [], {}
+
+            def use(s):
+                if s not in loc:
+                    loc[s] = len(order)
+                    order.append(s)
+                return loc[s]
+            use(spec["target_slot"])
+            T = CP.Tables()
+            facs = []
+            for fi, sf in spec["factors"]:
+                f = fz["factors"][fi]
+                D = fz["dists"][f.dist]
+                sl = [use(f.slot[k]) for k in range(f.arity)]
+                ks = use(D.slot) if D.kind == A.D_KDE else -1
+                facs.append((f, D, sl, ks, sf))
+            ns = len(order)
+            slots = (A.SlotDesc * ns)()
+            off = 0
+            for i, s in enumerate(order):
+                g = fz["slots"][s]
+                slots[i].dim, slots[i].circ_mask, slots[i].cap, slots[i].pts_off = g.dim, g.circ_mask, g.cap, off
+                off += g.dim * g.cap
+            factors = (A.FactorDesc * len(facs))()
+            dists = (A.DistDesc * len(facs))()
+            for k, (f, D, sl, ks, sf) in enumerate(facs):
+                C_ = factors[k]
+                C_.kind, C_.arity, C_.zdim, C_.dist, C_.nmh, C_.partial_mask = f.kind, f.arity, f.zdim, k, f.nmh, f.partial_mask
+                C_.nullhypo, C_.inflation = f.nullhypo, f.inflation
+                for i, s in enumerate(sl):
+                    C_.slot[i] = s
+                for i in range(f.nmh):
+                    C_.mh[i] = f.mh[i]
+                dists[k].kind, dists[k].dim, dists[k].ncomp, dists[k].comp_kind = D.kind, D.dim, D.ncomp, D.comp_kind
+                dists[k].slot, dists[k].poff = ks, D.poff                 # parameter block shared with the full plan
+            mini = dict(nslots=ns, slots=slots, nfactors=len(facs), factors=factors, ndists=len(facs), dists=dists,
+                        nparams=fz["nparams"], dparams=fz["dparams"], total_doubles=off)
+            op = CP.make_prop_ops([dict(target_slot=0, out_slot=0, factors=[(k, sf) for k, (_, _, _, _, sf) in enumerate(facs)],
+                                        N=spec["N"], call_id=spec["call_id"], any_multihypo=spec["any_multihypo"])])
+            stage = (np.zeros(off), np.zeros(ns * A.IIF_MAX_DIM), np.zeros(ns, dtype=np.int32), np.ones(ns, dtype=np.int32))
+            self.calls.append((order, mini, op, stage))
+        self.eng = Engine(self.calls[0][1], sp_c, device) if self.calls else None
+
+    def run(self, arena: CP.HostArena):
+        """one pass over the plan's ops in wave order, beliefs in `arena` (host)"""
+        fz, eng = self.plan.frozen, self.eng
+        for kind, a, b in self.plan.sched_waved:
+            if kind == A.S_COPY:
+                sa, sb = fz["slots"][a], fz["slots"][b]
+                n = int(arena.npts[a])
+                arena.pts[sb.pts_off:sb.pts_off + n * sa.dim] = arena.pts[sa.pts_off:sa.pts_off + n * sa.dim]
+                arena.bw[b * 4:b * 4 + 4] = arena.bw[a * 4:a * 4 + 4]
+                arena.ipc[b * 4:b * 4 + 4] = arena.ipc[a * 4:a * 4 + 4]
+                arena.npts[b], arena.flags[b] = n, arena.flags[a]
+                continue
+            if kind != A.S_PROPAGATE:
+                raise A.IIFB200Error("B3Driver: only PROPAGATE / COPY ops (useMsgLikelihoods = false plans)")
+            order, mini, op, (pts, bw, npts, flags) = self.calls[a]
+            for i, s in enumerate(order):
+                g, m = fz["slots"][s], mini["slots"][i]
+                pts[m.pts_off:m.pts_off + g.cap * g.dim] = arena.pts[g.pts_off:g.pts_off + g.cap * g.dim]
+                bw[i * 4:i * 4 + 4] = arena.bw[s * 4:s * 4 + 4]
+                npts[i], flags[i] = arena.npts[s], arena.flags[s]
+            eng.reset_graph(mini)                                          # iifb200_set_graph
+            eng.upload_slots(0, len(order), pts, bw, npts, flags)         # ONE transfer
+            eng.propagate_batch(op, 1)
+            p, w, ipc = eng.download_belief(0)
+            t = order[0]
+            g = fz["slots"][t]
+            arena.pts[g.pts_off:g.pts_off + p.size] = p.reshape(-1)
+            arena.bw[t * 4:t * 4 + g.dim], arena.ipc[t * 4:t * 4 + g.dim] = w, ipc
+            arena.npts[t], arena.flags[t] = p.shape[0], 1
+
+    def close(self):
+        if self.eng is not None:
+            self.eng.close()

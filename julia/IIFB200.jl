@@ -1,12 +1,27 @@
-# IIFB200.jl — reference-side binding of libiifb200.so (cannot be executed in the build image: no Julia).
+# IIFB200.jl — reference-side binding of libiifb200.so.
 #
-# Drop-in boundary B3 (SURVEY.md §8b): overrides IncrementalInference.propagateBelief for graphs whose
-# SolverParams.devParams[:backend] == "b200" and forwards to the C-ABI declared in include/iifb200.h.
-# Everything above (factor graph, Bayes tree, CliqueStateMachine, solveTree!) is unchanged Julia.
+# NOT EXECUTED in the build image (no Julia toolchain there); tests/test_julia_shim.py checks it as text: every
+# `ccall` symbol is declared in include/iifb200.h, every struct mirrors its C layout byte for byte, every helper the
+# module calls is defined in the module, every package it names is imported.
+#
+# Two drop-in boundaries (SURVEY.md §8b):
+#   B3  `propagateBelief(dfg, destvar, factors)` — GraphProductOperations.jl:16-64.  Graphs whose
+#       SolverParams.devParams[:backend] == "b200" forward ONE belief update per call to the C-ABI; everything above
+#       (factor graph, Bayes tree, CliqueStateMachine, solveTree!) is unchanged Julia.
+#   B4  `solveTree_b200!(dfg, tree)` — the whole up + down pass of a built Bayes tree in one schedule: the clique
+#       table (`tree.bt`: parent, frontals, separators, potentials, Gibbs variable classes of setCliqMCIDs!) goes to
+#       iifb200_plan_tree, the library lowers it to waves of independent belief updates (what the CSM would do clique
+#       by clique: upGibbsCliqueDensity SolveTree.jl:164-239, solveCliqDownFrontalProducts!
+#       CliqStateMachineUtils.jl:479-571), beliefs go up once, posteriors come back once.
 module IIFB200
 
 using IncrementalInference
 using DistributedFactorGraphs
+using Distributions
+using LinearAlgebra
+using Manifolds
+using StaticArrays
+using RecursiveArrayTools: ArrayPartition
 import IncrementalInference: propagateBelief
 const IIF = IncrementalInference
 const AMP = IIF.ApproxManifoldProducts
@@ -14,21 +29,40 @@ const AMP = IIF.ApproxManifoldProducts
 const LIB = get(ENV, "IIFB200_LIB", joinpath(@__DIR__, "..", "incrementalinference.jl_b200", "csrc", "libiifb200.so"))
 
 # ---- mirrors of the C structs (include/iifb200.h) -------------------------------------------------
-const MAX_DIM, MAX_ARITY, MAX_FACTORS = 4, 6, 8
+const MAX_DIM, MAX_ARITY, MAX_FACTORS, MAX_POINTS = 4, 6, 16, 256
 struct SlotDesc;   dim::Int32; circ_mask::Int32; cap::Int32; pts_off::Int32; end
 struct DistDesc;   kind::Int32; dim::Int32; ncomp::Int32; comp_kind::Int32; slot::Int32; poff::Int32; end
 struct FactorDesc
   kind::Int32; arity::Int32; zdim::Int32; dist::Int32
-  slot::NTuple{MAX_ARITY,Int32}; nmh::Int32; partial_mask::Int32
-  mh::NTuple{MAX_ARITY,Float64}; nullhypo::Float64; inflation::Float64
+  slot::NTuple{6,Int32}; nmh::Int32; partial_mask::Int32
+  mh::NTuple{6,Float64}; nullhypo::Float64; inflation::Float64
 end
 struct SolverParamsC; spreadNH::Float64; nullSurplusAdd::Float64; inflateCycles::Int32; gibbsNiter::Int32; seed::UInt64; end
 struct PropOp
   target_slot::Int32; out_slot::Int32; nfactors::Int32; N::Int32
-  factor::NTuple{MAX_FACTORS,Int32}; sfidx::NTuple{MAX_FACTORS,Int32}; call_id::Int32; any_multihypo::Int32
+  factor::NTuple{16,Int32}; sfidx::NTuple{16,Int32}; call_id::Int32; any_multihypo::Int32
 end
 struct SchedOp;  kind::Int32; a::Int32; b::Int32; lane::Int32; end      # kind: 1 PROPAGATE, 2 COPY, 3 DECONV
 struct DeconvOp; factor::Int32; out_slot::Int32; N::Int32; call_id::Int32; end
+struct GraphDesc
+  nvars::Int32; vars::Ptr{SlotDesc}; nfactors::Int32; factors::Ptr{FactorDesc}
+  ndists::Int32; dists::Ptr{DistDesc}; nparams::Int32; dparams::Ptr{Float64}
+end
+struct TreeDesc
+  ncliques::Int32; parent::Ptr{Int32}
+  frontal_off::Ptr{Int32}; frontals::Ptr{Int32}
+  separator_off::Ptr{Int32}; separators::Ptr{Int32}
+  potential_off::Ptr{Int32}; potentials::Ptr{Int32}
+  directFrtlMsg_off::Ptr{Int32}; directFrtlMsg::Ptr{Int32}
+  msgskip_off::Ptr{Int32}; msgskip::Ptr{Int32}
+  itervar_off::Ptr{Int32}; itervar::Ptr{Int32}
+  directPriorMsg_off::Ptr{Int32}; directPriorMsg::Ptr{Int32}
+end
+struct PlanOpts
+  N::Int32; gibbsIters::Int32; downIters::Int32; downsolve::Int32
+  lanes::Int32; forward_copies::Int32; useMsgLikelihoods::Int32; call_base::Int32
+  inflation::Float64
+end
 
 check(ctx, st, what) = st == 0 || error("iifb200 $what failed ($st): " *
         unsafe_string(ccall((:iifb200_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
@@ -40,13 +74,27 @@ function init(device::Integer = 0)
   return ctx[]
 end
 
-# factor kind / distribution lowering: only the built-in residual library runs on the device
+# one context per process (one process per GPU; the ordinal comes from the launcher's LOCAL_RANK)
+const _CTX = Ref{Ptr{Cvoid}}(C_NULL)
+const _CTX_LOCK = ReentrantLock()
+const _CALLS = Threads.Atomic{Int32}(0)              # Philox call ids: 16 per belief update, never reused
+function _ctx()
+  lock(_CTX_LOCK) do
+    _CTX[] == C_NULL && (_CTX[] = init(parse(Int, get(ENV, "LOCAL_RANK", "0"))))
+    return _CTX[]
+  end
+end
+_nextcall(n::Integer = 16) = Threads.atomic_add!(_CALLS, Int32(n))
+
+# ---- lowering of variables, distributions and factors ---------------------------------------------
+# factor kind: only the built-in residual library runs on the device
 factorkind(::Prior) = Int32(1); factorkind(::LinearRelative) = Int32(2)
 factorkind(::PriorCircular) = Int32(3); factorkind(::CircularCircular) = Int32(4)
 factorkind(::EuclidDistance) = Int32(5); factorkind(::IIF.MsgPrior) = Int32(6)
 factorkind(::IIF.PartialPrior) = Int32(7)
-factorkind(::ManifoldPrior) = Int32(8); factorkind(::IIF.ManifoldPriorPartial) = Int32(8)   # p is folded into Z's mean by _lower_factors
+factorkind(::ManifoldPrior) = Int32(8); factorkind(::IIF.ManifoldPriorPartial) = Int32(8)   # p is folded into Z's mean by _lower_dist
 factorkind(f::ManifoldFactor) = _manifoldfactorkind(f.M)
+factorkind(f::Mixture) = factorkind(f.mechanics)
 _manifoldfactorkind(::Manifolds.SpecialEuclidean{2}) = Int32(9)     # hybrid tangent representation (testSpecialEuclidean2Mani.jl:14)
 _manifoldfactorkind(::Manifolds.TranslationGroup) = Int32(2)
 _manifoldfactorkind(::Manifolds.RealCircleGroup) = Int32(4)
@@ -54,81 +102,318 @@ _manifoldfactorkind(M) = error("IIFB200: ManifoldFactor on $(M) has no device re
 factorkind(f) = error("IIFB200: factor $(typeof(f)) has no device residual (no CPU fallback on the b200 backend)")
 
 # circular-coordinate mask of a variable type; SpecialEuclidean(2) points ArrayPartition(t, R) travel as (t1, t2, theta)
-circmask(::Type{<:IIF.Circular}) = Int32(1)
-circmask(::Type{T}) where {T <: InferenceVariable} = getManifold(T) isa Manifolds.SpecialEuclidean{2} ? Int32(0b100) : Int32(0)
-circmask(::Any) = Int32(0)
+_isse2(T) = getManifold(T) isa Manifolds.SpecialEuclidean{2}
+circmask(T::Type{<:InferenceVariable}) = T <: IIF.Circular ? Int32(1) : (_isse2(T) ? Int32(0b100) : Int32(0))
+circmask(v::DFGVariable) = circmask(typeof(getVariableType(v)))
 se2coords(p) = (p.x[1][1], p.x[1][2], atan(p.x[2][2, 1], p.x[2][1, 1]))           # AMP.makeCoordsFromPoint
 se2point(c)  = ArrayPartition(SA[c[1], c[2]], SA[cos(c[3]) -sin(c[3]); sin(c[3]) cos(c[3])])   # AMP.makePointFromCoords
 
-"""
-    propagateBelief(dfg, destvar, factors; N, ...)   — GraphProductOperations.jl:16-64
+# points <-> the d x N coordinate block the device stores (== Vector{SVector{d,Float64}} in memory)
+function _packpoints(vartype, val::AbstractVector)
+  d = getDimension(vartype)
+  out = Matrix{Float64}(undef, d, length(val))
+  se2 = _isse2(typeof(vartype))
+  for (n, p) in enumerate(val)
+    c = se2 ? se2coords(p) : p
+    for k in 1:d
+      out[k, n] = c[k]
+    end
+  end
+  return out
+end
+function _unpackpoints(vartype, pts::AbstractMatrix{Float64})
+  d = size(pts, 1)
+  _isse2(typeof(vartype)) && return [se2point(view(pts, :, n)) for n in 1:size(pts, 2)]
+  vartype isa IIF.Circular && return [[pts[1, n]] for n in 1:size(pts, 2)]         # Vector{Vector{Float64}}
+  return [SVector{d, Float64}(view(pts, :, n)) for n in 1:size(pts, 2)]
+end
+_bw(v::DFGVariable, solveKey) = Vector{Float64}(getSolverData(v, solveKey).bw[:, 1])
 
-b200 backend: lowers the destination variable, its factors and their variables to the descriptor
-tables, uploads the particle blocks (zero-copy for `Vector{SVector{d,Float64}}`; `Circular`'s
-`Vector{Vector{Float64}}` is packed), runs iifb200_propagate_batch (F convolutions + KDE product) and
-rebuilds the ManifoldKernelDensity from the returned points and bandwidths.
+# an extra device slot that only holds the kernels of a ManifoldKernelDensity (the measurement of a MsgPrior)
+struct _BeliefSlot
+  vartype::Any
+  pts::Matrix{Float64}
+  bw::Vector{Float64}
+end
+
+# destination first, then the variables of every factor in factor order, each once
+function _collect_variables(dfg::AbstractDFG, destvar::DFGVariable, factors::AbstractVector)
+  vars = DFGVariable[destvar]
+  slotof = Dict{Symbol, Int32}(getLabel(destvar) => Int32(0))
+  for f in factors, lbl in getVariableOrder(f)
+    haskey(slotof, lbl) && continue
+    push!(vars, getVariable(dfg, lbl))
+    slotof[lbl] = Int32(length(vars) - 1)
+  end
+  return vars, slotof
+end
+
+# SamplableBelief -> (kind, dim, ncomp, comp_kind, slot) + parameter block; `shift` is added to the mean (ManifoldPrior's p)
+function _simpleblock(Z::Normal, shift)
+  return Int32(1), 1, Float64[mean(Z) + (shift === nothing ? 0.0 : shift[1]), std(Z)]
+end
+_simpleblock(Z::Uniform, shift) = (Int32(5), 1, Float64[minimum(Z), maximum(Z)])
+function _simpleblock(Z::AbstractMvNormal, shift)
+  d = length(Z)
+  mu = Vector{Float64}(mean(Z)) .+ (shift === nothing ? zeros(d) : collect(Float64, shift))
+  Lc = Matrix(cholesky(Symmetric(Matrix(cov(Z)))).L)
+  return Int32(2), d, vcat(mu, vec(permutedims(Lc)))          # row-major lower factor
+end
+_simpleblock(Z, shift) = error("IIFB200: distribution $(typeof(Z)) has no device sampler")
+
+function _lower_dist!(dists::Vector{DistDesc}, dparams::Vector{Float64}, extra::Vector{_BeliefSlot}, nvars::Int, Z, shift = nothing)
+  poff = Int32(length(dparams))
+  if Z isa AMP.ManifoldKernelDensity                      # MsgPrior(belief): kernels live in an extra slot
+    M = Z.manifold
+    vt = M isa Manifolds.RealCircleGroup ? IIF.Circular() : ContinuousEuclid(manifold_dimension(M))
+    push!(extra, _BeliefSlot(vt, _packpoints(vt, getPoints(Z, false)), Vector{Float64}(getBW(Z)[:, 1])))
+    push!(dists, DistDesc(Int32(4), Int32(manifold_dimension(M)), Int32(0), Int32(0), Int32(nvars + length(extra) - 1), poff))
+  else
+    kind, d, prm = _simpleblock(Z, shift)
+    append!(dparams, prm)
+    push!(dists, DistDesc(kind, Int32(d), Int32(0), Int32(0), Int32(-1), poff))
+  end
+  return Int32(length(dists) - 1)
+end
+
+function _lower_mixture!(dists, dparams, mix::Mixture)
+  poff = Int32(length(dparams))
+  comps = collect(values(mix.components))
+  blocks = [_simpleblock(c, nothing) for c in comps]
+  length(unique(b[1] for b in blocks)) == 1 && length(unique(b[2] for b in blocks)) == 1 ||
+    error("IIFB200: Mixture components must share one distribution kind and dimension")
+  append!(dparams, Vector{Float64}(probs(mix.diversity)))
+  foreach(b -> append!(dparams, b[3]), blocks)
+  push!(dists, DistDesc(Int32(3), Int32(blocks[1][2]), Int32(length(blocks)), blocks[1][1], Int32(-1), poff))
+  return Int32(length(dists) - 1)
+end
+
+_padtuple(v, n, T) = ntuple(i -> i <= length(v) ? T(v[i]) : zero(T), n)
+
+# factor objects -> descriptor tables; variables are referenced through `slotof`
+function _lower_factors(dfg::AbstractDFG, factors::AbstractVector, slotof::Dict{Symbol, Int32}, nvars::Int)
+  dists, dparams, fdescs, extra = DistDesc[], Float64[], FactorDesc[], _BeliefSlot[]
+  for f in factors
+    fnc = getFactorType(f)
+    ccw = IIF._getCCW(f)
+    vo = getVariableOrder(f)
+    length(vo) <= MAX_ARITY || error("IIFB200: factor $(getLabel(f)) has more than $MAX_ARITY variables")
+    shift = nothing
+    if fnc isa ManifoldPrior || fnc isa IIF.ManifoldPriorPartial
+      p = fnc isa ManifoldPrior ? fnc.p : nothing        # sample = retract(M, p, hat(Z)) = p (+) Z on these groups
+      shift = p === nothing ? nothing : (p isa ArrayPartition ? collect(se2coords(p)) : collect(Float64, p))
+    end
+    di = fnc isa Mixture ? _lower_mixture!(dists, dparams, fnc) : _lower_dist!(dists, dparams, extra, nvars, fnc.Z, shift)
+    pmask = Int32(0)
+    if hasfield(typeof(fnc), :partial)
+      for c in fnc.partial
+        pmask |= Int32(1) << (Int(c) - 1)
+      end
+    end
+    mh = ccw.hyporecipe.hypotheses === nothing ? Float64[] : Vector{Float64}(probs(ccw.hyporecipe.hypotheses))
+    push!(fdescs, FactorDesc(factorkind(fnc), Int32(length(vo)), dists[di + 1].dim, di,
+                             _padtuple([slotof[l] for l in vo], MAX_ARITY, Int32), Int32(length(mh)), pmask,
+                             _padtuple(mh, MAX_ARITY, Float64), ccw.nullhypo, ccw.inflation))
+  end
+  return dists, dparams, fdescs, extra
+end
+
+_solverparams(sp, seed = rand(UInt64)) = SolverParamsC(sp.spreadNH, sp.nullSurplusAdd, sp.inflateCycles, 1, seed)
+
+function _set_graph(ctx, slots, fdescs, dists, dparams, spc)
+  GC.@preserve slots dists dparams fdescs begin
+    check(ctx, ccall((:iifb200_set_graph, LIB), Int32,
+          (Ptr{Cvoid}, Int32, Ptr{SlotDesc}, Int32, Ptr{FactorDesc}, Int32, Ptr{DistDesc}, Int32, Ptr{Float64}, Ref{SolverParamsC}, Ptr{Cvoid}),
+          ctx, length(slots), slots, length(fdescs), fdescs, length(dists), dists, length(dparams), dparams, Ref(spc), C_NULL), "set_graph")
+  end
+end
+# all beliefs of a freshly set graph in ONE asynchronous transfer: slot i occupies cap_i * dim_i doubles of `pts`
+function _upload_all(ctx, slots::Vector{SlotDesc}, blocks::Vector{Matrix{Float64}}, bws::Vector{Vector{Float64}}, inits::Vector{Bool})
+  ns = length(slots)
+  pts = zeros(sum(Int(s.cap) * Int(s.dim) for s in slots)); bw = zeros(MAX_DIM, ns)
+  npts = zeros(Int32, ns); flags = zeros(Int32, ns)
+  off = 0
+  for i in 1:ns
+    p = blocks[i]
+    pts[(off + 1):(off + length(p))] .= vec(p)
+    off += Int(slots[i].cap) * Int(slots[i].dim)
+    bw[1:length(bws[i]), i] .= bws[i]; npts[i] = size(p, 2); flags[i] = inits[i]
+  end
+  check(ctx, ccall((:iifb200_upload_slots, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+        ctx, 0, ns, pts, bw, npts, flags), "upload_slots")
+  return pts   # keep alive until the next synchronising call
+end
+
+"""
+    propagateBelief(dfg, destvar, factors; N, ...)   — GraphProductOperations.jl:16-64   (boundary B3)
+
+b200 backend: lowers the destination variable, its factors and their variables to the descriptor tables, uploads the
+particle blocks, runs iifb200_propagate_batch (F convolutions + KDE product in two launches) and rebuilds the
+ManifoldKernelDensity from the returned points and bandwidths.  The library keeps its arena, tables and scratch
+between calls (grow-only), so a call costs the uploads, two kernels and one download.
 """
 function propagateBelief(dfg::AbstractDFG, destvar::DFGVariable, factors::AbstractVector;
                          solveKey::Symbol = :default, N::Integer = getSolverParams(dfg).N, kw...)
   get(getSolverParams(dfg).devParams, :backend, "") == "b200" ||
     return invoke(propagateBelief, Tuple{AbstractDFG, DFGVariable, AbstractVector}, dfg, destvar, factors; solveKey, N, kw...)
+  length(factors) <= MAX_FACTORS || error("IIFB200: $(length(factors)) factors exceed IIF_MAX_FACTORS = $MAX_FACTORS")
   ctx = _ctx()
-  vars, slotof = _collect_variables(dfg, destvar, factors)           # labels -> slot index
-  slots   = [SlotDesc(getDimension(v), circmask(getVariableType(v)), max(N, length(getVal(v; solveKey))), 0) for v in vars]
-  dists, dparams, fdescs = _lower_factors(dfg, factors, slotof)       # Normal / MvNormal / Mixture / MsgPrior(MKD)
-  sp = getSolverParams(dfg)
-  spc = Ref(SolverParamsC(sp.spreadNH, sp.nullSurplusAdd, sp.inflateCycles, 1, rand(UInt64)))
-  GC.@preserve slots dists dparams fdescs begin
-    check(ctx, ccall((:iifb200_set_graph, LIB), Int32,
-          (Ptr{Cvoid}, Int32, Ptr{SlotDesc}, Int32, Ptr{FactorDesc}, Int32, Ptr{DistDesc}, Int32, Ptr{Float64}, Ref{SolverParamsC}, Ptr{Cvoid}),
-          ctx, length(slots), slots, length(fdescs), fdescs, length(dists), dists, length(dparams), dparams, spc, C_NULL), "set_graph")
-    for (i, v) in enumerate(vars)
-      pts = _packpoints(getVal(v; solveKey))                         # reinterpret(Float64, val) when contiguous
-      bw  = getBW(v; solveKey)[:, 1]
-      check(ctx, ccall((:iifb200_upload_belief, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32),
-            ctx, i - 1, size(pts, 2), pts, bw, isInitialized(v, solveKey)), "upload_belief")
-    end
-    dest = slotof[getLabel(destvar)]
-    op = Ref(PropOp(dest, dest, length(fdescs), N,
-                    ntuple(i -> i <= length(fdescs) ? Int32(i - 1) : Int32(0), MAX_FACTORS),
-                    ntuple(i -> i <= length(fdescs) ? Int32(findfirst(==(getLabel(destvar)), getVariableOrder(factors[i]))) : Int32(0), MAX_FACTORS),
-                    0, any(IIF.isMultihypo.(factors))))
+  vars, slotof = _collect_variables(dfg, destvar, factors)           # labels -> slot index (destination = slot 0)
+  dists, dparams, fdescs, extra = _lower_factors(dfg, factors, slotof, length(vars))
+  slots = SlotDesc[SlotDesc(getDimension(v), circmask(v), max(N, length(getVal(v; solveKey)), 1), 0) for v in vars]
+  for e in extra
+    push!(slots, SlotDesc(size(e.pts, 1), circmask(typeof(e.vartype)), max(size(e.pts, 2), 1), 0))
+  end
+  local pts, bw, ipc
+  lock(_CTX_LOCK) do                                                 # one context: serialise the cliques' Tasks
+    _set_graph(ctx, slots, fdescs, dists, dparams, _solverparams(getSolverParams(dfg)))
+    staged = _upload_all(ctx, slots,
+                         vcat([_packpoints(getVariableType(v), getVal(v; solveKey)) for v in vars], [e.pts for e in extra]),
+                         vcat([_bw(v, solveKey) for v in vars], [e.bw for e in extra]),
+                         vcat(Bool[isInitialized(v, solveKey) for v in vars], fill(true, length(extra))))
+    dlbl = getLabel(destvar)
+    op = Ref(PropOp(0, 0, length(fdescs), N,
+                    _padtuple(collect(0:(length(fdescs) - 1)), MAX_FACTORS, Int32),
+                    _padtuple([findfirst(==(dlbl), getVariableOrder(f)) for f in factors], MAX_FACTORS, Int32),
+                    _nextcall(), any(IIF.isMultihypo.(factors))))
     # blocking ccall on a dedicated thread so the other cliques' Tasks keep running (SolverAPI.jl:59-96)
     st = @threadcall((:iifb200_propagate_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{PropOp}), ctx, 1, op)
     check(ctx, st, "propagate_batch")
     d = getDimension(destvar)
-    pts = Matrix{Float64}(undef, d, N); bw = zeros(d); ipc = zeros(d); npts = Ref{Int32}(0)
+    pts = Matrix{Float64}(undef, d, max(N, slots[1].cap)); bw = zeros(d); ipc = zeros(d); npts = Ref{Int32}(0)
     check(ctx, ccall((:iifb200_download_belief, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-          ctx, dest, npts, pts, bw, ipc), "download_belief")
+          ctx, 0, npts, pts, bw, ipc), "download_belief")
+    pts = pts[:, 1:npts[]]
   end
   M = getManifold(getVariableType(destvar))
   mkd = AMP.manikde!(M, _unpackpoints(getVariableType(destvar), pts); bw)   # bw given => no re-selection (FGOSUtils.jl:118-128)
   return mkd, ipc
 end
 
-"""
-    calcPPE(var, varType; solveKey)   — FGOSUtils.jl:237-278 (setPPE! at CSM step 5 funnels through it)
+# ---- boundary B4: the whole tree pass ---------------------------------------------------------------
+_csr(lists) = (Int32[0; cumsum(length.(lists))], Int32[x for l in lists for x in l])
 
-b200 backend: mean and KDE-max of a belief that is resident on the device (`slot` = its slot index in the
-tables uploaded by the enclosing clique solve) from one `iifb200_ppe_batch` launch.
 """
-function calcPPE_b200(slots::Vector{Int32})
-  ctx = _ctx(); V = length(slots)
-  mean = zeros(4, V); mx = zeros(4, V)
-  check(ctx, ccall((:iifb200_ppe_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
-        ctx, V, slots, mean, mx), "ppe_batch")
-  return mean, mx      # column v: coordinates of belief v; MeanMaxPPE(suggested = mean, max = mx, mean = mean)
+    solveTree_b200!(dfg, tree; solveKey, lanes, downsolve)
+
+Up + down pass of an already built Bayes tree (`buildTreeReset!`) on the device: `tree.bt`'s clique table goes through
+iifb200_plan_tree / iifb200_plan_upload, the graph's beliefs through iifb200_upload_slots, one iifb200_schedule_run
+replays the pass as a CUDA graph and iifb200_download_slots returns every posterior, which is written back with
+setValKDE! (CSM step 5, updateFromSubgraph).  useMsgLikelihoods = true plans are lowered host-side (tree.py mirror).
+"""
+function solveTree_b200!(dfg::AbstractDFG, tree; solveKey::Symbol = :default, lanes::Integer = 4,
+                         downsolve::Bool = getSolverParams(dfg).downsolve)
+  sp = getSolverParams(dfg)
+  ctx = _ctx()
+  vlbls = listVariables(dfg); sort!(vlbls; by = l -> getVariable(dfg, l).nstime)       # graph (insertion) order
+  flbls = listFactors(dfg);   sort!(flbls; by = l -> getFactor(dfg, l).nstime)
+  vidx = Dict(l => Int32(i - 1) for (i, l) in enumerate(vlbls))
+  fidx = Dict(l => Int32(i - 1) for (i, l) in enumerate(flbls))
+  vars = [getVariable(dfg, l) for l in vlbls]
+  fcts = [getFactor(dfg, l) for l in flbls]
+  N = sp.N
+  gslots = SlotDesc[SlotDesc(getDimension(v), circmask(v), max(N, length(getVal(v; solveKey)), 1), 0) for v in vars]
+  dists, dparams, fdescs, extra = _lower_factors(dfg, fcts, vidx, length(vars))
+  isempty(extra) || error("IIFB200: graph factors with belief-valued measurements are not supported in a tree plan")
+  # cliques numbered parents first: breadth-first from the roots over `tree.bt`
+  cliqs = collect(values(IIF.getCliques(tree)))
+  order = IIF.TreeClique[]; queue = [c for c in cliqs if isempty(IIF.getParent(tree, c))]
+  while !isempty(queue)
+    c = popfirst!(queue); push!(order, c); append!(queue, IIF.getChildren(tree, c))
+  end
+  cid = Dict(c.id => Int32(i - 1) for (i, c) in enumerate(order))
+  parent = Int32[isempty(IIF.getParent(tree, c)) ? Int32(-1) : cid[IIF.getParent(tree, c)[1].id] for c in order]
+  lists(get, idx) = _csr([[idx[x] for x in get(IIF.getCliqueData(c))] for c in order])
+  fo, fr = _csr([[vidx[x] for x in IIF.getCliqFrontalVarIds(c)] for c in order])
+  so, se = _csr([[vidx[x] for x in IIF.getCliqSeparatorVarIds(c)] for c in order])
+  po, pt = lists(d -> d.potentials, fidx)
+  d1o, d1 = lists(d -> d.directFrtlMsgIDs, vidx)
+  d2o, d2 = lists(d -> d.msgskipIDs, vidx)
+  d3o, d3 = lists(d -> d.itervarIDs, vidx)
+  d4o, d4 = lists(d -> d.directPriorMsgIDs, vidx)
+  plan = Ref{Ptr{Cvoid}}(C_NULL); sid = Ref{Int32}(-1)
+  nd = sum(s.cap * s.dim for s in gslots)
+  hpts = zeros(nd); hbw = zeros(MAX_DIM, length(vars)); hipc = zeros(MAX_DIM, length(vars))
+  hn = zeros(Int32, length(vars)); hfl = ones(Int32, length(vars))
+  off = 0
+  for (i, v) in enumerate(vars)
+    p = _packpoints(getVariableType(v), getVal(v; solveKey))
+    hpts[(off + 1):(off + length(p))] .= vec(p); off += gslots[i].cap * gslots[i].dim
+    hbw[1:size(p, 1), i] .= _bw(v, solveKey); hn[i] = size(p, 2); hfl[i] = isInitialized(v, solveKey)
+  end
+  GC.@preserve gslots fdescs dists dparams parent fo fr so se po pt d1o d1 d2o d2 d3o d3 d4o d4 begin
+    gd = Ref(GraphDesc(length(vars), pointer(gslots), length(fdescs), pointer(fdescs), length(dists), pointer(dists),
+                       length(dparams), pointer(dparams)))
+    td = Ref(TreeDesc(length(order), pointer(parent), pointer(fo), pointer(fr), pointer(so), pointer(se), pointer(po), pointer(pt),
+                      pointer(d1o), pointer(d1), pointer(d2o), pointer(d2), pointer(d3o), pointer(d3), pointer(d4o), pointer(d4)))
+    opts = Ref(PlanOpts(N, sp.gibbsIters, 3, downsolve, lanes, 1, 0, _nextcall(16 * 64 * length(vars)), sp.inflation))
+    st = ccall((:iifb200_plan_tree, LIB), Int32, (Ref{GraphDesc}, Ref{TreeDesc}, Ref{PlanOpts}, Ref{Ptr{Cvoid}}), gd, td, opts, plan)
+    st == 0 || error("iifb200_plan_tree failed ($st): " * unsafe_string(ccall((:iifb200_plan_error, LIB), Cstring, ())))
+  end
+  lock(_CTX_LOCK) do
+    check(ctx, ccall((:iifb200_plan_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{SolverParamsC}, Ptr{Cvoid}, Ref{Int32}),
+          ctx, plan[], Ref(_solverparams(sp)), C_NULL, sid), "plan_upload")
+    check(ctx, ccall((:iifb200_upload_slots, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+          ctx, 0, length(vars), hpts, hbw, hn, hfl), "upload_slots")
+    check(ctx, @threadcall((:iifb200_schedule_run, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), ctx, sid[], 0, -1), "schedule_run")
+    check(ctx, ccall((:iifb200_download_slots, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+          ctx, 0, length(vars), hpts, hbw, hipc, hn), "download_slots")
+    check(ctx, @threadcall((:iifb200_sync, LIB), Int32, (Ptr{Cvoid},), ctx), "sync")
+    check(ctx, ccall((:iifb200_schedule_free, LIB), Int32, (Ptr{Cvoid}, Int32), ctx, sid[]), "schedule_free")
+  end
+  ccall((:iifb200_plan_free, LIB), Cvoid, (Ptr{Cvoid},), plan[])
+  off = 0
+  for (i, v) in enumerate(vars)
+    d = Int(gslots[i].dim); n = Int(hn[i])
+    pts = reshape(hpts[(off + 1):(off + d * n)], d, n); off += gslots[i].cap * d
+    M = getManifold(getVariableType(v))
+    mkd = AMP.manikde!(M, _unpackpoints(getVariableType(v), pts); bw = hbw[1:d, i])
+    setValKDE!(v, mkd, true, hipc[1:d, i]; solveKey)                      # FactorGraph.jl:237-286
+    setPPE!(v, getVariableType(v), solveKey)                               # FGOSUtils.jl:546-570
+  end
+  return dfg
 end
 
 """
-    approxDeconv(dfg, fctsym)   — DeconvUtils.jl:176-202,  mmd(p1, p2, varType) — SolverUtilities.jl:25-47
+    calcPPE_b200(dfg, labels; solveKey)   — calcPPE, FGOSUtils.jl:237-278 (setPPE! at CSM step 5 funnels through it)
+
+Mean and KDE-max of several variables' beliefs from one `iifb200_ppe_batch` launch (beliefs are uploaded first).
 """
-function approxDeconv_b200(factor::Integer, N::Integer, zdim::Integer)
-  ctx = _ctx()
+function calcPPE_b200(dfg::AbstractDFG, labels::Vector{Symbol}; solveKey::Symbol = :default)
+  ctx = _ctx(); vars = [getVariable(dfg, l) for l in labels]; V = length(vars)
+  slots = SlotDesc[SlotDesc(getDimension(v), circmask(v), max(length(getVal(v; solveKey)), 1), 0) for v in vars]
+  mean = zeros(MAX_DIM, V); mx = zeros(MAX_DIM, V)
+  lock(_CTX_LOCK) do
+    _set_graph(ctx, slots, FactorDesc[], DistDesc[], Float64[], _solverparams(getSolverParams(dfg)))
+    staged = _upload_all(ctx, slots, [_packpoints(getVariableType(v), getVal(v; solveKey)) for v in vars],
+                         [_bw(v, solveKey) for v in vars], fill(true, V))
+    check(ctx, ccall((:iifb200_ppe_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+          ctx, V, Int32.(0:(V - 1)), mean, mx), "ppe_batch")
+  end
+  return [MeanMaxPPE(solveKey, mean[1:getDimension(v), i], mx[1:getDimension(v), i], mean[1:getDimension(v), i])
+          for (i, v) in enumerate(vars)]
+end
+
+"""
+    approxDeconv_b200(dfg, fctsym; solveKey)   — approxDeconv, DeconvUtils.jl:176-202
+"""
+function approxDeconv_b200(dfg::AbstractDFG, fctsym::Symbol; solveKey::Symbol = :default)
+  ctx = _ctx(); f = getFactor(dfg, fctsym)
+  vo = getVariableOrder(f); vars = [getVariable(dfg, l) for l in vo]
+  slotof = Dict(l => Int32(i - 1) for (i, l) in enumerate(vo))
+  dists, dparams, fdescs, extra = _lower_factors(dfg, [f], slotof, length(vars))
+  isempty(extra) || error("IIFB200: approxDeconv of a belief-valued prior is not supported")
+  N = length(getVal(vars[1]; solveKey)); zdim = Int(fdescs[1].zdim)
+  slots = SlotDesc[SlotDesc(getDimension(v), circmask(v), max(N, length(getVal(v; solveKey)), 1), 0) for v in vars]
   pred = zeros(zdim, N); meas = zeros(zdim, N)
-  check(ctx, ccall((:iifb200_deconv_batch, LIB), Int32,
-        (Ptr{Cvoid}, Int32, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ptr{Float64}, Ptr{Float64}),
-        ctx, 1, Int32(factor), Int32(N), Int32(rand(0:2^30)), pred, meas), "deconv_batch")
+  lock(_CTX_LOCK) do
+    _set_graph(ctx, slots, fdescs, dists, dparams, _solverparams(getSolverParams(dfg)))
+    staged = _upload_all(ctx, slots, [_packpoints(getVariableType(v), getVal(v; solveKey)) for v in vars],
+                         [_bw(v, solveKey) for v in vars], fill(true, length(vars)))
+    check(ctx, ccall((:iifb200_deconv_batch, LIB), Int32,
+          (Ptr{Cvoid}, Int32, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ptr{Float64}, Ptr{Float64}),
+          ctx, 1, Int32(0), Int32(N), _nextcall(), pred, meas), "deconv_batch")
+  end
   return pred, meas
 end
 
@@ -141,12 +426,8 @@ function mmd_b200(a::Matrix{Float64}, b::Matrix{Float64}; circmask::Integer = 0,
 end
 
 """
-    schedule(ctx, wave_off, ops, props, deconvs) -> id     — boundary B4 (whole clique / whole tree per replay)
-
-`ops` in wave order (`wave_off[w]:wave_off[w+1]` are mutually independent), `props` the propagateBelief descriptors,
-`deconvs` the differential-likelihood constructions of `useMsgLikelihoods=true` up messages
-(addLikelihoodsDifferentialCHILD!, TreeMessageUtils.jl:279-335).  `SchedOp.lane` marks independent sub-trees that
-the captured CUDA graph runs as parallel branches (0 = none).
+    schedule(ctx, wave_off, ops, props, deconvs) -> id     — explicit wave lists (plans lowered by the caller, e.g.
+useMsgLikelihoods = true with IIF_S_DECONV ops, addLikelihoodsDifferentialCHILD! TreeMessageUtils.jl:279-335)
 """
 function schedule(ctx, wave_off::Vector{Int32}, ops::Vector{SchedOp}, props::Vector{PropOp}, deconvs::Vector{DeconvOp} = DeconvOp[])
   id = Ref{Int32}(-1)
@@ -156,9 +437,5 @@ function schedule(ctx, wave_off::Vector{Int32}, ops::Vector{SchedOp}, props::Vec
   return id[]
 end
 run!(ctx, id; first = 0, last = -1) = check(ctx, ccall((:iifb200_schedule_run, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), ctx, id, first, last), "schedule_run")
-
-# throughput mode (boundary B4): IIF.upGibbsCliqueDensity / localProductAndUpdate! are lowered per tree by
-# iifb200_schedule_build and replayed by iifb200_schedule_run; see incrementalinference.jl_b200/tree.py for
-# the lowering that a Julia implementation mirrors 1:1 (same descriptor structs).
 
 end # module

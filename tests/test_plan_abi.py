@@ -113,3 +113,24 @@ def test_plan_upload_solves_like_the_python_path(built):
         for x, y in zip(ts.arena.get(ts.plan.var_slot[l]), tc.arena.get(tc.plan.var_slot[l])):
             assert np.array_equal(x, y), l
     ts.close(); tc.close()
+
+
+@pytest.mark.gpu
+def test_b3_per_call_path_equals_the_one_schedule_run(built):
+    """boundary B3 (one propagateBelief per C-ABI round trip, as julia/IIFB200.jl's propagateBelief does) gives the
+    posteriors of boundary B4 (one schedule): same ops, same Philox call ids; only the number of round trips differs."""
+    from iifb200 import solver as SV
+    fg, order = W.scalar_chain(24, N=64, seed=3), W.chain_nd_order(24)
+    ts = SV.TreeSolver(fg, order)
+    ts.load_from_graph(); ts.upload(); ts.run(); ts.download()
+    b3 = SV.B3Driver(ts.plan, ts.sp_c)
+    ar = CP.HostArena(ts.plan.frozen)
+    for l, v in fg.variables.items():
+        ar.set(ts.plan.var_slot[l], v.val, v.bw, True)
+    b3.run(ar)
+    n0 = b3.eng.launch_count()
+    assert n0 >= len(ts.plan.props)
+    for l in fg.variables:
+        a, b = ts.arena.get(ts.plan.var_slot[l]), ar.get(ts.plan.var_slot[l])
+        assert np.allclose(a[0], b[0], rtol=0, atol=1e-9) and np.allclose(a[1], b[1], rtol=1e-7), l
+    b3.close(); ts.close()
