@@ -121,8 +121,9 @@ def make_config(n_poses, world, order_kind, plan, lanes):
             "schedule": f"b200 arm: one CUDA graph per pass, {lanes} lanes (independent sub-trees as parallel graph "
                         "branches), separator copies forwarded; reference arm: the same plan, OpenMP over the "
                         "independent ops of a wave",
-            "sharding": "1 GPU" if world == 1 else f"{world} contiguous {POSES_PER_GPU}-pose segments, separator "
-                                                    "messages between ranks"}
+            "sharding": "1 GPU" if world == 1 else f"{world} ranks, sub-trees balanced by convolution count, separator "
+                                                    "messages pushed over NVLink inside the CUDA graphs (CUDA IPC peer "
+                                                    "arenas), posteriors gathered on rank 0"}
 
 
 def build_workload(n_poses, order_kind):
@@ -201,7 +202,7 @@ def run_reference(args, rank, world):
     plan = TR.compile_solve(fg, tree, lanes=4)
     cfg_plan = plan
     if world > 1:
-        fgN, orderN = build_workload(POSES_PER_GPU * world, args.order)
+        fgN, orderN = build_workload(POSES_PER_GPU * world if args.scaling == "weak" else POSES_PER_GPU, args.order)
         cfg_plan = TR.compile_solve(fgN, TR.buildTree(fgN, orderN), lanes=4)
     base = CP.HostArena(plan.frozen)
     for l, v in fg.variables.items():
@@ -223,9 +224,9 @@ def run_reference(args, rank, world):
     out = {
         "impl": "reference", "metric": "clique belief convolutions/sec (N=100 particles)", "value": val,
         "unit": "conv/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": make_config(POSES_PER_GPU * world, world, args.order, cfg_plan, 4),
+        "config": make_config(POSES_PER_GPU * world if args.scaling == "weak" else POSES_PER_GPU, world, args.order, cfg_plan, 4),
         "cpu_baseline": {"value": val, "unit": "conv/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "conv/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -307,13 +308,13 @@ def run_b200(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n_poses = POSES_PER_GPU * world
+    n_poses = POSES_PER_GPU * world if args.scaling == "weak" else POSES_PER_GPU
     fg, order = build_workload(n_poses, args.order)
     if world == 1:
         ts = SV.TreeSolver(fg, order, device=local_rank)
         runner = None
     else:
-        runner = ShardedTreeSolver(fg, order, rank, world, local_rank, dist)
+        runner = ShardedTreeSolver(fg, order, rank, world, local_rank, dist, gather="root")
         ts = runner.ts
     plan, eng = ts.plan, ts.eng
     nvars = len(fg.variables)
@@ -363,6 +364,8 @@ def run_b200(args, rank, world, local_rank):
     eng.upload_slots(0, nvars, hp, hbw, hn, hfl)
     for it in range(max(args.warmup, 3)):
         set_seed(1000 + it)
+        if dist is not None:
+            barrier()          # consecutive sharded passes are separated by a barrier (peer pushes land in replicas)
         solve()
     barrier()
 
@@ -375,6 +378,9 @@ def run_b200(args, rank, world, local_rank):
     l0 = eng.launch_count()
     ms_steps = []
     for it in range(args.steps):
+        hp[:] = init_pts                     # every timed step starts from the graph's initial beliefs (untimed upload)
+        eng.upload_slots(0, nvars, hp, hbw, hn, hfl)
+        eng.sync()
         flush_l2()
         set_seed(it)
         if dist is not None:
@@ -456,7 +462,7 @@ def run_b200(args, rank, world, local_rank):
     out = {
         "metric": "clique belief convolutions/sec (N=100 particles)", "value": val, "unit": "conv/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": make_config(n_poses, world, args.order, plan, max(plan.op_lane) if runner is None else max(runner.lanes)),
         "e2e": {"value": total_conv * args.steps / e2e_s, "unit": "conv/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -497,6 +503,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--order", default="nd", choices=["nd", "natural"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 1000 poses per GPU (default); strong: the 1000-pose chain itself over all GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-b3", action="store_true", help="skip the per-call (boundary B3) measurement")
     args = ap.parse_args()

@@ -162,10 +162,24 @@ typedef struct {
 enum iif_sched_kind {
   IIF_S_PROPAGATE = 1, /* propagateBelief + setBelief!  (SolveTree.jl:63-74)                */
   IIF_S_COPY = 2,      /* slot := slot (separator message adoption, TreeMessageUtils.jl:66) */
-  IIF_S_DECONV = 3     /* differential likelihood of an up message (useMsgLikelihoods=true):
+  IIF_S_DECONV = 3,    /* differential likelihood of an up message (useMsgLikelihoods=true):
                           slot := manikde!(exp(M, eps, approxDeconv(dummy factor)))
                           addLikelihoodsDifferentialCHILD!, TreeMessageUtils.jl:279-335            */
+  /* multi-GPU (one process per GPU, peer arenas attached with iifb200_ipc_attach): a separator message that crosses
+   * a GPU boundary (prepCliqueMsgUp TreeMessageUtils.jl:667-703 going up, CliqDownMessage CliqueStateMachine.jl:672-691
+   * coming down) is a PUSH node on the sender and a WAIT node on the receiver INSIDE the captured CUDA graphs: no host
+   * call, no graph split.  a = index into the iif_xfer_op table. */
+  IIF_S_PUSH = 4,      /* copy belief slot xfer.slot into the same slot of peer xfer.peer over NVLink, then raise the
+                          peer's flag xfer.msg (runs after the segment's kernels)                   */
+  IIF_S_WAIT = 5       /* spin until the local flag xfer.msg has been raised in this replay (runs before the segment's
+                          kernels)                                                                 */
 };
+typedef struct {
+  int32_t slot; /* belief slot (same index and layout on every rank: all ranks build the same slot table) */
+  int32_t peer; /* PUSH: destination rank;  WAIT: source rank (informational) */
+  int32_t msg;  /* message id == flag index, unique per (slot, destination) in a pass, < nflags */
+  int32_t _pad;
+} iif_xfer_op;
 
 /* One differential-likelihood construction (TreeMessageUtils.jl:314-321): approxDeconv of the (dummy)
  * relative factor `factor` over two separator beliefs, the predicted measurements mapped to points
@@ -305,6 +319,19 @@ int32_t iifb200_schedule_build_ex(iifb200_ctx* ctx, int32_t nwaves, const int32_
                                   int32_t nops, const iif_sched_op* ops, int32_t nprops,
                                   const iif_prop_op* props, int32_t ndeconvs,
                                   const iif_deconv_op* deconvs, int32_t* schedule_id_out);
+/* same, with IIF_S_PUSH / IIF_S_WAIT ops for schedules whose passes exchange beliefs with peer GPUs (call
+ * iifb200_ipc_attach first).  Such a schedule must be run whole (first_wave = 0, last_wave = -1): every replay advances
+ * the epoch the flags are compared with, on every rank alike. */
+int32_t iifb200_schedule_build_dist(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
+                                    const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props,
+                                    int32_t ndeconvs, const iif_deconv_op* deconvs, int32_t nxfers,
+                                    const iif_xfer_op* xfers, int32_t* schedule_id_out);
+/* Peer memory.  iifb200_ipc_export (after iifb200_set_graph, library-owned arena) allocates `nflags` message flags
+ * and returns the 64-byte CUDA IPC handles of the arena and of the flags; the caller all-gathers them (e.g. with
+ * torch.distributed) and hands every rank's handles to iifb200_ipc_attach, which maps the peers' arenas and flags. */
+int32_t iifb200_ipc_export(iifb200_ctx* ctx, int32_t nflags, void* arena_handle64, void* flags_handle64);
+int32_t iifb200_ipc_attach(iifb200_ctx* ctx, int32_t world, int32_t rank, const void* arena_handles,
+                           const void* flags_handles);
 /* Runs schedule asynchronously on the ctx stream; `first_wave,last_wave` select a wave range
  * (multi-GPU: run to a cut level, exchange separator messages with NCCL, continue). */
 int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t first_wave,

@@ -21,7 +21,7 @@ F_MANIFOLD_PRIOR, F_SE2_RELATIVE = 8, 9
 # iif_dist_kind
 D_NORMAL, D_MVNORMAL, D_MIXTURE, D_KDE, D_UNIFORM = 1, 2, 3, 4, 5
 # iif_sched_kind
-S_PROPAGATE, S_COPY, S_DECONV = 1, 2, 3
+S_PROPAGATE, S_COPY, S_DECONV, S_PUSH, S_WAIT = 1, 2, 3, 4, 5
 
 
 class DistDesc(C.Structure):
@@ -71,6 +71,10 @@ class DeconvOp(C.Structure):
 
 class SchedOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("lane", C.c_int32)]
+
+
+class XferOp(C.Structure):
+    _fields_ = [("slot", C.c_int32), ("peer", C.c_int32), ("msg", C.c_int32), ("_pad", C.c_int32)]
 
 
 class GraphDesc(C.Structure):
@@ -129,6 +133,10 @@ SYMBOLS = {
                                            P(PropOp), _ip]),
     "iifb200_schedule_build_ex": (C.c_int32, [_vp, C.c_int32, _ip, C.c_int32, P(SchedOp), C.c_int32,
                                               P(PropOp), C.c_int32, P(DeconvOp), _ip]),
+    "iifb200_schedule_build_dist": (C.c_int32, [_vp, C.c_int32, _ip, C.c_int32, P(SchedOp), C.c_int32, P(PropOp),
+                                                C.c_int32, P(DeconvOp), C.c_int32, P(XferOp), _ip]),
+    "iifb200_ipc_export": (C.c_int32, [_vp, C.c_int32, _vp, _vp]),
+    "iifb200_ipc_attach": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp, _vp]),
     "iifb200_schedule_run": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32]),
     "iifb200_schedule_free": (C.c_int32, [_vp, C.c_int32]),
     "iifb200_schedule_profile": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, P(C.c_float), _ip,

@@ -683,6 +683,51 @@ __global__ void iif_copy_kernel(DeviceGraph g, const int32_t* __restrict__ pairs
   }
 }
 
+// ---- multi-GPU separator messages inside the captured graph -------------------------------------------------
+// A message = one belief slot copied into the SAME slot of a peer GPU's arena (mapped through CUDA IPC), followed by a
+// flag raise in the peer's memory; the receiver's graph holds a WAIT node in front of the kernels that read the slot.
+// Flags carry the replay's epoch (a device counter every rank advances once per replay), so they never need clearing.
+struct PushTask {
+  int32_t slot, _pad;
+  double* r_pts;      // peer arena: points of the slot
+  double* r_bw;       // peer arena: bandwidth row of the slot
+  double* r_ipc;
+  int32_t* r_npts;
+  int32_t* r_flags;
+  int32_t* r_msgflag; // peer flag of this message
+};
+__global__ void iif_push_kernel(DeviceGraph g, const PushTask* __restrict__ tasks, int ntasks, const int32_t* __restrict__ epoch) {
+  const int k = blockIdx.x;
+  if (k >= ntasks) return;
+  const PushTask t = tasks[k];
+  const iif_slot_desc S = g.slots[t.slot];
+  const int n = g.npts[t.slot];
+  for (int i = threadIdx.x; i < n * S.dim; i += blockDim.x) t.r_pts[i] = g.pts[S.pts_off + i];
+  if (threadIdx.x < IIF_MAX_DIM) {
+    t.r_bw[threadIdx.x] = g.bw[t.slot * IIF_MAX_DIM + threadIdx.x];
+    t.r_ipc[threadIdx.x] = g.ipc[t.slot * IIF_MAX_DIM + threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    *t.r_npts = n;
+    *t.r_flags = g.flags[t.slot];
+  }
+  __threadfence_system();   // every thread: its stores are visible system-wide before the barrier releases thread 0
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *(volatile int32_t*)t.r_msgflag = *epoch;
+  }
+}
+__global__ void iif_wait_kernel(const int32_t* flags, const int32_t* __restrict__ ids, int n, const int32_t* __restrict__ epoch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t want = *epoch;
+  const volatile int32_t* f = flags + ids[i];
+  while (*f < want) __nanosleep(200);
+  __threadfence_system();
+}
+__global__ void iif_epoch_kernel(int32_t* epoch) { *epoch += 1; }
+
 // standalone bandwidth kernel (manikde! with bw === nothing on K point sets)
 struct BwTask {
   const double* pts;

@@ -43,6 +43,7 @@ struct TreeHost {
 struct Seg {
   int lane = 0;
   int conv0 = 0, nconv = 0, prod0 = 0, nprod = 0, copy0 = 0, ncopy = 0, dcv0 = 0, ndcv = 0;
+  int push0 = 0, npush = 0, wait0 = 0, nwait = 0;   // peer messages: waits run first, pushes last
 };
 struct Wave {
   std::vector<Seg> segs;
@@ -59,6 +60,9 @@ struct Schedule {
   ProdTask* d_prod = nullptr;
   int32_t* d_copy = nullptr;
   DeconvSlotTask* d_dcv = nullptr;
+  PushTask* d_push = nullptr;     // multi-GPU schedules (iifb200_schedule_build_dist)
+  int32_t* d_wait = nullptr;
+  bool dist = false;
   double* d_scratch = nullptr;
   int32_t* d_status = nullptr;  // nconv + nprod + ndcv device-side status codes
   int nconv = 0, nprod = 0, ndcv = 0;
@@ -98,6 +102,13 @@ struct iifb200_ctx {
   void* pool[2] = {nullptr, nullptr};
   size_t pool_cap[2] = {0, 0};
   size_t arena_cap = 0, tables_cap = 0;
+  // peer memory (one process per GPU; CUDA IPC): arenas and message flags of every rank, this rank's own included
+  int world = 1, rank = 0;
+  std::vector<void*> peer_arena;
+  std::vector<int32_t*> peer_flags;
+  int32_t* d_flags = nullptr;
+  int32_t* d_epoch = nullptr;
+  int nflags = 0;
   int64_t launches = 0;
   int max_smem_optin = 0;
   int num_sms = 148;
@@ -265,6 +276,7 @@ static void free_schedule(Schedule* s) {
   if (!s) return;
   for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second.first);
   for (auto e : s->events) cudaEventDestroy(e);
+  cudaFree(s->d_push); cudaFree(s->d_wait);
   if (!s->pooled) { cudaFree(s->d_conv); cudaFree(s->d_prod); cudaFree(s->d_copy); cudaFree(s->d_dcv); cudaFree(s->d_scratch); cudaFree(s->d_status); }
   delete s;
 }
@@ -303,7 +315,14 @@ void iifb200_free(iifb200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < (int)ctx->peer_arena.size(); ++r) {
+    if (r == ctx->rank) continue;
+    if (ctx->peer_arena[r]) cudaIpcCloseMemHandle(ctx->peer_arena[r]);
+    if (ctx->peer_flags[r]) cudaIpcCloseMemHandle(ctx->peer_flags[r]);
+  }
   free_graph(ctx, true);
+  cudaFree(ctx->d_flags);
+  cudaFree(ctx->d_epoch);
   for (auto& t : ctx->trees) if (t.d_blob) cudaFree(t.d_blob);
   cudaFree(ctx->d_trees);
   cudaFree(ctx->d_err);
@@ -948,7 +967,8 @@ int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_
 // ---- schedules: propagateBelief waves captured as a CUDA graph -----------------------------------
 static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
                               const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, int32_t ndeconvs,
-                              const iif_deconv_op* deconvs, Schedule** out, bool pooled = false) {
+                              const iif_deconv_op* deconvs, Schedule** out, bool pooled = false, int32_t nxfers = 0,
+                              const iif_xfer_op* xfers = nullptr) {
   for (int k = 0; k < ndeconvs; ++k) {
     const iif_deconv_op& D = deconvs[k];
     if (D.factor < 0 || D.factor >= (int)ctx->factors.size() || D.out_slot < 0 || D.out_slot >= (int)ctx->slots.size())
@@ -992,6 +1012,8 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
   std::vector<ProdTask> pt;
   std::vector<int32_t> cp;
   std::vector<DeconvSlotTask> dt;
+  std::vector<PushTask> pu;
+  std::vector<int32_t> wa;
   std::vector<char> dused(std::max(ndeconvs, 1), 0);
   s->pooled = pooled;
   if (pooled) {   // one-shot schedule (propagate_batch): every device array comes from the ctx pool
@@ -1030,6 +1052,7 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
     Seg G;
     G.lane = lanes[li];
     G.conv0 = (int)ct.size(); G.prod0 = (int)pt.size(); G.copy0 = (int)cp.size() / 2; G.dcv0 = (int)dt.size();
+    G.push0 = (int)pu.size(); G.wait0 = (int)wa.size();
     for (int k = wave_off[w]; k < wave_off[w + 1]; ++k) {
       const iif_sched_op& o = ops[k];
       if (!barrier && o.lane != G.lane) continue;
@@ -1037,6 +1060,25 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
         if (o.a < 0 || o.a >= (int)ctx->slots.size() || o.b < 0 || o.b >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "schedule: copy slot out of range");
         if (ctx->slots[o.a].dim != ctx->slots[o.b].dim || ctx->slots[o.b].cap < ctx->slots[o.a].cap) return fail(ctx, IIF_ERR_ARG, "schedule: copy slots incompatible");
         cp.push_back(o.a); cp.push_back(o.b);
+      } else if (o.kind == IIF_S_PUSH || o.kind == IIF_S_WAIT) {
+        if (o.a < 0 || o.a >= nxfers || !xfers) return fail(ctx, IIF_ERR_ARG, "schedule: transfer index out of range");
+        const iif_xfer_op& X = xfers[o.a];
+        if (X.msg < 0 || X.msg >= ctx->nflags) return fail(ctx, IIF_ERR_ARG, "schedule: message id exceeds the exported flags (iifb200_ipc_export)");
+        if (o.kind == IIF_S_WAIT) { wa.push_back(X.msg); continue; }
+        if (X.peer < 0 || X.peer >= ctx->world || X.peer == ctx->rank || (int)ctx->peer_arena.size() != ctx->world)
+          return fail(ctx, IIF_ERR_STATE, "schedule: PUSH to a peer that is not attached (iifb200_ipc_attach)");
+        if (X.slot < 0 || X.slot >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "schedule: transfer slot out of range");
+        const int64_t ns = (int64_t)ctx->slots.size();
+        double* rb = (double*)ctx->peer_arena[X.peer];
+        PushTask t;
+        t.slot = X.slot; t._pad = 0;
+        t.r_pts = rb + ctx->slots[X.slot].pts_off;
+        t.r_bw = rb + ctx->total_doubles + (int64_t)X.slot * IIF_MAX_DIM;
+        t.r_ipc = rb + ctx->total_doubles + ns * IIF_MAX_DIM + (int64_t)X.slot * IIF_MAX_DIM;
+        t.r_npts = (int32_t*)(rb + ctx->total_doubles + 2 * ns * IIF_MAX_DIM) + X.slot;
+        t.r_flags = t.r_npts + ns;
+        t.r_msgflag = ctx->peer_flags[X.peer] + X.msg;
+        pu.push_back(t);
       } else if (o.kind == IIF_S_DECONV) {
         if (o.a < 0 || o.a >= ndeconvs) return fail(ctx, IIF_ERR_ARG, "schedule: deconv index out of range");
         if (dused[o.a]) return fail(ctx, IIF_ERR_ARG, "schedule: a deconv op may appear once");
@@ -1092,6 +1134,7 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
     }
     G.nconv = (int)ct.size() - G.conv0; G.nprod = (int)pt.size() - G.prod0; G.ncopy = (int)cp.size() / 2 - G.copy0;
     G.ndcv = (int)dt.size() - G.dcv0;
+    G.npush = (int)pu.size() - G.push0; G.nwait = (int)wa.size() - G.wait0;
     W.nconv += G.nconv; W.nprod += G.nprod; W.ncopy += G.ncopy; W.ndcv += G.ndcv;
     W.segs.push_back(G);
    }
@@ -1108,6 +1151,15 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
   if (!pt.empty()) CK(cudaMemcpyAsync(s->d_prod, pt.data(), sizeof(ProdTask) * pt.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (!cp.empty()) CK(cudaMemcpyAsync(s->d_copy, cp.data(), sizeof(int32_t) * cp.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (!dt.empty()) CK(cudaMemcpyAsync(s->d_dcv, dt.data(), sizeof(DeconvSlotTask) * dt.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!pu.empty()) {
+    CK(cudaMalloc(&s->d_push, sizeof(PushTask) * pu.size()));
+    CK(cudaMemcpyAsync(s->d_push, pu.data(), sizeof(PushTask) * pu.size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!wa.empty()) {
+    CK(cudaMalloc(&s->d_wait, sizeof(int32_t) * wa.size()));
+    CK(cudaMemcpyAsync(s->d_wait, wa.data(), sizeof(int32_t) * wa.size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  s->dist = !pu.empty() || !wa.empty();
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
 }
@@ -1136,6 +1188,10 @@ int32_t iifb200_schedule_build_ex(iifb200_ctx* ctx, int32_t nwaves, const int32_
 // launches of one segment of a wave on stream `st`; CTA size and cluster choice follow the whole wave's width
 static int enqueue_seg(iifb200_ctx* ctx, Schedule* s, const Wave& W, const Seg& G, cudaStream_t st) {
   int k = 0;
+  if (G.nwait) {
+    iif_wait_kernel<<<(G.nwait + 127) / 128, 128, 0, st>>>(ctx->d_flags, s->d_wait + G.wait0, G.nwait, ctx->d_epoch);
+    ++k;
+  }
   if (G.ncopy) {
     iif_copy_kernel<<<G.ncopy, 128, 0, st>>>(ctx->dg, s->d_copy + 2 * G.copy0, G.ncopy);
     ++k;
@@ -1150,6 +1206,10 @@ static int enqueue_seg(iifb200_ctx* ctx, Schedule* s, const Wave& W, const Seg& 
   }
   if (G.nprod) {
     launch_k(iif_product_kernel, G.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, st, ctx->dg, s->d_prod + G.prod0, nullptr, nullptr, ctx->d_trees);
+    ++k;
+  }
+  if (G.npush) {
+    iif_push_kernel<<<G.npush, 128, 0, st>>>(ctx->dg, s->d_push + G.push0, G.npush, ctx->d_epoch);
     ++k;
   }
   return k;
@@ -1234,7 +1294,9 @@ int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t firs
         s->events.push_back(e);
       }
     }
+    if (s->dist && (first_wave != 0 || last_wave != nw)) return fail(ctx, IIF_ERR_ARG, "schedule_run: a schedule with peer messages must be run whole");
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    if (s->dist) iif_epoch_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_epoch);   // this replay's flag value
     int32_t st = enqueue_waves(ctx, s, first_wave, last_wave, &nk, true, &pool);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (st != IIF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
@@ -1301,6 +1363,67 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
   for (auto x : ev) cudaEventDestroy(x);
   ctx->launches += (int64_t)kind.size();
   if (e != cudaSuccess) return fail(ctx, IIF_ERR_CUDA, std::string("schedule_profile: ") + cudaGetErrorString(e));
+  return IIF_OK;
+}
+
+int32_t iifb200_schedule_build_dist(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
+                                    const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, int32_t ndeconvs,
+                                    const iif_deconv_op* deconvs, int32_t nxfers, const iif_xfer_op* xfers,
+                                    int32_t* schedule_id_out) {
+  NEED_GRAPH();
+  if (nwaves < 1 || !wave_off || nops < 0 || !ops || nprops < 0 || ndeconvs < 0 || (ndeconvs > 0 && !deconvs) || nxfers < 0 ||
+      (nxfers > 0 && !xfers) || !schedule_id_out)
+    return fail(ctx, IIF_ERR_ARG, "schedule_build_dist: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  Schedule* s = nullptr;
+  int32_t st = build_schedule(ctx, nwaves, wave_off, nops, ops, nprops, props, ndeconvs, deconvs, &s, false, nxfers, xfers);
+  if (st != IIF_OK) { free_schedule(s); return st; }
+  ctx->schedules.push_back(s);
+  *schedule_id_out = (int32_t)ctx->schedules.size() - 1;
+  return IIF_OK;
+}
+
+int32_t iifb200_ipc_export(iifb200_ctx* ctx, int32_t nflags, void* arena_handle64, void* flags_handle64) {
+  NEED_GRAPH();
+  if (nflags < 1 || !arena_handle64 || !flags_handle64) return fail(ctx, IIF_ERR_ARG, "ipc_export: bad arguments");
+  if (!ctx->arena_owned) return fail(ctx, IIF_ERR_STATE, "ipc_export: needs a library-owned arena (set_graph with ext_arena == NULL)");
+  CK(cudaSetDevice(ctx->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  if (ctx->d_flags && ctx->nflags < nflags) { cudaFree(ctx->d_flags); ctx->d_flags = nullptr; }
+  if (!ctx->d_flags) {
+    CK(cudaMalloc(&ctx->d_flags, sizeof(int32_t) * (size_t)nflags));
+    ctx->nflags = nflags;
+  }
+  CK(cudaMemset(ctx->d_flags, 0, sizeof(int32_t) * (size_t)ctx->nflags));
+  if (!ctx->d_epoch) CK(cudaMalloc(&ctx->d_epoch, sizeof(int32_t)));
+  CK(cudaMemset(ctx->d_epoch, 0, sizeof(int32_t)));
+  cudaIpcMemHandle_t ha, hf;
+  CK(cudaIpcGetMemHandle(&ha, ctx->arena));
+  CK(cudaIpcGetMemHandle(&hf, ctx->d_flags));
+  memcpy(arena_handle64, &ha, 64);
+  memcpy(flags_handle64, &hf, 64);
+  return IIF_OK;
+}
+
+int32_t iifb200_ipc_attach(iifb200_ctx* ctx, int32_t world, int32_t rank, const void* arena_handles, const void* flags_handles) {
+  NEED_GRAPH();
+  if (world < 1 || rank < 0 || rank >= world || !arena_handles || !flags_handles) return fail(ctx, IIF_ERR_ARG, "ipc_attach: bad arguments");
+  if (!ctx->d_flags) return fail(ctx, IIF_ERR_STATE, "ipc_attach: call iifb200_ipc_export first");
+  CK(cudaSetDevice(ctx->device));
+  ctx->world = world; ctx->rank = rank;
+  ctx->peer_arena.assign(world, nullptr);
+  ctx->peer_flags.assign(world, nullptr);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { ctx->peer_arena[r] = ctx->arena; ctx->peer_flags[r] = ctx->d_flags; continue; }
+    cudaIpcMemHandle_t ha, hf;
+    memcpy(&ha, (const char*)arena_handles + 64 * r, 64);
+    memcpy(&hf, (const char*)flags_handles + 64 * r, 64);
+    void *pa = nullptr, *pf = nullptr;
+    CK(cudaIpcOpenMemHandle(&pa, ha, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_arena[r] = pa;
+    ctx->peer_flags[r] = (int32_t*)pf;
+  }
   return IIF_OK;
 }
 

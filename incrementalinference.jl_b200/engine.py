@@ -228,6 +228,25 @@ class Engine:
                                                         prop_ops, C.cast(C.byref(sid), A._ip)), "schedule_build")
         return sid.value
 
+    def schedule_build_dist(self, wave_off, sched_ops, nops, prop_ops, nprops, deconv_ops, ndeconvs, xfer_ops, nxfers):
+        wo = np.ascontiguousarray(wave_off, dtype=np.int32)
+        sid = C.c_int32(-1)
+        self._check(self.lib.iifb200_schedule_build_dist(self.ctx, len(wo) - 1, A.as_ip(wo), nops, sched_ops, nprops,
+                                                         prop_ops, ndeconvs, deconv_ops if ndeconvs else None, nxfers,
+                                                         xfer_ops if nxfers else None, C.cast(C.byref(sid), A._ip)),
+                    "schedule_build_dist")
+        return sid.value
+
+    def ipc_export(self, nflags):
+        """-> (arena handle, flags handle): 64-byte CUDA IPC handles as bytes"""
+        ha, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+        self._check(self.lib.iifb200_ipc_export(self.ctx, int(nflags), C.cast(ha, C.c_void_p), C.cast(hf, C.c_void_p)), "ipc_export")
+        return ha.raw, hf.raw
+
+    def ipc_attach(self, world, rank, arena_handles: bytes, flags_handles: bytes):
+        a, f = C.create_string_buffer(arena_handles, len(arena_handles)), C.create_string_buffer(flags_handles, len(flags_handles))
+        self._check(self.lib.iifb200_ipc_attach(self.ctx, world, rank, C.cast(a, C.c_void_p), C.cast(f, C.c_void_p)), "ipc_attach")
+
     def schedule_run(self, sid, first=0, last=-1):
         self._check(self.lib.iifb200_schedule_run(self.ctx, sid, first, last), "schedule_run")
 

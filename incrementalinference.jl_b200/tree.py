@@ -721,8 +721,9 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
     frozen = T.freeze()
     return SolvePlan(T, frozen, props, sched, wave_off, sched_waved, var_slot, nconv[0], len(props), n_msgs,
                      up_last, [opc[i] for i in order], [waves[i] for i in order], [reads[i] for i in order],
-                     [writes[i] for i in order], {s: cid for (cid, _), s in cslot.items()}, deconvs,
-                     [lane[i] for i in order])
+                     [writes[i] for i in order],
+                     {**{s: cid for (cid, _), s in cslot.items()}, **{dc["out_slot"]: dc["clique"] for dc in deconvs}},
+                     deconvs, [lane[i] for i in order])
 
 
 def plan_call_span(plan: SolvePlan) -> int:
@@ -764,7 +765,7 @@ def _joint_up_message(fg, c: TreeClique, inst, slot_of, T, N, deconvs, sched, re
             vt = fg.variables[s1].vartype
             mslot = T.add_slot(vt, N)                                               # newBel = manikde!(sft, pts)
             dummy = T.add_factor(sft, [slot_of(s1), slot_of(s2)], None, 0.0, 5.0)   # tfg dummy factor, :314
-            deconvs.append(dict(factor=dummy, out_slot=mslot, N=N, call_id=-1))    # ids follow the props', see compile_solve
+            deconvs.append(dict(factor=dummy, out_slot=mslot, N=N, call_id=-1, clique=cur[0]))   # ids follow the props'
             sched.append((A.S_DECONV, len(deconvs) - 1, 0))
             reads.append(sorted({slot_of(s1), slot_of(s2)}))
             writes.append([mslot])

@@ -11,7 +11,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n, ret):
+def _worker(rank, world, port, n, ret, uml=False, kind="chain"):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -19,6 +19,7 @@ def _worker(rank, world, port, n, ret):
     import torch.distributed as dist
     import iifb200  # noqa: F401
     import oracle as O
+    from iifb200 import _abi as A
     from iifb200 import compile as CP
     from iifb200 import multigpu as MG
     from iifb200 import tree as TR
@@ -26,64 +27,76 @@ def _worker(rank, world, port, n, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    fg = W.scalar_chain(n, N=32, seed=7)
-    tree = TR.buildTree(fg, W.chain_nd_order(n))
+    if kind == "chain":
+        fg = W.scalar_chain(n, N=32, seed=7)
+        order = W.chain_nd_order(n)
+    else:
+        fg = W.euclid2_grid(rows=4, cols=n // 4, N=24, seed=7, closure_every=2)
+        order = TR.getEliminationOrder(fg, "nd")
+    fg.solverParams.useMsgLikelihoods = uml
+    tree = TR.buildTree(fg, order)
     plan = TR.compile_solve(fg, tree)
-    owner = MG.clique_owner(fg, tree, world)
-    op_rank, transfers = MG.partition_plan(plan, owner, world)
-    my_ops, my_wave_off = MG.rank_schedule(plan, op_rank, rank)
+    owner = MG.clique_owner_balanced(plan, tree, world)
+    sched = MG.dist_schedule(plan, tree, owner, world, rank, nlanes=4, gather="root")
     arena = CP.HostArena(plan.frozen)
     for l, v in fg.variables.items():
         arena.set(plan.var_slot[l], v.val, v.bw, True)
     nv = len(fg.variables)
-    arena.npts[nv:] = 32
+    arena.npts[nv:] = fg.solverParams.N
     arena.flags[nv:] = 1
     sp = CP.solver_params_c(fg.solverParams)
     orc = O.Oracle(plan.frozen, arena, sp)
-    props, ops = CP.make_prop_ops(plan.props), CP.make_sched_ops(my_ops)
-    nw = len(plan.wave_off) - 1
-    comm = sorted({t[0] for t in transfers if rank in (t[2], t[3])})     # as ShardedTreeSolver: own exchange waves only
+    props, deconvs = CP.make_prop_ops(plan.props), CP.make_deconv_ops(plan.deconvs or [])
     slots = plan.frozen["slots"]
+    xf = sched["xfers"]
 
-    def exchange(w):
-        for (ww, s, a, b) in transfers:
-            if ww != w or rank not in (a, b):
-                continue
-            sd = slots[s]
-            pts = torch.from_numpy(arena.pts[sd.pts_off:sd.pts_off + sd.cap * sd.dim])
-            bw = torch.from_numpy(arena.bw[s * 4:(s + 1) * 4])
-            for t in (pts, bw):
-                if rank == a:
-                    dist.send(t, b)
-                else:
-                    dist.recv(t, a)
+    def view(s):      # one message = the slot's points, bandwidths, ipc, point count and flags (what iif_push_kernel writes)
+        sd = slots[s]
+        return [arena.pts[sd.pts_off:sd.pts_off + sd.cap * sd.dim], arena.bw[s * 4:(s + 1) * 4], arena.ipc[s * 4:(s + 1) * 4]]
 
-    prev = 0
-    for w in comm:
-        if w > prev:
-            orc.schedule_run(my_wave_off, ops, props, prev, w)
-        exchange(w)
-        prev = w
-    orc.schedule_run(my_wave_off, ops, props, prev, nw)
-    # gather the posteriors of the variables whose frontal clique this rank owns
-    mine = {l: arena.get(plan.var_slot[l])[0] for l in fg.variables if owner[tree.frontal_of[l]] == rank}
-    out = [None] * world
-    dist.all_gather_object(out, mine)
+    pending, received = [], set()
+    nw = len(sched["wave_off"]) - 1
+    for w in range(nw):
+        ops_w = sched["ops"][sched["wave_off"][w]:sched["wave_off"][w + 1]]
+        for (k, a, _) in ops_w:                       # WAIT nodes run in front of the segment's kernels
+            if k == A.S_WAIT:
+                s, src, m = xf[a]
+                if m in received:                     # flags are level-triggered: later waits on a raised flag pass
+                    continue
+                received.add(m)
+                parts = view(s)
+                buf = torch.zeros(sum(len(x) for x in parts) + 2, dtype=torch.float64)
+                dist.recv(buf, src, tag=m)
+                o = 0
+                for x in parts:
+                    x[:] = buf[o:o + len(x)].numpy()
+                    o += len(x)
+                arena.npts[s], arena.flags[s] = int(buf[o]), int(buf[o + 1])
+        comp = [(k, a, b) for (k, a, b) in ops_w if k in (A.S_PROPAGATE, A.S_COPY, A.S_DECONV)]
+        if comp:
+            orc.schedule_run([0, len(comp)], CP.make_sched_ops(comp), props, deconvs=deconvs)
+        for (k, a, _) in ops_w:                       # PUSH nodes run behind them
+            if k == A.S_PUSH:
+                s, dst, m = xf[a]
+                parts = view(s)
+                buf = torch.from_numpy(np.concatenate(parts + [np.array([arena.npts[s], arena.flags[s]], dtype=np.float64)]))
+                pending.append(dist.isend(buf, dst, tag=m))
+    for h in pending:
+        h.wait()
     if rank == 0:
-        merged = {}
-        for d in out:
-            merged.update(d)
-        # single-process reference on the same plan
+        # rank 0 holds the whole solution after the gather wave; single-process reference on the same plan
         ar1 = CP.HostArena(plan.frozen)
         for l, v in fg.variables.items():
             ar1.set(plan.var_slot[l], v.val, v.bw, True)
         o1 = O.Oracle(plan.frozen, ar1, sp)
-        o1.schedule_run(plan.wave_off, CP.make_sched_ops(plan.sched_waved), props)
-        ok = all(np.array_equal(merged[l], ar1.get(plan.var_slot[l])[0]) for l in fg.variables)
+        o1.schedule_run(plan.wave_off, CP.make_sched_ops(plan.sched_waved), props, deconvs=deconvs)
+        ok = all(np.array_equal(arena.get(plan.var_slot[l])[0], ar1.get(plan.var_slot[l])[0]) and
+                 np.array_equal(arena.get(plan.var_slot[l])[1], ar1.get(plan.var_slot[l])[1]) for l in fg.variables)
         ret["ok"] = bool(ok)
-        ret["ntransfers"] = len(transfers)
-        ret["nvars"] = len(merged)
-        ret["split"] = [sum(1 for r in op_rank if r == k) for k in range(world)]
+        ret["nmsgs"] = len(sched["msgs"])
+        ret["nvars"] = nv
+        ret["split"] = [sum(1 for r in sched["op_rank"] if r == k) for k in range(world)]
+        ret["ndeconv"] = len(plan.deconvs or [])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -97,7 +110,7 @@ def test_sharded_solve_matches_single_process(built, n):
         mp.spawn(_worker, args=(2, port, n, ret), nprocs=2, join=True)
         assert ret["ok"], "sharded solve differs from the single-process solve"
         assert ret["nvars"] == n
-        assert 0 < ret["ntransfers"] <= 16      # only the cut's separator messages cross ranks
+        assert 0 < ret["nmsgs"] <= 16           # only the cut's separator messages cross ranks
         assert min(ret["split"]) > 0.3 * max(ret["split"])   # both ranks carry a real share
 
 
@@ -111,6 +124,57 @@ def test_sharded_solve_world4_matches_single_process(built):
         mp.spawn(_worker, args=(4, port, n, ret), nprocs=4, join=True)
         assert ret["ok"], "sharded solve differs from the single-process solve"
         assert ret["nvars"] == n and min(ret["split"]) > 0
+
+
+@pytest.mark.parametrize("uml,kind,n", [(True, "chain", 40), (False, "grid", 32), (True, "grid", 32)])
+def test_sharded_solve_with_differential_messages_and_grid(built, uml, kind, n):
+    """useMsgLikelihoods = true sharded (the differentials' measurement beliefs travel too) and a grid whose separators
+    hold several variables: rank 0's gathered solution equals the single-process solve bit for bit"""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() + 13 * n + 3 * uml) % 1000
+    with mp.Manager() as man:
+        ret = man.dict()
+        mp.spawn(_worker, args=(2, port, n, ret, uml, kind), nprocs=2, join=True)
+        assert ret["ok"], "sharded solve differs from the single-process solve"
+        assert ret["nmsgs"] > 0 and (ret["ndeconv"] > 0) == uml
+
+
+def test_dist_schedule_properties():
+    """messages: numbered alike on every rank, pushed from the producer's wave, awaited in every reader's wave"""
+    import iifb200  # noqa: F401
+    from iifb200 import _abi as A
+    from iifb200 import multigpu as MG
+    from iifb200 import tree as TR
+    from iifb200 import workloads as W
+    fg = W.scalar_chain(96, N=16)
+    tree = TR.buildTree(fg, W.chain_nd_order(96))
+    plan = TR.compile_solve(fg, tree)
+    for world in (2, 4, 8):
+        owner = MG.clique_owner_balanced(plan, tree, world)
+        load = [0.0] * world
+        for (k, a, _), c in zip(plan.sched_waved, plan.op_clique):
+            if k == A.S_PROPAGATE:
+                load[owner[c]] += len(plan.props[a]["factors"]) + 1
+        assert min(load) > 0.6 * max(load), load                       # balanced by convolution weight
+        sch = [MG.dist_schedule(plan, tree, owner, world, r, 4, "root") for r in range(world)]
+        assert all(s["msgs"] == sch[0]["msgs"] and s["nflags"] == sch[0]["nflags"] for s in sch)
+        pushes, waits = {}, {}
+        for r, s in enumerate(sch):
+            assert s["wave_off"][-1] == len(s["ops"]) == len(s["lanes"])
+            for w in range(len(s["wave_off"]) - 1):
+                for (k, a, _) in s["ops"][s["wave_off"][w]:s["wave_off"][w + 1]]:
+                    if k == A.S_PUSH:
+                        slot, dst, m = s["xfers"][a]
+                        assert m not in pushes and dst != r
+                        pushes[m] = (r, dst, w)
+                    elif k == A.S_WAIT:
+                        slot, src, m = s["xfers"][a]
+                        waits.setdefault(m, []).append((r, src, w))
+        assert set(pushes) == set(waits) == set(range(sch[0]["nflags"]))
+        for m, (src, dst, wp) in pushes.items():
+            for (r, s_, ww) in waits[m]:
+                assert r == dst and s_ == src and wp <= ww           # produced no later than it is awaited
+        assert sum(s["my_conv"] for s in sch) == plan.n_conv
 
 
 def test_partition_properties():
