@@ -115,6 +115,13 @@ typedef struct {
   int32_t slot[IIF_MAX_ARITY]; /* belief slot of each variable, in factor variable order */
   int32_t nmh;                 /* 0: no multihypo; else == arity */
   int32_t partial_mask;        /* 0: full; else bit c set: factor informs coordinate c */
+  int32_t solver;              /* per-sample solve of a relative factor (_solveLambdaNumeric, NumericalCalculations.jl:49-133):
+                                  0 = closed-form root where the residual has a unique one (what the optimiser converges
+                                  to), Nelder-Mead for EuclidDistance in more than one dimension (a ring of roots: the
+                                  result IS the optimiser's path); 1 = always Nelder-Mead over the solve-for point's
+                                  coordinates, restating Optim.NelderMead as the reference configures it (adaptive
+                                  parameters, affine initial simplex, g_abstol 1e-8, 1000 iterations) */
+  int32_t _pad;
   double mh[IIF_MAX_ARITY];    /* parseusermultihypo output (FactorGraph.jl:639-654): 0.0 = certain */
   double nullhypo;             /* CCW.nullhypo   FactorOperationalMemory.jl:51 */
   double inflation;            /* CCW.inflation  FactorOperationalMemory.jl:53 (default 5.0) */

@@ -37,7 +37,8 @@ class SlotDesc(C.Structure):
 class FactorDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("arity", C.c_int32), ("zdim", C.c_int32),
                 ("dist", C.c_int32), ("slot", C.c_int32 * IIF_MAX_ARITY), ("nmh", C.c_int32),
-                ("partial_mask", C.c_int32), ("mh", C.c_double * IIF_MAX_ARITY),
+                ("partial_mask", C.c_int32), ("solver", C.c_int32), ("_pad", C.c_int32),
+                ("mh", C.c_double * IIF_MAX_ARITY),
                 ("nullhypo", C.c_double), ("inflation", C.c_double)]
 
 

@@ -68,6 +68,7 @@ class Tables:
                 partial_mask |= 1 << (int(c) - 1)
         self.factors.append(dict(kind=fnc.kind, arity=len(slots), zdim=zdim, dist=d, slot=list(slots),
                                  nmh=0 if mh is None else len(mh), partial_mask=partial_mask,
+                                 solver=int(bool(getattr(fnc, "numeric", False))),
                                  mh=[] if mh is None else list(mh), nullhypo=float(nullhypo),
                                  inflation=float(inflation)))
         return len(self.factors) - 1
@@ -90,7 +91,7 @@ class Tables:
             fd.kind, fd.arity, fd.zdim, fd.dist = f["kind"], f["arity"], f["zdim"], f["dist"]
             for k, s in enumerate(f["slot"]):
                 fd.slot[k] = s
-            fd.nmh, fd.partial_mask = f["nmh"], f["partial_mask"]
+            fd.nmh, fd.partial_mask, fd.solver = f["nmh"], f["partial_mask"], f.get("solver", 0)
             for k, p in enumerate(f["mh"]):
                 fd.mh[k] = p
             fd.nullhypo, fd.inflation = f["nullhypo"], f["inflation"]

@@ -314,6 +314,111 @@ __device__ __forceinline__ void solve_binary(int kind, int d, int32_t cm, const 
   }
 }
 
+// sum(res.^2) of a binary relative factor with the solve-for point at x (CalcFactorNormSq, NumericalCalculations.jl:68-72);
+// residuals as in the oracle's iifo_residual (src/Factors/*.jl)
+__device__ __noinline__ double cost_binary(int kind, int d, int32_t cm, const double* z, const double* x, const double* other,
+                                           bool sf_second) {
+  const double* p = sf_second ? other : x;
+  const double* q = sf_second ? x : other;
+  double s = 0.0;
+  if (kind == IIF_F_LINEAR_RELATIVE) {
+    for (int c = 0; c < d; ++c) { const double r = __dsub_rn(z[c], __dsub_rn(q[c], p[c])); s = __dadd_rn(s, __dmul_rn(r, r)); }
+  } else if (kind == IIF_F_CIRCULAR_CIRCULAR) {
+    for (int c = 0; c < d; ++c) {
+      const double r = mdiff(madd(p[c], z[c], is_circ(cm, c)), q[c], is_circ(cm, c));
+      s = __dadd_rn(s, __dmul_rn(r, r));
+    }
+  } else if (kind == IIF_F_EUCLID_DISTANCE) {
+    double n2 = 0.0;
+    for (int c = 0; c < d; ++c) { const double e = __dsub_rn(q[c], p[c]); n2 = __dadd_rn(n2, __dmul_rn(e, e)); }
+    const double r = __dsub_rn(z[0], sqrt(n2));
+    s = __dmul_rn(r, r);
+  } else {  // IIF_F_SE2_RELATIVE
+    double sn, cs;
+    sincos(p[2], &sn, &cs);
+    const double r0 = __dsub_rn(__dsub_rn(__dadd_rn(p[0], __dmul_rn(cs, z[0])), __dmul_rn(sn, z[1])), q[0]);
+    const double r1 = __dsub_rn(__dadd_rn(__dadd_rn(p[1], __dmul_rn(sn, z[0])), __dmul_rn(cs, z[1])), q[1]);
+    const double r2 = wrap_pi(wrap_pi(p[2] + z[2]) - q[2]);
+    s = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+  }
+  return s;
+}
+
+// (explicit _rn arithmetic: no FMA contraction, so the simplex follows the oracle's path bit for bit)
+// Optim.NelderMead as _solveLambdaNumeric configures it (NumericalCalculations.jl:49-72, :90-133): AdaptiveParameters,
+// AffineSimplexer, sqrt(var(f_simplex) n/(n+1)) < 1e-8, <= 1000 iterations, result = better of best vertex and centroid
+// of the n best.  Same steps as the oracle's nelder_mead_binary.  One thread per particle; a rare path (EuclidDistance in
+// more than one dimension, or factors that ask for the numeric solve), so the simplex lives in local memory.
+__device__ __noinline__ void nelder_mead_binary(int kind, int d, int32_t cm, const double* z, const double* other,
+                                                bool sf_second, const double* x0, double* out) {
+  const int n = d, m = d + 1;
+  const double alpha = 1.0, beta = 1.0 + 2.0 / n, gamma = 0.75 - 1.0 / (2.0 * n), delta = 1.0 - 1.0 / n;
+  double S[IIF_MAX_DIM + 1][IIF_MAX_DIM], f[IIF_MAX_DIM + 1];
+  int ord[IIF_MAX_DIM + 1];
+  for (int i = 0; i < m; ++i) {
+    for (int c = 0; c < n; ++c) S[i][c] = x0[c];
+    if (i > 0) S[i][i - 1] = __dadd_rn(__dmul_rn(1.5, x0[i - 1]), 0.025);
+    f[i] = cost_binary(kind, d, cm, z, S[i], other, sf_second);
+  }
+  double cen[IIF_MAX_DIM], xr[IIF_MAX_DIM], xt[IIF_MAX_DIM];
+  for (int it = 0; it < 1000; ++it) {
+    for (int i = 0; i < m; ++i) ord[i] = i;
+    for (int i = 1; i < m; ++i) {
+      const int k = ord[i];
+      int j = i - 1;
+      while (j >= 0 && f[ord[j]] > f[k]) { ord[j + 1] = ord[j]; --j; }
+      ord[j + 1] = k;
+    }
+    const int lo = ord[0], hi = ord[m - 1], sh = ord[m - 2];
+    for (int c = 0; c < n; ++c) {
+      double s = 0;
+      for (int i = 0; i < m - 1; ++i) s += S[ord[i]][c];
+      cen[c] = s / n;
+    }
+    for (int c = 0; c < n; ++c) xr[c] = __dadd_rn(cen[c], __dmul_rn(alpha, __dsub_rn(cen[c], S[hi][c])));
+    const double fr = cost_binary(kind, d, cm, z, xr, other, sf_second);
+    bool shrink = false;
+    if (fr < f[lo]) {
+      for (int c = 0; c < n; ++c) xt[c] = __dadd_rn(cen[c], __dmul_rn(beta, __dsub_rn(xr[c], cen[c])));
+      const double fe = cost_binary(kind, d, cm, z, xt, other, sf_second);
+      if (fe < fr) { for (int c = 0; c < n; ++c) S[hi][c] = xt[c]; f[hi] = fe; }
+      else { for (int c = 0; c < n; ++c) S[hi][c] = xr[c]; f[hi] = fr; }
+    } else if (fr < f[sh]) {
+      for (int c = 0; c < n; ++c) S[hi][c] = xr[c];
+      f[hi] = fr;
+    } else if (fr < f[hi]) {
+      for (int c = 0; c < n; ++c) xt[c] = __dadd_rn(cen[c], __dmul_rn(gamma, __dsub_rn(xr[c], cen[c])));
+      const double fc = cost_binary(kind, d, cm, z, xt, other, sf_second);
+      if (fc <= fr) { for (int c = 0; c < n; ++c) S[hi][c] = xt[c]; f[hi] = fc; } else shrink = true;
+    } else {
+      for (int c = 0; c < n; ++c) xt[c] = __dsub_rn(cen[c], __dmul_rn(gamma, __dsub_rn(xr[c], cen[c])));
+      const double fc = cost_binary(kind, d, cm, z, xt, other, sf_second);
+      if (fc < f[hi]) { for (int c = 0; c < n; ++c) S[hi][c] = xt[c]; f[hi] = fc; } else shrink = true;
+    }
+    if (shrink)
+      for (int i = 1; i < m; ++i) {
+        const int k = ord[i];
+        for (int c = 0; c < n; ++c) S[k][c] = __dadd_rn(S[lo][c], __dmul_rn(delta, __dsub_rn(S[k][c], S[lo][c])));
+        f[k] = cost_binary(kind, d, cm, z, S[k], other, sf_second);
+      }
+    double mean = 0, var = 0;
+    for (int i = 0; i < m; ++i) mean += f[i];
+    mean /= m;
+    for (int i = 0; i < m; ++i) { const double e = __dsub_rn(f[i], mean); var = __dadd_rn(var, __dmul_rn(e, e)); }
+    if (sqrt(var / m) < 1e-8) break;
+  }
+  int best = 0, worst = 0;
+  for (int i = 1; i < m; ++i) { if (f[i] < f[best]) best = i; if (f[i] > f[worst]) worst = i; }
+  for (int c = 0; c < n; ++c) {
+    double s = 0;
+    for (int i = 0; i < m; ++i) if (i != worst) s += S[i][c];
+    cen[c] = s / n;
+  }
+  const double fcen = cost_binary(kind, d, cm, z, cen, other, sf_second);
+  const double* r = fcen < f[best] ? cen : S[best];
+  for (int c = 0; c < n; ++c) out[c] = is_circ(cm, c) ? wrap_pi(r[c]) : r[c];
+}
+
 __device__ __forceinline__ bool is_prior_kind(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR ||
          k == IIF_F_MANIFOLD_PRIOR;
@@ -481,7 +586,10 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
             add_entropy(hyp, pmask, sp, cyc);
             if (ok) {
               double r[IIF_MAX_DIM];
-              solve_binary(f.kind, d, cm, z, o, sf_second, my, r);
+              // islen1 (1-D: BFGS in the reference) keeps the closed form; in several dimensions EuclidDistance (a ring of
+              // roots) and factors that ask for it run the restated Nelder-Mead from the inflated start
+              if (d > 1 && (f.solver == 1 || f.kind == IIF_F_EUCLID_DISTANCE)) nelder_mead_binary(f.kind, d, cm, z, o, sf_second, my, r);
+              else solve_binary(f.kind, d, cm, z, o, sf_second, my, r);
               bool bad = false;
               for (int c = 0; c < d; ++c) bad |= isnan(r[c]);
               if (bad) nnan++;  // NumericalCalculations.jl:348-351: particle left unchanged

@@ -446,6 +446,7 @@ class B3Driver:
             for k, (f, D, sl, ks, sf) in enumerate(facs):
                 C_ = factors[k]
                 C_.kind, C_.arity, C_.zdim, C_.dist, C_.nmh, C_.partial_mask = f.kind, f.arity, f.zdim, k, f.nmh, f.partial_mask
+                C_.solver = f.solver
                 C_.nullhypo, C_.inflation = f.nullhypo, f.inflation
                 for i, s in enumerate(sl):
                     C_.slot[i] = s

@@ -34,7 +34,7 @@ struct SlotDesc;   dim::Int32; circ_mask::Int32; cap::Int32; pts_off::Int32; end
 struct DistDesc;   kind::Int32; dim::Int32; ncomp::Int32; comp_kind::Int32; slot::Int32; poff::Int32; end
 struct FactorDesc
   kind::Int32; arity::Int32; zdim::Int32; dist::Int32
-  slot::NTuple{6,Int32}; nmh::Int32; partial_mask::Int32
+  slot::NTuple{6,Int32}; nmh::Int32; partial_mask::Int32; solver::Int32; _pad::Int32
   mh::NTuple{6,Float64}; nullhypo::Float64; inflation::Float64
 end
 struct SolverParamsC; spreadNH::Float64; nullSurplusAdd::Float64; inflateCycles::Int32; gibbsNiter::Int32; seed::UInt64; end
@@ -213,6 +213,7 @@ function _lower_factors(dfg::AbstractDFG, factors::AbstractVector, slotof::Dict{
     mh = ccw.hyporecipe.hypotheses === nothing ? Float64[] : Vector{Float64}(probs(ccw.hyporecipe.hypotheses))
     push!(fdescs, FactorDesc(factorkind(fnc), Int32(length(vo)), dists[di + 1].dim, di,
                              _padtuple([slotof[l] for l in vo], MAX_ARITY, Int32), Int32(length(mh)), pmask,
+                             Int32(get(ENV, "IIFB200_NUMERIC_SOLVE", "0") == "1"), Int32(0),
                              _padtuple(mh, MAX_ARITY, Float64), ccw.nullhypo, ccw.inflation))
   end
   return dists, dparams, fdescs, extra

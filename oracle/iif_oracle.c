@@ -329,6 +329,93 @@ static void solve_binary(int kind, int d, int32_t cm, const double* z, const dou
   }
 }
 
+/* sum(res.^2) of a binary relative factor with the solve-for point at x (CalcFactorNormSq, NumericalCalculations.jl:68-72) */
+static double cost_binary(int kind, int d, int32_t cm, int zdim, const double* z, const double* x, const double* other,
+                          int sf_second) {
+  double xx[2 * IIF_MAX_DIM], res[IIF_MAX_DIM] = {0};
+  for (int c = 0; c < d; ++c) { xx[c] = sf_second ? other[c] : x[c]; xx[d + c] = sf_second ? x[c] : other[c]; }
+  iifo_residual(kind, d, cm, zdim, z, 2, xx, res);
+  double s = 0;
+  for (int c = 0; c < zdim; ++c) s += res[c] * res[c];
+  return s;
+}
+
+/* Optim.NelderMead as _solveLambdaNumeric configures it (NumericalCalculations.jl:49-72, :90-133): default
+ * AdaptiveParameters (alpha 1, beta 1 + 2/n, gamma 0.75 - 1/2n, delta 1 - 1/n), AffineSimplexer (vertex j+1 =
+ * x0 with coordinate j -> 1.5 x0_j + 0.025), convergence sqrt(var(f_simplex) n/(n+1)) < g_abstol = 1e-8, at most 1000
+ * iterations; the result is the better of the best vertex and the centroid of the n best.  Optim.jl is not vendored:
+ * restated from its published algorithm (PARITY UNPINNED against Julia; GPU and oracle follow the same steps). */
+static void nelder_mead_binary(int kind, int d, int32_t cm, int zdim, const double* z, const double* other,
+                               int sf_second, const double* x0, double* out) {
+  const int n = d, m = d + 1;
+  const double alpha = 1.0, beta = 1.0 + 2.0 / n, gamma = 0.75 - 1.0 / (2.0 * n), delta = 1.0 - 1.0 / n;
+  double S[IIF_MAX_DIM + 1][IIF_MAX_DIM], f[IIF_MAX_DIM + 1];
+  int ord[IIF_MAX_DIM + 1];
+  for (int i = 0; i < m; ++i) {
+    for (int c = 0; c < n; ++c) S[i][c] = x0[c];
+    if (i > 0) S[i][i - 1] = 1.5 * x0[i - 1] + 0.025;
+    f[i] = cost_binary(kind, d, cm, zdim, z, S[i], other, sf_second);
+  }
+  double cen[IIF_MAX_DIM], xr[IIF_MAX_DIM], xe[IIF_MAX_DIM], xc[IIF_MAX_DIM];
+  for (int it = 0; it < 1000; ++it) {
+    for (int i = 0; i < m; ++i) ord[i] = i;                     /* sortperm (stable insertion sort) */
+    for (int i = 1; i < m; ++i) {
+      int k = ord[i], j = i - 1;
+      while (j >= 0 && f[ord[j]] > f[k]) { ord[j + 1] = ord[j]; --j; }
+      ord[j + 1] = k;
+    }
+    const int lo = ord[0], hi = ord[m - 1], sh = ord[m - 2];
+    for (int c = 0; c < n; ++c) {
+      double s = 0;
+      for (int i = 0; i < m - 1; ++i) s += S[ord[i]][c];
+      cen[c] = s / n;
+    }
+    for (int c = 0; c < n; ++c) xr[c] = cen[c] + alpha * (cen[c] - S[hi][c]);
+    const double fr = cost_binary(kind, d, cm, zdim, z, xr, other, sf_second);
+    int shrink = 0;
+    if (fr < f[lo]) {
+      for (int c = 0; c < n; ++c) xe[c] = cen[c] + beta * (xr[c] - cen[c]);
+      const double fe = cost_binary(kind, d, cm, zdim, z, xe, other, sf_second);
+      if (fe < fr) { for (int c = 0; c < n; ++c) S[hi][c] = xe[c]; f[hi] = fe; }
+      else { for (int c = 0; c < n; ++c) S[hi][c] = xr[c]; f[hi] = fr; }
+    } else if (fr < f[sh]) {
+      for (int c = 0; c < n; ++c) S[hi][c] = xr[c];
+      f[hi] = fr;
+    } else if (fr < f[hi]) {                                   /* outside contraction */
+      for (int c = 0; c < n; ++c) xc[c] = cen[c] + gamma * (xr[c] - cen[c]);
+      const double fc = cost_binary(kind, d, cm, zdim, z, xc, other, sf_second);
+      if (fc <= fr) { for (int c = 0; c < n; ++c) S[hi][c] = xc[c]; f[hi] = fc; } else shrink = 1;
+    } else {                                                   /* inside contraction */
+      for (int c = 0; c < n; ++c) xc[c] = cen[c] - gamma * (xr[c] - cen[c]);
+      const double fc = cost_binary(kind, d, cm, zdim, z, xc, other, sf_second);
+      if (fc < f[hi]) { for (int c = 0; c < n; ++c) S[hi][c] = xc[c]; f[hi] = fc; } else shrink = 1;
+    }
+    if (shrink)
+      for (int i = 1; i < m; ++i) {
+        const int k = ord[i];
+        for (int c = 0; c < n; ++c) S[k][c] = S[lo][c] + delta * (S[k][c] - S[lo][c]);
+        f[k] = cost_binary(kind, d, cm, zdim, z, S[k], other, sf_second);
+      }
+    double mean = 0, var = 0;
+    for (int i = 0; i < m; ++i) mean += f[i];
+    mean /= m;
+    for (int i = 0; i < m; ++i) var += (f[i] - mean) * (f[i] - mean);
+    if (sqrt(var / m) < 1e-8) break;                          /* sqrt(var_corrected * n / (n + 1)) */
+  }
+  int best = 0;
+  for (int i = 1; i < m; ++i) if (f[i] < f[best]) best = i;
+  int worst = 0;
+  for (int i = 1; i < m; ++i) if (f[i] > f[worst]) worst = i;
+  for (int c = 0; c < n; ++c) {
+    double s = 0;
+    for (int i = 0; i < m; ++i) if (i != worst) s += S[i][c];
+    cen[c] = s / n;
+  }
+  const double fcen = cost_binary(kind, d, cm, zdim, z, cen, other, sf_second);
+  const double* r = fcen < f[best] ? cen : S[best];
+  for (int c = 0; c < n; ++c) out[c] = is_circ(cm, c) ? wrap_pi(r[c]) : r[c];     /* exp(M, eps, hat(minimizer)) */
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* Measurement sampling — sampleFactor! SolverUtilities.jl:50-76, getSample                */
 /* ManifoldSampling.jl:121-145, Mixture.jl:114-155, MsgPrior.jl:21-30, Circular.jl:30-33,62-68 */
@@ -798,8 +885,14 @@ int32_t iifo_conv(const iifo_graph* g, const iif_conv_op* op, const double* meas
               if (m >= lo) m = lo - 1;
             }
             double r[IIF_MAX_DIM];
-            solve_binary(f->kind, d, cm, z + n * IIF_MAX_DIM, g->pts + So->pts_off + m * So->dim,
-                         sf_second, dest + n * d, r);
+            /* islen1 (1-D: BFGS in the reference) keeps the closed form; in several dimensions EuclidDistance (a ring
+             * of roots) and factors flagged solver = 1 run the restated Nelder-Mead from the inflated start */
+            if (d > 1 && (f->solver == 1 || f->kind == IIF_F_EUCLID_DISTANCE))
+              nelder_mead_binary(f->kind, d, cm, f->zdim, z + n * IIF_MAX_DIM, g->pts + So->pts_off + m * So->dim,
+                                 sf_second, dest + n * d, r);
+            else
+              solve_binary(f->kind, d, cm, z + n * IIF_MAX_DIM, g->pts + So->pts_off + m * So->dim,
+                           sf_second, dest + n * d, r);
             int bad = 0;
             for (int c = 0; c < d; ++c) bad |= isnan(r[c]);
             if (bad) { nnan++; continue; }                   /* NumericalCalculations.jl:348-351 */

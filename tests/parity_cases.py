@@ -211,6 +211,30 @@ def conv_cases():
                                    dict(factor=fpt, sfidx=1, N=N, call_id=114), dict(factor=fpa, sfidx=1, N=N, call_id=115)], None
 
 
+    # 14. numeric per-sample solve: Nelder-Mead restated from Optim as _solveLambdaNumeric configures it —
+    # EuclidDistance in 2-D and 3-D (ring / sphere of roots: the result is the optimiser's path from the inflated
+    # start), and unique-root factors forced through the numeric solve (solver = 1)
+    P = Problem()
+    p0 = P.slot(G.Position(2), N, R.normal(0, 1, (N, 2)))
+    p1 = P.slot(G.Position(2), N, R.normal(0, 1, (N, 2)) + [5.0, -3.0])
+    q0 = P.slot(G.Position(3), N, R.normal(0, 1, (N, 3)))
+    q1 = P.slot(G.Position(3), N, R.normal(0, 1, (N, 3)) + [2.0, 2.0, -4.0])
+    fd2 = P.factor(G.EuclidDistance(G.Normal(6.0, 0.2)), [p0, p1])
+    fd3 = P.factor(G.EuclidDistance(G.Normal(5.0, 0.1)), [q0, q1])
+    lr = G.LinearRelative(G.MvNormal([5.0, -3.0], np.diag([0.04, 0.09])))
+    lr.numeric = True
+    fnm = P.factor(lr, [p0, p1])
+    se = G.SpecialEuclidean2
+    e0 = P.slot(se, N, np.column_stack([R.normal(0, 0.5, N), R.normal(0, 0.5, N), wrap(R.normal(0.3, 0.2, N))]))
+    e1 = P.slot(se, N, np.column_stack([R.normal(1, 0.5, N), R.normal(2, 0.5, N), wrap(R.normal(1.0, 0.2, N))]))
+    mf = G.ManifoldFactor(se, G.MvNormal([1.0, 2.0, np.pi / 4], np.diag([0.01, 0.01, 0.01])))
+    mf.numeric = True
+    fse = P.factor(mf, [e0, e1])
+    yield "numeric_solve", P.freeze(), [dict(factor=fd2, sfidx=2, N=N, call_id=120), dict(factor=fd2, sfidx=1, N=N, call_id=121),
+                                        dict(factor=fd3, sfidx=2, N=N, call_id=122), dict(factor=fnm, sfidx=2, N=N, call_id=123),
+                                        dict(factor=fnm, sfidx=1, N=N, call_id=124), dict(factor=fse, sfidx=2, N=N, call_id=125)], None
+
+
 def wrap(a):
     return (np.asarray(a) + np.pi) % (2 * np.pi) - np.pi
 

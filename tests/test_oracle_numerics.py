@@ -573,6 +573,44 @@ def test_special_orthogonal2_testSpecialOrthogonalMani():
     assert np.cos(t1).mean() < -0.9                                   # x1 sits at +-pi (the seam)
 
 
+def test_numeric_solver_nelder_mead():
+    """SURVEY a10b (_solveLambdaNumeric, NumericalCalculations.jl:49-133): the restated Optim.NelderMead.  Unique-root
+    factors forced through it land on the analytic root within the optimiser's own accuracy (its stopping rule
+    sqrt(var f) < 1e-8 leaves residuals of ~1e-4, which is why the reference's tests use loose bands); EuclidDistance
+    in 2-D / 3-D lands ON the ring / sphere z = |x2 - x1| at the point the simplex walks to from the inflated start
+    (the radial projection is only its 1-D special case)."""
+    name, P, specs, _ = [c for c in PC.conv_cases() if c[0] == "numeric_solve"][0]
+    orc = P.oracle()
+    ops = CP.make_conv_ops(specs)
+    fz = P.frozen
+    res = [orc.conv(ops[k]) for k in range(len(specs))]
+    # EuclidDistance: every proposal sits on the ring around its partner particle (labels all 1 => partner n)
+    for k in (0, 1, 2):
+        f = fz["factors"][specs[k]["factor"]]
+        d = fz["slots"][f.slot[0]].dim
+        other = f.slot[0] if specs[k]["sfidx"] == 2 else f.slot[1]
+        po = P.arena.get(other)[0]
+        dist = np.linalg.norm(res[k][0] - po, axis=1)
+        mu = 6.0 if d == 2 else 5.0
+        assert np.all(np.abs(dist - mu) < 5 * (0.2 if d == 2 else 0.1) + 1e-2), k        # z ~ Normal(mu, sigma)
+        assert dist.std() > 0.01 and res[k][4] == 0
+    # unique roots: the same convolutions with the closed form (solver = 0) agree within Nelder-Mead's accuracy
+    P2 = PC.Problem()
+    import copy
+    T2 = copy.deepcopy(P.T)
+    for f in T2.factors:
+        f["solver"] = 0
+    fz2 = T2.freeze()
+    orc2 = O.Oracle(fz2, P.arena.copy(), P.sp_c)
+    for k in (3, 4, 5):
+        ref = orc2.conv(ops[k])[0]
+        dlt = np.abs(res[k][0] - ref)
+        if k == 5:
+            dlt[:, 2] = np.minimum(dlt[:, 2], 2 * np.pi - dlt[:, 2])
+        assert dlt.max() < 2e-3 and dlt.max() > 0, (k, dlt.max())                          # close, but not the closed form
+    del P2
+
+
 def test_four_equal_peaks_testMultiHypo3Door():
     """test/testMultiHypo3Door.jl:40-99: x0 sees one of four doors (landmarks at 0, 10, 20, 40, sigma 0.01) through a
     5-ary LinearRelative(Normal(0, 0.25)) with multihypo = [1, 1/4, 1/4, 1/4, 1/4], N = 200: the proposal has four
