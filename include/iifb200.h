@@ -88,7 +88,10 @@ enum iif_dist_kind {
   IIF_D_MVNORMAL = 2, /* params: [mu(dim), L(dim*dim) row-major lower Cholesky factor]   */
   IIF_D_MIXTURE = 3,  /* params: [w(ncomp)] then ncomp component blocks of comp_kind     */
   IIF_D_KDE = 4,      /* ManifoldKernelDensity held in belief slot `slot` (MsgPrior)     */
-  IIF_D_UNIFORM = 5   /* params: [a, b]                                                  */
+  IIF_D_UNIFORM = 5,  /* params: [a, b]                                                  */
+  IIF_D_SAMPLES = 6   /* ANY SamplableBelief the host can draw from (sampleFactor! is `rand(Z)` per sample,
+                         SolverUtilities.jl:50-76; Rayleigh, Gamma, user types ...): params hold ncomp samples of dim values,
+                         row-major, drawn by the host; the device resamples the table uniformly with replacement */
 };
 
 typedef struct {

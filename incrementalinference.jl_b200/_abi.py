@@ -19,7 +19,7 @@ F_PRIOR, F_LINEAR_RELATIVE, F_PRIOR_CIRCULAR, F_CIRCULAR_CIRCULAR = 1, 2, 3, 4
 F_EUCLID_DISTANCE, F_MSG_PRIOR, F_PARTIAL_PRIOR = 5, 6, 7
 F_MANIFOLD_PRIOR, F_SE2_RELATIVE = 8, 9
 # iif_dist_kind
-D_NORMAL, D_MVNORMAL, D_MIXTURE, D_KDE, D_UNIFORM = 1, 2, 3, 4, 5
+D_NORMAL, D_MVNORMAL, D_MIXTURE, D_KDE, D_UNIFORM, D_SAMPLES = 1, 2, 3, 4, 5, 6
 # iif_sched_kind
 S_PROPAGATE, S_COPY, S_DECONV, S_PUSH, S_WAIT = 1, 2, 3, 4, 5
 

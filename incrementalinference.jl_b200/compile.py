@@ -51,6 +51,9 @@ class Tables:
             self.dists.append((A.D_MIXTURE, dims.pop(), len(blocks), kinds.pop(), -1, poff))
         elif isinstance(Z, G.SlotRef):
             self.dists.append((A.D_KDE, Z.dim, 0, 0, Z.slot, poff))
+        elif isinstance(Z, G.SampledBelief):
+            self.dparams += list(Z.samples.reshape(-1))
+            self.dists.append((A.D_SAMPLES, Z.dim, Z.samples.shape[0], 0, -1, poff))
         else:
             kind, dim, prm = self._simple_block(Z)
             self.dparams += prm

@@ -196,6 +196,12 @@ __device__ __noinline__ int sample_measurement(const DeviceGraph& g, const iif_f
       }
       return IIF_OK;
     }
+    case IIF_D_SAMPLES: {  // host-drawn sample table of any distribution: uniform resampling with replacement
+      const double u = rs_uniform(seed, call, IIF_RS_MIXLABEL, (uint32_t)n);
+      const int k = min((int)(u * D.ncomp), D.ncomp - 1);
+      for (int c = 0; c < D.dim; ++c) z[c] = prm[k * D.dim + c];
+      return IIF_OK;
+    }
     default: return IIF_ERR_UNSUPPORTED;
   }
 }

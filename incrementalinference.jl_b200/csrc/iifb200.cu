@@ -380,10 +380,13 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
     }
   }
   for (int k = 0; k < ndists; ++k) {
-    if (dists[k].kind < IIF_D_NORMAL || dists[k].kind > IIF_D_UNIFORM)
+    if (dists[k].kind < IIF_D_NORMAL || dists[k].kind > IIF_D_SAMPLES)
       return fail(ctx, IIF_ERR_UNSUPPORTED, "distribution kind has no device sampler");
     if (dists[k].kind == IIF_D_KDE && (dists[k].slot < 0 || dists[k].slot >= nslots))
       return fail(ctx, IIF_ERR_ARG, "KDE distribution slot out of range");
+    if (dists[k].kind == IIF_D_SAMPLES && (dists[k].ncomp < 1 || dists[k].poff < 0 ||
+                                           (int64_t)dists[k].poff + (int64_t)dists[k].ncomp * dists[k].dim > nparams))
+      return fail(ctx, IIF_ERR_ARG, "sample-table distribution exceeds the parameter array");
   }
   ctx->total_doubles = layout_slots(nslots, slots);
   ctx->slots.assign(slots, slots + nslots);

@@ -83,6 +83,21 @@ class Uniform:
     dim: int = 1
 
 
+class SampledBelief:
+    """Any SamplableBelief (`rand(Z)` is all sampleFactor! needs, SolverUtilities.jl:50-76): a table of host-drawn
+    samples that the device resamples with replacement — Rayleigh, Gamma, user-defined distributions ..."""
+
+    def __init__(self, samples):
+        s = np.ascontiguousarray(np.asarray(samples, dtype=np.float64))
+        self.samples = s.reshape(len(s), -1)
+        self.dim = self.samples.shape[1]
+
+    @classmethod
+    def from_sampler(cls, draw, count: int = 4096):
+        """`draw(count)` returns count samples (count x dim or count,), e.g. a scipy.stats frozen distribution's rvs"""
+        return cls(draw(count))
+
+
 class MvNormal:
     def __init__(self, mu, cov):
         self.mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))

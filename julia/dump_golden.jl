@@ -65,4 +65,42 @@ dump_case("door_odometry_to_x1", fg3, :x0x1f1, :x1)
 dump_case("door_multihypo_to_x1", fg3, :x1l0l1l2l3f1, :x1)
 mkd3, = propagateBelief(fg3, :x1, :)
 writedlm(joinpath(out, "door_x1_posterior.csv"), reduce(hcat, [collect(Float64, p) for p in getPoints(mkd3, false)])', ',')
+
+# case 4: a whole tree solve (VERDICT r1, next-round 1d): 10-pose scalar chain, nested-dissection elimination order
+# (odd-even reduction, as workloads.chain_nd_order), default SolverParams (useMsgLikelihoods = false), 20 seeds.
+# Per seed and pose: posterior mean and standard deviation after solveTree!.  tests/test_golden.py compares the
+# oracle's / the device's statistics over 20 seeds with these (band test: the reference's RNG is not reproduced).
+function chain_nd_order(n)
+  remaining = collect(0:(n - 1)); order = Int[]
+  while length(remaining) > 2
+    elim = isodd(length(remaining)) ? remaining[2:2:end] : remaining[2:2:(end - 1)]
+    isempty(elim) && break
+    append!(order, elim)
+    remaining = [k for k in remaining if !(k in elim)]
+  end
+  append!(order, remaining)
+  return [Symbol("x$k") for k in order]
+end
+let n = 10, rows = Vector{Vector{Float64}}()
+  for seed in 1:20
+    Random.seed!(seed)
+    fgc = initfg(); getSolverParams(fgc).N = N; getSolverParams(fgc).graphinit = false
+    for k in 0:(n - 1)
+      addVariable!(fgc, Symbol("x$k"), ContinuousScalar)
+    end
+    addFactor!(fgc, [:x0], Prior(Normal(0.0, 0.1)))
+    for k in 0:(n - 2)
+      addFactor!(fgc, [Symbol("x$k"), Symbol("x$(k+1)")], LinearRelative(Normal(1.0, 0.1)))
+    end
+    for k in 0:(n - 1)    # the initial beliefs workloads.scalar_chain generates: x_k ~ N(k, 0.1 sqrt(k + 1))
+      initVariable!(fgc, Symbol("x$k"), [[k + 0.1 * sqrt(k + 1.0) * randn()] for _ in 1:N])
+    end
+    solveTree!(fgc; eliminationOrder = chain_nd_order(n))
+    for k in 0:(n - 1)
+      p = [x[1] for x in getPoints(getBelief(fgc, Symbol("x$k")), false)]
+      push!(rows, [seed, k, sum(p) / length(p), sqrt(sum(abs2, p .- sum(p) / length(p)) / (length(p) - 1))])
+    end
+  end
+  writedlm(joinpath(out, "tree_chain10_nd.csv"), reduce(hcat, rows)', ',')     # seed, pose, mean, std
+end
 println("wrote golden vectors to ", out)

@@ -457,6 +457,13 @@ static int32_t sample_measurement(const iifo_graph* g, const iif_factor_desc* f,
       sample_simple(D->comp_kind, D->dim, cp, seed, call, n, f->zdim, z);
       break;
     }
+    case IIF_D_SAMPLES: { /* rand(Z) of any host-side distribution, pre-drawn into a table; uniform resampling */
+      double u = iifo_uniform(seed, call, IIF_RS_MIXLABEL, (uint32_t)n);
+      int k = (int)(u * D->ncomp);
+      if (k >= D->ncomp) k = D->ncomp - 1;
+      for (int c = 0; c < D->dim; ++c) z[c] = prm[k * D->dim + c];
+      break;
+    }
     case IIF_D_KDE: { /* MsgPrior.jl:27-30 samplePoint(mkd): pick a kernel, add bw-scaled jitter */
       const iif_slot_desc* S = &g->slots[D->slot];
       int np = g->npts[D->slot];

@@ -235,6 +235,22 @@ def conv_cases():
                                         dict(factor=fnm, sfidx=1, N=N, call_id=124), dict(factor=fse, sfidx=2, N=N, call_id=125)], None
 
 
+    # 15. measurement distributions beyond the parametric ones: a host-drawn sample table (here Rayleigh range noise
+    # and a skewed 2-D Gamma offset), resampled on the device
+    P = Problem()
+    x0 = P.slot(G.ContinuousScalar, N, R.normal(0, 1, (N, 1)))
+    x1 = P.slot(G.ContinuousScalar, N, R.normal(3, 1, (N, 1)))
+    y0 = P.slot(G.Position(2), N, R.normal(0, 1, (N, 2)))
+    y1 = P.slot(G.Position(2), N, R.normal(2, 1, (N, 2)))
+    ray = G.SampledBelief(R.rayleigh(2.0, 2048))
+    gam = G.SampledBelief(R.gamma(2.0, 0.5, (1024, 2)))
+    fr1 = P.factor(G.LinearRelative(ray), [x0, x1])
+    fp1 = P.factor(G.Prior(ray), [x0])
+    fr2 = P.factor(G.LinearRelative(gam), [y0, y1])
+    yield "sample_table", P.freeze(), [dict(factor=fr1, sfidx=2, N=N, call_id=130), dict(factor=fp1, sfidx=1, N=N, call_id=131),
+                                       dict(factor=fr2, sfidx=1, N=N, call_id=132)], None
+
+
 def wrap(a):
     return (np.asarray(a) + np.pi) % (2 * np.pi) - np.pi
 

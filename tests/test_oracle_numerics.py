@@ -573,6 +573,20 @@ def test_special_orthogonal2_testSpecialOrthogonalMani():
     assert np.cos(t1).mean() < -0.9                                   # x1 sits at +-pi (the seam)
 
 
+def test_sample_table_distribution():
+    """any host-side distribution as a measurement (sampleFactor! = rand(Z), SolverUtilities.jl:50-76): Rayleigh(2)
+    range noise through a prior and a relative factor keeps its mean sigma sqrt(pi/2) and its skew"""
+    name, P, specs, _ = [c for c in PC.conv_cases() if c[0] == "sample_table"][0]
+    orc = P.oracle()
+    ops = CP.make_conv_ops(specs)
+    pri = orc.conv(ops[1])[0][:, 0]
+    assert abs(pri.mean() - 2.0 * np.sqrt(np.pi / 2)) < 0.5 and pri.min() > 0 and abs(pri.std() - 2.0 * np.sqrt(2 - np.pi / 2)) < 0.45
+    rel = orc.conv(ops[0])[0][:, 0] - P.arena.get(0)[0][:, 0]          # x1 - x0 = z for every particle (label 1)
+    assert rel.min() > 0 and abs(rel.mean() - 2.0 * np.sqrt(np.pi / 2)) < 0.5
+    g2 = P.arena.get(3)[0] - orc.conv(ops[2])[0]                        # y1 - y0' = z (solving the first variable)
+    assert (g2 > 0).all() and np.abs(g2.mean(axis=0) - 1.0).max() < 0.3
+
+
 def test_numeric_solver_nelder_mead():
     """SURVEY a10b (_solveLambdaNumeric, NumericalCalculations.jl:49-133): the restated Optim.NelderMead.  Unique-root
     factors forced through it land on the analytic root within the optimiser's own accuracy (its stopping rule
