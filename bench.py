@@ -93,7 +93,7 @@ def ncu_traffic_per_block():
         if "iif_conv_kernel" in d.get("kernel", "") and "dram__bytes_read.sum" in d:
             rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
             tot = float(rd[0]) * unit.get(rd[1], 1.0) + float(wr[0]) * unit.get(wr[1], 1.0)
-            return tot / max(float(d["launch__grid_size"][0]), 1.0), name
+            return tot / max(float(d["launch__grid_size"][0]), 1.0), f"profiles/{name}.ncu-rep summary in profiles/{os.path.basename(p)}"
     return None, None
 
 
@@ -442,8 +442,7 @@ def run_b200(args, rank, world, local_rank):
         roof = {"bound": "hbm", "kernel": "iif_conv_kernel", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"],
                 "traffic": (tpb * cb / max(cl, 1)) if tpb is not None else None,
-                "traffic_source": (f"profiles/{tsrc}.ncu-rep summary in profiles/r01b_kernels.json: dram bytes per CTA x "
-                                   f"average CTAs per launch") if tpb is not None else None,
+                "traffic_source": (f"{tsrc}: dram bytes per CTA x average CTAs per launch") if tpb is not None else None,
                 "algorithmic_bytes_per_launch": byts / max(cl, 1),
                 "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)",
                 "launch_ms_avg": cms / max(cl, 1), "launches": cl, "blocks": cb,

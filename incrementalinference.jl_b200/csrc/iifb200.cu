@@ -598,6 +598,15 @@ static int pick_cluster(iifb200_ctx* ctx, int grid) {
   static const int want = env_int("IIFB200_CLUSTER", IIF_SPEC_CLUSTER);
   return (want == IIF_SPEC_CLUSTER && grid * IIF_SPEC_CLUSTER <= ctx->num_sms) ? IIF_SPEC_CLUSTER : 1;
 }
+// Development knob: products at the very top of the tree (at most 18 per launch) can take a larger cluster, dealing the
+// output samples — hence the Gibbs weight builds and picks — over up to eight SMs (the extra ranks ride along in the
+// three-way speculative bandwidth search).  Measured: no gain (profiles/r02_summary.md: a lone product is bound by its
+// sequence of per-level barriers, not by per-sample work), so the default stays at the three-CTA cluster.
+static int pick_cluster_prod(iifb200_ctx* ctx, int grid) {
+  static const int big = env_int("IIFB200_PROD_CLUSTER_BIG", 0);
+  if (big > IIF_SPEC_CLUSTER && big <= 8 && grid * big <= ctx->num_sms && pick_cluster(ctx, grid) == IIF_SPEC_CLUSTER) return big;
+  return pick_cluster(ctx, grid);
+}
 static bool is_prior_kind_h(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR ||
          k == IIF_F_MANIFOLD_PRIOR;
@@ -777,7 +786,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ProdTask) * V, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  launch_k(iif_product_kernel, V, pick_cluster(ctx, V), pick_threads_prod(ctx, V, pmaxN), smem, ctx->stream, ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
+  launch_k(iif_product_kernel, V, pick_cluster_prod(ctx, V), pick_threads_prod(ctx, V, pmaxN), smem, ctx->stream, ctx->dg, d_tasks, d_u, d_n, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -1208,7 +1217,7 @@ static int enqueue_seg(iifb200_ctx* ctx, Schedule* s, const Wave& W, const Seg& 
     ++k;
   }
   if (G.nprod) {
-    launch_k(iif_product_kernel, G.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, st, ctx->dg, s->d_prod + G.prod0, nullptr, nullptr, ctx->d_trees);
+    launch_k(iif_product_kernel, G.nprod, pick_cluster_prod(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, st, ctx->dg, s->d_prod + G.prod0, nullptr, nullptr, ctx->d_trees);
     ++k;
   }
   if (G.npush) {
@@ -1351,7 +1360,7 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
     }
     if (W.nprod) {
       mark();
-      launch_k(iif_product_kernel, W.nprod, pick_cluster(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream, ctx->dg, s->d_prod + W.segs[0].prod0, nullptr, nullptr, ctx->d_trees);
+      launch_k(iif_product_kernel, W.nprod, pick_cluster_prod(ctx, W.nprod), pick_threads_prod(ctx, W.nprod, W.maxN), W.prod_smem, ctx->stream, ctx->dg, s->d_prod + W.segs[0].prod0, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(1); blocks[1] += W.nprod;
     }
   }

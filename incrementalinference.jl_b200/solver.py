@@ -22,16 +22,26 @@ from .engine import Engine
 
 # --------------------------------------------------------------------------- per-graph engine
 class GraphEngine:
-    """Device mirror of one FactorGraph: slot i == variable i, factor table == graph factors."""
+    """Device mirror of one FactorGraph: slot i == variable i, factor table == graph factors.  ONE iifb200 context for
+    the graph's lifetime: structural changes (addVariable / addFactor) re-issue iifb200_set_graph on it (the library's
+    arena, tables and scratch are grow-only) instead of tearing the context down, and beliefs are re-uploaded in one
+    transfer (incremental construction with graphinit used to re-create the CUDA context per factor)."""
 
     def __init__(self, fg: G.FactorGraph, device: int = 0, cap: int = 0):
         self.fg = fg
+        self.device = device
+        self.eng = None
+        self.cap = 0
+        self._build(cap)
+
+    def _build(self, cap: int = 0):
+        fg = self.fg
         self.version = fg._version
         T = CP.Tables()
         self.N = fg.solverParams.N
         # slot capacity is the engine's own business: a call that asks for more points than SolverParams.N grows it
         # without touching the user's solver parameters
-        self.cap = max(self.N, int(cap))
+        self.cap = max(self.N, int(cap), self.cap)
         self.var_slot = {}
         for l, v in fg.variables.items():
             self.var_slot[l] = T.add_slot(v.vartype, max(self.cap, v.val.shape[0], 1))
@@ -41,16 +51,27 @@ class GraphEngine:
                                            f.nullhypo, f.inflation)
         self.frozen = T.freeze()
         self.sp_c = CP.solver_params_c(fg.solverParams)
-        self.eng = Engine(self.frozen, self.sp_c, device)
+        if self.eng is None:
+            self.eng = Engine(self.frozen, self.sp_c, self.device)
+        else:
+            self.eng.reset_graph(self.frozen, self.sp_c)      # same context, grow-only device memory
         self.dirty = set(fg.variables)
 
     def mark_dirty(self, lbl):
         self.dirty.add(lbl)
 
     def flush(self):
-        for l in list(self.dirty):
-            v = self.fg.variables[l]
-            self.eng.upload_belief(self.var_slot[l], v.val, v.bw, v.initialized)
+        if not self.dirty:
+            return
+        if len(self.dirty) > 4:                                # many beliefs: one transfer of the whole arena
+            ar = CP.HostArena(self.frozen)
+            for l, v in self.fg.variables.items():
+                ar.set(self.var_slot[l], v.val, v.bw, v.initialized, v.infoPerCoord)
+            self.eng.upload_arena(ar)
+        else:
+            for l in list(self.dirty):
+                v = self.fg.variables[l]
+                self.eng.upload_belief(self.var_slot[l], v.val, v.bw, v.initialized)
         self.dirty.clear()
 
     def next_call(self, n=16):
@@ -62,13 +83,11 @@ class GraphEngine:
 
 def _engine(fg: G.FactorGraph, cap: int = 0) -> GraphEngine:
     ge = fg._engine
-    if ge is None or ge.version != fg._version or ge.N != fg.solverParams.N or ge.cap < cap:
-        keep = 0
-        if ge is not None:
-            keep = ge.cap
-            ge.close()
-        ge = GraphEngine(fg, cap=max(cap, keep))
+    if ge is None:
+        ge = GraphEngine(fg, cap=cap)
         fg._engine = ge
+    elif ge.version != fg._version or ge.N != fg.solverParams.N or ge.cap < cap:
+        ge._build(cap)
     sp_c = CP.solver_params_c(fg.solverParams)
     if bytes(sp_c) != bytes(ge.sp_c):
         ge.sp_c = sp_c

@@ -14,6 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CSRC = os.path.join(ROOT, "incrementalinference.jl_b200", "csrc")
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 TIDS = [int(a) for a in sys.argv[2:]] or [0, 160]
+VWIDE = int(os.environ.get("IIFB200_PROBE_V", "1"))     # beliefs per launch: > 148 probes block 0 of a WIDE launch
 LOO = ["loo rows (hot loop)", "loo barrier1", "loo gather", "loo part+barrier2", "loo partsum+log+warpsum",
        "loo barrier3", "loo tot", "-"]
 KER = {"bandwidth": {8: "load", 13: "search+write"},
@@ -45,7 +46,7 @@ for tid in TIDS:
             ms = eng.last_elapsed_ms()
         L.iifb200_debug_phases(buf, 0)
         v = np.array(list(buf), dtype=np.float64)
-        print(f"--- {name} kernel, one belief, N={N}, tid {tid}: {ms*1e3:.1f} us (events around the launch)")
+        print(f"--- {name} kernel, {VWIDE} belief(s) per launch, block 0, N={N}, tid {tid}: {ms*1e3:.1f} us (events around the launch)")
         for k, nm in KER[name].items():
             print(f"   {nm:28s} {v[k]:9.0f} cyc  {v[k]/1.965e3:6.1f} us")
         print(f"   [cost of one phase mark: {v[31] / max(v[30] and 18, 1):.0f} cycles if 18 evaluations; raw {v[30]:.0f} {v[31]:.0f}]")
@@ -55,20 +56,22 @@ for tid in TIDS:
                 continue
             print(f"      {LOO[k]:25s} {v[k]:9.0f} cyc  {v[k]/1.965e3:6.1f} us")
 
-    pts = R.normal(0, 1, (1, N, 1))
-    Ns = np.full(1, N, dtype=np.int32); Ds = np.ones(1, dtype=np.int32); Ms = np.zeros(1, dtype=np.int32)
-    out = np.zeros(4)
-    report("bandwidth", lambda: eng._check(L.iifb200_kde_bandwidth(eng.ctx, 1, A.as_ip(Ns), A.as_ip(Ds), A.as_ip(Ms),
+    V = VWIDE
+    pts = R.normal(0, 1, (V, N, 1))
+    Ns = np.full(V, N, dtype=np.int32); Ds = np.ones(V, dtype=np.int32); Ms = np.zeros(V, dtype=np.int32)
+    out = np.zeros(4 * V)
+    report("bandwidth", lambda: eng._check(L.iifb200_kde_bandwidth(eng.ctx, V, A.as_ip(Ns), A.as_ip(Ds), A.as_ip(Ms),
                                                                     A.as_dp(pts), A.as_dp(out)), "bw"))
-    ops = CP.make_conv_ops([dict(factor=fs[1], sfidx=2, N=N, call_id=16)])
-    report("conv", lambda: eng.conv_batch(ops, 1))
-    a = R.normal(0, 1, (1, 2, N, 1))
-    bws = np.zeros((2, 4)); bws[:, 0] = 0.4
-    pop = (A.ProductOp * 1)()
-    pop[0].dim, pop[0].circ_mask, pop[0].nfactors, pop[0].N, pop[0].call_id = 1, 0, 2, N, 16
-    pop[0].randu_off = pop[0].randn_off = -1
-    o2 = np.zeros((1, N, 1)); obw = np.zeros(4)
-    report("product", lambda: eng._check(L.iifb200_product_batch(eng.ctx, 1, pop, A.as_dp(a), A.as_dp(bws), None, None, None,
+    ops = CP.make_conv_ops([dict(factor=fs[1], sfidx=2, N=N, call_id=16 * (k + 1)) for k in range(V)])
+    report("conv", lambda: eng.conv_batch(ops, V))
+    a = R.normal(0, 1, (V, 2, N, 1))
+    bws = np.zeros((2 * V, 4)); bws[:, 0] = 0.4
+    pop = (A.ProductOp * V)()
+    for v in range(V):
+        pop[v].dim, pop[v].circ_mask, pop[v].nfactors, pop[v].N, pop[v].call_id = 1, 0, 2, N, 16 * (v + 1)
+        pop[v].randu_off = pop[v].randn_off = -1
+    o2 = np.zeros((V, N, 1)); obw = np.zeros(4 * V)
+    report("product", lambda: eng._check(L.iifb200_product_batch(eng.ctx, V, pop, A.as_dp(a), A.as_dp(bws), None, None, None,
                                                                   None, A.as_dp(o2), A.as_dp(obw), None), "prod"))
     eng.close()
     os.remove(lib)
