@@ -78,9 +78,18 @@ enum iif_factor_kind {
   IIF_F_MANIFOLD_PRIOR = 8,    /* ManifoldPrior :163-214 / ManifoldPriorPartial :288-303: sample = retract(M, p, hat(Z))
                                   = p (+) Z coordinate-wise (angles wrapped); p is folded into Z's mean by the host;
                                   partial_mask != 0 selects the informed coordinates */
-  IIF_F_SE2_RELATIVE = 9       /* ManifoldFactor{SpecialEuclidean(2)} :64-100 with distanceTangent2Point :39-44:
+  IIF_F_SE2_RELATIVE = 9,      /* ManifoldFactor{SpecialEuclidean(2)} :64-100 with distanceTangent2Point :39-44:
                                   qhat = p o exp(eps, X), residual vee(log(q, qhat)); X = (dx, dy, dtheta) in p's frame */
+  /* SpecialOrthogonal(3) (test/testSpecialOrthogonalMani.jl:75-140).  Points are stored as rotation vectors
+   * omega = vee(log(eps, R)) (slot flag IIF_MANI_SO3); AMP treats these coordinates as (:Euclid, :Euclid, :Euclid)
+   * (same test, :80-81), so bandwidth and product work on them unchanged; the factors compose on the group. */
+  IIF_F_SO3_PRIOR = 10,        /* ManifoldPrior{SpecialOrthogonal(3)} :163-214: sample = retract(M, p, hat(Z)) = p Exp(z);
+                                  p's rotation vector in iif_factor_desc.aux */
+  IIF_F_SO3_RELATIVE = 11      /* ManifoldFactor{SpecialOrthogonal(3)}: qhat = p Exp(X), residual vee(log(q, qhat)) = Log(q^T qhat) */
 };
+/* iif_slot_desc.circ_mask, bit 8: the three coordinates are an SO(3) rotation vector — entropy, spread statistics and the
+ * group factors compose on the manifold; KDE bandwidth / product treat them as Euclid coordinates (AMP's convention). */
+#define IIF_MANI_SO3 0x100
 
 /* measurement distributions (SamplableBelief) */
 enum iif_dist_kind {
@@ -128,6 +137,7 @@ typedef struct {
   double mh[IIF_MAX_ARITY];    /* parseusermultihypo output (FactorGraph.jl:639-654): 0.0 = certain */
   double nullhypo;             /* CCW.nullhypo   FactorOperationalMemory.jl:51 */
   double inflation;            /* CCW.inflation  FactorOperationalMemory.jl:53 (default 5.0) */
+  double aux[IIF_MAX_DIM];     /* IIF_F_SO3_PRIOR: coordinates of the prior's point p (ManifoldPrior.p); else unused */
 } iif_factor_desc;
 
 /* SolverParams subset used on the hot path (src/entities/SolverParams.jl) */

@@ -18,6 +18,8 @@ IIF_OK, IIF_ERR_ARG, IIF_ERR_CUDA, IIF_ERR_UNSUPPORTED, IIF_ERR_STATE = 0, -1, -
 F_PRIOR, F_LINEAR_RELATIVE, F_PRIOR_CIRCULAR, F_CIRCULAR_CIRCULAR = 1, 2, 3, 4
 F_EUCLID_DISTANCE, F_MSG_PRIOR, F_PARTIAL_PRIOR = 5, 6, 7
 F_MANIFOLD_PRIOR, F_SE2_RELATIVE = 8, 9
+F_SO3_PRIOR, F_SO3_RELATIVE = 10, 11
+MANI_SO3 = 0x100
 # iif_dist_kind
 D_NORMAL, D_MVNORMAL, D_MIXTURE, D_KDE, D_UNIFORM, D_SAMPLES = 1, 2, 3, 4, 5, 6
 # iif_sched_kind
@@ -39,7 +41,7 @@ class FactorDesc(C.Structure):
                 ("dist", C.c_int32), ("slot", C.c_int32 * IIF_MAX_ARITY), ("nmh", C.c_int32),
                 ("partial_mask", C.c_int32), ("solver", C.c_int32), ("_pad", C.c_int32),
                 ("mh", C.c_double * IIF_MAX_ARITY),
-                ("nullhypo", C.c_double), ("inflation", C.c_double)]
+                ("nullhypo", C.c_double), ("inflation", C.c_double), ("aux", C.c_double * IIF_MAX_DIM)]
 
 
 class SolverParamsC(C.Structure):

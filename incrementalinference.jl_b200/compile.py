@@ -72,6 +72,7 @@ class Tables:
         self.factors.append(dict(kind=fnc.kind, arity=len(slots), zdim=zdim, dist=d, slot=list(slots),
                                  nmh=0 if mh is None else len(mh), partial_mask=partial_mask,
                                  solver=int(bool(getattr(fnc, "numeric", False))),
+                                 aux=[float(x) for x in getattr(fnc, "aux", [])],
                                  mh=[] if mh is None else list(mh), nullhypo=float(nullhypo),
                                  inflation=float(inflation)))
         return len(self.factors) - 1
@@ -98,6 +99,8 @@ class Tables:
             for k, p in enumerate(f["mh"]):
                 fd.mh[k] = p
             fd.nullhypo, fd.inflation = f["nullhypo"], f["inflation"]
+            for k, x in enumerate(f.get("aux", [])):
+                fd.aux[k] = x
         dparams = np.asarray(self.dparams if self.dparams else [0.0], dtype=np.float64)
         self._frozen = dict(nslots=ns, slots=slots, nfactors=nf, factors=factors, ndists=nd,
                             dists=dists, nparams=len(self.dparams), dparams=dparams,

@@ -212,6 +212,23 @@ __device__ __noinline__ int sample_measurement(const DeviceGraph& g, const iif_f
 // sequential geodesic recurrence on one thread (order dependent).  Result in mu_s (shared).
 __device__ void block_geodesic_mean(const double* pts, int n, int d, int32_t cm, double* mu_s, double* red,
                                     int& parity) {
+  if (is_so3(cm)) {  // mean(M, pts, GeodesicInterpolation()) on SO(3): mu <- mu Exp(Log(mu^T p_i) / (i + 1)), one thread
+    if (threadIdx.x == 0) {
+      double mu[3] = {0, 0, 0};
+      if (n > 0) for (int c = 0; c < 3; ++c) mu[c] = pts[c];
+      for (int i = 1; i < n; ++i) {
+        double dl[3], nx[3];
+        so3_between(mu, pts + i * 3, dl);
+        const double t = 1.0 / (double)(i + 1);
+        for (int c = 0; c < 3; ++c) dl[c] *= t;
+        so3_compose(mu, dl, nx);
+        for (int c = 0; c < 3; ++c) mu[c] = nx[c];
+      }
+      for (int c = 0; c < 3; ++c) mu_s[c] = mu[c];
+    }
+    __syncthreads();
+    return;
+  }
   double s[IIF_MAX_DIM] = {0, 0, 0, 0};
   for (int i = threadIdx.x; i < n; i += IIF_NT)
     for (int c = 0; c < d; ++c) s[c] += pts[i * d + c];
@@ -252,11 +269,19 @@ __device__ __noinline__ double block_std_basic_spread(const double* pts, int n, 
   if (n < 2) return 1.0;
   block_geodesic_mean(pts, n, d, cm, mu_s, red, parity);
   double acc = 0;
-  for (int i = threadIdx.x; i < n; i += IIF_NT)
-    for (int c = 0; c < d; ++c) {
-      double v = mdiff(pts[i * d + c], mu_s[c], is_circ(cm, c));
-      acc += v * v;
+  if (is_so3(cm)) {  // distance(M, mu, p)^2 = |log(mu, p)|_F^2 = 2 angle^2 (Frobenius metric of the skew matrices)
+    for (int i = threadIdx.x; i < n; i += IIF_NT) {
+      double dl[3];
+      so3_between(mu_s, pts + i * 3, dl);
+      acc += 2.0 * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
     }
+  } else {
+    for (int i = threadIdx.x; i < n; i += IIF_NT)
+      for (int c = 0; c < d; ++c) {
+        double v = mdiff(pts[i * d + c], mu_s[c], is_circ(cm, c));
+        acc += v * v;
+      }
+  }
   acc = block_sum1(acc, red, parity, (n + 31) >> 5);
   double sigma = sqrt(acc / (double)(n - 1));
   return (1e-10 < sigma) ? sigma : 1.0;
@@ -270,13 +295,20 @@ __device__ __noinline__ double block_spread_distance(const DeviceGraph& g, const
   const int d = Ssf.dim;
   if (in_list(R.cert, R.ncert, sfidx)) return kappa * block_std_basic_spread(dest, N, d, Ssf.circ_mask, mu_s, red, parity);
   double ref[IIF_MAX_DIM], m[IIF_MAX_DIM];
-  block_default_mean(dest, N, d, Ssf.circ_mask, ref, red, parity);
+  if (is_so3(Ssf.circ_mask)) {
+    __syncthreads();
+    block_geodesic_mean(dest, N, d, Ssf.circ_mask, mu_s, red, parity);
+    for (int c = 0; c < d; ++c) ref[c] = mu_s[c];
+    __syncthreads();
+  } else {
+    block_default_mean(dest, N, d, Ssf.circ_mask, ref, red, parity);
+  }
   double best = 1e-2;
   for (int v = 1; v <= f.arity; ++v) {
     const iif_slot_desc S = g.slots[f.slot[v - 1]];
     const double* p = (v == sfidx) ? dest : g.pts + S.pts_off;
     const int np = (v == sfidx) ? N : g.npts[f.slot[v - 1]];
-    if (in_list(R.cert, R.ncert, v)) {
+    if (in_list(R.cert, R.ncert, v) || is_so3(S.circ_mask)) {
       __syncthreads();
       block_geodesic_mean(p, np, S.dim, S.circ_mask, mu_s, red, parity);
       for (int c = 0; c < S.dim; ++c) m[c] = mu_s[c];
@@ -298,6 +330,10 @@ __device__ __forceinline__ void solve_binary(int kind, int d, int32_t cm, const 
                                              bool sf_second, const double* u0, double* out) {
   if (kind == IIF_F_LINEAR_RELATIVE || kind == IIF_F_CIRCULAR_CIRCULAR) {
     for (int c = 0; c < d; ++c) out[c] = madd(other[c], sf_second ? z[c] : -z[c], is_circ(cm, c));
+  } else if (kind == IIF_F_SO3_RELATIVE) {
+    // ManifoldFactor{SpecialOrthogonal(3)}: q = p Exp(X); p = q Exp(X)^-1 = q Exp(-X)
+    if (sf_second) so3_compose(other, z, out);
+    else { const double nz_[3] = {-z[0], -z[1], -z[2]}; so3_compose(other, nz_, out); }
   } else if (kind == IIF_F_SE2_RELATIVE) {
     // ManifoldFactor{SpecialEuclidean(2)}: q = p o exp(eps, X)  (GenericFunctions.jl:39-44, hybrid tangent
     // representation: exp(eps, X) = (X_t, R(X_theta))).  Solving q: theta_q = theta_p + X_theta,
@@ -339,6 +375,11 @@ __device__ __noinline__ double cost_binary(int kind, int d, int32_t cm, const do
     for (int c = 0; c < d; ++c) { const double e = __dsub_rn(q[c], p[c]); n2 = __dadd_rn(n2, __dmul_rn(e, e)); }
     const double r = __dsub_rn(z[0], sqrt(n2));
     s = __dmul_rn(r, r);
+  } else if (kind == IIF_F_SO3_RELATIVE) {  // |Log(q^T p Exp(z))|^2
+    double qh[3], r[3];
+    so3_compose(p, z, qh);
+    so3_between(q, qh, r);
+    s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
   } else {  // IIF_F_SE2_RELATIVE
     double sn, cs;
     sincos(p[2], &sn, &cs);
@@ -423,11 +464,17 @@ __device__ __noinline__ void nelder_mead_binary(int kind, int d, int32_t cm, con
   const double fcen = cost_binary(kind, d, cm, z, cen, other, sf_second);
   const double* r = fcen < f[best] ? cen : S[best];
   for (int c = 0; c < n; ++c) out[c] = is_circ(cm, c) ? wrap_pi(r[c]) : r[c];
+  if (is_so3(cm)) {  // exp(M, eps, hat(minimizer)): the principal rotation vector of the minimiser
+    const double zero[3] = {0, 0, 0};
+    double pr[3];
+    so3_compose(out, zero, pr);
+    for (int c = 0; c < 3; ++c) out[c] = pr[c];
+  }
 }
 
 __device__ __forceinline__ bool is_prior_kind(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR ||
-         k == IIF_F_MANIFOLD_PRIOR;
+         k == IIF_F_MANIFOLD_PRIOR || k == IIF_F_SO3_PRIOR;
 }
 
 __global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
@@ -523,10 +570,17 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   // addEntropyOnManifold! on this thread's particle (EvalFactor.jl:95-132)
   auto add_entropy = [&](int hyp, int32_t dimmask, double spread, int cyc) {
     if (active && label == hyp) {
-      for (int c = 0; c < d; ++c) {
-        if (!((dimmask >> c) & 1)) continue;
-        my[c] = madd(my[c], spread * (inflate_u(cyc, c) - 0.5), is_circ(cm, c));
-        dest[n * d + c] = my[c];
+      if (is_so3(cm)) {  // retract(M, p, get_vector(M, p, Xc)) = p Exp(Xc)
+        double dl[3], nx[3];
+        for (int c = 0; c < 3; ++c) dl[c] = ((dimmask >> c) & 1) ? spread * (inflate_u(cyc, c) - 0.5) : 0.0;
+        so3_compose(my, dl, nx);
+        for (int c = 0; c < 3; ++c) { my[c] = nx[c]; dest[n * d + c] = nx[c]; }
+      } else {
+        for (int c = 0; c < d; ++c) {
+          if (!((dimmask >> c) & 1)) continue;
+          my[c] = madd(my[c], spread * (inflate_u(cyc, c) - 0.5), is_circ(cm, c));
+          dest[n * d + c] = my[c];
+        }
       }
     }
   };
@@ -537,7 +591,11 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
       double spreadDist = g.sp->spreadNH * block_std_basic_spread(dest, N, d, cm, mu_s, red, parity);  // :464
       const bool wrap = (f.kind == IIF_F_PRIOR_CIRCULAR || f.kind == IIF_F_MSG_PRIOR || f.kind == IIF_F_MANIFOLD_PRIOR);
       if (active && label == 1) {
-        if (!f.partial_mask) {
+        if (f.kind == IIF_F_SO3_PRIOR) {
+          double nx[3];
+          so3_compose(f.aux, z, nx);     // retract(M, p, hat(Z)) = p Exp(z)
+          for (int c = 0; c < 3; ++c) my[c] = nx[c];
+        } else if (!f.partial_mask) {
           for (int c = 0; c < d; ++c) my[c] = (wrap && is_circ(cm, c)) ? wrap_pi(z[c]) : z[c];
         } else {
           int k = 0;

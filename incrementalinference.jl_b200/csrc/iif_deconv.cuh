@@ -57,6 +57,8 @@ __device__ __forceinline__ int deconv_sample(const DeviceGraph& g, const iif_fac
         if (!f.partial_mask || ((f.partial_mask >> c) & 1)) p[k++] = is_circ(S1.circ_mask, c) ? wrap_pi(x[0][c]) : x[0][c];
       break;
     }
+    case IIF_F_SO3_PRIOR: so3_between(f.aux, x[0], p); break;       // z with p Exp(z) = x1
+    case IIF_F_SO3_RELATIVE: so3_between(x[0], x[1], p); break;     // X = Log(p^T q)
     case IIF_F_SE2_RELATIVE: {    // X = vee(log(eps, p^-1 o q)): X_t = R(theta_p)^T (t_q - t_p), X_theta = theta_q - theta_p
       double sn, cs;
       sincos(x[0][2], &sn, &cs);

@@ -133,6 +133,40 @@ __device__ __forceinline__ bool is_circ(int32_t mask, int c) { return (mask >> c
 __device__ __forceinline__ double mdiff(double a, double b, bool circ) { return circ ? wrap_pi(a - b) : a - b; }
 __device__ __forceinline__ double madd(double a, double t, bool circ) { return circ ? wrap_pi(a + t) : a + t; }
 
+// SpecialOrthogonal(3): points travel as rotation vectors omega = vee(log(eps, R)), |omega| <= pi.  Group operations go
+// through unit quaternions (w, v) = (cos(|omega|/2), sin(|omega|/2) omega/|omega|).
+__device__ __forceinline__ bool is_so3(int32_t mask) { return (mask & IIF_MANI_SO3) != 0; }
+struct Quat { double w, x, y, z; };
+__device__ __forceinline__ Quat so3_quat(const double* om) {
+  const double t2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+  double s, w;
+  if (t2 < 1e-16) { s = 0.5 - t2 / 48.0; w = 1.0 - t2 / 8.0; }
+  else { const double t = sqrt(t2); sincos(0.5 * t, &s, &w); s /= t; }
+  Quat q = {w, s * om[0], s * om[1], s * om[2]};
+  return q;
+}
+__device__ __forceinline__ Quat quat_mul(const Quat& a, const Quat& b) {
+  Quat r = {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+            a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+  return r;
+}
+__device__ __forceinline__ void so3_rotvec(Quat q, double* om) {  // Log: rotation angle in [0, pi]
+  if (q.w < 0) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+  const double vn = sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+  const double k = vn < 1e-12 ? 2.0 : 2.0 * atan2(vn, q.w) / vn;
+  om[0] = k * q.x; om[1] = k * q.y; om[2] = k * q.z;
+}
+// out = Log(Exp(a) Exp(b)): p Exp(X) for a point p = Exp(a) and a tangent X = hat(b) (exp / retract at p, compose)
+__device__ __forceinline__ void so3_compose(const double* a, const double* b, double* out) {
+  so3_rotvec(quat_mul(so3_quat(a), so3_quat(b)), out);
+}
+// out = Log(Exp(a)^T Exp(b)) = vee(log(p, q)) for p = Exp(a), q = Exp(b)
+__device__ __forceinline__ void so3_between(const double* a, const double* b, double* out) {
+  Quat qa = so3_quat(a);
+  qa.x = -qa.x; qa.y = -qa.y; qa.z = -qa.z;
+  so3_rotvec(quat_mul(qa, so3_quat(b)), out);
+}
+
 // ------------------------------------------------------------------------------------------
 // Warp / block reductions.  `red` is shared scratch of IIF_RED_DOUBLES doubles split in two
 // parity halves; `parity` alternates so that one __syncthreads per reduction suffices (the two

@@ -365,13 +365,19 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
   }
   for (int f = 0; f < nfactors; ++f) {
     const iif_factor_desc& F = factors[f];
-    if (F.kind < IIF_F_PRIOR || F.kind > IIF_F_SE2_RELATIVE)
+    if (F.kind < IIF_F_PRIOR || F.kind > IIF_F_SO3_RELATIVE)
       return fail(ctx, IIF_ERR_UNSUPPORTED, "factor kind has no device residual (no CPU fallback)");
     if (F.arity < 1 || F.arity > IIF_MAX_ARITY) return fail(ctx, IIF_ERR_ARG, "factor arity out of range");
     if (F.dist < 0 || F.dist >= ndists) return fail(ctx, IIF_ERR_ARG, "factor distribution index out of range");
     if (F.nmh != 0 && F.nmh != F.arity) return fail(ctx, IIF_ERR_ARG, "multihypo length must equal arity");
     for (int v = 0; v < F.arity; ++v)
       if (F.slot[v] < 0 || F.slot[v] >= nslots) return fail(ctx, IIF_ERR_ARG, "factor slot out of range");
+    if (F.kind == IIF_F_SO3_PRIOR || F.kind == IIF_F_SO3_RELATIVE) {  // rotation-vector coordinates
+      if (F.zdim != 3) return fail(ctx, IIF_ERR_ARG, "SO(3) factors need zdim == 3");
+      for (int v = 0; v < F.arity; ++v)
+        if (slots[F.slot[v]].dim != 3 || !(slots[F.slot[v]].circ_mask & IIF_MANI_SO3))
+          return fail(ctx, IIF_ERR_ARG, "SO(3) factors need (dim 3, IIF_MANI_SO3) variables");
+    }
     if (F.kind == IIF_F_SE2_RELATIVE) {  // SpecialEuclidean(2) coordinates are (x, y, theta)
       if (F.zdim != 3 || F.arity < 2) return fail(ctx, IIF_ERR_ARG, "SE2 relative factor needs zdim == 3 and arity >= 2");
       for (int v = 0; v < F.arity; ++v)
@@ -609,7 +615,7 @@ static int pick_cluster_prod(iifb200_ctx* ctx, int grid) {
 }
 static bool is_prior_kind_h(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR ||
-         k == IIF_F_MANIFOLD_PRIOR;
+         k == IIF_F_MANIFOLD_PRIOR || k == IIF_F_SO3_PRIOR;
 }
 
 static int32_t validate_conv(iifb200_ctx* ctx, const iif_conv_op& op) {

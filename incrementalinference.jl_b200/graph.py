@@ -44,6 +44,50 @@ SpecialEuclidean2 = InferenceVariable("SpecialEuclidean2", 3, 0b100)
 SpecialOrthogonal2 = InferenceVariable("SpecialOrthogonal2", 1, 1)
 
 
+# @defVariable SO3 SpecialOrthogonal(3) (test/testSpecialOrthogonalMani.jl:84): device points are rotation vectors
+# omega = vee(log(M, eps, R)); AMP's KDE treats them as (:Euclid, :Euclid, :Euclid) (same test, :80-81), the factors,
+# entropy and statistics compose on the group (slot flag IIF_MANI_SO3)
+SpecialOrthogonal3 = InferenceVariable("SpecialOrthogonal3", 3, A.MANI_SO3)
+
+
+def so3_point_to_coords(R) -> np.ndarray:
+    """rotation matrix -> rotation vector (log at the identity, DefaultOrthogonalBasis: [X32, X13, X21])"""
+    R = np.asarray(R, dtype=np.float64)
+    c = np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)
+    th = np.arccos(c)
+    v = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    if th < 1e-9:
+        return 0.5 * v
+    if np.pi - th < 1e-6:                                        # near pi: axis from the symmetric part
+        A_ = (R + np.eye(3)) / 2.0
+        ax = np.sqrt(np.maximum(np.diag(A_), 0.0))
+        k = int(np.argmax(ax))
+        ax = A_[:, k] / ax[k]
+        return th * ax / np.linalg.norm(ax)
+    return th / (2.0 * np.sin(th)) * v
+
+
+def so3_coords_to_point(w) -> np.ndarray:
+    """rotation vector -> rotation matrix (Rodrigues)"""
+    w = np.asarray(w, dtype=np.float64)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+
+
+def so3_mean(pts) -> np.ndarray:
+    """mean(SpecialOrthogonal(3), pts) as a rotation matrix (iterated Karcher mean on rotation vectors)"""
+    Rm = so3_coords_to_point(pts[0])
+    for _ in range(20):
+        d = np.mean([so3_point_to_coords(Rm.T @ so3_coords_to_point(p)) for p in pts], axis=0)
+        Rm = Rm @ so3_coords_to_point(d)
+        if np.linalg.norm(d) < 1e-12:
+            break
+    return Rm
+
+
 def so2_point_to_coords(R) -> np.ndarray:
     R = np.asarray(R, dtype=np.float64)
     return np.array([np.arctan2(R[1, 0], R[0, 0])])
@@ -197,6 +241,12 @@ class ManifoldPrior:
 
     def __init__(self, M: InferenceVariable, p, Z):
         self.M, self.p, self.Z0 = M, np.atleast_1d(np.asarray(p, dtype=np.float64)), Z
+        if M.circ_mask & A.MANI_SO3:
+            # SpecialOrthogonal(3): retract(M, p, hat(Z)) = p Exp(z) is not coordinate-additive: p travels with the factor
+            if self.p.shape == (3, 3):
+                self.p = so3_point_to_coords(self.p)
+            self.kind, self.aux, self.Z = A.F_SO3_PRIOR, self.p, Z
+            return
         assert self.p.shape[0] == M.dim, "p must be given in coordinates (see se2_point_to_coords)"
         if isinstance(Z, MvNormal):
             self.Z = MvNormal(Z.mu + self.p, Z.cov)
@@ -224,6 +274,8 @@ class ManifoldFactor:
         self.M, self.Z = M, Z
         if M.name == "SpecialEuclidean2":
             self.kind = A.F_SE2_RELATIVE
+        elif M.circ_mask & A.MANI_SO3:
+            self.kind = A.F_SO3_RELATIVE              # q = p Exp(X) on SpecialOrthogonal(3)
         elif M.circ_mask == 0:
             self.kind = A.F_LINEAR_RELATIVE           # TranslationGroup: exp(p, X) = p + X
         elif M.dim == 1 and M.circ_mask == 1:

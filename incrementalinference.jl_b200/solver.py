@@ -466,6 +466,8 @@ class B3Driver:
                 C_ = factors[k]
                 C_.kind, C_.arity, C_.zdim, C_.dist, C_.nmh, C_.partial_mask = f.kind, f.arity, f.zdim, k, f.nmh, f.partial_mask
                 C_.solver = f.solver
+                for i in range(A.IIF_MAX_DIM):
+                    C_.aux[i] = f.aux[i]
                 C_.nullhypo, C_.inflation = f.nullhypo, f.inflation
                 for i, s in enumerate(sl):
                     C_.slot[i] = s

@@ -35,7 +35,7 @@ struct DistDesc;   kind::Int32; dim::Int32; ncomp::Int32; comp_kind::Int32; slot
 struct FactorDesc
   kind::Int32; arity::Int32; zdim::Int32; dist::Int32
   slot::NTuple{6,Int32}; nmh::Int32; partial_mask::Int32; solver::Int32; _pad::Int32
-  mh::NTuple{6,Float64}; nullhypo::Float64; inflation::Float64
+  mh::NTuple{6,Float64}; nullhypo::Float64; inflation::Float64; aux::NTuple{4,Float64}
 end
 struct SolverParamsC; spreadNH::Float64; nullSurplusAdd::Float64; inflateCycles::Int32; gibbsNiter::Int32; seed::UInt64; end
 struct PropOp
@@ -92,18 +92,23 @@ factorkind(::Prior) = Int32(1); factorkind(::LinearRelative) = Int32(2)
 factorkind(::PriorCircular) = Int32(3); factorkind(::CircularCircular) = Int32(4)
 factorkind(::EuclidDistance) = Int32(5); factorkind(::IIF.MsgPrior) = Int32(6)
 factorkind(::IIF.PartialPrior) = Int32(7)
-factorkind(::ManifoldPrior) = Int32(8); factorkind(::IIF.ManifoldPriorPartial) = Int32(8)   # p is folded into Z's mean by _lower_dist
+factorkind(f::ManifoldPrior) = _so3prior(f) ? Int32(10) : Int32(8)                             # 8: p is folded into Z's mean by _lower_dist
+factorkind(::IIF.ManifoldPriorPartial) = Int32(8)
 factorkind(f::ManifoldFactor) = _manifoldfactorkind(f.M)
 factorkind(f::Mixture) = factorkind(f.mechanics)
 _manifoldfactorkind(::Manifolds.SpecialEuclidean{2}) = Int32(9)     # hybrid tangent representation (testSpecialEuclidean2Mani.jl:14)
 _manifoldfactorkind(::Manifolds.TranslationGroup) = Int32(2)
 _manifoldfactorkind(::Manifolds.RealCircleGroup) = Int32(4)
+_manifoldfactorkind(::Manifolds.SpecialOrthogonal{3}) = Int32(11)   # rotation-vector coordinates, IIF_MANI_SO3 slots
 _manifoldfactorkind(M) = error("IIFB200: ManifoldFactor on $(M) has no device residual")
+_so3prior(f) = f isa ManifoldPrior && f.M isa Manifolds.SpecialOrthogonal{3}
+_so3coords(R) = collect(Float64, vee(SpecialOrthogonal(3), Matrix(1.0I, 3, 3), log(SpecialOrthogonal(3), Matrix(1.0I, 3, 3), Matrix(R))))
 factorkind(f) = error("IIFB200: factor $(typeof(f)) has no device residual (no CPU fallback on the b200 backend)")
 
 # circular-coordinate mask of a variable type; SpecialEuclidean(2) points ArrayPartition(t, R) travel as (t1, t2, theta)
 _isse2(T) = getManifold(T) isa Manifolds.SpecialEuclidean{2}
-circmask(T::Type{<:InferenceVariable}) = T <: IIF.Circular ? Int32(1) : (_isse2(T) ? Int32(0b100) : Int32(0))
+_isso3(T) = getManifold(T) isa Manifolds.SpecialOrthogonal{3}
+circmask(T::Type{<:InferenceVariable}) = T <: IIF.Circular ? Int32(1) : (_isse2(T) ? Int32(0b100) : (_isso3(T) ? Int32(0x100) : Int32(0)))
 circmask(v::DFGVariable) = circmask(typeof(getVariableType(v)))
 se2coords(p) = (p.x[1][1], p.x[1][2], atan(p.x[2][2, 1], p.x[2][1, 1]))           # AMP.makeCoordsFromPoint
 se2point(c)  = ArrayPartition(SA[c[1], c[2]], SA[cos(c[3]) -sin(c[3]); sin(c[3]) cos(c[3])])   # AMP.makePointFromCoords
@@ -112,9 +117,9 @@ se2point(c)  = ArrayPartition(SA[c[1], c[2]], SA[cos(c[3]) -sin(c[3]); sin(c[3])
 function _packpoints(vartype, val::AbstractVector)
   d = getDimension(vartype)
   out = Matrix{Float64}(undef, d, length(val))
-  se2 = _isse2(typeof(vartype))
+  se2 = _isse2(typeof(vartype)); so3 = _isso3(typeof(vartype))
   for (n, p) in enumerate(val)
-    c = se2 ? se2coords(p) : p
+    c = se2 ? se2coords(p) : (so3 ? _so3coords(p) : p)
     for k in 1:d
       out[k, n] = c[k]
     end
@@ -124,6 +129,7 @@ end
 function _unpackpoints(vartype, pts::AbstractMatrix{Float64})
   d = size(pts, 1)
   _isse2(typeof(vartype)) && return [se2point(view(pts, :, n)) for n in 1:size(pts, 2)]
+  _isso3(typeof(vartype)) && return [exp(SpecialOrthogonal(3), Matrix(1.0I, 3, 3), hat(SpecialOrthogonal(3), Matrix(1.0I, 3, 3), pts[:, n])) for n in 1:size(pts, 2)]
   vartype isa IIF.Circular && return [[pts[1, n]] for n in 1:size(pts, 2)]         # Vector{Vector{Float64}}
   return [SVector{d, Float64}(view(pts, :, n)) for n in 1:size(pts, 2)]
 end
@@ -199,7 +205,7 @@ function _lower_factors(dfg::AbstractDFG, factors::AbstractVector, slotof::Dict{
     vo = getVariableOrder(f)
     length(vo) <= MAX_ARITY || error("IIFB200: factor $(getLabel(f)) has more than $MAX_ARITY variables")
     shift = nothing
-    if fnc isa ManifoldPrior || fnc isa IIF.ManifoldPriorPartial
+    if (fnc isa ManifoldPrior && !_so3prior(fnc)) || fnc isa IIF.ManifoldPriorPartial
       p = fnc isa ManifoldPrior ? fnc.p : nothing        # sample = retract(M, p, hat(Z)) = p (+) Z on these groups
       shift = p === nothing ? nothing : (p isa ArrayPartition ? collect(se2coords(p)) : collect(Float64, p))
     end
@@ -214,7 +220,8 @@ function _lower_factors(dfg::AbstractDFG, factors::AbstractVector, slotof::Dict{
     push!(fdescs, FactorDesc(factorkind(fnc), Int32(length(vo)), dists[di + 1].dim, di,
                              _padtuple([slotof[l] for l in vo], MAX_ARITY, Int32), Int32(length(mh)), pmask,
                              Int32(get(ENV, "IIFB200_NUMERIC_SOLVE", "0") == "1"), Int32(0),
-                             _padtuple(mh, MAX_ARITY, Float64), ccw.nullhypo, ccw.inflation))
+                             _padtuple(mh, MAX_ARITY, Float64), ccw.nullhypo, ccw.inflation,
+                             _padtuple(_so3prior(fnc) ? _so3coords(fnc.p) : Float64[], MAX_DIM, Float64)))
   end
   return dists, dparams, fdescs, extra
 end

@@ -90,7 +90,49 @@ int64_t iifo_layout(int32_t nslots, iif_slot_desc* slots) {
 
 /* mean(M, pts, GeodesicInterpolation()) — Manifolds.jl sequential geodesic interpolation,
  * called from calcStdBasicSpread (src/services/VariableStatistics.jl:30). */
+/* SpecialOrthogonal(3) (test/testSpecialOrthogonalMani.jl:75-140): points as rotation vectors omega = vee(log(eps, R));
+ * group operations through unit quaternions.  AMP treats the coordinates as (:Euclid, :Euclid, :Euclid) (:80-81). */
+static inline int is_so3(int32_t mask) { return (mask & IIF_MANI_SO3) != 0; }
+typedef struct { double w, x, y, z; } quat;
+static quat so3_quat(const double* om) {
+  double t2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2], s, w;
+  if (t2 < 1e-16) { s = 0.5 - t2 / 48.0; w = 1.0 - t2 / 8.0; }
+  else { double t = sqrt(t2); s = sin(0.5 * t) / t; w = cos(0.5 * t); }
+  quat q = {w, s * om[0], s * om[1], s * om[2]};
+  return q;
+}
+static quat quat_mul(quat a, quat b) {
+  quat r = {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+            a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+  return r;
+}
+static void so3_rotvec(quat q, double* om) {
+  if (q.w < 0) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+  double vn = sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+  double k = vn < 1e-12 ? 2.0 : 2.0 * atan2(vn, q.w) / vn;
+  om[0] = k * q.x; om[1] = k * q.y; om[2] = k * q.z;
+}
+static void so3_compose(const double* a, const double* b, double* out) { /* Log(Exp(a) Exp(b)) = p Exp(X) */
+  so3_rotvec(quat_mul(so3_quat(a), so3_quat(b)), out);
+}
+static void so3_between(const double* a, const double* b, double* out) { /* Log(Exp(a)^T Exp(b)) = vee(log(p, q)) */
+  quat qa = so3_quat(a);
+  qa.x = -qa.x; qa.y = -qa.y; qa.z = -qa.z;
+  so3_rotvec(quat_mul(qa, so3_quat(b)), out);
+}
+
 static void geodesic_mean(const double* pts, int n, int d, int32_t cm, double* mu) {
+  if (is_so3(cm)) { /* mu <- mu Exp(Log(mu^T p_i) / (i + 1)) */
+    for (int c = 0; c < 3; ++c) mu[c] = n > 0 ? pts[c] : 0.0;
+    for (int i = 1; i < n; ++i) {
+      double dl[3], nx[3], t = 1.0 / (double)(i + 1);
+      so3_between(mu, pts + i * 3, dl);
+      for (int c = 0; c < 3; ++c) dl[c] *= t;
+      so3_compose(mu, dl, nx);
+      for (int c = 0; c < 3; ++c) mu[c] = nx[c];
+    }
+    return;
+  }
   for (int c = 0; c < d; ++c) mu[c] = n > 0 ? pts[c] : 0.0;
   for (int i = 1; i < n; ++i) {
     double t = 1.0 / (double)(i + 1);
@@ -122,11 +164,20 @@ double iifo_std_basic_spread(const double* pts, int32_t n, int32_t d, int32_t cm
   double mu[IIF_MAX_DIM];
   geodesic_mean(pts, n, d, cm, mu);
   double acc = 0;
-  for (int i = 0; i < n; ++i)
-    for (int c = 0; c < d; ++c) {
-      double v = mdiff(pts[i * d + c], mu[c], is_circ(cm, c));
-      acc += v * v;
+  if (is_so3(cm)) { /* distance(M, mu, p)^2 = |log(mu, p)|_F^2 = 2 angle^2: ASSUMPTION (Manifolds' Frobenius metric on the
+                       skew matrices); only scales the entropy spread, never the roots */
+    for (int i = 0; i < n; ++i) {
+      double dl[3];
+      so3_between(mu, pts + i * 3, dl);
+      acc += 2.0 * (dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
     }
+  } else {
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c < d; ++c) {
+        double v = mdiff(pts[i * d + c], mu[c], is_circ(cm, c));
+        acc += v * v;
+      }
+  }
   double sigma = sqrt(acc / (double)(n - 1));
   return (1e-10 < sigma) ? sigma : 1.0;
 }
@@ -280,6 +331,13 @@ int32_t iifo_residual(int32_t kind, int32_t d, int32_t cm, int32_t zdim, const d
     case IIF_F_MANIFOLD_PRIOR: /* GenericFunctions.jl:209-214  vee(M, p, log(M, p, m)) in (Euclid.., angle..) coords */
       for (int c = 0; c < zdim; ++c) res[c] = mdiff(z[c], x[c], is_circ(cm, c));
       return IIF_OK;
+    case IIF_F_SO3_RELATIVE: { /* qhat = p Exp(X); vee(log(q, qhat)) = Log(q^T qhat) */
+      if (arity != 2 || d != 3) return IIF_ERR_ARG;
+      double qh[3];
+      so3_compose(x, z, qh);
+      so3_between(x + d, qh, res);
+      return IIF_OK;
+    }
     case IIF_F_SE2_RELATIVE: { /* GenericFunctions.jl:39-44: qhat = compose(p, exp(M, eps, X)); vee(M, q, log(M, q, qhat));
                                   hybrid tangent representation (testSpecialEuclidean2Mani.jl:14): exp(eps, X) = (X_t, R(X_th)),
                                   log(q, qhat) = (t_qhat - t_q, th_qhat - th_q) */
@@ -309,6 +367,9 @@ static void solve_binary(int kind, int d, int32_t cm, const double* z, const dou
       int circ = is_circ(cm, c);
       out[c] = sf_second ? madd(other[c], z[c], circ) : madd(other[c], -z[c], circ);
     }
+  } else if (kind == IIF_F_SO3_RELATIVE) { /* q = p Exp(X); p = q Exp(-X) */
+    if (sf_second) so3_compose(other, z, out);
+    else { double nz[3] = {-z[0], -z[1], -z[2]}; so3_compose(other, nz, out); }
   } else if (kind == IIF_F_SE2_RELATIVE) {
     /* unique root of the residual above: solving q: q = p o (X_t, R(X_th)); solving p: th_p = th_q - X_th,
      * t_p = t_q - R(th_p) X_t */
@@ -414,6 +475,7 @@ static void nelder_mead_binary(int kind, int d, int32_t cm, int zdim, const doub
   const double fcen = cost_binary(kind, d, cm, zdim, z, cen, other, sf_second);
   const double* r = fcen < f[best] ? cen : S[best];
   for (int c = 0; c < n; ++c) out[c] = is_circ(cm, c) ? wrap_pi(r[c]) : r[c];     /* exp(M, eps, hat(minimizer)) */
+  if (is_so3(cm)) { double zero[3] = {0, 0, 0}, pr[3]; so3_compose(out, zero, pr); for (int c = 0; c < 3; ++c) out[c] = pr[c]; }   /* principal rotation vector */
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -680,6 +742,8 @@ int32_t iifo_deconv(const iifo_graph* g, int32_t factor, int32_t N, int32_t call
             p[k++] = is_circ(S1->circ_mask, c) ? wrap_pi(x[0][c]) : x[0][c];
         break;
       }
+      case IIF_F_SO3_PRIOR: so3_between(f->aux, x[0], p); break;
+      case IIF_F_SO3_RELATIVE: so3_between(x[0], x[1], p); break;
       case IIF_F_SE2_RELATIVE: { /* X = vee(log(eps, p^-1 o q)) */
         double sn = sin(x[0][2]), cs = cos(x[0][2]);
         double dx = x[1][0] - x[0][0], dy = x[1][1] - x[0][1];
@@ -731,7 +795,7 @@ double iifo_mmd(const double* a, int32_t na, const double* b, int32_t nb, int32_
 /* ------------------------------------------------------------------------------------ */
 static int is_prior_kind(int k) {
   return k == IIF_F_PRIOR || k == IIF_F_PRIOR_CIRCULAR || k == IIF_F_MSG_PRIOR || k == IIF_F_PARTIAL_PRIOR ||
-         k == IIF_F_MANIFOLD_PRIOR;
+         k == IIF_F_MANIFOLD_PRIOR || k == IIF_F_SO3_PRIOR;
 }
 
 static double inflate_u(const iifo_graph* g, const iif_conv_op* op, const double* uinf, int cyc,
@@ -747,6 +811,13 @@ static void add_entropy(const iifo_graph* g, const iif_conv_op* op, const double
                         double spread, int cyc) {
   for (int n = 0; n < N; ++n) {
     if (mhidx[n] != hyp) continue;
+    if (is_so3(cm)) { /* retract(M, p, get_vector(M, p, Xc)) = p Exp(Xc) */
+      double dl[3], nx[3];
+      for (int c = 0; c < 3; ++c) dl[c] = ((dimmask >> c) & 1) ? spread * (inflate_u(g, op, uinf, cyc, n, c, N, d) - 0.5) : 0.0;
+      so3_compose(dest + n * 3, dl, nx);
+      for (int c = 0; c < 3; ++c) dest[n * 3 + c] = nx[c];
+      continue;
+    }
     for (int c = 0; c < d; ++c) {
       if (!((dimmask >> c) & 1)) continue;
       double u = inflate_u(g, op, uinf, cyc, n, c, N, d);
@@ -764,13 +835,14 @@ static double spread_distance(const iifo_graph* g, const iif_factor_desc* f, int
   if (in_list(certain, nc, sfidx))                           /* :50-54 */
     return kappa * iifo_std_basic_spread(dest, N, d, Ssf->circ_mask);
   double ref[IIF_MAX_DIM], m[IIF_MAX_DIM];
-  default_mean(dest, N, d, Ssf->circ_mask, ref);             /* :71-74 */
+  if (is_so3(Ssf->circ_mask)) geodesic_mean(dest, N, d, Ssf->circ_mask, ref);
+  else default_mean(dest, N, d, Ssf->circ_mask, ref);        /* :71-74 */
   double best = 1e-2;                                        /* :90 */
   for (int v = 1; v <= f->arity; ++v) {
     const iif_slot_desc* S = &g->slots[f->slot[v - 1]];
     const double* p = (v == sfidx) ? dest : g->pts + S->pts_off;
     int np = (v == sfidx) ? N : g->npts[f->slot[v - 1]];
-    if (in_list(certain, nc, v)) geodesic_mean(p, np, S->dim, S->circ_mask, m);  /* :84-88 */
+    if (in_list(certain, nc, v) || is_so3(S->circ_mask)) geodesic_mean(p, np, S->dim, S->circ_mask, m);  /* :84-88 */
     else default_mean(p, np, S->dim, S->circ_mask, m);       /* :64-67 */
     double s = 0;
     for (int c = 0; c < d && c < S->dim; ++c) s += (ref[c] - m[c]) * (ref[c] - m[c]);
@@ -842,7 +914,9 @@ int32_t iifo_conv(const iifo_graph* g, const iif_conv_op* op, const double* meas
     int wrap = (f->kind == IIF_F_PRIOR_CIRCULAR || f->kind == IIF_F_MSG_PRIOR || f->kind == IIF_F_MANIFOLD_PRIOR);
     for (int n = 0; n < N; ++n) {
       if (mhidx[n] != 1) continue;                           /* ahmask :438 */
-      if (!f->partial_mask) {                                /* setPointsMani! :469-474 */
+      if (f->kind == IIF_F_SO3_PRIOR) {                      /* retract(M, p, hat(Z)) = p Exp(z), GenericFunctions.jl:186-195 */
+        so3_compose(f->aux, z + n * IIF_MAX_DIM, dest + n * 3);
+      } else if (!f->partial_mask) {                         /* setPointsMani! :469-474 */
         for (int c = 0; c < d; ++c) {
           double v = z[n * IIF_MAX_DIM + c];
           dest[n * d + c] = (wrap && is_circ(cm, c)) ? wrap_pi(v) : v;

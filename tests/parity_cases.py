@@ -251,6 +251,25 @@ def conv_cases():
                                        dict(factor=fr2, sfidx=1, N=N, call_id=132)], None
 
 
+    # 16. SpecialOrthogonal(3) (test/testSpecialOrthogonalMani.jl:75-140): rotation-vector coordinates; prior
+    # p Exp(z), relative q = p Exp(X) solved both ways, null-hypothesis entropy on the manifold, and the relative factor
+    # through the numeric solve
+    P = Problem()
+    so3 = G.SpecialOrthogonal3
+    w0 = R.normal(0, 0.4, (N, 3)) + [0.3, -0.2, 0.5]
+    w1 = R.normal(0, 0.4, (N, 3)) + [-0.4, 0.6, 0.1]
+    r0, r1 = P.slot(so3, N, w0), P.slot(so3, N, w1)
+    fp3 = P.factor(G.ManifoldPrior(so3, [0.2, -0.1, 0.4], G.MvNormal([0, 0, 0], np.diag([0.01, 0.02, 0.01]))), [r0])
+    fr3 = P.factor(G.ManifoldFactor(so3, G.MvNormal([0.3, 0.1, -0.2], np.diag([0.01, 0.01, 0.02]))), [r0, r1])
+    fn3 = P.factor(G.ManifoldFactor(so3, G.MvNormal([0.3, 0.1, -0.2], np.diag([0.01, 0.01, 0.02]))), [r0, r1], nullhypo=0.3)
+    mfn = G.ManifoldFactor(so3, G.MvNormal([0.3, 0.1, -0.2], np.diag([0.01, 0.01, 0.02])))
+    mfn.numeric = True
+    fnm3 = P.factor(mfn, [r0, r1])
+    yield "so3", P.freeze(), [dict(factor=fp3, sfidx=1, N=N, call_id=140), dict(factor=fr3, sfidx=2, N=N, call_id=141),
+                              dict(factor=fr3, sfidx=1, N=N, call_id=142), dict(factor=fn3, sfidx=2, N=N, call_id=143),
+                              dict(factor=fnm3, sfidx=2, N=N, call_id=144)], None
+
+
 def wrap(a):
     return (np.asarray(a) + np.pi) % (2 * np.pi) - np.pi
 

@@ -387,3 +387,32 @@ def test_independent_sessions_in_one_pass(built):
         for k in (0, n // 2, n - 1):
             p = _pts(fg, f"s{b}x{k}")
             assert abs(p.mean() - (10.0 * b + k)) < 0.35 + 0.15 * np.sqrt(k + 1.0), (b, k, p.mean())
+
+
+def test_so3_solveTree_testSpecialOrthogonalMani(built):
+    """SURVEY 8f-4, test/testSpecialOrthogonalMani.jl:75-140: SpecialOrthogonal(3) ManifoldPrior at the identity
+    (MvNormal([0.01, 0.01, 0.01])) and ManifoldFactor MvNormal([0.01, 0.01, 0.01], [0.01, 0.01, 0.01]): mean(M, pts)
+    within atol 0.01 of I resp. Exp([0.01, 0.01, 0.01]) after doautoinit! and after solveTree!; all points valid."""
+    so3 = G.SpecialOrthogonal3
+    fg = G.initfg(G.SolverParams(seed=23))
+    G.addVariable(fg, "x0", so3)
+    G.addFactor(fg, ["x0"], G.ManifoldPrior(so3, np.eye(3), G.MvNormal([0, 0, 0], np.diag([1e-4] * 3))))
+    SV.doautoinit(fg, "x0")
+    assert np.abs(G.so3_mean(fg.variables["x0"].val) - np.eye(3)).max() < 0.01
+    G.addVariable(fg, "x1", so3)
+    G.addFactor(fg, ["x0", "x1"], G.ManifoldFactor(so3, G.MvNormal([0.01, 0.01, 0.01], np.diag([1e-4] * 3))))
+    SV.doautoinit(fg, "x1")
+    want = np.array([[0.9999, -0.00995, 0.01005], [0.01005, 0.9999, -0.00995], [-0.00995, 0.01005, 0.9999]])
+    assert np.abs(G.so3_mean(fg.variables["x1"].val) - want).max() < 0.01
+    SV.solveTree(fg)
+    assert np.abs(G.so3_mean(fg.variables["x0"].val) - np.eye(3)).max() < 0.01
+    assert np.abs(G.so3_mean(fg.variables["x1"].val) - want).max() < 0.01
+    for l in ("x0", "x1"):
+        p = fg.variables[l].val
+        assert p.shape == (100, 3) and (np.linalg.norm(p, axis=1) <= np.pi).all()
+    # a larger rotation chain: x2 = x1 Exp((0.8, -0.5, 1.1)) keeps composing on the group, not in coordinates
+    G.addVariable(fg, "x2", so3)
+    G.addFactor(fg, ["x1", "x2"], G.ManifoldFactor(so3, G.MvNormal([0.8, -0.5, 1.1], np.diag([1e-4] * 3))))
+    SV.solveTree(fg)
+    want2 = want @ G.so3_coords_to_point([0.8, -0.5, 1.1])
+    assert np.abs(G.so3_mean(fg.variables["x2"].val) - want2).max() < 0.03

@@ -573,6 +573,55 @@ def test_special_orthogonal2_testSpecialOrthogonalMani():
     assert np.cos(t1).mean() < -0.9                                   # x1 sits at +-pi (the seam)
 
 
+def test_so3_known_answers_and_bands_testSpecialOrthogonalMani():
+    """SURVEY 8f-4, test/testSpecialOrthogonalMani.jl:75-140 (SpecialOrthogonal(3)): proposals of the relative factor are
+    roots of vee(log(q, p Exp(X))) (checked with rotation MATRICES built by numpy, independent of the oracle's
+    quaternions); ManifoldPrior at the identity with MvNormal([0.01, 0.01, 0.01]) gives mean(M, pts) ~ I (atol 0.01);
+    ManifoldFactor MvNormal([0.01, 0.01, 0.01], [0.01, 0.01, 0.01]) puts x1 at Exp([0.01, 0.01, 0.01]) before and after
+    solveTree!; every point is a valid rotation (|omega| <= pi)."""
+    name, P, specs, _ = [c for c in PC.conv_cases() if c[0] == "so3"][0]
+    orc = P.oracle()
+    ops = CP.make_conv_ops(specs)
+    w0, w1 = P.arena.get(0)[0], P.arena.get(1)[0]
+    e2m = G.so3_coords_to_point
+    # forward: q = p Exp(z) => Exp(w0)^T q is a rotation of angle |z| ~ |(0.3, 0.1, -0.2)|; backward likewise
+    q = orc.conv(ops[1])[0]
+    z = np.array([G.so3_point_to_coords(e2m(w0[n]).T @ e2m(q[n])) for n in range(len(q))])
+    assert np.abs(z.mean(axis=0) - [0.3, 0.1, -0.2]).max() < 0.05 and np.abs(z.std(axis=0) - [0.1, 0.1, 0.1414]).max() < 0.04
+    p = orc.conv(ops[2])[0]
+    z = np.array([G.so3_point_to_coords(e2m(p[n]).T @ e2m(w1[n])) for n in range(len(p))])
+    assert np.abs(z.mean(axis=0) - [0.3, 0.1, -0.2]).max() < 0.05
+    # prior: p Exp(z) around the point with rotation vector (0.2, -0.1, 0.4)
+    pr = orc.conv(ops[0])[0]
+    z = np.array([G.so3_point_to_coords(e2m([0.2, -0.1, 0.4]).T @ e2m(pr[n])) for n in range(len(pr))])
+    assert np.abs(z.mean(axis=0)).max() < 0.05 and np.abs(z.std(axis=0) - [0.1, 0.1414, 0.1]).max() < 0.04
+    # null hypothesis: ~30 % of the particles keep their (entropy-spread) value, the rest are roots
+    qn, _, _, lab, _ = orc.conv(ops[3])
+    assert 10 < (lab == 0).sum() < 55
+    # numeric solve lands on the closed-form root within Nelder-Mead's accuracy
+    qm = orc.conv(ops[4])[0]
+    ref = P.oracle().conv(CP.make_conv_ops([dict(specs[4], factor=specs[1]["factor"])])[0])[0]
+    assert np.abs(qm - ref).max() < 5e-3 and np.abs(qm - ref).max() > 0
+    assert (np.linalg.norm(q, axis=1) <= np.pi + 1e-12).all()
+    # the reference's test graph, 6 seeds
+    so3 = G.SpecialOrthogonal3
+    for seed in range(6):
+        fg = G.initfg(G.SolverParams(seed=seed, graphinit=False))
+        G.addVariable(fg, "x0", so3)
+        G.addFactor(fg, ["x0"], G.ManifoldPrior(so3, np.eye(3), G.MvNormal([0, 0, 0], np.diag([1e-4] * 3))))
+        PC.oracle_initAll(fg)
+        assert np.abs(G.so3_mean(fg.variables["x0"].val) - np.eye(3)).max() < 0.01
+        G.addVariable(fg, "x1", so3)
+        G.addFactor(fg, ["x0", "x1"], G.ManifoldFactor(so3, G.MvNormal([0.01, 0.01, 0.01], np.diag([1e-4] * 3))))
+        PC.oracle_initAll(fg)
+        want = np.array([[0.9999, -0.00995, 0.01005], [0.01005, 0.9999, -0.00995], [-0.00995, 0.01005, 0.9999]])
+        assert np.abs(G.so3_mean(fg.variables["x1"].val) - want).max() < 0.01
+        PC.oracle_solveTree(fg)
+        assert np.abs(G.so3_mean(fg.variables["x0"].val) - np.eye(3)).max() < 0.01
+        assert np.abs(G.so3_mean(fg.variables["x1"].val) - want).max() < 0.01
+        assert (np.linalg.norm(fg.variables["x1"].val, axis=1) <= np.pi).all()
+
+
 def test_sample_table_distribution():
     """any host-side distribution as a measurement (sampleFactor! = rand(Z), SolverUtilities.jl:50-76): Rayleigh(2)
     range noise through a prior and a relative factor keeps its mean sigma sqrt(pi/2) and its skew"""

@@ -48,7 +48,7 @@ def _factor_tuple(frozen, i):
         n = {A.D_NORMAL: 2, A.D_UNIFORM: 2}.get(D.kind, D.dim + D.dim * D.dim)
         dist = (D.kind, D.dim, tuple(prm[D.poff:D.poff + n]))
     return (f.kind, f.arity, f.zdim, tuple(f.slot[k] for k in range(f.arity)), f.nmh, f.partial_mask, f.solver,
-            tuple(f.mh[k] for k in range(f.nmh)), f.nullhypo, f.inflation, dist)
+            tuple(f.mh[k] for k in range(f.nmh)), f.nullhypo, f.inflation, tuple(f.aux), dist)
 
 
 @pytest.mark.parametrize("case", list(graphs()), ids=lambda c: c[0])
