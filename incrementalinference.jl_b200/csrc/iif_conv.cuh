@@ -330,10 +330,6 @@ __device__ __forceinline__ void solve_binary(int kind, int d, int32_t cm, const 
                                              bool sf_second, const double* u0, double* out) {
   if (kind == IIF_F_LINEAR_RELATIVE || kind == IIF_F_CIRCULAR_CIRCULAR) {
     for (int c = 0; c < d; ++c) out[c] = madd(other[c], sf_second ? z[c] : -z[c], is_circ(cm, c));
-  } else if (kind == IIF_F_SO3_RELATIVE) {
-    // ManifoldFactor{SpecialOrthogonal(3)}: q = p Exp(X); p = q Exp(X)^-1 = q Exp(-X)
-    if (sf_second) so3_compose(other, z, out);
-    else { const double nz_[3] = {-z[0], -z[1], -z[2]}; so3_compose(other, nz_, out); }
   } else if (kind == IIF_F_SE2_RELATIVE) {
     // ManifoldFactor{SpecialEuclidean(2)}: q = p o exp(eps, X)  (GenericFunctions.jl:39-44, hybrid tangent
     // representation: exp(eps, X) = (X_t, R(X_theta))).  Solving q: theta_q = theta_p + X_theta,
@@ -477,8 +473,41 @@ __device__ __forceinline__ bool is_prior_kind(int k) {
          k == IIF_F_MANIFOLD_PRIOR || k == IIF_F_SO3_PRIOR;
 }
 
-__global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
-iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double* __restrict__ meas,
+// Rare per-particle paths (SpecialOrthogonal(3) composition, the numeric Nelder-Mead solve), out of line and with BY-VALUE
+// arguments so that the per-particle state of the caller stays in registers.
+struct Vec4 { double v[IIF_MAX_DIM]; };
+__device__ __forceinline__ Vec4 pack4(const double* a) { Vec4 r = {{a[0], a[1], a[2], a[3]}}; return r; }
+__device__ __noinline__ Vec4 so3_compose_v(Vec4 a, Vec4 b) {
+  Vec4 r = {{0, 0, 0, 0}};
+  so3_compose(a.v, b.v, r.v);
+  return r;
+}
+__device__ __noinline__ Vec4 solve_rare(int kind, int d, int32_t cm, Vec4 z, Vec4 other, bool sf_second, Vec4 u0, bool numeric) {
+  Vec4 r = {{0, 0, 0, 0}};
+  if (numeric) nelder_mead_binary(kind, d, cm, z.v, other.v, sf_second, u0.v, r.v);
+  else if (kind == IIF_F_SO3_RELATIVE) {  // ManifoldFactor{SpecialOrthogonal(3)}: q = p Exp(X); p = q Exp(X)^-1 = q Exp(-X)
+    if (sf_second) so3_compose(other.v, z.v, r.v);
+    else { const double nz_[3] = {-z.v[0], -z.v[1], -z.v[2]}; so3_compose(other.v, nz_, r.v); }
+  } else solve_binary(kind, d, cm, z.v, other.v, sf_second, u0.v, r.v);
+  return r;
+}
+// does this convolution need the RARE variant of the kernel?  (host and device agree through this one predicate)
+__host__ __device__ inline bool conv_needs_rare(const iif_factor_desc& F, const iif_slot_desc* slots, int sfidx) {
+  if (F.kind == IIF_F_SO3_PRIOR || F.kind == IIF_F_SO3_RELATIVE) return true;
+  for (int v = 0; v < F.arity; ++v)
+    if (slots[F.slot[v]].circ_mask & IIF_MANI_SO3) return true;
+  const int d = slots[F.slot[sfidx - 1]].dim;
+  const bool relative = !(F.kind == IIF_F_PRIOR || F.kind == IIF_F_PRIOR_CIRCULAR || F.kind == IIF_F_MSG_PRIOR ||
+                          F.kind == IIF_F_PARTIAL_PRIOR || F.kind == IIF_F_MANIFOLD_PRIOR);
+  return relative && d > 1 && (F.solver == 1 || F.kind == IIF_F_EUCLID_DISTANCE);
+}
+
+// The kernel exists in two variants.  RARE = false is the hot one: everything the common factors need and nothing
+// else, so the per-particle phase keeps its state in registers (the SO(3) / Nelder-Mead paths cost the common kernel
+// 8 % when they were compiled into it).  RARE = true adds those paths; the host picks the variant per launch
+// (conv_needs_rare), and a task that needs them but lands in the lean kernel fails with IIF_ERR_STATE.
+template <bool RARE>
+__device__ __forceinline__ void conv_body(DeviceGraph g, const ConvTask* __restrict__ tasks, const double* __restrict__ meas,
                 const int32_t* __restrict__ mhidx_in, const double* __restrict__ uinf,
                 const TreeStruct* __restrict__ trees) {
   // dynamic shared memory, sized by the host for the launch's largest N (conv_smem_bytes)
@@ -549,6 +578,7 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
     if (R.status != IIF_OK) s_status = R.status;
     for (int v = 0; v < f.arity; ++v)
       if (v + 1 != sfidx && g.npts[f.slot[v]] > N) s_status = IIF_ERR_ARG;
+    if (!RARE && conv_needs_rare(f, g.slots, sfidx)) s_status = IIF_ERR_STATE;   // host picked the wrong variant
   }
   __syncthreads();
   int label = 1;
@@ -570,11 +600,11 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   // addEntropyOnManifold! on this thread's particle (EvalFactor.jl:95-132)
   auto add_entropy = [&](int hyp, int32_t dimmask, double spread, int cyc) {
     if (active && label == hyp) {
-      if (is_so3(cm)) {  // retract(M, p, get_vector(M, p, Xc)) = p Exp(Xc)
-        double dl[3], nx[3];
-        for (int c = 0; c < 3; ++c) dl[c] = ((dimmask >> c) & 1) ? spread * (inflate_u(cyc, c) - 0.5) : 0.0;
-        so3_compose(my, dl, nx);
-        for (int c = 0; c < 3; ++c) { my[c] = nx[c]; dest[n * d + c] = nx[c]; }
+      if (RARE && is_so3(cm)) {  // retract(M, p, get_vector(M, p, Xc)) = p Exp(Xc)
+        Vec4 dl = {{0, 0, 0, 0}};
+        for (int c = 0; c < 3; ++c) dl.v[c] = ((dimmask >> c) & 1) ? spread * (inflate_u(cyc, c) - 0.5) : 0.0;
+        const Vec4 nx = so3_compose_v(pack4(my), dl);
+        for (int c = 0; c < 3; ++c) { my[c] = nx.v[c]; dest[n * d + c] = nx.v[c]; }
       } else {
         for (int c = 0; c < d; ++c) {
           if (!((dimmask >> c) & 1)) continue;
@@ -591,10 +621,9 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
       double spreadDist = g.sp->spreadNH * block_std_basic_spread(dest, N, d, cm, mu_s, red, parity);  // :464
       const bool wrap = (f.kind == IIF_F_PRIOR_CIRCULAR || f.kind == IIF_F_MSG_PRIOR || f.kind == IIF_F_MANIFOLD_PRIOR);
       if (active && label == 1) {
-        if (f.kind == IIF_F_SO3_PRIOR) {
-          double nx[3];
-          so3_compose(f.aux, z, nx);     // retract(M, p, hat(Z)) = p Exp(z)
-          for (int c = 0; c < 3; ++c) my[c] = nx[c];
+        if (RARE && f.kind == IIF_F_SO3_PRIOR) {
+          const Vec4 nx = so3_compose_v(pack4(f.aux), pack4(z));     // retract(M, p, hat(Z)) = p Exp(z)
+          for (int c = 0; c < 3; ++c) my[c] = nx.v[c];
         } else if (!f.partial_mask) {
           for (int c = 0; c < d; ++c) my[c] = (wrap && is_circ(cm, c)) ? wrap_pi(z[c]) : z[c];
         } else {
@@ -652,8 +681,11 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
               double r[IIF_MAX_DIM];
               // islen1 (1-D: BFGS in the reference) keeps the closed form; in several dimensions EuclidDistance (a ring of
               // roots) and factors that ask for it run the restated Nelder-Mead from the inflated start
-              if (d > 1 && (f.solver == 1 || f.kind == IIF_F_EUCLID_DISTANCE)) nelder_mead_binary(f.kind, d, cm, z, o, sf_second, my, r);
-              else solve_binary(f.kind, d, cm, z, o, sf_second, my, r);
+              if (RARE) {
+                const bool numeric = d > 1 && (f.solver == 1 || f.kind == IIF_F_EUCLID_DISTANCE);
+                const Vec4 r4 = solve_rare(f.kind, d, cm, pack4(z), pack4(o), sf_second, pack4(my), numeric);
+                for (int c = 0; c < IIF_MAX_DIM; ++c) r[c] = r4.v[c];
+              } else solve_binary(f.kind, d, cm, z, o, sf_second, my, r);
               bool bad = false;
               for (int c = 0; c < d; ++c) bad |= isnan(r[c]);
               if (bad) nnan++;  // NumericalCalculations.jl:348-351: particle left unchanged
@@ -712,4 +744,15 @@ iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double*
   }
   IIF_PHASE(13);
   IIF_PHASE_FLUSH();
+}
+
+__global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
+iif_conv_kernel(DeviceGraph g, const ConvTask* __restrict__ tasks, const double* __restrict__ meas,
+                const int32_t* __restrict__ mhidx_in, const double* __restrict__ uinf, const TreeStruct* __restrict__ trees) {
+  conv_body<false>(g, tasks, meas, mhidx_in, uinf, trees);
+}
+__global__ void __launch_bounds__(IIF_MAX_THREADS, 1)
+iif_conv_kernel_rare(DeviceGraph g, const ConvTask* __restrict__ tasks, const double* __restrict__ meas,
+                     const int32_t* __restrict__ mhidx_in, const double* __restrict__ uinf, const TreeStruct* __restrict__ trees) {
+  conv_body<true>(g, tasks, meas, mhidx_in, uinf, trees);
 }

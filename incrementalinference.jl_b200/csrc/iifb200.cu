@@ -46,6 +46,7 @@ struct Seg {
   int push0 = 0, npush = 0, wait0 = 0, nwait = 0;   // peer messages: waits run first, pushes last
 };
 struct Wave {
+  bool conv_rare = false;  // some convolution of the wave needs the kernel variant with the SO(3) / Nelder-Mead paths
   std::vector<Seg> segs;
   int nconv = 0, nprod = 0, ncopy = 0, ndcv = 0;  // wave totals: CTA size / cluster choice follow the whole wave's width
   size_t prod_smem = 0, conv_smem = 0, dcv_smem = 0;
@@ -262,6 +263,9 @@ int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
   if ((e = cudaFuncSetAttribute(iif_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ctx->max_smem_optin - 4096)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(conv smem)", e);
+  if ((e = cudaFuncSetAttribute(iif_conv_kernel_rare, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(conv smem, rare variant)", e);
   if ((e = cudaFuncSetAttribute(iif_bandwidth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ctx->max_smem_optin - 4096)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(bandwidth smem)", e);
@@ -690,7 +694,9 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
   }
   CKC(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ConvTask) * K, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaEventRecord(ctx->ev0, ctx->stream));
-  launch_k(iif_conv_kernel, K, pick_cluster(ctx, K), pick_threads(ctx, K, cmaxN), csmem, ctx->stream, ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
+  bool rare = false;
+  for (int k = 0; k < K; ++k) rare |= conv_needs_rare(ctx->factors[ops[k].factor], ctx->slots.data(), ops[k].sfidx);
+  launch_k(rare ? iif_conv_kernel_rare : iif_conv_kernel, K, pick_cluster(ctx, K), pick_threads(ctx, K, cmaxN), csmem, ctx->stream, ctx->dg, d_tasks, d_meas, d_labin, d_uinf, ctx->d_trees);
   CKC(cudaGetLastError());
   CKC(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -1133,6 +1139,7 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
           c.out_status = s->d_status + cidx[o.a] + f;
           // one full-dimension factor: the convolution writes the posterior itself, no product task
           c.out_slot = (P.nfactors == 1 && F.partial_mask == 0) ? P.out_slot : -1;
+          W.conv_rare |= conv_needs_rare(F, ctx->slots.data(), c.op.sfidx);
           ct.push_back(c);
           t.mask[f] = F.partial_mask;
         }
@@ -1219,7 +1226,7 @@ static int enqueue_seg(iifb200_ctx* ctx, Schedule* s, const Wave& W, const Seg& 
     ++k;
   }
   if (G.nconv) {
-    launch_k(iif_conv_kernel, G.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, st, ctx->dg, s->d_conv + G.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+    launch_k(W.conv_rare ? iif_conv_kernel_rare : iif_conv_kernel, G.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, st, ctx->dg, s->d_conv + G.conv0, nullptr, nullptr, nullptr, ctx->d_trees);
     ++k;
   }
   if (G.nprod) {
@@ -1361,7 +1368,7 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
     }
     if (W.nconv) {
       mark();
-      launch_k(iif_conv_kernel, W.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream, ctx->dg, s->d_conv + W.segs[0].conv0, nullptr, nullptr, nullptr, ctx->d_trees);
+      launch_k(W.conv_rare ? iif_conv_kernel_rare : iif_conv_kernel, W.nconv, pick_cluster(ctx, W.nconv), pick_threads(ctx, W.nconv, W.maxN), W.conv_smem, ctx->stream, ctx->dg, s->d_conv + W.segs[0].conv0, nullptr, nullptr, nullptr, ctx->d_trees);
       mark(); kind.push_back(0); blocks[0] += W.nconv;
     }
     if (W.nprod) {
