@@ -378,6 +378,16 @@ typedef struct {
   const iif_dist_desc* dists;
   int32_t nparams;
   const double* dparams;
+  /* only read when iif_plan_opts.useMsgLikelihoods != 0 (differential separator messages, TreeMessageUtils.jl:279-446);
+   * may be NULL otherwise.  Type ids are the caller's own numbering of factor / variable TYPES (e.g. an index into a
+   * table of type names): the joint-message rules compare them only for equality. */
+  const int32_t* factor_type;           /* per factor: id of typeof(getFactorType(fct)) */
+  const int32_t* var_type;              /* per variable: id of its variable type */
+  const int32_t* var_relative_kind;     /* per variable type T: iif_factor_kind of selectFactorType(T, T) (DefaultNodeTypes.jl:
+                                           12-31: Position{N} -> LinearRelative{N}, Circular -> CircularCircular) or 0 */
+  const int32_t* var_relative_type;     /* ... and that factor type's id in the numbering of `factor_type` */
+  int32_t msgprior_type;                /* type id of MsgPrior in the numbering of `factor_type` */
+  int32_t _pad;
 } iif_graph_desc;
 
 /* Bayes tree in CSR form; cliques are numbered parents first (parent id < child id, roots have parent -1), children of a
@@ -401,7 +411,8 @@ typedef struct {
   int32_t downsolve;          /* SolverParams.downsolve */
   int32_t lanes;              /* parallel graph branches for independent sub-trees (0 = none, <= 8) */
   int32_t forward_copies;     /* collapse separator copy chains */
-  int32_t useMsgLikelihoods;  /* must be 0 here (differential messages are lowered by the host mirror) */
+  int32_t useMsgLikelihoods;  /* SolverParams.useMsgLikelihoods: joint up messages (differentials as IIF_S_DECONV ops + one
+                                 MsgPrior per class), kept for the down solve (CliqueStateMachine.jl:825-834) */
   int32_t call_base;          /* first Philox call id of the pass (prop k uses call_base + 16 k) */
   double inflation;           /* SolverParams.inflation, for the message priors */
 } iif_plan_opts;
@@ -411,12 +422,14 @@ int32_t iifb200_plan_tree(const iif_graph_desc* graph, const iif_tree_desc* tree
                           iifb200_plan** plan_out);
 const char* iifb200_plan_error(void); /* message of the last failed iifb200_plan_tree on this thread */
 void iifb200_plan_free(iifb200_plan* plan);
-/* counts[16]: nslots, nfactors, ndists, nparams, nprops, nops, nwaves, n_conv, n_prod, n_msgs, up_last_wave, nvars, 0.. */
+/* counts[16]: nslots, nfactors, ndists, nparams, nprops, nops, nwaves, n_conv, n_prod, n_msgs, up_last_wave, nvars,
+ * ndeconvs, 0.. */
 int32_t iifb200_plan_counts(const iifb200_plan* plan, int32_t* counts);
 /* copies the plan's tables into caller arrays sized from iifb200_plan_counts (any pointer may be NULL) */
 int32_t iifb200_plan_export(const iifb200_plan* plan, iif_slot_desc* slots, iif_factor_desc* factors,
                             iif_dist_desc* dists, double* dparams, iif_prop_op* props, iif_sched_op* ops,
                             int32_t* wave_off /* nwaves + 1 */);
+int32_t iifb200_plan_export_deconvs(const iifb200_plan* plan, iif_deconv_op* deconvs /* counts[12] */);
 /* iifb200_set_graph + iifb200_schedule_build of a plan in one call; beliefs of the graph variables then go to slots
  * 0..nvars-1 (iifb200_upload_slots), iifb200_schedule_run solves, iifb200_download_slots reads the posteriors. */
 int32_t iifb200_plan_upload(iifb200_ctx* ctx, const iifb200_plan* plan, const iif_solver_params* sp,

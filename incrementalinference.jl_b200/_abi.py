@@ -83,7 +83,10 @@ class XferOp(C.Structure):
 class GraphDesc(C.Structure):
     _fields_ = [("nvars", C.c_int32), ("vars", C.POINTER(SlotDesc)), ("nfactors", C.c_int32),
                 ("factors", C.POINTER(FactorDesc)), ("ndists", C.c_int32), ("dists", C.POINTER(DistDesc)),
-                ("nparams", C.c_int32), ("dparams", C.POINTER(C.c_double))]
+                ("nparams", C.c_int32), ("dparams", C.POINTER(C.c_double)),
+                ("factor_type", C.POINTER(C.c_int32)), ("var_type", C.POINTER(C.c_int32)),
+                ("var_relative_kind", C.POINTER(C.c_int32)), ("var_relative_type", C.POINTER(C.c_int32)),
+                ("msgprior_type", C.c_int32), ("_pad", C.c_int32)]
 
 
 _ipt = C.POINTER(C.c_int32)
@@ -149,6 +152,7 @@ SYMBOLS = {
     "iifb200_plan_free": (None, [_vp]),
     "iifb200_plan_counts": (C.c_int32, [_vp, _ip]),
     "iifb200_plan_export": (C.c_int32, [_vp, P(SlotDesc), P(FactorDesc), P(DistDesc), _dp, P(PropOp), P(SchedOp), _ip]),
+    "iifb200_plan_export_deconvs": (C.c_int32, [_vp, P(DeconvOp)]),
     "iifb200_plan_upload": (C.c_int32, [_vp, _vp, P(SolverParamsC), _vp, _ip]),
     "iifb200_sync": (C.c_int32, [_vp]),
     "iifb200_launch_count": (C.c_int64, [_vp]),

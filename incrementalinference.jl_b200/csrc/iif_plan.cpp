@@ -27,6 +27,7 @@ struct iifb200_plan {
   std::vector<iif_dist_desc> dists;
   std::vector<double> dparams;
   std::vector<iif_prop_op> props;
+  std::vector<iif_deconv_op> deconvs; // IIF_S_DECONV ops (useMsgLikelihoods)
   std::vector<iif_sched_op> ops;      // sorted by wave
   std::vector<int32_t> wave_off;
   int32_t n_conv = 0, n_prod = 0, n_msgs = 0, up_last_wave = 0, nvars = 0;
@@ -35,6 +36,8 @@ struct iifb200_plan {
 static thread_local std::string g_plan_error;
 
 namespace {
+
+bool has(const std::vector<int>& v, int x);
 
 struct Op {
   int kind, a, b, clique;
@@ -47,7 +50,45 @@ struct Inst {  // one factor instance of a clique sub-graph
   std::vector<int> rd;
   int fi;
   bool mh;
+  int type = -1;        // caller's factor-type id (joint-message rules compare types for equality only)
+  bool prior = false;
+  int tag = 0;          // 0 potential, 1 UPWARD_COMMON message prior, 2 differential
 };
+struct Relative {       // one differential of a joint up message (addLikelihoodsDifferentialCHILD!, TreeMessageUtils.jl:279-335)
+  int v1, v2, kind, type, slot, zdim;
+};
+struct UpMsg {
+  std::vector<Relative> relatives;
+  std::vector<std::pair<int, int>> priors;   // (variable, source slot)
+  bool hasPriors = false;
+};
+
+// findShortestPathDijkstra on the bipartite variable / factor graph of a clique sub-graph (unit weights => BFS, neighbours
+// in insertion order): the factor types along the path; `found` false when the variables are not connected
+std::vector<int> path_types(const std::vector<Inst>& inst, int src, int dst, int only_type, bool& found) {
+  found = true;
+  if (src == dst) return {};
+  std::unordered_map<int, std::pair<int, int>> prev;   // variable -> (previous variable, instance)
+  prev[src] = {-1, -1};
+  std::vector<int> frontier{src};
+  while (!frontier.empty()) {
+    std::vector<int> nxt;
+    for (int u : frontier)
+      for (size_t k = 0; k < inst.size(); ++k) {
+        const Inst& e = inst[k];
+        if (!has(e.vars, u) || (only_type >= 0 && e.type != only_type)) continue;
+        for (int w : e.vars)
+          if (!prev.count(w)) { prev[w] = {u, (int)k}; nxt.push_back(w); }
+      }
+    if (prev.count(dst)) break;
+    frontier = nxt;
+  }
+  if (!prev.count(dst)) { found = false; return {}; }
+  std::vector<int> types;
+  for (int w = dst; prev[w].first >= 0; w = prev[w].first) types.push_back(inst[prev[w].second].type);
+  std::reverse(types.begin(), types.end());
+  return types;
+}
 
 std::vector<int> csr(const int32_t* off, const int32_t* val, int i) {
   return std::vector<int>(val + off[i], val + off[i + 1]);
@@ -160,9 +201,9 @@ int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const
   auto fail = [&](int32_t code, const std::string& msg) { g_plan_error = msg; return code; };
   if (!g || !t || !o || !out) return fail(IIF_ERR_ARG, "plan_tree: null argument");
   *out = nullptr;
-  if (o->useMsgLikelihoods)
-    return fail(IIF_ERR_UNSUPPORTED, "plan_tree: useMsgLikelihoods = true plans are lowered by the host mirror (tree.compile_solve) "
-                                     "and submitted through iifb200_schedule_build_ex");
+  const bool uml = o->useMsgLikelihoods != 0;
+  if (uml && (!g->factor_type || !g->var_type || !g->var_relative_kind || !g->var_relative_type))
+    return fail(IIF_ERR_ARG, "plan_tree: useMsgLikelihoods needs the type tables of iif_graph_desc");
   const int nv = g->nvars, nf = g->nfactors, ncl = t->ncliques, N = o->N;
   if (nv < 1 || ncl < 1 || N < 2 || N > IIF_MAX_POINTS) return fail(IIF_ERR_ARG, "plan_tree: bad sizes");
   for (int f = 0; f < nf; ++f) {
@@ -186,6 +227,11 @@ int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const
     return (int)P->slots.size() - 1;
   };
   for (int v = 0; v < nv; ++v) add_slot(v);   // main graph: slot v == variable v
+  std::unordered_map<int, UpMsg> upmsg;                 // child clique -> joint up message
+  std::unordered_map<int, std::vector<Inst>> kept_diffs; // clique -> differentials kept for the down solve
+  // selectFactorType(T1, T2): the default relative factor between two variables of one type (DefaultNodeTypes.jl:12-31)
+  auto sel_kind = [&](int a, int b) { return (g->var_type[a] == g->var_type[b]) ? g->var_relative_kind[a] : 0; };
+  auto sel_type = [&](int a, int b) { return (g->var_type[a] == g->var_type[b] && g->var_relative_kind[a]) ? g->var_relative_type[a] : -1; };
   // clique-local copies
   std::vector<std::vector<int>> fr(ncl), sp(ncl), allv(ncl), children(ncl);
   std::vector<std::unordered_map<int, int>> cslot(ncl);
@@ -300,10 +346,58 @@ int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const
       }
       e.fi = fac_instance(f, e.rd);
       e.mh = F.nmh != 0;
+      e.type = uml ? g->factor_type[f] : -1;
+      e.prior = F.arity == 1;
       inst.push_back(e);
     }
+    auto add_msg_prior = [&](int s, int src) {
+      auto it = cslot[cid].find(s);
+      iif_dist_desc D;
+      memset(&D, 0, sizeof(D));
+      D.kind = IIF_D_KDE; D.dim = g->vars[s].dim; D.slot = src; D.poff = (int)P->dparams.size();
+      P->dists.push_back(D);
+      iif_factor_desc F;
+      memset(&F, 0, sizeof(F));
+      F.kind = IIF_F_MSG_PRIOR; F.arity = 1; F.zdim = D.dim; F.dist = (int)P->dists.size() - 1;
+      F.slot[0] = it->second; F.nullhypo = 0.0; F.inflation = o->inflation;
+      P->factors.push_back(F);
+      Inst e;
+      e.vars = {s}; e.rd = {it->second, src}; e.fi = (int)P->factors.size() - 1; e.mh = false;
+      e.type = uml ? g->msgprior_type : -1; e.prior = true; e.tag = 1;
+      inst.push_back(e);
+      n_msgs++;
+    };
+    if (uml)
+      for (int ch : children[cid]) {
+        const UpMsg& msg = upmsg[ch];
+        // addLikelihoodsDifferential! (TreeMessageUtils.jl:225-233): the relatives of the joint message, each sampling its
+        // measurements from the belief slot its IIF_S_DECONV op filled (`_sft(newBel)`, :321)
+        for (const Relative& rel : msg.relatives) {
+          iif_dist_desc D;
+          memset(&D, 0, sizeof(D));
+          D.kind = IIF_D_KDE; D.dim = rel.zdim; D.slot = rel.slot; D.poff = (int)P->dparams.size();
+          P->dists.push_back(D);
+          iif_factor_desc F;
+          memset(&F, 0, sizeof(F));
+          F.kind = rel.kind; F.arity = 2; F.zdim = rel.zdim; F.dist = (int)P->dists.size() - 1;
+          F.slot[0] = cslot[cid][rel.v1]; F.slot[1] = cslot[cid][rel.v2]; F.nullhypo = 0.0; F.inflation = o->inflation;
+          P->factors.push_back(F);
+          Inst e;
+          e.vars = {rel.v1, rel.v2}; e.rd = {F.slot[0], F.slot[1], rel.slot}; e.fi = (int)P->factors.size() - 1;
+          e.mh = false; e.type = rel.type; e.prior = false; e.tag = 2;
+          inst.push_back(e);
+          n_msgs++;
+        }
+        // addLikelihoodPriorCommon! (TreeMessageUtils.jl:454-469)
+        for (auto& pr : msg.priors) {
+          bool touched = false;
+          for (auto& e : inst) touched |= has(e.vars, pr.first);
+          if (msg.hasPriors || !touched) add_msg_prior(pr.first, pr.second);
+        }
+      }
     for (int ch : children[cid])
       for (int s : sp[ch]) {   // addMsgFactors!: one MsgPrior per separator variable of the child
+        if (uml) break;
         auto it = cslot[cid].find(s);
         if (it == cslot[cid].end()) continue;
         const int src = cslot[ch][s];
@@ -341,6 +435,114 @@ int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const
       fmcmc(l, 1);
     }
     if (!err.empty()) { delete P; return fail(IIF_ERR_ARG, err); }
+    if (uml) {
+      // only UPWARD_COMMON is deleted after the up solve (CSM :559-563): the differentials stay for the down solve
+      for (auto& e : inst) if (e.tag == 2) kept_diffs[cid].push_back(e);
+      if (t->parent[cid] >= 0) {
+        // prepCliqueMsgUp (TreeMessageUtils.jl:667-703) -> _generateMsgJointRelativesPriors (:417-446)
+        UpMsg msg;
+        const std::vector<int>& seps = sp[cid];
+        std::vector<int> idx(seps.size());
+        for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return g->vars[seps[a]].dim > g->vars[seps[b]].dim; });
+        std::vector<int> dec, acc;
+        for (int i : idx) dec.push_back(seps[i]);
+        acc.assign(dec.rbegin(), dec.rend());
+        std::vector<int> already;
+        for (int s1 : dec) {
+          already.push_back(s1);
+          for (int s2 : acc) {
+            if (has(already, s2)) continue;
+            bool found;
+            std::vector<int> types = path_types(inst, s1, s2, -1, found);           // isPathFactorsHomogeneous (DFG)
+            if (!found || types.empty()) continue;
+            bool homog = true;
+            for (int ty : types) homog &= (ty == types[0]);
+            if (!homog) continue;
+            const int kind = sel_kind(s1, s2), type = sel_type(s1, s2);
+            if (!kind || type != types[0]) continue;
+            // newBel = manikde!(sft, approxDeconv(dummy factor)): a fresh measurement slot + one IIF_S_DECONV op
+            iif_slot_desc ms = g->vars[s1];
+            ms.cap = N; ms.pts_off = 0;
+            P->slots.push_back(ms);
+            const int mslot = (int)P->slots.size() - 1;
+            const int d = g->vars[s1].dim;
+            iif_dist_desc D;                     // the dummy's own measurement model: LinearRelative{N}() / CircularCircular(Normal(0, 0.1))
+            memset(&D, 0, sizeof(D));
+            D.poff = (int)P->dparams.size(); D.dim = d; D.slot = -1;
+            if (kind == IIF_F_CIRCULAR_CIRCULAR) { D.kind = IIF_D_NORMAL; P->dparams.push_back(0.0); P->dparams.push_back(0.1); }
+            else if (d == 1) { D.kind = IIF_D_NORMAL; P->dparams.push_back(0.0); P->dparams.push_back(1.0); }
+            else {
+              D.kind = IIF_D_MVNORMAL;
+              for (int c = 0; c < d; ++c) P->dparams.push_back(0.0);
+              for (int r = 0; r < d; ++r) for (int c = 0; c < d; ++c) P->dparams.push_back(r == c ? 1.0 : 0.0);
+            }
+            P->dists.push_back(D);
+            iif_factor_desc F;
+            memset(&F, 0, sizeof(F));
+            F.kind = kind; F.arity = 2; F.zdim = d; F.dist = (int)P->dists.size() - 1;
+            F.slot[0] = cslot[cid][s1]; F.slot[1] = cslot[cid][s2]; F.nullhypo = 0.0; F.inflation = 5.0;
+            P->factors.push_back(F);
+            iif_deconv_op dc;
+            dc.factor = (int)P->factors.size() - 1; dc.out_slot = mslot; dc.N = N; dc.call_id = -1;
+            P->deconvs.push_back(dc);
+            std::vector<int> rd{F.slot[0], F.slot[1]};
+            std::sort(rd.begin(), rd.end());
+            rd.erase(std::unique(rd.begin(), rd.end()), rd.end());
+            Op op{IIF_S_DECONV, (int)P->deconvs.size() - 1, 0, cur, rd, {mslot}, 1.0};
+            ops.push_back(op);
+            msg.relatives.push_back({s1, s2, kind, type, mslot, d});
+          }
+        }
+        // _findSubgraphsFactorType (:118-205): classes of separators connected through the default relative type
+        std::unordered_map<int, int> count, cls;
+        for (int s_ : seps) count[s_] = 0;
+        for (auto& r : msg.relatives) { count[r.v1]++; count[r.v2]++; }
+        int ncls = 0;
+        for (int s_ : seps) if (count[s_] == 0) cls[s_] = ++ncls;
+        std::vector<int> rest;
+        for (int s_ : seps) if (!cls.count(s_)) rest.push_back(s_);
+        for (int k1 : rest) {
+          if (!cls.count(k1)) cls[k1] = ++ncls;
+          std::vector<int> rest2;
+          for (int s_ : seps) if (!cls.count(s_)) rest2.push_back(s_);
+          for (int k2 : rest2) {
+            const int ty = sel_type(k1, k2);
+            bool found = false;
+            std::vector<int> pth;
+            if (ty >= 0) pth = path_types(inst, k1, k2, ty, found);
+            if (ty < 0 || !found || pth.empty()) cls[k2] = ++ncls;
+            else cls[k2] = cls[k1];
+          }
+        }
+        std::vector<int> class_order;
+        std::unordered_map<int, std::vector<int>> classes;
+        for (int s_ : seps) {
+          if (!classes.count(cls[s_])) class_order.push_back(cls[s_]);
+          classes[cls[s_]].push_back(s_);
+        }
+        bool pot_has_prior = false, any_prior = false;                                  // :431, :681
+        for (auto& e : inst) { pot_has_prior |= (e.tag == 0 && e.prior); any_prior |= e.prior; }
+        for (int c_ : class_order) {
+          const std::vector<int>& syms = classes[c_];
+          if (syms.size() == 1 || pot_has_prior) {                                      // :402-408
+            int md = 0;
+            for (int v : syms) md = std::max(md, (int)g->vars[v].dim);
+            std::vector<int> cand;
+            for (int v : syms) if (g->vars[v].dim == md) cand.push_back(v);
+            int best = 0, best_adj = -1;
+            for (size_t i = 0; i < cand.size(); ++i) {     // sortperm(mdAdj; rev = true)[1]: first maximum
+              int adj = 0;
+              for (auto& e : inst) adj += has(e.vars, cand[i]) ? 1 : 0;
+              if (adj > best_adj) { best_adj = adj; best = (int)i; }
+            }
+            msg.priors.push_back({cand[best], cslot[cid][cand[best]]});
+          }
+        }
+        msg.hasPriors = any_prior;
+        upmsg[cid] = msg;
+      }
+    }
   }
   const size_t n_up_ops = ops.size();
   // ---- down pass (parents before children); the root keeps its up-solve result
@@ -361,6 +563,11 @@ int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const
       std::sort(touching.begin(), touching.end());
       touching.erase(std::unique(touching.begin(), touching.end()), touching.end());
       std::vector<Inst> inst;
+      if (uml) {
+        // the clique sub-graph as the up solve left it: potentials + the children's differentials, no
+        // addDownVariableFactors! (CliqueStateMachine.jl:825-834)
+        touching = csr(t->potential_off, t->potentials, cid);
+      }
       for (int f : touching) {
         const iif_factor_desc& F = g->factors[f];
         Inst e;
@@ -373,6 +580,8 @@ int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const
         e.mh = F.nmh != 0;
         inst.push_back(e);
       }
+      if (uml)
+        for (auto& e : kept_diffs[cid]) inst.push_back(e);
       auto local_product = [&](int v) {
         std::vector<Inst*> use;
         for (auto& e : inst) if (has(e.vars, v)) use.push_back(&e);
@@ -396,6 +605,8 @@ int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const
     cur = c;
     for (int v : fr[c]) add_copy(cslot[c][v], v);
   }
+  for (size_t k = 0; k < P->deconvs.size(); ++k)      // Philox call ids: props first (16 apart), then the deconvolutions
+    P->deconvs[k].call_id = o->call_base + 16 * ((int)P->props.size() + (int)k);
   // ---- waves, lanes
   std::vector<int> waves = levelize(ops);
   int nw = 0;
@@ -429,8 +640,8 @@ int32_t iifb200_plan_counts(const iifb200_plan* p, int32_t* c) {
   c[0] = (int32_t)p->slots.size(); c[1] = (int32_t)p->factors.size(); c[2] = (int32_t)p->dists.size();
   c[3] = (int32_t)p->dparams.size(); c[4] = (int32_t)p->props.size(); c[5] = (int32_t)p->ops.size();
   c[6] = (int32_t)p->wave_off.size() - 1; c[7] = p->n_conv; c[8] = p->n_prod; c[9] = p->n_msgs;
-  c[10] = p->up_last_wave; c[11] = p->nvars;
-  for (int k = 12; k < 16; ++k) c[k] = 0;
+  c[10] = p->up_last_wave; c[11] = p->nvars; c[12] = (int32_t)p->deconvs.size();
+  for (int k = 13; k < 16; ++k) c[k] = 0;
   return IIF_OK;
 }
 
@@ -447,9 +658,16 @@ int32_t iifb200_plan_export(const iifb200_plan* p, iif_slot_desc* slots, iif_fac
   return IIF_OK;
 }
 
+int32_t iifb200_plan_export_deconvs(const iifb200_plan* p, iif_deconv_op* deconvs) {
+  if (!p || (!deconvs && !p->deconvs.empty())) return IIF_ERR_ARG;
+  std::copy(p->deconvs.begin(), p->deconvs.end(), deconvs);
+  return IIF_OK;
+}
+
 }  // extern "C"
 
 // accessors for iifb200.cu (iifb200_plan_upload)
+const std::vector<iif_deconv_op>& iif_plan_deconvs(const iifb200_plan* p) { return p->deconvs; }
 const std::vector<iif_slot_desc>& iif_plan_slots(const iifb200_plan* p) { return p->slots; }
 const std::vector<iif_factor_desc>& iif_plan_factors(const iifb200_plan* p) { return p->factors; }
 const std::vector<iif_dist_desc>& iif_plan_dists(const iifb200_plan* p) { return p->dists; }

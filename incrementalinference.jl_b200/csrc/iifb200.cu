@@ -27,6 +27,7 @@ const std::vector<double>& iif_plan_dparams(const iifb200_plan* p);
 const std::vector<iif_prop_op>& iif_plan_props(const iifb200_plan* p);
 const std::vector<iif_sched_op>& iif_plan_ops(const iifb200_plan* p);
 const std::vector<int32_t>& iif_plan_wave_off(const iifb200_plan* p);
+const std::vector<iif_deconv_op>& iif_plan_deconvs(const iifb200_plan* p);
 
 static std::string g_init_error;
 
@@ -1504,8 +1505,10 @@ int32_t iifb200_plan_upload(iifb200_ctx* ctx, const iifb200_plan* plan, const ii
   const auto& wo = iif_plan_wave_off(plan);
   const auto& ops = iif_plan_ops(plan);
   const auto& props = iif_plan_props(plan);
-  return iifb200_schedule_build(ctx, (int32_t)wo.size() - 1, wo.data(), (int32_t)ops.size(), ops.data(),
-                                (int32_t)props.size(), props.data(), schedule_id_out);
+  const auto& dcv = iif_plan_deconvs(plan);
+  return iifb200_schedule_build_ex(ctx, (int32_t)wo.size() - 1, wo.data(), (int32_t)ops.size(), ops.data(),
+                                   (int32_t)props.size(), props.data(), (int32_t)dcv.size(), dcv.empty() ? nullptr : dcv.data(),
+                                   schedule_id_out);
 }
 
 int32_t iifb200_sync(iifb200_ctx* ctx) {

@@ -49,10 +49,24 @@ def plan_tree(fg: G.FactorGraph, tree: TR.BayesTree, N=None, downsolve=True, gib
     sp = fg.solverParams
     N = N or sp.N
     frozen, var_idx, fac_idx = graph_tables(fg, min(N, A.IIF_MAX_POINTS))
+    # type tables of iif_graph_desc: ids stand for Julia types; the joint-message rules compare them for equality only
+    tid = {}
+
+    def type_id(name):
+        return tid.setdefault(name, len(tid))
+    ftype = np.asarray([type_id(type(f.fnc).__name__) for f in fg.factors.values()] or [0], dtype=np.int32)
+    vtype = np.asarray([type_id("var:" + v.vartype.name) for v in fg.variables.values()], dtype=np.int32)
+    vrelkind = np.zeros(len(vtype), dtype=np.int32)
+    vreltype = np.full(len(vtype), -1, dtype=np.int32)
+    for i, v in enumerate(fg.variables.values()):
+        sel = TR.selectFactorType(v.vartype, v.vartype)      # DefaultNodeTypes.jl:12-31
+        if sel is not None:
+            vrelkind[i], vreltype[i] = sel[1].kind, type_id(sel[0])
+    keep = [ftype, vtype, vrelkind, vreltype]
     gd = A.GraphDesc(frozen["nslots"], frozen["slots"], frozen["nfactors"], frozen["factors"], frozen["ndists"],
-                     frozen["dists"], frozen["nparams"], A.as_dp(frozen["dparams"]))
+                     frozen["dists"], frozen["nparams"], A.as_dp(frozen["dparams"]), A.as_ip(ftype), A.as_ip(vtype),
+                     A.as_ip(vrelkind), A.as_ip(vreltype), type_id("MsgPrior"), 0)
     cl = tree.cliques
-    keep = []
 
     def lists(get, idx):
         off, flat = _csr([[idx[x] for x in get(c)] for c in cl])
@@ -76,7 +90,7 @@ def plan_tree(fg: G.FactorGraph, tree: TR.BayesTree, N=None, downsolve=True, gib
         raise A.IIFB200Error(f"iifb200_plan_tree failed ({st}): {lib.iifb200_plan_error().decode()}")
     cnt = np.zeros(16, dtype=np.int32)
     lib.iifb200_plan_counts(h, A.as_ip(cnt))
-    ns, nf, nd, npar, nprops, nops, nw, n_conv, n_prod, n_msgs, up_last, nvars = (int(x) for x in cnt[:12])
+    ns, nf, nd, npar, nprops, nops, nw, n_conv, n_prod, n_msgs, up_last, nvars, ndec = (int(x) for x in cnt[:13])
     slots = (A.SlotDesc * max(ns, 1))()
     factors = (A.FactorDesc * max(nf, 1))()
     dists = (A.DistDesc * max(nd, 1))()
@@ -85,6 +99,10 @@ def plan_tree(fg: G.FactorGraph, tree: TR.BayesTree, N=None, downsolve=True, gib
     ops = (A.SchedOp * max(nops, 1))()
     wave_off = np.zeros(nw + 1, dtype=np.int32)
     lib.iifb200_plan_export(h, slots, factors, dists, A.as_dp(dparams), props, ops, A.as_ip(wave_off))
+    dcv = (A.DeconvOp * max(ndec, 1))()
+    if ndec:
+        lib.iifb200_plan_export_deconvs(h, dcv)
+    deconvs = [dict(factor=d.factor, out_slot=d.out_slot, N=d.N, call_id=d.call_id) for d in dcv[:ndec]]
     total = slots[ns - 1].pts_off + slots[ns - 1].cap * slots[ns - 1].dim
     fz = dict(nslots=ns, slots=slots, nfactors=nf, factors=factors, ndists=nd, dists=dists, nparams=npar,
               dparams=dparams, total_doubles=total)
@@ -93,6 +111,6 @@ def plan_tree(fg: G.FactorGraph, tree: TR.BayesTree, N=None, downsolve=True, gib
                    any_multihypo=p.any_multihypo) for p in props[:nprops]]
     sched = [(o.kind, o.a, o.b) for o in ops[:nops]]
     plan = TR.SolvePlan(None, fz, pspecs, sched, [int(x) for x in wave_off], sched, dict(var_idx), n_conv, n_prod,
-                        n_msgs, up_last, None, None, None, None, None, [], [o.lane for o in ops[:nops]])
+                        n_msgs, up_last, None, None, None, None, None, deconvs, [o.lane for o in ops[:nops]])
     plan.c_plan = CPlan(h, lib)
     return plan

@@ -339,20 +339,21 @@ class TreeSolver:
         # independent sub-trees become parallel branches ("lanes") of the captured CUDA graph (tree.assign_lanes)
         lanes = int(os.environ.get("IIFB200_LANES", "4")) if lanes is None else lanes
         # `planner`: "c" = iifb200_plan_tree inside libiifb200.so (what a Julia caller uses: the clique table goes in,
-        # the schedule comes out), "python" = the mirror in tree.py (also lowers useMsgLikelihoods = true).  Both give
-        # the same plan bit for bit (tests/test_plan_abi.py); default: the library's planner whenever it applies.
+        # the schedule comes out), "python" = the mirror in tree.py.  Both give the same plan bit for bit, differential
+        # (useMsgLikelihoods = true) messages included (tests/test_plan_abi.py); default: the library's planner.
         uml = bool(fg.solverParams.useMsgLikelihoods)
-        planner = planner or os.environ.get("IIFB200_PLANNER") or ("python" if uml else "c")
+        planner = planner or os.environ.get("IIFB200_PLANNER") or "c"
         self.sp_c = CP.solver_params_c(fg.solverParams)
         self.plan_handle = None
         if planner == "c":
             from . import planner as PL
-            self.plan = PL.plan_tree(fg, self.tree, downsolve=ds, lanes=lanes, forward_copies=forward_copies)
+            self.plan = PL.plan_tree(fg, self.tree, downsolve=ds, lanes=lanes, forward_copies=forward_copies,
+                                     useMsgLikelihoods=uml)
             if call_base == "auto":
                 call_base = fg.next_call(TR.plan_call_span(self.plan))
             if call_base:       # ids are baked into the library's plan: plan again with the base
                 self.plan = PL.plan_tree(fg, self.tree, downsolve=ds, lanes=lanes, forward_copies=forward_copies,
-                                         call_base=int(call_base))
+                                         useMsgLikelihoods=uml, call_base=int(call_base))
             self.plan_handle = self.plan.c_plan
             self.eng, self.sid = Engine.from_plan(self.plan.frozen, self.plan_handle.handle, self.sp_c, device, ext_arena_ptr)
         else:

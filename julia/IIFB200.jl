@@ -47,6 +47,8 @@ struct DeconvOp; factor::Int32; out_slot::Int32; N::Int32; call_id::Int32; end
 struct GraphDesc
   nvars::Int32; vars::Ptr{SlotDesc}; nfactors::Int32; factors::Ptr{FactorDesc}
   ndists::Int32; dists::Ptr{DistDesc}; nparams::Int32; dparams::Ptr{Float64}
+  factor_type::Ptr{Int32}; var_type::Ptr{Int32}; var_relative_kind::Ptr{Int32}; var_relative_type::Ptr{Int32}
+  msgprior_type::Int32; _pad::Int32
 end
 struct TreeDesc
   ncliques::Int32; parent::Ptr{Int32}
@@ -307,7 +309,8 @@ _csr(lists) = (Int32[0; cumsum(length.(lists))], Int32[x for l in lists for x in
 Up + down pass of an already built Bayes tree (`buildTreeReset!`) on the device: `tree.bt`'s clique table goes through
 iifb200_plan_tree / iifb200_plan_upload, the graph's beliefs through iifb200_upload_slots, one iifb200_schedule_run
 replays the pass as a CUDA graph and iifb200_download_slots returns every posterior, which is written back with
-setValKDE! (CSM step 5, updateFromSubgraph).  useMsgLikelihoods = true plans are lowered host-side (tree.py mirror).
+setValKDE! (CSM step 5, updateFromSubgraph).  SolverParams.useMsgLikelihoods is honoured: the library builds the joint
+up messages (differentials + one MsgPrior per class) itself.
 """
 function solveTree_b200!(dfg::AbstractDFG, tree; solveKey::Symbol = :default, lanes::Integer = 4,
                          downsolve::Bool = getSolverParams(dfg).downsolve)
@@ -339,6 +342,26 @@ function solveTree_b200!(dfg::AbstractDFG, tree; solveKey::Symbol = :default, la
   d2o, d2 = lists(d -> d.msgskipIDs, vidx)
   d3o, d3 = lists(d -> d.itervarIDs, vidx)
   d4o, d4 = lists(d -> d.directPriorMsgIDs, vidx)
+  # type tables for the joint up messages of useMsgLikelihoods = true (ids are positions in `tnames`)
+  tnames = String[]
+  function _tid(n::String)
+    i = findfirst(==(n), tnames)
+    i === nothing || return Int32(i - 1)
+    push!(tnames, n)
+    return Int32(length(tnames) - 1)
+  end
+  ftype = Int32[_tid(string(nameof(typeof(getFactorType(f))))) for f in fcts]
+  vtype = Int32[_tid("var:" * string(typeof(getVariableType(v)))) for v in vars]
+  msgprior_t = _tid("MsgPrior")
+  vrelkind = zeros(Int32, length(vars)); vreltype = fill(Int32(-1), length(vars))
+  for (i, v) in enumerate(vars)        # selectFactorType(T, T), DefaultNodeTypes.jl:12-31
+    T = typeof(getVariableType(v))
+    sft = try IIF.selectFactorType(T, T) catch; nothing end
+    sft === nothing && continue
+    vrelkind[i] = sft <: LinearRelative ? Int32(2) : (sft <: CircularCircular ? Int32(4) : Int32(0))
+    vrelkind[i] == 0 && continue       # no device kind for this default relative: the pair gets no differential
+    vreltype[i] = _tid(string(nameof(sft)))
+  end
   plan = Ref{Ptr{Cvoid}}(C_NULL); sid = Ref{Int32}(-1)
   nd = sum(s.cap * s.dim for s in gslots)
   hpts = zeros(nd); hbw = zeros(MAX_DIM, length(vars)); hipc = zeros(MAX_DIM, length(vars))
@@ -349,12 +372,13 @@ function solveTree_b200!(dfg::AbstractDFG, tree; solveKey::Symbol = :default, la
     hpts[(off + 1):(off + length(p))] .= vec(p); off += gslots[i].cap * gslots[i].dim
     hbw[1:size(p, 1), i] .= _bw(v, solveKey); hn[i] = size(p, 2); hfl[i] = isInitialized(v, solveKey)
   end
-  GC.@preserve gslots fdescs dists dparams parent fo fr so se po pt d1o d1 d2o d2 d3o d3 d4o d4 begin
+  GC.@preserve gslots fdescs dists dparams parent fo fr so se po pt d1o d1 d2o d2 d3o d3 d4o d4 ftype vtype vrelkind vreltype begin
     gd = Ref(GraphDesc(length(vars), pointer(gslots), length(fdescs), pointer(fdescs), length(dists), pointer(dists),
-                       length(dparams), pointer(dparams)))
+                       length(dparams), pointer(dparams), pointer(ftype), pointer(vtype), pointer(vrelkind), pointer(vreltype),
+                       msgprior_t, 0))
     td = Ref(TreeDesc(length(order), pointer(parent), pointer(fo), pointer(fr), pointer(so), pointer(se), pointer(po), pointer(pt),
                       pointer(d1o), pointer(d1), pointer(d2o), pointer(d2), pointer(d3o), pointer(d3), pointer(d4o), pointer(d4)))
-    opts = Ref(PlanOpts(N, sp.gibbsIters, 3, downsolve, lanes, 1, 0, _nextcall(16 * 64 * length(vars)), sp.inflation))
+    opts = Ref(PlanOpts(N, sp.gibbsIters, 3, downsolve, lanes, 1, sp.useMsgLikelihoods, _nextcall(16 * 64 * length(vars)), sp.inflation))
     st = ccall((:iifb200_plan_tree, LIB), Int32, (Ref{GraphDesc}, Ref{TreeDesc}, Ref{PlanOpts}, Ref{Ptr{Cvoid}}), gd, td, opts, plan)
     st == 0 || error("iifb200_plan_tree failed ($st): " * unsafe_string(ccall((:iifb200_plan_error, LIB), Cstring, ())))
   end

@@ -33,6 +33,20 @@ def graphs():
     yield "circular_no_forwarding", fg, W.chain_nd_order(15), dict(forward_copies=False)
     fg = W.four_door(N=64)
     yield "mixture_priors", fg, TR.getEliminationOrder(fg, "qr"), dict(gibbsIters=5)
+    # useMsgLikelihoods = true (fourdoortest.jl:19, testCircular.jl:12): differential separator messages
+    yield "uml_chain", W.scalar_chain(37, N=32, seed=1), W.chain_nd_order(37), dict(useMsgLikelihoods=True)
+    fg = W.four_door(N=64)
+    yield "uml_four_door", fg, TR.getEliminationOrder(fg, "qr"), dict(useMsgLikelihoods=True)
+    fg = W.circular_chain(n=15, N=40)
+    yield "uml_circular", fg, W.chain_nd_order(15), dict(useMsgLikelihoods=True)
+    fg = W.euclid2_grid(rows=4, cols=7, N=24, seed=2, closure_every=2)
+    yield "uml_grid", fg, TR.getEliminationOrder(fg, "nd"), dict(useMsgLikelihoods=True)
+    fg = W.generateGraph_Kaess(N=20)
+    yield "uml_kaess", fg, TR.getEliminationOrder(fg, "qr"), dict(useMsgLikelihoods=True, downsolve=False)
+    fg = three_door_graph(1, poses=3, N=50)
+    yield "uml_multihypo", fg, TR.getEliminationOrder(fg, "qr"), dict(useMsgLikelihoods=True)
+    fg = W.generateGraph_CaesarRing1D(N=20)
+    yield "uml_caesar_ring", fg, TR.getEliminationOrder(fg, "qr"), dict(useMsgLikelihoods=True)
 
 
 def _factor_tuple(frozen, i):
@@ -56,7 +70,9 @@ def test_c_planner_reproduces_python_plan(built, case):
     name, fg, order, kw = case
     tree = TR.buildTree(fg, order)
     for lanes in (0, 4):
-        ref = TR.compile_solve(fg, tree, lanes=lanes, useMsgLikelihoods=False, **kw)
+        kw = dict(kw)
+        kw.setdefault("useMsgLikelihoods", False)
+        ref = TR.compile_solve(fg, tree, lanes=lanes, **kw)
         got = PL.plan_tree(fg, tree, lanes=lanes, **kw)
         a, b = ref.frozen, got.frozen
         assert a["nslots"] == b["nslots"] and a["nfactors"] == b["nfactors"]
@@ -66,6 +82,11 @@ def test_c_planner_reproduces_python_plan(built, case):
         for i in range(a["nfactors"]):
             assert _factor_tuple(a, i) == _factor_tuple(b, i), (name, i)
         assert ref.props == got.props
+        assert [{k: d[k] for k in ("factor", "out_slot", "N", "call_id")} for d in ref.deconvs or []] == got.deconvs
+        if name in ("uml_grid", "uml_caesar_ring"):      # multi-variable separators: differentials exist
+            assert got.deconvs, name
+        if not kw["useMsgLikelihoods"]:
+            assert not got.deconvs
         assert ref.sched_waved == got.sched_waved
         assert list(ref.wave_off) == list(got.wave_off)
         assert list(ref.op_lane) == list(got.op_lane)
@@ -92,8 +113,6 @@ def test_c_planner_runs_on_the_oracle(built):
 def test_c_planner_errors(built):
     fg, order = W.scalar_chain(5, N=16), W.chain_nd_order(5)
     tree = TR.buildTree(fg, order)
-    with pytest.raises(A.IIFB200Error, match="useMsgLikelihoods"):
-        PL.plan_tree(fg, tree, useMsgLikelihoods=True)
     with pytest.raises(A.IIFB200Error):
         PL.plan_tree(fg, tree, N=100000)
 
