@@ -477,6 +477,7 @@ def run_b200(args, rank, world, local_rank):
         for l, v in fg.variables.items():
             ar.set(plan.var_slot[l], v.val, v.bw, True)
         b3.run(ar.copy())                      # warm-up: pools reach their size
+        ar0 = ar.copy()
         t0 = time.perf_counter()
         b3.run(ar)
         dt = time.perf_counter() - t0
@@ -485,6 +486,18 @@ def run_b200(args, rank, world, local_rank):
                          "note": "one propagateBelief per call through set_graph / upload_slots / propagate_batch / "
                                  "download_belief (Python mirror of the Julia shim's B3 sequence; descriptor tables "
                                  "prebuilt outside the timed region)"}
+        b3.close()
+        # the same sequence with the shim's context pool: the reference runs sibling cliques as concurrent Tasks, so
+        # independent propagateBelief calls (the ops of one wave) overlap, each on its own library context
+        K = int(os.environ.get("IIFB200_B3_CONTEXTS", "8"))
+        b3 = SV.B3Driver(plan, CP.solver_params_c(fg.solverParams, 7), contexts=K)
+        b3.run(ar0.copy())
+        arc = ar0.copy()
+        t0 = time.perf_counter()
+        b3.run(arc)
+        dtc = time.perf_counter() - t0
+        out["e2e_b3"]["concurrent"] = {"contexts": K, "value": total_conv / dtc, "unit": "conv/s", "ms_per_step": 1e3 * dtc,
+                                       "equal_to_serial": bool(np.array_equal(arc.pts, ar.pts))}
         b3.close()
     if cpu is not None:
         out["cpu_baseline"] = cpu

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(IIF_PPE_THREADS, 1)
 iif_ppe_kernel(DeviceGraph g, const PpeTask* __restrict__ tasks) {
   __shared__ double x[IIF_MAX_POINTS + 8];
   __shared__ double red[IIF_RED_DOUBLES];
-  __shared__ double tab[16];
+  __shared__ double tab[IIF_GTAB_N];
   __shared__ double wv[IIF_PPE_THREADS / 32];
   __shared__ int wi[IIF_PPE_THREADS / 32];
   const PpeTask t = tasks[blockIdx.x];
@@ -29,7 +29,7 @@ iif_ppe_kernel(DeviceGraph g, const PpeTask* __restrict__ tasks) {
   const int n = g.npts[t.slot], d = S.dim;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int parity = 0;
-  if (tid < 16) tab[tid] = IIF_EXP2TAB[tid];
+  gauss_stage_table(tab);
   for (int c = 0; c < d; ++c) {
     const bool circ = is_circ(S.circ_mask, c);
     __syncthreads();

@@ -87,10 +87,10 @@ __device__ __forceinline__ double cond_gauss(int F, const double* mean, const do
   return lam;
 }
 
-// |a| clamped to 127 by integer min on the high word (the low word keeps its bits: |result| < 127.00001).  The Gaussian
+// |a| clamped to 510 by integer min on the high word (the low word keeps its bits: |result| < 510.0001).  The Gaussian
 // kernel value of a clamped argument is below 1e-300, i.e. nothing, and the lock-step evaluation stays on its fast path.
-__device__ __forceinline__ double clamp_abs127(double a) {
-  return __hiloint2double(min(__double2hiint(a) & 0x7fffffff, 0x405FC000), __double2loint(a));
+__device__ __forceinline__ double clamp_gauss_arg(double a) {
+  return __hiloint2double(min(__double2hiint(a) & 0x7fffffff, IIF_GCLAMP_HI), __double2loint(a));
 }
 
 // Weights of the four candidate nodes [zb, zb+4) of one density at one level given a Gaussian (m, cv) per coordinate
@@ -109,7 +109,7 @@ __device__ __forceinline__ void gibbs_piece_d1(const double* __restrict__ mean, 
     for (int u = 0; u < 4; ++u) {
       const int z = zb + u;
       const double rs = POINT ? irs[z] : LEAF ? rsl : rsqrt(var[z] + cv0);
-      a[u] = clamp_abs127((mean[z] - m0) * (rs * IIF_GSCALE));
+      a[u] = clamp_gauss_arg((mean[z] - m0) * (rs * IIF_GSCALE));
       pre[u] = wt[z] * rs;
     }
   } else {  // last piece of the level: clamp the index, padding lanes weigh nothing
@@ -117,7 +117,7 @@ __device__ __forceinline__ void gibbs_piece_d1(const double* __restrict__ mean, 
     for (int u = 0; u < 4; ++u) {
       const int z = min(zb + u, nz - 1);
       const double rs = POINT ? irs[z] : LEAF ? rsl : rsqrt(var[z] + cv0);
-      a[u] = clamp_abs127((mean[z] - m0) * (rs * IIF_GSCALE));
+      a[u] = clamp_gauss_arg((mean[z] - m0) * (rs * IIF_GSCALE));
       pre[u] = (zb + u < nz) ? wt[z] * rs : 0.0;
     }
   }
@@ -295,8 +295,8 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
   }
   const int32_t fullmask = (1 << d) - 1;
   __shared__ int32_t masks[IIF_MAX_FACTORS];
-  __shared__ double gtab[16];  // 2^(j/16) for gauss_negU
-  if (tid < 16) gtab[tid] = IIF_EXP2TAB[tid];
+  __shared__ double gtab[IIF_GTAB_N];  // 2^(j/256) for gauss_negU
+  gauss_stage_table(gtab);
   sm.tab = gtab;
   if (tid < F) masks[tid] = t.mask[tid] ? t.mask[tid] : fullmask;
   for (int i = tid; i < F * N * d; i += IIF_NT) sm.P[i] = t.dens_pts[i];

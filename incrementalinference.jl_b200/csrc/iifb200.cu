@@ -29,6 +29,9 @@ const std::vector<iif_sched_op>& iif_plan_ops(const iifb200_plan* p);
 const std::vector<int32_t>& iif_plan_wave_off(const iifb200_plan* p);
 const std::vector<iif_deconv_op>& iif_plan_deconvs(const iifb200_plan* p);
 
+// upper bound of any kernel's static shared memory (the 2 KB Gaussian table appears twice in the product kernel:
+// its own and the bandwidth search's; ptxas reports 4.8 KB for the convolution kernel)
+#define IIF_STATIC_SMEM_RESERVE 8192
 static std::string g_init_error;
 
 struct TreeHost {
@@ -112,7 +115,7 @@ struct iifb200_ctx {
   int32_t* d_epoch = nullptr;
   int nflags = 0;
   int64_t launches = 0;
-  int max_smem_optin = 0;
+  int max_smem_optin = 0;  // dynamic budget of a kernel = this - IIF_STATIC_SMEM_RESERVE
   int num_sms = 148;
 };
 
@@ -259,19 +262,19 @@ int32_t iifb200_init(int32_t device_ordinal, iifb200_ctx** ctx_out) {
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_ordinal);
   cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device_ordinal);
   if ((e = cudaFuncSetAttribute(iif_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+                                ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(product smem)", e);
   if ((e = cudaFuncSetAttribute(iif_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+                                ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(conv smem)", e);
   if ((e = cudaFuncSetAttribute(iif_conv_kernel_rare, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+                                ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(conv smem, rare variant)", e);
   if ((e = cudaFuncSetAttribute(iif_bandwidth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+                                ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(bandwidth smem)", e);
   if ((e = cudaFuncSetAttribute(iif_deconv_slot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ctx->max_smem_optin - 4096)) != cudaSuccess)
+                                ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(deconv smem)", e);
   *ctx_out = ctx;
   return IIF_OK;
@@ -750,7 +753,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
     pmaxN = std::max(pmaxN, (int)o.N);
   }
   if ((n_u && !randU) || (n_n && !randN)) return fail(ctx, IIF_ERR_ARG, "product_batch: explicit stream offset given but array is NULL");
-  if ((int)smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "product op exceeds the shared-memory budget (F*N*d too large)");
+  if ((int)smem > ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE) return fail(ctx, IIF_ERR_ARG, "product op exceeds the shared-memory budget (F*N*d too large)");
   double *d_in = nullptr, *d_bw = nullptr, *d_old = nullptr, *d_u = nullptr, *d_n = nullptr, *d_out = nullptr, *d_obw = nullptr;
   int32_t *d_lab = nullptr, *d_st = nullptr;
   ProdTask* d_tasks = nullptr;
@@ -957,7 +960,7 @@ int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_
     ob[k + 1] = ob[k] + (int64_t)nb[k] * dim[k];
     smem = std::max(smem, sizeof(double) * (size_t)(na[k] + nb[k]) * dim[k]);
   }
-  if ((int)smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "mmd: point sets exceed the shared-memory budget");
+  if ((int)smem > ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE) return fail(ctx, IIF_ERR_ARG, "mmd: point sets exceed the shared-memory budget");
   double *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
   MmdTask* d_t = nullptr;
   {
@@ -980,7 +983,7 @@ int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_
   CK(cudaMemcpyAsync(d_a, a, sizeof(double) * oa[K], cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_b, b, sizeof(double) * ob[K], cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_t, t.data(), sizeof(MmdTask) * K, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaFuncSetAttribute(iif_mmd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - 4096));
+  CK(cudaFuncSetAttribute(iif_mmd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE));
   iif_mmd_kernel<<<K, 256, smem, ctx->stream>>>(d_t);
   CK(cudaGetLastError());
   ctx->launches += 1;
@@ -1164,7 +1167,7 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
     W.nconv += G.nconv; W.nprod += G.nprod; W.ncopy += G.ncopy; W.ndcv += G.ndcv;
     W.segs.push_back(G);
    }
-    if ((int)W.prod_smem > ctx->max_smem_optin - 4096) return fail(ctx, IIF_ERR_ARG, "schedule: product exceeds the shared-memory budget");
+    if ((int)W.prod_smem > ctx->max_smem_optin - IIF_STATIC_SMEM_RESERVE) return fail(ctx, IIF_ERR_ARG, "schedule: product exceeds the shared-memory budget");
     s->waves.push_back(W);
   }
   if (!pooled) {

@@ -431,9 +431,13 @@ class B3Driver:
     factors' variables, message beliefs}, ONE iifb200_upload_slots of their beliefs, iifb200_propagate_batch(1) and
     iifb200_download_belief of the posterior.  Beliefs live on the host between calls (as they do in the DFG's
     VariableNodeData); separator copies are host copies.  Same Philox call ids as the plan => same posteriors as the
-    one-schedule (B4) run; what differs is the cost of 7 000 round trips instead of one."""
+    one-schedule (B4) run; what differs is the cost of 7 000 round trips instead of one.
 
-    def __init__(self, plan: TR.SolvePlan, sp_c, device: int = 0):
+    `contexts` > 1 mirrors the shim's context pool: the reference solves sibling cliques as concurrent Tasks
+    (SolverAPI.jl:59-96), so independent propagateBelief calls — here: the ops of one wave — are in flight at once,
+    each on its own library context (own stream, arena and scratch) from its own host thread."""
+
+    def __init__(self, plan: TR.SolvePlan, sp_c, device: int = 0, contexts: int = 1):
         self.plan, self.sp_c = plan, sp_c
         fz = plan.frozen
         self.calls = []
@@ -482,22 +486,52 @@ class B3Driver:
                                         N=spec["N"], call_id=spec["call_id"], any_multihypo=spec["any_multihypo"])])
             stage = (np.zeros(off), np.zeros(ns * A.IIF_MAX_DIM), np.zeros(ns, dtype=np.int32), np.ones(ns, dtype=np.int32))
             self.calls.append((order, mini, op, stage))
-        self.eng = Engine(self.calls[0][1], sp_c, device) if self.calls else None
+        self.engs = [Engine(self.calls[0][1], sp_c, device) for _ in range(max(1, contexts))] if self.calls else []
+        self.eng = self.engs[0] if self.engs else None
+        self.pool = None
+        if len(self.engs) > 1:
+            import concurrent.futures
+            import queue
+            self.pool = concurrent.futures.ThreadPoolExecutor(len(self.engs))
+            self.free = queue.SimpleQueue()
+            for e in self.engs:
+                self.free.put(e)
 
     def run(self, arena: CP.HostArena):
         """one pass over the plan's ops in wave order, beliefs in `arena` (host)"""
-        fz, eng = self.plan.frozen, self.eng
-        for kind, a, b in self.plan.sched_waved:
-            if kind == A.S_COPY:
-                sa, sb = fz["slots"][a], fz["slots"][b]
-                n = int(arena.npts[a])
-                arena.pts[sb.pts_off:sb.pts_off + n * sa.dim] = arena.pts[sa.pts_off:sa.pts_off + n * sa.dim]
-                arena.bw[b * 4:b * 4 + 4] = arena.bw[a * 4:a * 4 + 4]
-                arena.ipc[b * 4:b * 4 + 4] = arena.ipc[a * 4:a * 4 + 4]
-                arena.npts[b], arena.flags[b] = n, arena.flags[a]
-                continue
-            if kind != A.S_PROPAGATE:
-                raise A.IIFB200Error("B3Driver: only PROPAGATE / COPY ops (useMsgLikelihoods = false plans)")
+        fz = self.plan.frozen
+        sched, wo = self.plan.sched_waved, self.plan.wave_off
+        for w in range(len(wo) - 1):
+            props = []
+            for kind, a, b in sched[wo[w]:wo[w + 1]]:
+                if kind == A.S_COPY:
+                    sa, sb = fz["slots"][a], fz["slots"][b]
+                    n = int(arena.npts[a])
+                    arena.pts[sb.pts_off:sb.pts_off + n * sa.dim] = arena.pts[sa.pts_off:sa.pts_off + n * sa.dim]
+                    arena.bw[b * 4:b * 4 + 4] = arena.bw[a * 4:a * 4 + 4]
+                    arena.ipc[b * 4:b * 4 + 4] = arena.ipc[a * 4:a * 4 + 4]
+                    arena.npts[b], arena.flags[b] = n, arena.flags[a]
+                elif kind == A.S_PROPAGATE:
+                    props.append(a)
+                else:
+                    raise A.IIFB200Error("B3Driver: only PROPAGATE / COPY ops (useMsgLikelihoods = false plans)")
+            # the ops of one wave touch disjoint destinations and read nothing another op of the wave writes
+            if self.pool is None:
+                for a in props:
+                    self._call(self.eng, arena, a)
+            else:
+                def job(a):
+                    eng = self.free.get()
+                    try:
+                        self._call(eng, arena, a)
+                    finally:
+                        self.free.put(eng)
+                for f in [self.pool.submit(job, a) for a in props]:
+                    f.result()
+
+    def _call(self, eng, arena, a):
+        fz = self.plan.frozen
+        if True:
             order, mini, op, (pts, bw, npts, flags) = self.calls[a]
             for i, s in enumerate(order):
                 g, m = fz["slots"][s], mini["slots"][i]
@@ -515,5 +549,7 @@ class B3Driver:
             arena.npts[t], arena.flags[t] = p.shape[0], 1
 
     def close(self):
-        if self.eng is not None:
-            self.eng.close()
+        if self.pool is not None:
+            self.pool.shutdown()
+        for e in self.engs:
+            e.close()

@@ -88,6 +88,32 @@ function _ctx()
 end
 _nextcall(n::Integer = 16) = Threads.atomic_add!(_CALLS, Int32(n))
 
+# B3 context pool: solveTree! runs sibling cliques as concurrent Tasks (SolverAPI.jl:59-96); every propagateBelief call
+# checks a context out (own stream, arena, tables and scratch), so independent calls overlap on the device instead of
+# queueing behind one lock.  IIFB200_CONTEXTS sets the pool size (default 8; a lone propagateBelief occupies 3-6 SMs).
+const _POOL = Ref{Union{Nothing, Channel{Ptr{Cvoid}}}}(nothing)
+function _pool()
+  lock(_CTX_LOCK) do
+    if _POOL[] === nothing
+      k = parse(Int, get(ENV, "IIFB200_CONTEXTS", "8")); dev = parse(Int, get(ENV, "LOCAL_RANK", "0"))
+      ch = Channel{Ptr{Cvoid}}(k)
+      for _ in 1:k
+        put!(ch, init(dev))
+      end
+      _POOL[] = ch
+    end
+    return _POOL[]
+  end
+end
+function _with_context(f)
+  pool = _pool(); ctx = take!(pool)
+  try
+    return f(ctx)
+  finally
+    put!(pool, ctx)
+  end
+end
+
 # ---- lowering of variables, distributions and factors ---------------------------------------------
 # factor kind: only the built-in residual library runs on the device
 factorkind(::Prior) = Int32(1); factorkind(::LinearRelative) = Int32(2)
@@ -267,7 +293,6 @@ function propagateBelief(dfg::AbstractDFG, destvar::DFGVariable, factors::Abstra
   get(getSolverParams(dfg).devParams, :backend, "") == "b200" ||
     return invoke(propagateBelief, Tuple{AbstractDFG, DFGVariable, AbstractVector}, dfg, destvar, factors; solveKey, N, kw...)
   length(factors) <= MAX_FACTORS || error("IIFB200: $(length(factors)) factors exceed IIF_MAX_FACTORS = $MAX_FACTORS")
-  ctx = _ctx()
   vars, slotof = _collect_variables(dfg, destvar, factors)           # labels -> slot index (destination = slot 0)
   dists, dparams, fdescs, extra = _lower_factors(dfg, factors, slotof, length(vars))
   slots = SlotDesc[SlotDesc(getDimension(v), circmask(v), max(N, length(getVal(v; solveKey)), 1), 0) for v in vars]
@@ -275,7 +300,7 @@ function propagateBelief(dfg::AbstractDFG, destvar::DFGVariable, factors::Abstra
     push!(slots, SlotDesc(size(e.pts, 1), circmask(typeof(e.vartype)), max(size(e.pts, 2), 1), 0))
   end
   local pts, bw, ipc
-  lock(_CTX_LOCK) do                                                 # one context: serialise the cliques' Tasks
+  _with_context() do ctx                                             # one context per call in flight (pool above)
     _set_graph(ctx, slots, fdescs, dists, dparams, _solverparams(getSolverParams(dfg)))
     staged = _upload_all(ctx, slots,
                          vcat([_packpoints(getVariableType(v), getVal(v; solveKey)) for v in vars], [e.pts for e in extra]),

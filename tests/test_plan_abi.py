@@ -153,3 +153,23 @@ def test_b3_per_call_path_equals_the_one_schedule_run(built):
         a, b = ts.arena.get(ts.plan.var_slot[l]), ar.get(ts.plan.var_slot[l])
         assert np.allclose(a[0], b[0], rtol=0, atol=1e-9) and np.allclose(a[1], b[1], rtol=1e-7), l
     b3.close(); ts.close()
+
+
+@pytest.mark.gpu
+def test_b3_context_pool_equals_the_serial_calls(built):
+    """the shim's context pool (independent propagateBelief calls in flight at once, one library context each, from
+    several host threads) returns the serial per-call result bit for bit: contexts share nothing but the device"""
+    from iifb200 import solver as SV
+    fg, order = W.scalar_chain(40, N=64, seed=5), W.chain_nd_order(40)
+    ts = SV.TreeSolver(fg, order)
+    res = []
+    for k in (1, 4):
+        b3 = SV.B3Driver(ts.plan, ts.sp_c, contexts=k)
+        ar = CP.HostArena(ts.plan.frozen)
+        for l, v in fg.variables.items():
+            ar.set(ts.plan.var_slot[l], v.val, v.bw, True)
+        b3.run(ar)
+        res.append(ar)
+        b3.close()
+    ts.close()
+    assert np.array_equal(res[0].pts, res[1].pts) and np.array_equal(res[0].bw, res[1].bw)
