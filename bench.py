@@ -432,10 +432,10 @@ def run_b200(args, rank, world, local_rank):
         byts = conv_bytes(plan) * (my_conv / max(total_conv, 1))
         ach = byts / (cms * 1e-3) / 1e9 if cms > 0 else 0.0
         tpb, tsrc = ncu_traffic_per_block()
-        # FP64-pipe view of the same kernel: 13 FP64 instructions per Gaussian kernel value, N(N-1)/2 values per
+        # FP64-pipe view of the same kernel: 11 FP64 instructions per Gaussian kernel value, N(N-1)/2 values per
         # objective evaluation, ~18 evaluations per bandwidth search; the pipe retires one
         # warp instruction per 2 cycles per SM sub-partition (profiles/ubench/fp64_pipe.cu, measured).
-        n_eval, fp64_per_pair = 18, 13
+        n_eval, fp64_per_pair = 18, 11
         pairs = NPART * (NPART - 1) // 2
         sm_hz = 1e6 * float(pk.get("sm_max_mhz", 1965.0))
         floor_s = cb * pairs * n_eval * fp64_per_pair / 32.0 * 2.0 / 4.0 / sm_hz / 148.0
@@ -448,7 +448,7 @@ def run_b200(args, rank, world, local_rank):
                 "launch_ms_avg": cms / max(cl, 1), "launches": cl, "blocks": cb,
                 "kernel_ms": {k: v[0] for k, v in prof.items()},
                 "fp64_pipe": {"floor_ms": 1e3 * floor_s, "frac_of_floor": (1e3 * floor_s) / cms if cms > 0 else None,
-                              "model": "13 FP64 instr/pair x N(N-1)/2 pairs x 18 evaluations, 2 cycles per warp "
+                              "model": "11 FP64 instr/pair x N(N-1)/2 pairs x 18 evaluations, 2 cycles per warp "
                                        "instruction per SM sub-partition, 148 SMs"},
                 "note": "FP64-pipe / issue bound, not HBM bound: the exact O(N^2) leave-one-out bandwidth search "
                         "dominates (DESIGN.md section 4); the HBM fraction is reported because the metric asks for it"}
