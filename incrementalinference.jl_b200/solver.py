@@ -531,22 +531,21 @@ class B3Driver:
 
     def _call(self, eng, arena, a):
         fz = self.plan.frozen
-        if True:
-            order, mini, op, (pts, bw, npts, flags) = self.calls[a]
-            for i, s in enumerate(order):
-                g, m = fz["slots"][s], mini["slots"][i]
-                pts[m.pts_off:m.pts_off + g.cap * g.dim] = arena.pts[g.pts_off:g.pts_off + g.cap * g.dim]
-                bw[i * 4:i * 4 + 4] = arena.bw[s * 4:s * 4 + 4]
-                npts[i], flags[i] = arena.npts[s], arena.flags[s]
-            eng.reset_graph(mini)                                          # iifb200_set_graph
-            eng.upload_slots(0, len(order), pts, bw, npts, flags)         # ONE transfer
-            eng.propagate_batch(op, 1)
-            p, w, ipc = eng.download_belief(0)
-            t = order[0]
-            g = fz["slots"][t]
-            arena.pts[g.pts_off:g.pts_off + p.size] = p.reshape(-1)
-            arena.bw[t * 4:t * 4 + g.dim], arena.ipc[t * 4:t * 4 + g.dim] = w, ipc
-            arena.npts[t], arena.flags[t] = p.shape[0], 1
+        order, mini, op, (pts, bw, npts, flags) = self.calls[a]
+        for i, s in enumerate(order):
+            g, m = fz["slots"][s], mini["slots"][i]
+            pts[m.pts_off:m.pts_off + g.cap * g.dim] = arena.pts[g.pts_off:g.pts_off + g.cap * g.dim]
+            bw[i * 4:i * 4 + 4] = arena.bw[s * 4:s * 4 + 4]
+            npts[i], flags[i] = arena.npts[s], arena.flags[s]
+        eng.reset_graph(mini)                                          # iifb200_set_graph
+        eng.upload_slots(0, len(order), pts, bw, npts, flags)         # ONE transfer
+        eng.propagate_batch(op, 1)
+        p, w, ipc = eng.download_belief(0)
+        t = order[0]
+        g = fz["slots"][t]
+        arena.pts[g.pts_off:g.pts_off + p.size] = p.reshape(-1)
+        arena.bw[t * 4:t * 4 + g.dim], arena.ipc[t * 4:t * 4 + g.dim] = w, ipc
+        arena.npts[t], arena.flags[t] = p.shape[0], 1
 
     def close(self):
         if self.pool is not None:
