@@ -126,11 +126,24 @@ def make_config(n_poses, world, order_kind, plan, lanes):
                                                     "arenas), posteriors gathered on rank 0"}
 
 
-def build_workload(n_poses, order_kind):
+def build_workload(n_poses, order_kind, library=True):
     import iifb200  # noqa: F401
     from iifb200 import workloads as W
     fg = W.scalar_chain(n_poses, N=NPART, seed=42)
-    order = W.chain_nd_order(n_poses) if order_kind == "nd" else [f"x{k}" for k in range(n_poses)]
+    if order_kind == "is":          # independent-set (generalised odd-even) order computed from the graph:
+        if library:                 # iifb200_elimination_order_is, or (reference arm, CPU baseline: nothing of the
+            from iifb200 import planner as PL   # library on that path) its Python mirror - same order
+            order = PL.elimination_order_is(fg)
+        else:
+            from iifb200 import tree as TR
+            order = TR.independent_set_order(fg)
+    elif order_kind == "nd":        # level-set bisection (iifb200_elimination_order_nd)
+        from iifb200 import tree as TR
+        order = TR.nested_dissection_order(fg)
+    elif order_kind == "nd-chain":  # hand-made balanced bisection of a chain (what round 1 benchmarked)
+        order = W.chain_nd_order(n_poses)
+    else:
+        order = [f"x{k}" for k in range(n_poses)]
     return fg, order
 
 
@@ -151,7 +164,7 @@ def run_reference_julia(args):
     cores = os.cpu_count() or 1
     n_sample = POSES_PER_GPU          # the metric's configuration, not a reduced one
     from iifb200 import tree as TR
-    fg, order = build_workload(n_sample, args.order)
+    fg, order = build_workload(n_sample, args.order, library=False)
     n_conv = TR.compile_solve(fg, TR.buildTree(fg, order)).n_conv      # the unit count both arms are divided into
     env = dict(os.environ, JULIA_NUM_THREADS=str(cores))
     try:
@@ -197,12 +210,12 @@ def run_reference(args, rank, world):
     # independent ops) the device runs, all host threads.  Under torchrun (N > 1) the b200 arm solves an N x 1000-pose
     # chain; the CPU arm times one 1000-pose segment per step (conv/s on the CPU does not depend on the chain length).
     n_poses = POSES_PER_GPU
-    fg, order = build_workload(n_poses, args.order)
+    fg, order = build_workload(n_poses, args.order, library=False)
     tree = TR.buildTree(fg, order)
     plan = TR.compile_solve(fg, tree, lanes=4)
     cfg_plan = plan
     if world > 1:
-        fgN, orderN = build_workload(POSES_PER_GPU * world if args.scaling == "weak" else POSES_PER_GPU, args.order)
+        fgN, orderN = build_workload(POSES_PER_GPU * world if args.scaling == "weak" else POSES_PER_GPU, args.order, library=False)
         cfg_plan = TR.compile_solve(fgN, TR.buildTree(fgN, orderN), lanes=4)
     base = CP.HostArena(plan.frozen)
     for l, v in fg.variables.items():
@@ -249,7 +262,7 @@ def cpu_baseline_sample(order_kind):
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
     except OSError:
         cores = 1
-    fg, order = build_workload(POSES_PER_GPU, order_kind)
+    fg, order = build_workload(POSES_PER_GPU, order_kind, library=False)
     plan = TR.compile_solve(fg, TR.buildTree(fg, order), lanes=4)
     base = CP.HostArena(plan.frozen)
     for l, v in fg.variables.items():
@@ -514,7 +527,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--order", default="nd", choices=["nd", "natural"])
+    ap.add_argument("--order", default="is", choices=["is", "nd", "nd-chain", "natural"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 1000 poses per GPU (default); strong: the 1000-pose chain itself over all GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")

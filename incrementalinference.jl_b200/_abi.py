@@ -154,6 +154,8 @@ SYMBOLS = {
     "iifb200_plan_export": (C.c_int32, [_vp, P(SlotDesc), P(FactorDesc), P(DistDesc), _dp, P(PropOp), P(SchedOp), _ip]),
     "iifb200_plan_export_deconvs": (C.c_int32, [_vp, P(DeconvOp)]),
     "iifb200_plan_upload": (C.c_int32, [_vp, _vp, P(SolverParamsC), _vp, _ip]),
+    "iifb200_elimination_order_nd": (C.c_int32, [C.c_int32, C.c_int32, _ip, _ip, _ip]),
+    "iifb200_elimination_order_is": (C.c_int32, [C.c_int32, C.c_int32, _ip, _ip, C.c_int32, _ip]),
     "iifb200_sync": (C.c_int32, [_vp]),
     "iifb200_launch_count": (C.c_int64, [_vp]),
     "iifb200_set_stream": (C.c_int32, [_vp, _vp]),

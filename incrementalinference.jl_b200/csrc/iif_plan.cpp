@@ -12,9 +12,12 @@
 //   determineCliqVariableDownSequence / downGibbs       CliqStateMachineUtils.jl:438-571
 //   updateFromSubgraph (frontals back to the graph)     CliqueStateMachine.jl:928-966
 #include <algorithm>
+#include <climits>
 #include <cstdint>
 #include <cstring>
+#include <iterator>
 #include <map>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -661,6 +664,141 @@ int32_t iifb200_plan_export(const iifb200_plan* p, iif_slot_desc* slots, iif_fac
 int32_t iifb200_plan_export_deconvs(const iifb200_plan* p, iif_deconv_op* deconvs) {
   if (!p || (!deconvs && !p->deconvs.empty())) return IIF_ERR_ARG;
   std::copy(p->deconvs.begin(), p->deconvs.end(), deconvs);
+  return IIF_OK;
+}
+
+int32_t iifb200_elimination_order_nd(int32_t nvars, int32_t nfactors, const int32_t* fac_off, const int32_t* fac_vars,
+                                     int32_t* order_out) {
+  auto fail = [&](int32_t code, const std::string& msg) { g_plan_error = msg; return code; };
+  if (nvars < 0 || nfactors < 0 || (nvars && !order_out) || (nfactors && (!fac_off || !fac_vars))) return fail(IIF_ERR_ARG, "elimination_order_nd: null argument");
+  // variable adjacency, neighbours in variable order (deterministic)
+  std::vector<std::vector<int>> adj(nvars);
+  for (int f = 0; f < nfactors; ++f)
+    for (int a = fac_off[f]; a < fac_off[f + 1]; ++a)
+      for (int b = fac_off[f]; b < fac_off[f + 1]; ++b) {
+        const int u = fac_vars[a], w = fac_vars[b];
+        if (u < 0 || u >= nvars || w < 0 || w >= nvars) return fail(IIF_ERR_ARG, "elimination_order_nd: variable id out of range");
+        if (u != w) adj[u].push_back(w);
+      }
+  for (auto& a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+  std::vector<int> order;
+  order.reserve(nvars);
+  std::vector<int> in(nvars, 0), seen(nvars, 0);   // stamps: in[v] == tag <=> v in the current node set
+  int tag = 0, stag = 0;
+  // BFS level sets of `nodes` (marked in[] == t) from `start`; returns the levels
+  auto levels = [&](int t, int start, std::vector<std::vector<int>>& lev) {
+    lev.clear();
+    ++stag;
+    seen[start] = stag;
+    std::vector<int> frontier{start};
+    while (!frontier.empty()) {
+      lev.push_back(frontier);
+      std::vector<int> nxt;
+      for (int u : frontier)
+        for (int w : adj[u])
+          if (in[w] == t && seen[w] != stag) { seen[w] = stag; nxt.push_back(w); }
+      frontier.swap(nxt);
+    }
+  };
+  // recursive bisection of a sorted node list
+  struct Rec {
+    static void run(std::vector<int> nodes, std::vector<int>& order, std::vector<int>& in, int& tag,
+                    const decltype(levels)& levels) {
+      while (!nodes.empty()) {
+        if (nodes.size() <= 2) { order.insert(order.end(), nodes.begin(), nodes.end()); return; }
+        const int t = ++tag;
+        for (int v : nodes) in[v] = t;
+        std::vector<std::vector<int>> lev;
+        levels(t, nodes.front(), lev);                   // start = smallest variable index
+        size_t reached = 0;
+        for (auto& l : lev) reached += l.size();
+        if (reached < nodes.size()) {                    // disconnected: this component first, then the rest
+          std::vector<int> comp, rest;
+          for (auto& l : lev) comp.insert(comp.end(), l.begin(), l.end());
+          std::sort(comp.begin(), comp.end());
+          std::set_difference(nodes.begin(), nodes.end(), comp.begin(), comp.end(), std::back_inserter(rest));
+          run(comp, order, in, tag, levels);
+          nodes.swap(rest);
+          continue;
+        }
+        const int far = lev.back().back();               // last variable the search reached: a peripheral one
+        const int t2 = ++tag;
+        for (int v : nodes) in[v] = t2;
+        levels(t2, far, lev);
+        if (lev.size() < 3) { order.insert(order.end(), nodes.begin(), nodes.end()); return; }
+        const double half = (double)nodes.size() / 2.0;
+        size_t acc = 0;
+        int cut = (int)lev.size() / 2;
+        for (size_t i = 0; i < lev.size(); ++i) {
+          acc += lev[i].size();
+          if ((double)acc >= half) { cut = std::min(std::max((int)i, 1), (int)lev.size() - 2); break; }
+        }
+        std::vector<int> left, right, sep = lev[cut];
+        for (int i = 0; i < cut; ++i) left.insert(left.end(), lev[i].begin(), lev[i].end());
+        for (size_t i = cut + 1; i < lev.size(); ++i) right.insert(right.end(), lev[i].begin(), lev[i].end());
+        std::sort(left.begin(), left.end());
+        std::sort(right.begin(), right.end());
+        std::sort(sep.begin(), sep.end());
+        run(left, order, in, tag, levels);
+        run(right, order, in, tag, levels);
+        order.insert(order.end(), sep.begin(), sep.end());
+        return;
+      }
+    }
+  };
+  std::vector<int> all(nvars);
+  for (int v = 0; v < nvars; ++v) all[v] = v;
+  Rec::run(all, order, in, tag, levels);
+  if ((int)order.size() != nvars) return fail(IIF_ERR_STATE, "elimination_order_nd: internal error");
+  std::copy(order.begin(), order.end(), order_out);
+  return IIF_OK;
+}
+
+int32_t iifb200_elimination_order_is(int32_t nvars, int32_t nfactors, const int32_t* fac_off, const int32_t* fac_vars,
+                                     int32_t slack, int32_t* order_out) {
+  auto fail = [&](int32_t code, const std::string& msg) { g_plan_error = msg; return code; };
+  if (nvars < 0 || nfactors < 0 || slack < 0 || (nvars && !order_out) || (nfactors && (!fac_off || !fac_vars)))
+    return fail(IIF_ERR_ARG, "elimination_order_is: bad argument");
+  std::vector<std::set<int>> adj(nvars);
+  for (int f = 0; f < nfactors; ++f)
+    for (int a = fac_off[f]; a < fac_off[f + 1]; ++a)
+      for (int b = fac_off[f]; b < fac_off[f + 1]; ++b) {
+        const int u = fac_vars[a], w = fac_vars[b];
+        if (u < 0 || u >= nvars || w < 0 || w >= nvars) return fail(IIF_ERR_ARG, "elimination_order_is: variable id out of range");
+        if (u != w) adj[u].insert(w);
+      }
+  std::vector<char> alive(nvars, 1), blocked(nvars, 0);
+  std::vector<int> order;
+  order.reserve(nvars);
+  int remaining = nvars;
+  while (remaining > 0) {
+    if (remaining <= 3) {
+      for (int v = 0; v < nvars; ++v) if (alive[v]) order.push_back(v);
+      break;
+    }
+    size_t mind = SIZE_MAX;
+    for (int v = 0; v < nvars; ++v) if (alive[v]) mind = std::min(mind, adj[v].size());
+    std::fill(blocked.begin(), blocked.end(), 0);
+    std::vector<int> chosen;
+    for (int v = 0; v < nvars; ++v) {              // greedy maximal independent set in variable order
+      if (!alive[v] || blocked[v] || adj[v].size() > mind + (size_t)slack) continue;
+      chosen.push_back(v);
+      blocked[v] = 1;
+      for (int w : adj[v]) blocked[w] = 1;
+    }
+    for (int v : chosen) {                         // eliminate: the neighbours become a clique
+      const std::vector<int> nb(adj[v].begin(), adj[v].end());
+      for (int a : nb) {
+        adj[a].erase(v);
+        for (int b : nb) if (b != a) adj[a].insert(b);
+      }
+      adj[v].clear();
+      alive[v] = 0;
+      --remaining;
+    }
+    order.insert(order.end(), chosen.begin(), chosen.end());
+  }
+  std::copy(order.begin(), order.end(), order_out);
   return IIF_OK;
 }
 

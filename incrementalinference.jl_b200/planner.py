@@ -114,3 +114,27 @@ def plan_tree(fg: G.FactorGraph, tree: TR.BayesTree, N=None, downsolve=True, gib
                         n_msgs, up_last, None, None, None, None, None, deconvs, [o.lane for o in ops[:nops]])
     plan.c_plan = CPlan(h, lib)
     return plan
+
+
+def _order(fg: G.FactorGraph, call):
+    lib = A.load_library()
+    labels = list(fg.variables)
+    idx = {l: i for i, l in enumerate(labels)}
+    off, flat = _csr([[idx[v] for v in f.variables] for f in fg.factors.values()])
+    out = np.zeros(max(len(labels), 1), dtype=np.int32)
+    st = call(lib, len(labels), len(fg.factors), A.as_ip(off), A.as_ip(flat), A.as_ip(out))
+    if st != A.IIF_OK:
+        raise A.IIFB200Error(f"elimination order failed ({st}): {lib.iifb200_plan_error().decode()}")
+    return [labels[i] for i in out[:len(labels)]]
+
+
+def elimination_order_nd(fg: G.FactorGraph):
+    """level-set bisection order from the library (iifb200_elimination_order_nd)"""
+    return _order(fg, lambda lib, nv, nf, off, flat, out: lib.iifb200_elimination_order_nd(nv, nf, off, flat, out))
+
+
+def elimination_order_is(fg: G.FactorGraph, slack: int = 1):
+    """independent-set (generalised odd-even reduction) order from the library (iifb200_elimination_order_is): what a
+    Julia caller passes as `solveTree!(fg; eliminationOrder = ...)` to get a bushy Bayes tree instead of the default
+    order's path"""
+    return _order(fg, lambda lib, nv, nf, off, flat, out: lib.iifb200_elimination_order_is(nv, nf, off, flat, slack, out))

@@ -325,6 +325,29 @@ function propagateBelief(dfg::AbstractDFG, destvar::DFGVariable, factors::Abstra
   return mkd, ipc
 end
 
+"""
+    parallelEliminationOrder(dfg; method = :is, slack = 1) -> Vector{Symbol}
+
+Variable elimination order from the library, for `solveTree!(dfg; eliminationOrder = IIFB200.parallelEliminationOrder(dfg))`
+(SolverAPI.jl:338) or `buildTreeReset!`: the Bayes tree of a pose chain gets depth O(log n) instead of n, so the cliques
+of a level solve side by side.  `:is` = rounds of independent low-degree variables (generalised odd-even reduction,
+iifb200_elimination_order_is), `:nd` = level-set bisection (iifb200_elimination_order_nd).
+"""
+function parallelEliminationOrder(dfg::AbstractDFG; method::Symbol = :is, slack::Integer = 1)
+  vlabels = ls(dfg); vidx = Dict(l => Int32(i - 1) for (i, l) in enumerate(vlabels))
+  flists = [Int32[vidx[v] for v in getVariableOrder(getFactor(dfg, f))] for f in lsf(dfg)]
+  off, flat = _csr(flists)
+  isempty(flat) && push!(flat, Int32(0))
+  order = zeros(Int32, max(length(vlabels), 1))
+  st = method == :nd ?
+    ccall((:iifb200_elimination_order_nd, LIB), Int32, (Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+          length(vlabels), length(flists), off, flat, order) :
+    ccall((:iifb200_elimination_order_is, LIB), Int32, (Int32, Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}),
+          length(vlabels), length(flists), off, flat, slack, order)
+  st == 0 || error("iifb200_elimination_order failed ($st): " * unsafe_string(ccall((:iifb200_plan_error, LIB), Cstring, ())))
+  return Symbol[vlabels[i + 1] for i in order[1:length(vlabels)]]
+end
+
 # ---- boundary B4: the whole tree pass ---------------------------------------------------------------
 _csr(lists) = (Int32[0; cumsum(length.(lists))], Int32[x for l in lists for x in l])
 

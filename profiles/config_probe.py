@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import iifb200  # noqa: E402,F401
 from iifb200 import compile as CP  # noqa: E402
+from iifb200 import planner as PL  # noqa: E402
 from iifb200 import solver as SV  # noqa: E402
 from iifb200 import tree as TR  # noqa: E402
 from iifb200 import workloads as W  # noqa: E402
@@ -40,6 +41,6 @@ def probe(name, fg, order):
 fg = W.four_door(N=200, seed=42)
 probe("C3 four-door N=200", fg, TR.getEliminationOrder(fg, "qr"))
 fg = W.circular_chain(n=500, N=150, seed=42)
-probe("C4 circular chain 500 poses N=150", fg, W.chain_nd_order(500))
+probe("C4 circular chain 500 poses N=150", fg, PL.elimination_order_is(fg))
 fg = W.euclid2_grid(rows=50, cols=100, N=100, seed=42, closure_every=5)
-probe("C5 Euclid(2) grid 5000 poses N=100", fg, TR.getEliminationOrder(fg, "nd"))
+probe("C5 Euclid(2) grid 5000 poses N=100", fg, PL.elimination_order_is(fg) if os.environ.get("IIFB200_PROBE_ORDER", "is") == "is" else TR.getEliminationOrder(fg, "nd"))

@@ -173,3 +173,37 @@ def test_b3_context_pool_equals_the_serial_calls(built):
         b3.close()
     ts.close()
     assert np.array_equal(res[0].pts, res[1].pts) and np.array_equal(res[0].bw, res[1].bw)
+
+
+def test_library_elimination_orders(built):
+    """iifb200_elimination_order_nd / _is reproduce the Python mirror's order on chains, grids with loop closures, forests
+    (disconnected graphs), rings and the reference's small canonical graphs; on a chain the resulting tree has
+    logarithmic depth (the default order's tree is a path)."""
+    cases = [W.scalar_chain(37, N=8, seed=1), W.scalar_chain(1000, N=8, seed=1),
+             W.euclid2_grid(rows=5, cols=9, N=8, seed=2, closure_every=2), W.scalar_chain_sessions(3, 12, N=8),
+             W.circular_chain(n=15, N=8), W.generateGraph_Kaess(N=8), W.generateGraph_CaesarRing1D(N=8), W.four_door(N=8)]
+    for fg in cases:
+        ref = TR.nested_dissection_order(fg)
+        got = PL.elimination_order_nd(fg)
+        assert got == ref
+        assert sorted(got) == sorted(fg.variables)
+        for slack in (0, 1, 2):
+            assert PL.elimination_order_is(fg, slack) == TR.independent_set_order(fg, slack)
+    fg = cases[1]
+    for order in (PL.elimination_order_nd(fg), PL.elimination_order_is(fg)):
+        tree = TR.buildTree(fg, order)
+        depth = {}
+        for c in tree.cliques:                      # parents are created before their children
+            depth[c.id] = 0 if c.parent is None else depth[c.parent] + 1
+        assert max(depth.values()) <= 2 * int(np.ceil(np.log2(1000))) + 2
+        assert max(len(c.frontals) for c in tree.cliques) <= 3
+    tree = TR.buildTree(fg, PL.elimination_order_nd(fg))
+    depth = {}
+    for c in tree.cliques:                      # parents are created before their children
+        depth[c.id] = 0 if c.parent is None else depth[c.parent] + 1
+    assert max(depth.values()) <= 2 * int(np.ceil(np.log2(1000))) + 2
+    tree_nat = TR.buildTree(fg, TR.getEliminationOrder(fg, "natural"))
+    dn = {}
+    for c in tree_nat.cliques:
+        dn[c.id] = 0 if c.parent is None else dn[c.parent] + 1
+    assert max(dn.values()) > 900
