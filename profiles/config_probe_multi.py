@@ -16,6 +16,7 @@ import torch.distributed as dist  # noqa: E402
 
 import iifb200  # noqa: E402,F401
 from iifb200 import compile as CP  # noqa: E402
+from iifb200 import planner as PL  # noqa: E402
 from iifb200 import tree as TR  # noqa: E402
 from iifb200 import workloads as W  # noqa: E402
 from iifb200.multigpu import ShardedTreeSolver  # noqa: E402
@@ -28,14 +29,16 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 if what == "c4":
     n = 500
-    fg, order = W.circular_chain(n=n, N=150, seed=42), W.chain_nd_order(500)
+    fg = W.circular_chain(n=n, N=150, seed=42)
+    order = PL.elimination_order_is(fg)
 elif what == "c5":
     rows, cols = 50, 100
     fg = W.euclid2_grid(rows=rows, cols=cols, N=100, seed=42, closure_every=5)
-    order = TR.getEliminationOrder(fg, "nd")
+    order = PL.elimination_order_is(fg)
 else:
     n = 1000
-    fg, order = W.scalar_chain(n, N=100, seed=42), W.chain_nd_order(1000)
+    fg = W.scalar_chain(n, N=100, seed=42)
+    order = PL.elimination_order_is(fg)
 fg.solverParams.useMsgLikelihoods = uml
 sv = ShardedTreeSolver(fg, order, rank, world, local, dist, gather="root")
 nv = len(fg.variables)
