@@ -456,6 +456,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         if (k + 3 * ch < np) s3 += rowp[k + 3 * ch];
       }
       const double c1 = s0 + s1, c2 = c1 + s2, tot = c2 + s3;
+      IIF_PHASE(21);
       if (!(tot > 1e-280)) return exact();   // every weight underflowed (or NaN): the oracle's exact form
       const double thr = u * tot;
       double run = 0.0;
@@ -469,8 +470,10 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         if (thr < nx) break;
         run = nx;
       }
+      IIF_PHASE(22);
       double w[4];
       eval(pc << 2, w);
+      IIF_PHASE(23);
       int pick = min((pc << 2) + 3, nz - 1);  // rounding left thr >= total: the last candidate (as the oracle does)
       double cum = run;
 #pragma unroll
@@ -478,6 +481,7 @@ iif_product_kernel(DeviceGraph g, const ProdTask* __restrict__ tasks, const doub
         cum += w[q];
         if ((pc << 2) + q < nz && thr < cum) { pick = (pc << 2) + q; break; }
       }
+      IIF_PHASE(24);
       return pick;
     };
     // per-level random numbers of the owned sample, drawn by ALL threads during the build pass

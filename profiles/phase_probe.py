@@ -22,7 +22,8 @@ KER = {"bandwidth": {8: "load", 13: "search+write"},
                 12: "bandwidth (all)", 13: "write bw/slot"},
        "product": {8: "load", 9: "ball trees", 10: "node stats + rsqrt", 20: "gibbs: samplePoint per level",
                    16: "gibbs: conditional setup", 17: "gibbs: barrier before build", 7: "gibbs: flat weight build",
-                   18: "gibbs: barrier after build", 15: "gibbs: owner pick", 11: "gibbs: rest",
+                   18: "gibbs: barrier after build", 15: "gibbs: owner pick (rest)", 21: "  pick: row sums", 22: "  pick: walk to the piece",
+                   23: "  pick: piece re-evaluation", 24: "  pick: candidate", 11: "gibbs: rest",
                    12: "final sample", 13: "bandwidth (all)", 14: "write"}}
 from iifb200 import _abi as A, compile as CP  # noqa: E402
 import parity_cases as PC  # noqa: E402
