@@ -334,8 +334,9 @@ of a level solve side by side.  `:is` = rounds of independent low-degree variabl
 iifb200_elimination_order_is), `:nd` = level-set bisection (iifb200_elimination_order_nd).
 """
 function parallelEliminationOrder(dfg::AbstractDFG; method::Symbol = :is, slack::Integer = 1)
-  vlabels = ls(dfg); vidx = Dict(l => Int32(i - 1) for (i, l) in enumerate(vlabels))
-  flists = [Int32[vidx[v] for v in getVariableOrder(getFactor(dfg, f))] for f in lsf(dfg)]
+  vlabels = listVariables(dfg); sort!(vlabels; by = l -> getVariable(dfg, l).nstime)   # graph (insertion) order
+  vidx = Dict(l => Int32(i - 1) for (i, l) in enumerate(vlabels))
+  flists = [Int32[vidx[v] for v in getVariableOrder(getFactor(dfg, f))] for f in listFactors(dfg)]
   off, flat = _csr(flists)
   isempty(flat) && push!(flat, Int32(0))
   order = zeros(Int32, max(length(vlabels), 1))
@@ -360,6 +361,8 @@ replays the pass as a CUDA graph and iifb200_download_slots returns every poster
 setValKDE! (CSM step 5, updateFromSubgraph).  SolverParams.useMsgLikelihoods is honoured: the library builds the joint
 up messages (differentials + one MsgPrior per class) itself.
 """
+solveTree_b200!(dfg::AbstractDFG; kw...) =                      # order from the library, tree from the reference
+  solveTree_b200!(dfg, IIF.buildTreeReset!(dfg, parallelEliminationOrder(dfg)); kw...)
 function solveTree_b200!(dfg::AbstractDFG, tree; solveKey::Symbol = :default, lanes::Integer = 4,
                          downsolve::Bool = getSolverParams(dfg).downsolve)
   sp = getSolverParams(dfg)
