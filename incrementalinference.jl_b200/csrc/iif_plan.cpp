@@ -247,8 +247,14 @@ int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const
       if (v < 0 || v >= nv) { delete P; return fail(IIF_ERR_ARG, "plan_tree: clique variable index out of range"); }
       cslot[c][v] = add_slot(v);
     }
+    if (t->parent[c] >= ncl || t->parent[c] == c) { delete P; return fail(IIF_ERR_ARG, "plan_tree: clique parent index out of range"); }
     if (t->parent[c] >= 0) children[t->parent[c]].push_back(c);
   }
+  // running-intersection property: a clique's separators live in its parent (messages are addressed through them)
+  for (int c = 0; c < ncl; ++c)
+    if (t->parent[c] >= 0)
+      for (int v : sp[c])
+        if (!cslot[t->parent[c]].count(v)) { delete P; return fail(IIF_ERR_ARG, "plan_tree: separator missing from the parent clique"); }
   // variable -> factors (graph order)
   std::vector<std::vector<int>> by_var(nv);
   for (int f = 0; f < nf; ++f)

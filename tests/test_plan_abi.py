@@ -115,6 +115,13 @@ def test_c_planner_errors(built):
     tree = TR.buildTree(fg, order)
     with pytest.raises(A.IIFB200Error):
         PL.plan_tree(fg, tree, N=100000)
+    # a malformed clique table (a separator its parent does not hold) is refused, not lowered
+    bad = TR.buildTree(fg, order)
+    child = next(c for c in bad.cliques if c.parent is not None)
+    stranger = next(v for v in fg.variables if v not in bad.cliques[child.parent].allvars and v not in child.allvars)
+    child.separators = child.separators + [stranger]
+    with pytest.raises(A.IIFB200Error, match="separator missing"):
+        PL.plan_tree(fg, bad)
 
 
 @pytest.mark.gpu
