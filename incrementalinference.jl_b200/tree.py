@@ -382,6 +382,8 @@ class SolvePlan:
     deconvs: Optional[list] = None    # IIF_S_DECONV specs (useMsgLikelihoods=true): factor, out_slot, N, call_id
     op_lane: Optional[List[int]] = None   # lane of every op of `sched_waved` (0 = none), see assign_lanes
     c_plan: object = None             # planner.CPlan when the plan was made by iifb200_plan_tree (libiifb200.so)
+    up_messages: Optional[dict] = None  # useMsgLikelihoods: clique id -> content of its joint up message (LikelihoodMessage
+    #                                     .jointmsg: relatives as variable pairs, prior variables, hasPriors) for inspection
 
 
 def _levelize(ops, reads, writes):
@@ -761,11 +763,13 @@ def compile_solve(fg: G.FactorGraph, tree: BayesTree, N: Optional[int] = None, d
           for (k, a, _) in sched]
     lane = assign_lanes(tree, opc, wt, waves, reads, writes, lanes)
     frozen = T.freeze()
+    msgs = {cid: dict(relatives=[tuple(r["variables"]) for r in m["relatives"]], priors=[l for l, _ in m["priors"]],
+                      hasPriors=m["hasPriors"]) for cid, m in upmsg.items()} if uml else None
     return SolvePlan(T, frozen, props, sched, wave_off, sched_waved, var_slot, nconv[0], len(props), n_msgs,
                      up_last, [opc[i] for i in order], [waves[i] for i in order], [reads[i] for i in order],
                      [writes[i] for i in order],
                      {**{s: cid for (cid, _), s in cslot.items()}, **{dc["out_slot"]: dc["clique"] for dc in deconvs}},
-                     deconvs, [lane[i] for i in order])
+                     deconvs, [lane[i] for i in order], None, msgs)
 
 
 def plan_call_span(plan: SolvePlan) -> int:

@@ -303,3 +303,53 @@ def test_api_fourdoor_and_circular_as_written(built):
         p = G.getPoints(G.getBelief(fg, f"x{k}"))[:, 0]
         mu = np.arctan2(np.sin(p).mean(), np.cos(p).mean())
         assert abs(PC.wrap(mu - k)) < 0.35, (k, mu)
+
+
+@pytest.mark.parametrize("kind", ["disjoint", "homogeneous"])
+def test_joint_enforcement_known_answers(built, kind):
+    """testJointEnforcement.jl — the reference's known answers for _generateMsgJointRelativesPriors on the clique of x3
+    with separators {x0, x2} (eliminationOrder x3, x1, x2, x0):
+      :3-77   x3 tied to x0 and x2 by EuclidDistance factors: the path between the separators is homogeneous but NOT
+              of the default relative type of ContinuousEuclid{2} (LinearRelative) => 0 relatives, 2 priors;
+      :80-150 the same with LinearRelative factors => 1 relative between {x0, x2}, 0 priors.
+    Checked on the plan of the Python mirror and on the library's planner (iifb200_plan_tree)."""
+    from iifb200 import planner as PL
+    rng = np.random.default_rng(1)
+    fg = G.initfg(G.SolverParams(N=32, graphinit=False, useMsgLikelihoods=True))
+    for k, off in (("x0", 0.0), ("x1", 10.0), ("x2", 20.0)):
+        G.addVariable(fg, k, G.Position(2))
+        G.initVariable(fg, k, rng.standard_normal((32, 2)) + off, bw=[1.0, 1.0])
+    Z = G.MvNormal([10.0, 10.0], np.eye(2))
+    G.addFactor(fg, ["x0", "x1"], G.LinearRelative(Z), graphinit=False)
+    G.addFactor(fg, ["x1", "x2"], G.LinearRelative(Z), graphinit=False)
+    G.addVariable(fg, "x3", G.Position(2))
+    G.initVariable(fg, "x3", rng.standard_normal((32, 2)) + 30.0, bw=[1.0, 1.0])
+    if kind == "disjoint":
+        G.addFactor(fg, ["x2", "x3"], G.EuclidDistance(G.Normal(10.0, 1.0)), graphinit=False)
+        G.addFactor(fg, ["x0", "x3"], G.EuclidDistance(G.Normal(30.0, 1.0)), graphinit=False)
+    else:
+        G.addFactor(fg, ["x2", "x3"], G.LinearRelative(Z), graphinit=False)
+        G.addFactor(fg, ["x0", "x3"], G.LinearRelative(Z), graphinit=False)
+    tree = TR.buildTree(fg, ["x3", "x1", "x2", "x0"])
+    c3 = next(c for c in tree.cliques if "x3" in c.frontals)
+    assert sorted(c3.separators) == ["x0", "x2"]
+    plan = TR.compile_solve(fg, tree, useMsgLikelihoods=True)
+    fz = plan.frozen
+    mine = [d for d in plan.deconvs if d["clique"] == c3.id]                      # relatives of x3's up message
+    slots3 = {s for s, cid in plan.slot_clique.items() if cid == c3.id}
+    priors = [i for i in range(fz["nfactors"]) if fz["factors"][i].kind == A.F_MSG_PRIOR
+              and fz["dists"][fz["factors"][i].dist].slot in slots3]             # MsgPriors built from x3's beliefs
+    msg = plan.up_messages[c3.id]                                                # the message itself (upTx.jointmsg)
+    if kind == "disjoint":
+        assert len(msg["relatives"]) == 0 and sorted(msg["priors"]) == ["x0", "x2"]          # :72-76
+        # the parent adds none of the two priors: the sending sub-graph holds no prior (hasPriors false) and both
+        # variables are touched by the parent's own factors (addLikelihoodPriorCommon!, TreeMessageUtils.jl:454-469)
+        assert len(mine) == 0 and not msg["hasPriors"] and len(priors) == 0
+    else:
+        assert [set(r) for r in msg["relatives"]] == [{"x0", "x2"}] and msg["priors"] == []  # :145-149
+        assert len(mine) == 1 and len(priors) == 0
+        f = fz["factors"][mine[0]["factor"]]
+        assert f.kind == A.F_LINEAR_RELATIVE and {plan.slot_clique[f.slot[0]], plan.slot_clique[f.slot[1]]} == {c3.id}
+    got = PL.plan_tree(fg, tree, useMsgLikelihoods=True)
+    assert [{k: d[k] for k in ("factor", "out_slot", "N", "call_id")} for d in plan.deconvs] == got.deconvs
+    assert got.frozen["nfactors"] == fz["nfactors"] and got.props == plan.props

@@ -149,3 +149,30 @@ def test_solve_sets_ppe(built):
         first[l] = ppe.suggested[0]
     SV.solveTree(fg)
     assert any(abs(SV.getPPE(fg, l).suggested[0] - first[l]) > 0 for l in fg.variables)   # fresh noise, fresh estimate
+
+
+@pytest.mark.parametrize("seed", [42, 7, 19])
+def test_multimodal_1d(built, seed):
+    """testMultimodal1D.jl:34-101: landmark priors at -30 / +30, two sightings from x1 (-20 and +20, sigma 1) with
+    multihypo = [1, 0.4, 0.6] between a free landmark and the prior one; gibbsIters = 6, spreadNH = 0.3, given
+    elimination order.  x1 sits on one of the two consistent modes, the prior landmarks stay, the free ones keep mass
+    near the sighted positions."""
+    l1, l2, p_meas = -30.0, 30.0, 0.4
+    fg = G.initfg(G.SolverParams(N=100, gibbsIters=6, spreadNH=0.3, seed=seed))
+    G.addVariable(fg, "lp1", G.ContinuousScalar)
+    G.addFactor(fg, ["lp1"], G.Prior(G.Normal(l1, 1.0)), graphinit=False)
+    G.addVariable(fg, "lp2", G.ContinuousScalar)
+    G.addFactor(fg, ["lp2"], G.Prior(G.Normal(l2, 1.0)), graphinit=False)
+    G.addVariable(fg, "x1", G.ContinuousScalar)
+    G.addVariable(fg, "lm2", G.ContinuousScalar)
+    G.addFactor(fg, ["x1", "lm2", "lp2"], G.LinearRelative(G.Normal(20.0, 1.0)), multihypo=[1.0, p_meas, 1 - p_meas], graphinit=False)
+    G.addVariable(fg, "lm1", G.ContinuousScalar)
+    G.addFactor(fg, ["x1", "lm1", "lp1"], G.LinearRelative(G.Normal(-20.0, 1.0)), multihypo=[1.0, p_meas, 1 - p_meas], graphinit=False)
+    SV.solveTree(fg, eliminationOrder=["x1", "lm1", "lm2", "lp1", "lp2"])
+    n = fg.solverParams.N
+    p = {l: G.getPoints(G.getBelief(fg, l))[:, 0] for l in fg.variables}
+    assert 0.7 * n < ((-20 < p["x1"]) & (p["x1"] < 0)).sum() + ((0 < p["x1"]) & (p["x1"] < 20)).sum(), np.sort(p["x1"])[::10]
+    assert 0.7 * n < ((-38 < p["lp1"]) & (p["lp1"] < -28)).sum()
+    assert 0.7 * n < ((28 < p["lp2"]) & (p["lp2"] < 38)).sum()
+    assert 0.1 * n < ((-38 < p["lm1"]) & (p["lm1"] < -25)).sum(), np.sort(p["lm1"])[::10]
+    assert 0.1 * n < ((25 < p["lm2"]) & (p["lm2"] < 38)).sum(), np.sort(p["lm2"])[::10]
