@@ -185,3 +185,32 @@ def generateGraph_CaesarRing1D(N=100, seed=42, graphinit=False):
     G.addFactor(fg, ["x0", "l1"], G.LinearRelative(G.Normal()))
     G.addFactor(fg, ["x6", "l1"], G.LinearRelative(G.Normal()))
     return fg
+
+
+def generateGraph_LineStep(lineLength, poseEvery=2, landmarkEvery=4, posePriorsAt=(0,), landmarkPriorsAt=(), sightDistance=4,
+                           graphinit=False, sigma_pose_prior=0.1, sigma_lm_prior=0.1, sigma_pose_pose=0.1, sigma_pose_lm=0.1,
+                           solverParams=None):
+    """CanonicalGraphExamples.jl:154-238 (scalar, noise-free means): poses every `poseEvery` steps along a line, landmarks
+    every `landmarkEvery`, odometry between consecutive poses, sightings within `sightDistance`."""
+    fg = G.initfg(solverParams or G.SolverParams(graphinit=graphinit))
+    xs, lms = [], []
+    for i in range(lineLength + 1):
+        if i % poseEvery == 0:
+            xs.append(i)
+            G.addVariable(fg, f"x{i}", G.ContinuousScalar)
+            if i in posePriorsAt:
+                G.addFactor(fg, [f"x{i}"], G.Prior(G.Normal(float(i), sigma_pose_prior)), graphinit=graphinit)
+            if i > 0:
+                G.addFactor(fg, [f"x{i - poseEvery}", f"x{i}"], G.LinearRelative(G.Normal(float(poseEvery), sigma_pose_pose)),
+                            graphinit=graphinit)
+        if landmarkEvery != 0 and i % landmarkEvery == 0:
+            lms.append(i)
+            G.addVariable(fg, f"lm{i}", G.ContinuousScalar)
+            if i in landmarkPriorsAt:
+                G.addFactor(fg, [f"lm{i}"], G.Prior(G.Normal(float(i), sigma_lm_prior)), graphinit=graphinit)
+    for xi in xs:
+        for lmi in lms:
+            dist = lmi - xi
+            if abs(dist) < sightDistance:
+                G.addFactor(fg, [f"x{xi}", f"lm{lmi}"], G.LinearRelative(G.Normal(float(dist), sigma_pose_lm)), graphinit=graphinit)
+    return fg

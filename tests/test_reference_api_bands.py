@@ -176,3 +176,48 @@ def test_multimodal_1d(built, seed):
     assert 0.7 * n < ((28 < p["lp2"]) & (p["lp2"] < 38)).sum()
     assert 0.1 * n < ((-38 < p["lm1"]) & (p["lm1"] < -25)).sum(), np.sort(p["lm1"])[::10]
     assert 0.1 * n < ((25 < p["lm2"]) & (p["lm2"] < 38)).sum(), np.sort(p["lm2"])[::10]
+
+
+def test_forest_of_orphaned_graphs(built):
+    """testSolveOrphanedFG.jl: two disconnected chains in one graph, given elimination order: a forest with two roots
+    (the cliques of x1 and x10), one child each, and the reference's mean bands."""
+    from iifb200 import tree as TR
+    fg = G.initfg(G.SolverParams(N=100, seed=4))
+    G.addVariable(fg, "x0", G.ContinuousScalar)
+    G.addFactor(fg, ["x0"], G.Prior(G.Normal(0.0, 0.1)))
+    G.addVariable(fg, "x1", G.ContinuousScalar)
+    G.addFactor(fg, ["x0", "x1"], G.LinearRelative(G.Normal(10.0, 0.1)))
+    G.addVariable(fg, "x2", G.ContinuousScalar)
+    G.addFactor(fg, ["x1", "x2"], G.LinearRelative(G.Normal(10.0, 0.1)))
+    G.addVariable(fg, "x10", G.ContinuousScalar)
+    G.addFactor(fg, ["x10"], G.Prior(G.Normal(0.0, 1.0)))
+    G.addVariable(fg, "x11", G.ContinuousScalar)
+    G.addFactor(fg, ["x10", "x11"], G.LinearRelative(G.Normal(-10.0, 1.0)))
+    G.addVariable(fg, "x12", G.ContinuousScalar)
+    G.addFactor(fg, ["x11", "x12"], G.LinearRelative(G.Normal(-10.0, 1.0)))
+    vo = ["x12", "x2", "x0", "x11", "x1", "x10"]
+    ts = SV.solveTree(fg, eliminationOrder=vo)
+    cl = ts.tree.cliques
+    of = lambda v: next(c for c in cl if v in c.frontals)  # noqa: E731
+    assert of("x1").parent is None and of("x10").parent is None
+    assert len(of("x1").children) == 1 and len(of("x10").children) == 1
+    assert len(of("x2").children) == 0 and len(of("x12").children) == 0
+    for l, want, band in (("x0", 0, 1.0), ("x1", 10, 2.0), ("x2", 20, 3.0), ("x10", 0, 2.0), ("x11", -10, 4.0), ("x12", -20, 5.0)):
+        assert abs(_mean(fg, l) - want) < band, (l, _mean(fg, l))
+
+
+def test_skip_downsolve_with_msg_likelihoods(built):
+    """testSkipUpDown.jl:8-32 (first half): generateGraph_LineStep(6; poseEvery = 1) with the landmark lm0 sighted from
+    x0 and x6 only, useMsgLikelihoods = true, downsolve = false: every PPE within 0.2 of the variable's index."""
+    fg = W.generateGraph_LineStep(6, poseEvery=1, landmarkEvery=7, posePriorsAt=(0,), landmarkPriorsAt=(), sightDistance=1,
+                                  solverParams=G.SolverParams(N=100, seed=6, graphinit=False))
+    G.addFactor(fg, ["x6", "lm0"], G.LinearRelative(G.Normal(-6.0, 0.1)), graphinit=False)    # x0lm0f1 came with sightDistance 1
+    assert sorted(fg.factors) == sorted(["x0f1", "x0lm0f1", "x6lm0f1"] + [f"x{k}x{k+1}f1" for k in range(6)])
+    fg.solverParams.graphinit = True
+    fg.solverParams.useMsgLikelihoods = True
+    fg.solverParams.downsolve = False
+    ts = SV.solveTree(fg)
+    assert ts.plan.up_last_wave == len(ts.plan.wave_off) - 1 or all(k == 2 for k, _, _ in ts.plan.sched_waved[ts.plan.wave_off[ts.plan.up_last_wave]:])
+    for l in fg.variables:
+        want = float(l.lstrip("xlm"))
+        assert abs(SV.getPPE(fg, l).suggested[0] - want) < 0.2, (l, SV.getPPE(fg, l).suggested)
