@@ -483,8 +483,8 @@ def run_b200(args, rank, world, local_rank):
         "posterior_mean_abs_err_max": post_mean_err,
     }
     if world == 1 and not args.no_b3:
-        # boundary B3 for comparison: the same pass driven ONE propagateBelief per C-ABI round trip (set_graph on the
-        # mini graph, one upload, propagate, download), the call sequence of julia/IIFB200.jl's propagateBelief
+        # boundary B3 for comparison: the same pass driven ONE propagateBelief per C-ABI round trip
+        # (iifb200_propagate_once on the mini graph), the call julia/IIFB200.jl's propagateBelief makes
         b3 = SV.B3Driver(plan, CP.solver_params_c(fg.solverParams, 7))
         ar = CP.HostArena(plan.frozen)
         for l, v in fg.variables.items():
@@ -496,8 +496,8 @@ def run_b200(args, rank, world, local_rank):
         dt = time.perf_counter() - t0
         out["e2e_b3"] = {"value": total_conv / dt, "unit": "conv/s", "ms_per_step": 1e3 * dt,
                          "round_trips_per_step": len(plan.props),
-                         "note": "one propagateBelief per call through set_graph / upload_slots / propagate_batch / "
-                                 "download_belief (Python mirror of the Julia shim's B3 sequence; descriptor tables "
+                         "note": "one propagateBelief per C-ABI call (iifb200_propagate_once: descriptor tables + host beliefs "
+                                 "in, posterior out; Python mirror of the Julia shim's B3 sequence; descriptor tables "
                                  "prebuilt outside the timed region)"}
         b3.close()
         # the same sequence with the shim's context pool: the reference runs sibling cliques as concurrent Tasks, so

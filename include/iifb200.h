@@ -317,6 +317,15 @@ int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_
 /* V independent propagateBelief calls on device-resident slots (one launch sequence).
  * Posteriors are written into out_slot on the device; nothing is copied to the host. */
 int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* ops);
+/* ONE propagateBelief per call, host buffers in and out (boundary B3, GraphProductOperations.jl:16-64): what
+ * iifb200_set_graph + iifb200_upload_slots(0, nslots) + iifb200_propagate_batch(1) + iifb200_download_belief(op->out_slot)
+ * do, with one stream synchronisation instead of five.  pts / bw / npts / flags cover all nslots slots, packed as for
+ * iifb200_upload_slots; out_pts receives op->N points of the destination's dimension. */
+int32_t iifb200_propagate_once(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots, int32_t nfactors,
+                               const iif_factor_desc* factors, int32_t ndists, const iif_dist_desc* dists, int32_t nparams,
+                               const double* dparams, const iif_solver_params* sp, const double* pts, const double* bw,
+                               const int32_t* npts, const int32_t* flags, const iif_prop_op* op, int32_t* out_npts,
+                               double* out_pts, double* out_bw, double* out_ipc);
 
 /* ---- clique / tree schedule (throughput mode, boundary B4) ------------------------ */
 /* A schedule is a sequence of waves; wave w holds ops [wave_off[w], wave_off[w+1]) that are

@@ -135,6 +135,8 @@ SYMBOLS = {
     "iifb200_deconv_batch": (C.c_int32, [_vp, C.c_int32, _ip, _ip, _ip, _dp, _dp]),
     "iifb200_mmd": (C.c_int32, [_vp, C.c_int32, _ip, _ip, _ip, _ip, _dp, _dp, C.c_double, _dp]),
     "iifb200_propagate_batch": (C.c_int32, [_vp, C.c_int32, P(PropOp)]),
+    "iifb200_propagate_once": (C.c_int32, [_vp, C.c_int32, P(SlotDesc), C.c_int32, P(FactorDesc), C.c_int32, P(DistDesc),
+                                           C.c_int32, _dp, P(SolverParamsC), _dp, _dp, _ip, _ip, P(PropOp), _ip, _dp, _dp, _dp]),
     "iifb200_schedule_build": (C.c_int32, [_vp, C.c_int32, _ip, C.c_int32, P(SchedOp), C.c_int32,
                                            P(PropOp), _ip]),
     "iifb200_schedule_build_ex": (C.c_int32, [_vp, C.c_int32, _ip, C.c_int32, P(SchedOp), C.c_int32,

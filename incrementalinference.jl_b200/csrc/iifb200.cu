@@ -116,6 +116,7 @@ struct iifb200_ctx {
   int nflags = 0;
   int64_t launches = 0;
   int max_smem_optin = 0;  // dynamic budget of a kernel = this - IIF_STATIC_SMEM_RESERVE
+  bool defer_sync = false; // inside iifb200_propagate_once: set_graph leaves the stream unsynchronised
   int num_sms = 148;
 };
 
@@ -365,7 +366,7 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
   if (!ctx) return IIF_ERR_ARG;
   if (nslots < 1 || !slots || nfactors < 0 || ndists < 0 || !sp) return fail(ctx, IIF_ERR_ARG, "set_graph: bad arguments");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->defer_sync) CK(cudaStreamSynchronize(ctx->stream));
   free_graph(ctx, false);
   for (int s = 0; s < nslots; ++s) {
     if (slots[s].dim < 1 || slots[s].dim > IIF_MAX_DIM) return fail(ctx, IIF_ERR_ARG, "slot dim out of range");
@@ -449,7 +450,7 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
   dg.sp = ctx->d_sp;
   CK(cudaMemcpyAsync(ctx->d_sp, sp, sizeof(iif_solver_params), cudaMemcpyHostToDevice, ctx->stream));
   dg.nslots = nslots; dg.nfactors = nfactors; dg.ndists = ndists;
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->defer_sync) CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
 }
 
@@ -1489,6 +1490,57 @@ int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* 
     if (e != cudaSuccess) { free_schedule(s); return fail(ctx, IIF_ERR_CUDA, std::string("propagate_batch: ") + cudaGetErrorString(e)); }
     for (size_t i = 0; i < stat.size(); ++i)
       if (stat[i] != IIF_OK) { st = fail(ctx, stat[i], std::string("propagate_batch: device reported '") + status_name(stat[i]) + "'"); break; }
+  }
+  free_schedule(s);
+  return st;
+}
+
+int32_t iifb200_propagate_once(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots, int32_t nfactors,
+                               const iif_factor_desc* factors, int32_t ndists, const iif_dist_desc* dists, int32_t nparams,
+                               const double* dparams, const iif_solver_params* sp, const double* pts, const double* bw,
+                               const int32_t* npts, const int32_t* flags, const iif_prop_op* op, int32_t* out_npts,
+                               double* out_pts, double* out_bw, double* out_ipc) {
+  if (!ctx) return IIF_ERR_ARG;
+  if (!op || !pts || !bw || !npts || !flags || !out_pts) return fail(ctx, IIF_ERR_ARG, "propagate_once: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));   // earlier work of this context is complete (normally a no-op)
+  ctx->defer_sync = true;
+  int32_t st = iifb200_set_graph(ctx, nslots, slots, nfactors, factors, ndists, dists, nparams, dparams, sp, nullptr);
+  ctx->defer_sync = false;
+  if (st != IIF_OK) return st;
+  st = iifb200_upload_slots(ctx, 0, nslots, pts, bw, npts, flags);
+  if (st != IIF_OK) return st;
+  if (op->out_slot < 0 || op->out_slot >= nslots) return fail(ctx, IIF_ERR_ARG, "propagate_once: out_slot out of range");
+  iif_sched_op so;
+  so.kind = IIF_S_PROPAGATE; so.a = 0; so.b = 0; so.lane = 0;
+  int32_t wo[2] = {0, 1};
+  Schedule* s = nullptr;
+  st = build_schedule(ctx, 1, wo, 1, &so, 1, op, 0, nullptr, &s, true);
+  if (st != IIF_OK) { free_schedule(s); return st; }
+  int nk = 0;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  st = enqueue_waves(ctx, s, 0, 1, &nk, false);
+  if (st == IIF_OK) {
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->timed = true;
+    ctx->launches += nk;
+    const iif_slot_desc& S = ctx->slots[op->out_slot];
+    const int n = op->N;                      // a propagateBelief always leaves N points in its destination
+    std::vector<int32_t> stat(s->nstatus());
+    double b[IIF_MAX_DIM], q[IIF_MAX_DIM];
+    cudaError_t e = cudaMemcpyAsync(stat.data(), s->d_status, sizeof(int32_t) * stat.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_pts, ctx->dg.pts + S.pts_off, sizeof(double) * n * S.dim, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b, ctx->dg.bw + (int64_t)op->out_slot * IIF_MAX_DIM, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q, ctx->dg.ipc + (int64_t)op->out_slot * IIF_MAX_DIM, sizeof(q), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free_schedule(s); return fail(ctx, IIF_ERR_CUDA, std::string("propagate_once: ") + cudaGetErrorString(e)); }
+    for (size_t i = 0; i < stat.size(); ++i)
+      if (stat[i] != IIF_OK) { st = fail(ctx, stat[i], std::string("propagate_once: device reported '") + status_name(stat[i]) + "'"); break; }
+    if (st == IIF_OK) {
+      if (out_npts) *out_npts = n;
+      if (out_bw) for (int c = 0; c < S.dim; ++c) out_bw[c] = b[c];
+      if (out_ipc) for (int c = 0; c < S.dim; ++c) out_ipc[c] = q[c];
+    }
   }
   free_schedule(s);
   return st;

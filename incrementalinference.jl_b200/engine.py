@@ -48,6 +48,24 @@ class Engine:
             self.ctx, frozen["nslots"], frozen["slots"], frozen["nfactors"], frozen["factors"], frozen["ndists"],
             frozen["dists"], frozen["nparams"], A.as_dp(frozen["dparams"]), C.byref(self.sp_c), None), "set_graph")
 
+    def propagate_once(self, frozen, pts, bw, npts, flags, prop_op, sp_c=None):
+        """iifb200_propagate_once: set_graph + upload of all slots + ONE propagateBelief + download of its destination in a
+        single C-ABI call (boundary B3); returns (points, bw, ipc) of prop_op's out_slot"""
+        self.frozen = frozen
+        if sp_c is not None:
+            self.sp_c = sp_c
+        out = prop_op[0].out_slot
+        s = frozen["slots"][out]
+        n = C.c_int32(0)
+        opts = np.zeros((max(prop_op[0].N, 1), s.dim))
+        obw, oipc = np.zeros(A.IIF_MAX_DIM), np.zeros(A.IIF_MAX_DIM)
+        self._check(self.lib.iifb200_propagate_once(
+            self.ctx, frozen["nslots"], frozen["slots"], frozen["nfactors"], frozen["factors"], frozen["ndists"],
+            frozen["dists"], frozen["nparams"], A.as_dp(frozen["dparams"]), C.byref(self.sp_c), A.as_dp(pts), A.as_dp(bw),
+            A.as_ip(npts), A.as_ip(flags), prop_op, C.cast(C.byref(n), A._ip), A.as_dp(opts), A.as_dp(obw), A.as_dp(oipc)),
+            "propagate_once")
+        return opts[:n.value], obw[:s.dim].copy(), oipc[:s.dim].copy()
+
     # ---- plumbing
     def _check(self, st, what):
         if st != A.IIF_OK:

@@ -427,9 +427,9 @@ solveGraph = solveTree
 # --------------------------------------------------------------------------- boundary B3 driver
 class B3Driver:
     """Drives a compiled plan ONE propagateBelief at a time, with the call sequence julia/IIFB200.jl's
-    `propagateBelief` makes per belief update (boundary B3): iifb200_set_graph on the mini graph {destination, its
-    factors' variables, message beliefs}, ONE iifb200_upload_slots of their beliefs, iifb200_propagate_batch(1) and
-    iifb200_download_belief of the posterior.  Beliefs live on the host between calls (as they do in the DFG's
+    `propagateBelief` makes per belief update (boundary B3): iifb200_propagate_once on the mini graph {destination, its
+    factors' variables, message beliefs} — or, with fused = False, its four constituents: iifb200_set_graph, ONE
+    iifb200_upload_slots of their beliefs, iifb200_propagate_batch(1) and iifb200_download_belief of the posterior.  Beliefs live on the host between calls (as they do in the DFG's
     VariableNodeData); separator copies are host copies.  Same Philox call ids as the plan => same posteriors as the
     one-schedule (B4) run; what differs is the cost of 7 000 round trips instead of one.
 
@@ -437,8 +437,8 @@ class B3Driver:
     (SolverAPI.jl:59-96), so independent propagateBelief calls — here: the ops of one wave — are in flight at once,
     each on its own library context (own stream, arena and scratch) from its own host thread."""
 
-    def __init__(self, plan: TR.SolvePlan, sp_c, device: int = 0, contexts: int = 1):
-        self.plan, self.sp_c = plan, sp_c
+    def __init__(self, plan: TR.SolvePlan, sp_c, device: int = 0, contexts: int = 1, fused: bool = True):
+        self.plan, self.sp_c, self.fused = plan, sp_c, fused
         fz = plan.frozen
         self.calls = []
         for spec in plan.props:
@@ -537,10 +537,13 @@ class B3Driver:
             pts[m.pts_off:m.pts_off + g.cap * g.dim] = arena.pts[g.pts_off:g.pts_off + g.cap * g.dim]
             bw[i * 4:i * 4 + 4] = arena.bw[s * 4:s * 4 + 4]
             npts[i], flags[i] = arena.npts[s], arena.flags[s]
-        eng.reset_graph(mini)                                          # iifb200_set_graph
-        eng.upload_slots(0, len(order), pts, bw, npts, flags)         # ONE transfer
-        eng.propagate_batch(op, 1)
-        p, w, ipc = eng.download_belief(0)
+        if self.fused:
+            p, w, ipc = eng.propagate_once(mini, pts, bw, npts, flags, op)   # all four steps behind one C-ABI call
+        else:
+            eng.reset_graph(mini)                                          # iifb200_set_graph
+            eng.upload_slots(0, len(order), pts, bw, npts, flags)         # ONE transfer
+            eng.propagate_batch(op, 1)
+            p, w, ipc = eng.download_belief(0)
         t = order[0]
         g = fz["slots"][t]
         arena.pts[g.pts_off:g.pts_off + p.size] = p.reshape(-1)

@@ -283,10 +283,10 @@ end
 """
     propagateBelief(dfg, destvar, factors; N, ...)   — GraphProductOperations.jl:16-64   (boundary B3)
 
-b200 backend: lowers the destination variable, its factors and their variables to the descriptor tables, uploads the
-particle blocks, runs iifb200_propagate_batch (F convolutions + KDE product in two launches) and rebuilds the
-ManifoldKernelDensity from the returned points and bandwidths.  The library keeps its arena, tables and scratch
-between calls (grow-only), so a call costs the uploads, two kernels and one download.
+b200 backend: lowers the destination variable, its factors and their variables to the descriptor tables and hands
+them, with the particle blocks, to iifb200_propagate_once (F convolutions + KDE product in two launches, one stream
+synchronisation), then rebuilds the ManifoldKernelDensity from the returned points and bandwidths.  The library keeps its
+arena, tables and scratch between calls (grow-only), so a call costs the transfers and two kernels.
 """
 function propagateBelief(dfg::AbstractDFG, destvar::DFGVariable, factors::AbstractVector;
                          solveKey::Symbol = :default, N::Integer = getSolverParams(dfg).N, kw...)
@@ -299,27 +299,41 @@ function propagateBelief(dfg::AbstractDFG, destvar::DFGVariable, factors::Abstra
   for e in extra
     push!(slots, SlotDesc(size(e.pts, 1), circmask(typeof(e.vartype)), max(size(e.pts, 2), 1), 0))
   end
-  local pts, bw, ipc
-  _with_context() do ctx                                             # one context per call in flight (pool above)
-    _set_graph(ctx, slots, fdescs, dists, dparams, _solverparams(getSolverParams(dfg)))
-    staged = _upload_all(ctx, slots,
-                         vcat([_packpoints(getVariableType(v), getVal(v; solveKey)) for v in vars], [e.pts for e in extra]),
-                         vcat([_bw(v, solveKey) for v in vars], [e.bw for e in extra]),
-                         vcat(Bool[isInitialized(v, solveKey) for v in vars], fill(true, length(extra))))
-    dlbl = getLabel(destvar)
-    op = Ref(PropOp(0, 0, length(fdescs), N,
-                    _padtuple(collect(0:(length(fdescs) - 1)), MAX_FACTORS, Int32),
-                    _padtuple([findfirst(==(dlbl), getVariableOrder(f)) for f in factors], MAX_FACTORS, Int32),
-                    _nextcall(), any(IIF.isMultihypo.(factors))))
-    # blocking ccall on a dedicated thread so the other cliques' Tasks keep running (SolverAPI.jl:59-96)
-    st = @threadcall((:iifb200_propagate_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{PropOp}), ctx, 1, op)
-    check(ctx, st, "propagate_batch")
-    d = getDimension(destvar)
-    pts = Matrix{Float64}(undef, d, max(N, slots[1].cap)); bw = zeros(d); ipc = zeros(d); npts = Ref{Int32}(0)
-    check(ctx, ccall((:iifb200_download_belief, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-          ctx, 0, npts, pts, bw, ipc), "download_belief")
-    pts = pts[:, 1:npts[]]
+  blocks = vcat([_packpoints(getVariableType(v), getVal(v; solveKey)) for v in vars], [e.pts for e in extra])
+  bws = vcat([_bw(v, solveKey) for v in vars], [e.bw for e in extra])
+  inits = vcat(Bool[isInitialized(v, solveKey) for v in vars], fill(true, length(extra)))
+  ns = length(slots)
+  hpts = zeros(sum(Int(s.cap) * Int(s.dim) for s in slots)); hbw = zeros(MAX_DIM, ns)
+  hn = zeros(Int32, ns); hfl = zeros(Int32, ns)
+  off = 0
+  for i in 1:ns                                                      # slot i occupies cap_i * dim_i doubles of `hpts`
+    p = blocks[i]
+    hpts[(off + 1):(off + length(p))] .= vec(p)
+    off += Int(slots[i].cap) * Int(slots[i].dim)
+    hbw[1:length(bws[i]), i] .= bws[i]; hn[i] = size(p, 2); hfl[i] = inits[i]
   end
+  dlbl = getLabel(destvar)
+  op = Ref(PropOp(0, 0, length(fdescs), N,
+                  _padtuple(collect(0:(length(fdescs) - 1)), MAX_FACTORS, Int32),
+                  _padtuple([findfirst(==(dlbl), getVariableOrder(f)) for f in factors], MAX_FACTORS, Int32),
+                  _nextcall(), any(IIF.isMultihypo.(factors))))
+  d = getDimension(destvar)
+  pts = Matrix{Float64}(undef, d, N); bw = zeros(MAX_DIM); ipc = zeros(MAX_DIM); npts = Ref{Int32}(0)
+  spc = Ref(_solverparams(getSolverParams(dfg)))
+  _with_context() do ctx                                             # one context per call in flight (pool above)
+    # ONE C-ABI call: descriptor tables + beliefs in, F convolutions + product, posterior out.  Blocking, so it runs on a
+    # dedicated thread and the other cliques' Tasks keep going (SolverAPI.jl:59-96)
+    GC.@preserve slots fdescs dists dparams hpts hbw hn hfl pts bw ipc begin
+      st = @threadcall((:iifb200_propagate_once, LIB), Int32,
+                       (Ptr{Cvoid}, Int32, Ptr{SlotDesc}, Int32, Ptr{FactorDesc}, Int32, Ptr{DistDesc}, Int32, Ptr{Float64},
+                        Ref{SolverParamsC}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ref{PropOp}, Ref{Int32},
+                        Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       ctx, ns, slots, length(fdescs), fdescs, length(dists), dists, length(dparams), dparams, spc,
+                       hpts, hbw, hn, hfl, op, npts, pts, bw, ipc)
+      check(ctx, st, "propagate_once")
+    end
+  end
+  pts = pts[:, 1:npts[]]; bw = bw[1:d]; ipc = ipc[1:d]
   M = getManifold(getVariableType(destvar))
   mkd = AMP.manikde!(M, _unpackpoints(getVariableType(destvar), pts); bw)   # bw given => no re-selection (FGOSUtils.jl:118-128)
   return mkd, ipc

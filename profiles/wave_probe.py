@@ -14,7 +14,8 @@ from iifb200 import workloads as W  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 fg = W.scalar_chain(n, N=100, seed=42)
-ts = SV.TreeSolver(fg, W.chain_nd_order(n))
+from iifb200 import planner as PL  # noqa: E402
+ts = SV.TreeSolver(fg, PL.elimination_order_is(fg))   # the bench's order
 ts.load_from_graph()
 ts.upload()
 for _ in range(3):

@@ -22,8 +22,8 @@ def test_every_ccall_symbol_is_declared_in_the_header():
     declared = set(re.findall(r"\b(iifb200_[a-z_0-9]+)\s*\(", re.sub(r"/\*.*?\*/", "", HDR, flags=re.S)))
     assert syms and syms <= declared, syms - declared
     # the B3 and the B4 sequences are both complete
-    for need in ("set_graph", "propagate_batch", "download_belief", "plan_tree", "plan_upload",
-                 "upload_slots", "schedule_run", "download_slots", "sync", "plan_free"):
+    for need in ("propagate_once", "set_graph", "plan_tree", "plan_upload", "upload_slots", "schedule_run",
+                 "download_slots", "sync", "plan_free", "elimination_order_is"):
         assert f"iifb200_{need}" in syms, need
 
 

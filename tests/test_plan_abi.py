@@ -149,17 +149,19 @@ def test_b3_per_call_path_equals_the_one_schedule_run(built):
     fg, order = W.scalar_chain(24, N=64, seed=3), W.chain_nd_order(24)
     ts = SV.TreeSolver(fg, order)
     ts.load_from_graph(); ts.upload(); ts.run(); ts.download()
-    b3 = SV.B3Driver(ts.plan, ts.sp_c)
-    ar = CP.HostArena(ts.plan.frozen)
-    for l, v in fg.variables.items():
-        ar.set(ts.plan.var_slot[l], v.val, v.bw, True)
-    b3.run(ar)
-    n0 = b3.eng.launch_count()
-    assert n0 >= len(ts.plan.props)
-    for l in fg.variables:
-        a, b = ts.arena.get(ts.plan.var_slot[l]), ar.get(ts.plan.var_slot[l])
-        assert np.allclose(a[0], b[0], rtol=0, atol=1e-9) and np.allclose(a[1], b[1], rtol=1e-7), l
-    b3.close(); ts.close()
+    for fused in (True, False):     # iifb200_propagate_once, and its four constituent calls
+        b3 = SV.B3Driver(ts.plan, ts.sp_c, fused=fused)
+        ar = CP.HostArena(ts.plan.frozen)
+        for l, v in fg.variables.items():
+            ar.set(ts.plan.var_slot[l], v.val, v.bw, True)
+        b3.run(ar)
+        n0 = b3.eng.launch_count()
+        assert n0 >= len(ts.plan.props)
+        for l in fg.variables:
+            a, b = ts.arena.get(ts.plan.var_slot[l]), ar.get(ts.plan.var_slot[l])
+            assert np.allclose(a[0], b[0], rtol=0, atol=1e-9) and np.allclose(a[1], b[1], rtol=1e-7), (fused, l)
+        b3.close()
+    ts.close()
 
 
 @pytest.mark.gpu
