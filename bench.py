@@ -319,6 +319,10 @@ def run_b200(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's own log lines (NCCL_DEBUG=VERSION / INFO print there) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # its one line is printf'ed to stdout regardless
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n_poses = POSES_PER_GPU * world if args.scaling == "weak" else POSES_PER_GPU
