@@ -28,3 +28,16 @@ fg = W.scalar_chain(24, N=64, seed=3)
 ts = SV.TreeSolver(fg, W.chain_nd_order(24))
 ts.load_from_graph(); ts.upload(); ts.run(); ts.run(); ts.download(); ts.close()
 print("tree solve ok")
+# boundary B3: one propagateBelief per C-ABI call (iifb200_propagate_once), serial and through a pool of contexts
+from iifb200 import compile as CP  # noqa: E402
+fg = W.scalar_chain(12, N=64, seed=3)
+ts = SV.TreeSolver(fg, W.chain_nd_order(12))
+for k in (1, 3):
+    b3 = SV.B3Driver(ts.plan, ts.sp_c, contexts=k)
+    ar = CP.HostArena(ts.plan.frozen)
+    for l, v in fg.variables.items():
+        ar.set(ts.plan.var_slot[l], v.val, v.bw, True)
+    b3.run(ar)
+    b3.close()
+ts.close()
+print("per-call path ok")
