@@ -18,6 +18,7 @@
 #include <iterator>
 #include <map>
 #include <set>
+#include <stdexcept>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -200,7 +201,17 @@ const char* iifb200_plan_error(void) { return g_plan_error.c_str(); }
 
 void iifb200_plan_free(iifb200_plan* p) { delete p; }
 
+static int32_t plan_tree_impl(const iif_graph_desc* g, const iif_tree_desc* t, const iif_plan_opts* o, iifb200_plan** out);
 int32_t iifb200_plan_tree(const iif_graph_desc* g, const iif_tree_desc* t, const iif_plan_opts* o, iifb200_plan** out) {
+  try {   // nothing crosses the C-ABI but status codes
+    return plan_tree_impl(g, t, o, out);
+  } catch (const std::exception& e) {
+    g_plan_error = std::string("plan_tree: ") + e.what();
+    if (out) *out = nullptr;
+    return IIF_ERR_STATE;
+  }
+}
+static int32_t plan_tree_impl(const iif_graph_desc* g, const iif_tree_desc* t, const iif_plan_opts* o, iifb200_plan** out) {
   auto fail = [&](int32_t code, const std::string& msg) { g_plan_error = msg; return code; };
   if (!g || !t || !o || !out) return fail(IIF_ERR_ARG, "plan_tree: null argument");
   *out = nullptr;
