@@ -363,6 +363,7 @@ int64_t iifb200_arena_bytes(int32_t nslots, const iif_slot_desc* slots) {
 int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots, int32_t nfactors,
                           const iif_factor_desc* factors, int32_t ndists, const iif_dist_desc* dists,
                           int32_t nparams, const double* dparams, const iif_solver_params* sp, void* ext_arena) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   if (nslots < 1 || !slots || nfactors < 0 || ndists < 0 || !sp) return fail(ctx, IIF_ERR_ARG, "set_graph: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -452,9 +453,14 @@ int32_t iifb200_set_graph(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots
   dg.nslots = nslots; dg.nfactors = nfactors; dg.ndists = ndists;
   if (!ctx->defer_sync) CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_set_graph: ") + e.what());
+  }
 }
 
 int32_t iifb200_set_solver_params(iifb200_ctx* ctx, const iif_solver_params* sp) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx || !sp) return IIF_ERR_ARG;
   // Kernels read the params through a device pointer, so captured CUDA graphs stay valid; the copy
   // is stream-ordered after earlier launches.  nullSurplusAdd is baked into schedules at build time.
@@ -462,6 +468,10 @@ int32_t iifb200_set_solver_params(iifb200_ctx* ctx, const iif_solver_params* sp)
   ctx->sp = *sp;
   CK(cudaMemcpyAsync(ctx->d_sp, &ctx->sp, sizeof(iif_solver_params), cudaMemcpyHostToDevice, ctx->stream));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_set_solver_params: ") + e.what());
+  }
 }
 
 // ---- belief I/O --------------------------------------------------------------------------
@@ -469,6 +479,7 @@ int32_t iifb200_set_solver_params(iifb200_ctx* ctx, const iif_solver_params* sp)
 
 int32_t iifb200_upload_belief(iifb200_ctx* ctx, int32_t slot, int32_t npts, const double* pts, const double* bw,
                               int32_t initialized) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "slot out of range");
   const iif_slot_desc& S = ctx->slots[slot];
@@ -482,9 +493,14 @@ int32_t iifb200_upload_belief(iifb200_ctx* ctx, int32_t slot, int32_t npts, cons
   CK(cudaMemcpyAsync(ctx->dg.flags + slot, &fl, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_upload_belief: ") + e.what());
+  }
 }
 
 int32_t iifb200_download_belief(iifb200_ctx* ctx, int32_t slot, int32_t* npts, double* pts, double* bw, double* ipc) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "slot out of range");
   const iif_slot_desc& S = ctx->slots[slot];
@@ -500,9 +516,14 @@ int32_t iifb200_download_belief(iifb200_ctx* ctx, int32_t slot, int32_t* npts, d
   if (bw) for (int c = 0; c < S.dim; ++c) bw[c] = b[c];
   if (ipc) for (int c = 0; c < S.dim; ++c) ipc[c] = q[c];
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_download_belief: ") + e.what());
+  }
 }
 
 int32_t iifb200_upload_all(iifb200_ctx* ctx, const double* pts, const double* bw, const int32_t* npts, const int32_t* flags) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   const int64_t ns = (int64_t)ctx->slots.size();
   if (pts) CK(cudaMemcpyAsync(ctx->dg.pts, pts, sizeof(double) * ctx->total_doubles, cudaMemcpyHostToDevice, ctx->stream));
@@ -510,9 +531,14 @@ int32_t iifb200_upload_all(iifb200_ctx* ctx, const double* pts, const double* bw
   if (npts) CK(cudaMemcpyAsync(ctx->dg.npts, npts, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, ctx->stream));
   if (flags) CK(cudaMemcpyAsync(ctx->dg.flags, flags, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, ctx->stream));
   return IIF_OK;  // stream-ordered: later launches on the ctx stream see the data
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_upload_all: ") + e.what());
+  }
 }
 
 int32_t iifb200_download_all(iifb200_ctx* ctx, double* pts, double* bw, double* ipc, int32_t* npts) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   const int64_t ns = (int64_t)ctx->slots.size();
   if (pts) CK(cudaMemcpyAsync(pts, ctx->dg.pts, sizeof(double) * ctx->total_doubles, cudaMemcpyDeviceToHost, ctx->stream));
@@ -521,10 +547,15 @@ int32_t iifb200_download_all(iifb200_ctx* ctx, double* pts, double* bw, double* 
   if (npts) CK(cudaMemcpyAsync(npts, ctx->dg.npts, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_download_all: ") + e.what());
+  }
 }
 
 int32_t iifb200_upload_slots(iifb200_ctx* ctx, int32_t first, int32_t count, const double* pts, const double* bw,
                              const int32_t* npts, const int32_t* flags) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   const int ns = (int)ctx->slots.size();
   if (first < 0 || count < 1 || first + count > ns) return fail(ctx, IIF_ERR_ARG, "upload_slots: slot range out of bounds");
@@ -535,10 +566,15 @@ int32_t iifb200_upload_slots(iifb200_ctx* ctx, int32_t first, int32_t count, con
   if (npts) CK(cudaMemcpyAsync(ctx->dg.npts + first, npts, sizeof(int32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
   if (flags) CK(cudaMemcpyAsync(ctx->dg.flags + first, flags, sizeof(int32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_upload_slots: ") + e.what());
+  }
 }
 
 int32_t iifb200_download_slots(iifb200_ctx* ctx, int32_t first, int32_t count, double* pts, double* bw, double* ipc,
                                int32_t* npts) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   const int ns = (int)ctx->slots.size();
   if (first < 0 || count < 1 || first + count > ns) return fail(ctx, IIF_ERR_ARG, "download_slots: slot range out of bounds");
@@ -549,9 +585,14 @@ int32_t iifb200_download_slots(iifb200_ctx* ctx, int32_t first, int32_t count, d
   if (ipc) CK(cudaMemcpyAsync(ipc, ctx->dg.ipc + (int64_t)first * IIF_MAX_DIM, sizeof(double) * count * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   if (npts) CK(cudaMemcpyAsync(npts, ctx->dg.npts + first, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
   return IIF_OK;  // asynchronous: iifb200_sync before reading
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_download_slots: ") + e.what());
+  }
 }
 
 int32_t iifb200_host_alloc(iifb200_ctx* ctx, int64_t bytes, void** ptr_out) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx || !ptr_out || bytes < 1) return IIF_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   void* p = nullptr;
@@ -559,23 +600,37 @@ int32_t iifb200_host_alloc(iifb200_ctx* ctx, int64_t bytes, void** ptr_out) {
   ctx->pinned.push_back(p);
   *ptr_out = p;
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_host_alloc: ") + e.what());
+  }
 }
 
 int32_t iifb200_host_free(iifb200_ctx* ctx, void* ptr) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx || !ptr) return IIF_ERR_ARG;
   auto it = std::find(ctx->pinned.begin(), ctx->pinned.end(), ptr);
   if (it == ctx->pinned.end()) return fail(ctx, IIF_ERR_ARG, "host_free: pointer not from iifb200_host_alloc");
   ctx->pinned.erase(it);
   CK(cudaFreeHost(ptr));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_host_free: ") + e.what());
+  }
 }
 
 int32_t iifb200_slot_device_ptr(iifb200_ctx* ctx, int32_t slot, void** pts_ptr, void** bw_ptr) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, IIF_ERR_ARG, "slot out of range");
   if (pts_ptr) *pts_ptr = ctx->dg.pts + ctx->slots[slot].pts_off;
   if (bw_ptr) *bw_ptr = ctx->dg.bw + (int64_t)slot * IIF_MAX_DIM;
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_slot_device_ptr: ") + e.what());
+  }
 }
 
 // ---- helpers -------------------------------------------------------------------------------
@@ -640,6 +695,7 @@ static int32_t validate_conv(iifb200_ctx* ctx, const iif_conv_op& op) {
 int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, const double* meas,
                            const int32_t* mhidx, const double* uinf, double* out_pts, double* out_bw,
                            double* out_ipc, int32_t* out_mhidx, int32_t* out_nan) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (K < 1 || !ops || !out_pts || !out_bw || !out_ipc) return fail(ctx, IIF_ERR_ARG, "conv_batch: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -723,6 +779,10 @@ int32_t iifb200_conv_batch(iifb200_ctx* ctx, int32_t K, const iif_conv_op* ops, 
       return fail(ctx, misc[K + k], b);
     }
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_conv_batch: ") + e.what());
+  }
 }
 
 // ---- hot path: product batch -------------------------------------------------------------------
@@ -730,6 +790,7 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
                               const double* dens_bw, const int32_t* dens_mask, const double* old_pts,
                               const double* randU, const double* randN, double* out_pts, double* out_bw,
                               int32_t* out_labels) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   if (V < 1 || !ops || !dens_pts || !dens_bw || !out_pts || !out_bw) return fail(ctx, IIF_ERR_ARG, "product_batch: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -815,11 +876,16 @@ int32_t iifb200_product_batch(iifb200_ctx* ctx, int32_t V, const iif_product_op*
   cleanup();
 #undef CKC
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_product_batch: ") + e.what());
+  }
 }
 
 // ---- KDE bandwidth of K point sets ---------------------------------------------------------------
 int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, const int32_t* dim,
                               const int32_t* circ_mask, const double* pts, double* out_bw) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   if (K < 1 || !N || !dim || !circ_mask || !pts || !out_bw) return fail(ctx, IIF_ERR_ARG, "kde_bandwidth: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -859,10 +925,15 @@ int32_t iifb200_kde_bandwidth(iifb200_ctx* ctx, int32_t K, const int32_t* N, con
   CK(cudaMemcpyAsync(out_bw, d_bw, sizeof(double) * K * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_kde_bandwidth: ") + e.what());
+  }
 }
 
 // ---- point estimates of V device-resident beliefs (calcPPE, FGOSUtils.jl:237-278) ------------------------
 int32_t iifb200_ppe_batch(iifb200_ctx* ctx, int32_t V, const int32_t* slots, double* out_mean, double* out_max) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (V < 1 || !slots || !out_mean || !out_max) return fail(ctx, IIF_ERR_ARG, "ppe_batch: bad arguments");
   for (int v = 0; v < V; ++v)
@@ -896,11 +967,16 @@ int32_t iifb200_ppe_batch(iifb200_ctx* ctx, int32_t V, const int32_t* slots, dou
   CK(cudaMemcpyAsync(out_max, d_out + (int64_t)V * IIF_MAX_DIM, sizeof(double) * V * IIF_MAX_DIM, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_ppe_batch: ") + e.what());
+  }
 }
 
 // ---- approxDeconv of K factors on device-resident beliefs (DeconvUtils.jl:32-162) ----------------------------
 int32_t iifb200_deconv_batch(iifb200_ctx* ctx, int32_t K, const int32_t* factors, const int32_t* N,
                              const int32_t* call_ids, double* out_pred, double* out_meas) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (K < 1 || !factors || !N || !call_ids || !out_pred || !out_meas) return fail(ctx, IIF_ERR_ARG, "deconv_batch: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -945,11 +1021,16 @@ int32_t iifb200_deconv_batch(iifb200_ctx* ctx, int32_t K, const int32_t* factors
   for (int k = 0; k < K; ++k)
     if (st[k] != IIF_OK) return fail(ctx, st[k], std::string("deconv_batch: device reported '") + status_name(st[k]) + "'");
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_deconv_batch: ") + e.what());
+  }
 }
 
 // ---- mmd kernel-embedding distance of K pairs of point sets (SolverUtilities.jl:25-47 / AMP.mmd!) ---------------
 int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_t* nb, const int32_t* dim,
                     const int32_t* circ_mask, const double* a, const double* b, double bw, double* out) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   if (K < 1 || !na || !nb || !dim || !circ_mask || !a || !b || !out) return fail(ctx, IIF_ERR_ARG, "mmd: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -991,6 +1072,10 @@ int32_t iifb200_mmd(iifb200_ctx* ctx, int32_t K, const int32_t* na, const int32_
   CK(cudaMemcpyAsync(out, d_o, sizeof(double) * K, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_mmd: ") + e.what());
+  }
 }
 
 // ---- schedules: propagateBelief waves captured as a CUDA graph -----------------------------------
@@ -1197,12 +1282,18 @@ static int32_t build_schedule(iifb200_ctx* ctx, int32_t nwaves, const int32_t* w
 int32_t iifb200_schedule_build(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
                                const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props,
                                int32_t* schedule_id_out) {
+  try {   // nothing but status codes crosses the C-ABI
   return iifb200_schedule_build_ex(ctx, nwaves, wave_off, nops, ops, nprops, props, 0, nullptr, schedule_id_out);
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_schedule_build: ") + e.what());
+  }
 }
 
 int32_t iifb200_schedule_build_ex(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
                                   const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, int32_t ndeconvs,
                                   const iif_deconv_op* deconvs, int32_t* schedule_id_out) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (nwaves < 1 || !wave_off || nops < 0 || !ops || nprops < 0 || ndeconvs < 0 || (ndeconvs > 0 && !deconvs) || !schedule_id_out)
     return fail(ctx, IIF_ERR_ARG, "schedule_build: bad arguments");
@@ -1213,6 +1304,10 @@ int32_t iifb200_schedule_build_ex(iifb200_ctx* ctx, int32_t nwaves, const int32_
   ctx->schedules.push_back(s);
   *schedule_id_out = (int32_t)ctx->schedules.size() - 1;
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_schedule_build_ex: ") + e.what());
+  }
 }
 
 // launches of one segment of a wave on stream `st`; CTA size and cluster choice follow the whole wave's width
@@ -1295,6 +1390,7 @@ static int32_t enqueue_waves(iifb200_ctx* ctx, Schedule* s, int w0, int w1, int*
 }
 
 int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t first_wave, int32_t last_wave) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (schedule_id < 0 || schedule_id >= (int)ctx->schedules.size() || !ctx->schedules[schedule_id]) return fail(ctx, IIF_ERR_ARG, "schedule_run: bad schedule id");
   Schedule* s = ctx->schedules[schedule_id];
@@ -1343,10 +1439,15 @@ int32_t iifb200_schedule_run(iifb200_ctx* ctx, int32_t schedule_id, int32_t firs
   ctx->timed = true;
   ctx->launches += it->second.second;
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_schedule_run: ") + e.what());
+  }
 }
 
 int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t first_wave, int32_t last_wave,
                                  float* ms, int32_t* launches, int64_t* blocks) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (schedule_id < 0 || schedule_id >= (int)ctx->schedules.size() || !ctx->schedules[schedule_id] || !ms || !launches || !blocks)
     return fail(ctx, IIF_ERR_ARG, "schedule_profile: bad arguments");
@@ -1394,12 +1495,17 @@ int32_t iifb200_schedule_profile(iifb200_ctx* ctx, int32_t schedule_id, int32_t 
   ctx->launches += (int64_t)kind.size();
   if (e != cudaSuccess) return fail(ctx, IIF_ERR_CUDA, std::string("schedule_profile: ") + cudaGetErrorString(e));
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_schedule_profile: ") + e.what());
+  }
 }
 
 int32_t iifb200_schedule_build_dist(iifb200_ctx* ctx, int32_t nwaves, const int32_t* wave_off, int32_t nops,
                                     const iif_sched_op* ops, int32_t nprops, const iif_prop_op* props, int32_t ndeconvs,
                                     const iif_deconv_op* deconvs, int32_t nxfers, const iif_xfer_op* xfers,
                                     int32_t* schedule_id_out) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (nwaves < 1 || !wave_off || nops < 0 || !ops || nprops < 0 || ndeconvs < 0 || (ndeconvs > 0 && !deconvs) || nxfers < 0 ||
       (nxfers > 0 && !xfers) || !schedule_id_out)
@@ -1411,9 +1517,14 @@ int32_t iifb200_schedule_build_dist(iifb200_ctx* ctx, int32_t nwaves, const int3
   ctx->schedules.push_back(s);
   *schedule_id_out = (int32_t)ctx->schedules.size() - 1;
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_schedule_build_dist: ") + e.what());
+  }
 }
 
 int32_t iifb200_ipc_export(iifb200_ctx* ctx, int32_t nflags, void* arena_handle64, void* flags_handle64) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (nflags < 1 || !arena_handle64 || !flags_handle64) return fail(ctx, IIF_ERR_ARG, "ipc_export: bad arguments");
   if (!ctx->arena_owned) return fail(ctx, IIF_ERR_STATE, "ipc_export: needs a library-owned arena (set_graph with ext_arena == NULL)");
@@ -1433,9 +1544,14 @@ int32_t iifb200_ipc_export(iifb200_ctx* ctx, int32_t nflags, void* arena_handle6
   memcpy(arena_handle64, &ha, 64);
   memcpy(flags_handle64, &hf, 64);
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_ipc_export: ") + e.what());
+  }
 }
 
 int32_t iifb200_ipc_attach(iifb200_ctx* ctx, int32_t world, int32_t rank, const void* arena_handles, const void* flags_handles) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (world < 1 || rank < 0 || rank >= world || !arena_handles || !flags_handles) return fail(ctx, IIF_ERR_ARG, "ipc_attach: bad arguments");
   if (!ctx->d_flags) return fail(ctx, IIF_ERR_STATE, "ipc_attach: call iifb200_ipc_export first");
@@ -1455,19 +1571,29 @@ int32_t iifb200_ipc_attach(iifb200_ctx* ctx, int32_t world, int32_t rank, const 
     ctx->peer_flags[r] = (int32_t*)pf;
   }
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_ipc_attach: ") + e.what());
+  }
 }
 
 int32_t iifb200_schedule_free(iifb200_ctx* ctx, int32_t schedule_id) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   if (schedule_id < 0 || schedule_id >= (int)ctx->schedules.size()) return fail(ctx, IIF_ERR_ARG, "schedule_free: bad id");
   CK(cudaStreamSynchronize(ctx->stream));
   free_schedule(ctx->schedules[schedule_id]);
   ctx->schedules[schedule_id] = nullptr;
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_schedule_free: ") + e.what());
+  }
 }
 
 // V independent propagateBelief calls: a one-wave schedule, not cached
 int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* ops) {
+  try {   // nothing but status codes crosses the C-ABI
   NEED_GRAPH();
   if (V < 1 || !ops) return fail(ctx, IIF_ERR_ARG, "propagate_batch: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -1493,6 +1619,10 @@ int32_t iifb200_propagate_batch(iifb200_ctx* ctx, int32_t V, const iif_prop_op* 
   }
   free_schedule(s);
   return st;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_propagate_batch: ") + e.what());
+  }
 }
 
 int32_t iifb200_propagate_once(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* slots, int32_t nfactors,
@@ -1500,6 +1630,7 @@ int32_t iifb200_propagate_once(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* 
                                const double* dparams, const iif_solver_params* sp, const double* pts, const double* bw,
                                const int32_t* npts, const int32_t* flags, const iif_prop_op* op, int32_t* out_npts,
                                double* out_pts, double* out_bw, double* out_ipc) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   if (!op || !pts || !bw || !npts || !flags || !out_pts) return fail(ctx, IIF_ERR_ARG, "propagate_once: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -1544,10 +1675,15 @@ int32_t iifb200_propagate_once(iifb200_ctx* ctx, int32_t nslots, iif_slot_desc* 
   }
   free_schedule(s);
   return st;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_propagate_once: ") + e.what());
+  }
 }
 
 int32_t iifb200_plan_upload(iifb200_ctx* ctx, const iifb200_plan* plan, const iif_solver_params* sp, void* ext_arena,
                             int32_t* schedule_id_out) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   if (!plan || !sp || !schedule_id_out) return fail(ctx, IIF_ERR_ARG, "plan_upload: bad arguments");
   std::vector<iif_slot_desc> slots = iif_plan_slots(plan);   // set_graph fills pts_off in place
@@ -1564,9 +1700,14 @@ int32_t iifb200_plan_upload(iifb200_ctx* ctx, const iifb200_plan* plan, const ii
   return iifb200_schedule_build_ex(ctx, (int32_t)wo.size() - 1, wo.data(), (int32_t)ops.size(), ops.data(),
                                    (int32_t)props.size(), props.data(), (int32_t)dcv.size(), dcv.empty() ? nullptr : dcv.data(),
                                    schedule_id_out);
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_plan_upload: ") + e.what());
+  }
 }
 
 int32_t iifb200_sync(iifb200_ctx* ctx) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1583,15 +1724,24 @@ int32_t iifb200_sync(iifb200_ctx* ctx) {
       }
   }
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_sync: ") + e.what());
+  }
 }
 
 int64_t iifb200_launch_count(const iifb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int32_t iifb200_set_stream(iifb200_ctx* ctx, void* stream) {
+  try {   // nothing but status codes crosses the C-ABI
   if (!ctx) return IIF_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
   return IIF_OK;
+  } catch (const std::exception& e) {
+    if (!ctx) return IIF_ERR_STATE;
+    return fail(ctx, IIF_ERR_STATE, std::string("iifb200_set_stream: ") + e.what());
+  }
 }
 void* iifb200_stream(iifb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 #ifdef IIF_PHASES
